@@ -1,0 +1,97 @@
+"""Generate golden fixtures from the UNMODIFIED Python reference (build container only).
+
+    python oracle/gen_golden.py            # writes tests/golden/*.npz
+
+Each fixture is a seeded rollout of the reference env (ref_harness.rollout): the full
+per-vehicle state after reset and after every env.step, plus obs / reward / terminated /
+truncated and the action sequence.  Stepping continues past termination so all
+trajectories have fixed length.  tests/test_oracle_golden.py pins the C oracle to these;
+the `-m gpu` tests pin the CUDA path to them (teacher-forced and free-running on the
+well-conditioned prefix, see DESIGN.md "parity protocol").
+"""
+from __future__ import annotations
+
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import ref_harness as rh  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+# name -> (env_id, config override, seeds, n_steps, action kind)
+CASES = {
+    # BASELINE.json configs[0]: highway-fast-v0 defaults (V = 21)
+    "highway_fast_v20": ("highway-fast-v0", None, list(range(6)), 30, "discrete5"),
+    # configs[1]: highway-fast-v0, vehicles_count = 50 (V = 51)
+    "highway_fast_v50": ("highway-fast-v0", {"vehicles_count": 50}, list(range(100, 106)), 30, "discrete5"),
+    # highway-v0 defaults: all-pairs collisions, 15 substeps, 4 lanes
+    "highway_v50": ("highway-v0", None, list(range(200, 203)), 20, "discrete5"),
+    # configs[4] shape: highway-v0, vehicles_count = 100, ContinuousAction (V = 101)
+    "highway_v100_continuous": (
+        "highway-v0",
+        {"vehicles_count": 100, "action": {"type": "ContinuousAction"}},
+        list(range(300, 303)),
+        12,
+        "box2",
+    ),
+}
+
+
+def main() -> None:
+    os.makedirs(OUT, exist_ok=True)
+    for name, (env_id, over, seeds, T, akind) in CASES.items():
+        t0 = time.time()
+        rng = np.random.default_rng(abs(hash(name)) % (2**31) if False else sum(map(ord, name)))
+        per_seed = []
+        for seed in seeds:
+            if akind == "discrete5":
+                actions = rng.integers(0, 5, size=T).astype(np.int64)
+            else:
+                actions = rng.uniform(-1, 1, size=(T, 2)).astype(np.float32)
+            per_seed.append(rh.rollout(env_id, over, seed, list(actions)))
+        out = {k: np.stack([p[k] for p in per_seed]) for k in per_seed[0].keys()}
+        out["seeds"] = np.array(seeds, dtype=np.int64)
+        env = rh.make_reference_env(env_id, over)
+        import json
+
+        cfg = dict(env.config)
+        cfg["_others_check_collisions"] = 0 if env_id == "highway-fast-v0" else 1
+        cfg["_env_id"] = env_id
+        out["config_json"] = np.array(json.dumps(cfg))
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, **out)
+        print(f"{name}: {len(seeds)} seeds x {T} steps -> {path} "
+              f"({os.path.getsize(path)/1e3:.0f} kB, {time.time()-t0:.1f}s)")
+
+    # reset-only fixtures: pins the numpy-PCG64 spawn restatement on many seeds
+    for name, (env_id, over) in {
+        "reset_highway_fast_v50": ("highway-fast-v0", {"vehicles_count": 50}),
+        "reset_highway_v100": ("highway-v0", {"vehicles_count": 100, "action": {"type": "ContinuousAction"}}),
+    }.items():
+        env = rh.make_reference_env(env_id, over)
+        seeds = list(range(1000, 1032))
+        states, obs = [], []
+        for seed in seeds:
+            o, _ = env.reset(seed=seed)
+            states.append(rh.dump_state(env))
+            obs.append(o)
+            # a second reset WITHOUT seed continues the stream (gymnasium autoreset)
+            o2, _ = env.reset()
+            states.append(rh.dump_state(env))
+            obs.append(o2)
+        out = {k: np.stack([s[k] for s in states]) for k in states[0].keys()}
+        out["obs"] = np.stack(obs)
+        out["seeds"] = np.array(seeds, dtype=np.int64)
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, **out)
+        print(f"{name}: -> {path} ({os.path.getsize(path)/1e3:.0f} kB)")
+
+
+if __name__ == "__main__":
+    if not rh.reference_available():
+        raise SystemExit("reference not mounted; golden fixtures can only be generated in the build container")
+    main()

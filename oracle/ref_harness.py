@@ -1,0 +1,146 @@
+"""Live-reference harness — TEST INFRASTRUCTURE ONLY (never imported by the product).
+
+Imports the UNMODIFIED reference package from ``/root/reference`` (read-only) under the
+stub ``gymnasium``/``pygame``/``matplotlib`` in ``oracle/shim`` and exposes helpers to
+(a) build a reference env, (b) dump its state in this repo's structure-of-arrays schema,
+(c) step it.  It only works in the build container: ``/root/reference`` does not exist on
+the GPU box, so nothing under ``tests -m gpu``, ``bench.py`` or ``smoke()`` may use it.
+Golden fixtures are produced from it by ``oracle/gen_golden.py`` and committed under
+``tests/golden/``.
+
+Reference entry points driven here (file:line in /root/reference):
+  * ``AbstractEnv.reset``  highway_env/envs/common/abstract.py:219-249
+  * ``AbstractEnv.step``   highway_env/envs/common/abstract.py:259-285
+  * ``Road.act/step``      highway_env/road/road.py:464-481
+"""
+from __future__ import annotations
+
+import importlib
+import os
+import sys
+
+import numpy as np
+
+REFERENCE_ROOT = os.environ.get("HWY_REFERENCE_ROOT", "/root/reference")
+_SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shim")
+
+
+def reference_available() -> bool:
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "highway_env"))
+
+
+def _ensure_imports() -> None:
+    if "highway_env" in sys.modules:
+        return
+    try:  # a real gymnasium wins if it is ever installed
+        importlib.import_module("gymnasium")
+    except ModuleNotFoundError:
+        sys.path.insert(0, _SHIM)
+    for mod in ("pygame", "matplotlib"):
+        try:
+            importlib.import_module(mod)
+        except ModuleNotFoundError:
+            if _SHIM not in sys.path:
+                sys.path.insert(0, _SHIM)
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.append(REFERENCE_ROOT)
+    importlib.import_module("highway_env")
+
+
+ENV_CLASSES = {
+    "highway-v0": ("highway_env.envs.highway_env", "HighwayEnv"),
+    "highway-fast-v0": ("highway_env.envs.highway_env", "HighwayEnvFast"),
+    "intersection-v0": ("highway_env.envs.intersection_env", "IntersectionEnv"),
+    "roundabout-v0": ("highway_env.envs.roundabout_env", "RoundaboutEnv"),
+}
+
+
+def make_reference_env(env_id: str, config: dict | None = None):
+    """Construct the reference env (``gym.make`` equivalent without wrappers)."""
+    _ensure_imports()
+    mod, cls = ENV_CLASSES[env_id]
+    return getattr(importlib.import_module(mod), cls)(config=config)
+
+
+def lane_list(env):
+    """Lanes in graph-enumeration order (road.py:65-71) with their indices."""
+    out = []
+    for _from, tos in env.road.network.graph.items():
+        for _to, lanes in tos.items():
+            for _id, lane in enumerate(lanes):
+                out.append(((_from, _to, _id), lane))
+    return out
+
+
+def dump_state(env) -> dict:
+    """Snapshot the reference road in the SoA schema used by ``highwayenv_b200``.
+
+    Fields (per vehicle, list order = ``road.vehicles`` order):
+      x, y, heading, speed (f64); target_speed, timer, delta (f64, NaN when the vehicle
+      class has none); lane, target_lane (index into the graph enumeration, -1 = none);
+      crashed (bool); impact (f64[2], NaN when ``None``); speed_index (ego MDPVehicle).
+    """
+    idx_of = {li: k for k, (li, _) in enumerate(lane_list(env))}
+    vs = env.road.vehicles
+    n = len(vs)
+    d = {
+        "x": np.array([v.position[0] for v in vs], dtype=np.float64),
+        "y": np.array([v.position[1] for v in vs], dtype=np.float64),
+        "heading": np.array([float(v.heading) for v in vs], dtype=np.float64),
+        "speed": np.array([float(v.speed) for v in vs], dtype=np.float64),
+        "target_speed": np.array(
+            [float(getattr(v, "target_speed", np.nan)) for v in vs], dtype=np.float64
+        ),
+        "timer": np.array([float(getattr(v, "timer", np.nan)) for v in vs], dtype=np.float64),
+        "delta": np.array(
+            [float(v.DELTA) if hasattr(v, "DELTA") else np.nan for v in vs], dtype=np.float64
+        ),
+        "lane": np.array([idx_of[tuple(v.lane_index)] for v in vs], dtype=np.int32),
+        "target_lane": np.array(
+            [
+                idx_of[tuple(v.target_lane_index)] if hasattr(v, "target_lane_index") else -1
+                for v in vs
+            ],
+            dtype=np.int32,
+        ),
+        "crashed": np.array([bool(v.crashed) for v in vs], dtype=np.bool_),
+        "impact": np.array(
+            [
+                (np.nan, np.nan) if v.impact is None else (float(v.impact[0]), float(v.impact[1]))
+                for v in vs
+            ],
+            dtype=np.float64,
+        ).reshape(n, 2),
+        "check_collisions": np.array([bool(v.check_collisions) for v in vs], dtype=np.bool_),
+        "speed_index": np.array([int(getattr(v, "speed_index", -1)) for v in vs], dtype=np.int32),
+        "time": np.float64(env.time),
+        "steps": np.int64(env.steps),
+    }
+    return d
+
+
+def rollout(env_id: str, config: dict | None, seed: int, actions, record_substeps: bool = False):
+    """Reset with ``seed`` and apply ``actions``; returns dict of stacked arrays.
+
+    Stepping continues after termination (the reference allows it), so trajectories have
+    a fixed length ``len(actions)``; ``terminated``/``truncated`` are recorded per step.
+    """
+    env = make_reference_env(env_id, config)
+    obs0, _ = env.reset(seed=seed)
+    states = [dump_state(env)]
+    obs, rew, term, trunc = [np.asarray(obs0)], [], [], []
+    for a in actions:
+        o, r, te, tr, _info = env.step(a)
+        states.append(dump_state(env))
+        obs.append(np.asarray(o))
+        rew.append(float(r))
+        term.append(bool(te))
+        trunc.append(bool(tr))
+    keys = [k for k in states[0].keys()]
+    out = {k: np.stack([s[k] for s in states]) for k in keys}
+    out["obs"] = np.stack(obs)
+    out["reward"] = np.array(rew, dtype=np.float64)
+    out["terminated"] = np.array(term, dtype=np.bool_)
+    out["truncated"] = np.array(trunc, dtype=np.bool_)
+    out["actions"] = np.asarray(actions)
+    return out
