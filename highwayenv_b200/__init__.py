@@ -1,0 +1,58 @@
+"""highwayenv_b200 — B200-native batched backend for HighwayEnv's simulation hot path.
+
+Drop-in for the path ``AbstractEnv._simulate -> Road.act / Road.step -> observe / reward``
+of Farama-Foundation/HighwayEnv 1.12.1, for thousands of independent envs at once:
+
+    import highwayenv_b200 as hb
+    env = hb.make("highway-fast-v0", num_envs=4096, config={"vehicles_count": 50})
+    obs, info = env.reset(seed=0)
+    obs, reward, terminated, truncated, info = env.step(actions)   # device tensors
+
+The env ids, ``config`` keys and observation/action plugin names are the reference's
+(highway_env/__init__.py:36-184).  Kernels are hand-written CUDA for sm_100a behind the C
+ABI of include/hwyb200.h; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import importlib
+from typing import Any, Optional
+
+__version__ = "0.1.0"
+
+# id -> "module:Class" (same ids as the reference registers, highway_env/__init__.py:46-54)
+REGISTRY = {
+    "highway-v0": "highwayenv_b200.envs.highway_env:BatchedHighwayEnv",
+    "highway-fast-v0": "highwayenv_b200.envs.highway_env:BatchedHighwayEnvFast",
+}
+
+
+def make(env_id: str, num_envs: int = 1, config: Optional[dict] = None, device: Any = None,
+         render_mode: Optional[str] = None, **kwargs):
+    """``gym.make`` equivalent for the batched backend (``"highwayenv_b200:highway-v0"`` and
+    ``"highway_env:highway-v0"`` module-prefixed ids are accepted too)."""
+    if ":" in env_id:
+        env_id = env_id.split(":", 1)[1]
+    if env_id not in REGISTRY:
+        raise KeyError(f"{env_id!r} is not on the accelerated path; available: {sorted(REGISTRY)}")
+    mod, cls = REGISTRY[env_id].split(":")
+    env_cls = getattr(importlib.import_module(mod), cls)
+    return env_cls(config=config, render_mode=render_mode, num_envs=num_envs, device=device, **kwargs)
+
+
+def _register_with_gymnasium() -> None:
+    """When gymnasium is installed, expose the ids as vector envs:
+    ``gymnasium.make_vec("hwyb200/highway-fast-v0", num_envs=4096)``."""
+    try:
+        from gymnasium.envs.registration import register, registry  # type: ignore
+    except Exception:
+        return
+    for env_id, entry in REGISTRY.items():
+        gid = f"hwyb200/{env_id}"
+        if gid not in registry:
+            try:
+                register(id=gid, vector_entry_point=entry)
+            except Exception:
+                pass
+
+
+_register_with_gymnasium()

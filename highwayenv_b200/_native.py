@@ -1,0 +1,103 @@
+"""ctypes binding of the C ABI declared in include/hwyb200.h.
+
+The shared library ``csrc/libhwyb200.so`` is built in-tree by ``highwayenv_b200.build``
+(nvcc, sm_100a).  There is NO CPU fallback: if the library is missing, or no CUDA device is
+visible when a kernel entry point is called, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libhwyb200.so")
+
+HWY_ABI_VERSION = 1
+HWY_MAX_LANES = 8
+HWY_MAX_TARGET_SPEEDS = 8
+HWY_MAX_VEHICLES = 128
+HWY_MAX_OBS_VEHICLES = 16
+
+KIND_IDM, KIND_MDP, KIND_VEHICLE = 0, 1, 2
+META_LANE_SHIFT, META_TARGET_SHIFT = 0, 8
+META_CRASHED, META_HAS_IMPACT, META_CHECK_COLLISIONS = 1 << 16, 1 << 17, 1 << 18
+META_KIND_SHIFT, META_PRESENT = 19, 1 << 21
+AUTORESET_DISABLED, AUTORESET_SAME_STEP = 0, 1
+
+
+class HwyStraightLane(C.Structure):
+    _fields_ = [(n, C.c_double) for n in (
+        "start_x", "start_y", "dir_x", "dir_y", "lat_x", "lat_y", "heading", "length", "width",
+        "speed_limit")]
+
+
+class HwyHighwayParams(C.Structure):
+    _fields_ = (
+        [(n, C.c_int32) for n in (
+            "lanes_count", "n_vehicles", "simulation_frequency", "policy_frequency", "action_type",
+            "others_check_collisions", "normalize_reward", "offroad_terminal", "obs_vehicles_count",
+            "obs_see_behind", "obs_absolute", "obs_normalize", "obs_clip", "n_target_speeds",
+            "initial_lane_id", "act_clip")]
+        + [("duration", C.c_double), ("target_speeds", C.c_double * HWY_MAX_TARGET_SPEEDS)]
+        + [(n, C.c_double) for n in (
+            "collision_reward", "right_lane_reward", "high_speed_reward", "reward_speed_lo",
+            "reward_speed_hi", "acc_lo", "acc_hi", "steer_lo", "steer_hi", "ego_spacing",
+            "vehicles_density", "ego_speed", "spawn_exp", "acc_max", "comfort_acc_max",
+            "comfort_acc_min", "distance_wanted", "time_wanted", "politeness",
+            "lane_change_min_acc_gain", "lane_change_max_braking_imposed", "lane_change_delay",
+            "delta_lo", "delta_hi", "perception_distance")]
+        + [("lanes", HwyStraightLane * HWY_MAX_LANES)]
+    )
+
+
+class HwyHighwayState(C.Structure):
+    _fields_ = [
+        ("n_envs", C.c_int32), ("vp", C.c_int32),
+        ("pos", C.c_void_p), ("hs", C.c_void_p), ("tt", C.c_void_p), ("imp", C.c_void_p),
+        ("delta", C.c_void_p), ("meta", C.c_void_p), ("speed_index", C.c_void_p),
+        ("time", C.c_void_p), ("rng", C.c_void_p),
+    ]
+
+
+EXPORTS = (
+    "hwy_abi_version", "hwy_last_error", "hwy_highway_slot_stride", "hwy_highway_reset",
+    "hwy_highway_observe", "hwy_highway_step", "hwy_launch_count",
+)
+
+_lib = None
+
+
+def load():
+    """Load libhwyb200.so (raises RuntimeError when it has not been built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m highwayenv_b200.build` "
+            "(nvcc, sm_100a). highwayenv_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    lib.hwy_abi_version.restype = C.c_int
+    lib.hwy_last_error.restype = C.c_char_p
+    lib.hwy_launch_count.restype = C.c_uint64
+    lib.hwy_highway_slot_stride.restype = C.c_int
+    lib.hwy_highway_slot_stride.argtypes = [C.c_int]
+    P, S = C.POINTER(HwyHighwayParams), C.POINTER(HwyHighwayState)
+    lib.hwy_highway_reset.restype = C.c_int
+    lib.hwy_highway_reset.argtypes = [P, S, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.hwy_highway_observe.restype = C.c_int
+    lib.hwy_highway_observe.argtypes = [P, S, C.c_void_p, C.c_void_p]
+    lib.hwy_highway_step.restype = C.c_int
+    lib.hwy_highway_step.argtypes = [P, S, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                     C.c_void_p, C.c_void_p]
+    if lib.hwy_abi_version() != HWY_ABI_VERSION:
+        raise RuntimeError("libhwyb200.so ABI version mismatch; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise RuntimeError("hwyb200: " + load().hwy_last_error().decode())

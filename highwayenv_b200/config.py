@@ -1,0 +1,103 @@
+"""Environment configuration dictionaries (same keys and defaults as the reference).
+
+Restates, per registered id, the class-chain ``default_config()`` of the reference:
+``AbstractEnv.default_config`` (highway_env/envs/common/abstract.py:102-125) <-
+``HighwayEnv`` (envs/highway_env.py:25-53) <- ``HighwayEnvFast`` (:162-175), and the
+validation rule of ``utils.update_config`` (highway_env/utils.py:440-478): a nested mapping
+override must redefine every key of the mapping it replaces.  ``configure`` itself is a
+shallow ``dict.update`` (abstract.py:127-129).
+"""
+from __future__ import annotations
+
+import copy
+from typing import Any, Mapping
+
+
+def abstract_default_config() -> dict:
+    return {
+        "observation": {"type": "Kinematics"},
+        "action": {"type": "DiscreteMetaAction"},
+        "simulation_frequency": 15,
+        "policy_frequency": 1,
+        "other_vehicles_type": "highway_env.vehicle.behavior.IDMVehicle",
+        "screen_width": 600,
+        "screen_height": 150,
+        "centering_position": [0.3, 0.5],
+        "scaling": 5.5,
+        "show_trajectories": False,
+        "render_agent": True,
+        "offscreen_rendering": None,
+        "manual_control": False,
+        "real_time_rendering": False,
+        "neighbour_vehicles_connected_lanes": False,
+    }
+
+
+def update_config_check(config: Mapping[str, Any], delta: Mapping[str, Any], path: str = "config") -> None:
+    for key, val in config.items():
+        if key not in delta or not isinstance(val, Mapping):
+            continue
+        sub = f"{path}.{key}"
+        new_val = delta[key]
+        assert isinstance(new_val, Mapping), f"{sub} must be a mapping, got {type(new_val).__name__}"
+        if key in ("action", "observation"):
+            nested = new_val.get(key + "_config")
+            if isinstance(nested, Mapping):
+                new_val = {**new_val, **nested}
+        missing_keys = val.keys() - new_val.keys()
+        assert not missing_keys, f"{sub} invalid: {missing_keys=}"
+        update_config_check(val, new_val, sub)
+
+
+def update_config(config: dict, delta: Mapping[str, Any]) -> dict:
+    update_config_check(config, delta)
+    config.update(delta)
+    return config
+
+
+def highway_default_config() -> dict:
+    config = abstract_default_config()
+    update_config(config, {
+        "observation": {"type": "Kinematics"},
+        "action": {"type": "DiscreteMetaAction"},
+        "lanes_count": 4,
+        "vehicles_count": 50,
+        "controlled_vehicles": 1,
+        "initial_lane_id": None,
+        "duration": 40,
+        "ego_spacing": 2,
+        "vehicles_density": 1,
+        "collision_reward": -1,
+        "right_lane_reward": 0.1,
+        "high_speed_reward": 0.4,
+        "lane_change_reward": 0,
+        "reward_speed_range": [20, 30],
+        "normalize_reward": True,
+        "offroad_terminal": False,
+    })
+    return config
+
+
+def highway_fast_default_config() -> dict:
+    cfg = highway_default_config()
+    update_config(cfg, {
+        "simulation_frequency": 5,
+        "lanes_count": 3,
+        "vehicles_count": 20,
+        "duration": 30,
+        "ego_spacing": 1.5,
+    })
+    return cfg
+
+
+# backend keys the reference ignores
+BACKEND_DEFAULTS = {"num_envs": 1, "device": "cuda"}
+
+DEFAULTS = {
+    "highway-v0": highway_default_config,
+    "highway-fast-v0": highway_fast_default_config,
+}
+
+
+def default_config(env_id: str) -> dict:
+    return copy.deepcopy(DEFAULTS[env_id]())

@@ -1,0 +1,113 @@
+// hwy_math.cuh — scalar helpers shared by the sm_100a kernels.
+//
+// The simulation arithmetic is fp64 and follows the reference's operation order; the
+// translation unit is compiled with -fmad=false so the compiler never contracts a*b+c.
+// The only fused operations are the explicit fma() below, which reproduce what numpy
+// itself does for 2-vector np.dot / np.linalg.norm (see DESIGN.md "numerics").
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace hwy {
+
+constexpr double kPi = 3.141592653589793;        // np.pi
+constexpr double kTwoPi = 2 * 3.141592653589793;  // 2 * np.pi
+constexpr double kVehLength = 5.0;                // vehicle/kinematics.py:21
+constexpr double kVehWidth = 2.0;                 // vehicle/kinematics.py:23
+constexpr double kMaxSpeed = 40.0;                // vehicle/kinematics.py:27
+constexpr double kMinSpeed = -40.0;               // vehicle/kinematics.py:29
+constexpr double kLaneVehLength = 5.0;            // road/lane.py:17
+// ControlledVehicle gains, vehicle/controller.py:24-33
+constexpr double kTauAcc = 0.6, kTauHeading = 0.2, kTauLateral = 0.6;
+constexpr double kTauPursuit = 0.5 * kTauHeading;
+constexpr double kKpA = 1 / kTauAcc;
+constexpr double kKpHeading = 1 / kTauHeading;
+constexpr double kKpLateral = 1 / kTauLateral;
+constexpr double kMaxSteer = kPi / 3;
+
+// np.dot on 2-vectors: fma(a1*b1 + round(a0*b0))
+__device__ __forceinline__ double dot2(double a0, double a1, double b0, double b1) {
+    return fma(a1, b1, a0 * b0);
+}
+__device__ __forceinline__ double norm2(double a0, double a1) { return sqrt(dot2(a0, a1, a0, a1)); }
+__device__ __forceinline__ double clipd(double x, double lo, double hi) {
+    return fmin(fmax(x, lo), hi);
+}
+// utils.py:50-56
+__device__ __forceinline__ double not_zero(double x) {
+    const double eps = 1e-2;
+    if (fabs(x) > eps) return x;
+    return x >= 0 ? eps : -eps;
+}
+// Python floored float modulo (b > 0 here); fast path when 0 <= a < b (fmod is exact: a).
+__device__ __forceinline__ double py_mod_pos(double a, double b) {
+    if (a >= 0.0 && a < b) return a;
+    double m = fmod(a, b);
+    if (m != 0.0) {
+        if (m < 0) m += b;
+    } else {
+        m = 0.0;
+    }
+    return m;
+}
+// utils.py:59-60
+__device__ __forceinline__ double wrap_to_pi(double x) { return py_mod_pos(x + kPi, kTwoPi) - kPi; }
+// utils.py:31-33
+__device__ __forceinline__ double lmap(double v, double x0, double x1, double y0, double y1) {
+    return y0 + (v - x0) * (y1 - y0) / (x1 - x0);
+}
+
+// numpy Generator(PCG64): 128-bit LCG, XSL-RR output (numpy/random/src/pcg64/pcg64.h)
+struct Pcg64 {
+    uint64_t s_hi, s_lo, i_hi, i_lo;
+    uint32_t has32, u32;
+
+    __device__ __forceinline__ uint64_t next64() {
+        const uint64_t m_hi = 0x2360ed051fc65da4ULL, m_lo = 0x4385df649fccf645ULL;
+        uint64_t lo = s_lo * m_lo;
+        uint64_t hi = __umul64hi(s_lo, m_lo) + s_hi * m_lo + s_lo * m_hi;
+        uint64_t nlo = lo + i_lo;
+        uint64_t carry = nlo < lo ? 1 : 0;
+        s_lo = nlo;
+        s_hi = hi + i_hi + carry;
+        uint64_t x = s_hi ^ s_lo;
+        unsigned rot = (unsigned)(s_hi >> 58);
+        return (x >> rot) | (x << ((64 - rot) & 63));
+    }
+    __device__ __forceinline__ uint32_t next32() {
+        if (has32) {
+            has32 = 0;
+            return u32;
+        }
+        uint64_t n = next64();
+        has32 = 1;
+        u32 = (uint32_t)(n >> 32);
+        return (uint32_t)n;
+    }
+    __device__ __forceinline__ double next_double() {
+        return (double)(next64() >> 11) * (1.0 / 9007199254740992.0);
+    }
+    // Generator.uniform (distributions.c random_uniform)
+    __device__ __forceinline__ double uniform(double lo, double hi) {
+        double range = hi - lo;
+        return lo + range * next_double();
+    }
+    // Generator.choice(n) / integers(0, n): Lemire rejection on buffered 32-bit draws
+    __device__ __forceinline__ int choice(int n) {
+        uint32_t rng = (uint32_t)(n - 1);
+        if (rng == 0) return 0;
+        uint32_t rng_excl = rng + 1;
+        uint64_t m = (uint64_t)next32() * rng_excl;
+        uint32_t leftover = (uint32_t)m;
+        if (leftover < rng_excl) {
+            uint32_t threshold = (0xffffffffu - rng) % rng_excl;
+            while (leftover < threshold) {
+                m = (uint64_t)next32() * rng_excl;
+                leftover = (uint32_t)m;
+            }
+        }
+        return (int)(m >> 32);
+    }
+};
+
+}  // namespace hwy

@@ -1,0 +1,157 @@
+/*
+ * hwyb200.h — C ABI of the B200-native batched HighwayEnv hot path.
+ *
+ * Plain pointers and sizes only (no torch / C++ types).  Every pointer in the *State
+ * structs and every array argument is a DEVICE pointer owned by the caller (the Python
+ * host allocates them as torch CUDA tensors); kernels run on the `stream` argument
+ * (a cudaStream_t passed as void*, NULL = legacy default stream) and never allocate.
+ * All functions return 0 on success, non-zero on error (hwy_last_error() gives the text);
+ * there is no CPU fallback anywhere behind this interface.
+ *
+ * The reference (HighwayEnv 1.12.1, pure Python) has no FFI; the seam these entry points
+ * replace is the operator interface AbstractEnv._simulate drives
+ * (highway_env/envs/common/abstract.py:287-317):
+ *     action_type.act(action); road.act(); road.step(1 / simulation_frequency)
+ * followed by observation_type.observe(), _reward(), _is_terminated(), _is_truncated()
+ * (abstract.py:277-280), and AbstractEnv.reset()'s _reset() (abstract.py:219-249).
+ * INTEGRATION.md shows the ctypes binding a reference maintainer would add.
+ */
+#ifndef HWYB200_H
+#define HWYB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HWY_ABI_VERSION 1
+#define HWY_MAX_LANES 8
+#define HWY_MAX_TARGET_SPEEDS 8
+#define HWY_MAX_VEHICLES 128 /* per env, incl. the ego */
+#define HWY_MAX_OBS_VEHICLES 16
+
+/* vehicle kinds (bits 19-20 of `meta`) */
+#define HWY_KIND_IDM 0     /* highway_env/vehicle/behavior.py:12   IDMVehicle */
+#define HWY_KIND_MDP 1     /* highway_env/vehicle/controller.py:256 MDPVehicle */
+#define HWY_KIND_VEHICLE 2 /* highway_env/vehicle/kinematics.py:13  Vehicle */
+
+/* meta word layout (one int32 per vehicle slot) */
+#define HWY_META_LANE_SHIFT 0         /* 8 bits: lane_index (graph enumeration order) */
+#define HWY_META_TARGET_SHIFT 8       /* 8 bits: target_lane_index */
+#define HWY_META_CRASHED (1 << 16)
+#define HWY_META_HAS_IMPACT (1 << 17) /* Vehicle.impact is not None */
+#define HWY_META_CHECK_COLLISIONS (1 << 18)
+#define HWY_META_KIND_SHIFT 19        /* 2 bits */
+#define HWY_META_PRESENT (1 << 21)
+
+/* autoreset modes of hwy_highway_step (gymnasium.vector.AutoresetMode) */
+#define HWY_AUTORESET_DISABLED 0
+#define HWY_AUTORESET_SAME_STEP 1 /* reset inside the step that ended; obs = reset obs */
+
+/* A StraightLane (highway_env/road/lane.py:159-213), fields as its __init__ computes them. */
+typedef struct HwyStraightLane {
+    double start_x, start_y;
+    double dir_x, dir_y;         /* direction */
+    double lat_x, lat_y;         /* direction_lateral */
+    double heading, length, width, speed_limit;
+} HwyStraightLane;
+
+/* Scenario parameters of the straight multi-lane highway family: highway-v0 and
+ * highway-fast-v0 (highway_env/envs/highway_env.py:25-53,162-182 over
+ * envs/common/abstract.py:102-125).  Passed by value to the kernels. */
+typedef struct HwyHighwayParams {
+    int32_t lanes_count;
+    int32_t n_vehicles;              /* controlled (1) + vehicles_count, <= HWY_MAX_VEHICLES */
+    int32_t simulation_frequency;
+    int32_t policy_frequency;
+    int32_t action_type;             /* 0 DiscreteMetaAction (action.py:199-298), 1 ContinuousAction (:73-162) */
+    int32_t others_check_collisions; /* 0 = highway-fast-v0 (highway_env.py:177-182) */
+    int32_t normalize_reward;
+    int32_t offroad_terminal;
+    int32_t obs_vehicles_count;      /* KinematicObservation.vehicles_count (observation.py:163) */
+    int32_t obs_see_behind;
+    int32_t obs_absolute;
+    int32_t obs_normalize;
+    int32_t obs_clip;
+    int32_t n_target_speeds;
+    int32_t initial_lane_id;         /* -1 = None */
+    int32_t act_clip;                /* ContinuousAction.clip */
+    double duration;
+    double target_speeds[HWY_MAX_TARGET_SPEEDS]; /* MDPVehicle.target_speeds (controller.py:259) */
+    double collision_reward, right_lane_reward, high_speed_reward;
+    double reward_speed_lo, reward_speed_hi;
+    double acc_lo, acc_hi, steer_lo, steer_hi;   /* action.py:82-86 */
+    double ego_spacing, vehicles_density, ego_speed;
+    double spawn_exp;                /* np.exp(-5/40*lanes) evaluated on the host (kinematics.py:95) */
+    /* IDM / MOBIL (behavior.py:21-46) */
+    double acc_max, comfort_acc_max, comfort_acc_min, distance_wanted, time_wanted;
+    double politeness, lane_change_min_acc_gain, lane_change_max_braking_imposed, lane_change_delay;
+    double delta_lo, delta_hi;
+    double perception_distance;      /* abstract.py:56 */
+    HwyStraightLane lanes[HWY_MAX_LANES];
+} HwyHighwayParams;
+
+/* Device-resident state of n_envs independent roads, structure of arrays over
+ * (env, vehicle slot); slot stride `vp` (see hwy_highway_slot_stride).  Packed pairs are
+ * interleaved doubles so that one thread moves one vehicle with 128-bit accesses.
+ *   pos[2*(e*vp+v)+{0,1}] = position x, y         hs = heading, speed
+ *   tt  = target_speed, timer (IDM lane-change timer) imp = Vehicle.impact x, y
+ * Per env: speed_index (MDPVehicle.speed_index), time (AbstractEnv.time), and the numpy
+ * Generator(PCG64) stream of env.np_random as 5 words rng[k*n_envs+e]:
+ *   k=0 state_hi, 1 state_lo, 2 inc_hi, 3 inc_lo, 4 (has_uint32 << 32) | uinteger. */
+typedef struct HwyHighwayState {
+    int32_t n_envs;
+    int32_t vp;
+    double *pos, *hs, *tt, *imp; /* [n_envs*vp*2] */
+    double *delta;               /* [n_envs*vp]   IDMVehicle.DELTA */
+    int32_t *meta;               /* [n_envs*vp] */
+    int32_t *speed_index;        /* [n_envs] */
+    double *time;                /* [n_envs] */
+    uint64_t *rng;               /* [5*n_envs] */
+} HwyHighwayState;
+
+int hwy_abi_version(void);
+const char *hwy_last_error(void);
+
+/* Slot stride for n_vehicles (next multiple of 2; 128-bit alignment of the packed pairs). */
+int hwy_highway_slot_stride(int n_vehicles);
+
+/* AbstractEnv.reset()'s _reset() for the envs whose mask byte is non-zero (mask == NULL:
+ * all): HighwayEnv._create_road/_create_vehicles (highway_env.py:55-98,177-182) with
+ * Vehicle.create_random (kinematics.py:50-104), drawing from each env's PCG64 stream in
+ * the reference's order.  If obs != NULL also writes the reset observation
+ * [n_envs][obs_vehicles_count][5] float32 of those envs. */
+int hwy_highway_reset(const HwyHighwayParams *p, const HwyHighwayState *s, const uint8_t *mask,
+                      float *obs, void *stream);
+
+/* KinematicObservation.observe() (observation.py:234-276) for all envs. */
+int hwy_highway_observe(const HwyHighwayParams *p, const HwyHighwayState *s, float *obs,
+                        void *stream);
+
+/* One AbstractEnv.step (abstract.py:259-285) for all envs: simulation_frequency //
+ * policy_frequency substeps of {action_type.act on frame 0; Road.act; Road.step}, then
+ * observe / _reward / _is_terminated / _is_truncated.
+ *   action_i [n_envs] int32 (DiscreteMetaAction) or action_f [n_envs][2] float32
+ *   (ContinuousAction); the unused one may be NULL.
+ *   obs [n_envs][K][5] f32, reward [n_envs] f64, terminated/truncated [n_envs] u8.
+ *   info_speed [n_envs] f64 / info_crashed [n_envs] u8 (either may be NULL): the ego's speed
+ *   and crashed flag of AbstractEnv._info (abstract.py:200-217) at the end of the step,
+ *   before any autoreset.
+ *   autoreset = HWY_AUTORESET_SAME_STEP: envs that ended are reset from their RNG stream
+ *   in the same call and `obs` holds the reset observation; `final_obs` (may be NULL)
+ *   receives the pre-reset observation of every env. */
+int hwy_highway_step(const HwyHighwayParams *p, const HwyHighwayState *s, const int32_t *action_i,
+                     const float *action_f, float *obs, double *reward, uint8_t *terminated,
+                     uint8_t *truncated, double *info_speed, uint8_t *info_crashed, int autoreset,
+                     float *final_obs, void *stream);
+
+/* Kernel launches issued by the calling thread through this library since load (the
+ * `gpu_launches` claim of bench.py). */
+uint64_t hwy_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
