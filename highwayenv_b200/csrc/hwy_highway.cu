@@ -924,6 +924,16 @@ int hwy_highway_reset(const HwyHighwayParams* p, const HwyHighwayState* s, const
     return 0;
 }
 
+int hwy_highway_autoreset(const HwyHighwayParams* p, const HwyHighwayState* s,
+                          const uint8_t* terminated, const uint8_t* truncated, float* obs,
+                          void* stream) {
+    if (validate(p, s)) return 1;
+    if (!terminated || !truncated || !obs) return fail("%s", "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (launch_reset(p, s, terminated, truncated, 1, st)) return 1;
+    return launch_observe(p, s, terminated, truncated, 1, obs, st);
+}
+
 int hwy_highway_step(const HwyHighwayParams* p, const HwyHighwayState* s, const int32_t* action_i,
                      const float* action_f, float* obs, double* reward, uint8_t* terminated,
                      uint8_t* truncated, double* info_speed, uint8_t* info_crashed, int autoreset,

@@ -147,6 +147,13 @@ int hwy_highway_step(const HwyHighwayParams *p, const HwyHighwayState *s, const 
                      uint8_t *truncated, double *info_speed, uint8_t *info_crashed, int autoreset,
                      float *final_obs, void *stream);
 
+/* The SameStep autoreset half of hwy_highway_step on its own: re-spawn the envs whose
+ * terminated | truncated byte is set and overwrite their rows of `obs` with the reset
+ * observation (lets a caller time / schedule the two halves separately). */
+int hwy_highway_autoreset(const HwyHighwayParams *p, const HwyHighwayState *s,
+                          const uint8_t *terminated, const uint8_t *truncated, float *obs,
+                          void *stream);
+
 /* Kernel launches issued by the calling thread through this library since load (the
  * `gpu_launches` claim of bench.py). */
 uint64_t hwy_launch_count(void);
