@@ -1,0 +1,177 @@
+// hwy_device.cuh — device functions of the highway hot path that do not depend on the
+// kernel's thread mapping: StraightLane geometry, the steering law, the SAT collision test,
+// MDPVehicle speed indexing.  Reference paths are relative to /root/reference/highway_env.
+#pragma once
+#include "../../include/hwyb200.h"
+#include "hwy_math.cuh"
+
+namespace hwy {
+
+typedef unsigned long long u64;
+
+// ------------------------------------------------------------------ lane geometry
+// road/lane.py:205-209 StraightLane.local_coordinates
+__device__ __forceinline__ void lane_local(const HwyStraightLane& L, double x, double y, double& s,
+                                           double& lat) {
+    double ddx = x - L.start_x, ddy = y - L.start_y;
+    s = dot2(ddx, ddy, L.dir_x, L.dir_y);
+    lat = dot2(ddx, ddy, L.lat_x, L.lat_y);
+}
+__device__ __forceinline__ double lane_s(const HwyStraightLane& L, double x, double y) {
+    return dot2(x - L.start_x, y - L.start_y, L.dir_x, L.dir_y);
+}
+// road/lane.py:80-102 on_lane
+__device__ __forceinline__ bool lane_on(const HwyStraightLane& L, double s, double lat, double margin) {
+    return fabs(lat) <= L.width / 2 + margin && -kLaneVehLength <= s && s < L.length + kLaneVehLength;
+}
+// road/lane.py:104-118 is_reachable_from (forbidden is False on the highway)
+__device__ __forceinline__ bool lane_reachable(const HwyStraightLane& L, double x, double y) {
+    double s, lat;
+    lane_local(L, x, y, s, lat);
+    return fabs(lat) <= 2 * L.width && 0 <= s && s < L.length + kLaneVehLength;
+}
+// road/road.py:55-71 get_closest_lane_index with lane.py:132-143 distance_with_heading:
+// first minimum in graph-enumeration order.
+__device__ __forceinline__ int closest_lane(const HwyHighwayParams& P, double x, double y, double h) {
+    int best = 0;
+    double bd = 0;
+    for (int l = 0; l < P.lanes_count; ++l) {
+        const HwyStraightLane& L = P.lanes[l];
+        double s, r;
+        lane_local(L, x, y, s, r);
+        double angle = fabs(wrap_to_pi(h - L.heading));
+        double d = fabs(r) + fmax(s - L.length, 0.0) + fmax(0.0 - s, 0.0) + 1.0 * angle;
+        if (l == 0 || d < bd) {
+            bd = d;
+            best = l;
+        }
+    }
+    return best;
+}
+// All lanes share origin-x and an x-aligned direction (RoadNetwork.straight_road_network with
+// angle 0, road/road.py:291-321): the longitudinal coordinate is then bitwise lane independent.
+__device__ __forceinline__ bool lanes_aligned(const HwyHighwayParams& P) {
+    bool ok = P.lanes[0].dir_y == 0.0;
+    for (int l = 1; l < P.lanes_count; ++l)
+        ok = ok && P.lanes[l].start_x == P.lanes[0].start_x && P.lanes[l].dir_x == P.lanes[0].dir_x &&
+             P.lanes[l].dir_y == 0.0;
+    return ok;
+}
+
+// vehicle/controller.py:145-187 steering_control on a StraightLane
+__device__ __forceinline__ double steering_control(const HwyStraightLane& L, double x, double y,
+                                                   double heading, double speed) {
+    double lc_s, lc_lat;
+    lane_local(L, x, y, lc_s, lc_lat);
+    double lane_future_heading = L.heading;  // StraightLane.heading_at
+    double lateral_speed_command = -kKpLateral * lc_lat;
+    double heading_command = asin(clipd(lateral_speed_command / not_zero(speed), -1.0, 1.0));
+    double heading_ref = lane_future_heading + clipd(heading_command, -kPi / 4, kPi / 4);
+    double heading_rate_command = kKpHeading * wrap_to_pi(heading_ref - heading);
+    double slip_angle =
+        asin(clipd(kVehLength / 2 / not_zero(speed) * heading_rate_command, -1.0, 1.0));
+    double steering_angle = atan(2 * tan(slip_angle));
+    return clipd(steering_angle, -kMaxSteer, kMaxSteer);
+}
+
+// vehicle/controller.py:326-344 speed_to_index (np.round: half to even)
+__device__ __forceinline__ int speed_to_index(const HwyHighwayParams& P, double speed) {
+    int n = P.n_target_speeds;
+    double x = (speed - P.target_speeds[0]) / (P.target_speeds[n - 1] - P.target_speeds[0]);
+    return (int)clipd(rint(x * (n - 1)), 0.0, (double)(n - 1));
+}
+
+// ------------------------------------------------------------------ collision (SAT)
+// vehicle/objects.py:169-181 polygon()
+__device__ __forceinline__ void polygon(double x, double y, double c, double s, double (&p)[5][2]) {
+    const double hl = kVehLength / 2, hw = kVehWidth / 2;
+    const double lx[4] = {-hl, -hl, +hl, +hl};
+    const double ly[4] = {-hw, +hw, +hw, -hw};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        p[k][0] = (c * lx[k] + (-s) * ly[k]) + x;
+        p[k][1] = (s * lx[k] + c * ly[k]) + y;
+    }
+    p[4][0] = p[0][0];
+    p[4][1] = p[0][1];
+}
+
+__device__ __forceinline__ void project_polygon(const double (&p)[5][2], double ax, double ay,
+                                                double& mn, double& mx) {
+    mn = mx = dot2(p[0][0], p[0][1], ax, ay);
+#pragma unroll
+    for (int k = 1; k < 5; ++k) {
+        double pr = dot2(p[k][0], p[k][1], ax, ay);
+        if (pr < mn) mn = pr;
+        if (pr > mx) mx = pr;
+    }
+}
+__device__ __forceinline__ double interval_distance(double min_a, double max_a, double min_b,
+                                                    double max_b) {
+    return min_a < min_b ? min_b - max_a : min_a - max_b;
+}
+
+// utils.py:196-241 are_polygons_intersecting: SAT over the 4+4 edge normals with the relative
+// displacement extension; returns (intersecting, will_intersect, translation).
+__device__ __noinline__ void polygons_intersecting(const double (&a)[5][2], const double (&b)[5][2],
+                                                   double dax, double day, double dbx, double dby,
+                                                   bool& intersecting, bool& will_intersect,
+                                                   double& trx, double& try_) {
+    intersecting = true;
+    will_intersect = true;
+    double min_distance = INFINITY;
+    double tax = 0, tay = 0;
+    double cax = (((a[0][0] + a[1][0]) + a[2][0]) + a[3][0]) / 4.0;
+    double cay = (((a[0][1] + a[1][1]) + a[2][1]) + a[3][1]) / 4.0;
+    double cbx = (((b[0][0] + b[1][0]) + b[2][0]) + b[3][0]) / 4.0;
+    double cby = (((b[0][1] + b[1][1]) + b[2][1]) + b[3][1]) / 4.0;
+    double dcx = cax - cbx, dcy = cay - cby;
+    for (int poly = 0; poly < 2; ++poly) {
+        for (int e = 0; e < 4; ++e) {
+            double p1x = poly == 0 ? a[e][0] : b[e][0], p1y = poly == 0 ? a[e][1] : b[e][1];
+            double p2x = poly == 0 ? a[e + 1][0] : b[e + 1][0];
+            double p2y = poly == 0 ? a[e + 1][1] : b[e + 1][1];
+            double nx = -p2y + p1y, ny = p2x - p1x;
+            double nn = norm2(nx, ny);
+            nx /= nn;
+            ny /= nn;
+            double min_a, max_a, min_b, max_b;
+            project_polygon(a, nx, ny, min_a, max_a);
+            project_polygon(b, nx, ny, min_b, max_b);
+            if (interval_distance(min_a, max_a, min_b, max_b) > 0) intersecting = false;
+            double vp = dot2(nx, ny, dax - dbx, day - dby);
+            if (vp < 0)
+                min_a += vp;
+            else
+                max_a += vp;
+            double distance = interval_distance(min_a, max_a, min_b, max_b);
+            if (distance > 0) will_intersect = false;
+            if (!intersecting && !will_intersect) break;  // leaves the inner loop only
+            if (fabs(distance) < min_distance) {
+                min_distance = fabs(distance);
+                if (dot2(dcx, dcy, nx, ny) > 0) {
+                    tax = nx;
+                    tay = ny;
+                } else {
+                    tax = -nx;
+                    tay = -ny;
+                }
+            }
+        }
+    }
+    trx = will_intersect ? min_distance * tax : 0.0;
+    try_ = will_intersect ? min_distance * tay : 0.0;
+}
+
+// ------------------------------------------------------------------ packed meta word
+__device__ __forceinline__ int meta_lane(int m) { return (m >> HWY_META_LANE_SHIFT) & 0xff; }
+__device__ __forceinline__ int meta_target(int m) { return (m >> HWY_META_TARGET_SHIFT) & 0xff; }
+__device__ __forceinline__ int meta_kind(int m) { return (m >> HWY_META_KIND_SHIFT) & 3; }
+__device__ __forceinline__ int meta_set_lane(int m, int l) {
+    return (m & ~(0xff << HWY_META_LANE_SHIFT)) | (l << HWY_META_LANE_SHIFT);
+}
+__device__ __forceinline__ int meta_set_target(int m, int l) {
+    return (m & ~(0xff << HWY_META_TARGET_SHIFT)) | (l << HWY_META_TARGET_SHIFT);
+}
+
+}  // namespace hwy

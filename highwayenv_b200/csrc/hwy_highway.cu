@@ -1,79 +1,57 @@
 // hwy_highway.cu — sm_100a kernels + C ABI for the straight-highway family
 // (highway-v0 / highway-fast-v0) of the batched HighwayEnv hot path.
 //
-// One (env, vehicle) pair per thread; TPE threads per env (32/64/128, the next power of
-// two >= n_vehicles).  The whole AbstractEnv.step — all substeps of Road.act/Road.step,
-// then observe/reward/termination — runs in ONE kernel: the SoA state makes one HBM round
-// trip per env-step, neighbour data is staged in shared memory once per substep, and the
-// O(V^2) searches (IDM front/rear vehicle, MOBIL, abort scan, collision sweep) broadcast
-// from shared memory.  The reference's sequential semantics (Gauss-Seidel target-lane
-// updates in Road.act, last-writer-wins impacts in Road.step) are reproduced with an
-// ordered bit-mask fix-up, see DESIGN.md.
+// Thread mapping: one (env, vehicle) pair per thread, TPE threads per env (32/64/128, the
+// next power of two >= n_vehicles).  The whole AbstractEnv.step — every substep of
+// Road.act/Road.step, then observe/reward/termination — runs in ONE kernel, so the SoA state
+// makes one HBM round trip per env-step (128-bit loads/stores per vehicle).
 //
-// Reference paths are relative to /root/reference/highway_env.
+// Per substep each env stages its vehicles in shared memory ("Frame", double buffered) and
+// derives, in parallel and without divergence:
+//   * the rank of every vehicle along the road and per-lane membership bit-masks in rank
+//     order, which turn Road.neighbour_vehicles (the reference's 65 % hot spot, an O(V) scan
+//     per query) into two bit-scans;
+//   * per-lane target / lane bit-masks that prune IDMVehicle.change_lane_policy's abort scan
+//     to the handful of vehicles that can matter;
+//   * the collision sweep as a pair-parallel pass (sphere pre-check per pair, SAT only for
+//     the rare close pairs) reduced per vehicle with shared-memory atomics.
+// The reference's sequential semantics (Gauss-Seidel target-lane updates in Road.act,
+// last-writer-wins impacts in Road.step, tie rules of the neighbour search) are preserved:
+// see DESIGN.md "ordering".  Reference paths are relative to /root/reference/highway_env.
 #include <cstdio>
 #include <cstring>
 #include <cuda_runtime.h>
 
 #include "../../include/hwyb200.h"
+#include "hwy_device.cuh"
 #include "hwy_math.cuh"
 
 namespace hwy {
 
-typedef unsigned long long u64;
-
-// ------------------------------------------------------------------ lane geometry
-// road/lane.py:205-209 StraightLane.local_coordinates
-__device__ __forceinline__ void lane_local(const HwyStraightLane& L, double x, double y, double& s,
-                                           double& lat) {
-    double ddx = x - L.start_x, ddy = y - L.start_y;
-    s = dot2(ddx, ddy, L.dir_x, L.dir_y);
-    lat = dot2(ddx, ddy, L.lat_x, L.lat_y);
-}
-__device__ __forceinline__ double lane_s(const HwyStraightLane& L, double x, double y) {
-    return dot2(x - L.start_x, y - L.start_y, L.dir_x, L.dir_y);
-}
-// road/lane.py:80-102 on_lane
-__device__ __forceinline__ bool lane_on(const HwyStraightLane& L, double s, double lat, double margin) {
-    return fabs(lat) <= L.width / 2 + margin && -kLaneVehLength <= s && s < L.length + kLaneVehLength;
-}
-// road/lane.py:104-118 is_reachable_from (forbidden is False on the highway)
-__device__ __forceinline__ bool lane_reachable(const HwyStraightLane& L, double x, double y) {
-    double s, lat;
-    lane_local(L, x, y, s, lat);
-    return fabs(lat) <= 2 * L.width && 0 <= s && s < L.length + kLaneVehLength;
-}
-// road/road.py:55-71 get_closest_lane_index with lane.py:132-143 distance_with_heading
-__device__ __forceinline__ int closest_lane(const HwyHighwayParams& P, double x, double y, double h) {
-    int best = 0;
-    double bd = 0;
-    for (int l = 0; l < P.lanes_count; ++l) {
-        const HwyStraightLane& L = P.lanes[l];
-        double s, r;
-        lane_local(L, x, y, s, r);
-        double angle = fabs(wrap_to_pi(h - L.heading));
-        double d = fabs(r) + fmax(s - L.length, 0.0) + fmax(0.0 - s, 0.0) + 1.0 * angle;
-        if (l == 0 || d < bd) {
-            bd = d;
-            best = l;
-        }
-    }
-    return best;
-}
-
 // ------------------------------------------------------------------ shared staging
 template <int TPE>
-struct EnvShared {
-    static constexpr int NW = (TPE + 63) / 64;
+struct Frame {
+    static constexpr int NW = TPE / 32;
     double x[TPE], y[TPE], c[TPE], s[TPE], v[TPE], ts[TPE];
-    double key[TPE];  // observation sort keys
-    u64 geo[TPE][NW];             // abort-scan geometric candidates of mid-change vehicles
-    u64 tm[HWY_MAX_LANES][NW];    // vehicles whose current target lane is l
-    u64 lane_ne[HWY_MAX_LANES][NW];  // vehicles whose lane_index != l
-    u64 mid[NW];                  // active mid-change IDM vehicles (lane != target)
-    u64 changed[NW];              // IDM vehicles whose MOBIL decision changed the target
-    u64 aborted[NW];
-    unsigned char lane[TPE], tgt[TPE], tgt1[TPE], flags[TPE];  // flags: 1 check_collisions, 2 controlled
+    double ls[TPE];                          // longitudinal coordinate on lane 0
+    uint32_t smask[HWY_MAX_LANES][NW];       // rank-ordered on_lane(margin=1) membership of lane l
+    uint32_t tm[HWY_MAX_LANES][NW];          // vehicles whose target lane is l   (slot order)
+    uint32_t lane_is[HWY_MAX_LANES][NW];     // vehicles whose lane_index is l    (slot order)
+    uint32_t fired[NW];                      // IDM vehicles whose lane-change timer will fire
+    unsigned char lane[TPE], tgt[TPE], perm[TPE], rank[TPE];
+    int slow;                                // ties in ls or unaligned lanes: use the linear scans
+};
+
+template <int TPE>
+struct EnvShared {
+    static constexpr int NW = TPE / 32;
+    Frame<TPE> f[2];
+    double key[TPE];                         // observation sort keys
+    uint32_t geo[TPE][NW];                   // abort-scan hits (0 < d < d*) of mid-change vehicles
+    uint32_t mid[NW], changed[NW], aborted[NW];
+    uint32_t ctrl[NW], cc[NW];               // ControlledVehicle instances / check_collisions
+    int last_will[TPE];                      // collision sweep: largest partner with will_intersect
+    unsigned char crash_hit[TPE], tgt1[TPE];
 };
 
 template <int TPE>
@@ -84,19 +62,26 @@ __device__ __forceinline__ void env_sync() {
         __syncthreads();
 }
 
-// road/road.py:483-547 neighbour_vehicles (same-segment search).  Ties: front `<=` keeps the
-// later index, rear `>` keeps the earlier one.
+template <int NW>
+__device__ __forceinline__ bool test_bit(const uint32_t (&m)[NW], int i) {
+    return (m[i >> 5] >> (i & 31)) & 1u;
+}
+
+// ------------------------------------------------------------------ neighbour search
+// road/road.py:483-547 neighbour_vehicles, same-segment search, exact linear form (used when
+// two vehicles share a longitudinal coordinate or the lanes are not axis aligned).
+// Ties: front `<=` keeps the later index, rear `>` keeps the earlier one.
 template <int TPE>
-__device__ __forceinline__ void neighbours(const EnvShared<TPE>& sm, const HwyStraightLane& L, int V,
-                                           int self, int& front, int& rear) {
-    double s = lane_s(L, sm.x[self], sm.y[self]);
+__device__ __noinline__ void neighbours_linear(const Frame<TPE>& F, const HwyStraightLane L, int V,
+                                               int self, int& front, int& rear) {
+    double s = lane_s(L, F.x[self], F.y[self]);
     double s_front = 0, s_rear = 0;
     front = -1;
     rear = -1;
     for (int v = 0; v < V; ++v) {
         if (v == self) continue;
         double s_v, lat_v;
-        lane_local(L, sm.x[v], sm.y[v], s_v, lat_v);
+        lane_local(L, F.x[v], F.y[v], s_v, lat_v);
         if (!lane_on(L, s_v, lat_v, 1.0)) continue;
         if (s <= s_v && (front < 0 || s_v <= s_front)) {
             s_front = s_v;
@@ -109,186 +94,97 @@ __device__ __forceinline__ void neighbours(const EnvShared<TPE>& sm, const HwySt
     }
 }
 
-// vehicle/behavior.py:192-217 desired_gap(ego, front), projected
+// Same query through the rank-ordered membership mask: the preceding vehicle is the member of
+// lane l with the lowest rank above ours, the following one the highest rank below.
 template <int TPE>
-__device__ __forceinline__ double desired_gap(const HwyHighwayParams& P, const EnvShared<TPE>& sm,
-                                              int ego, int front) {
+__device__ __forceinline__ void neighbours(const HwyHighwayParams& P, const Frame<TPE>& F, int V, int l,
+                                           int self, int& front, int& rear) {
+    constexpr int NW = TPE / 32;
+    if (F.slow) {
+        neighbours_linear(F, P.lanes[l], V, self, front, rear);
+        return;
+    }
+    const int r = F.rank[self];
+    const int w0 = r >> 5, b = r & 31;
+    front = -1;
+    rear = -1;
+    uint32_t m = F.smask[l][w0] & (b == 31 ? 0u : (~0u << (b + 1)));
+    int w = w0;
+    while (m == 0 && ++w < NW) m = F.smask[l][w];
+    if (m) front = F.perm[w * 32 + __ffs(m) - 1];
+    m = F.smask[l][w0] & ((1u << b) - 1u);
+    w = w0;
+    while (m == 0 && --w >= 0) m = F.smask[l][w];
+    if (m) rear = F.perm[w * 32 + 31 - __clz(m)];
+}
+
+// ------------------------------------------------------------------ IDM (vehicle/behavior.py)
+// :192-217 desired_gap(ego, front), projected
+template <int TPE>
+__device__ __forceinline__ double desired_gap(const HwyHighwayParams& P, const Frame<TPE>& F, int ego,
+                                              int front) {
     double ab = -P.comfort_acc_max * P.comfort_acc_min;
-    double dvx = sm.v[ego] * sm.c[ego] - sm.v[front] * sm.c[front];
-    double dvy = sm.v[ego] * sm.s[ego] - sm.v[front] * sm.s[front];
-    double dv = dot2(dvx, dvy, sm.c[ego], sm.s[ego]);
-    return P.distance_wanted + sm.v[ego] * P.time_wanted + sm.v[ego] * dv / (2 * sqrt(ab));
+    double dvx = F.v[ego] * F.c[ego] - F.v[front] * F.c[front];
+    double dvy = F.v[ego] * F.s[ego] - F.v[front] * F.s[front];
+    double dv = dot2(dvx, dvy, F.c[ego], F.s[ego]);
+    return P.distance_wanted + F.v[ego] * P.time_wanted + F.v[ego] * dv / (2 * sqrt(ab));
 }
-
-// vehicle/behavior.py:150-190 acceleration(ego_vehicle, front_vehicle) with the CALLER's DELTA
+// lane_distance_to on the ego's own lane (vehicle/objects.py:183-198)
 template <int TPE>
-__device__ __forceinline__ double idm_acceleration(const HwyHighwayParams& P, const EnvShared<TPE>& sm,
-                                                   double delta, int ego, int front) {
+__device__ __forceinline__ double lane_distance(const HwyHighwayParams& P, const Frame<TPE>& F,
+                                                bool aligned, int ego, int other) {
+    if (aligned) return F.ls[other] - F.ls[ego];
+    const HwyStraightLane& L = P.lanes[F.lane[ego]];
+    return lane_s(L, F.x[other], F.y[other]) - lane_s(L, F.x[ego], F.y[ego]);
+}
+// :150-190 acceleration(): free-road term with the CALLER's DELTA ...
+__device__ __forceinline__ double idm_free_term(const HwyHighwayParams& P, double speed,
+                                                double target_speed, double speed_limit, double delta) {
+    double ego_target_speed = clipd(target_speed, 0.0, speed_limit);
+    return P.comfort_acc_max * (1 - pow(fmax(speed, 0.0) / fabs(not_zero(ego_target_speed)), delta));
+}
+// ... and the interaction term COMFORT_ACC_MAX * (d* / not_zero(d))^2
+template <int TPE>
+__device__ __forceinline__ double idm_gap_term(const HwyHighwayParams& P, const Frame<TPE>& F,
+                                               bool aligned, int ego, int front) {
+    double d = lane_distance(P, F, aligned, ego, front);
+    double q = desired_gap(P, F, ego, front) / not_zero(d);
+    return P.comfort_acc_max * (q * q);  // np.power(q, 2)
+}
+// acceleration(ego_vehicle=ego, front_vehicle=front) for an `ego` other than the caller
+template <int TPE>
+__device__ __forceinline__ double idm_acceleration_of(const HwyHighwayParams& P, const Frame<TPE>& F,
+                                                      bool aligned, double delta, int ego, int front) {
     if (ego < 0) return 0.0;
-    const HwyStraightLane& L = P.lanes[sm.lane[ego]];
-    double ego_target_speed = clipd(sm.ts[ego], 0.0, L.speed_limit);
-    double acc = P.comfort_acc_max *
-                 (1 - pow(fmax(sm.v[ego], 0.0) / fabs(not_zero(ego_target_speed)), delta));
-    if (front >= 0) {
-        double d = lane_s(L, sm.x[front], sm.y[front]) - lane_s(L, sm.x[ego], sm.y[ego]);
-        double q = desired_gap(P, sm, ego, front) / not_zero(d);
-        acc -= P.comfort_acc_max * (q * q);  // np.power(q, 2)
-    }
+    double acc = idm_free_term(P, F.v[ego], F.ts[ego], P.lanes[F.lane[ego]].speed_limit, delta);
+    if (front >= 0) acc -= idm_gap_term(P, F, aligned, ego, front);
     return acc;
-}
-
-// vehicle/controller.py:145-187 steering_control on a StraightLane
-__device__ __forceinline__ double steering_control(const HwyStraightLane& L, double x, double y,
-                                                   double heading, double speed) {
-    double lc_s, lc_lat;
-    lane_local(L, x, y, lc_s, lc_lat);
-    double lane_future_heading = L.heading;  // StraightLane.heading_at
-    double lateral_speed_command = -kKpLateral * lc_lat;
-    double heading_command = asin(clipd(lateral_speed_command / not_zero(speed), -1.0, 1.0));
-    double heading_ref = lane_future_heading + clipd(heading_command, -kPi / 4, kPi / 4);
-    double heading_rate_command = kKpHeading * wrap_to_pi(heading_ref - heading);
-    double slip_angle =
-        asin(clipd(kVehLength / 2 / not_zero(speed) * heading_rate_command, -1.0, 1.0));
-    double steering_angle = atan(2 * tan(slip_angle));
-    return clipd(steering_angle, -kMaxSteer, kMaxSteer);
-}
-
-// vehicle/behavior.py:265-324 mobil(lane_index); route is None on the highway
-template <int TPE>
-__device__ __forceinline__ bool mobil(const HwyHighwayParams& P, const EnvShared<TPE>& sm, int V, int i,
-                                      double delta, int cand, int old_preceding, int old_following) {
-    int new_preceding, new_following;
-    neighbours(sm, P.lanes[cand], V, i, new_preceding, new_following);
-    double new_following_pred_a = idm_acceleration(P, sm, delta, new_following, i);
-    if (new_following_pred_a < -P.lane_change_max_braking_imposed) return false;
-    double self_pred_a = idm_acceleration(P, sm, delta, i, new_preceding);
-    double self_a = idm_acceleration(P, sm, delta, i, old_preceding);
-    double jerk = self_pred_a - self_a;
-    if (P.politeness != 0.0) {
-        double new_following_a = idm_acceleration(P, sm, delta, new_following, new_preceding);
-        double old_following_a = idm_acceleration(P, sm, delta, old_following, i);
-        double old_following_pred_a = idm_acceleration(P, sm, delta, old_following, old_preceding);
-        jerk = self_pred_a - self_a +
-               P.politeness * (new_following_pred_a - new_following_a + old_following_pred_a -
-                               old_following_a);
-    }
-    return !(jerk < P.lane_change_min_acc_gain);
-}
-
-// vehicle/objects.py:169-181 polygon()
-template <int TPE>
-__device__ __forceinline__ void polygon(const EnvShared<TPE>& sm, int v, double (&p)[5][2]) {
-    const double hl = kVehLength / 2, hw = kVehWidth / 2;
-    const double lx[4] = {-hl, -hl, +hl, +hl};
-    const double ly[4] = {-hw, +hw, +hw, -hw};
-    double c = sm.c[v], s = sm.s[v];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        p[k][0] = (c * lx[k] + (-s) * ly[k]) + sm.x[v];
-        p[k][1] = (s * lx[k] + c * ly[k]) + sm.y[v];
-    }
-    p[4][0] = p[0][0];
-    p[4][1] = p[0][1];
-}
-
-__device__ __forceinline__ void project_polygon(const double (&p)[5][2], double ax, double ay,
-                                                double& mn, double& mx) {
-    mn = mx = dot2(p[0][0], p[0][1], ax, ay);
-#pragma unroll
-    for (int k = 1; k < 5; ++k) {
-        double pr = dot2(p[k][0], p[k][1], ax, ay);
-        if (pr < mn) mn = pr;
-        if (pr > mx) mx = pr;
-    }
-}
-__device__ __forceinline__ double interval_distance(double min_a, double max_a, double min_b,
-                                                    double max_b) {
-    return min_a < min_b ? min_b - max_a : min_a - max_b;
-}
-
-// utils.py:196-241 are_polygons_intersecting: SAT over the 4+4 edge normals with the
-// relative displacement extension; returns (intersecting, will_intersect, translation).
-__device__ __noinline__ void polygons_intersecting(const double (&a)[5][2], const double (&b)[5][2],
-                                                   double dax, double day, double dbx, double dby,
-                                                   bool& intersecting, bool& will_intersect,
-                                                   double& trx, double& try_) {
-    intersecting = true;
-    will_intersect = true;
-    double min_distance = INFINITY;
-    double tax = 0, tay = 0;
-    double cax = (((a[0][0] + a[1][0]) + a[2][0]) + a[3][0]) / 4.0;
-    double cay = (((a[0][1] + a[1][1]) + a[2][1]) + a[3][1]) / 4.0;
-    double cbx = (((b[0][0] + b[1][0]) + b[2][0]) + b[3][0]) / 4.0;
-    double cby = (((b[0][1] + b[1][1]) + b[2][1]) + b[3][1]) / 4.0;
-    double dcx = cax - cbx, dcy = cay - cby;
-    for (int poly = 0; poly < 2; ++poly) {
-        for (int e = 0; e < 4; ++e) {
-            double p1x = poly == 0 ? a[e][0] : b[e][0], p1y = poly == 0 ? a[e][1] : b[e][1];
-            double p2x = poly == 0 ? a[e + 1][0] : b[e + 1][0];
-            double p2y = poly == 0 ? a[e + 1][1] : b[e + 1][1];
-            double nx = -p2y + p1y, ny = p2x - p1x;
-            double nn = norm2(nx, ny);
-            nx /= nn;
-            ny /= nn;
-            double min_a, max_a, min_b, max_b;
-            project_polygon(a, nx, ny, min_a, max_a);
-            project_polygon(b, nx, ny, min_b, max_b);
-            if (interval_distance(min_a, max_a, min_b, max_b) > 0) intersecting = false;
-            double vp = dot2(nx, ny, dax - dbx, day - dby);
-            if (vp < 0)
-                min_a += vp;
-            else
-                max_a += vp;
-            double distance = interval_distance(min_a, max_a, min_b, max_b);
-            if (distance > 0) will_intersect = false;
-            if (!intersecting && !will_intersect) break;  // leaves the inner loop only
-            if (fabs(distance) < min_distance) {
-                min_distance = fabs(distance);
-                if (dot2(dcx, dcy, nx, ny) > 0) {
-                    tax = nx;
-                    tay = ny;
-                } else {
-                    tax = -nx;
-                    tay = -ny;
-                }
-            }
-        }
-    }
-    trx = will_intersect ? min_distance * tax : 0.0;
-    try_ = will_intersect ? min_distance * tay : 0.0;
-}
-
-// vehicle/controller.py:326-344 speed_to_index (np.round: half to even)
-__device__ __forceinline__ int speed_to_index(const HwyHighwayParams& P, double speed) {
-    int n = P.n_target_speeds;
-    double x = (speed - P.target_speeds[0]) / (P.target_speeds[n - 1] - P.target_speeds[0]);
-    return (int)clipd(rint(x * (n - 1)), 0.0, (double)(n - 1));
 }
 
 // ------------------------------------------------------------------ observation
 // envs/common/observation.py:234-276 KinematicObservation.observe (presence,x,y,vx,vy; order
 // "sorted") with road/road.py:421-450 close_objects_to and kinematics.py:237-261 to_dict.
-// Requires sm.{x,y,c,s,v,lane[0]} published; `i` is the vehicle slot of the calling thread.
 template <int TPE>
-__device__ __forceinline__ void kinematics_observe(const HwyHighwayParams& P, EnvShared<TPE>& sm,
-                                                   int i, float* __restrict__ obs_env) {
+__device__ __forceinline__ void kinematics_observe(const HwyHighwayParams& P, const Frame<TPE>& F,
+                                                   double* key_scratch, int i,
+                                                   float* __restrict__ obs_env) {
     const int V = P.n_vehicles, K = P.obs_vehicles_count;
-    const HwyStraightLane& Le = P.lanes[sm.lane[0]];
-    const double ex = sm.x[0], ey = sm.y[0];
-    const double evx = sm.v[0] * sm.c[0], evy = sm.v[0] * sm.s[0];
+    const HwyStraightLane& Le = P.lanes[F.lane[0]];
+    const double ex = F.x[0], ey = F.y[0];
+    const double evx = F.v[0] * F.c[0], evy = F.v[0] * F.s[0];
     double key = INFINITY;
     if (i > 0 && i < V) {
-        bool ok = norm2(sm.x[i] - ex, sm.y[i] - ey) < P.perception_distance;
-        double d = lane_s(Le, sm.x[i], sm.y[i]) - lane_s(Le, ex, ey);
+        bool ok = norm2(F.x[i] - ex, F.y[i] - ey) < P.perception_distance;
+        double d = lane_s(Le, F.x[i], F.y[i]) - lane_s(Le, ex, ey);
         ok = ok && (P.obs_see_behind || -2 * kVehLength < d);
         if (ok) key = fabs(d);
     }
-    sm.key[i] = key;
+    key_scratch[i] = key;
     env_sync<TPE>();
-    // stable rank among valid candidates (python sorted() on |lane_distance_to|)
+    // stable rank among the valid candidates (python sorted() on |lane_distance_to|)
     int rank = 0, n_valid = 0;
     for (int u = 1; u < V; ++u) {
-        double ku = sm.key[u];
+        double ku = key_scratch[u];
         n_valid += ku < INFINITY;
         rank += (ku < key) || (ku == key && u < i);
     }
@@ -303,10 +199,10 @@ __device__ __forceinline__ void kinematics_observe(const HwyHighwayParams& P, En
         r4 = evy;
     } else if (key < INFINITY && rank < K - 1) {
         row = rank + 1;
-        r1 = sm.x[i];
-        r2 = sm.y[i];
-        r3 = sm.v[i] * sm.c[i];
-        r4 = sm.v[i] * sm.s[i];
+        r1 = F.x[i];
+        r2 = F.y[i];
+        r3 = F.v[i] * F.c[i];
+        r4 = F.v[i] * F.s[i];
         if (!P.obs_absolute) {
             r1 -= ex;
             r2 -= ey;
@@ -334,8 +230,7 @@ __device__ __forceinline__ void kinematics_observe(const HwyHighwayParams& P, En
         o[3] = (float)r3;
         o[4] = (float)r4;
     }
-    // zero padding of missing rows
-    int filled = 1 + (n_valid < K - 1 ? n_valid : K - 1);
+    int filled = 1 + (n_valid < K - 1 ? n_valid : K - 1);  // zero padding of missing rows
     if (i < K && i >= filled) {
         float* o = obs_env + 5 * i;
         o[0] = o[1] = o[2] = o[3] = o[4] = 0.0f;
@@ -373,34 +268,152 @@ __device__ __forceinline__ void store_vehicle(const HwyHighwayState& S, size_t s
     S.meta[slot] = r.meta;  // delta never changes during a step
 }
 
-__device__ __forceinline__ int meta_lane(int m) { return (m >> HWY_META_LANE_SHIFT) & 0xff; }
-__device__ __forceinline__ int meta_target(int m) { return (m >> HWY_META_TARGET_SHIFT) & 0xff; }
-__device__ __forceinline__ int meta_kind(int m) { return (m >> HWY_META_KIND_SHIFT) & 3; }
-__device__ __forceinline__ int meta_set_lane(int m, int l) {
-    return (m & ~(0xff << HWY_META_LANE_SHIFT)) | (l << HWY_META_LANE_SHIFT);
-}
-__device__ __forceinline__ int meta_set_target(int m, int l) {
-    return (m & ~(0xff << HWY_META_TARGET_SHIFT)) | (l << HWY_META_TARGET_SHIFT);
+// Stage one vehicle into frame F (plain stores) and clear the words of F that build_frame fills
+// with atomics.  Callers put a barrier between publish() and build_frame().
+template <int TPE>
+__device__ __forceinline__ void publish(const HwyHighwayParams& P, Frame<TPE>& F, int i, bool active,
+                                        const VehicleRegs& r) {
+    constexpr int NW = TPE / 32;
+    if (active) {
+        double sn, cs;
+        sincos(r.heading, &sn, &cs);
+        F.x[i] = r.x;
+        F.y[i] = r.y;
+        F.c[i] = cs;
+        F.s[i] = sn;
+        F.v[i] = r.speed;
+        // getattr(ego_vehicle, "target_speed", 0): a plain Vehicle has none (behavior.py:172)
+        F.ts[i] = meta_kind(r.meta) == HWY_KIND_VEHICLE ? 0.0 : r.target_speed;
+        F.ls[i] = lane_s(P.lanes[0], r.x, r.y);
+        F.lane[i] = (unsigned char)meta_lane(r.meta);
+        F.tgt[i] = (unsigned char)meta_target(r.meta);
+    }
+    if (i < HWY_MAX_LANES * NW) (&F.smask[0][0])[i] = 0;
+    if (i == 0) F.slow = 0;
 }
 
+// Collision test of the pair a < b on the staged positions (vehicle/objects.py:92-138):
+// handle_collisions' gate is applied by the caller, _is_colliding here.
 template <int TPE>
-__device__ __forceinline__ void publish(EnvShared<TPE>& sm, int i, const VehicleRegs& r) {
-    double sn, cs;
-    sincos(r.heading, &sn, &cs);
-    sm.x[i] = r.x;
-    sm.y[i] = r.y;
-    sm.c[i] = cs;
-    sm.s[i] = sn;
-    sm.v[i] = r.speed;
-    // getattr(ego_vehicle, "target_speed", 0): a plain Vehicle has none (behavior.py:172)
-    sm.ts[i] = meta_kind(r.meta) == HWY_KIND_VEHICLE ? 0.0 : r.target_speed;
-    sm.lane[i] = (unsigned char)meta_lane(r.meta);
-    sm.tgt[i] = (unsigned char)meta_target(r.meta);
+__device__ __forceinline__ bool pair_precheck(const Frame<TPE>& F, int a, int b, double dt) {
+    const double diag = sqrt(kVehLength * kVehLength + kVehWidth * kVehWidth);
+    double dist = norm2(F.x[b] - F.x[a], F.y[b] - F.y[a]);
+    return !(dist > (diag + diag) / 2 + F.v[a] * dt);
+}
+template <int TPE>
+__device__ __noinline__ void pair_sat(const Frame<TPE>& F, int a, int b, double dt, bool& inter,
+                                      bool& will, double& trx, double& try_) {
+    double pa[5][2], pb[5][2];
+    polygon(F.x[a], F.y[a], F.c[a], F.s[a], pa);
+    polygon(F.x[b], F.y[b], F.c[b], F.s[b], pb);
+    polygons_intersecting(pa, pb, F.v[a] * F.c[a] * dt, F.v[a] * F.s[a] * dt, F.v[b] * F.c[b] * dt,
+                          F.v[b] * F.s[b] * dt, inter, will, trx, try_);
 }
 
+// After a barrier that follows publish(): ranks, rank-ordered membership masks, lane / target
+// masks (warp ballots) and the first pass of the collision sweep of Road.step
+// (road/road.py:477-481).  All threads of the env call this convergently.
 template <int TPE>
-__device__ __forceinline__ void set_bit(u64 (&m)[(TPE + 63) / 64], int i) {
-    atomicOr(&m[i >> 6], 1ull << (i & 63));
+__device__ __forceinline__ void build_frame(const HwyHighwayParams& P, EnvShared<TPE>& sm, Frame<TPE>& F,
+                                            int i, bool active, bool aligned, const VehicleRegs& r,
+                                            double dt, bool do_sweep) {
+    const int V = P.n_vehicles;
+    const int wie = i >> 5;  // warp within the env
+    const int lane = meta_lane(r.meta), tgt = meta_target(r.meta);
+    // -- rank along the road (s, slot) and tie detection
+    const double si = active ? F.ls[i] : 0.0;
+    int rank = 0;
+    bool tie = false;
+    for (int u = 0; u < V; ++u) {
+        double su = F.ls[u];
+        rank += (su < si) || (su == si && u < i);
+        tie = tie || (su == si && u != i);
+    }
+    if (active) {
+        F.perm[rank] = (unsigned char)i;
+        F.rank[i] = (unsigned char)rank;
+        if (tie || !aligned) F.slow = 1;
+        for (int l = 0; l < P.lanes_count; ++l) {
+            double s_l, lat_l;
+            lane_local(P.lanes[l], r.x, r.y, s_l, lat_l);
+            if (lane_on(P.lanes[l], s_l, lat_l, 1.0)) atomicOr(&F.smask[l][rank >> 5], 1u << (rank & 31));
+        }
+    }
+    // -- slot-ordered masks by ballot
+    const bool is_idm = meta_kind(r.meta) == HWY_KIND_IDM;
+    for (int l = 0; l < P.lanes_count; ++l) {
+        uint32_t b_lane = __ballot_sync(0xffffffffu, active && lane == l);
+        uint32_t b_tgt = __ballot_sync(0xffffffffu, active && tgt == l);
+        if ((i & 31) == 0) {
+            F.lane_is[l][wie] = b_lane;
+            F.tm[l][wie] = b_tgt;
+        }
+    }
+    // superset of the vehicles whose MOBIL decision may fire in the coming act (the crashed
+    // flag may still be stale here; crashed vehicles never fire, so this only over-approximates)
+    uint32_t b_fired = __ballot_sync(0xffffffffu, active && is_idm && lane == tgt && P.lane_change_delay < r.timer);
+    if ((i & 31) == 0) F.fired[wie] = b_fired;
+
+    // -- collision sweep, pass 1: every gated pair once.  A pair with exactly one
+    // check_collisions side is taken by the other side's thread (so the controlled vehicle's
+    // pairs are spread over the block); pairs of two checking vehicles are dealt round-robin.
+    if (active && do_sweep) {
+        const bool cc_i = test_bit(sm.cc, i);
+        auto do_pair = [&](int a, int b) {
+            if (!pair_precheck(F, a, b, dt)) return;
+            bool inter, will;
+            double trx, try_;
+            pair_sat(F, a, b, dt, inter, will, trx, try_);
+            if (will) {
+                atomicMax(&sm.last_will[a], b);
+                atomicMax(&sm.last_will[b], a);
+            }
+            if (inter) sm.crash_hit[a] = sm.crash_hit[b] = 1;
+        };
+        if (cc_i) {
+            for (int k = 1; 2 * k <= V; ++k) {
+                int j = i + k;
+                if (j >= V) j -= V;
+                if (!test_bit(sm.cc, j)) continue;
+                if (2 * k == V && i > j) continue;
+                do_pair(i < j ? i : j, i < j ? j : i);
+            }
+        } else {
+#pragma unroll
+            for (int w = 0; w < TPE / 32; ++w) {
+                uint32_t m = sm.cc[w];
+                while (m) {
+                    int j = w * 32 + __ffs(m) - 1;
+                    m &= m - 1;
+                    do_pair(i < j ? i : j, i < j ? j : i);
+                }
+            }
+        }
+    }
+}
+
+// Collision sweep, pass 2 (own slot): `crashed` is an OR over the intersecting partners, the
+// impact is the one of the LAST writer in the reference's (i < j) double loop = the largest
+// partner index with will_intersect (vehicle/objects.py:103-116).  SAT is recomputed for that
+// one pair (deterministic, rare).
+template <int TPE>
+__device__ __forceinline__ void apply_collisions(EnvShared<TPE>& sm, const Frame<TPE>& F, int i,
+                                                 VehicleRegs& r, double dt) {
+    if (sm.crash_hit[i]) {
+        r.meta |= HWY_META_CRASHED;
+        sm.crash_hit[i] = 0;
+    }
+    int j = sm.last_will[i];
+    if (j >= 0) {
+        int a = i < j ? i : j, b = i < j ? j : i;
+        bool inter, will;
+        double trx, try_;
+        pair_sat(F, a, b, dt, inter, will, trx, try_);
+        r.imp_x = i == a ? trx / 2 : -trx / 2;
+        r.imp_y = i == a ? try_ / 2 : -try_ / 2;
+        r.meta |= HWY_META_HAS_IMPACT;
+        sm.last_will[i] = -1;
+    }
 }
 
 // ------------------------------------------------------------------ the step kernel
@@ -412,38 +425,50 @@ highway_step_kernel(const HwyHighwayParams P, const HwyHighwayState S,
                     uint8_t* __restrict__ terminated, uint8_t* __restrict__ truncated,
                     double* __restrict__ info_speed, uint8_t* __restrict__ info_crashed) {
     constexpr int EPB = TPE == 32 ? 4 : 1;  // envs per block (a warp per env when TPE == 32)
-    constexpr int NW = (TPE + 63) / 64;
+    constexpr int NW = TPE / 32;
     __shared__ EnvShared<TPE> smem[EPB];
     const int sub = threadIdx.x / TPE;
     const int i = threadIdx.x % TPE;
     const int env = blockIdx.x * EPB + sub;
-    // Whole blocks (TPE >= 64: EPB envs share __syncthreads) must stay together: out-of-range
-    // envs clamp to the last env and skip their stores.
-    const bool env_ok = env < S.n_envs;
+    const bool env_ok = env < S.n_envs;  // TPE == 32 only: surplus warps mirror the last env
     const int e = env_ok ? env : S.n_envs - 1;
     EnvShared<TPE>& sm = smem[sub];
     const int V = P.n_vehicles;
     const bool active = i < V;
     const size_t slot = (size_t)e * S.vp + (active ? i : 0);
+    const bool aligned = lanes_aligned(P);
 
     VehicleRegs r;
     load_vehicle(S, slot, r);
     const int kind = meta_kind(r.meta);
     int speed_index = (i == 0) ? S.speed_index[e] : 0;
     double act_steer = 0.0, act_accel = 0.0;
-
-    if (active) {
-        sm.flags[i] = (unsigned char)(((r.meta & HWY_META_CHECK_COLLISIONS) ? 1 : 0) |
-                                      (kind != HWY_KIND_VEHICLE ? 2 : 0));
-        publish(sm, i, r);
-    }
-    env_sync<TPE>();
-
     const int frames = P.simulation_frequency / P.policy_frequency;
     const double dt = 1.0 / P.simulation_frequency;
-    const double diag = sqrt(kVehLength * kVehLength + kVehWidth * kVehWidth);
+
+    // ---- prologue: static masks, first frame
+    {
+        uint32_t b_cc = __ballot_sync(0xffffffffu, active && (r.meta & HWY_META_CHECK_COLLISIONS));
+        uint32_t b_ctrl = __ballot_sync(0xffffffffu, active && kind != HWY_KIND_VEHICLE);
+        if ((i & 31) == 0) {
+            sm.cc[i >> 5] = b_cc;
+            sm.ctrl[i >> 5] = b_ctrl;
+            sm.mid[i >> 5] = sm.changed[i >> 5] = sm.aborted[i >> 5] = 0;
+        }
+        sm.last_will[i] = -1;
+        sm.crash_hit[i] = 0;
+        publish(P, sm.f[0], i, active, r);
+        env_sync<TPE>();
+        // masks only: the collision sweep of the stored state ran at the end of the substep
+        // that produced it (previous launch).
+        build_frame(P, sm, sm.f[0], i, active, aligned, r, dt, false);
+        env_sync<TPE>();
+    }
+    int p = 0;
 
     for (int frame = 0; frame < frames; ++frame) {
+        Frame<TPE>& F = sm.f[p];
+        Frame<TPE>& G = sm.f[p ^ 1];
         // ---- action_type.act(action) on the first frame (abstract.py:294-304)
         if (frame == 0) {
             if (i == 0) {
@@ -458,13 +483,16 @@ highway_step_kernel(const HwyHighwayParams P, const HwyHighwayState S,
                         idx = max(0, min(idx, P.n_target_speeds - 1));
                         speed_index = idx;
                         r.target_speed = P.target_speeds[idx];
-                        sm.ts[0] = r.target_speed;
+                        F.ts[0] = r.target_speed;
                     } else if (a == 0 || a == 2) {
-                        int id = meta_target(r.meta) + (a == 2 ? 1 : -1);
+                        int old = meta_target(r.meta);
+                        int id = old + (a == 2 ? 1 : -1);
                         id = max(0, min(id, P.lanes_count - 1));
                         if (lane_reachable(P.lanes[id], r.x, r.y)) {
                             r.meta = meta_set_target(r.meta, id);
-                            sm.tgt[0] = (unsigned char)id;
+                            F.tgt[0] = (unsigned char)id;
+                            F.tm[old][0] &= ~1u;
+                            F.tm[id][0] |= 1u;
                         }
                     }
                 } else {
@@ -495,88 +523,104 @@ highway_step_kernel(const HwyHighwayParams P, const HwyHighwayState S,
         const bool idm_active = active && kind == HWY_KIND_IDM && !crashed;  // behavior.py:102-103
         int tgt1 = tgt0;
         bool is_mid = false;
-        double acc = 0.0;
-        if (i < NW) {
-            sm.mid[i] = 0;
-            sm.changed[i] = 0;
-            sm.aborted[i] = 0;
-        }
-        if (active) {
-#pragma unroll
-            for (int w = 0; w < NW; ++w) sm.geo[i][w] = 0;
-        }
-        env_sync<TPE>();
+        double acc = 0.0, free_i = 0.0;
         if (idm_active) {
+            free_i = idm_free_term(P, r.speed, r.target_speed, P.lanes[lane].speed_limit, r.delta);
             int f_own, r_own;
-            neighbours(sm, P.lanes[lane], V, i, f_own, r_own);
-            acc = idm_acceleration(P, sm, r.delta, i, f_own);  // behavior.py:115-120
+            neighbours(P, F, V, lane, i, f_own, r_own);
+            acc = free_i;  // behavior.py:115-120
+            if (f_own >= 0) acc -= idm_gap_term(P, F, aligned, i, f_own);
             if (lane != tgt0) {
-                // change_lane_policy, ongoing change (behavior.py:229-244): geometric part of the
-                // abort scan, 0 < d < d*; the target-lane conditions are resolved in order below.
+                // change_lane_policy, ongoing change (behavior.py:229-244).  Only a controlled
+                // vehicle v that is not on our target lane T and whose target is T when we act
+                // can abort us: candidates = (target is T now) or (may switch to T this act).
                 is_mid = true;
-                const HwyStraightLane& L = P.lanes[lane];
-                double s_i = lane_s(L, r.x, r.y);
-                u64 g[NW];
+                uint32_t g[NW];
 #pragma unroll
-                for (int w = 0; w < NW; ++w) g[w] = 0;
-                for (int v = 0; v < V; ++v) {
-                    if (v == i || !(sm.flags[v] & 2)) continue;
-                    double d = lane_s(L, sm.x[v], sm.y[v]) - s_i;
-                    double d_star = desired_gap(P, sm, i, v);
-                    if (0 < d && d < d_star) g[v >> 6] |= 1ull << (v & 63);
+                for (int w = 0; w < NW; ++w) {
+                    uint32_t may = F.tm[tgt0][w];
+                    uint32_t adj = (tgt0 > 0 ? F.lane_is[tgt0 - 1][w] : 0u) |
+                                   (tgt0 < P.lanes_count - 1 ? F.lane_is[tgt0 + 1][w] : 0u);
+                    may |= F.fired[w] & adj;
+                    uint32_t cand = may & sm.ctrl[w] & ~F.lane_is[tgt0][w];
+                    if (w == (i >> 5)) cand &= ~(1u << (i & 31));
+                    g[w] = 0;
+                    while (cand) {
+                        int b = __ffs(cand) - 1;
+                        cand &= cand - 1;
+                        int v = w * 32 + b;
+                        double d = lane_distance(P, F, aligned, i, v);
+                        double d_star = desired_gap(P, F, i, v);
+                        if (0 < d && d < d_star) g[w] |= 1u << b;
+                    }
+                    sm.geo[i][w] = g[w];
                 }
-#pragma unroll
-                for (int w = 0; w < NW; ++w) sm.geo[i][w] = g[w];
-                set_bit<TPE>(sm.mid, i);
+                atomicOr(&sm.mid[i >> 5], 1u << (i & 31));
             } else if (P.lane_change_delay < r.timer) {  // utils.do_every (utils.py:27-28)
                 r.timer = 0.0;
-                // side_lanes (road/road.py:200-211): id-1 then id+1; no break => last wins
+                // side_lanes (road/road.py:200-211): id-1 then id+1; no break => last wins.
+                // mobil() (behavior.py:265-324), route None => acceleration-gain branch.
                 for (int k = 0; k < 2; ++k) {
                     int cand = k == 0 ? lane - 1 : lane + 1;
                     if (cand < 0 || cand > P.lanes_count - 1) continue;
                     if (!lane_reachable(P.lanes[cand], r.x, r.y)) continue;
                     if (fabs(r.speed) < 1) continue;
-                    if (mobil(P, sm, V, i, r.delta, cand, f_own, r_own)) tgt1 = cand;
+                    int new_preceding, new_following;
+                    neighbours(P, F, V, cand, i, new_preceding, new_following);
+                    double new_following_pred_a = idm_acceleration_of(P, F, aligned, r.delta, new_following, i);
+                    if (new_following_pred_a < -P.lane_change_max_braking_imposed) continue;
+                    double self_pred_a = free_i;
+                    if (new_preceding >= 0) self_pred_a -= idm_gap_term(P, F, aligned, i, new_preceding);
+                    double self_a = acc;  // acceleration(self, old_preceding)
+                    double jerk = self_pred_a - self_a;
+                    if (P.politeness != 0.0) {
+                        double new_following_a =
+                            idm_acceleration_of(P, F, aligned, r.delta, new_following, new_preceding);
+                        double old_following_a = idm_acceleration_of(P, F, aligned, r.delta, r_own, i);
+                        double old_following_pred_a =
+                            idm_acceleration_of(P, F, aligned, r.delta, r_own, f_own);
+                        jerk = self_pred_a - self_a +
+                               P.politeness * (new_following_pred_a - new_following_a +
+                                               old_following_pred_a - old_following_a);
+                    }
+                    if (jerk < P.lane_change_min_acc_gain) continue;
+                    tgt1 = cand;
                 }
-                if (tgt1 != tgt0) set_bit<TPE>(sm.changed, i);
+                if (tgt1 != tgt0) atomicOr(&sm.changed[i >> 5], 1u << (i & 31));
             }
         }
         if (active) sm.tgt1[i] = (unsigned char)tgt1;
         env_sync<TPE>();
 
         // ---- ordered fix-up of the Gauss-Seidel abort scan (one thread per env).  Vehicles act
-        // in list order; vehicle i sees the NEW target of every j < i and the OLD one of j > i.
-        if (i == 0 && (sm.mid[0] | (NW > 1 ? sm.mid[NW - 1] : 0ull))) {
-            for (int l = 0; l < P.lanes_count; ++l)
+        // in list order: vehicle i sees the NEW target of every j < i and the OLD one of j > i.
+        if (i == 0) {
+            uint32_t any_mid = 0;
 #pragma unroll
-                for (int w = 0; w < NW; ++w) sm.tm[l][w] = sm.lane_ne[l][w] = 0;
-            for (int v = 0; v < V; ++v) {
-                u64 bit = 1ull << (v & 63);
-                sm.tm[sm.tgt[v]][v >> 6] |= bit;
-                for (int l = 0; l < P.lanes_count; ++l)
-                    if (sm.lane[v] != l) sm.lane_ne[l][v >> 6] |= bit;
-            }
+            for (int w = 0; w < NW; ++w) any_mid |= sm.mid[w];
+            if (any_mid) {
 #pragma unroll
-            for (int w = 0; w < NW; ++w) {
-                u64 ev = sm.mid[w] | sm.changed[w];
-                while (ev) {
-                    int b = __ffsll((long long)ev) - 1;
-                    ev &= ev - 1;
-                    int v = w * 64 + b;
-                    u64 bit = 1ull << b;
-                    int t0 = sm.tgt[v];
-                    if (sm.changed[w] & bit) {  // MOBIL decision becomes visible to later vehicles
-                        sm.tm[t0][w] &= ~bit;
-                        sm.tm[sm.tgt1[v]][w] |= bit;
-                    } else {
-                        u64 hit = 0;
+                for (int w = 0; w < NW; ++w) {
+                    uint32_t ev = sm.mid[w] | sm.changed[w];
+                    while (ev) {
+                        int b = __ffs(ev) - 1;
+                        ev &= ev - 1;
+                        int v = w * 32 + b;
+                        uint32_t bit = 1u << b;
+                        int t0 = F.tgt[v];
+                        if (sm.changed[w] & bit) {  // MOBIL decision becomes visible to later vehicles
+                            F.tm[t0][w] &= ~bit;
+                            F.tm[sm.tgt1[v]][w] |= bit;
+                        } else {
+                            uint32_t hit = 0;
 #pragma unroll
-                        for (int w2 = 0; w2 < NW; ++w2)
-                            hit |= sm.geo[v][w2] & sm.tm[t0][w2] & sm.lane_ne[t0][w2];
-                        if (hit) {  // behavior.py:241-243: target := current lane
-                            sm.aborted[w] |= bit;
-                            sm.tm[t0][w] &= ~bit;
-                            sm.tm[sm.lane[v]][w] |= bit;
+                            for (int w2 = 0; w2 < NW; ++w2)
+                                hit |= sm.geo[v][w2] & F.tm[t0][w2] & ~F.lane_is[t0][w2];
+                            if (hit) {  // behavior.py:241-243: target := current lane
+                                sm.aborted[w] |= bit;
+                                F.tm[t0][w] &= ~bit;
+                                F.tm[F.lane[v]][w] |= bit;
+                            }
                         }
                     }
                 }
@@ -584,16 +628,20 @@ highway_step_kernel(const HwyHighwayParams P, const HwyHighwayState S,
         }
         env_sync<TPE>();
 
-        // ---- Road.act() phase B: steering + target-lane IDM with the final target
+        // ---- Road.act() phase B (steering + target-lane IDM with the final target), then
+        // Road.step(dt): Vehicle.step (kinematics.py:130-177; IDMVehicle.step behavior.py:139-148).
+        // The new state goes to the other frame, so no barrier is needed before staging it.
         if (active) {
             int tgt = tgt1;
-            if (is_mid && (sm.aborted[i >> 6] >> (i & 63)) & 1) tgt = lane;
+            if (is_mid && test_bit(sm.aborted, i)) tgt = lane;
             if (idm_active) {
                 double steering = steering_control(P.lanes[tgt], r.x, r.y, r.heading, r.speed);
                 if (lane != tgt) {  // behavior.py:121-131
                     int f_t, r_t;
-                    neighbours(sm, P.lanes[tgt], V, i, f_t, r_t);
-                    acc = fmin(acc, idm_acceleration(P, sm, r.delta, i, f_t));
+                    neighbours(P, F, V, tgt, i, f_t, r_t);
+                    double tacc = free_i;
+                    if (f_t >= 0) tacc -= idm_gap_term(P, F, aligned, i, f_t);
+                    acc = fmin(acc, tacc);
                 }
                 act_steer = steering;
                 act_accel = clipd(acc, -P.acc_max, P.acc_max);
@@ -603,11 +651,7 @@ highway_step_kernel(const HwyHighwayParams P, const HwyHighwayState S,
                 act_accel = kKpA * (r.target_speed - r.speed);  // speed_control :189-198
             }
             r.meta = meta_set_target(r.meta, tgt);
-        }
 
-        // ---- Road.step(dt): Vehicle.step (kinematics.py:130-177; IDMVehicle.step behavior.py:139-148)
-        env_sync<TPE>();  // everyone is done reading the pre-step staging
-        if (active) {
             if (kind == HWY_KIND_IDM) r.timer += dt;
             if (crashed) {  // clip_actions :155-168
                 act_steer = 0.0;
@@ -633,52 +677,31 @@ highway_step_kernel(const HwyHighwayParams P, const HwyHighwayState S,
             int nl = closest_lane(P, r.x, r.y, r.heading);  // on_state_update :170-177
             r.meta = meta_set_lane(r.meta, nl);
             if (kind == HWY_KIND_VEHICLE) r.meta = meta_set_target(r.meta, nl);  // schema: mirrors lane
-            publish(sm, i, r);
         }
+        publish(P, G, i, active, r);
         env_sync<TPE>();
-
-        // ---- Road.step collision sweep (road/road.py:477-481; objects.py:92-138).  Thread i
-        // visits its partners in ascending order, so the surviving impact is the one written by
-        // the largest partner index, exactly as the reference's (i < j) double loop leaves it.
-        if (active) {
-            const bool cc_i = sm.flags[i] & 1;
-            for (int j = 0; j < V; ++j) {
-                if (j == i || !(cc_i || (sm.flags[j] & 1))) continue;
-                int a = i < j ? i : j, b = i < j ? j : i;
-                double dist = norm2(sm.x[b] - sm.x[a], sm.y[b] - sm.y[a]);
-                if (dist > (diag + diag) / 2 + sm.v[a] * dt) continue;
-                double pa[5][2], pb[5][2];
-                polygon(sm, a, pa);
-                polygon(sm, b, pb);
-                bool inter, will;
-                double trx, try_;
-                polygons_intersecting(pa, pb, sm.v[a] * sm.c[a] * dt, sm.v[a] * sm.s[a] * dt,
-                                      sm.v[b] * sm.c[b] * dt, sm.v[b] * sm.s[b] * dt, inter, will,
-                                      trx, try_);
-                if (will) {
-                    r.imp_x = i == a ? trx / 2 : -trx / 2;
-                    r.imp_y = i == a ? try_ / 2 : -try_ / 2;
-                    r.meta |= HWY_META_HAS_IMPACT;
-                }
-                if (inter) r.meta |= HWY_META_CRASHED;
-            }
-        }
-        // no barrier needed here: the next frame's first shared writes (mid/geo/tgt1) touch
-        // arrays the sweep does not read, and a barrier follows them.
+        if (i < NW) sm.mid[i] = sm.changed[i] = sm.aborted[i] = 0;  // all readers are past phase B
+        // ---- masks of the new frame + Road.step collision sweep (pass 1), then pass 2
+        build_frame(P, sm, G, i, active, aligned, r, dt, true);
+        env_sync<TPE>();
+        if (active) apply_collisions(sm, G, i, r, dt);
+        p ^= 1;
     }
 
     // ---- epilogue: state back to HBM, observation, reward, termination
+    const Frame<TPE>& F = sm.f[p];
     if (active && env_ok) store_vehicle(S, slot, r);
-    env_sync<TPE>();
     float* obs_env = obs + (size_t)e * P.obs_vehicles_count * 5;
-    if (env_ok) kinematics_observe(P, sm, i, obs_env);
-    else env_sync<TPE>();
+    if (env_ok)
+        kinematics_observe(P, F, sm.key, i, obs_env);
+    else
+        env_sync<TPE>();
     if (i == 0 && env_ok) {
         // envs/highway_env.py:100-151
         const int lane = meta_lane(r.meta);
         const HwyStraightLane& L = P.lanes[lane];
         int rl = kind == HWY_KIND_VEHICLE ? lane : meta_target(r.meta);
-        double forward_speed = r.speed * sm.c[0];
+        double forward_speed = r.speed * F.c[0];
         double scaled_speed = lmap(forward_speed, P.reward_speed_lo, P.reward_speed_hi, 0.0, 1.0);
         double es, elat;
         lane_local(L, r.x, r.y, es, elat);
@@ -706,25 +729,31 @@ highway_step_kernel(const HwyHighwayParams P, const HwyHighwayState S,
 
 // ------------------------------------------------------------------ observe-only kernel
 template <int TPE>
+struct ObsShared {
+    Frame<TPE> f;
+    double key[TPE];
+};
+
+template <int TPE>
 __global__ void __launch_bounds__(TPE == 32 ? 128 : TPE)
 highway_observe_kernel(const HwyHighwayParams P, const HwyHighwayState S,
                        const uint8_t* __restrict__ mask_a, const uint8_t* __restrict__ mask_b,
                        int use_mask, float* __restrict__ obs) {
     constexpr int EPB = TPE == 32 ? 4 : 1;
-    __shared__ EnvShared<TPE> smem[EPB];
+    __shared__ ObsShared<TPE> smem[EPB];
     const int sub = threadIdx.x / TPE, i = threadIdx.x % TPE;
     const int env = blockIdx.x * EPB + sub;
     const bool env_ok = env < S.n_envs;
     const int e = env_ok ? env : S.n_envs - 1;
-    EnvShared<TPE>& sm = smem[sub];
+    ObsShared<TPE>& sm = smem[sub];
     const bool active = i < P.n_vehicles;
     VehicleRegs r;
     load_vehicle(S, (size_t)e * S.vp + (active ? i : 0), r);
-    if (active) publish(sm, i, r);
+    publish(P, sm.f, i, active, r);
     env_sync<TPE>();
     const bool wanted = env_ok && (!use_mask || (mask_a && mask_a[e]) || (mask_b && mask_b[e]));
     if (wanted)
-        kinematics_observe(P, sm, i, obs + (size_t)e * P.obs_vehicles_count * 5);
+        kinematics_observe(P, sm.f, sm.key, i, obs + (size_t)e * P.obs_vehicles_count * 5);
     else
         env_sync<TPE>();
 }
@@ -752,9 +781,9 @@ highway_reset_kernel(const HwyHighwayParams P, const HwyHighwayState S,
     g.u32 = (uint32_t)w4;
 
     double x_max = 0.0;  // running max of the longitudinal coordinates of spawned vehicles
-    bool lanes_aligned = true;  // all lanes share origin-x and direction => s is lane independent
+    bool aligned = true;  // all lanes share origin-x and direction => s is lane independent
     for (int l = 1; l < P.lanes_count; ++l)
-        lanes_aligned = lanes_aligned && P.lanes[l].start_x == P.lanes[0].start_x &&
+        aligned = aligned && P.lanes[l].start_x == P.lanes[0].start_x &&
                         P.lanes[l].dir_x == P.lanes[0].dir_x && P.lanes[l].dir_y == 0.0 &&
                         P.lanes[0].dir_y == 0.0;
     double2* pos = reinterpret_cast<double2*>(S.pos);
@@ -774,7 +803,7 @@ highway_reset_kernel(const HwyHighwayParams P, const HwyHighwayState S,
         double offset = spacing * default_spacing * P.spawn_exp;
         double x0;
         if (v > 0) {
-            if (lanes_aligned) {
+            if (aligned) {
                 x0 = x_max;
             } else {  // np.max over lane.local_coordinates(v.position)[0] on the chosen lane
                 x0 = lane_s(L, pos[base].x, pos[base].y);

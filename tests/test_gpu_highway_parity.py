@@ -206,3 +206,30 @@ def test_abi_errors_are_loud():
     env = hb.make("highway-fast-v0", num_envs=2)
     with pytest.raises(RuntimeError):
         env.step([1, 1])  # before reset
+
+
+def test_longitudinal_ties_take_the_exact_path():
+    """Vehicles sharing a longitudinal coordinate (the `<=` / `>` tie rules of
+    Road.neighbour_vehicles, road/road.py:539-544) route the env to the linear scans."""
+    name, n = "highway_fast_v50", 64
+    g, cfg, oc, ob = _oracle_pair(name, n, 7000)
+    env = make_env(cfg, n, autoreset_mode="Disabled")
+    env.reset(seed=7000)
+    ob.reset()
+    rng = np.random.default_rng(3)
+    for t in range(6):
+        # force ties: copy the x of vehicle k onto vehicle k+1 for a few random k per env
+        for e_ in range(n):
+            for k in rng.integers(1, 49, size=3):
+                ob.a["x"][e_, k + 1] = ob.a["x"][e_, k]
+        sd = {k: ob.a[k].copy() for k in ob.a}
+        env.load_state_dict(sd)
+        act = rng.integers(0, 5, size=n).astype(np.int32)
+        o_obs, o_rew, o_term, o_trunc = ob.step(act)
+        obs, rew, term, trunc, _ = env.step(act)
+        sd = env.state_dict()
+        for k in ("x", "y", "heading", "speed", "timer"):
+            assert np.max(np.abs(sd[k] - ob.a[k])) <= 1e-7, (t, k)
+        for k in ("lane", "target_lane", "crashed", "has_impact"):
+            assert np.array_equal(sd[k].astype(np.int32), ob.a[k].astype(np.int32)), (t, k)
+        assert np.array_equal(term.cpu().numpy(), o_term.astype(bool))
