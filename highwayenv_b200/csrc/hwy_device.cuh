@@ -59,18 +59,18 @@ __device__ __forceinline__ bool lanes_aligned(const HwyHighwayParams& P) {
 }
 
 // vehicle/controller.py:145-187 steering_control on a StraightLane
-__device__ __forceinline__ double steering_control(const HwyStraightLane& L, double x, double y,
-                                                   double heading, double speed) {
+__device__ __noinline__ double steering_control(const HwyStraightLane L, double x, double y,
+                                                double heading, double speed) {
     double lc_s, lc_lat;
     lane_local(L, x, y, lc_s, lc_lat);
     double lane_future_heading = L.heading;  // StraightLane.heading_at
     double lateral_speed_command = -kKpLateral * lc_lat;
-    double heading_command = asin(clipd(lateral_speed_command / not_zero(speed), -1.0, 1.0));
+    double heading_command = m_asin(clipd(lateral_speed_command / not_zero(speed), -1.0, 1.0));
     double heading_ref = lane_future_heading + clipd(heading_command, -kPi / 4, kPi / 4);
     double heading_rate_command = kKpHeading * wrap_to_pi(heading_ref - heading);
     double slip_angle =
-        asin(clipd(kVehLength / 2 / not_zero(speed) * heading_rate_command, -1.0, 1.0));
-    double steering_angle = atan(2 * tan(slip_angle));
+        m_asin(clipd(kVehLength / 2 / not_zero(speed) * heading_rate_command, -1.0, 1.0));
+    double steering_angle = m_atan(2 * m_tan(slip_angle));
     return clipd(steering_angle, -kMaxSteer, kMaxSteer);
 }
 
@@ -82,83 +82,105 @@ __device__ __forceinline__ int speed_to_index(const HwyHighwayParams& P, double 
 }
 
 // ------------------------------------------------------------------ collision (SAT)
-// vehicle/objects.py:169-181 polygon()
-__device__ __forceinline__ void polygon(double x, double y, double c, double s, double (&p)[5][2]) {
+// A vehicle rectangle as RoadObject.polygon() builds it (vehicle/objects.py:169-181): the 4
+// corners (rotation @ points).T + position; the closing 5th point repeats the first and adds
+// nothing to projections (same value), so it is not materialised.
+struct Quad {
+    double x[4], y[4];
+};
+__device__ __forceinline__ Quad make_polygon(double px, double py, double c, double s) {
     const double hl = kVehLength / 2, hw = kVehWidth / 2;
     const double lx[4] = {-hl, -hl, +hl, +hl};
     const double ly[4] = {-hw, +hw, +hw, -hw};
+    Quad q;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        p[k][0] = (c * lx[k] + (-s) * ly[k]) + x;
-        p[k][1] = (s * lx[k] + c * ly[k]) + y;
+        q.x[k] = (c * lx[k] + (-s) * ly[k]) + px;
+        q.y[k] = (s * lx[k] + c * ly[k]) + py;
     }
-    p[4][0] = p[0][0];
-    p[4][1] = p[0][1];
+    return q;
 }
-
-__device__ __forceinline__ void project_polygon(const double (&p)[5][2], double ax, double ay,
-                                                double& mn, double& mx) {
-    mn = mx = dot2(p[0][0], p[0][1], ax, ay);
+// utils.py:177-185 project_polygon
+__device__ __forceinline__ void project_polygon(const Quad& p, double ax, double ay, double& mn,
+                                                double& mx) {
+    mn = mx = dot2(p.x[0], p.y[0], ax, ay);
 #pragma unroll
-    for (int k = 1; k < 5; ++k) {
-        double pr = dot2(p[k][0], p[k][1], ax, ay);
+    for (int k = 1; k < 4; ++k) {
+        double pr = dot2(p.x[k], p.y[k], ax, ay);
         if (pr < mn) mn = pr;
         if (pr > mx) mx = pr;
     }
 }
+// utils.py:188-193
 __device__ __forceinline__ double interval_distance(double min_a, double max_a, double min_b,
                                                     double max_b) {
     return min_a < min_b ? min_b - max_a : min_a - max_b;
 }
 
 // utils.py:196-241 are_polygons_intersecting: SAT over the 4+4 edge normals with the relative
-// displacement extension; returns (intersecting, will_intersect, translation).
-__device__ __noinline__ void polygons_intersecting(const double (&a)[5][2], const double (&b)[5][2],
-                                                   double dax, double day, double dbx, double dby,
-                                                   bool& intersecting, bool& will_intersect,
-                                                   double& trx, double& try_) {
-    intersecting = true;
-    will_intersect = true;
-    double min_distance = INFINITY;
-    double tax = 0, tay = 0;
-    double cax = (((a[0][0] + a[1][0]) + a[2][0]) + a[3][0]) / 4.0;
-    double cay = (((a[0][1] + a[1][1]) + a[2][1]) + a[3][1]) / 4.0;
-    double cbx = (((b[0][0] + b[1][0]) + b[2][0]) + b[3][0]) / 4.0;
-    double cby = (((b[0][1] + b[1][1]) + b[2][1]) + b[3][1]) / 4.0;
-    double dcx = cax - cbx, dcy = cay - cby;
-    for (int poly = 0; poly < 2; ++poly) {
-        for (int e = 0; e < 4; ++e) {
-            double p1x = poly == 0 ? a[e][0] : b[e][0], p1y = poly == 0 ? a[e][1] : b[e][1];
-            double p2x = poly == 0 ? a[e + 1][0] : b[e + 1][0];
-            double p2y = poly == 0 ? a[e + 1][1] : b[e + 1][1];
-            double nx = -p2y + p1y, ny = p2x - p1x;
-            double nn = norm2(nx, ny);
-            nx /= nn;
-            ny /= nn;
-            double min_a, max_a, min_b, max_b;
-            project_polygon(a, nx, ny, min_a, max_a);
-            project_polygon(b, nx, ny, min_b, max_b);
-            if (interval_distance(min_a, max_a, min_b, max_b) > 0) intersecting = false;
-            double vp = dot2(nx, ny, dax - dbx, day - dby);
-            if (vp < 0)
-                min_a += vp;
-            else
-                max_a += vp;
-            double distance = interval_distance(min_a, max_a, min_b, max_b);
-            if (distance > 0) will_intersect = false;
-            if (!intersecting && !will_intersect) break;  // leaves the inner loop only
-            if (fabs(distance) < min_distance) {
-                min_distance = fabs(distance);
-                if (dot2(dcx, dcy, nx, ny) > 0) {
-                    tax = nx;
-                    tay = ny;
-                } else {
-                    tax = -nx;
-                    tay = -ny;
-                }
-            }
-        }
+// displacement extension; returns (intersecting, will_intersect, translation).  One rolled
+// loop over the 8 edges: the polygon whose edges are being visited is rotated in registers so
+// the current edge is always (point 0 -> point 1); projections are order independent.
+__device__ __forceinline__ void rotate_quad(Quad& q) {
+    double tx = q.x[0], ty = q.y[0];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        q.x[k] = q.x[k + 1];
+        q.y[k] = q.y[k + 1];
     }
+    q.x[3] = tx;
+    q.y[3] = ty;
+}
+__device__ __forceinline__ void polygons_intersecting(Quad a, Quad b, double dax, double day,
+                                                      double dbx, double dby, bool& intersecting_out,
+                                                      bool& will_intersect_out, double& trx,
+                                                      double& try_) {
+    bool intersecting = true, will_intersect = true;
+    double min_distance = INFINITY, tax = 0.0, tay = 0.0;
+    // centre difference a[:-1].mean(axis=0) - b[:-1].mean(axis=0): sequential row sums / 4
+    const double dcx = (((a.x[0] + a.x[1]) + a.x[2]) + a.x[3]) / 4.0 - (((b.x[0] + b.x[1]) + b.x[2]) + b.x[3]) / 4.0;
+    const double dcy = (((a.y[0] + a.y[1]) + a.y[2]) + a.y[3]) / 4.0 - (((b.y[0] + b.y[1]) + b.y[2]) + b.y[3]) / 4.0;
+    const double rdx = dax - dbx, rdy = day - dby;
+    bool brk = false;
+#pragma unroll 1
+    for (int e = 0; e < 8; ++e) {
+        if (e == 4) brk = false;  // the `break` leaves only the inner loop (utils.py:232-233)
+        if (brk) continue;
+        const bool on_a = e < 4;
+        double p1x = on_a ? a.x[0] : b.x[0], p1y = on_a ? a.y[0] : b.y[0];
+        double p2x = on_a ? a.x[1] : b.x[1], p2y = on_a ? a.y[1] : b.y[1];
+        double nx = -p2y + p1y, ny = p2x - p1x;
+        double nn = norm2(nx, ny);
+        nx /= nn;
+        ny /= nn;
+        double min_a, max_a, min_b, max_b;
+        project_polygon(a, nx, ny, min_a, max_a);
+        project_polygon(b, nx, ny, min_b, max_b);
+        if (interval_distance(min_a, max_a, min_b, max_b) > 0) intersecting = false;
+        double vp = dot2(nx, ny, rdx, rdy);
+        if (vp < 0)
+            min_a += vp;
+        else
+            max_a += vp;
+        double distance = interval_distance(min_a, max_a, min_b, max_b);
+        if (distance > 0) will_intersect = false;
+        if (!intersecting && !will_intersect) {
+            brk = true;
+            continue;
+        }
+        if (fabs(distance) < min_distance) {
+            min_distance = fabs(distance);
+            bool pos = dot2(dcx, dcy, nx, ny) > 0;
+            tax = pos ? nx : -nx;
+            tay = pos ? ny : -ny;
+        }
+        if (on_a)
+            rotate_quad(a);
+        else
+            rotate_quad(b);
+    }
+    intersecting_out = intersecting;
+    will_intersect_out = will_intersect;
     trx = will_intersect ? min_distance * tax : 0.0;
     try_ = will_intersect ? min_distance * tay : 0.0;
 }

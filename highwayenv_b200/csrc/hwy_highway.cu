@@ -119,15 +119,26 @@ __device__ __forceinline__ void neighbours(const HwyHighwayParams& P, const Fram
 }
 
 // ------------------------------------------------------------------ IDM (vehicle/behavior.py)
+// Scalars of the IDM the out-of-line helpers need (passing the kernel-parameter struct by
+// reference to a __noinline__ function would force a per-thread local copy of it).
+struct IdmK {
+    double comfort_acc_max, distance_wanted, time_wanted, two_sqrt_ab;
+};
+__device__ __forceinline__ IdmK make_idm(const HwyHighwayParams& P) {
+    IdmK k;
+    k.comfort_acc_max = P.comfort_acc_max;
+    k.distance_wanted = P.distance_wanted;
+    k.time_wanted = P.time_wanted;
+    k.two_sqrt_ab = 2 * sqrt(-P.comfort_acc_max * P.comfort_acc_min);  // 2 * np.sqrt(ab)
+    return k;
+}
 // :192-217 desired_gap(ego, front), projected
 template <int TPE>
-__device__ __forceinline__ double desired_gap(const HwyHighwayParams& P, const Frame<TPE>& F, int ego,
-                                              int front) {
-    double ab = -P.comfort_acc_max * P.comfort_acc_min;
+__device__ __forceinline__ double desired_gap(const IdmK& K, const Frame<TPE>& F, int ego, int front) {
     double dvx = F.v[ego] * F.c[ego] - F.v[front] * F.c[front];
     double dvy = F.v[ego] * F.s[ego] - F.v[front] * F.s[front];
     double dv = dot2(dvx, dvy, F.c[ego], F.s[ego]);
-    return P.distance_wanted + F.v[ego] * P.time_wanted + F.v[ego] * dv / (2 * sqrt(ab));
+    return K.distance_wanted + F.v[ego] * K.time_wanted + F.v[ego] * dv / K.two_sqrt_ab;
 }
 // lane_distance_to on the ego's own lane (vehicle/objects.py:183-198)
 template <int TPE>
@@ -138,26 +149,31 @@ __device__ __forceinline__ double lane_distance(const HwyHighwayParams& P, const
     return lane_s(L, F.x[other], F.y[other]) - lane_s(L, F.x[ego], F.y[ego]);
 }
 // :150-190 acceleration(): free-road term with the CALLER's DELTA ...
-__device__ __forceinline__ double idm_free_term(const HwyHighwayParams& P, double speed,
-                                                double target_speed, double speed_limit, double delta) {
+__device__ __noinline__ double idm_free_term(double comfort_acc_max, double speed, double target_speed,
+                                             double speed_limit, double delta) {
     double ego_target_speed = clipd(target_speed, 0.0, speed_limit);
-    return P.comfort_acc_max * (1 - pow(fmax(speed, 0.0) / fabs(not_zero(ego_target_speed)), delta));
+    return comfort_acc_max * (1 - m_pow(fmax(speed, 0.0) / fabs(not_zero(ego_target_speed)), delta));
 }
-// ... and the interaction term COMFORT_ACC_MAX * (d* / not_zero(d))^2
+// ... and the interaction term COMFORT_ACC_MAX * (d* / not_zero(d))^2 for a given gap d
 template <int TPE>
-__device__ __forceinline__ double idm_gap_term(const HwyHighwayParams& P, const Frame<TPE>& F,
-                                               bool aligned, int ego, int front) {
-    double d = lane_distance(P, F, aligned, ego, front);
-    double q = desired_gap(P, F, ego, front) / not_zero(d);
-    return P.comfort_acc_max * (q * q);  // np.power(q, 2)
+__device__ __noinline__ double idm_gap_core(const IdmK K, const Frame<TPE>& F, int ego, int front, double d) {
+    double q = desired_gap(K, F, ego, front) / not_zero(d);
+    return K.comfort_acc_max * (q * q);  // np.power(q, 2)
+}
+template <int TPE>
+__device__ __forceinline__ double idm_gap_term(const HwyHighwayParams& P, const IdmK& K,
+                                               const Frame<TPE>& F, bool aligned, int ego, int front) {
+    return idm_gap_core(K, F, ego, front, lane_distance(P, F, aligned, ego, front));
 }
 // acceleration(ego_vehicle=ego, front_vehicle=front) for an `ego` other than the caller
 template <int TPE>
-__device__ __forceinline__ double idm_acceleration_of(const HwyHighwayParams& P, const Frame<TPE>& F,
-                                                      bool aligned, double delta, int ego, int front) {
+__device__ __forceinline__ double idm_acceleration_of(const HwyHighwayParams& P, const IdmK& K,
+                                                      const Frame<TPE>& F, bool aligned, double delta,
+                                                      int ego, int front) {
     if (ego < 0) return 0.0;
-    double acc = idm_free_term(P, F.v[ego], F.ts[ego], P.lanes[F.lane[ego]].speed_limit, delta);
-    if (front >= 0) acc -= idm_gap_term(P, F, aligned, ego, front);
+    double acc = idm_free_term(K.comfort_acc_max, F.v[ego], F.ts[ego],
+                               P.lanes[F.lane[ego]].speed_limit, delta);
+    if (front >= 0) acc -= idm_gap_term(P, K, F, aligned, ego, front);
     return acc;
 }
 
@@ -276,7 +292,7 @@ __device__ __forceinline__ void publish(const HwyHighwayParams& P, Frame<TPE>& F
     constexpr int NW = TPE / 32;
     if (active) {
         double sn, cs;
-        sincos(r.heading, &sn, &cs);
+        m_sincos(r.heading, &sn, &cs);
         F.x[i] = r.x;
         F.y[i] = r.y;
         F.c[i] = cs;
@@ -303,9 +319,8 @@ __device__ __forceinline__ bool pair_precheck(const Frame<TPE>& F, int a, int b,
 template <int TPE>
 __device__ __noinline__ void pair_sat(const Frame<TPE>& F, int a, int b, double dt, bool& inter,
                                       bool& will, double& trx, double& try_) {
-    double pa[5][2], pb[5][2];
-    polygon(F.x[a], F.y[a], F.c[a], F.s[a], pa);
-    polygon(F.x[b], F.y[b], F.c[b], F.s[b], pb);
+    Quad pa = make_polygon(F.x[a], F.y[a], F.c[a], F.s[a]);
+    Quad pb = make_polygon(F.x[b], F.y[b], F.c[b], F.s[b]);
     polygons_intersecting(pa, pb, F.v[a] * F.c[a] * dt, F.v[a] * F.s[a] * dt, F.v[b] * F.c[b] * dt,
                           F.v[b] * F.s[b] * dt, inter, will, trx, try_);
 }
@@ -370,23 +385,22 @@ __device__ __forceinline__ void build_frame(const HwyHighwayParams& P, EnvShared
             }
             if (inter) sm.crash_hit[a] = sm.crash_hit[b] = 1;
         };
-        if (cc_i) {
-            for (int k = 1; 2 * k <= V; ++k) {
-                int j = i + k;
-                if (j >= V) j -= V;
-                if (!test_bit(sm.cc, j)) continue;
-                if (2 * k == V && i > j) continue;
-                do_pair(i < j ? i : j, i < j ? j : i);
-            }
-        } else {
+        // partners = vehicles that check collisions; a pair of two checking vehicles is dealt
+        // round-robin (thread i takes j = i+k mod V, k <= V/2), a pair with one checking side is
+        // taken by the other side's thread.
 #pragma unroll
-            for (int w = 0; w < TPE / 32; ++w) {
-                uint32_t m = sm.cc[w];
-                while (m) {
-                    int j = w * 32 + __ffs(m) - 1;
-                    m &= m - 1;
-                    do_pair(i < j ? i : j, i < j ? j : i);
+        for (int w = 0; w < TPE / 32; ++w) {
+            uint32_t m = sm.cc[w];
+            if (w == (i >> 5)) m &= ~(1u << (i & 31));
+            while (m) {
+                int j = w * 32 + __ffs(m) - 1;
+                m &= m - 1;
+                if (cc_i) {
+                    int k = j - i;
+                    if (k < 0) k += V;
+                    if (2 * k > V || (2 * k == V && i > j)) continue;
                 }
+                do_pair(i < j ? i : j, i < j ? j : i);
             }
         }
     }
@@ -417,8 +431,11 @@ __device__ __forceinline__ void apply_collisions(EnvShared<TPE>& sm, const Frame
 }
 
 // ------------------------------------------------------------------ the step kernel
+#ifndef HWY_MINB64
+#define HWY_MINB64 8  // resident blocks per SM the 64-thread variant is compiled for
+#endif
 template <int TPE>
-__global__ void __launch_bounds__(TPE == 32 ? 128 : TPE)
+__global__ void __launch_bounds__(TPE == 32 ? 128 : TPE, TPE == 64 ? HWY_MINB64 : 1)
 highway_step_kernel(const HwyHighwayParams P, const HwyHighwayState S,
                     const int32_t* __restrict__ action_i, const float* __restrict__ action_f,
                     float* __restrict__ obs, double* __restrict__ reward,
@@ -446,7 +463,7 @@ highway_step_kernel(const HwyHighwayParams P, const HwyHighwayState S,
     const int frames = P.simulation_frequency / P.policy_frequency;
     const double dt = 1.0 / P.simulation_frequency;
 
-    // ---- prologue: static masks, first frame
+    // ---- static masks
     {
         uint32_t b_cc = __ballot_sync(0xffffffffu, active && (r.meta & HWY_META_CHECK_COLLISIONS));
         uint32_t b_ctrl = __ballot_sync(0xffffffffu, active && kind != HWY_KIND_VEHICLE);
@@ -457,18 +474,25 @@ highway_step_kernel(const HwyHighwayParams P, const HwyHighwayState S,
         }
         sm.last_will[i] = -1;
         sm.crash_hit[i] = 0;
-        publish(P, sm.f[0], i, active, r);
-        env_sync<TPE>();
-        // masks only: the collision sweep of the stored state ran at the end of the substep
-        // that produced it (previous launch).
-        build_frame(P, sm, sm.f[0], i, active, aligned, r, dt, false);
-        env_sync<TPE>();
     }
-    int p = 0;
+    const IdmK K = make_idm(P);
+    int p = 1;
 
-    for (int frame = 0; frame < frames; ++frame) {
+    // One iteration = stage the current state, derive its masks (+ the collision sweep of the
+    // substep that produced it), then — except after the last substep — act and integrate.
+    for (int frame = 0;; ++frame) {
+        p ^= 1;
         Frame<TPE>& F = sm.f[p];
-        Frame<TPE>& G = sm.f[p ^ 1];
+        publish(P, F, i, active, r);
+        env_sync<TPE>();
+        if (i < NW) sm.mid[i] = sm.changed[i] = sm.aborted[i] = 0;  // all readers are past phase B
+        // frame 0: masks only — the sweep of the stored state ran at the end of the substep that
+        // produced it (previous launch).  Later: Road.step's sweep (road/road.py:477-481).
+        build_frame(P, sm, F, i, active, aligned, r, dt, frame > 0);
+        env_sync<TPE>();
+        if (active && frame > 0) apply_collisions(sm, F, i, r, dt);
+        if (frame == frames) break;
+
         // ---- action_type.act(action) on the first frame (abstract.py:294-304)
         if (frame == 0) {
             if (i == 0) {
@@ -525,11 +549,11 @@ highway_step_kernel(const HwyHighwayParams P, const HwyHighwayState S,
         bool is_mid = false;
         double acc = 0.0, free_i = 0.0;
         if (idm_active) {
-            free_i = idm_free_term(P, r.speed, r.target_speed, P.lanes[lane].speed_limit, r.delta);
+            free_i = idm_free_term(K.comfort_acc_max, r.speed, r.target_speed, P.lanes[lane].speed_limit, r.delta);
             int f_own, r_own;
             neighbours(P, F, V, lane, i, f_own, r_own);
             acc = free_i;  // behavior.py:115-120
-            if (f_own >= 0) acc -= idm_gap_term(P, F, aligned, i, f_own);
+            if (f_own >= 0) acc -= idm_gap_term(P, K, F, aligned, i, f_own);
             if (lane != tgt0) {
                 // change_lane_policy, ongoing change (behavior.py:229-244).  Only a controlled
                 // vehicle v that is not on our target lane T and whose target is T when we act
@@ -550,7 +574,7 @@ highway_step_kernel(const HwyHighwayParams P, const HwyHighwayState S,
                         cand &= cand - 1;
                         int v = w * 32 + b;
                         double d = lane_distance(P, F, aligned, i, v);
-                        double d_star = desired_gap(P, F, i, v);
+                        double d_star = desired_gap(K, F, i, v);
                         if (0 < d && d < d_star) g[w] |= 1u << b;
                     }
                     sm.geo[i][w] = g[w];
@@ -567,18 +591,18 @@ highway_step_kernel(const HwyHighwayParams P, const HwyHighwayState S,
                     if (fabs(r.speed) < 1) continue;
                     int new_preceding, new_following;
                     neighbours(P, F, V, cand, i, new_preceding, new_following);
-                    double new_following_pred_a = idm_acceleration_of(P, F, aligned, r.delta, new_following, i);
+                    double new_following_pred_a = idm_acceleration_of(P, K, F, aligned, r.delta, new_following, i);
                     if (new_following_pred_a < -P.lane_change_max_braking_imposed) continue;
                     double self_pred_a = free_i;
-                    if (new_preceding >= 0) self_pred_a -= idm_gap_term(P, F, aligned, i, new_preceding);
+                    if (new_preceding >= 0) self_pred_a -= idm_gap_term(P, K, F, aligned, i, new_preceding);
                     double self_a = acc;  // acceleration(self, old_preceding)
                     double jerk = self_pred_a - self_a;
                     if (P.politeness != 0.0) {
                         double new_following_a =
-                            idm_acceleration_of(P, F, aligned, r.delta, new_following, new_preceding);
-                        double old_following_a = idm_acceleration_of(P, F, aligned, r.delta, r_own, i);
+                            idm_acceleration_of(P, K, F, aligned, r.delta, new_following, new_preceding);
+                        double old_following_a = idm_acceleration_of(P, K, F, aligned, r.delta, r_own, i);
                         double old_following_pred_a =
-                            idm_acceleration_of(P, F, aligned, r.delta, r_own, f_own);
+                            idm_acceleration_of(P, K, F, aligned, r.delta, r_own, f_own);
                         jerk = self_pred_a - self_a +
                                P.politeness * (new_following_pred_a - new_following_a +
                                                old_following_pred_a - old_following_a);
@@ -634,20 +658,20 @@ highway_step_kernel(const HwyHighwayParams P, const HwyHighwayState S,
         if (active) {
             int tgt = tgt1;
             if (is_mid && test_bit(sm.aborted, i)) tgt = lane;
+            // IDMVehicle.act (behavior.py:109-112) and ControlledVehicle.act(None)
+            // (controller.py:126-133, runs even when crashed) share the steering law
+            if (idm_active || kind == HWY_KIND_MDP)
+                act_steer = steering_control(P.lanes[tgt], r.x, r.y, r.heading, r.speed);
             if (idm_active) {
-                double steering = steering_control(P.lanes[tgt], r.x, r.y, r.heading, r.speed);
                 if (lane != tgt) {  // behavior.py:121-131
                     int f_t, r_t;
                     neighbours(P, F, V, tgt, i, f_t, r_t);
                     double tacc = free_i;
-                    if (f_t >= 0) tacc -= idm_gap_term(P, F, aligned, i, f_t);
+                    if (f_t >= 0) tacc -= idm_gap_term(P, K, F, aligned, i, f_t);
                     acc = fmin(acc, tacc);
                 }
-                act_steer = steering;
                 act_accel = clipd(acc, -P.acc_max, P.acc_max);
             } else if (kind == HWY_KIND_MDP) {
-                // ControlledVehicle.act(None) (controller.py:126-133); runs even when crashed
-                act_steer = steering_control(P.lanes[tgt], r.x, r.y, r.heading, r.speed);
                 act_accel = kKpA * (r.target_speed - r.speed);  // speed_control :189-198
             }
             r.meta = meta_set_target(r.meta, tgt);
@@ -661,9 +685,9 @@ highway_step_kernel(const HwyHighwayParams P, const HwyHighwayState S,
                 act_accel = fmin(act_accel, 1.0 * (kMaxSpeed - r.speed));
             else if (r.speed < kMinSpeed)
                 act_accel = fmax(act_accel, 1.0 * (kMinSpeed - r.speed));
-            double beta = atan(0.5 * tan(act_steer));
+            double beta = m_atan(0.5 * m_tan(act_steer));
             double sn, cs;
-            sincos(r.heading + beta, &sn, &cs);
+            m_sincos(r.heading + beta, &sn, &cs);
             double vx = r.speed * cs, vy = r.speed * sn;
             r.x += vx * dt;
             r.y += vy * dt;
@@ -672,20 +696,12 @@ highway_step_kernel(const HwyHighwayParams P, const HwyHighwayState S,
                 r.y += r.imp_y;
                 r.meta = (r.meta | HWY_META_CRASHED) & ~HWY_META_HAS_IMPACT;
             }
-            r.heading += r.speed * sin(beta) / (kVehLength / 2) * dt;
+            r.heading += r.speed * m_sin(beta) / (kVehLength / 2) * dt;
             r.speed += act_accel * dt;
             int nl = closest_lane(P, r.x, r.y, r.heading);  // on_state_update :170-177
             r.meta = meta_set_lane(r.meta, nl);
             if (kind == HWY_KIND_VEHICLE) r.meta = meta_set_target(r.meta, nl);  // schema: mirrors lane
         }
-        publish(P, G, i, active, r);
-        env_sync<TPE>();
-        if (i < NW) sm.mid[i] = sm.changed[i] = sm.aborted[i] = 0;  // all readers are past phase B
-        // ---- masks of the new frame + Road.step collision sweep (pass 1), then pass 2
-        build_frame(P, sm, G, i, active, aligned, r, dt, true);
-        env_sync<TPE>();
-        if (active) apply_collisions(sm, G, i, r, dt);
-        p ^= 1;
     }
 
     // ---- epilogue: state back to HBM, observation, reward, termination
