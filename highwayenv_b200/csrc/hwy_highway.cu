@@ -19,6 +19,7 @@
 // last-writer-wins impacts in Road.step, tie rules of the neighbour search) are preserved:
 // see DESIGN.md "ordering".  Reference paths are relative to /root/reference/highway_env.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cuda_runtime.h>
 
@@ -34,6 +35,7 @@ struct Frame {
     static constexpr int NW = TPE / 32;
     double x[TPE], y[TPE], c[TPE], s[TPE], v[TPE], ts[TPE];
     double ls[TPE];                          // longitudinal coordinate on lane 0
+    float lsf[TPE];                          // the same rounded to float (monotone): rank pre-sort key
     uint32_t smask[HWY_MAX_LANES][NW];       // rank-ordered on_lane(margin=1) membership of lane l
     uint32_t tm[HWY_MAX_LANES][NW];          // vehicles whose target lane is l   (slot order)
     uint32_t lane_is[HWY_MAX_LANES][NW];     // vehicles whose lane_index is l    (slot order)
@@ -54,12 +56,12 @@ struct EnvShared {
     unsigned char crash_hit[TPE], tgt1[TPE];
 };
 
+// All envs of a block advance in lock-step (block-wide barriers): besides ordering the shared
+// staging it keeps the block's warps on the same code at the same time, which is what the
+// instruction cache wants from a ~100 KB kernel (measured: 1.4x over per-env barriers).
 template <int TPE>
 __device__ __forceinline__ void env_sync() {
-    if (TPE <= 32)
-        __syncwarp();
-    else
-        __syncthreads();
+    __syncthreads();
 }
 
 template <int NW>
@@ -301,6 +303,7 @@ __device__ __forceinline__ void publish(const HwyHighwayParams& P, Frame<TPE>& F
         // getattr(ego_vehicle, "target_speed", 0): a plain Vehicle has none (behavior.py:172)
         F.ts[i] = meta_kind(r.meta) == HWY_KIND_VEHICLE ? 0.0 : r.target_speed;
         F.ls[i] = lane_s(P.lanes[0], r.x, r.y);
+        F.lsf[i] = (float)F.ls[i];
         F.lane[i] = (unsigned char)meta_lane(r.meta);
         F.tgt[i] = (unsigned char)meta_target(r.meta);
     }
@@ -319,6 +322,31 @@ __device__ __forceinline__ bool pair_precheck(const Frame<TPE>& F, int a, int b,
 template <int TPE>
 __device__ __noinline__ void pair_sat(const Frame<TPE>& F, int a, int b, double dt, bool& inter,
                                       bool& will, double& trx, double& try_) {
+    // Conservative shortcut.  The reference's flags are sticky ANDs over the visited edge
+    // normals and its `break` only triggers once both are False, so if ONE of the four distinct
+    // rectangle axes separates the rectangles statically AND after the relative-displacement
+    // extension, the result is (False, False, None) whatever the other axes say.  We test that
+    // in closed form with a 1e-6 m safety margin (>> the ~1e-12 rounding of either evaluation);
+    // anything closer runs the exact SAT below.
+    {
+        const double hl = kVehLength / 2, hw = kVehWidth / 2, margin = 1e-6;
+        const double ca = F.c[a], sa = F.s[a], cb = F.c[b], sb = F.s[b];
+        const double dx = F.x[b] - F.x[a], dy = F.y[b] - F.y[a];
+        const double rvx = (F.v[a] * ca - F.v[b] * cb) * dt, rvy = (F.v[a] * sa - F.v[b] * sb) * dt;
+        const double cd = fabs(ca * cb + sa * sb), sd = fabs(sa * cb - ca * sb);  // |cos|, |sin| of the heading difference
+        bool separated = false;
+        // axes of a: longitudinal (ca, sa) and lateral (-sa, ca); of b likewise
+        separated |= fabs(dx * ca + dy * sa) - (hl + hl * cd + hw * sd) - fabs(rvx * ca + rvy * sa) > margin;
+        separated |= fabs(-dx * sa + dy * ca) - (hw + hl * sd + hw * cd) - fabs(-rvx * sa + rvy * ca) > margin;
+        separated |= fabs(dx * cb + dy * sb) - (hl + hl * cd + hw * sd) - fabs(rvx * cb + rvy * sb) > margin;
+        separated |= fabs(-dx * sb + dy * cb) - (hw + hl * sd + hw * cd) - fabs(-rvx * sb + rvy * cb) > margin;
+        if (separated) {
+            inter = false;
+            will = false;
+            trx = try_ = 0.0;
+            return;
+        }
+    }
     Quad pa = make_polygon(F.x[a], F.y[a], F.c[a], F.s[a]);
     Quad pb = make_polygon(F.x[b], F.y[b], F.c[b], F.s[b]);
     polygons_intersecting(pa, pb, F.v[a] * F.c[a] * dt, F.v[a] * F.s[a] * dt, F.v[b] * F.c[b] * dt,
@@ -335,14 +363,25 @@ __device__ __forceinline__ void build_frame(const HwyHighwayParams& P, EnvShared
     const int V = P.n_vehicles;
     const int wie = i >> 5;  // warp within the env
     const int lane = meta_lane(r.meta), tgt = meta_target(r.meta);
-    // -- rank along the road (s, slot) and tie detection
+    // -- rank along the road (s, slot) and tie detection.  Float keys first: rounding to float
+    // is monotone, so fu < fi implies su < si; only equal float keys need the doubles.
     const double si = active ? F.ls[i] : 0.0;
+    const float fi = active ? F.lsf[i] : 0.0f;
     int rank = 0;
-    bool tie = false;
+    bool ambiguous = false;
     for (int u = 0; u < V; ++u) {
-        double su = F.ls[u];
-        rank += (su < si) || (su == si && u < i);
-        tie = tie || (su == si && u != i);
+        float fu = F.lsf[u];
+        rank += fu < fi;
+        ambiguous = ambiguous || (fu == fi && u != i);
+    }
+    bool tie = false;
+    if (ambiguous) {
+        rank = 0;
+        for (int u = 0; u < V; ++u) {
+            double su = F.ls[u];
+            rank += (su < si) || (su == si && u < i);
+            tie = tie || (su == si && u != i);
+        }
     }
     if (active) {
         F.perm[rank] = (unsigned char)i;
@@ -431,23 +470,24 @@ __device__ __forceinline__ void apply_collisions(EnvShared<TPE>& sm, const Frame
 }
 
 // ------------------------------------------------------------------ the step kernel
-#ifndef HWY_MINB64
-#define HWY_MINB64 8  // resident blocks per SM the 64-thread variant is compiled for
-#endif
+constexpr int kMaxBlockThreads = 512;  // 128 registers/thread => one full register file
+
+// blockDim.x = TPE * (envs per block); dynamic shared memory = envs per block * sizeof(EnvShared).
 template <int TPE>
-__global__ void __launch_bounds__(TPE == 32 ? 128 : TPE, TPE == 64 ? HWY_MINB64 : 1)
+__global__ void __launch_bounds__(kMaxBlockThreads, 1)
 highway_step_kernel(const HwyHighwayParams P, const HwyHighwayState S,
                     const int32_t* __restrict__ action_i, const float* __restrict__ action_f,
                     float* __restrict__ obs, double* __restrict__ reward,
                     uint8_t* __restrict__ terminated, uint8_t* __restrict__ truncated,
                     double* __restrict__ info_speed, uint8_t* __restrict__ info_crashed) {
-    constexpr int EPB = TPE == 32 ? 4 : 1;  // envs per block (a warp per env when TPE == 32)
     constexpr int NW = TPE / 32;
-    __shared__ EnvShared<TPE> smem[EPB];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    EnvShared<TPE>* smem = reinterpret_cast<EnvShared<TPE>*>(smem_raw);
+    const int EPB = blockDim.x / TPE;
     const int sub = threadIdx.x / TPE;
     const int i = threadIdx.x % TPE;
     const int env = blockIdx.x * EPB + sub;
-    const bool env_ok = env < S.n_envs;  // TPE == 32 only: surplus warps mirror the last env
+    const bool env_ok = env < S.n_envs;  // surplus envs of the last block mirror the last env
     const int e = env_ok ? env : S.n_envs - 1;
     EnvShared<TPE>& sm = smem[sub];
     const int V = P.n_vehicles;
@@ -925,6 +965,43 @@ Grid grid_for(int tpe, int n_envs) {
     return Grid{(n_envs + epb - 1) / epb, tpe * epb};
 }
 
+// Envs per block of the step kernel: as many as fit 512 threads (lock-step, see env_sync),
+// reduced when that leaves the last wave of blocks mostly empty.  HWYB200_EPB overrides.
+int step_envs_per_block(int tpe, int n_envs) {
+    int max_epb = hwy::kMaxBlockThreads / tpe;
+    if (const char* e = getenv("HWYB200_EPB")) {
+        int v = atoi(e);
+        if (v >= 1 && v <= max_epb) return v;
+    }
+    // Two resident blocks per SM measured best (0.40 ms vs 0.43 ms for one 8-env block and
+    // 0.55 ms for eight 1-env blocks at 4096 envs x 51 vehicles): the blocks cover each other's
+    // barrier stalls.  Small batches shrink the block so every SM still gets work.
+    int n_sm = 148;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    int epb = max_epb >= 2 ? max_epb / 2 : 1;
+    while (epb > 1 && (long)n_envs < (long)epb * 2 * n_sm) --epb;
+    return epb;
+}
+
+template <int TPE>
+int launch_step(const HwyHighwayParams* p, const HwyHighwayState* s, const int32_t* action_i,
+                const float* action_f, float* obs, double* reward, uint8_t* terminated,
+                uint8_t* truncated, double* info_speed, uint8_t* info_crashed, int blocks, int epb,
+                cudaStream_t st) {
+    size_t smem = (size_t)epb * sizeof(hwy::EnvShared<TPE>);
+    static thread_local size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t err = cudaFuncSetAttribute(hwy::highway_step_kernel<TPE>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return fail("cudaFuncSetAttribute: %s", cudaGetErrorString(err));
+        configured = smem;
+    }
+    hwy::highway_step_kernel<TPE><<<blocks, TPE * epb, smem, st>>>(
+        *p, *s, action_i, action_f, obs, reward, terminated, truncated, info_speed, info_crashed);
+    return 0;
+}
+
 int launch_observe(const HwyHighwayParams* p, const HwyHighwayState* s, const uint8_t* mask_a,
                    const uint8_t* mask_b, int use_mask, float* obs, cudaStream_t st) {
     int tpe = tpe_for(p->n_vehicles);
@@ -991,19 +1068,18 @@ int hwy_highway_step(const HwyHighwayParams* p, const HwyHighwayState* s, const 
         return fail("%s", "unknown autoreset mode");
     cudaStream_t st = (cudaStream_t)stream;
     int tpe = tpe_for(p->n_vehicles);
-    Grid g = grid_for(tpe, s->n_envs);
-    if (tpe == 32)
-        hwy::highway_step_kernel<32><<<g.blocks, g.threads, 0, st>>>(*p, *s, action_i, action_f, obs,
-                                                                    reward, terminated, truncated, info_speed,
-            info_crashed);
-    else if (tpe == 64)
-        hwy::highway_step_kernel<64><<<g.blocks, g.threads, 0, st>>>(*p, *s, action_i, action_f, obs,
-                                                                    reward, terminated, truncated, info_speed,
-            info_crashed);
-    else
-        hwy::highway_step_kernel<128><<<g.blocks, g.threads, 0, st>>>(*p, *s, action_i, action_f, obs,
-                                                                     reward, terminated, truncated, info_speed,
-            info_crashed);
+    int epb = step_envs_per_block(tpe, s->n_envs);
+    int blocks = (s->n_envs + epb - 1) / epb;
+    if (tpe == 32) {
+        if (launch_step<32>(p, s, action_i, action_f, obs, reward, terminated, truncated, info_speed,
+                            info_crashed, blocks, epb, st)) return 1;
+    } else if (tpe == 64) {
+        if (launch_step<64>(p, s, action_i, action_f, obs, reward, terminated, truncated, info_speed,
+                            info_crashed, blocks, epb, st)) return 1;
+    } else {
+        if (launch_step<128>(p, s, action_i, action_f, obs, reward, terminated, truncated, info_speed,
+                             info_crashed, blocks, epb, st)) return 1;
+    }
     if (check_launch("highway_step_kernel")) return 1;
     if (autoreset == HWY_AUTORESET_SAME_STEP) {
         if (final_obs) {
