@@ -58,9 +58,11 @@ __device__ __forceinline__ bool lanes_aligned(const HwyHighwayParams& P) {
     return ok;
 }
 
-// vehicle/controller.py:145-187 steering_control on a StraightLane
-__device__ __noinline__ double steering_control(const HwyStraightLane L, double x, double y,
-                                                double heading, double speed) {
+// vehicle/controller.py:145-187 steering_control on a StraightLane, up to the argument of the
+// last arcsin: returns x = clip(LENGTH/2/not_zero(speed) * heading_rate_command, -1, 1), i.e.
+// the SINE of the commanded slip angle.
+__device__ __noinline__ double steering_sin_slip(const HwyStraightLane L, double x, double y,
+                                                 double heading, double speed) {
     double lc_s, lc_lat;
     lane_local(L, x, y, lc_s, lc_lat);
     double lane_future_heading = L.heading;  // StraightLane.heading_at
@@ -68,10 +70,35 @@ __device__ __noinline__ double steering_control(const HwyStraightLane L, double 
     double heading_command = m_asin(clipd(lateral_speed_command / not_zero(speed), -1.0, 1.0));
     double heading_ref = lane_future_heading + clipd(heading_command, -kPi / 4, kPi / 4);
     double heading_rate_command = kKpHeading * wrap_to_pi(heading_ref - heading);
-    double slip_angle =
-        m_asin(clipd(kVehLength / 2 / not_zero(speed) * heading_rate_command, -1.0, 1.0));
-    double steering_angle = m_atan(2 * m_tan(slip_angle));
-    return clipd(steering_angle, -kMaxSteer, kMaxSteer);
+    return clipd(kVehLength / 2 / not_zero(speed) * heading_rate_command, -1.0, 1.0);
+}
+
+// The reference then computes  delta = clip(arctan(2 tan(arcsin(x))), +-pi/3)  (controller.py:
+// 176-186) and, in Vehicle.step,  beta = arctan(1/2 tan(delta))  (kinematics.py:141-142), of which
+// only sin(beta) and cos(beta) are used.  When delta is not clipped the two maps cancel:
+// beta = arcsin(x), so sin(beta) = x and cos(beta) = sqrt(1 - x^2); when it is clipped
+// (2 |tan(arcsin x)| > tan(pi/3)) beta = +-arctan(tan(pi/3)/2).  Evaluating that closed form
+// replaces six libm calls per vehicle-substep by two square roots; it differs from the
+// reference's rounded chain by a few ulp (same order as CUDA-vs-glibc libm differences).
+__device__ __forceinline__ void beta_of_controlled(double x, double& sin_beta, double& cos_beta) {
+    const double T3 = 1.7320508075688767;  // np.tan(np.pi / 3)
+    double c = sqrt(1.0 - x * x);          // cos(arcsin x) >= 0
+    if (2.0 * fabs(x) > T3 * c) {          // steering saturated at MAX_STEERING_ANGLE
+        double t = copysign(0.5 * T3, x);
+        double inv = 1.0 / sqrt(1.0 + t * t);
+        sin_beta = t * inv;
+        cos_beta = inv;
+    } else {
+        sin_beta = x;
+        cos_beta = c;
+    }
+}
+// beta = arctan(1/2 tan(delta)) for an explicit steering angle (ContinuousAction ego)
+__device__ __forceinline__ void beta_of_angle(double delta, double& sin_beta, double& cos_beta) {
+    double t = 0.5 * m_tan(delta);
+    double inv = 1.0 / sqrt(1.0 + t * t);
+    sin_beta = t * inv;
+    cos_beta = inv;
 }
 
 // vehicle/controller.py:326-344 speed_to_index (np.round: half to even)

@@ -29,6 +29,22 @@
 
 namespace hwy {
 
+// Optional per-phase cycle accounting (-DHWY_PHASE_TIMING): warp-level clock64() deltas summed
+// into g_phase_cycles; read with hwy_debug_phase_cycles().  Off in the shipped build.
+#ifdef HWY_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[16];
+#define PHASE_INIT() long long _pt = clock64()
+#define PHASE_MARK(k)                                                                 \
+    do {                                                                              \
+        long long _n = clock64();                                                     \
+        if ((threadIdx.x & 31) == 0) atomicAdd(&g_phase_cycles[k], (unsigned long long)(_n - _pt)); \
+        _pt = _n;                                                                     \
+    } while (0)
+#else
+#define PHASE_INIT()
+#define PHASE_MARK(k)
+#endif
+
 // ------------------------------------------------------------------ shared staging
 template <int TPE>
 struct Frame {
@@ -50,7 +66,8 @@ struct EnvShared {
     Frame<TPE> f[2];
     double key[TPE];                         // observation sort keys
     uint32_t geo[TPE][NW];                   // abort-scan hits (0 < d < d*) of mid-change vehicles
-    uint32_t mid[NW], changed[NW], aborted[NW];
+    uint32_t mid[NW];                        // active mid-change IDM vehicles (lane != target)
+    uint32_t chg_to[HWY_MAX_LANES][NW];      // vehicles whose MOBIL decision switched the target to l
     uint32_t ctrl[NW], cc[NW];               // ControlledVehicle instances / check_collisions
     int last_will[TPE];                      // collision sweep: largest partner with will_intersect
     unsigned char crash_hit[TPE], tgt1[TPE];
@@ -510,13 +527,16 @@ highway_step_kernel(const HwyHighwayParams P, const HwyHighwayState S,
         if ((i & 31) == 0) {
             sm.cc[i >> 5] = b_cc;
             sm.ctrl[i >> 5] = b_ctrl;
-            sm.mid[i >> 5] = sm.changed[i >> 5] = sm.aborted[i >> 5] = 0;
+            sm.mid[i >> 5] = 0;
         }
         sm.last_will[i] = -1;
         sm.crash_hit[i] = 0;
+        if (i < HWY_MAX_LANES * NW) (&sm.chg_to[0][0])[i] = 0;
     }
     const IdmK K = make_idm(P);
     int p = 1;
+    PHASE_INIT();
+    PHASE_MARK(0);  // load + static masks
 
     // One iteration = stage the current state, derive its masks (+ the collision sweep of the
     // substep that produced it), then — except after the last substep — act and integrate.
@@ -524,13 +544,19 @@ highway_step_kernel(const HwyHighwayParams P, const HwyHighwayState S,
         p ^= 1;
         Frame<TPE>& F = sm.f[p];
         publish(P, F, i, active, r);
+        PHASE_MARK(1);  // publish
         env_sync<TPE>();
-        if (i < NW) sm.mid[i] = sm.changed[i] = sm.aborted[i] = 0;  // all readers are past phase B
+        PHASE_MARK(2);  // barrier after publish
+        if (i < NW) sm.mid[i] = 0;  // all readers are past phase B
+        if (i < HWY_MAX_LANES * NW) (&sm.chg_to[0][0])[i] = 0;
         // frame 0: masks only — the sweep of the stored state ran at the end of the substep that
         // produced it (previous launch).  Later: Road.step's sweep (road/road.py:477-481).
         build_frame(P, sm, F, i, active, aligned, r, dt, frame > 0);
+        PHASE_MARK(3);  // ranks, masks, sweep pass 1
         env_sync<TPE>();
+        PHASE_MARK(4);  // barrier after build
         if (active && frame > 0) apply_collisions(sm, F, i, r, dt);
+        PHASE_MARK(5);  // sweep pass 2
         if (frame == frames) break;
 
         // ---- action_type.act(action) on the first frame (abstract.py:294-304)
@@ -580,6 +606,7 @@ highway_step_kernel(const HwyHighwayParams P, const HwyHighwayState S,
             env_sync<TPE>();
         }
 
+        PHASE_MARK(6);  // ego action (+ barrier on frame 0)
         // ---- Road.act() (road/road.py:464-467), phase A: own-lane IDM + lane-change policy
         const int lane = meta_lane(r.meta);
         const int tgt0 = meta_target(r.meta);
@@ -650,58 +677,66 @@ highway_step_kernel(const HwyHighwayParams P, const HwyHighwayState S,
                     if (jerk < P.lane_change_min_acc_gain) continue;
                     tgt1 = cand;
                 }
-                if (tgt1 != tgt0) atomicOr(&sm.changed[i >> 5], 1u << (i & 31));
+                if (tgt1 != tgt0) atomicOr(&sm.chg_to[tgt1][i >> 5], 1u << (i & 31));
             }
         }
         if (active) sm.tgt1[i] = (unsigned char)tgt1;
+        PHASE_MARK(7);  // phase A
         env_sync<TPE>();
-
-        // ---- ordered fix-up of the Gauss-Seidel abort scan (one thread per env).  Vehicles act
-        // in list order: vehicle i sees the NEW target of every j < i and the OLD one of j > i.
-        if (i == 0) {
-            uint32_t any_mid = 0;
-#pragma unroll
-            for (int w = 0; w < NW; ++w) any_mid |= sm.mid[w];
-            if (any_mid) {
-#pragma unroll
-                for (int w = 0; w < NW; ++w) {
-                    uint32_t ev = sm.mid[w] | sm.changed[w];
-                    while (ev) {
-                        int b = __ffs(ev) - 1;
-                        ev &= ev - 1;
-                        int v = w * 32 + b;
-                        uint32_t bit = 1u << b;
-                        int t0 = F.tgt[v];
-                        if (sm.changed[w] & bit) {  // MOBIL decision becomes visible to later vehicles
-                            F.tm[t0][w] &= ~bit;
-                            F.tm[sm.tgt1[v]][w] |= bit;
-                        } else {
-                            uint32_t hit = 0;
-#pragma unroll
-                            for (int w2 = 0; w2 < NW; ++w2)
-                                hit |= sm.geo[v][w2] & F.tm[t0][w2] & ~F.lane_is[t0][w2];
-                            if (hit) {  // behavior.py:241-243: target := current lane
-                                sm.aborted[w] |= bit;
-                                F.tm[t0][w] &= ~bit;
-                                F.tm[F.lane[v]][w] |= bit;
-                            }
-                        }
-                    }
-                }
-            }
-        }
-        env_sync<TPE>();
+        PHASE_MARK(8);  // barrier after phase A
 
         // ---- Road.act() phase B (steering + target-lane IDM with the final target), then
         // Road.step(dt): Vehicle.step (kinematics.py:130-177; IDMVehicle.step behavior.py:139-148).
         // The new state goes to the other frame, so no barrier is needed before staging it.
         if (active) {
             int tgt = tgt1;
-            if (is_mid && test_bit(sm.aborted, i)) tgt = lane;
+            if (is_mid) {
+                // Ordered resolution of the Gauss-Seidel abort scan (behavior.py:229-244).  Vehicles
+                // act in list order: vehicle j sees the NEW target of every earlier vehicle and the
+                // OLD one of every later vehicle.  Only events on our target lane T matter (a
+                // vehicle leaving T, or an aborting vehicle returning to its own lane, sits ON the
+                // lane it now targets and is excluded by `lane_index != T`), so each mid-change
+                // vehicle replays, redundantly and in registers, the decisions of the earlier
+                // mid-change vehicles that share its target.
+                const int T = tgt0, iw = i >> 5, ib = i & 31;
+                uint32_t tmT[NW], lneT[NW], chgT[NW], ab[NW];
+#pragma unroll
+                for (int w = 0; w < NW; ++w) {
+                    tmT[w] = F.tm[T][w];
+                    lneT[w] = ~F.lane_is[T][w];
+                    chgT[w] = sm.chg_to[T][w];
+                    ab[w] = 0;
+                }
+#pragma unroll
+                for (int w = 0; w < NW; ++w) {
+                    uint32_t m = sm.mid[w] & tmT[w];
+                    if (w > iw) m = 0;
+                    if (w == iw) m &= (2u << ib) - 1u;  // mids up to and including ourselves
+                    while (m) {
+                        int b = __ffs(m) - 1;
+                        m &= m - 1;
+                        int j = w * 32 + b;
+                        uint32_t hit = 0;
+#pragma unroll
+                        for (int w2 = 0; w2 < NW; ++w2) {
+                            uint32_t below = w2 < w ? ~0u : (w2 == w ? (1u << b) - 1u : 0u);
+                            uint32_t cur = (tmT[w2] & ~ab[w2]) | (chgT[w2] & below);
+                            hit |= sm.geo[j][w2] & lneT[w2] & cur;
+                        }
+                        if (hit) ab[w] |= 1u << b;  // behavior.py:241-243: target := current lane
+                    }
+                }
+                if ((ab[iw] >> ib) & 1u) tgt = lane;
+            }
             // IDMVehicle.act (behavior.py:109-112) and ControlledVehicle.act(None)
             // (controller.py:126-133, runs even when crashed) share the steering law
-            if (idm_active || kind == HWY_KIND_MDP)
-                act_steer = steering_control(P.lanes[tgt], r.x, r.y, r.heading, r.speed);
+            double sin_beta = 0.0, cos_beta = 1.0;  // crashed: steering 0 (clip_actions :155-158)
+            if (idm_active || (kind == HWY_KIND_MDP && !crashed)) {
+                double xs = steering_sin_slip(P.lanes[tgt], r.x, r.y, r.heading, r.speed);
+                beta_of_controlled(xs, sin_beta, cos_beta);
+            } else if (kind == HWY_KIND_VEHICLE && !crashed) {
+                beta_of_angle(act_steer, sin_beta, cos_beta);
+            }
             if (idm_active) {
                 if (lane != tgt) {  // behavior.py:121-131
                     int f_t, r_t;
@@ -716,6 +751,7 @@ highway_step_kernel(const HwyHighwayParams P, const HwyHighwayState S,
             }
             r.meta = meta_set_target(r.meta, tgt);
 
+            PHASE_MARK(9);  // phase B
             if (kind == HWY_KIND_IDM) r.timer += dt;
             if (crashed) {  // clip_actions :155-168
                 act_steer = 0.0;
@@ -725,9 +761,9 @@ highway_step_kernel(const HwyHighwayParams P, const HwyHighwayState S,
                 act_accel = fmin(act_accel, 1.0 * (kMaxSpeed - r.speed));
             else if (r.speed < kMinSpeed)
                 act_accel = fmax(act_accel, 1.0 * (kMinSpeed - r.speed));
-            double beta = m_atan(0.5 * m_tan(act_steer));
-            double sn, cs;
-            m_sincos(r.heading + beta, &sn, &cs);
+            // cos/sin(heading + beta) by angle addition from the staged cos/sin(heading)
+            const double ch = F.c[i], sh = F.s[i];
+            double cs = ch * cos_beta - sh * sin_beta, sn = sh * cos_beta + ch * sin_beta;
             double vx = r.speed * cs, vy = r.speed * sn;
             r.x += vx * dt;
             r.y += vy * dt;
@@ -736,14 +772,16 @@ highway_step_kernel(const HwyHighwayParams P, const HwyHighwayState S,
                 r.y += r.imp_y;
                 r.meta = (r.meta | HWY_META_CRASHED) & ~HWY_META_HAS_IMPACT;
             }
-            r.heading += r.speed * m_sin(beta) / (kVehLength / 2) * dt;
+            r.heading += r.speed * sin_beta / (kVehLength / 2) * dt;
             r.speed += act_accel * dt;
             int nl = closest_lane(P, r.x, r.y, r.heading);  // on_state_update :170-177
             r.meta = meta_set_lane(r.meta, nl);
             if (kind == HWY_KIND_VEHICLE) r.meta = meta_set_target(r.meta, nl);  // schema: mirrors lane
         }
+        PHASE_MARK(10);  // integrate
     }
 
+    PHASE_MARK(11);
     // ---- epilogue: state back to HBM, observation, reward, termination
     const Frame<TPE>& F = sm.f[p];
     if (active && env_ok) store_vehicle(S, slot, r);
@@ -781,6 +819,7 @@ highway_step_kernel(const HwyHighwayParams P, const HwyHighwayState S,
         if (info_speed) info_speed[e] = r.speed;  // abstract.py:200-217 _info
         if (info_crashed) info_crashed[e] = (uint8_t)is_crashed;
     }
+    PHASE_MARK(12);  // epilogue
 }
 
 // ------------------------------------------------------------------ observe-only kernel
@@ -1044,6 +1083,19 @@ int hwy_highway_reset(const HwyHighwayParams* p, const HwyHighwayState* s, const
     if (launch_reset(p, s, mask, nullptr, use_mask, st)) return 1;
     if (obs) return launch_observe(p, s, mask, nullptr, use_mask, obs, st);
     return 0;
+}
+
+// debug: read and clear the per-phase cycle counters (all zero unless built with HWY_PHASE_TIMING)
+int hwy_debug_phase_cycles(unsigned long long* out16) {
+#ifdef HWY_PHASE_TIMING
+    unsigned long long zero[16] = {0};
+    if (cudaMemcpyFromSymbol(out16, hwy::g_phase_cycles, sizeof(zero)) != cudaSuccess) return 1;
+    if (cudaMemcpyToSymbol(hwy::g_phase_cycles, zero, sizeof(zero)) != cudaSuccess) return 1;
+    return 0;
+#else
+    for (int k = 0; k < 16; ++k) out16[k] = 0;
+    return 0;
+#endif
 }
 
 int hwy_highway_autoreset(const HwyHighwayParams* p, const HwyHighwayState* s,
