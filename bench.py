@@ -206,20 +206,15 @@ def run_gpu_arm(args) -> None:
         N.check(lib.hwy_highway_step(
             C.byref(P), C.byref(S), actions[t].data_ptr(), None, env._obs.data_ptr(), env._reward.data_ptr(),
             env._terminated.data_ptr(), env._truncated.data_ptr(), env._info_speed.data_ptr(),
-            env._info_crashed.data_ptr(), N.AUTORESET_DISABLED, None, sp))
-
-    def abi_autoreset():
-        N.check(lib.hwy_highway_autoreset(C.byref(P), C.byref(S), env._terminated.data_ptr(),
-                                          env._truncated.data_ptr(), env._obs.data_ptr(), sp))
+            env._info_crashed.data_ptr(), N.AUTORESET_SAME_STEP, None, sp))
 
     # ---- warm-up
     for t in range(W):
         abi_step(t)
-        abi_autoreset()
     barrier()
 
     # ---- timed: K steps, CUDA events per step, L2 flushed between steps
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K)]
     launches0 = lib.hwy_launch_count()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
@@ -229,16 +224,14 @@ def run_gpu_arm(args) -> None:
     for k in range(K):
         flush.fill_(k & 0xFF)
         ev[k][0].record(stream)
-        abi_step(W + k)
+        abi_step(W + k)  # ONE launch: substeps + observation + reward + SameStep autoreset
         ev[k][1].record(stream)
-        abi_autoreset()
-        ev[k][2].record(stream)
     barrier()
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop() if sampler else None
     launches = int(lib.hwy_launch_count() - launches0)
-    step_ms = [ev[k][0].elapsed_time(ev[k][2]) for k in range(K)]
-    kern_ms = [ev[k][0].elapsed_time(ev[k][1]) for k in range(K)]
+    step_ms = [ev[k][0].elapsed_time(ev[k][1]) for k in range(K)]
+    kern_ms = step_ms
     total_ms = sum(step_ms)
     kern_ms_avg = sum(kern_ms) / K
 

@@ -51,7 +51,7 @@ struct Frame {
     static constexpr int NW = TPE / 32;
     double x[TPE], y[TPE], c[TPE], s[TPE], v[TPE], ts[TPE];
     double ls[TPE];                          // longitudinal coordinate on lane 0
-    float lsf[TPE];                          // the same rounded to float (monotone): rank pre-sort key
+    __align__(16) float lsf[TPE];            // the same rounded to float (monotone): rank pre-sort key
     uint32_t smask[HWY_MAX_LANES][NW];       // rank-ordered on_lane(margin=1) membership of lane l
     uint32_t tm[HWY_MAX_LANES][NW];          // vehicles whose target lane is l   (slot order)
     uint32_t lane_is[HWY_MAX_LANES][NW];     // vehicles whose lane_index is l    (slot order)
@@ -67,10 +67,19 @@ struct EnvShared {
     double key[TPE];                         // observation sort keys
     uint32_t geo[TPE][NW];                   // abort-scan hits (0 < d < d*) of mid-change vehicles
     uint32_t mid[NW];                        // active mid-change IDM vehicles (lane != target)
-    uint32_t chg_to[HWY_MAX_LANES][NW];      // vehicles whose MOBIL decision switched the target to l
+    // MOBIL work list: (vehicle, candidate lane) items pushed by the vehicles whose timer fired
+    // and evaluated densely by the env's first threads; accepted candidates set ok_left/ok_right.
+    uint32_t ok_left[NW], ok_right[NW];
+    int n_items;
+    unsigned short items[2 * TPE];
+    double free_t[TPE], acc_own[TPE], delta[TPE];  // own IDM free-road term / own-lane acceleration / DELTA
+    signed char f_own[TPE], r_own[TPE];      // own-lane preceding / following vehicle (-1: none)
     uint32_t ctrl[NW], cc[NW];               // ControlledVehicle instances / check_collisions
     int last_will[TPE];                      // collision sweep: largest partner with will_intersect
-    unsigned char crash_hit[TPE], tgt1[TPE];
+    unsigned char crash_hit[TPE];
+    // fused autoreset staging (Vehicle.create_random chain): per-vehicle spawn increment / position
+    double sp_x[TPE];
+    int done, sp_fallback;
 };
 
 // All envs of a block advance in lock-step (block-wide barriers): besides ordering the shared
@@ -202,7 +211,8 @@ __device__ __forceinline__ double idm_acceleration_of(const HwyHighwayParams& P,
 template <int TPE>
 __device__ __forceinline__ void kinematics_observe(const HwyHighwayParams& P, const Frame<TPE>& F,
                                                    double* key_scratch, int i,
-                                                   float* __restrict__ obs_env) {
+                                                   float* __restrict__ obs_env,
+                                                   float* __restrict__ obs_env2 = nullptr) {
     const int V = P.n_vehicles, K = P.obs_vehicles_count;
     const HwyStraightLane& Le = P.lanes[F.lane[0]];
     const double ex = F.x[0], ey = F.y[0];
@@ -264,11 +274,23 @@ __device__ __forceinline__ void kinematics_observe(const HwyHighwayParams& P, co
         o[2] = (float)r2;
         o[3] = (float)r3;
         o[4] = (float)r4;
+        if (obs_env2) {
+            o = obs_env2 + 5 * row;
+            o[0] = 1.0f;
+            o[1] = (float)r1;
+            o[2] = (float)r2;
+            o[3] = (float)r3;
+            o[4] = (float)r4;
+        }
     }
     int filled = 1 + (n_valid < K - 1 ? n_valid : K - 1);  // zero padding of missing rows
     if (i < K && i >= filled) {
         float* o = obs_env + 5 * i;
         o[0] = o[1] = o[2] = o[3] = o[4] = 0.0f;
+        if (obs_env2) {
+            o = obs_env2 + 5 * i;
+            o[0] = o[1] = o[2] = o[3] = o[4] = 0.0f;
+        }
     }
 }
 
@@ -333,8 +355,12 @@ __device__ __forceinline__ void publish(const HwyHighwayParams& P, Frame<TPE>& F
 template <int TPE>
 __device__ __forceinline__ bool pair_precheck(const Frame<TPE>& F, int a, int b, double dt) {
     const double diag = sqrt(kVehLength * kVehLength + kVehWidth * kVehWidth);
-    double dist = norm2(F.x[b] - F.x[a], F.y[b] - F.y[a]);
-    return !(dist > (diag + diag) / 2 + F.v[a] * dt);
+    const double thr = (diag + diag) / 2 + F.v[a] * dt;
+    const double dx = F.x[b] - F.x[a], dy = F.y[b] - F.y[a];
+    // far pairs (the vast majority): d^2 clearly above thr^2 => the exact test below is true too
+    if (thr >= 0.0 && dx * dx + dy * dy > thr * thr * 1.000001 + 1e-9) return false;
+    double dist = norm2(dx, dy);
+    return !(dist > thr);
 }
 template <int TPE>
 __device__ __noinline__ void pair_sat(const Frame<TPE>& F, int a, int b, double dt, bool& inter,
@@ -386,10 +412,21 @@ __device__ __forceinline__ void build_frame(const HwyHighwayParams& P, EnvShared
     const float fi = active ? F.lsf[i] : 0.0f;
     int rank = 0;
     bool ambiguous = false;
-    for (int u = 0; u < V; ++u) {
-        float fu = F.lsf[u];
-        rank += fu < fi;
-        ambiguous = ambiguous || (fu == fi && u != i);
+    {
+        const float4* lsf4 = reinterpret_cast<const float4*>(F.lsf);
+        const int n4 = V >> 2;
+        for (int q = 0; q < n4; ++q) {
+            float4 f = lsf4[q];
+            const int u = q << 2;
+            rank += (f.x < fi) + (f.y < fi) + (f.z < fi) + (f.w < fi);
+            ambiguous = ambiguous || (f.x == fi && u != i) || (f.y == fi && u + 1 != i) ||
+                        (f.z == fi && u + 2 != i) || (f.w == fi && u + 3 != i);
+        }
+        for (int u = n4 << 2; u < V; ++u) {
+            float fu = F.lsf[u];
+            rank += fu < fi;
+            ambiguous = ambiguous || (fu == fi && u != i);
+        }
     }
     bool tie = false;
     if (ambiguous) {
@@ -486,6 +523,233 @@ __device__ __forceinline__ void apply_collisions(EnvShared<TPE>& sm, const Frame
     }
 }
 
+// ------------------------------------------------------------------ fused autoreset
+// PCG64 jump table: state_n = A^n * state_0 + G_n * inc (mod 2^128), G_n = sum_{j<n} A^j, so a
+// thread can enter the env's numpy stream at any output index with two 128-bit multiplies.
+constexpr int kPcgJumpN = 4 * HWY_MAX_VEHICLES + 8;
+__device__ uint64_t g_pcg_jump[kPcgJumpN][4];  // A^n hi, lo, G_n hi, lo
+
+struct U128 {
+    uint64_t hi, lo;
+};
+__device__ __forceinline__ U128 mul128(U128 a, U128 b) {
+    U128 r;
+    r.lo = a.lo * b.lo;
+    r.hi = __umul64hi(a.lo, b.lo) + a.hi * b.lo + a.lo * b.hi;
+    return r;
+}
+__device__ __forceinline__ U128 add128(U128 a, U128 b) {
+    U128 r;
+    r.lo = a.lo + b.lo;
+    r.hi = a.hi + b.hi + (r.lo < a.lo ? 1 : 0);
+    return r;
+}
+__global__ void pcg_jump_init_kernel() {
+    const U128 A = {0x2360ed051fc65da4ULL, 0x4385df649fccf645ULL};
+    U128 an = {0, 1}, gn = {0, 0};
+    for (int n = 0; n < kPcgJumpN; ++n) {
+        g_pcg_jump[n][0] = an.hi;
+        g_pcg_jump[n][1] = an.lo;
+        g_pcg_jump[n][2] = gn.hi;
+        g_pcg_jump[n][3] = gn.lo;
+        gn = add128(mul128(gn, A), U128{0, 1});  // G_{n+1} = G_n * A + 1
+        an = mul128(an, A);
+    }
+}
+// generator positioned so that its next next64() returns output number n of the stream `g0`
+__device__ __forceinline__ Pcg64 pcg_at(const Pcg64& g0, int n) {
+    U128 an = {g_pcg_jump[n][0], g_pcg_jump[n][1]}, gn = {g_pcg_jump[n][2], g_pcg_jump[n][3]};
+    U128 st = add128(mul128(an, U128{g0.s_hi, g0.s_lo}), mul128(gn, U128{g0.i_hi, g0.i_lo}));
+    Pcg64 g = g0;
+    g.s_hi = st.hi;
+    g.s_lo = st.lo;
+    g.has32 = 0;
+    g.u32 = 0;
+    return g;
+}
+
+// HighwayEnv._create_vehicles (envs/highway_env.py:72-98,177-182) for one env inside the step
+// kernel, one vehicle per thread.  Vehicle.create_random (vehicle/kinematics.py:50-104) draws,
+// per vehicle and in list order, [choice(lanes): one 32-bit word][uniform: 64 bit] for the ego
+// and [32][64 speed][64 position][64 DELTA] for traffic; numpy serves 32-bit words as the low
+// then the buffered high half of one 64-bit output.  Absent a Lemire rejection (p = 2^-32 per
+// draw) every vehicle's position in the stream is therefore known in closed form; the only
+// sequential part is the running sum of the longitudinal positions (kept sequential so it
+// rounds like the reference).  Rejections, or lanes that are not the x-aligned highway, fall
+// back to the serial draw order on one thread.  All threads of the BLOCK must call this
+// (barriers); only envs with do_reset do work.  On return r/speed_index hold the new state.
+template <int TPE>
+__device__ __forceinline__ void spawn_fused(const HwyHighwayParams& P, const HwyHighwayState& S,
+                                            EnvShared<TPE>& sm, int e, int i, bool active,
+                                            bool do_reset, bool simple_geometry, VehicleRegs& r,
+                                            int& speed_index) {
+    const int V = P.n_vehicles, L = P.lanes_count;
+    const size_t n = (size_t)S.n_envs;
+    Pcg64 g0;
+    double speed = 0.0, delta = 4.0, incr = 0.0;
+    int lane_id = 0;
+    if (do_reset) {
+        g0.s_hi = S.rng[0 * n + e];
+        g0.s_lo = S.rng[1 * n + e];
+        g0.i_hi = S.rng[2 * n + e];
+        g0.i_lo = S.rng[3 * n + e];
+        uint64_t w4 = S.rng[4 * n + e];
+        g0.has32 = (uint32_t)(w4 >> 32);
+        g0.u32 = (uint32_t)w4;
+    }
+    const int h0 = do_reset ? (int)g0.has32 : 0;
+    const int n32 = L > 1 ? 1 : 0;                            // choice(1) draws nothing
+    const int ego32 = (n32 && P.initial_lane_id < 0) ? 1 : 0;
+    auto q_before = [&](int k) { return k == 0 ? 0 : ego32 + (k - 1) * n32; };       // 32-bit requests before k
+    auto n64_before = [&](int k) { return k == 0 ? 0 : 1 + 3 * (k - 1); };            // 64-bit outputs before k
+    auto fresh_before = [&](int q) { return h0 == 0 ? (q + 1) / 2 : q / 2; };         // outputs used by requests < q
+    auto base_of = [&](int k) { return fresh_before(q_before(k)) + n64_before(k); };  // outputs before vehicle k
+    if (do_reset && active && simple_geometry) {
+        const int k = i;
+        const bool has32 = k == 0 ? ego32 : n32;
+        Pcg64 g = pcg_at(g0, base_of(k));
+        uint32_t r32 = 0;
+        if (has32) {
+            const int rq = q_before(k);
+            if (((h0 + rq) & 1) == 0) {
+                r32 = (uint32_t)g.next64();  // fresh output: low half (the high half stays buffered)
+            } else if (rq == 0) {
+                r32 = g0.u32;                // the half buffered before this reset
+            } else {
+                // high half of the output the previous requester opened: vehicle k-1
+                Pcg64 gp = pcg_at(g0, base_of(k - 1));
+                r32 = (uint32_t)(gp.next64() >> 32);
+            }
+            // Lemire (random_bounded_uint64, rng = L-1): rejection => serial fallback
+            uint64_t m = (uint64_t)r32 * (uint32_t)L;
+            uint32_t leftover = (uint32_t)m;
+            if (leftover < (uint32_t)L && leftover < (0xffffffffu - (uint32_t)(L - 1)) % (uint32_t)L)
+                sm.sp_fallback = 1;
+            lane_id = (int)(m >> 32);
+        }
+        if (k == 0 && P.initial_lane_id >= 0) lane_id = P.initial_lane_id;
+        const HwyStraightLane& Ln = P.lanes[lane_id];
+        const bool is_ego = k == 0;
+        speed = is_ego ? P.ego_speed : g.uniform(0.7 * Ln.speed_limit, 0.8 * Ln.speed_limit);
+        double spacing = is_ego ? P.ego_spacing : 1 / P.vehicles_density;
+        double default_spacing = 12 + 1.0 * speed;
+        double offset = spacing * default_spacing * P.spawn_exp;
+        incr = offset * g.uniform(0.9, 1.1);
+        if (!is_ego) delta = g.uniform(P.delta_lo, P.delta_hi);
+        sm.sp_x[k] = is_ego ? 3 * offset + incr : incr;  // x0 = 3 * offset; x0 += offset * U
+    }
+    env_sync<TPE>();
+    if (do_reset && i == 0) {
+        if (simple_geometry && !sm.sp_fallback) {
+            // x_k = max_j<k s_j + incr_k; positions increase strictly, so the max is x_{k-1}
+            double x = sm.sp_x[0];
+            for (int k = 1; k < V; ++k) {
+                x = x + sm.sp_x[k];
+                sm.sp_x[k] = x;
+            }
+            // stream position after the reset
+            const int Q = ego32 + (V - 1) * n32;
+            Pcg64 ge = pcg_at(g0, fresh_before(Q) + n64_before(V));
+            uint32_t has_f = (uint32_t)((h0 + Q) & 1), u_f = g0.u32;
+            if (Q > 0) {
+                int rf = Q - 1;  // last fresh request
+                if (((h0 + rf) & 1) != 0) rf -= 1;
+                if (rf >= 0) {
+                    int kf = ego32 ? rf : rf + 1;  // vehicle issuing request rf
+                    Pcg64 gp = pcg_at(g0, base_of(kf));
+                    u_f = (uint32_t)(gp.next64() >> 32);
+                }
+            }
+            S.rng[0 * n + e] = ge.s_hi;
+            S.rng[1 * n + e] = ge.s_lo;
+            S.rng[4 * n + e] = ((uint64_t)has_f << 32) | u_f;
+        }
+    }
+    env_sync<TPE>();
+    const bool fallback = do_reset && (!simple_geometry || sm.sp_fallback);
+    if (fallback && i == 0) {
+        // serial draw order, results staged through HBM (rare path)
+        Pcg64 g = g0;
+        double2* pos = reinterpret_cast<double2*>(S.pos);
+        double2* hs = reinterpret_cast<double2*>(S.hs);
+        const size_t base = (size_t)e * S.vp;
+        for (int v = 0; v < V; ++v) {
+            const bool is_ego = v == 0;
+            int id = (is_ego && P.initial_lane_id >= 0) ? P.initial_lane_id : g.choice(L);
+            const HwyStraightLane& Lv = P.lanes[id];
+            double sp = is_ego ? P.ego_speed : g.uniform(0.7 * Lv.speed_limit, 0.8 * Lv.speed_limit);
+            double spacing = is_ego ? P.ego_spacing : 1 / P.vehicles_density;
+            double offset = spacing * (12 + 1.0 * sp) * P.spawn_exp;
+            double x0;
+            if (v > 0) {
+                x0 = lane_s(Lv, pos[base].x, pos[base].y);
+                for (int j = 1; j < v; ++j) x0 = fmax(x0, lane_s(Lv, pos[base + j].x, pos[base + j].y));
+            } else {
+                x0 = 3 * offset;
+            }
+            x0 += offset * g.uniform(0.9, 1.1);
+            double px = (Lv.start_x + x0 * Lv.dir_x) + 0.0 * Lv.lat_x;
+            double py = (Lv.start_y + x0 * Lv.dir_y) + 0.0 * Lv.lat_y;
+            pos[base + v] = make_double2(px, py);
+            hs[base + v] = make_double2(Lv.heading, sp);
+            S.delta[base + v] = is_ego ? 4.0 : g.uniform(P.delta_lo, P.delta_hi);
+        }
+        S.rng[0 * n + e] = g.s_hi;
+        S.rng[1 * n + e] = g.s_lo;
+        S.rng[4 * n + e] = ((uint64_t)g.has32 << 32) | g.u32;
+        __threadfence_block();
+    }
+    env_sync<TPE>();
+    if (do_reset && active) {
+        const bool is_ego = i == 0;
+        double px, py, heading;
+        if (fallback) {
+            const size_t slot = (size_t)e * S.vp + i;  // staged by thread 0 before the barrier
+            px = S.pos[2 * slot];
+            py = S.pos[2 * slot + 1];
+            heading = S.hs[2 * slot];
+            speed = S.hs[2 * slot + 1];
+            delta = S.delta[slot];
+        } else {
+            const HwyStraightLane& Ln = P.lanes[lane_id];
+            double x0 = sm.sp_x[i];
+            px = (Ln.start_x + x0 * Ln.dir_x) + 0.0 * Ln.lat_x;  // lane.position(x0, 0)
+            py = (Ln.start_y + x0 * Ln.dir_y) + 0.0 * Ln.lat_y;
+            heading = Ln.heading;
+        }
+        int lane = closest_lane(P, px, py, heading);  // RoadObject.__init__ objects.py:46-50
+        double target_speed = speed;                   // `target_speed or self.speed`
+        double timer = 0.0;
+        int kind, cc;
+        if (is_ego) {
+            cc = 1;
+            delta = 4.0;
+            if (P.action_type == 0) {
+                kind = HWY_KIND_MDP;
+                speed_index = speed_to_index(P, target_speed);
+                target_speed = P.target_speeds[speed_index];
+            } else {
+                kind = HWY_KIND_VEHICLE;
+                speed_index = -1;
+            }
+        } else {
+            kind = HWY_KIND_IDM;
+            cc = P.others_check_collisions;
+            timer = py_mod_pos((px + py) * kPi, P.lane_change_delay);  // behavior.py:64
+        }
+        r.x = px;
+        r.y = py;
+        r.heading = heading;
+        r.speed = speed;
+        r.target_speed = target_speed;
+        r.timer = timer;
+        r.delta = delta;
+        r.imp_x = r.imp_y = 0.0;
+        r.meta = (lane << HWY_META_LANE_SHIFT) | (lane << HWY_META_TARGET_SHIFT) |
+                 (cc ? HWY_META_CHECK_COLLISIONS : 0) | (kind << HWY_META_KIND_SHIFT) | HWY_META_PRESENT;
+    }
+}
+
 // ------------------------------------------------------------------ the step kernel
 constexpr int kMaxBlockThreads = 512;  // 128 registers/thread => one full register file
 
@@ -496,7 +760,8 @@ highway_step_kernel(const HwyHighwayParams P, const HwyHighwayState S,
                     const int32_t* __restrict__ action_i, const float* __restrict__ action_f,
                     float* __restrict__ obs, double* __restrict__ reward,
                     uint8_t* __restrict__ terminated, uint8_t* __restrict__ truncated,
-                    double* __restrict__ info_speed, uint8_t* __restrict__ info_crashed) {
+                    double* __restrict__ info_speed, uint8_t* __restrict__ info_crashed,
+                    const int autoreset, float* __restrict__ final_obs) {
     constexpr int NW = TPE / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EnvShared<TPE>* smem = reinterpret_cast<EnvShared<TPE>*>(smem_raw);
@@ -531,7 +796,9 @@ highway_step_kernel(const HwyHighwayParams P, const HwyHighwayState S,
         }
         sm.last_will[i] = -1;
         sm.crash_hit[i] = 0;
-        if (i < HWY_MAX_LANES * NW) (&sm.chg_to[0][0])[i] = 0;
+        if (i < NW) sm.ok_left[i] = sm.ok_right[i] = 0;
+        if (i == 0) sm.n_items = 0;
+        if (active) sm.delta[i] = r.delta;
     }
     const IdmK K = make_idm(P);
     int p = 1;
@@ -547,8 +814,8 @@ highway_step_kernel(const HwyHighwayParams P, const HwyHighwayState S,
         PHASE_MARK(1);  // publish
         env_sync<TPE>();
         PHASE_MARK(2);  // barrier after publish
-        if (i < NW) sm.mid[i] = 0;  // all readers are past phase B
-        if (i < HWY_MAX_LANES * NW) (&sm.chg_to[0][0])[i] = 0;
+        if (i < NW) sm.mid[i] = sm.ok_left[i] = sm.ok_right[i] = 0;  // all readers are past phase B
+        if (i == 0) sm.n_items = 0;
         // frame 0: masks only — the sweep of the stored state ran at the end of the substep that
         // produced it (previous launch).  Later: Road.step's sweep (road/road.py:477-481).
         build_frame(P, sm, F, i, active, aligned, r, dt, frame > 0);
@@ -607,13 +874,12 @@ highway_step_kernel(const HwyHighwayParams P, const HwyHighwayState S,
         }
 
         PHASE_MARK(6);  // ego action (+ barrier on frame 0)
-        // ---- Road.act() (road/road.py:464-467), phase A: own-lane IDM + lane-change policy
+        // ---- Road.act() (road/road.py:464-467), phase A1: own-lane IDM; lane-change policy set-up
         const int lane = meta_lane(r.meta);
         const int tgt0 = meta_target(r.meta);
         const bool crashed = (r.meta & HWY_META_CRASHED) != 0;
         const bool idm_active = active && kind == HWY_KIND_IDM && !crashed;  // behavior.py:102-103
-        int tgt1 = tgt0;
-        bool is_mid = false;
+        bool is_mid = false, fired = false;
         double acc = 0.0, free_i = 0.0;
         if (idm_active) {
             free_i = idm_free_term(K.comfort_acc_max, r.speed, r.target_speed, P.lanes[lane].speed_limit, r.delta);
@@ -649,47 +915,71 @@ highway_step_kernel(const HwyHighwayParams P, const HwyHighwayState S,
                 atomicOr(&sm.mid[i >> 5], 1u << (i & 31));
             } else if (P.lane_change_delay < r.timer) {  // utils.do_every (utils.py:27-28)
                 r.timer = 0.0;
-                // side_lanes (road/road.py:200-211): id-1 then id+1; no break => last wins.
-                // mobil() (behavior.py:265-324), route None => acceleration-gain branch.
-                for (int k = 0; k < 2; ++k) {
-                    int cand = k == 0 ? lane - 1 : lane + 1;
-                    if (cand < 0 || cand > P.lanes_count - 1) continue;
-                    if (!lane_reachable(P.lanes[cand], r.x, r.y)) continue;
-                    if (fabs(r.speed) < 1) continue;
-                    int new_preceding, new_following;
-                    neighbours(P, F, V, cand, i, new_preceding, new_following);
-                    double new_following_pred_a = idm_acceleration_of(P, K, F, aligned, r.delta, new_following, i);
-                    if (new_following_pred_a < -P.lane_change_max_braking_imposed) continue;
-                    double self_pred_a = free_i;
-                    if (new_preceding >= 0) self_pred_a -= idm_gap_term(P, K, F, aligned, i, new_preceding);
-                    double self_a = acc;  // acceleration(self, old_preceding)
-                    double jerk = self_pred_a - self_a;
-                    if (P.politeness != 0.0) {
-                        double new_following_a =
-                            idm_acceleration_of(P, K, F, aligned, r.delta, new_following, new_preceding);
-                        double old_following_a = idm_acceleration_of(P, K, F, aligned, r.delta, r_own, i);
-                        double old_following_pred_a =
-                            idm_acceleration_of(P, K, F, aligned, r.delta, r_own, f_own);
-                        jerk = self_pred_a - self_a +
-                               P.politeness * (new_following_pred_a - new_following_a +
-                                               old_following_pred_a - old_following_a);
+                fired = true;
+                // side_lanes (road/road.py:200-211): id-1 then id+1.  Each admissible candidate
+                // becomes a work item; mobil() itself runs in phase A2 on a dense set of threads.
+                sm.free_t[i] = free_i;
+                sm.acc_own[i] = acc;
+                sm.f_own[i] = (signed char)f_own;
+                sm.r_own[i] = (signed char)r_own;
+                if (!(fabs(r.speed) < 1)) {
+                    for (int k = 0; k < 2; ++k) {
+                        int cand = k == 0 ? lane - 1 : lane + 1;
+                        if (cand < 0 || cand > P.lanes_count - 1) continue;
+                        if (!lane_reachable(P.lanes[cand], r.x, r.y)) continue;
+                        int slot_ = atomicAdd(&sm.n_items, 1);
+                        sm.items[slot_] = (unsigned short)(i | (cand << 8) | (k << 15));
                     }
-                    if (jerk < P.lane_change_min_acc_gain) continue;
-                    tgt1 = cand;
                 }
-                if (tgt1 != tgt0) atomicOr(&sm.chg_to[tgt1][i >> 5], 1u << (i & 31));
             }
         }
-        if (active) sm.tgt1[i] = (unsigned char)tgt1;
-        PHASE_MARK(7);  // phase A
+        PHASE_MARK(7);  // phase A1
         env_sync<TPE>();
-        PHASE_MARK(8);  // barrier after phase A
+        PHASE_MARK(8);  // barrier after phase A1
+
+        // ---- phase A2: mobil(lane_index) (behavior.py:265-324; route None => acceleration-gain
+        // branch) for the queued (vehicle, candidate) items, one item per thread.
+        for (int t = i; t < sm.n_items; t += TPE) {
+            const int it = sm.items[t];
+            const int v = it & 0xff, cand = (it >> 8) & 0x7f, right = it >> 15;
+            const double delta_v = sm.delta[v];
+            int new_preceding, new_following;
+            neighbours(P, F, V, cand, v, new_preceding, new_following);
+            double new_following_pred_a = idm_acceleration_of(P, K, F, aligned, delta_v, new_following, v);
+            if (new_following_pred_a < -P.lane_change_max_braking_imposed) continue;
+            double self_pred_a = sm.free_t[v];
+            if (new_preceding >= 0) self_pred_a -= idm_gap_term(P, K, F, aligned, v, new_preceding);
+            double self_a = sm.acc_own[v];  // acceleration(self, old_preceding)
+            double jerk = self_pred_a - self_a;
+            if (P.politeness != 0.0) {
+                const int f_o = sm.f_own[v], r_o = sm.r_own[v];
+                double new_following_a =
+                    idm_acceleration_of(P, K, F, aligned, delta_v, new_following, new_preceding);
+                double old_following_a = idm_acceleration_of(P, K, F, aligned, delta_v, r_o, v);
+                double old_following_pred_a = idm_acceleration_of(P, K, F, aligned, delta_v, r_o, f_o);
+                jerk = self_pred_a - self_a +
+                       P.politeness * (new_following_pred_a - new_following_a + old_following_pred_a -
+                                       old_following_a);
+            }
+            if (jerk < P.lane_change_min_acc_gain) continue;
+            atomicOr(right ? &sm.ok_right[v >> 5] : &sm.ok_left[v >> 5], 1u << (v & 31));
+        }
+        PHASE_MARK(13);  // phase A2
+        env_sync<TPE>();
+        PHASE_MARK(14);  // barrier after phase A2
 
         // ---- Road.act() phase B (steering + target-lane IDM with the final target), then
         // Road.step(dt): Vehicle.step (kinematics.py:130-177; IDMVehicle.step behavior.py:139-148).
         // The new state goes to the other frame, so no barrier is needed before staging it.
         if (active) {
-            int tgt = tgt1;
+            // both side lanes may pass mobil(); the later one (id+1) wins (behavior.py:252-263)
+            int tgt = tgt0;
+            if (fired) {
+                if (test_bit(sm.ok_right, i))
+                    tgt = lane + 1;
+                else if (test_bit(sm.ok_left, i))
+                    tgt = lane - 1;
+            }
             if (is_mid) {
                 // Ordered resolution of the Gauss-Seidel abort scan (behavior.py:229-244).  Vehicles
                 // act in list order: vehicle j sees the NEW target of every earlier vehicle and the
@@ -704,7 +994,9 @@ highway_step_kernel(const HwyHighwayParams P, const HwyHighwayState S,
                 for (int w = 0; w < NW; ++w) {
                     tmT[w] = F.tm[T][w];
                     lneT[w] = ~F.lane_is[T][w];
-                    chgT[w] = sm.chg_to[T][w];
+                    // vehicles whose MOBIL decision just switched their target to T
+                    chgT[w] = (T > 0 ? sm.ok_right[w] & F.lane_is[T - 1][w] : 0u) |
+                              (T < P.lanes_count - 1 ? sm.ok_left[w] & ~sm.ok_right[w] & F.lane_is[T + 1][w] : 0u);
                     ab[w] = 0;
                 }
 #pragma unroll
@@ -784,12 +1076,16 @@ highway_step_kernel(const HwyHighwayParams P, const HwyHighwayState S,
     PHASE_MARK(11);
     // ---- epilogue: state back to HBM, observation, reward, termination
     const Frame<TPE>& F = sm.f[p];
-    if (active && env_ok) store_vehicle(S, slot, r);
-    float* obs_env = obs + (size_t)e * P.obs_vehicles_count * 5;
+    const size_t obs_off = (size_t)e * P.obs_vehicles_count * 5;
+    float* obs_env = obs + obs_off;
     if (env_ok)
-        kinematics_observe(P, F, sm.key, i, obs_env);
+        kinematics_observe(P, F, sm.key, i, obs_env, (autoreset && final_obs) ? final_obs + obs_off : nullptr);
     else
         env_sync<TPE>();
+    if (i == 0) {
+        sm.done = 0;
+        sm.sp_fallback = 0;
+    }
     if (i == 0 && env_ok) {
         // envs/highway_env.py:100-151
         const int lane = meta_lane(r.meta);
@@ -818,7 +1114,30 @@ highway_step_kernel(const HwyHighwayParams P, const HwyHighwayState S,
         truncated[e] = (uint8_t)(t >= P.duration);
         if (info_speed) info_speed[e] = r.speed;  // abstract.py:200-217 _info
         if (info_crashed) info_crashed[e] = (uint8_t)is_crashed;
+        sm.done = autoreset && (is_crashed || (P.offroad_terminal && !on_road) || t >= P.duration);
     }
+    if (autoreset) {
+        // ---- SameStep autoreset fused into the step: envs that ended re-spawn from their own
+        // numpy stream and return the reset observation (gymnasium AutoresetMode.SAME_STEP)
+        env_sync<TPE>();
+        const bool do_reset = env_ok && sm.done;
+        const bool simple_geometry = aligned && P.lanes[0].start_x == 0.0 && P.lanes[0].dir_x == 1.0;
+        spawn_fused(P, S, sm, e, i, active, do_reset, simple_geometry, r, speed_index);
+        Frame<TPE>& G = sm.f[p ^ 1];
+        if (do_reset) publish(P, G, i, active, r);
+        env_sync<TPE>();
+        if (do_reset) {
+            kinematics_observe(P, G, sm.key, i, obs_env);
+            if (i == 0) {
+                S.time[e] = 0.0;
+                S.speed_index[e] = speed_index;
+            }
+        } else {
+            env_sync<TPE>();
+        }
+    }
+    if (active && env_ok) store_vehicle(S, slot, r);
+    if (autoreset && active && env_ok && sm.done) S.delta[slot] = r.delta;
     PHASE_MARK(12);  // epilogue
 }
 
@@ -1023,11 +1342,25 @@ int step_envs_per_block(int tpe, int n_envs) {
     return epb;
 }
 
+// One-time (per device) fill of the PCG64 jump table used by the fused autoreset.
+int ensure_pcg_jump(cudaStream_t st) {
+    static bool ready[64] = {false};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return fail("%s", "cudaGetDevice failed");
+    if (!ready[dev]) {
+        hwy::pcg_jump_init_kernel<<<1, 1, 0, st>>>();
+        if (check_launch("pcg_jump_init_kernel")) return 1;
+        ready[dev] = true;
+    }
+    return 0;
+}
+
 template <int TPE>
 int launch_step(const HwyHighwayParams* p, const HwyHighwayState* s, const int32_t* action_i,
                 const float* action_f, float* obs, double* reward, uint8_t* terminated,
-                uint8_t* truncated, double* info_speed, uint8_t* info_crashed, int blocks, int epb,
-                cudaStream_t st) {
+                uint8_t* truncated, double* info_speed, uint8_t* info_crashed, int autoreset,
+                float* final_obs, int blocks, int epb, cudaStream_t st) {
+    if (autoreset && ensure_pcg_jump(st)) return 1;
     size_t smem = (size_t)epb * sizeof(hwy::EnvShared<TPE>);
     static thread_local size_t configured = 0;
     if (smem > configured) {
@@ -1037,7 +1370,8 @@ int launch_step(const HwyHighwayParams* p, const HwyHighwayState* s, const int32
         configured = smem;
     }
     hwy::highway_step_kernel<TPE><<<blocks, TPE * epb, smem, st>>>(
-        *p, *s, action_i, action_f, obs, reward, terminated, truncated, info_speed, info_crashed);
+        *p, *s, action_i, action_f, obs, reward, terminated, truncated, info_speed, info_crashed,
+        autoreset, final_obs);
     return 0;
 }
 
@@ -1124,25 +1458,15 @@ int hwy_highway_step(const HwyHighwayParams* p, const HwyHighwayState* s, const 
     int blocks = (s->n_envs + epb - 1) / epb;
     if (tpe == 32) {
         if (launch_step<32>(p, s, action_i, action_f, obs, reward, terminated, truncated, info_speed,
-                            info_crashed, blocks, epb, st)) return 1;
+                            info_crashed, autoreset, final_obs, blocks, epb, st)) return 1;
     } else if (tpe == 64) {
         if (launch_step<64>(p, s, action_i, action_f, obs, reward, terminated, truncated, info_speed,
-                            info_crashed, blocks, epb, st)) return 1;
+                            info_crashed, autoreset, final_obs, blocks, epb, st)) return 1;
     } else {
         if (launch_step<128>(p, s, action_i, action_f, obs, reward, terminated, truncated, info_speed,
-                             info_crashed, blocks, epb, st)) return 1;
+                             info_crashed, autoreset, final_obs, blocks, epb, st)) return 1;
     }
     if (check_launch("highway_step_kernel")) return 1;
-    if (autoreset == HWY_AUTORESET_SAME_STEP) {
-        if (final_obs) {
-            size_t bytes = (size_t)s->n_envs * p->obs_vehicles_count * 5 * sizeof(float);
-            cudaError_t err = cudaMemcpyAsync(final_obs, obs, bytes, cudaMemcpyDeviceToDevice, st);
-            if (err != cudaSuccess) return fail("final_obs copy: %s", cudaGetErrorString(err));
-        }
-        // envs with terminated | truncated restart from their own RNG stream; obs := reset obs
-        if (launch_reset(p, s, terminated, truncated, 1, st)) return 1;
-        return launch_observe(p, s, terminated, truncated, 1, obs, st);
-    }
     return 0;
 }
 

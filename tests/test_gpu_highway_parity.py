@@ -185,8 +185,45 @@ def test_autoreset_same_step_matches_oracle():
             assert np.array_equal(sd["lane"][done], ob.a["lane"][done])
             assert np.array_equal(obs.cpu().numpy()[done], o_obs[done])
             assert np.all(sd["time"][done] == 0)
+            assert np.array_equal(info["final_obs"].cpu().numpy()[~done], obs.cpu().numpy()[~done])
         assert np.max(np.abs(obs.cpu().numpy() - o_obs)) <= 1e-6
+        # the numpy PCG64 streams stay bit-identical (state, inc, buffered 32-bit half)
+        rng_w = sd["rng"]
+        assert np.array_equal(rng_w[0], ob.rng["state_hi"]) and np.array_equal(rng_w[1], ob.rng["state_lo"])
+        assert np.array_equal(rng_w[2], ob.rng["inc_hi"]) and np.array_equal(rng_w[3], ob.rng["inc_lo"])
+        assert np.array_equal(rng_w[4] >> np.uint64(32), ob.rng["has_uint32"].astype(np.uint64))
+        hb_ = ob.rng["has_uint32"] == 1
+        assert np.array_equal((rng_w[4] & np.uint64(0xFFFFFFFF))[hb_], ob.rng["uinteger"][hb_].astype(np.uint64))
     assert resets > n  # every env ended at least once (duration 30 < 40 steps)
+
+
+@pytest.mark.parametrize("name,n", [("highway_fast_v50", 64), ("highway_v100_continuous", 16), ("highway_v50", 32)])
+def test_autoreset_streams_other_configs(name, n):
+    """Fused autoreset on the other thread mappings (64 / 128 threads per env, 4 lanes)."""
+    g, cfg, oc, ob = _oracle_pair(name, n, 11000)
+    cfg = dict(cfg)
+    cfg["duration"] = 3  # force frequent truncation
+    oc = ho.cfg_from_dict(cfg)
+    ob = ho.OracleBatch(oc, n, seeds=range(11000, 11000 + n), threads=8)
+    env = make_env(cfg, n)
+    obs0, _ = env.reset(seed=11000)
+    assert np.array_equal(obs0.cpu().numpy(), ob.reset())
+    rng = np.random.default_rng(5)
+    for t in range(8):
+        env.load_state_dict({k: ob.a[k].copy() for k in ob.a})
+        if oc.action_type == 0:
+            act = rng.integers(0, 5, size=n).astype(np.int32)
+        else:
+            act = rng.uniform(-1, 1, size=(n, 2)).astype(np.float32)
+        o_obs, o_rew, o_term, o_trunc = ob.step(act, autoreset=True)
+        obs, rew, term, trunc, info = env.step(act)
+        done = (o_term | o_trunc).astype(bool)
+        sd = env.state_dict()
+        for k in ("x", "y", "heading", "speed", "timer", "delta", "target_speed"):
+            assert np.array_equal(sd[k][done], ob.a[k][done]), (t, k)
+        assert np.array_equal(sd["lane"][done], ob.a["lane"][done])
+        assert np.array_equal(obs.cpu().numpy()[done], o_obs[done])
+        assert np.array_equal(sd["rng"][0], ob.rng["state_hi"]) and np.array_equal(sd["rng"][1], ob.rng["state_lo"])
 
 
 def test_abi_errors_are_loud():

@@ -1,3 +1,5 @@
+"""Per-phase cycle shares of the step kernel (needs a -DHWY_PHASE_TIMING build, see hwy_highway.cu):
+  nvcc ... -DHWY_PHASE_TIMING -o highwayenv_b200/csrc/variants/lib_timing.so ...; HWYB200_LIB=that python tools/phase_probe.py"""
 import ctypes as C, os, sys
 sys.path.insert(0, os.getcwd())
 import torch
@@ -14,7 +16,7 @@ for t in range(10): env.step(acts[t])
 torch.cuda.synchronize(); lib.hwy_debug_phase_cycles(buf)
 for t in range(10,40): env.step(acts[t])
 torch.cuda.synchronize(); lib.hwy_debug_phase_cycles(buf)
-names = ["load+static","publish","bar(publish)","build(rank/masks/sweep1)","bar(build)","sweep2","ego action","phase A","bar(phaseA)","phase B","integrate","(loop exit)","epilogue"]
+names = ["load+static","publish","bar(publish)","build(rank/masks/sweep1)","bar(build)","sweep2","ego action","phase A1","bar(A1)","phase B","integrate","(loop exit)","epilogue","phase A2 (MOBIL items)","bar(A2)"]
 tot = sum(buf)
 for k,n in enumerate(names): print(f"{n:28s} {buf[k]/tot*100:5.1f}%")
 print("cycles per warp per step:", tot/(30*4096*2))
