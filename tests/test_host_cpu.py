@@ -1,0 +1,178 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/hwyb200.h declares,
+the host mirror's config / plugin logic, loud failure without a GPU, and the world_size-2 gloo
+path of the env-range sharding."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from highwayenv_b200 import _native as N
+
+    lib = N.load()
+    hdr = open(os.path.join(ROOT, "include", "hwyb200.h")).read()
+    declared = set(re.findall(r"\b(hwy_[a-z_0-9]+)\s*\(", hdr))
+    assert {"hwy_highway_step", "hwy_highway_reset", "hwy_highway_observe", "hwy_highway_autoreset",
+            "hwy_highway_slot_stride", "hwy_abi_version", "hwy_last_error", "hwy_launch_count"} <= declared
+    for sym in declared:
+        assert getattr(lib, sym) is not None, sym
+    assert lib.hwy_abi_version() == N.HWY_ABI_VERSION
+    assert lib.hwy_highway_slot_stride(51) == 52 and lib.hwy_highway_slot_stride(20) == 20
+
+
+def test_struct_layout_matches_header():
+    """ctypes mirrors must have the C sizes (gcc as the referee)."""
+    import ctypes as C
+    import tempfile
+
+    from highwayenv_b200 import _native as N
+
+    src = '#include <stdio.h>\n#include "hwyb200.h"\nint main(){printf("%zu %zu %zu\\n", sizeof(HwyHighwayParams), sizeof(HwyHighwayState), sizeof(HwyStraightLane));return 0;}\n'
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        exe = os.path.join(d, "t")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", exe])
+        sizes = [int(x) for x in subprocess.check_output([exe]).split()]
+    assert sizes == [C.sizeof(N.HwyHighwayParams), C.sizeof(N.HwyHighwayState), C.sizeof(N.HwyStraightLane)]
+
+
+def test_abi_validation_without_gpu():
+    import ctypes as C
+
+    from highwayenv_b200 import _native as N
+
+    lib = N.load()
+    assert lib.hwy_highway_step(None, None, None, None, None, None, None, None, None, None, 0, None, None) != 0
+    assert b"null" in lib.hwy_last_error()
+    p, s = N.HwyHighwayParams(), N.HwyHighwayState()
+    p.n_vehicles = 500
+    assert lib.hwy_highway_observe(C.byref(p), C.byref(s), None, None) != 0
+    assert b"n_vehicles" in lib.hwy_last_error()
+
+
+def test_default_configs_match_reference_values():
+    from highwayenv_b200.config import default_config
+
+    fast, hw = default_config("highway-fast-v0"), default_config("highway-v0")
+    # envs/highway_env.py:25-53,162-175 over envs/common/abstract.py:102-125
+    assert (fast["simulation_frequency"], fast["lanes_count"], fast["vehicles_count"], fast["duration"],
+            fast["ego_spacing"]) == (5, 3, 20, 30, 1.5)
+    assert (hw["simulation_frequency"], hw["lanes_count"], hw["vehicles_count"], hw["duration"],
+            hw["ego_spacing"]) == (15, 4, 50, 40, 2)
+    for c in (fast, hw):
+        assert c["policy_frequency"] == 1 and c["collision_reward"] == -1
+        assert c["reward_speed_range"] == [20, 30] and c["observation"] == {"type": "Kinematics"}
+        assert c["other_vehicles_type"] == "highway_env.vehicle.behavior.IDMVehicle"
+
+
+def test_golden_config_equals_our_defaults():
+    """The defaults restated in config.py equal the reference env's merged config dict."""
+    from highwayenv_b200.config import default_config
+    from parity_utils import load_golden
+
+    for name, env_id, over in (("highway_fast_v20", "highway-fast-v0", {}),
+                               ("highway_fast_v50", "highway-fast-v0", {"vehicles_count": 50}),
+                               ("highway_v50", "highway-v0", {})):
+        ref = dict(load_golden(name)["config"])
+        ref.pop("_env_id"), ref.pop("_others_check_collisions")
+        ours = default_config(env_id)
+        ours.update(over)
+        ours["offscreen_rendering"] = ref["offscreen_rendering"]  # set by configure() from render_mode
+        assert ours == ref, name
+
+
+def test_update_config_validation_rule():
+    from highwayenv_b200.config import update_config
+
+    cfg = {"observation": {"type": "Kinematics", "vehicles_count": 5}, "x": 1}
+    with pytest.raises(AssertionError):  # nested mapping must redefine every key (utils.py:453-464)
+        update_config(cfg, {"observation": {"type": "Kinematics"}})
+    update_config(cfg, {"observation": {"type": "Kinematics", "vehicles_count": 7}, "x": 2})
+    assert cfg["observation"]["vehicles_count"] == 7 and cfg["x"] == 2
+
+
+def test_plugin_factories():
+    from highwayenv_b200.envs.common.action import action_factory
+    from highwayenv_b200.envs.common.observation import observation_factory
+
+    a = action_factory(None, {"type": "DiscreteMetaAction"})
+    assert a.space().n == 5 and a.actions[3] == "FASTER"
+    c = action_factory(None, {"type": "ContinuousAction"})
+    assert c.space().shape == (2,) and c.space().dtype == np.float32
+    o = observation_factory(None, {"type": "Kinematics", "vehicles_count": 7})
+    assert o.space().shape == (7, 5) and o.space().dtype == np.float32
+    with pytest.raises(ValueError, match="Unknown action type"):
+        action_factory(None, {"type": "Nope"})
+    with pytest.raises(ValueError, match="Unknown observation type"):
+        observation_factory(None, {"type": "Nope"})
+    with pytest.raises(NotImplementedError):
+        observation_factory(None, {"type": "OccupancyGrid"})
+
+
+def test_no_silent_cpu_fallback():
+    import torch
+
+    import highwayenv_b200 as hb
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        hb.make("highway-fast-v0", num_envs=2)
+    with pytest.raises(KeyError):
+        hb.make("parking-v0")
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "highwayenv_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dp, f)).read()
+                assert "hwy_oracle" not in text and "ref_harness" not in text, f
+
+
+def test_env_range_and_split():
+    from highwayenv_b200.parallel import env_range, split_envs
+
+    assert env_range(0, 8, 8192) == (0, 8192) and env_range(7, 8, 8192) == (57344, 65536)
+    assert split_envs(10, 4) == (3, 3, 2, 2) and sum(split_envs(65536, 8)) == 65536
+    with pytest.raises(ValueError):
+        env_range(8, 8, 1)
+
+
+_GLOO_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from highwayenv_b200.parallel import all_gather_batch, env_range
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank = dist.get_rank()
+E = 3
+lo, hi = env_range(rank, 2, E)
+local = (torch.arange(lo, hi, dtype=torch.float32).view(E, 1, 1) * torch.ones(E, 5, 5))
+full = all_gather_batch(local)
+assert full.shape == (6, 5, 5)
+assert torch.equal(full[:, 0, 0], torch.arange(6, dtype=torch.float32)), full[:, 0, 0]
+# value = all units / max-over-ranks time, as bench.py computes it
+t = torch.tensor([1.0 + rank], dtype=torch.float64)
+dist.all_reduce(t, op=dist.ReduceOp.MAX)
+assert t.item() == 2.0
+dist.barrier(); dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_gloo_world_size_2_gather(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_WORKER)
+    port = str(29600 + os.getpid() % 300)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "ok 0" in outs[0] and "ok 1" in outs[1]
