@@ -38,12 +38,19 @@ CASES = {
         12,
         "box2",
     ),
+    # roundabout-v0 defaults (Kinematics absolute) and BASELINE configs[3] shape (TimeToCollision)
+    "roundabout_kin": ("roundabout-v0", None, list(range(400, 406)), 11, "discrete5"),
+    "roundabout_ttc": ("roundabout-v0", {"observation": {"type": "TimeToCollision", "horizon": 10}},
+                       list(range(500, 506)), 11, "discrete5"),
 }
 
 
 def main() -> None:
     os.makedirs(OUT, exist_ok=True)
+    only = sys.argv[1:]
     for name, (env_id, over, seeds, T, akind) in CASES.items():
+        if only and name not in only:
+            continue
         t0 = time.time()
         rng = np.random.default_rng(abs(hash(name)) % (2**31) if False else sum(map(ord, name)))
         per_seed = []
@@ -59,6 +66,9 @@ def main() -> None:
         import json
 
         cfg = dict(env.config)
+        if not env_id.startswith("highway"):
+            env.reset(seed=0)
+            out.update(rh.dump_network(env))
         cfg["_others_check_collisions"] = 0 if env_id == "highway-fast-v0" else 1
         cfg["_env_id"] = env_id
         out["config_json"] = np.array(json.dumps(cfg))
@@ -68,7 +78,7 @@ def main() -> None:
               f"({os.path.getsize(path)/1e3:.0f} kB, {time.time()-t0:.1f}s)")
 
     # reset-only fixtures: pins the numpy-PCG64 spawn restatement on many seeds
-    for name, (env_id, over) in {
+    for name, (env_id, over) in {} if only else {
         "reset_highway_fast_v50": ("highway-fast-v0", {"vehicles_count": 50}),
         "reset_highway_v100": ("highway-v0", {"vehicles_count": 100, "action": {"type": "ContinuousAction"}}),
     }.items():

@@ -1,0 +1,877 @@
+/*
+ * net_oracle.c — scalar CPU restatement of the HighwayEnv hot path on a general road network
+ * (roundabout-v0).  TEST INFRASTRUCTURE ONLY — see net_oracle.h.  Same build flags and numpy
+ * fused-operation conventions as hwy_oracle.c.  Paths relative to /root/reference/highway_env.
+ */
+#include "net_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define VEH_LENGTH 5.0
+#define VEH_WIDTH 2.0
+#define MAX_SPEED 40.0
+#define MIN_SPEED (-40.0)
+#define LANE_VEHICLE_LENGTH 5.0
+static const double TAU_ACC = 0.6, TAU_HEADING = 0.2, TAU_LATERAL = 0.6;
+#define TAU_PURSUIT (0.5 * TAU_HEADING)
+#define KP_A (1 / TAU_ACC)
+#define KP_HEADING (1 / TAU_HEADING)
+#define KP_LATERAL (1 / TAU_LATERAL)
+#define MAX_STEERING_ANGLE (M_PI / 3)
+
+/* ------------------------------------------------------------------ utils.py */
+
+static inline double dot2(double a0, double a1, double b0, double b1) {
+    return fma(a1, b1, a0 * b0); /* np.dot on 2-vectors, see file header */
+}
+static inline double norm2(double a0, double a1) { return sqrt(dot2(a0, a1, a0, a1)); }
+static inline double clipd(double x, double lo, double hi) { /* np.clip */
+    return fmin(fmax(x, lo), hi);
+}
+
+/* utils.py:50-56 */
+static double orc_not_zero(double x) {
+    const double eps = 1e-2;
+    if (fabs(x) > eps) return x;
+    return x >= 0 ? eps : -eps;
+}
+
+/* Python / numpy floored float modulo (npy_divmod) */
+static inline double py_mod(double a, double b) {
+    double m = fmod(a, b);
+    if (m != 0.0) {
+        if ((b < 0) != (m < 0)) m += b;
+    } else {
+        m = copysign(0.0, b);
+    }
+    return m;
+}
+
+/* utils.py:59-60 */
+static double orc_wrap_to_pi(double x) { return py_mod(x + M_PI, 2 * M_PI) - M_PI; }
+
+/* utils.py:31-33 */
+static inline double lmap(double v, double x0, double x1, double y0, double y1) {
+    return y0 + (v - x0) * (y1 - y0) / (x1 - x0);
+}
+
+/* utils.py:77-95 point_in_rotated_rectangle (rotation by -angle... r = [[c,-s],[s,c]],
+ * ru = r.dot(point - center): matrix-vector through BLAS gemv; rounding detail is
+ * irrelevant to the inclusive-bound KATs, plain expressions are used). */
+static int point_in_rotated_rectangle(double px, double py, double cx, double cy, double length,
+                                      double width, double angle) {
+    double c = cos(angle), s = sin(angle);
+    double dx = px - cx, dy = py - cy;
+    double rx = c * dx + (-s) * dy, ry = s * dx + c * dy;
+    return (-length / 2 <= rx && rx <= length / 2 && -width / 2 <= ry && ry <= width / 2);
+}
+
+/* utils.py:160-174 has_corner_inside with rect_corners(include_midpoints, include_center) :128-157 */
+static int has_corner_inside(double c1x, double c1y, double l1, double w1, double a1, double c2x,
+                             double c2y, double l2, double w2, double a2) {
+    double hl = l1 / 2, hw = w1 / 2;
+    const double pts[9][2] = {{-hl, -hw}, {-hl, hw}, {hl, hw},  {hl, -hw}, {0, 0},
+                              {-hl, 0},   {hl, 0},   {0, -hw}, {0, hw}};
+    double c = cos(a1), s = sin(a1);
+    for (int k = 0; k < 9; k++) {
+        double px = c * pts[k][0] + (-s) * pts[k][1] + c1x;
+        double py = s * pts[k][0] + c * pts[k][1] + c1y;
+        if (point_in_rotated_rectangle(px, py, c2x, c2y, l2, w2, a2)) return 1;
+    }
+    return 0;
+}
+
+/* utils.py:115-125 */
+static int orc_rotated_rectangles_intersect(double c1x, double c1y, double l1, double w1, double a1,
+                                     double c2x, double c2y, double l2, double w2, double a2) {
+    return has_corner_inside(c1x, c1y, l1, w1, a1, c2x, c2y, l2, w2, a2) ||
+           has_corner_inside(c2x, c2y, l2, w2, a2, c1x, c1y, l1, w1, a1);
+}
+
+/* utils.py:177-185 */
+static void project_polygon(const double p[5][2], double ax, double ay, double *mn, double *mx) {
+    double lo = 0, hi = 0;
+    for (int k = 0; k < 5; k++) {
+        double pr = dot2(p[k][0], p[k][1], ax, ay);
+        if (k == 0 || pr < lo) lo = pr;
+        if (k == 0 || pr > hi) hi = pr;
+    }
+    *mn = lo;
+    *mx = hi;
+}
+
+/* utils.py:188-193 */
+static inline double interval_distance(double min_a, double max_a, double min_b, double max_b) {
+    return min_a < min_b ? min_b - max_a : min_a - max_b;
+}
+
+/* utils.py:196-241 are_polygons_intersecting (SAT with velocity extension) */
+static void orc_polygons_intersecting(const double a[5][2], const double b[5][2], double dax, double day,
+                               double dbx, double dby, int *intersecting_out,
+                               int *will_intersect_out, double trans[2]) {
+    int intersecting = 1, will_intersect = 1;
+    double min_distance = INFINITY;
+    double tax = 0, tay = 0;
+    /* centre difference a[:-1].mean(axis=0) - b[:-1].mean(axis=0): sequential row sum / 4 */
+    double cax = (((a[0][0] + a[1][0]) + a[2][0]) + a[3][0]) / 4.0;
+    double cay = (((a[0][1] + a[1][1]) + a[2][1]) + a[3][1]) / 4.0;
+    double cbx = (((b[0][0] + b[1][0]) + b[2][0]) + b[3][0]) / 4.0;
+    double cby = (((b[0][1] + b[1][1]) + b[2][1]) + b[3][1]) / 4.0;
+    double dcx = cax - cbx, dcy = cay - cby;
+    for (int poly = 0; poly < 2; poly++) {
+        const double(*pg)[2] = poly == 0 ? a : b;
+        for (int e = 0; e < 4; e++) {
+            double nx = -pg[e + 1][1] + pg[e][1];
+            double ny = pg[e + 1][0] - pg[e][0];
+            double nn = norm2(nx, ny);
+            nx /= nn;
+            ny /= nn;
+            double min_a, max_a, min_b, max_b;
+            project_polygon(a, nx, ny, &min_a, &max_a);
+            project_polygon(b, nx, ny, &min_b, &max_b);
+            if (interval_distance(min_a, max_a, min_b, max_b) > 0) intersecting = 0;
+            double vp = dot2(nx, ny, dax - dbx, day - dby);
+            if (vp < 0)
+                min_a += vp;
+            else
+                max_a += vp;
+            double distance = interval_distance(min_a, max_a, min_b, max_b);
+            if (distance > 0) will_intersect = 0;
+            if (!intersecting && !will_intersect) break; /* leaves the inner loop only */
+            if (fabs(distance) < min_distance) {
+                min_distance = fabs(distance);
+                if (dot2(dcx, dcy, nx, ny) > 0) {
+                    tax = nx;
+                    tay = ny;
+                } else {
+                    tax = -nx;
+                    tay = -ny;
+                }
+            }
+        }
+    }
+    *intersecting_out = intersecting;
+    *will_intersect_out = will_intersect;
+    if (will_intersect) {
+        trans[0] = min_distance * tax;
+        trans[1] = min_distance * tay;
+    } else {
+        trans[0] = trans[1] = 0.0;
+    }
+}
+
+
+/* ------------------------------------------------------------------ lanes (road/lane.py) */
+
+/* local_coordinates: StraightLane :205-209, SineLane :285-289, CircularLane :351-358 */
+void net_lane_local(const NetLane *L, double x, double y, double *s, double *lat) {
+    if (L->type == NET_LANE_CIRCULAR) {
+        double ddx = x - L->cx, ddy = y - L->cy;
+        double phi = atan2(ddy, ddx);
+        phi = L->start_phase + orc_wrap_to_pi(phi - L->start_phase);
+        double r = norm2(ddx, ddy);
+        *s = L->direction * (phi - L->start_phase) * L->radius;
+        *lat = L->direction * (L->radius - r);
+        return;
+    }
+    double ddx = x - L->sx, ddy = y - L->sy;
+    double lon = dot2(ddx, ddy, L->dx, L->dy);
+    double la = dot2(ddx, ddy, L->lx, L->ly);
+    if (L->type == NET_LANE_SINE) la = la - L->amplitude * sin(L->pulsation * lon + L->phase);
+    *s = lon;
+    *lat = la;
+}
+/* position: StraightLane :192-197, SineLane :268-273, CircularLane :338-342 */
+void net_lane_position(const NetLane *L, double s, double lat, double *x, double *y) {
+    if (L->type == NET_LANE_CIRCULAR) {
+        double phi = L->direction * s / L->radius + L->start_phase;
+        double rr = L->radius - lat * L->direction;
+        *x = L->cx + rr * cos(phi);
+        *y = L->cy + rr * sin(phi);
+        return;
+    }
+    if (L->type == NET_LANE_SINE) lat = lat + L->amplitude * sin(L->pulsation * s + L->phase);
+    *x = (L->sx + s * L->dx) + lat * L->lx;
+    *y = (L->sy + s * L->dy) + lat * L->ly;
+}
+/* heading_at: StraightLane :199-200, SineLane :275-280, CircularLane :344-347 */
+double net_lane_heading_at(const NetLane *L, double s) {
+    if (L->type == NET_LANE_CIRCULAR) {
+        double phi = L->direction * s / L->radius + L->start_phase;
+        return phi + M_PI / 2 * L->direction;
+    }
+    if (L->type == NET_LANE_SINE)
+        return L->heading + atan(L->amplitude * L->pulsation * cos(L->pulsation * s + L->phase));
+    return L->heading;
+}
+static inline double lane_s(const NetLane *L, double x, double y) {
+    double s, lat;
+    net_lane_local(L, x, y, &s, &lat);
+    return s;
+}
+/* :80-102 */
+static inline int lane_on_lane(const NetLane *L, double s, double lat, double margin) {
+    return fabs(lat) <= L->width / 2 + margin && -LANE_VEHICLE_LENGTH <= s &&
+           s < L->length + LANE_VEHICLE_LENGTH;
+}
+/* :104-118 */
+static inline int lane_reachable(const NetLane *L, double x, double y) {
+    if (L->forbidden) return 0;
+    double s, lat;
+    net_lane_local(L, x, y, &s, &lat);
+    return fabs(lat) <= 2 * L->width && 0 <= s && s < L->length + LANE_VEHICLE_LENGTH;
+}
+/* :120-125 after_end (longitudinal recomputed) */
+static inline int lane_after_end(const NetLane *L, double x, double y) {
+    return lane_s(L, x, y) > L->length - LANE_VEHICLE_LENGTH / 2;
+}
+/* :127-130 distance */
+static inline double lane_distance(const NetLane *L, double x, double y) {
+    double s, r;
+    net_lane_local(L, x, y, &s, &r);
+    return fabs(r) + fmax(s - L->length, 0) + fmax(0 - s, 0);
+}
+/* :132-147 distance_with_heading / local_angle */
+static inline double lane_distance_with_heading(const NetLane *L, double x, double y, double h) {
+    double s, r;
+    net_lane_local(L, x, y, &s, &r);
+    double angle = fabs(orc_wrap_to_pi(h - net_lane_heading_at(L, s)));
+    return fabs(r) + fmax(s - L->length, 0) + fmax(0 - s, 0) + 1.0 * angle;
+}
+/* road/road.py:55-71 get_closest_lane_index */
+int net_closest_lane(const NetGraph *g, double x, double y, double h) {
+    int best = 0;
+    double bd = 0;
+    for (int l = 0; l < g->n_lanes; l++) {
+        double d = lane_distance_with_heading(&g->lanes[l], x, y, h);
+        if (l == 0 || d < bd) {
+            bd = d;
+            best = l;
+        }
+    }
+    return best;
+}
+
+/* ------------------------------------------------------------------ world */
+
+typedef struct {
+    const NetGraph *g;
+    const NetCfg *c;
+    NetState *s;
+    double *act_steer, *act_accel;
+    int V;
+} World;
+
+#define RT_FROM(e) ((e)&0xff)
+#define RT_TO(e) (((e) >> 8) & 0xff)
+#define RT_ID(e) ((((e) >> 16) & 0xff) - 1) /* -1 = None */
+
+static inline const NetLane *LANE(const World *w, int idx) { return &w->g->lanes[idx]; }
+
+/* lane table index of road (from, to): -1 if the road does not exist */
+static int road_first(const NetGraph *g, int from, int to) {
+    for (int k = 0; k < g->succ_count[from]; k++) {
+        int f = g->succ[from][k];
+        if (g->lanes[f].to_node == to) return f;
+    }
+    return -1;
+}
+
+/* vehicle/objects.py:183-198 */
+static inline double lane_distance_to(const World *w, int self, int other) {
+    const NetLane *L = LANE(w, w->s->lane[self]);
+    return lane_s(L, w->s->x[other], w->s->y[other]) - lane_s(L, w->s->x[self], w->s->y[self]);
+}
+
+/* road/road.py:483-547 neighbour_vehicles (same-segment search) */
+static void neighbour_vehicles(const World *w, int veh, int lane_idx, int *front, int *rear) {
+    const NetLane *L = LANE(w, lane_idx);
+    double s = lane_s(L, w->s->x[veh], w->s->y[veh]);
+    double s_front = 0, s_rear = 0;
+    int v_front = -1, v_rear = -1;
+    for (int v = 0; v < w->V; v++) {
+        if (v == veh) continue;
+        double s_v, lat_v;
+        net_lane_local(L, w->s->x[v], w->s->y[v], &s_v, &lat_v);
+        if (!lane_on_lane(L, s_v, lat_v, 1.0)) continue;
+        if (s <= s_v && (v_front < 0 || s_v <= s_front)) {
+            s_front = s_v;
+            v_front = v;
+        }
+        if (s_v < s && (v_rear < 0 || s_v > s_rear)) {
+            s_rear = s_v;
+            v_rear = v;
+        }
+    }
+    *front = v_front;
+    *rear = v_rear;
+}
+
+/* vehicle/behavior.py:192-217 */
+static double desired_gap(const World *w, int ego, int front) {
+    const NetCfg *c = w->c;
+    const NetState *s = w->s;
+    double ab = -c->comfort_acc_max * c->comfort_acc_min;
+    double ce = cos(s->heading[ego]), se = sin(s->heading[ego]);
+    double cf = cos(s->heading[front]), sf = sin(s->heading[front]);
+    double dvx = s->speed[ego] * ce - s->speed[front] * cf;
+    double dvy = s->speed[ego] * se - s->speed[front] * sf;
+    double dv = dot2(dvx, dvy, ce, se);
+    return c->distance_wanted + s->speed[ego] * c->time_wanted + s->speed[ego] * dv / (2 * sqrt(ab));
+}
+
+/* vehicle/behavior.py:150-190 */
+static double idm_acceleration(const World *w, int self_, int ego, int front) {
+    const NetCfg *c = w->c;
+    const NetState *s = w->s;
+    if (ego < 0) return 0;
+    double ego_target_speed = clipd(s->target_speed[ego], 0, LANE(w, s->lane[ego])->speed_limit);
+    double acceleration =
+        c->comfort_acc_max *
+        (1 - pow(fmax(s->speed[ego], 0) / fabs(orc_not_zero(ego_target_speed)), s->delta[self_]));
+    if (front >= 0) {
+        double d = lane_distance_to(w, ego, front);
+        double q = desired_gap(w, ego, front) / orc_not_zero(d);
+        acceleration -= c->comfort_acc_max * pow(q, 2);
+    }
+    return acceleration;
+}
+
+/* vehicle/controller.py:145-187 */
+static double steering_control(const World *w, int v, int target_lane) {
+    const NetState *s = w->s;
+    const NetLane *L = LANE(w, target_lane);
+    double lc_s, lc_lat;
+    net_lane_local(L, s->x[v], s->y[v], &lc_s, &lc_lat);
+    double lane_next_coords = lc_s + s->speed[v] * TAU_PURSUIT;
+    double lane_future_heading = net_lane_heading_at(L, lane_next_coords);
+    double lateral_speed_command = -KP_LATERAL * lc_lat;
+    double heading_command = asin(clipd(lateral_speed_command / orc_not_zero(s->speed[v]), -1, 1));
+    double heading_ref = lane_future_heading + clipd(heading_command, -M_PI / 4, M_PI / 4);
+    double heading_rate_command = KP_HEADING * orc_wrap_to_pi(heading_ref - s->heading[v]);
+    double slip_angle =
+        asin(clipd(VEH_LENGTH / 2 / orc_not_zero(s->speed[v]) * heading_rate_command, -1, 1));
+    double steering_angle = atan(2 * tan(slip_angle));
+    return clipd(steering_angle, -MAX_STEERING_ANGLE, MAX_STEERING_ANGLE);
+}
+
+/* road/road.py:138-157 next_lane_given_next_road; next_id < 0 == None */
+static int next_lane_given_next_road(const NetGraph *g, int cur, int next_first, int next_id,
+                                     double px, double py, double *dist) {
+    const NetLane *C = &g->lanes[cur];
+    int n_next = g->lanes[next_first].road_count;
+    if (C->road_count == n_next) {
+        if (next_id < 0) next_id = C->lane_id;
+    } else {
+        int best = 0;
+        double bd = 0;
+        for (int l = 0; l < n_next; l++) {
+            double d = lane_distance(&g->lanes[next_first + l], px, py);
+            if (l == 0 || d < bd) {
+                bd = d;
+                best = l;
+            }
+        }
+        next_id = best;
+    }
+    *dist = lane_distance(&g->lanes[next_first + next_id], px, py);
+    return next_id;
+}
+
+/* road/road.py:73-136 next_lane; mutates the vehicle's route (pop(0)) */
+static int next_lane(World *w, int v, int cur) {
+    const NetGraph *g = w->g;
+    NetState *s = w->s;
+    const NetLane *C = &g->lanes[cur];
+    int32_t *route = s->route + (size_t)v * NET_MAX_ROUTE;
+    int *rlen = &s->route_len[v];
+    int next_first = -1, next_id = -1;
+    if (*rlen > 0) {
+        if (RT_FROM(route[0]) == C->from_node && RT_TO(route[0]) == C->to_node) {
+            for (int k = 1; k < *rlen; k++) route[k - 1] = route[k];
+            (*rlen)--;
+        }
+        if (*rlen > 0 && RT_FROM(route[0]) == C->to_node) {
+            next_first = road_first(g, RT_FROM(route[0]), RT_TO(route[0]));
+            next_id = RT_ID(route[0]);
+        }
+        /* else: logger.warning only */
+    }
+    double lon, lat, px, py;
+    net_lane_local(C, s->x[v], s->y[v], &lon, &lat);
+    net_lane_position(C, lon, 0, &px, &py);
+    if (next_first < 0) {
+        int n_succ = g->succ_count[C->to_node];
+        if (n_succ == 0) return cur; /* KeyError: graph[_to] */
+        int best_first = -1, best_id = -1;
+        double bd = 0;
+        for (int k = 0; k < n_succ; k++) {
+            int nf = g->succ[C->to_node][k];
+            double d;
+            int nid = next_lane_given_next_road(g, cur, nf, next_id, px, py, &d);
+            if (k == 0 || d < bd) { /* min(): first minimum */
+                bd = d;
+                best_first = nf;
+                best_id = nid;
+            }
+        }
+        return best_first + best_id;
+    }
+    double d;
+    next_id = next_lane_given_next_road(g, cur, next_first, next_id, px, py, &d);
+    return next_first + next_id;
+}
+
+/* vehicle/controller.py:135-143 */
+static void follow_road(World *w, int v) {
+    NetState *s = w->s;
+    if (lane_after_end(LANE(w, s->target_lane[v]), s->x[v], s->y[v]))
+        s->target_lane[v] = next_lane(w, v, s->target_lane[v]);
+}
+
+static inline int isign(int a) { return (a > 0) - (a < 0); }
+
+/* vehicle/behavior.py:265-324 */
+static int mobil(const World *w, int v, int lane_index) {
+    const NetCfg *c = w->c;
+    const NetState *s = w->s;
+    int new_preceding, new_following;
+    neighbour_vehicles(w, v, lane_index, &new_preceding, &new_following);
+    double new_following_a = idm_acceleration(w, v, new_following, new_preceding);
+    double new_following_pred_a = idm_acceleration(w, v, new_following, v);
+    if (new_following_pred_a < -c->lane_change_max_braking_imposed) return 0;
+    int old_preceding, old_following;
+    neighbour_vehicles(w, v, s->lane[v], &old_preceding, &old_following);
+    double self_pred_a = idm_acceleration(w, v, v, new_preceding);
+    const int32_t *route = s->route + (size_t)v * NET_MAX_ROUTE;
+    if (s->route_len[v] > 0 && RT_ID(route[0]) >= 0) {
+        int tid = w->g->lanes[s->target_lane[v]].lane_id;
+        int cid = w->g->lanes[lane_index].lane_id;
+        if (isign(cid - tid) != isign(RT_ID(route[0]) - tid)) return 0;
+        if (self_pred_a < -c->lane_change_max_braking_imposed) return 0;
+    } else {
+        double self_a = idm_acceleration(w, v, v, old_preceding);
+        double old_following_a = idm_acceleration(w, v, old_following, v);
+        double old_following_pred_a = idm_acceleration(w, v, old_following, old_preceding);
+        double jerk = self_pred_a - self_a +
+                      c->politeness * (new_following_pred_a - new_following_a +
+                                       old_following_pred_a - old_following_a);
+        if (jerk < c->lane_change_min_acc_gain) return 0;
+    }
+    return 1;
+}
+
+/* vehicle/behavior.py:219-263 */
+static void change_lane_policy(World *w, int v) {
+    const NetCfg *c = w->c;
+    NetState *s = w->s;
+    const NetGraph *g = w->g;
+    if (s->lane[v] != s->target_lane[v]) {
+        const NetLane *A = &g->lanes[s->lane[v]], *B = &g->lanes[s->target_lane[v]];
+        if (A->from_node == B->from_node && A->to_node == B->to_node) {
+            for (int o = 0; o < w->V; o++) {
+                if (o != v && s->lane[o] != s->target_lane[v] && s->target_lane[o] == s->target_lane[v]) {
+                    double d = lane_distance_to(w, v, o);
+                    double d_star = desired_gap(w, v, o);
+                    if (0 < d && d < d_star) {
+                        s->target_lane[v] = s->lane[v];
+                        break;
+                    }
+                }
+            }
+        }
+        return;
+    }
+    if (!(c->lane_change_delay < s->timer[v])) return;
+    s->timer[v] = 0;
+    const NetLane *A = &g->lanes[s->lane[v]];
+    int cand[2], nc = 0; /* road/road.py:200-211 side_lanes */
+    if (A->lane_id > 0) cand[nc++] = s->lane[v] - 1;
+    if (A->lane_id < A->road_count - 1) cand[nc++] = s->lane[v] + 1;
+    for (int k = 0; k < nc; k++) {
+        if (!lane_reachable(&g->lanes[cand[k]], s->x[v], s->y[v])) continue;
+        if (fabs(s->speed[v]) < 1) continue;
+        if (mobil(w, v, cand[k])) s->target_lane[v] = cand[k];
+    }
+}
+
+/* vehicle/behavior.py:93-137 */
+static void idm_act(World *w, int v) {
+    const NetCfg *c = w->c;
+    NetState *s = w->s;
+    if (s->crashed[v]) return;
+    follow_road(w, v);
+    change_lane_policy(w, v);
+    double steering = steering_control(w, v, s->target_lane[v]);
+    steering = clipd(steering, -MAX_STEERING_ANGLE, MAX_STEERING_ANGLE);
+    int front, rear;
+    neighbour_vehicles(w, v, s->lane[v], &front, &rear);
+    double acc = idm_acceleration(w, v, v, front);
+    if (s->lane[v] != s->target_lane[v]) {
+        neighbour_vehicles(w, v, s->target_lane[v], &front, &rear);
+        acc = fmin(acc, idm_acceleration(w, v, v, front));
+    }
+    w->act_steer[v] = steering;
+    w->act_accel[v] = clipd(acc, -c->acc_max, c->acc_max);
+}
+
+/* vehicle/controller.py:89-133; label 0 LANE_LEFT, 2 LANE_RIGHT, else none */
+static void controlled_act(World *w, int v, int label) {
+    NetState *s = w->s;
+    const NetGraph *g = w->g;
+    follow_road(w, v);
+    if (label == 0 || label == 2) {
+        const NetLane *T = &g->lanes[s->target_lane[v]];
+        int id = T->lane_id + (label == 2 ? 1 : -1);
+        if (id < 0) id = 0;
+        if (id > T->road_count - 1) id = T->road_count - 1;
+        int cand = T->road_first + id;
+        if (lane_reachable(&g->lanes[cand], s->x[v], s->y[v])) s->target_lane[v] = cand;
+    }
+    double steering = steering_control(w, v, s->target_lane[v]);
+    w->act_steer[v] = clipd(steering, -MAX_STEERING_ANGLE, MAX_STEERING_ANGLE);
+    w->act_accel[v] = KP_A * (s->target_speed[v] - s->speed[v]);
+}
+
+/* vehicle/controller.py:326-344 */
+static int speed_to_index(const NetCfg *c, double speed) {
+    int n = c->n_target_speeds;
+    double x = (speed - c->target_speeds[0]) / (c->target_speeds[n - 1] - c->target_speeds[0]);
+    return (int)clipd(rint(x * (n - 1)), 0, n - 1);
+}
+
+/* vehicle/controller.py:295-315; action.py:204 labels */
+static void mdp_act(World *w, int v, int action) {
+    const NetCfg *c = w->c;
+    NetState *s = w->s;
+    if (action == 3 || action == 4) {
+        int idx = speed_to_index(c, s->speed[v]) + (action == 3 ? 1 : -1);
+        if (idx < 0) idx = 0;
+        if (idx > c->n_target_speeds - 1) idx = c->n_target_speeds - 1;
+        s->speed_index[0] = idx;
+        s->target_speed[v] = c->target_speeds[idx];
+        controlled_act(w, v, -1);
+    } else {
+        controlled_act(w, v, action);
+    }
+}
+
+static void road_act(World *w) {
+    for (int v = 0; v < w->V; v++) {
+        if (w->s->kind[v] == NET_KIND_IDM)
+            idm_act(w, v);
+        else
+            controlled_act(w, v, -1);
+    }
+}
+
+/* vehicle/kinematics.py:130-177 (+ behavior.py:139-148) */
+static void vehicle_step(World *w, int v, double dt) {
+    NetState *s = w->s;
+    if (s->kind[v] == NET_KIND_IDM) s->timer[v] += dt;
+    if (s->crashed[v]) {
+        w->act_steer[v] = 0;
+        w->act_accel[v] = -1.0 * s->speed[v];
+    }
+    if (s->speed[v] > MAX_SPEED)
+        w->act_accel[v] = fmin(w->act_accel[v], 1.0 * (MAX_SPEED - s->speed[v]));
+    else if (s->speed[v] < MIN_SPEED)
+        w->act_accel[v] = fmax(w->act_accel[v], 1.0 * (MIN_SPEED - s->speed[v]));
+    double beta = atan(1.0 / 2 * tan(w->act_steer[v]));
+    double vx = s->speed[v] * cos(s->heading[v] + beta);
+    double vy = s->speed[v] * sin(s->heading[v] + beta);
+    s->x[v] += vx * dt;
+    s->y[v] += vy * dt;
+    if (s->has_impact[v]) {
+        s->x[v] += s->impact_x[v];
+        s->y[v] += s->impact_y[v];
+        s->crashed[v] = 1;
+        s->has_impact[v] = 0;
+    }
+    s->heading[v] += s->speed[v] * sin(beta) / (VEH_LENGTH / 2) * dt;
+    s->speed[v] += w->act_accel[v] * dt;
+    s->lane[v] = net_closest_lane(w->g, s->x[v], s->y[v], s->heading[v]);
+}
+
+static void polygon(const NetState *s, int v, double p[5][2]) {
+    static const double loc[4][2] = {{-VEH_LENGTH / 2, -VEH_WIDTH / 2},
+                                     {-VEH_LENGTH / 2, +VEH_WIDTH / 2},
+                                     {+VEH_LENGTH / 2, +VEH_WIDTH / 2},
+                                     {+VEH_LENGTH / 2, -VEH_WIDTH / 2}};
+    double c = cos(s->heading[v]), sn = sin(s->heading[v]);
+    for (int k = 0; k < 4; k++) {
+        p[k][0] = (c * loc[k][0] + (-sn) * loc[k][1]) + s->x[v];
+        p[k][1] = (sn * loc[k][0] + c * loc[k][1]) + s->y[v];
+    }
+    p[4][0] = p[0][0];
+    p[4][1] = p[0][1];
+}
+
+/* vehicle/objects.py:92-138 */
+static void handle_collisions(World *w, int a, int b, double dt) {
+    NetState *s = w->s;
+    if (!(s->check_collisions[a] || s->check_collisions[b])) return;
+    double diag = sqrt(VEH_LENGTH * VEH_LENGTH + VEH_WIDTH * VEH_WIDTH);
+    double dist = norm2(s->x[b] - s->x[a], s->y[b] - s->y[a]);
+    if (dist > (diag + diag) / 2 + s->speed[a] * dt) return;
+    double pa[5][2], pb[5][2], tr[2];
+    polygon(s, a, pa);
+    polygon(s, b, pb);
+    double ca = cos(s->heading[a]), sa = sin(s->heading[a]);
+    double cb = cos(s->heading[b]), sb = sin(s->heading[b]);
+    int inter, will;
+    orc_polygons_intersecting(pa, pb, s->speed[a] * ca * dt, s->speed[a] * sa * dt,
+                              s->speed[b] * cb * dt, s->speed[b] * sb * dt, &inter, &will, tr);
+    if (will) {
+        s->impact_x[a] = tr[0] / 2;
+        s->impact_y[a] = tr[1] / 2;
+        s->has_impact[a] = 1;
+        s->impact_x[b] = -tr[0] / 2;
+        s->impact_y[b] = -tr[1] / 2;
+        s->has_impact[b] = 1;
+    }
+    if (inter) {
+        s->crashed[a] = 1;
+        s->crashed[b] = 1;
+    }
+}
+
+static void road_step(World *w, double dt) {
+    for (int v = 0; v < w->V; v++) vehicle_step(w, v, dt);
+    for (int i = 0; i < w->V; i++)
+        for (int j = i + 1; j < w->V; j++) handle_collisions(w, i, j, dt);
+}
+
+/* ------------------------------------------------------------------ observations */
+
+/* road/road.py:231-276 is_connected_road(l1, l2, route, same_lane=False, depth) with l1 given
+ * as (from, to) — lane ids are irrelevant when same_lane is False. */
+static int is_connected_road(const NetGraph *g, int f1, int t1, int f2, int t2, const int32_t *route,
+                             int rlen, int depth) {
+    if ((f2 == f1 && t2 == t1) || (t2 == f1)) return 1; /* is_same_road or is_leading_to_road */
+    if (depth > 0) {
+        if (rlen > 0 && RT_FROM(route[0]) == f1 && RT_TO(route[0]) == t1)
+            return is_connected_road(g, f1, t1, f2, t2, route + 1, rlen - 1, depth);
+        if (rlen > 0 && RT_FROM(route[0]) == t1)
+            return is_connected_road(g, RT_FROM(route[0]), RT_TO(route[0]), f2, t2, route + 1,
+                                     rlen - 1, depth - 1);
+        int any = 0;
+        for (int k = 0; k < g->succ_count[t1]; k++) {
+            int nf = g->succ[t1][k];
+            if (is_connected_road(g, t1, g->lanes[nf].to_node, f2, t2, route, rlen, depth - 1)) any = 1;
+        }
+        return any;
+    }
+    return 0;
+}
+
+/* envs/common/finite_mdp.py:104-163 compute_ttc_grid + observation.py:128-152 */
+static void observe_ttc(const World *w, float *obs) {
+    const NetCfg *c = w->c;
+    const NetState *s = w->s;
+    const NetGraph *g = w->g;
+    const int ego = 0;
+    const NetLane *EL = &g->lanes[s->lane[ego]];
+    int n_speeds = c->n_target_speeds, n_lanes = EL->road_count;
+    int n_t = (int)(c->ttc_horizon / (1.0 / c->policy_frequency));
+    double tq = 1.0 / c->policy_frequency;
+    double *grid = (double *)calloc((size_t)n_speeds * n_lanes * n_t, sizeof(double));
+    double ce = cos(s->heading[ego]), se = sin(s->heading[ego]);
+    const int32_t *route = s->route; /* ego is slot 0 */
+    for (int si = 0; si < n_speeds; si++) {
+        double ego_speed = c->target_speeds[si];
+        for (int o = 0; o < w->V; o++) {
+            if (o == ego || ego_speed == s->speed[o]) continue;
+            double margin = VEH_LENGTH / 2 + VEH_LENGTH / 2;
+            const double ms[3] = {0, -margin, margin}, costs[3] = {1, 0.5, 0.5};
+            const NetLane *OL = &g->lanes[s->lane[o]];
+            for (int k = 0; k < 3; k++) {
+                double distance = lane_distance_to(w, ego, o) + ms[k];
+                double other_projected_speed =
+                    s->speed[o] * dot2(cos(s->heading[o]), sin(s->heading[o]), ce, se);
+                double ttc = distance / orc_not_zero(ego_speed - other_projected_speed);
+                if (ttc < 0) continue;
+                if (!is_connected_road(g, EL->from_node, EL->to_node, OL->from_node, OL->to_node, route,
+                                       s->route_len[ego], 3))
+                    continue;
+                int l0 = 0, l1 = n_lanes; /* all lanes */
+                if (OL->road_count == EL->road_count) {
+                    l0 = OL->lane_id;
+                    l1 = l0 + 1;
+                }
+                int times[2] = {(int)(ttc / tq), (int)ceil(ttc / tq)};
+                for (int q = 0; q < 2; q++) {
+                    int t = times[q];
+                    if (0 <= t && t < n_t)
+                        for (int l = l0; l < l1; l++) {
+                            double *cell = &grid[((size_t)si * n_lanes + l) * n_t + t];
+                            *cell = fmax(*cell, costs[k]);
+                        }
+                }
+            }
+        }
+    }
+    /* pad lanes with ones, crop 3 around the ego lane; repeat first/last speed rows, crop 3 */
+    int ego_lane_id = EL->lane_id, si_e = s->speed_index[0];
+    for (int a = 0; a < 3; a++) {
+        int vrow = n_speeds + si_e - 1 + a; /* index into the repeated array */
+        /* repeated rows: row0 x (1+n_speeds), middle rows x1, last x (1+n_speeds) */
+        int src;
+        if (vrow < 1 + n_speeds)
+            src = 0;
+        else if (vrow < 1 + n_speeds + (n_speeds - 2))
+            src = 1 + (vrow - (1 + n_speeds));
+        else
+            src = n_speeds - 1;
+        if (n_speeds == 1) src = 0;
+        for (int b = 0; b < 3; b++) {
+            int lcol = n_lanes + ego_lane_id - 1 + b; /* index into [ones | grid | ones] */
+            for (int t = 0; t < n_t; t++) {
+                double val;
+                if (lcol < n_lanes || lcol >= 2 * n_lanes)
+                    val = 1.0;
+                else
+                    val = grid[((size_t)src * n_lanes + (lcol - n_lanes)) * n_t + t];
+                obs[(a * 3 + b) * n_t + t] = (float)val;
+            }
+        }
+    }
+    free(grid);
+}
+
+/* envs/common/observation.py:234-276 with explicit features_range / absolute */
+static void observe_kinematics(const World *w, float *obs) {
+    const NetCfg *c = w->c;
+    const NetState *s = w->s;
+    int K = c->obs_vehicles_count, V = w->V;
+    double *rows = (double *)calloc((size_t)K * 5, sizeof(double));
+    const int ego = 0;
+    double evx = s->speed[ego] * cos(s->heading[ego]), evy = s->speed[ego] * sin(s->heading[ego]);
+    rows[0] = 1;
+    rows[1] = s->x[ego];
+    rows[2] = s->y[ego];
+    rows[3] = evx;
+    rows[4] = evy;
+    int *cand = (int *)malloc(sizeof(int) * V);
+    double *key = (double *)malloc(sizeof(double) * V);
+    int nc = 0;
+    for (int v = 0; v < V; v++) {
+        if (!(norm2(s->x[v] - s->x[ego], s->y[v] - s->y[ego]) < c->perception_distance)) continue;
+        if (v == ego) continue;
+        double d = lane_distance_to(w, ego, v);
+        if (!(c->obs_see_behind || -2 * VEH_LENGTH < d)) continue;
+        cand[nc] = v;
+        key[nc] = fabs(d);
+        nc++;
+    }
+    for (int i = 1; i < nc; i++) {
+        int cv = cand[i];
+        double ck = key[i];
+        int j = i - 1;
+        while (j >= 0 && key[j] > ck) {
+            cand[j + 1] = cand[j];
+            key[j + 1] = key[j];
+            j--;
+        }
+        cand[j + 1] = cv;
+        key[j + 1] = ck;
+    }
+    int n_rows = 1;
+    for (int k = 0; k < nc && k < K - 1; k++) {
+        int v = cand[k];
+        double *r = rows + 5 * n_rows;
+        r[0] = 1;
+        r[1] = s->x[v];
+        r[2] = s->y[v];
+        r[3] = s->speed[v] * cos(s->heading[v]);
+        r[4] = s->speed[v] * sin(s->heading[v]);
+        if (!c->obs_absolute) {
+            r[1] -= s->x[ego];
+            r[2] -= s->y[ego];
+            r[3] -= evx;
+            r[4] -= evy;
+        }
+        n_rows++;
+    }
+    if (c->obs_normalize) {
+        for (int k = 0; k < n_rows; k++) {
+            double *r = rows + 5 * k;
+            r[1] = lmap(r[1], c->obs_x_lo, c->obs_x_hi, -1, 1);
+            r[2] = lmap(r[2], c->obs_y_lo, c->obs_y_hi, -1, 1);
+            r[3] = lmap(r[3], c->obs_vx_lo, c->obs_vx_hi, -1, 1);
+            r[4] = lmap(r[4], c->obs_vy_lo, c->obs_vy_hi, -1, 1);
+            if (c->obs_clip)
+                for (int f = 1; f < 5; f++) r[f] = clipd(r[f], -1, 1);
+        }
+    }
+    for (int k = 0; k < K * 5; k++) obs[k] = (float)rows[k];
+    free(rows);
+    free(cand);
+    free(key);
+}
+
+int net_obs_size(const NetCfg *c) {
+    if (c->obs_type == NET_OBS_TTC) return 3 * 3 * (int)(c->ttc_horizon / (1.0 / c->policy_frequency));
+    return c->obs_vehicles_count * 5;
+}
+
+void net_observe(const NetGraph *g, const NetCfg *c, const NetState *s, float *obs) {
+    World w;
+    w.g = g;
+    w.c = c;
+    w.s = (NetState *)s;
+    w.V = c->n_vehicles;
+    if (c->obs_type == NET_OBS_TTC)
+        observe_ttc(&w, obs);
+    else
+        observe_kinematics(&w, obs);
+}
+
+/* envs/roundabout_env.py:44-71 */
+static void reward_done(const World *w, int action, double *reward, int32_t *terminated,
+                        int32_t *truncated) {
+    const NetCfg *c = w->c;
+    const NetState *s = w->s;
+    const int ego = 0;
+    const NetLane *L = LANE(w, s->lane[ego]);
+    double es, elat;
+    net_lane_local(L, s->x[ego], s->y[ego], &es, &elat);
+    int on_road = lane_on_lane(L, es, elat, 0.0);
+    double r = 0;
+    r = r + c->collision_reward * (double)(s->crashed[ego] != 0);
+    /* MDPVehicle.get_speed_index / (DEFAULT_TARGET_SPEEDS.size - 1) */
+    r = r + c->high_speed_reward * ((double)s->speed_index[0] / (double)(3 - 1));
+    r = r + c->lane_change_reward * (double)(action == 0 || action == 2);
+    r = r + 0 * (double)on_road;
+    if (c->normalize_reward) r = lmap(r, c->collision_reward, c->high_speed_reward, 0, 1);
+    r *= (double)on_road;
+    *reward = r;
+    *terminated = s->crashed[ego] != 0;
+    *truncated = s->time[0] >= c->duration;
+}
+
+/* envs/common/abstract.py:259-317 */
+void net_step(const NetGraph *g, const NetCfg *c, NetState *s, int action, float *obs, double *reward,
+              int32_t *terminated, int32_t *truncated) {
+    World w;
+    w.g = g;
+    w.c = c;
+    w.s = s;
+    w.V = c->n_vehicles;
+    double *act_buf = (double *)calloc(2 * (size_t)c->n_vehicles, sizeof(double));
+    w.act_steer = act_buf;
+    w.act_accel = act_buf + c->n_vehicles;
+    int frames = c->simulation_frequency / c->policy_frequency;
+    double dt = 1.0 / c->simulation_frequency;
+    s->time[0] += 1.0 / c->policy_frequency;
+    for (int frame = 0; frame < frames; frame++) {
+        if (frame == 0) mdp_act(&w, 0, action);
+        road_act(&w);
+        road_step(&w, dt);
+    }
+    if (obs) net_observe(g, c, s, obs);
+    reward_done(&w, action, reward, terminated, truncated);
+    free(act_buf);
+}

@@ -1,0 +1,98 @@
+/*
+ * net_oracle.h — CPU restatement of the HighwayEnv hot path on a GENERAL road network
+ * (StraightLane / SineLane / CircularLane, planned routes): roundabout-v0.
+ * TEST INFRASTRUCTURE ONLY, same rules as hwy_oracle.h: never included, linked or called by
+ * the product.  Scalar, sequential, per-vehicle; each function cites the reference
+ * file:line it follows (paths relative to /root/reference/highway_env).  Pinned by
+ * tests/test_net_oracle_golden.py against golden rollouts of the unmodified reference.
+ */
+#ifndef NET_ORACLE_H
+#define NET_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NET_MAX_LANES 64
+#define NET_MAX_NODES 64
+#define NET_MAX_SUCC 6
+#define NET_MAX_ROUTE 16
+#define NET_MAX_TARGET_SPEEDS 8
+
+#define NET_LANE_STRAIGHT 0 /* road/lane.py:159 */
+#define NET_LANE_SINE 1     /* road/lane.py:236 */
+#define NET_LANE_CIRCULAR 2 /* road/lane.py:311 */
+
+#define NET_KIND_IDM 0
+#define NET_KIND_MDP 1
+
+#define NET_OBS_KINEMATICS 0 /* envs/common/observation.py:155 */
+#define NET_OBS_TTC 2        /* envs/common/observation.py:115 */
+
+/* One lane of RoadNetwork.graph[from][to][lane_id]; table order = graph enumeration order
+ * (road/road.py:65-71). */
+typedef struct NetLane {
+    int32_t type, from_node, to_node, lane_id;
+    int32_t road_first, road_count; /* table index of lane 0 of this road, lanes on the road */
+    int32_t forbidden, priority;
+    double width, speed_limit, length;
+    double sx, sy, ex, ey, dx, dy, lx, ly, heading; /* StraightLane fields (lane.py:183-194) */
+    double amplitude, pulsation, phase;             /* SineLane */
+    double cx, cy, radius, start_phase, end_phase, direction; /* CircularLane */
+} NetLane;
+
+typedef struct NetGraph {
+    int32_t n_lanes, n_nodes;
+    NetLane lanes[NET_MAX_LANES];
+    /* graph[node].keys() in insertion order: first-lane table index of each outgoing road */
+    int32_t succ_count[NET_MAX_NODES];
+    int32_t succ[NET_MAX_NODES][NET_MAX_SUCC];
+} NetGraph;
+
+typedef struct NetCfg {
+    int32_t n_vehicles;
+    int32_t simulation_frequency, policy_frequency;
+    int32_t n_target_speeds;
+    int32_t obs_type;
+    int32_t obs_vehicles_count, obs_see_behind, obs_absolute, obs_normalize, obs_clip;
+    int32_t ttc_horizon;
+    int32_t normalize_reward;
+    double duration;
+    double target_speeds[NET_MAX_TARGET_SPEEDS];
+    double obs_x_lo, obs_x_hi, obs_y_lo, obs_y_hi, obs_vx_lo, obs_vx_hi, obs_vy_lo, obs_vy_hi;
+    double collision_reward, high_speed_reward, lane_change_reward; /* roundabout_env.py:30-34 */
+    double acc_max, comfort_acc_max, comfort_acc_min, distance_wanted, time_wanted;
+    double politeness, lane_change_min_acc_gain, lane_change_max_braking_imposed, lane_change_delay;
+    double perception_distance;
+} NetCfg;
+
+/* route entry: from | to << 8 | (lane_id + 1) << 16   (lane_id + 1 == 0: None) */
+#define NET_ROUTE(from, to, id) ((from) | ((to) << 8) | (((id) + 1) << 16))
+
+typedef struct NetState {
+    double *x, *y, *heading, *speed, *target_speed, *timer, *delta, *impact_x, *impact_y;
+    int32_t *lane, *target_lane, *kind, *crashed, *has_impact, *check_collisions;
+    int32_t *route;     /* [V][NET_MAX_ROUTE] */
+    int32_t *route_len; /* [V] */
+    int32_t *speed_index; /* [1] */
+    double *time;         /* [1] */
+} NetState;
+
+/* One AbstractEnv.step of a roundabout-v0 style env (MDPVehicle ego in slot 0). */
+void net_step(const NetGraph *g, const NetCfg *c, NetState *s, int action, float *obs,
+              double *reward, int32_t *terminated, int32_t *truncated);
+void net_observe(const NetGraph *g, const NetCfg *c, const NetState *s, float *obs);
+int net_obs_size(const NetCfg *c);
+
+/* geometry KATs */
+void net_lane_local(const NetLane *L, double x, double y, double *s, double *lat);
+void net_lane_position(const NetLane *L, double s, double lat, double *x, double *y);
+double net_lane_heading_at(const NetLane *L, double s);
+int net_closest_lane(const NetGraph *g, double x, double y, double heading);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

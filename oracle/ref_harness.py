@@ -72,6 +72,78 @@ def lane_list(env):
     return out
 
 
+NET_MAX_ROUTE = 16
+
+
+def node_ids(env) -> dict:
+    """Node name -> integer id: graph keys in insertion order, then sink nodes as they appear."""
+    ids = {}
+    g = env.road.network.graph
+    for f in g.keys():
+        ids.setdefault(f, len(ids))
+    for f in g.keys():
+        for t in g[f].keys():
+            ids.setdefault(t, len(ids))
+    return ids
+
+
+def dump_network(env) -> dict:
+    """Lane table in graph-enumeration order (road/road.py:65-71) + successor lists, as arrays."""
+    from highway_env.road.lane import CircularLane, SineLane, StraightLane
+
+    ids = node_ids(env)
+    lanes = lane_list(env)
+    idx_of = {li: k for k, (li, _) in enumerate(lanes)}
+    n = len(lanes)
+    f = {k: np.zeros(n, dtype=np.float64) for k in (
+        "width", "speed_limit", "length", "sx", "sy", "ex", "ey", "dx", "dy", "lx", "ly", "heading",
+        "amplitude", "pulsation", "phase", "cx", "cy", "radius", "start_phase", "end_phase", "direction")}
+    i = {k: np.zeros(n, dtype=np.int32) for k in (
+        "type", "from_node", "to_node", "lane_id", "road_first", "road_count", "forbidden", "priority")}
+    for k, ((fr, to, lid), lane) in enumerate(lanes):
+        i["from_node"][k], i["to_node"][k], i["lane_id"][k] = ids[fr], ids[to], lid
+        i["road_first"][k] = idx_of[(fr, to, 0)]
+        i["road_count"][k] = len(env.road.network.graph[fr][to])
+        i["forbidden"][k], i["priority"][k] = int(lane.forbidden), int(lane.priority)
+        f["width"][k], f["speed_limit"][k], f["length"][k] = lane.width, lane.speed_limit, lane.length
+        if isinstance(lane, CircularLane):
+            i["type"][k] = 2
+            f["cx"][k], f["cy"][k] = lane.center
+            f["radius"][k], f["start_phase"][k], f["end_phase"][k] = lane.radius, lane.start_phase, lane.end_phase
+            f["direction"][k] = lane.direction
+        elif isinstance(lane, StraightLane):
+            i["type"][k] = 1 if isinstance(lane, SineLane) else 0
+            f["sx"][k], f["sy"][k] = lane.start
+            f["ex"][k], f["ey"][k] = lane.end
+            f["dx"][k], f["dy"][k] = lane.direction
+            f["lx"][k], f["ly"][k] = lane.direction_lateral
+            f["heading"][k] = lane.heading
+            if isinstance(lane, SineLane):
+                f["amplitude"][k], f["pulsation"][k], f["phase"][k] = lane.amplitude, lane.pulsation, lane.phase
+        else:
+            raise NotImplementedError(type(lane))
+    succ = np.full((len(ids), 6), -1, dtype=np.int32)
+    succ_count = np.zeros(len(ids), dtype=np.int32)
+    for fr, tos in env.road.network.graph.items():
+        for to in tos.keys():
+            succ[ids[fr], succ_count[ids[fr]]] = idx_of[(fr, to, 0)]
+            succ_count[ids[fr]] += 1
+    out = {"net_" + k: v for k, v in {**f, **i}.items()}
+    out["net_succ"], out["net_succ_count"] = succ, succ_count
+    out["net_node_names"] = np.array(list(ids.keys()))
+    return out
+
+
+def encode_route(env, vehicle) -> tuple:
+    ids = node_ids(env)
+    route = getattr(vehicle, "route", None) or []
+    enc = np.zeros(NET_MAX_ROUTE, dtype=np.int32)
+    assert len(route) <= NET_MAX_ROUTE, len(route)
+    for k, (fr, to, lid) in enumerate(route):
+        enc[k] = ids[fr] | (ids[to] << 8) | (((-1 if lid is None else int(lid)) + 1) << 16)
+    return enc, len(route)
+
+
 def dump_state(env) -> dict:
     """Snapshot the reference road in the SoA schema used by ``highwayenv_b200``.
 
@@ -116,6 +188,10 @@ def dump_state(env) -> dict:
         "time": np.float64(env.time),
         "steps": np.int64(env.steps),
     }
+    if any(getattr(v, "route", None) for v in vs):
+        enc = [encode_route(env, v) for v in vs]
+        d["route"] = np.stack([e[0] for e in enc])
+        d["route_len"] = np.array([e[1] for e in enc], dtype=np.int32)
     return d
 
 
