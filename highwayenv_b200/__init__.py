@@ -23,6 +23,7 @@ __version__ = "0.1.0"
 REGISTRY = {
     "highway-v0": "highwayenv_b200.envs.highway_env:BatchedHighwayEnv",
     "highway-fast-v0": "highwayenv_b200.envs.highway_env:BatchedHighwayEnvFast",
+    "roundabout-v0": "highwayenv_b200.envs.roundabout_env:BatchedRoundaboutEnv",
 }
 
 

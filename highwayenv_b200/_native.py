@@ -59,9 +59,60 @@ class HwyHighwayState(C.Structure):
     ]
 
 
+# ---- general road networks (roundabout-v0)
+HWY_NET_MAX_LANES, HWY_NET_MAX_NODES, HWY_NET_MAX_SUCC, HWY_NET_MAX_ROUTE, HWY_NET_GROUP = 64, 64, 6, 16, 8
+LANE_STRAIGHT, LANE_SINE, LANE_CIRCULAR = 0, 1, 2
+OBS_KINEMATICS, OBS_TTC = 0, 2
+
+NET_LANE_INT_FIELDS = ("type", "from_node", "to_node", "lane_id", "road_first", "road_count", "forbidden",
+                       "priority")
+NET_LANE_F64_FIELDS = ("width", "speed_limit", "length", "sx", "sy", "ex", "ey", "dx", "dy", "lx", "ly",
+                       "heading", "amplitude", "pulsation", "phase", "cx", "cy", "radius", "start_phase",
+                       "end_phase", "direction")
+
+
+class HwyNetLane(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in NET_LANE_INT_FIELDS] + [(n, C.c_double) for n in NET_LANE_F64_FIELDS]
+
+
+class HwyNetGraph(C.Structure):
+    _fields_ = [
+        ("n_lanes", C.c_int32), ("n_nodes", C.c_int32),
+        ("lanes", HwyNetLane * HWY_NET_MAX_LANES),
+        ("succ_count", C.c_int32 * HWY_NET_MAX_NODES),
+        ("succ", (C.c_int32 * HWY_NET_MAX_SUCC) * HWY_NET_MAX_NODES),
+    ]
+
+
+class HwyNetParams(C.Structure):
+    _fields_ = (
+        [(n, C.c_int32) for n in (
+            "n_vehicles", "simulation_frequency", "policy_frequency", "n_target_speeds", "obs_type",
+            "obs_vehicles_count", "obs_see_behind", "obs_absolute", "obs_normalize", "obs_clip",
+            "ttc_horizon", "normalize_reward")]
+        + [("duration", C.c_double), ("target_speeds", C.c_double * HWY_MAX_TARGET_SPEEDS)]
+        + [(n, C.c_double) for n in (
+            "obs_x_lo", "obs_x_hi", "obs_y_lo", "obs_y_hi", "obs_vx_lo", "obs_vx_hi", "obs_vy_lo",
+            "obs_vy_hi", "collision_reward", "high_speed_reward", "lane_change_reward", "acc_max",
+            "comfort_acc_max", "comfort_acc_min", "distance_wanted", "time_wanted", "politeness",
+            "lane_change_min_acc_gain", "lane_change_max_braking_imposed", "lane_change_delay",
+            "perception_distance")]
+    )
+
+
+class HwyNetState(C.Structure):
+    _fields_ = [
+        ("n_envs", C.c_int32), ("vp", C.c_int32),
+        ("pos", C.c_void_p), ("hs", C.c_void_p), ("tt", C.c_void_p), ("imp", C.c_void_p),
+        ("delta", C.c_void_p), ("meta", C.c_void_p), ("route", C.c_void_p), ("route_len", C.c_void_p),
+        ("speed_index", C.c_void_p), ("time", C.c_void_p),
+    ]
+
+
 EXPORTS = (
     "hwy_abi_version", "hwy_last_error", "hwy_highway_slot_stride", "hwy_highway_reset",
     "hwy_highway_observe", "hwy_highway_step", "hwy_highway_autoreset", "hwy_launch_count",
+    "hwy_network_obs_size", "hwy_network_step", "hwy_network_observe",
 )
 
 _lib = None
@@ -94,6 +145,14 @@ def load():
                                      C.c_void_p, C.c_void_p]
     lib.hwy_highway_autoreset.restype = C.c_int
     lib.hwy_highway_autoreset.argtypes = [P, S, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    NP, NG, NS = C.POINTER(HwyNetParams), C.c_void_p, C.POINTER(HwyNetState)
+    lib.hwy_network_obs_size.restype = C.c_int
+    lib.hwy_network_obs_size.argtypes = [NP]
+    lib.hwy_network_step.restype = C.c_int
+    lib.hwy_network_step.argtypes = [NP, NG, NS, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.hwy_network_observe.restype = C.c_int
+    lib.hwy_network_observe.argtypes = [NP, NG, NS, C.c_void_p, C.c_void_p]
     if lib.hwy_abi_version() != HWY_ABI_VERSION:
         raise RuntimeError("libhwyb200.so ABI version mismatch; rebuild")
     _lib = lib

@@ -10,9 +10,9 @@ import subprocess
 import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = [os.path.join(_HERE, "csrc", "hwy_highway.cu")]
-DEPS = SRC + [os.path.join(_HERE, "csrc", "hwy_math.cuh"),
-              os.path.join(os.path.dirname(_HERE), "include", "hwyb200.h")]
+SRC = [os.path.join(_HERE, "csrc", "hwy_highway.cu"), os.path.join(_HERE, "csrc", "hwy_network.cu")]
+DEPS = SRC + [os.path.join(_HERE, "csrc", h) for h in ("hwy_math.cuh", "hwy_device.cuh", "hwy_abi.h")] + [
+    os.path.join(os.path.dirname(_HERE), "include", "hwyb200.h")]
 OUT = os.path.join(_HERE, "csrc", "libhwyb200.so")
 
 NVCC_FLAGS = [

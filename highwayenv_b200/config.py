@@ -101,3 +101,30 @@ DEFAULTS = {
 
 def default_config(env_id: str) -> dict:
     return copy.deepcopy(DEFAULTS[env_id]())
+
+
+def roundabout_default_config() -> dict:
+    """RoundaboutEnv.default_config (highway_env/envs/roundabout_env.py:13-42)."""
+    config = abstract_default_config()
+    update_config(config, {
+        "observation": {
+            "type": "Kinematics",
+            "absolute": True,
+            "features_range": {"x": [-100, 100], "y": [-100, 100], "vx": [-15, 15], "vy": [-15, 15]},
+        },
+        "action": {"type": "DiscreteMetaAction", "target_speeds": [0, 8, 16]},
+        "incoming_vehicle_destination": None,
+        "collision_reward": -1,
+        "high_speed_reward": 0.2,
+        "right_lane_reward": 0,
+        "lane_change_reward": -0.05,
+        "screen_width": 600,
+        "screen_height": 600,
+        "centering_position": [0.5, 0.6],
+        "duration": 11,
+        "normalize_reward": True,
+    })
+    return config
+
+
+DEFAULTS["roundabout-v0"] = roundabout_default_config

@@ -61,7 +61,7 @@ __device__ __forceinline__ bool lanes_aligned(const HwyHighwayParams& P) {
 // vehicle/controller.py:145-187 steering_control on a StraightLane, up to the argument of the
 // last arcsin: returns x = clip(LENGTH/2/not_zero(speed) * heading_rate_command, -1, 1), i.e.
 // the SINE of the commanded slip angle.
-__device__ __noinline__ double steering_sin_slip(const HwyStraightLane L, double x, double y,
+static __device__ __noinline__ double steering_sin_slip(const HwyStraightLane L, double x, double y,
                                                  double heading, double speed) {
     double lc_s, lc_lat;
     lane_local(L, x, y, lc_s, lc_lat);

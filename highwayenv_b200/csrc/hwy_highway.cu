@@ -1273,7 +1273,8 @@ highway_reset_kernel(const HwyHighwayParams P, const HwyHighwayState S,
 }  // namespace hwy
 
 // ====================================================================== C ABI
-namespace {
+// error text / launch counter shared by the translation units of the library (hwy_abi.h)
+namespace hwy_abi {
 thread_local char g_err[512] = "";
 thread_local unsigned long long g_launches = 0;
 
@@ -1290,6 +1291,13 @@ int check_launch(const char* what) {
     }
     return 0;
 }
+}  // namespace hwy_abi
+
+namespace {
+using hwy_abi::check_launch;
+using hwy_abi::fail;
+using hwy_abi::g_err;
+using hwy_abi::g_launches;
 int validate(const HwyHighwayParams* p, const HwyHighwayState* s) {
     if (!p || !s) return fail("%s", "null params/state");
     if (p->n_vehicles < 1 || p->n_vehicles > HWY_MAX_VEHICLES) return fail("%s", "n_vehicles out of range");

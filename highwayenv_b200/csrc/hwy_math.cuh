@@ -42,13 +42,13 @@ __device__ __forceinline__ double not_zero(double x) {
 // Out-of-line copies of the fp64 libm routines: every call site shares one body, which keeps
 // the step kernel inside the instruction cache (the inlined versions made it > 140 KB and
 // ~half of all issue slots stalled on instruction fetch).
-__device__ __noinline__ double m_asin(double x) { return asin(x); }
-__device__ __noinline__ double m_tan(double x) { return tan(x); }
-__device__ __noinline__ double m_atan(double x) { return atan(x); }
-__device__ __noinline__ double m_sin(double x) { return sin(x); }
-__device__ __noinline__ void m_sincos(double x, double* s, double* c) { sincos(x, s, c); }
-__device__ __noinline__ double m_pow(double x, double y) { return pow(x, y); }
-__device__ __noinline__ double m_fmod(double a, double b) { return fmod(a, b); }
+static __device__ __noinline__ double m_asin(double x) { return asin(x); }
+static __device__ __noinline__ double m_tan(double x) { return tan(x); }
+static __device__ __noinline__ double m_atan(double x) { return atan(x); }
+static __device__ __noinline__ double m_sin(double x) { return sin(x); }
+static __device__ __noinline__ void m_sincos(double x, double* s, double* c) { sincos(x, s, c); }
+static __device__ __noinline__ double m_pow(double x, double y) { return pow(x, y); }
+static __device__ __noinline__ double m_fmod(double a, double b) { return fmod(a, b); }
 
 // Python floored float modulo (b > 0 here); fast path when 0 <= a < b (fmod is exact: a).
 __device__ __forceinline__ double py_mod_pos(double a, double b) {

@@ -1,0 +1,887 @@
+// hwy_network.cu — sm_100a kernels + C ABI for envs on a GENERAL road network (roundabout-v0):
+// StraightLane / SineLane / CircularLane geometry, planned routes with RoadNetwork.next_lane,
+// IDM + MOBIL with the route branch, all-pairs SAT collisions, absolute Kinematics or
+// TimeToCollision observation, roundabout reward.
+//
+// Thread mapping: G = 8 threads per env (vehicle slot = thread; roundabout has 5 vehicles), 32
+// envs per 256-thread block.  The per-vehicle work is branchy; the one regular O(V*L) piece —
+// Vehicle.on_state_update's get_closest_lane_index over ALL lanes (47 % of the reference's step
+// on networks) — is spread over the group: thread t evaluates lanes t, t+G, ... for each
+// vehicle and a shuffle arg-min (first minimum wins, as np.argmin) picks the lane.
+// Road.act's Gauss-Seidel part (follow_road + change_lane_policy mutate target lanes / routes that
+// later vehicles read) runs in list order, one vehicle at a time, exactly like the reference;
+// steering, IDM acceleration, integration and the collision sweep run one vehicle per thread.
+// The lane table lives in HBM (HwyNetGraph) and is staged into shared memory once per block.
+//
+// Reference paths are relative to /root/reference/highway_env.
+#include <cstdio>
+#include <cuda_runtime.h>
+
+#include "../../include/hwyb200.h"
+#include "hwy_abi.h"
+#include "hwy_device.cuh"
+#include "hwy_math.cuh"
+
+namespace hwynet {
+using namespace hwy;
+
+constexpr int G = HWY_NET_GROUP;
+constexpr int R = HWY_NET_MAX_ROUTE;
+constexpr int kBlockEnvs = 32;
+constexpr int kBlockThreads = kBlockEnvs * G;
+
+struct GraphShared {
+    int n_lanes, n_nodes;
+    HwyNetLane lanes[HWY_NET_MAX_LANES];
+    int succ_count[HWY_NET_MAX_NODES];
+    int succ[HWY_NET_MAX_NODES][HWY_NET_MAX_SUCC];
+};
+
+struct EnvStage {
+    double x[G], y[G], heading[G], c[G], s[G], v[G], ts[G];
+    int lane[G], tgt[G];
+    int route[G][R];
+    int route_len[G];
+    double ttc[3][4][12];  // TimeToCollision grid [speed][lane on road][time]
+    double key[G];
+};
+
+// ------------------------------------------------------------------ lanes (road/lane.py)
+// local_coordinates: StraightLane :205-209, SineLane :285-289, CircularLane :351-358
+__device__ __noinline__ void lane_local(const HwyNetLane& L, double x, double y, double& s, double& lat) {
+    if (L.type == HWY_LANE_CIRCULAR) {
+        double ddx = x - L.cx, ddy = y - L.cy;
+        double phi = atan2(ddy, ddx);
+        phi = L.start_phase + wrap_to_pi(phi - L.start_phase);
+        double r = norm2(ddx, ddy);
+        s = L.direction * (phi - L.start_phase) * L.radius;
+        lat = L.direction * (L.radius - r);
+        return;
+    }
+    double ddx = x - L.sx, ddy = y - L.sy;
+    double lon = dot2(ddx, ddy, L.dx, L.dy);
+    double la = dot2(ddx, ddy, L.lx, L.ly);
+    if (L.type == HWY_LANE_SINE) la = la - L.amplitude * m_sin(L.pulsation * lon + L.phase);
+    s = lon;
+    lat = la;
+}
+// position: StraightLane :192-197, SineLane :268-273, CircularLane :338-342
+__device__ __noinline__ void lane_position(const HwyNetLane& L, double s, double lat, double& x, double& y) {
+    if (L.type == HWY_LANE_CIRCULAR) {
+        double phi = L.direction * s / L.radius + L.start_phase;
+        double rr = L.radius - lat * L.direction;
+        double sn, cs;
+        m_sincos(phi, &sn, &cs);
+        x = L.cx + rr * cs;
+        y = L.cy + rr * sn;
+        return;
+    }
+    if (L.type == HWY_LANE_SINE) lat = lat + L.amplitude * m_sin(L.pulsation * s + L.phase);
+    x = (L.sx + s * L.dx) + lat * L.lx;
+    y = (L.sy + s * L.dy) + lat * L.ly;
+}
+// heading_at: StraightLane :199-200, SineLane :275-280, CircularLane :344-347
+__device__ __noinline__ double lane_heading_at(const HwyNetLane& L, double s) {
+    if (L.type == HWY_LANE_CIRCULAR) {
+        double phi = L.direction * s / L.radius + L.start_phase;
+        return phi + kPi / 2 * L.direction;
+    }
+    if (L.type == HWY_LANE_SINE) {
+        double sn, cs;
+        m_sincos(L.pulsation * s + L.phase, &sn, &cs);
+        return L.heading + m_atan(L.amplitude * L.pulsation * cs);
+    }
+    return L.heading;
+}
+__device__ __forceinline__ double lane_s_of(const HwyNetLane& L, double x, double y) {
+    double s, lat;
+    lane_local(L, x, y, s, lat);
+    return s;
+}
+__device__ __forceinline__ bool lane_on(const HwyNetLane& L, double s, double lat, double margin) {
+    return fabs(lat) <= L.width / 2 + margin && -kLaneVehLength <= s && s < L.length + kLaneVehLength;
+}
+__device__ __forceinline__ bool lane_reachable(const HwyNetLane& L, double x, double y) {
+    if (L.forbidden) return false;
+    double s, lat;
+    lane_local(L, x, y, s, lat);
+    return fabs(lat) <= 2 * L.width && 0 <= s && s < L.length + kLaneVehLength;
+}
+// :127-130 distance
+__device__ __forceinline__ double lane_distance(const HwyNetLane& L, double x, double y) {
+    double s, r;
+    lane_local(L, x, y, s, r);
+    return fabs(r) + fmax(s - L.length, 0.0) + fmax(0.0 - s, 0.0);
+}
+// :132-147 distance_with_heading
+__device__ __forceinline__ double lane_distance_with_heading(const HwyNetLane& L, double x, double y,
+                                                             double h) {
+    double s, r;
+    lane_local(L, x, y, s, r);
+    double angle = fabs(wrap_to_pi(h - lane_heading_at(L, s)));
+    return fabs(r) + fmax(s - L.length, 0.0) + fmax(0.0 - s, 0.0) + 1.0 * angle;
+}
+
+#define RT_FROM(e) ((e)&0xff)
+#define RT_TO(e) (((e) >> 8) & 0xff)
+#define RT_ID(e) ((((e) >> 16) & 0xff) - 1)
+
+__device__ __forceinline__ int road_first(const GraphShared& g, int from, int to) {
+    for (int k = 0; k < g.succ_count[from]; ++k) {
+        int f = g.succ[from][k];
+        if (g.lanes[f].to_node == to) return f;
+    }
+    return -1;
+}
+
+// road/road.py:138-157 next_lane_given_next_road (next_id < 0 == None)
+__device__ __forceinline__ int next_lane_given_next_road(const GraphShared& g, int cur, int next_first,
+                                                         int next_id, double px, double py, double& dist) {
+    const HwyNetLane& C = g.lanes[cur];
+    int n_next = g.lanes[next_first].road_count;
+    if (C.road_count == n_next) {
+        if (next_id < 0) next_id = C.lane_id;
+    } else {
+        int best = 0;
+        double bd = 0;
+        for (int l = 0; l < n_next; ++l) {
+            double d = lane_distance(g.lanes[next_first + l], px, py);
+            if (l == 0 || d < bd) {
+                bd = d;
+                best = l;
+            }
+        }
+        next_id = best;
+    }
+    dist = lane_distance(g.lanes[next_first + next_id], px, py);
+    return next_id;
+}
+
+// road/road.py:73-136 next_lane: pops the vehicle's route in place
+__device__ __noinline__ int next_lane(const GraphShared& g, EnvStage& st, int v, int cur) {
+    const HwyNetLane& C = g.lanes[cur];
+    int* route = st.route[v];
+    int rlen = st.route_len[v];
+    int next_first = -1, next_id = -1;
+    if (rlen > 0) {
+        if (RT_FROM(route[0]) == C.from_node && RT_TO(route[0]) == C.to_node) {
+            for (int k = 1; k < rlen; ++k) route[k - 1] = route[k];
+            --rlen;
+            st.route_len[v] = rlen;
+        }
+        if (rlen > 0 && RT_FROM(route[0]) == C.to_node) {
+            next_first = road_first(g, RT_FROM(route[0]), RT_TO(route[0]));
+            next_id = RT_ID(route[0]);
+        }
+    }
+    double lon, lat, px, py;
+    lane_local(C, st.x[v], st.y[v], lon, lat);
+    lane_position(C, lon, 0.0, px, py);
+    if (next_first < 0) {
+        int n_succ = g.succ_count[C.to_node];
+        if (n_succ == 0) return cur;  // KeyError on graph[_to]: keep the current lane
+        int best = -1;
+        double bd = 0;
+        for (int k = 0; k < n_succ; ++k) {
+            int nf = g.succ[C.to_node][k];
+            double d;
+            int nid = next_lane_given_next_road(g, cur, nf, next_id, px, py, d);
+            if (k == 0 || d < bd) {
+                bd = d;
+                best = nf + nid;
+            }
+        }
+        return best;
+    }
+    double d;
+    next_id = next_lane_given_next_road(g, cur, next_first, next_id, px, py, d);
+    return next_first + next_id;
+}
+
+// vehicle/controller.py:135-143 follow_road
+__device__ __forceinline__ void follow_road(const GraphShared& g, EnvStage& st, int v) {
+    const HwyNetLane& T = g.lanes[st.tgt[v]];
+    if (lane_s_of(T, st.x[v], st.y[v]) > T.length - kLaneVehLength / 2)  // after_end (lane.py:120-125)
+        st.tgt[v] = next_lane(g, st, v, st.tgt[v]);
+}
+
+// road/road.py:483-547 neighbour_vehicles, same-segment search
+__device__ __noinline__ void neighbours(const GraphShared& g, const EnvStage& st, int V, int veh,
+                                        int lane_idx, int& front, int& rear) {
+    const HwyNetLane& L = g.lanes[lane_idx];
+    double s = lane_s_of(L, st.x[veh], st.y[veh]);
+    double s_front = 0, s_rear = 0;
+    front = -1;
+    rear = -1;
+    for (int v = 0; v < V; ++v) {
+        if (v == veh) continue;
+        double s_v, lat_v;
+        lane_local(L, st.x[v], st.y[v], s_v, lat_v);
+        if (!lane_on(L, s_v, lat_v, 1.0)) continue;
+        if (s <= s_v && (front < 0 || s_v <= s_front)) {
+            s_front = s_v;
+            front = v;
+        }
+        if (s_v < s && (rear < 0 || s_v > s_rear)) {
+            s_rear = s_v;
+            rear = v;
+        }
+    }
+}
+
+__device__ __forceinline__ double lane_distance_to(const GraphShared& g, const EnvStage& st, int self,
+                                                   int other) {
+    const HwyNetLane& L = g.lanes[st.lane[self]];
+    return lane_s_of(L, st.x[other], st.y[other]) - lane_s_of(L, st.x[self], st.y[self]);
+}
+// vehicle/behavior.py:192-217
+__device__ __forceinline__ double desired_gap(const HwyNetParams& P, const EnvStage& st, int ego, int front) {
+    double ab = -P.comfort_acc_max * P.comfort_acc_min;
+    double dvx = st.v[ego] * st.c[ego] - st.v[front] * st.c[front];
+    double dvy = st.v[ego] * st.s[ego] - st.v[front] * st.s[front];
+    double dv = dot2(dvx, dvy, st.c[ego], st.s[ego]);
+    return P.distance_wanted + st.v[ego] * P.time_wanted + st.v[ego] * dv / (2 * sqrt(ab));
+}
+// vehicle/behavior.py:150-190 with the caller's DELTA
+__device__ __noinline__ double idm_acceleration(const HwyNetParams& P, const GraphShared& g,
+                                                const EnvStage& st, double delta, int ego, int front) {
+    if (ego < 0) return 0.0;
+    double ego_target_speed = clipd(st.ts[ego], 0.0, g.lanes[st.lane[ego]].speed_limit);
+    double acc = P.comfort_acc_max *
+                 (1 - m_pow(fmax(st.v[ego], 0.0) / fabs(not_zero(ego_target_speed)), delta));
+    if (front >= 0) {
+        double d = lane_distance_to(g, st, ego, front);
+        double q = desired_gap(P, st, ego, front) / not_zero(d);
+        acc -= P.comfort_acc_max * (q * q);
+    }
+    return acc;
+}
+
+__device__ __forceinline__ int isign(int a) { return (a > 0) - (a < 0); }
+
+// vehicle/behavior.py:265-324 mobil(lane_index), incl. the planned-route branch
+__device__ __noinline__ bool mobil(const HwyNetParams& P, const GraphShared& g, const EnvStage& st, int V,
+                                   int v, double delta, int lane_index) {
+    int new_preceding, new_following;
+    neighbours(g, st, V, v, lane_index, new_preceding, new_following);
+    double new_following_pred_a = idm_acceleration(P, g, st, delta, new_following, v);
+    if (new_following_pred_a < -P.lane_change_max_braking_imposed) return false;
+    int old_preceding, old_following;
+    neighbours(g, st, V, v, st.lane[v], old_preceding, old_following);
+    double self_pred_a = idm_acceleration(P, g, st, delta, v, new_preceding);
+    if (st.route_len[v] > 0 && RT_ID(st.route[v][0]) >= 0) {
+        int tid = g.lanes[st.tgt[v]].lane_id, cid = g.lanes[lane_index].lane_id;
+        if (isign(cid - tid) != isign(RT_ID(st.route[v][0]) - tid)) return false;  // wrong direction
+        if (self_pred_a < -P.lane_change_max_braking_imposed) return false;
+    } else {
+        double self_a = idm_acceleration(P, g, st, delta, v, old_preceding);
+        double jerk = self_pred_a - self_a;
+        if (P.politeness != 0.0) {
+            double new_following_a = idm_acceleration(P, g, st, delta, new_following, new_preceding);
+            double old_following_a = idm_acceleration(P, g, st, delta, old_following, v);
+            double old_following_pred_a = idm_acceleration(P, g, st, delta, old_following, old_preceding);
+            jerk = self_pred_a - self_a + P.politeness * (new_following_pred_a - new_following_a +
+                                                          old_following_pred_a - old_following_a);
+        }
+        if (jerk < P.lane_change_min_acc_gain) return false;
+    }
+    return true;
+}
+
+// vehicle/behavior.py:219-263 change_lane_policy; returns the (possibly reset) timer
+__device__ __forceinline__ double change_lane_policy(const HwyNetParams& P, const GraphShared& g,
+                                                     EnvStage& st, int V, int v, double delta,
+                                                     double timer) {
+    const int lane = st.lane[v];
+    if (lane != st.tgt[v]) {
+        const HwyNetLane &A = g.lanes[lane], &B = g.lanes[st.tgt[v]];
+        if (A.from_node == B.from_node && A.to_node == B.to_node) {
+            for (int o = 0; o < V; ++o) {
+                if (o != v && st.lane[o] != st.tgt[v] && st.tgt[o] == st.tgt[v]) {
+                    double d = lane_distance_to(g, st, v, o);
+                    double d_star = desired_gap(P, st, v, o);
+                    if (0 < d && d < d_star) {
+                        st.tgt[v] = lane;
+                        break;
+                    }
+                }
+            }
+        }
+        return timer;
+    }
+    if (!(P.lane_change_delay < timer)) return timer;
+    const HwyNetLane& A = g.lanes[lane];
+    for (int k = 0; k < 2; ++k) {  // side_lanes: id-1 then id+1 (road/road.py:200-211)
+        if (k == 0 && !(A.lane_id > 0)) continue;
+        if (k == 1 && !(A.lane_id < A.road_count - 1)) continue;
+        int cand = k == 0 ? lane - 1 : lane + 1;
+        if (!lane_reachable(g.lanes[cand], st.x[v], st.y[v])) continue;
+        if (fabs(st.v[v]) < 1) continue;
+        if (mobil(P, g, st, V, v, delta, cand)) st.tgt[v] = cand;
+    }
+    return 0.0;
+}
+
+// vehicle/controller.py:145-187 steering_control up to the argument of the last arcsin
+__device__ __noinline__ double steering_sin_slip(const HwyNetLane& L, double x, double y, double heading,
+                                                 double speed) {
+    double lc_s, lc_lat;
+    lane_local(L, x, y, lc_s, lc_lat);
+    double lane_future_heading = lane_heading_at(L, lc_s + speed * kTauPursuit);
+    double lateral_speed_command = -kKpLateral * lc_lat;
+    double heading_command = m_asin(clipd(lateral_speed_command / not_zero(speed), -1.0, 1.0));
+    double heading_ref = lane_future_heading + clipd(heading_command, -kPi / 4, kPi / 4);
+    double heading_rate_command = kKpHeading * wrap_to_pi(heading_ref - heading);
+    return clipd(kVehLength / 2 / not_zero(speed) * heading_rate_command, -1.0, 1.0);
+}
+
+__device__ __forceinline__ int speed_to_index(const HwyNetParams& P, double speed) {
+    int n = P.n_target_speeds;
+    double x = (speed - P.target_speeds[0]) / (P.target_speeds[n - 1] - P.target_speeds[0]);
+    return (int)clipd(rint(x * (n - 1)), 0.0, (double)(n - 1));
+}
+
+// group-wide helpers (G consecutive lanes of a warp)
+__device__ __forceinline__ unsigned group_mask() {
+    return ((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1));
+}
+__device__ __forceinline__ void group_sync() { __syncwarp(group_mask()); }
+
+// road/road.py:55-71 get_closest_lane_index for every vehicle, cooperatively: thread t scans lanes
+// t, t+G, ...; arg-min over (distance, lane index) keeps the first minimum like np.argmin.
+__device__ __forceinline__ int closest_lane_group(const GraphShared& g, const EnvStage& st, int V, int i) {
+    int mine = 0;
+    const unsigned mask = group_mask();
+    for (int v = 0; v < V; ++v) {
+        double bd = INFINITY;
+        int bl = 0x7fffffff;
+        const double x = st.x[v], y = st.y[v], h = st.heading[v];
+        for (int l = i; l < g.n_lanes; l += G) {
+            double d = lane_distance_with_heading(g.lanes[l], x, y, h);
+            if (d < bd) {
+                bd = d;
+                bl = l;
+            }
+        }
+#pragma unroll
+        for (int off = G / 2; off > 0; off >>= 1) {
+            double od = __shfl_xor_sync(mask, bd, off, G);
+            int ol = __shfl_xor_sync(mask, bl, off, G);
+            if (od < bd || (od == bd && ol < bl)) {
+                bd = od;
+                bl = ol;
+            }
+        }
+        if (v == i) mine = bl;
+    }
+    return mine;
+}
+
+// ------------------------------------------------------------------ observations
+// road/road.py:231-276 is_connected_road(l1, l2, route, same_lane=False, depth).  The two
+// route-following cases are tail calls (a loop here); the "all roads at the intersection" case
+// branches, so pending (road, route offset, depth) items sit on a small explicit stack.
+__device__ __noinline__ bool is_connected_road(const GraphShared& g, int f1, int t1, int f2, int t2,
+                                               const int* route, int rlen, int depth) {
+    struct Item {
+        short f, t, ro, d;
+    };
+    Item stack[24];
+    int sp = 0;
+    stack[sp++] = Item{(short)f1, (short)t1, 0, (short)depth};
+    while (sp > 0) {
+        Item it = stack[--sp];
+        int f = it.f, t = it.t, ro = it.ro, d = it.d;
+        for (;;) {
+            if ((f2 == f && t2 == t) || t2 == f) return true;  // is_same_road or is_leading_to_road
+            if (d <= 0) break;
+            if (ro < rlen && RT_FROM(route[ro]) == f && RT_TO(route[ro]) == t) {
+                ++ro;  // route starts at the current road: skip it
+                continue;
+            }
+            if (ro < rlen && RT_FROM(route[ro]) == t) {
+                f = RT_FROM(route[ro]);  // route continues from the current road: follow it
+                t = RT_TO(route[ro]);
+                ++ro;
+                --d;
+                continue;
+            }
+            for (int k = 0; k < g.succ_count[t] && sp < 24; ++k)
+                stack[sp++] = Item{(short)t, (short)g.lanes[g.succ[t][k]].to_node, (short)ro, (short)(d - 1)};
+            break;
+        }
+    }
+    return false;
+}
+
+// envs/common/finite_mdp.py:104-163 compute_ttc_grid + observation.py:128-152 (pad / crop)
+__device__ __forceinline__ void observe_ttc(const HwyNetParams& P, const GraphShared& g, EnvStage& st,
+                                            int V, int i, int speed_index, float* __restrict__ obs_env) {
+    const HwyNetLane& EL = g.lanes[st.lane[0]];
+    const int n_speeds = P.n_target_speeds, n_lanes = EL.road_count;
+    const double tq = 1.0 / P.policy_frequency;
+    const int n_t = (int)(P.ttc_horizon / tq);
+    for (int k = i; k < 3 * 4 * 12; k += G) (&st.ttc[0][0][0])[k] = 0.0;
+    group_sync();
+    if (i > 0 && i < V) {  // one thread per other vehicle; cells take the max cost (atomic on bits)
+        const int o = i;
+        const HwyNetLane& OL = g.lanes[st.lane[o]];
+        const bool connected = is_connected_road(g, EL.from_node, EL.to_node, OL.from_node, OL.to_node,
+                                                 st.route[0], st.route_len[0], 3);
+        const double margin = kVehLength / 2 + kVehLength / 2;
+        const double base = lane_distance_to(g, st, 0, o);
+        const double other_projected_speed = st.v[o] * dot2(st.c[o], st.s[o], st.c[0], st.s[0]);
+        for (int si = 0; si < n_speeds; ++si) {
+            const double ego_speed = P.target_speeds[si];
+            if (ego_speed == st.v[o]) continue;
+            for (int k = 0; k < 3; ++k) {
+                const double m = k == 0 ? 0.0 : (k == 1 ? -margin : margin);
+                const double cost = k == 0 ? 1.0 : 0.5;
+                double ttc = (base + m) / not_zero(ego_speed - other_projected_speed);
+                if (ttc < 0 || !connected) continue;
+                int l0 = 0, l1 = n_lanes;
+                if (OL.road_count == EL.road_count) {
+                    l0 = OL.lane_id;
+                    l1 = l0 + 1;
+                }
+                int times[2] = {(int)(ttc / tq), (int)ceil(ttc / tq)};
+                for (int q = 0; q < 2; ++q) {
+                    int t = times[q];
+                    if (0 <= t && t < n_t)
+                        for (int l = l0; l < l1; ++l)  // positive doubles order like their bit patterns
+                            atomicMax(reinterpret_cast<unsigned long long*>(&st.ttc[si][l][t]),
+                                      (unsigned long long)__double_as_longlong(cost));
+                }
+            }
+        }
+    }
+    group_sync();
+    const int ego_lane_id = EL.lane_id;
+    for (int k = i; k < 9 * n_t; k += G) {
+        int a = k / (3 * n_t), b = (k / n_t) % 3, t = k % n_t;
+        int vrow = n_speeds + speed_index - 1 + a;
+        int src = vrow < 1 + n_speeds ? 0 : (vrow < 1 + n_speeds + (n_speeds - 2) ? 1 + (vrow - (1 + n_speeds)) : n_speeds - 1);
+        if (n_speeds == 1) src = 0;
+        int lcol = n_lanes + ego_lane_id - 1 + b;
+        double val = (lcol < n_lanes || lcol >= 2 * n_lanes) ? 1.0 : st.ttc[src][lcol - n_lanes][t];
+        obs_env[k] = (float)val;
+    }
+}
+
+// envs/common/observation.py:234-276 with explicit features_range (absolute or relative)
+__device__ __forceinline__ void observe_kinematics(const HwyNetParams& P, const GraphShared& g, EnvStage& st,
+                                                   int V, int i, float* __restrict__ obs_env) {
+    const int K = P.obs_vehicles_count;
+    const double ex = st.x[0], ey = st.y[0];
+    const double evx = st.v[0] * st.c[0], evy = st.v[0] * st.s[0];
+    double key = INFINITY;
+    if (i > 0 && i < V) {
+        bool ok = norm2(st.x[i] - ex, st.y[i] - ey) < P.perception_distance;
+        double d = lane_distance_to(g, st, 0, i);
+        ok = ok && (P.obs_see_behind || -2 * kVehLength < d);
+        if (ok) key = fabs(d);
+    }
+    st.key[i] = key;
+    group_sync();
+    int rank = 0, n_valid = 0;
+    for (int u = 1; u < V; ++u) {
+        double ku = st.key[u];
+        n_valid += ku < INFINITY;
+        rank += (ku < key) || (ku == key && u < i);
+    }
+    int row = -1;
+    double r1 = 0, r2 = 0, r3 = 0, r4 = 0;
+    if (i == 0) {
+        row = 0;
+        r1 = ex;
+        r2 = ey;
+        r3 = evx;
+        r4 = evy;
+    } else if (key < INFINITY && rank < K - 1) {
+        row = rank + 1;
+        r1 = st.x[i];
+        r2 = st.y[i];
+        r3 = st.v[i] * st.c[i];
+        r4 = st.v[i] * st.s[i];
+        if (!P.obs_absolute) {
+            r1 -= ex;
+            r2 -= ey;
+            r3 -= evx;
+            r4 -= evy;
+        }
+    }
+    if (row >= 0) {
+        if (P.obs_normalize) {
+            r1 = lmap(r1, P.obs_x_lo, P.obs_x_hi, -1.0, 1.0);
+            r2 = lmap(r2, P.obs_y_lo, P.obs_y_hi, -1.0, 1.0);
+            r3 = lmap(r3, P.obs_vx_lo, P.obs_vx_hi, -1.0, 1.0);
+            r4 = lmap(r4, P.obs_vy_lo, P.obs_vy_hi, -1.0, 1.0);
+            if (P.obs_clip) {
+                r1 = clipd(r1, -1.0, 1.0);
+                r2 = clipd(r2, -1.0, 1.0);
+                r3 = clipd(r3, -1.0, 1.0);
+                r4 = clipd(r4, -1.0, 1.0);
+            }
+        }
+        float* o = obs_env + 5 * row;
+        o[0] = 1.0f;
+        o[1] = (float)r1;
+        o[2] = (float)r2;
+        o[3] = (float)r3;
+        o[4] = (float)r4;
+    }
+    int filled = 1 + (n_valid < K - 1 ? n_valid : K - 1);
+    for (int k = i; k < K; k += G)
+        if (k >= filled) {
+            float* o = obs_env + 5 * k;
+            o[0] = o[1] = o[2] = o[3] = o[4] = 0.0f;
+        }
+}
+
+__device__ __forceinline__ int obs_size(const HwyNetParams& P) {
+    if (P.obs_type == HWY_OBS_TTC) return 9 * (int)(P.ttc_horizon / (1.0 / P.policy_frequency));
+    return P.obs_vehicles_count * 5;
+}
+
+// ------------------------------------------------------------------ state I/O
+struct Regs {
+    double x, y, heading, speed, target_speed, timer, delta, imp_x, imp_y;
+    int meta;
+};
+__device__ __forceinline__ void load_regs(const HwyNetState& S, size_t slot, Regs& r) {
+    double2 a = reinterpret_cast<const double2*>(S.pos)[slot];
+    double2 b = reinterpret_cast<const double2*>(S.hs)[slot];
+    double2 c = reinterpret_cast<const double2*>(S.tt)[slot];
+    double2 d = reinterpret_cast<const double2*>(S.imp)[slot];
+    r.x = a.x;
+    r.y = a.y;
+    r.heading = b.x;
+    r.speed = b.y;
+    r.target_speed = c.x;
+    r.timer = c.y;
+    r.imp_x = d.x;
+    r.imp_y = d.y;
+    r.delta = S.delta[slot];
+    r.meta = S.meta[slot];
+}
+__device__ __forceinline__ void store_regs(const HwyNetState& S, size_t slot, const Regs& r) {
+    reinterpret_cast<double2*>(S.pos)[slot] = make_double2(r.x, r.y);
+    reinterpret_cast<double2*>(S.hs)[slot] = make_double2(r.heading, r.speed);
+    reinterpret_cast<double2*>(S.tt)[slot] = make_double2(r.target_speed, r.timer);
+    reinterpret_cast<double2*>(S.imp)[slot] = make_double2(r.imp_x, r.imp_y);
+    S.meta[slot] = r.meta;
+}
+__device__ __forceinline__ void publish(EnvStage& st, int i, const Regs& r) {
+    double sn, cs;
+    m_sincos(r.heading, &sn, &cs);
+    st.x[i] = r.x;
+    st.y[i] = r.y;
+    st.heading[i] = r.heading;
+    st.c[i] = cs;
+    st.s[i] = sn;
+    st.v[i] = r.speed;
+    st.ts[i] = r.target_speed;
+}
+
+__device__ __forceinline__ void stage_graph(GraphShared& gs, const HwyNetGraph* __restrict__ graph) {
+    // word-wise copy of the immutable lane table into shared memory
+    static_assert(sizeof(GraphShared) == sizeof(HwyNetGraph), "layout");
+    const int* src = reinterpret_cast<const int*>(graph);
+    int* dst = reinterpret_cast<int*>(&gs);
+    for (int k = threadIdx.x; k < (int)(sizeof(HwyNetGraph) / sizeof(int)); k += blockDim.x) dst[k] = src[k];
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------ the step kernel
+__global__ void __launch_bounds__(kBlockThreads)
+network_step_kernel(const HwyNetParams P, const HwyNetGraph* __restrict__ graph, const HwyNetState S,
+                    const int32_t* __restrict__ action, float* __restrict__ obs,
+                    double* __restrict__ reward, uint8_t* __restrict__ terminated,
+                    uint8_t* __restrict__ truncated, double* __restrict__ info_speed,
+                    uint8_t* __restrict__ info_crashed) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    GraphShared& g = *reinterpret_cast<GraphShared*>(smem_raw);
+    EnvStage* stages = reinterpret_cast<EnvStage*>(smem_raw + ((sizeof(GraphShared) + 15) & ~size_t(15)));
+    stage_graph(g, graph);
+
+    const int sub = threadIdx.x / G, i = threadIdx.x % G;
+    const int env = blockIdx.x * kBlockEnvs + sub;
+    const bool env_ok = env < S.n_envs;
+    const int e = env_ok ? env : S.n_envs - 1;
+    EnvStage& st = stages[sub];
+    const int V = P.n_vehicles;
+    const bool active = i < V;
+    const size_t slot = (size_t)e * S.vp + i;
+
+    Regs r;
+    load_regs(S, slot, r);
+    const int kind = meta_kind(r.meta);
+    int speed_index = i == 0 ? S.speed_index[e] : 0;
+    {
+        const int* src = S.route + slot * R;
+        for (int k = 0; k < R; ++k) st.route[i][k] = src[k];
+        st.route_len[i] = S.route_len[slot];
+    }
+    const int frames = P.simulation_frequency / P.policy_frequency;
+    const double dt = 1.0 / P.simulation_frequency;
+    const int act = action[e];
+    double sin_beta = 0.0, cos_beta = 1.0, act_accel = 0.0;
+
+    publish(st, i, r);
+    st.lane[i] = meta_lane(r.meta);
+    st.tgt[i] = meta_target(r.meta);
+    group_sync();
+
+    for (int frame = 0; frame < frames; ++frame) {
+        // ---- Road.act (road/road.py:464-467), ordered part: follow_road + lane-change policy,
+        // one vehicle at a time in list order (later vehicles read earlier vehicles' new targets).
+        if (frame == 0 && i == 0) {
+            // action_type.act: MDPVehicle.act (controller.py:295-315) -> ControlledVehicle.act
+            follow_road(g, st, 0);
+            if (act == 3 || act == 4) {
+                int idx = speed_to_index(P, r.speed) + (act == 3 ? 1 : -1);
+                idx = max(0, min(idx, P.n_target_speeds - 1));
+                speed_index = idx;
+                r.target_speed = P.target_speeds[idx];
+                st.ts[0] = r.target_speed;
+            } else if (act == 0 || act == 2) {
+                const HwyNetLane& T = g.lanes[st.tgt[0]];
+                int id = max(0, min(T.lane_id + (act == 2 ? 1 : -1), T.road_count - 1));
+                int cand = T.road_first + id;
+                if (lane_reachable(g.lanes[cand], r.x, r.y)) st.tgt[0] = cand;
+            }
+        }
+        group_sync();
+        const bool crashed = (r.meta & HWY_META_CRASHED) != 0;
+        for (int v = 0; v < V; ++v) {
+            if (i == v) {
+                if (kind == HWY_KIND_IDM) {
+                    if (!crashed) {  // behavior.py:102-103
+                        follow_road(g, st, v);
+                        r.timer = change_lane_policy(P, g, st, V, v, r.delta, r.timer);
+                    }
+                } else {
+                    follow_road(g, st, v);  // ControlledVehicle.act(None) (controller.py:98)
+                }
+            }
+            group_sync();
+        }
+        // ---- parallel part: steering + acceleration, then Vehicle.step
+        if (active) {
+            const int lane = st.lane[i], tgt = st.tgt[i];
+            sin_beta = 0.0;
+            cos_beta = 1.0;
+            if (!crashed) {
+                double xs = steering_sin_slip(g.lanes[tgt], r.x, r.y, r.heading, r.speed);
+                beta_of_controlled(xs, sin_beta, cos_beta);
+            }
+            if (kind == HWY_KIND_IDM) {
+                if (!crashed) {
+                    int f, rr;
+                    neighbours(g, st, V, i, lane, f, rr);
+                    double acc = idm_acceleration(P, g, st, r.delta, i, f);
+                    if (lane != tgt) {
+                        neighbours(g, st, V, i, tgt, f, rr);
+                        acc = fmin(acc, idm_acceleration(P, g, st, r.delta, i, f));
+                    }
+                    act_accel = clipd(acc, -P.acc_max, P.acc_max);
+                }
+            } else {
+                act_accel = kKpA * (r.target_speed - r.speed);
+            }
+            // Vehicle.step (kinematics.py:130-177), IDMVehicle.step timer (behavior.py:139-148)
+            if (kind == HWY_KIND_IDM) r.timer += dt;
+            if (crashed) act_accel = -1.0 * r.speed;
+            if (r.speed > kMaxSpeed)
+                act_accel = fmin(act_accel, 1.0 * (kMaxSpeed - r.speed));
+            else if (r.speed < kMinSpeed)
+                act_accel = fmax(act_accel, 1.0 * (kMinSpeed - r.speed));
+            const double ch = st.c[i], sh = st.s[i];
+            double cs = ch * cos_beta - sh * sin_beta, sn = sh * cos_beta + ch * sin_beta;
+            r.x += (r.speed * cs) * dt;
+            r.y += (r.speed * sn) * dt;
+            if (r.meta & HWY_META_HAS_IMPACT) {
+                r.x += r.imp_x;
+                r.y += r.imp_y;
+                r.meta = (r.meta | HWY_META_CRASHED) & ~HWY_META_HAS_IMPACT;
+            }
+            r.heading += r.speed * sin_beta / (kVehLength / 2) * dt;
+            r.speed += act_accel * dt;
+        }
+        group_sync();  // everyone is done reading the pre-step staging
+        if (active) publish(st, i, r);
+        group_sync();
+        // ---- on_state_update: closest lane of every vehicle, cooperatively
+        int nl = closest_lane_group(g, st, V, i);
+        if (active) st.lane[i] = nl;
+        group_sync();
+        // ---- Road.step collision sweep (road/road.py:477-481): partners in ascending order, so
+        // the surviving impact is the one of the largest partner index
+        if (active) {
+            const double diag = sqrt(kVehLength * kVehLength + kVehWidth * kVehWidth);
+            for (int j = 0; j < V; ++j) {
+                if (j == i) continue;
+                int a = i < j ? i : j, b = i < j ? j : i;
+                double dist = norm2(st.x[b] - st.x[a], st.y[b] - st.y[a]);
+                if (dist > (diag + diag) / 2 + st.v[a] * dt) continue;
+                Quad pa = make_polygon(st.x[a], st.y[a], st.c[a], st.s[a]);
+                Quad pb = make_polygon(st.x[b], st.y[b], st.c[b], st.s[b]);
+                bool inter, will;
+                double trx, try_;
+                polygons_intersecting(pa, pb, st.v[a] * st.c[a] * dt, st.v[a] * st.s[a] * dt,
+                                      st.v[b] * st.c[b] * dt, st.v[b] * st.s[b] * dt, inter, will, trx, try_);
+                if (will) {
+                    r.imp_x = i == a ? trx / 2 : -trx / 2;
+                    r.imp_y = i == a ? try_ / 2 : -try_ / 2;
+                    r.meta |= HWY_META_HAS_IMPACT;
+                }
+                if (inter) r.meta |= HWY_META_CRASHED;
+            }
+        }
+    }
+
+    // ---- epilogue
+    if (active) {
+        r.meta = meta_set_target(meta_set_lane(r.meta, st.lane[i]), st.tgt[i]);
+        if (env_ok) {
+            store_regs(S, slot, r);
+            int* dst = S.route + slot * R;
+            for (int k = 0; k < R; ++k) dst[k] = st.route[i][k];
+            S.route_len[slot] = st.route_len[i];
+        }
+    }
+    float* obs_env = obs + (size_t)e * obs_size(P);
+    if (P.obs_type == HWY_OBS_TTC)
+        observe_ttc(P, g, st, V, i, speed_index, obs_env);
+    else
+        observe_kinematics(P, g, st, V, i, obs_env);
+    if (i == 0 && env_ok) {
+        // envs/roundabout_env.py:44-71
+        const HwyNetLane& L = g.lanes[st.lane[0]];
+        double es, elat;
+        lane_local(L, r.x, r.y, es, elat);
+        bool on_road = lane_on(L, es, elat, 0.0);
+        bool is_crashed = (r.meta & HWY_META_CRASHED) != 0;
+        double rew = 0.0;
+        rew = rew + P.collision_reward * (is_crashed ? 1.0 : 0.0);
+        rew = rew + P.high_speed_reward * ((double)speed_index / (double)(3 - 1));
+        rew = rew + P.lane_change_reward * ((act == 0 || act == 2) ? 1.0 : 0.0);
+        rew = rew + 0.0 * (on_road ? 1.0 : 0.0);
+        if (P.normalize_reward) rew = lmap(rew, P.collision_reward, P.high_speed_reward, 0.0, 1.0);
+        rew *= on_road ? 1.0 : 0.0;
+        double t = S.time[e] + 1.0 / P.policy_frequency;
+        S.time[e] = t;
+        S.speed_index[e] = speed_index;
+        reward[e] = rew;
+        terminated[e] = (uint8_t)is_crashed;
+        truncated[e] = (uint8_t)(t >= P.duration);
+        if (info_speed) info_speed[e] = r.speed;
+        if (info_crashed) info_crashed[e] = (uint8_t)is_crashed;
+    }
+}
+
+__global__ void __launch_bounds__(kBlockThreads)
+network_observe_kernel(const HwyNetParams P, const HwyNetGraph* __restrict__ graph, const HwyNetState S,
+                       float* __restrict__ obs) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    GraphShared& g = *reinterpret_cast<GraphShared*>(smem_raw);
+    EnvStage* stages = reinterpret_cast<EnvStage*>(smem_raw + ((sizeof(GraphShared) + 15) & ~size_t(15)));
+    stage_graph(g, graph);
+    const int sub = threadIdx.x / G, i = threadIdx.x % G;
+    const int env = blockIdx.x * kBlockEnvs + sub;
+    const bool env_ok = env < S.n_envs;
+    const int e = env_ok ? env : S.n_envs - 1;
+    EnvStage& st = stages[sub];
+    const size_t slot = (size_t)e * S.vp + i;
+    Regs r;
+    load_regs(S, slot, r);
+    {
+        const int* src = S.route + slot * R;
+        for (int k = 0; k < R; ++k) st.route[i][k] = src[k];
+        st.route_len[i] = S.route_len[slot];
+    }
+    publish(st, i, r);
+    st.lane[i] = meta_lane(r.meta);
+    st.tgt[i] = meta_target(r.meta);
+    group_sync();
+    float* obs_env = obs + (size_t)e * obs_size(P);
+    const int speed_index = S.speed_index[e];
+    if (P.obs_type == HWY_OBS_TTC)
+        observe_ttc(P, g, st, P.n_vehicles, i, speed_index, obs_env);
+    else
+        observe_kinematics(P, g, st, P.n_vehicles, i, obs_env);
+}
+
+}  // namespace hwynet
+
+// ====================================================================== C ABI
+namespace {
+using hwy_abi::check_launch;
+using hwy_abi::fail;
+
+int validate_net(const HwyNetParams* p, const HwyNetGraph* graph, const HwyNetState* s) {
+    if (!p || !graph || !s) return fail("%s", "null params/graph/state");
+    if (p->n_vehicles < 1 || p->n_vehicles > HWY_NET_GROUP) return fail("%s", "n_vehicles out of range for the network kernels");
+    if (p->n_target_speeds < 1 || p->n_target_speeds > 3) return fail("%s", "network kernels support up to 3 target speeds");
+    if (p->obs_type != HWY_OBS_KINEMATICS && p->obs_type != HWY_OBS_TTC) return fail("%s", "unknown obs_type");
+    if (p->obs_type == HWY_OBS_TTC && (p->ttc_horizon * p->policy_frequency < 1 || p->ttc_horizon * p->policy_frequency > 12))
+        return fail("%s", "ttc horizon out of range");
+    if (p->obs_type == HWY_OBS_KINEMATICS && (p->obs_vehicles_count < 1 || p->obs_vehicles_count > HWY_MAX_OBS_VEHICLES))
+        return fail("%s", "obs_vehicles_count out of range");
+    if (p->simulation_frequency < 1 || p->policy_frequency < 1 || p->simulation_frequency < p->policy_frequency)
+        return fail("%s", "bad simulation/policy frequency");
+    if (s->n_envs < 1 || s->vp != HWY_NET_GROUP) return fail("%s", "bad n_envs / slot stride");
+    if (!s->pos || !s->hs || !s->tt || !s->imp || !s->delta || !s->meta || !s->route || !s->route_len ||
+        !s->speed_index || !s->time)
+        return fail("%s", "null state pointer");
+    int dev_count = 0;
+    if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count < 1) {
+        cudaGetLastError();
+        return fail("%s", "no CUDA device: this library has no CPU fallback");
+    }
+    return 0;
+}
+
+size_t net_smem_bytes() {
+    return ((sizeof(hwynet::GraphShared) + 15) & ~size_t(15)) + hwynet::kBlockEnvs * sizeof(hwynet::EnvStage);
+}
+template <typename K>
+int configure_smem(K kernel) {
+    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)net_smem_bytes());
+    if (err != cudaSuccess) return fail("cudaFuncSetAttribute: %s", cudaGetErrorString(err));
+    return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int hwy_network_obs_size(const HwyNetParams* p) {
+    if (!p) return 0;
+    if (p->obs_type == HWY_OBS_TTC) return 9 * (int)(p->ttc_horizon / (1.0 / p->policy_frequency));
+    return p->obs_vehicles_count * 5;
+}
+
+int hwy_network_step(const HwyNetParams* p, const HwyNetGraph* graph, const HwyNetState* s,
+                     const int32_t* action, float* obs, double* reward, uint8_t* terminated,
+                     uint8_t* truncated, double* info_speed, uint8_t* info_crashed, void* stream) {
+    if (validate_net(p, graph, s)) return 1;
+    if (!action || !obs || !reward || !terminated || !truncated) return fail("%s", "null pointer");
+    if (configure_smem(hwynet::network_step_kernel)) return 1;
+    int blocks = (s->n_envs + hwynet::kBlockEnvs - 1) / hwynet::kBlockEnvs;
+    hwynet::network_step_kernel<<<blocks, hwynet::kBlockThreads, net_smem_bytes(), (cudaStream_t)stream>>>(
+        *p, graph, *s, action, obs, reward, terminated, truncated, info_speed, info_crashed);
+    return check_launch("network_step_kernel");
+}
+
+int hwy_network_observe(const HwyNetParams* p, const HwyNetGraph* graph, const HwyNetState* s, float* obs,
+                        void* stream) {
+    if (validate_net(p, graph, s)) return 1;
+    if (!obs) return fail("%s", "obs is null");
+    if (configure_smem(hwynet::network_observe_kernel)) return 1;
+    int blocks = (s->n_envs + hwynet::kBlockEnvs - 1) / hwynet::kBlockEnvs;
+    hwynet::network_observe_kernel<<<blocks, hwynet::kBlockThreads, net_smem_bytes(), (cudaStream_t)stream>>>(
+        *p, graph, *s, obs);
+    return check_launch("network_observe_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,412 @@
+"""Batched roundabout-v0 on the B200 backend.
+
+Host-side mirror of the reference's ``RoundaboutEnv`` (highway_env/envs/roundabout_env.py:12-391):
+same config dictionary, road geometry and spawn procedure; stepping runs in
+``hwy_network_step`` (include/hwyb200.h) for ``num_envs`` independent roundabouts.
+
+Reset is host-exact: every env owns the numpy ``Generator(PCG64)`` a reference env seeded with
+``seed + env_index_offset + i`` would own and ``_make_vehicles`` draws from it in the reference's
+order (normal, normal, choice, uniform per traffic vehicle); positions use the same numpy lane
+expressions as the reference.  Autoreset (SameStep) therefore goes through the host: the ended
+envs' states are rebuilt with numpy and uploaded.  (The highway family resets on the device.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Optional
+
+import numpy as np
+import torch
+
+from .. import _native as N
+from ..config import default_config
+from ..road.network import NetworkTable
+from ..spaces import Box, Discrete, batch_space
+from .common.action import DiscreteMetaAction
+
+
+def make_roundabout_network() -> NetworkTable:
+    """RoundaboutEnv._make_road (roundabout_env.py:77-315): two rings of 8 circular arcs
+    (radii 20 / 24 m), and per branch a straight access road, a sine entry and a sine exit."""
+    net = NetworkTable()
+    center, radius, alpha = [0, 0], 20, 24
+    radii = [radius, radius + 4]
+    # (from, to, start angle [deg], end angle [deg]) in the reference's insertion order
+    arcs = [
+        ("se", "ex", 90 - alpha, alpha), ("ex", "ee", alpha, -alpha), ("ee", "nx", -alpha, -90 + alpha),
+        ("nx", "ne", -90 + alpha, -90 - alpha), ("ne", "wx", -90 - alpha, -180 + alpha),
+        ("wx", "we", -180 + alpha, -180 - alpha), ("we", "sx", 180 - alpha, 90 + alpha),
+        ("sx", "se", 90 + alpha, 90 - alpha),
+    ]
+    for lane in (0, 1):
+        for f, t, a0, a1 in arcs:
+            net.add_circular(f, t, center, radii[lane], np.deg2rad(a0), np.deg2rad(a1), clockwise=False)
+    access, dev, a = 170, 85, 5
+    delta_st = 0.2 * dev
+    delta_en = dev - delta_st
+    w = 2 * np.pi / dev
+    ph_in, ph_out = -np.pi / 2, -np.pi / 2 + w * delta_en
+    # south
+    net.add_straight("ser", "ses", [2, access], [2, dev / 2])
+    net.add_straight("ses", "se", [2 + a, dev / 2], [2 + a, dev / 2 - delta_st], sine=(a, w, ph_in))
+    net.add_straight("sx", "sxs", [-2 - a, -dev / 2 + delta_en], [-2 - a, dev / 2], sine=(a, w, ph_out))
+    net.add_straight("sxs", "sxr", [-2, dev / 2], [-2, access])
+    # east
+    net.add_straight("eer", "ees", [access, -2], [dev / 2, -2])
+    net.add_straight("ees", "ee", [dev / 2, -2 - a], [dev / 2 - delta_st, -2 - a], sine=(a, w, ph_in))
+    net.add_straight("ex", "exs", [-dev / 2 + delta_en, 2 + a], [dev / 2, 2 + a], sine=(a, w, ph_out))
+    net.add_straight("exs", "exr", [dev / 2, 2], [access, 2])
+    # north
+    net.add_straight("ner", "nes", [-2, -access], [-2, -dev / 2])
+    net.add_straight("nes", "ne", [-2 - a, -dev / 2], [-2 - a, -dev / 2 + delta_st], sine=(a, w, ph_in))
+    net.add_straight("nx", "nxs", [2 + a, dev / 2 - delta_en], [2 + a, -dev / 2], sine=(a, w, ph_out))
+    net.add_straight("nxs", "nxr", [2, -dev / 2], [2, -access])
+    # west
+    net.add_straight("wer", "wes", [-access, 2], [-dev / 2, 2])
+    net.add_straight("wes", "we", [-dev / 2, 2 + a], [-dev / 2 + delta_st, 2 + a], sine=(a, w, ph_in))
+    net.add_straight("wx", "wxs", [dev / 2 - delta_en, -2 - a], [-dev / 2, -2 - a], sine=(a, w, ph_out))
+    net.add_straight("wxs", "wxr", [-dev / 2, -2], [-access, -2])
+    net.finalize()
+    return net
+
+
+class RoundaboutSpawner:
+    """RoundaboutEnv._make_vehicles (roundabout_env.py:317-391) with numpy, for a list of per-env
+    generators (CPU only; testable without a GPU)."""
+
+    N_VEHICLES = 5
+    DESTINATIONS = ["exr", "sxr", "nxr"]  # roundabout_env.py:345
+
+    def __init__(self, net: NetworkTable, config: dict, target_speeds: np.ndarray) -> None:
+        self.net, self.config, self.target_speeds = net, config, np.asarray(target_speeds, dtype=np.float64)
+        self._route_cache = {}
+
+    def _route_of(self, lane_idx: int, destination: str):
+        key = (lane_idx, destination)
+        if key not in self._route_cache:
+            li = self.net.lane_index_of[lane_idx]
+            self._route_cache[key] = self.net.encode_route(self.net.plan_route(li, destination))
+        return self._route_cache[key]
+
+    def spawn(self, rngs) -> dict:
+        net, m, V = self.net, len(rngs), self.N_VEHICLES
+        position_deviation = speed_deviation = 2.0
+        fixed_dest = self.config["incoming_vehicle_destination"]
+        # per-env draws, in the reference's order: for each of the 4 traffic vehicles
+        # normal (longitudinal), normal (speed), choice(destinations), uniform (DELTA)
+        lon = np.zeros((m, 4))
+        spd = np.zeros((m, 4))
+        dest = np.zeros((m, 4), dtype=np.int64)
+        delta = np.zeros((m, 4))
+        base_lon = [5.0, 20.0 * float(1), 20.0 * float(-1), 50.0]
+        for k, g in enumerate(rngs):
+            for j in range(4):
+                lon[k, j] = base_lon[j] + g.normal() * position_deviation
+                spd[k, j] = 16.0 + g.normal() * speed_deviation if j else 16 + g.normal() * speed_deviation
+                if j == 0 and fixed_dest is not None:
+                    dest[k, j] = int(fixed_dest)
+                else:
+                    dest[k, j] = self.DESTINATIONS.index(str(g.choice(self.DESTINATIONS)))
+                delta[k, j] = g.uniform(low=3.5, high=4.5)  # randomize_behavior, behavior.py:66-69
+        spawn_lane = [net.index[("we", "sx", 1)], net.index[("we", "sx", 0)], net.index[("we", "sx", 0)],
+                      net.index[("eer", "ees", 0)]]
+        x, y, h, v = (np.zeros((m, V)) for _ in range(4))
+        ego_lane = net.index[("ser", "ses", 0)]
+        ex, ey = net.position(ego_lane, 125.0, 0.0)
+        x[:, 0], y[:, 0], h[:, 0], v[:, 0] = ex, ey, net.heading_at(ego_lane, 140.0), 8.0
+        for j in range(4):
+            px, py = net.position(spawn_lane[j], lon[:, j], 0.0)  # make_on_lane, objects.py:68-90
+            x[:, j + 1], y[:, j + 1] = px, py
+            h[:, j + 1] = net.heading_at(spawn_lane[j], lon[:, j])
+            v[:, j + 1] = spd[:, j]
+        lane = np.stack([net.closest_lane(x[:, c], y[:, c], h[:, c]) for c in range(V)], axis=1)
+        route = np.zeros((m, V, N.HWY_NET_MAX_ROUTE), dtype=np.int32)
+        route_len = np.zeros((m, V), dtype=np.int32)
+        for k in range(m):
+            route[k, 0], route_len[k, 0] = self._route_of(int(lane[k, 0]), "nxs")
+            for j in range(4):
+                route[k, j + 1], route_len[k, j + 1] = self._route_of(int(lane[k, j + 1]), self.DESTINATIONS[dest[k, j]])
+        ts = self.target_speeds
+        si = int(np.clip(np.round((8.0 - ts[0]) / (ts[-1] - ts[0]) * (ts.size - 1)), 0, ts.size - 1))
+        target_speed = v.copy()
+        target_speed[:, 0] = ts[si]
+        timer = ((x + y) * np.pi) % 1.0  # IDMVehicle.__init__, behavior.py:64
+        timer[:, 0] = 0.0
+        dl = np.full((m, V), 4.0)
+        dl[:, 1:] = delta
+        kind = np.zeros((m, V), dtype=np.int64)
+        kind[:, 0] = N.KIND_MDP
+        return dict(x=x, y=y, heading=h, speed=v, target_speed=target_speed, timer=timer, delta=dl, lane=lane,
+                    target_lane=lane.copy(), kind=kind, route=route, route_len=route_len,
+                    speed_index=np.full(m, si, dtype=np.int32))
+
+
+
+class TimeToCollisionObservation:
+    """TimeToCollisionObservation (reference envs/common/observation.py:115-152): [3, 3, horizon]."""
+
+    def __init__(self, horizon: int = 10, **kwargs):
+        self.horizon = int(horizon)
+
+    def space(self, policy_frequency: int = 1):
+        return Box(low=0, high=1, shape=(3, 3, int(self.horizon * policy_frequency)), dtype=np.float32)
+
+
+class BatchedRoundaboutEnv:
+    ENV_ID = "roundabout-v0"
+    N_VEHICLES = 5
+    metadata = {"render_modes": [], "autoreset_mode": "SameStep"}
+
+    @classmethod
+    def default_config(cls) -> dict:
+        return default_config(cls.ENV_ID)
+
+    def __init__(self, config: Optional[dict] = None, render_mode: Optional[str] = None, num_envs: int = 1,
+                 device: Any = None, autoreset_mode: str = "SameStep", env_index_offset: int = 0) -> None:
+        if render_mode is not None:
+            raise NotImplementedError("rendering is out of scope of the accelerated path")
+        if not torch.cuda.is_available():
+            raise RuntimeError("highwayenv_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        if autoreset_mode not in ("SameStep", "Disabled"):
+            raise NotImplementedError(autoreset_mode)
+        self._lib = N.load()
+        self.render_mode = None
+        self.num_envs = int(num_envs)
+        self.device = torch.device(device if device is not None else "cuda")
+        self.autoreset_mode = autoreset_mode
+        self.env_index_offset = int(env_index_offset)
+        self.config = self.default_config()
+        if config:
+            self.config.update(config)
+        self.net = make_roundabout_network()
+        self._graph_dev = torch.from_numpy(
+            np.frombuffer(bytes(self.net.to_struct()), dtype=np.uint8).copy()).to(self.device)
+        self._rngs = None
+        self.define_spaces()
+        self._allocate()
+
+    # ------------------------------------------------------------------ configuration
+    def configure(self, config: Optional[dict]) -> None:
+        if config:
+            self.config.update(config)
+
+    def define_spaces(self) -> None:
+        cfg = self.config
+        act = cfg["action"]
+        if act["type"] != "DiscreteMetaAction":
+            if act["type"] in ("ContinuousAction", "DiscreteAction", "MultiAgentAction"):
+                raise NotImplementedError(f"action type {act['type']!r} on roundabout-v0")
+            raise ValueError("Unknown action type")
+        self.action_type = DiscreteMetaAction(**act)
+        if self.action_type.target_speeds.size > 3:
+            raise NotImplementedError("more than 3 target speeds on the network kernels")
+        obs = cfg["observation"]
+        p = N.HwyNetParams()
+        p.n_vehicles = self.N_VEHICLES
+        p.simulation_frequency = int(cfg["simulation_frequency"])
+        p.policy_frequency = int(cfg["policy_frequency"])
+        p.n_target_speeds = int(self.action_type.target_speeds.size)
+        for k, t in enumerate(self.action_type.target_speeds):
+            p.target_speeds[k] = float(t)
+        if obs["type"] == "TimeToCollision":
+            self.observation_type = TimeToCollisionObservation(**obs)
+            p.obs_type = N.OBS_TTC
+            p.ttc_horizon = self.observation_type.horizon
+            p.obs_vehicles_count = 5
+            self.single_observation_space = self.observation_type.space(p.policy_frequency)
+        elif obs["type"] == "Kinematics":
+            fr = obs.get("features_range")
+            if fr is None:
+                raise NotImplementedError("Kinematics without features_range on roundabout-v0")
+            if obs.get("features") not in (None, ["presence", "x", "y", "vx", "vy"]) or obs.get("order", "sorted") != "sorted":
+                raise NotImplementedError("Kinematics features / order")
+            p.obs_type = N.OBS_KINEMATICS
+            p.obs_vehicles_count = int(obs.get("vehicles_count", 5))
+            p.obs_see_behind = int(bool(obs.get("see_behind", False)))
+            p.obs_absolute = int(bool(obs.get("absolute", False)))
+            p.obs_normalize = int(bool(obs.get("normalize", True)))
+            p.obs_clip = int(bool(obs.get("clip", True)))
+            (p.obs_x_lo, p.obs_x_hi), (p.obs_y_lo, p.obs_y_hi) = (map(float, fr["x"]), map(float, fr["y"]))
+            (p.obs_vx_lo, p.obs_vx_hi), (p.obs_vy_lo, p.obs_vy_hi) = (map(float, fr["vx"]), map(float, fr["vy"]))
+            self.observation_type = None
+            self.single_observation_space = Box(low=-np.inf, high=np.inf, shape=(p.obs_vehicles_count, 5),
+                                                dtype=np.float32)
+        elif obs["type"] in ("OccupancyGrid", "KinematicsGoal", "GrayscaleObservation", "LidarObservation"):
+            raise NotImplementedError(f"observation type {obs['type']!r} on roundabout-v0")
+        else:
+            raise ValueError("Unknown observation type")
+        p.normalize_reward = int(bool(cfg["normalize_reward"]))
+        p.duration = float(cfg["duration"])
+        p.collision_reward = float(cfg["collision_reward"])
+        p.high_speed_reward = float(cfg["high_speed_reward"])
+        p.lane_change_reward = float(cfg["lane_change_reward"])
+        p.acc_max, p.comfort_acc_max, p.comfort_acc_min = 6.0, 3.0, -5.0  # behavior.py:21-46
+        p.distance_wanted, p.time_wanted = 10.0, 1.5
+        p.politeness, p.lane_change_min_acc_gain = 0.0, 0.2
+        p.lane_change_max_braking_imposed, p.lane_change_delay = 2.0, 1.0
+        p.perception_distance = 200.0
+        self._params = p
+        self.single_action_space = Discrete(5)
+        self.spawner = RoundaboutSpawner(self.net, self.config, self.action_type.target_speeds)
+        self.observation_space = batch_space(self.single_observation_space, self.num_envs)
+        self.action_space = batch_space(self.single_action_space, self.num_envs)
+        self.obs_shape = tuple(self.single_observation_space.shape)
+
+    def _allocate(self) -> None:
+        n, dev, vp = self.num_envs, self.device, N.HWY_NET_GROUP
+        z = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, device=dev)  # noqa: E731
+        self.V, self.vp = self.N_VEHICLES, vp
+        self._pos, self._hs, self._tt, self._imp = (z(n, vp, 2, dtype=torch.float64) for _ in range(4))
+        self._delta = z(n, vp, dtype=torch.float64)
+        self._meta = z(n, vp, dtype=torch.int32)
+        self._route = z(n, vp, N.HWY_NET_MAX_ROUTE, dtype=torch.int32)
+        self._route_len = z(n, vp, dtype=torch.int32)
+        self._speed_index = z(n, dtype=torch.int32)
+        self._time = z(n, dtype=torch.float64)
+        self._obs = z(n, *self.obs_shape, dtype=torch.float32)
+        self._final_obs = z(n, *self.obs_shape, dtype=torch.float32)
+        self._reward = z(n, dtype=torch.float64)
+        self._terminated = z(n, dtype=torch.uint8)
+        self._truncated = z(n, dtype=torch.uint8)
+        self._info_speed = z(n, dtype=torch.float64)
+        self._info_crashed = z(n, dtype=torch.uint8)
+        self._action_buf = z(n, dtype=torch.int32)
+        st = N.HwyNetState()
+        st.n_envs, st.vp = n, vp
+        st.pos, st.hs, st.tt, st.imp = (t.data_ptr() for t in (self._pos, self._hs, self._tt, self._imp))
+        st.delta, st.meta = self._delta.data_ptr(), self._meta.data_ptr()
+        st.route, st.route_len = self._route.data_ptr(), self._route_len.data_ptr()
+        st.speed_index, st.time = self._speed_index.data_ptr(), self._time.data_ptr()
+        self._state = st
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    # ------------------------------------------------------------------ host-exact reset
+    def _spawn(self, env_ids: np.ndarray) -> dict:
+        return self.spawner.spawn([self._rngs[e] for e in env_ids])
+
+    def _upload(self, env_ids: np.ndarray, sp: dict) -> None:
+        dev, V = self.device, self.N_VEHICLES
+        idx = torch.from_numpy(np.asarray(env_ids, dtype=np.int64)).to(dev)
+        f = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+        self._pos[idx, :V] = f(np.stack([sp["x"], sp["y"]], axis=-1))
+        self._hs[idx, :V] = f(np.stack([sp["heading"], sp["speed"]], axis=-1))
+        self._tt[idx, :V] = f(np.stack([sp["target_speed"], sp["timer"]], axis=-1))
+        self._imp[idx, :V] = 0.0
+        self._delta[idx, :V] = f(sp["delta"])
+        meta = ((sp["lane"].astype(np.int64) << N.META_LANE_SHIFT) | (sp["target_lane"].astype(np.int64) << N.META_TARGET_SHIFT)
+                | (sp["kind"] << N.META_KIND_SHIFT) | N.META_CHECK_COLLISIONS | N.META_PRESENT).astype(np.int32)
+        self._meta[idx, :V] = f(meta)
+        self._route[idx, :V] = f(sp["route"])
+        self._route_len[idx, :V] = f(sp["route_len"])
+        self._speed_index[idx] = f(sp["speed_index"])
+        self._time[idx] = 0.0
+
+    def _seed_streams(self, seed) -> None:
+        n = self.num_envs
+        if seed is None:
+            ss = np.random.SeedSequence()
+            seeds = [int(s.generate_state(1)[0]) for s in ss.spawn(n)]
+        elif isinstance(seed, (int, np.integer)):
+            seeds = [int(seed) + self.env_index_offset + i for i in range(n)]
+        else:
+            seeds = [int(s) for s in seed]
+        self._rngs = [np.random.Generator(np.random.PCG64(np.random.SeedSequence(s))) for s in seeds]
+        self.np_random_seed = seeds
+
+    # ------------------------------------------------------------------ gym API
+    def reset(self, *, seed=None, options: Optional[dict] = None):
+        if options and "config" in options:
+            self.configure(options["config"])
+            self.define_spaces()
+            self._allocate()
+        if seed is not None or self._rngs is None:
+            self._seed_streams(seed)
+        ids = np.arange(self.num_envs)
+        if options and options.get("reset_mask") is not None:
+            ids = np.nonzero(np.asarray(options["reset_mask"]))[0]
+        if len(ids):
+            self._upload(ids, self._spawn(ids))
+        self.observe()
+        return self._obs, {"speed": self._hs[:, 0, 1], "crashed": (self._meta[:, 0] & N.META_CRASHED) != 0}
+
+    def observe(self) -> torch.Tensor:
+        with torch.cuda.device(self.device):
+            N.check(self._lib.hwy_network_observe(C.byref(self._params), self._graph_dev.data_ptr(),
+                                                  C.byref(self._state), self._obs.data_ptr(), self._stream()))
+        return self._obs
+
+    def step(self, actions):
+        if self._rngs is None:
+            raise RuntimeError("call reset() before step()")
+        buf = self._action_buf
+        if isinstance(actions, torch.Tensor) and actions.device == buf.device and actions.dtype == buf.dtype \
+                and actions.shape == buf.shape and actions.is_contiguous():
+            act = actions
+        else:
+            buf.copy_(torch.as_tensor(np.asarray(actions.cpu() if isinstance(actions, torch.Tensor) else actions))
+                      .reshape(buf.shape).to(buf.dtype), non_blocking=True)
+            act = buf
+        with torch.cuda.device(self.device):
+            N.check(self._lib.hwy_network_step(
+                C.byref(self._params), self._graph_dev.data_ptr(), C.byref(self._state), act.data_ptr(),
+                self._obs.data_ptr(), self._reward.data_ptr(), self._terminated.data_ptr(),
+                self._truncated.data_ptr(), self._info_speed.data_ptr(), self._info_crashed.data_ptr(),
+                self._stream()))
+        info = {"speed": self._info_speed, "crashed": self._info_crashed.view(torch.bool), "action": act}
+        if self.autoreset_mode == "SameStep":
+            done = (self._terminated | self._truncated).cpu().numpy().astype(bool)
+            if done.any():
+                self._final_obs.copy_(self._obs)
+                info["final_obs"] = self._final_obs
+                ids = np.nonzero(done)[0]
+                self._upload(ids, self._spawn(ids))
+                self.observe()
+        return (self._obs, self._reward, self._terminated.view(torch.bool), self._truncated.view(torch.bool), info)
+
+    def close(self) -> None:
+        pass
+
+    @property
+    def unwrapped(self):
+        return self
+
+    # ------------------------------------------------------------------ state import / export
+    def state_dict(self) -> dict:
+        V = self.V
+        pos, hs, tt, imp = (t[:, :V].cpu().numpy() for t in (self._pos, self._hs, self._tt, self._imp))
+        meta = self._meta[:, :V].cpu().numpy()
+        return {
+            "x": pos[..., 0].copy(), "y": pos[..., 1].copy(), "heading": hs[..., 0].copy(),
+            "speed": hs[..., 1].copy(), "target_speed": tt[..., 0].copy(), "timer": tt[..., 1].copy(),
+            "delta": self._delta[:, :V].cpu().numpy(), "impact_x": imp[..., 0].copy(), "impact_y": imp[..., 1].copy(),
+            "lane": (meta >> N.META_LANE_SHIFT) & 0xFF, "target_lane": (meta >> N.META_TARGET_SHIFT) & 0xFF,
+            "kind": (meta >> N.META_KIND_SHIFT) & 3, "crashed": (meta & N.META_CRASHED) != 0,
+            "has_impact": (meta & N.META_HAS_IMPACT) != 0, "check_collisions": (meta & N.META_CHECK_COLLISIONS) != 0,
+            "route": self._route[:, :V].cpu().numpy(), "route_len": self._route_len[:, :V].cpu().numpy(),
+            "speed_index": self._speed_index.cpu().numpy(), "time": self._time.cpu().numpy(),
+        }
+
+    def load_state_dict(self, sd: dict) -> None:
+        n, V, dev = self.num_envs, self.V, self.device
+        f = lambda k: torch.from_numpy(np.ascontiguousarray(sd[k], dtype=np.float64)).to(dev)  # noqa: E731
+        self._pos[:, :V, 0], self._pos[:, :V, 1] = f("x"), f("y")
+        self._hs[:, :V, 0], self._hs[:, :V, 1] = f("heading"), f("speed")
+        self._tt[:, :V, 0], self._tt[:, :V, 1] = f("target_speed"), f("timer")
+        self._imp[:, :V, 0], self._imp[:, :V, 1] = f("impact_x"), f("impact_y")
+        self._delta[:, :V] = f("delta")
+        meta = ((np.asarray(sd["lane"], dtype=np.int64) << N.META_LANE_SHIFT)
+                | (np.asarray(sd["target_lane"], dtype=np.int64) << N.META_TARGET_SHIFT)
+                | (np.asarray(sd["kind"], dtype=np.int64) << N.META_KIND_SHIFT)
+                | np.where(np.asarray(sd["crashed"], dtype=bool), N.META_CRASHED, 0)
+                | np.where(np.asarray(sd["has_impact"], dtype=bool), N.META_HAS_IMPACT, 0)
+                | np.where(np.asarray(sd["check_collisions"], dtype=bool), N.META_CHECK_COLLISIONS, 0)
+                | N.META_PRESENT).astype(np.int32)
+        self._meta[:, :V] = torch.from_numpy(meta.reshape(n, V)).to(dev)
+        self._route[:, :V] = torch.from_numpy(np.ascontiguousarray(sd["route"], dtype=np.int32)).to(dev)
+        self._route_len[:, :V] = torch.from_numpy(np.ascontiguousarray(sd["route_len"], dtype=np.int32)).to(dev)
+        self._speed_index.copy_(torch.from_numpy(np.asarray(sd["speed_index"], dtype=np.int32).reshape(n)))
+        self._time.copy_(torch.from_numpy(np.asarray(sd["time"], dtype=np.float64).reshape(n)))
+        if self._rngs is None:
+            self._seed_streams(0)

@@ -154,6 +154,87 @@ int hwy_highway_autoreset(const HwyHighwayParams *p, const HwyHighwayState *s,
                           const uint8_t *terminated, const uint8_t *truncated, float *obs,
                           void *stream);
 
+
+/* ====================================================================== general road networks
+ * roundabout-v0 (envs/roundabout_env.py): Straight / Sine / Circular lanes (road/lane.py:159-384),
+ * planned routes and RoadNetwork.next_lane (road/road.py:73-157), TimeToCollision or absolute
+ * Kinematics observation.  Same conventions as the highway entry points above. */
+#define HWY_NET_MAX_LANES 64
+#define HWY_NET_MAX_NODES 64
+#define HWY_NET_MAX_SUCC 6
+#define HWY_NET_MAX_ROUTE 16
+#define HWY_NET_GROUP 8 /* vehicle slots per env (threads per env) */
+
+#define HWY_LANE_STRAIGHT 0
+#define HWY_LANE_SINE 1
+#define HWY_LANE_CIRCULAR 2
+
+#define HWY_OBS_KINEMATICS 0
+#define HWY_OBS_TTC 2
+
+/* One lane of RoadNetwork.graph[from][to][lane_id]; table order = graph enumeration order
+ * (road/road.py:65-71: from-node insertion order, to-node insertion order, lane id). */
+typedef struct HwyNetLane {
+    int32_t type, from_node, to_node, lane_id;
+    int32_t road_first, road_count; /* table index of lane 0 of this road; lanes on the road */
+    int32_t forbidden, priority;
+    double width, speed_limit, length;
+    double sx, sy, ex, ey, dx, dy, lx, ly, heading;            /* StraightLane / SineLane base */
+    double amplitude, pulsation, phase;                         /* SineLane */
+    double cx, cy, radius, start_phase, end_phase, direction;   /* CircularLane */
+} HwyNetLane;
+
+/* Device-resident, immutable after construction. */
+typedef struct HwyNetGraph {
+    int32_t n_lanes, n_nodes;
+    HwyNetLane lanes[HWY_NET_MAX_LANES];
+    int32_t succ_count[HWY_NET_MAX_NODES];            /* graph[node].keys() in insertion order: */
+    int32_t succ[HWY_NET_MAX_NODES][HWY_NET_MAX_SUCC]; /* first-lane table index of each road   */
+} HwyNetGraph;
+
+typedef struct HwyNetParams {
+    int32_t n_vehicles; /* <= HWY_NET_GROUP; slot 0 is the MDPVehicle ego */
+    int32_t simulation_frequency, policy_frequency;
+    int32_t n_target_speeds;
+    int32_t obs_type;   /* HWY_OBS_* */
+    int32_t obs_vehicles_count, obs_see_behind, obs_absolute, obs_normalize, obs_clip;
+    int32_t ttc_horizon;
+    int32_t normalize_reward;
+    double duration;
+    double target_speeds[HWY_MAX_TARGET_SPEEDS];
+    double obs_x_lo, obs_x_hi, obs_y_lo, obs_y_hi, obs_vx_lo, obs_vx_hi, obs_vy_lo, obs_vy_hi;
+    double collision_reward, high_speed_reward, lane_change_reward; /* roundabout_env.py:30-34 */
+    double acc_max, comfort_acc_max, comfort_acc_min, distance_wanted, time_wanted;
+    double politeness, lane_change_min_acc_gain, lane_change_max_braking_imposed, lane_change_delay;
+    double perception_distance;
+} HwyNetParams;
+
+/* route entry: from_node | to_node << 8 | (lane_id + 1) << 16  (lane_id + 1 == 0: None) */
+typedef struct HwyNetState {
+    int32_t n_envs;
+    int32_t vp;                  /* slot stride == HWY_NET_GROUP */
+    double *pos, *hs, *tt, *imp; /* [n_envs*vp*2], as HwyHighwayState */
+    double *delta;               /* [n_envs*vp] */
+    int32_t *meta;               /* [n_envs*vp] lane(8) | target lane(8) | flags, as above */
+    int32_t *route;              /* [n_envs*vp*HWY_NET_MAX_ROUTE] ControlledVehicle.route */
+    int32_t *route_len;          /* [n_envs*vp] */
+    int32_t *speed_index;        /* [n_envs] */
+    double *time;                /* [n_envs] */
+} HwyNetState;
+
+/* observation size in floats: Kinematics K*5, TimeToCollision 3*3*(horizon*policy_frequency) */
+int hwy_network_obs_size(const HwyNetParams *p);
+
+/* AbstractEnv.step (abstract.py:259-285) on a general network: action [n_envs] int32
+ * (DiscreteMetaAction labels, action.py:204).  graph is a DEVICE pointer. */
+int hwy_network_step(const HwyNetParams *p, const HwyNetGraph *graph, const HwyNetState *s,
+                     const int32_t *action, float *obs, double *reward, uint8_t *terminated,
+                     uint8_t *truncated, double *info_speed, uint8_t *info_crashed, void *stream);
+
+/* observation_type.observe() of the current state */
+int hwy_network_observe(const HwyNetParams *p, const HwyNetGraph *graph, const HwyNetState *s,
+                        float *obs, void *stream);
+
 /* Kernel launches issued by the calling thread through this library since load (the
  * `gpu_launches` claim of bench.py). */
 uint64_t hwy_launch_count(void);
