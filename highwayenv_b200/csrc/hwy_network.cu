@@ -751,6 +751,8 @@ network_step_kernel(const HwyNetParams P, const HwyNetGraph* __restrict__ graph,
         }
     }
     float* obs_env = obs + (size_t)e * obs_size(P);
+    // the ego's thread owns speed_index: broadcast it to the group for the observation crop
+    speed_index = __shfl_sync(group_mask(), speed_index, 0, G);
     if (P.obs_type == HWY_OBS_TTC)
         observe_ttc(P, g, st, V, i, speed_index, obs_env);
     else
