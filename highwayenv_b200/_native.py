@@ -109,10 +109,22 @@ class HwyNetState(C.Structure):
     ]
 
 
+class HwyRoundaboutSpawn(C.Structure):
+    _fields_ = [
+        ("ego_lane", C.c_int32), ("spawn_lane", C.c_int32 * 4), ("fixed_destination", C.c_int32),
+        ("ego_speed_index", C.c_int32), ("_pad", C.c_int32),
+        ("base_longitudinal", C.c_double * 4),
+        ("ego_longitudinal", C.c_double), ("ego_heading_longitudinal", C.c_double), ("ego_speed", C.c_double),
+        ("position_deviation", C.c_double), ("speed_deviation", C.c_double), ("traffic_speed", C.c_double),
+        ("delta_lo", C.c_double), ("delta_hi", C.c_double),
+        ("route_table", C.c_void_p), ("route_len", C.c_void_p),
+    ]
+
+
 EXPORTS = (
     "hwy_abi_version", "hwy_last_error", "hwy_highway_slot_stride", "hwy_highway_reset",
     "hwy_highway_observe", "hwy_highway_step", "hwy_highway_autoreset", "hwy_launch_count",
-    "hwy_network_obs_size", "hwy_network_step", "hwy_network_observe",
+    "hwy_network_obs_size", "hwy_network_step", "hwy_network_observe", "hwy_roundabout_reset",
 )
 
 _lib = None
@@ -153,6 +165,9 @@ def load():
                                      C.c_void_p, C.c_void_p, C.c_void_p]
     lib.hwy_network_observe.restype = C.c_int
     lib.hwy_network_observe.argtypes = [NP, NG, NS, C.c_void_p, C.c_void_p]
+    lib.hwy_roundabout_reset.restype = C.c_int
+    lib.hwy_roundabout_reset.argtypes = [NP, NG, C.POINTER(HwyRoundaboutSpawn), NS, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]
     if lib.hwy_abi_version() != HWY_ABI_VERSION:
         raise RuntimeError("libhwyb200.so ABI version mismatch; rebuild")
     _lib = lib

@@ -8,6 +8,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "hwy_ziggurat_tables.h"
+
 namespace hwy {
 
 constexpr double kPi = 3.141592653589793;        // np.pi
@@ -102,6 +104,34 @@ struct Pcg64 {
     __device__ __forceinline__ double uniform(double lo, double hi) {
         double range = hi - lo;
         return lo + range * next_double();
+    }
+    // Generator.normal() = random_standard_normal (distributions.c): 256-layer ziggurat on one
+    // 64-bit output (8 bits layer, 1 bit sign, 52 bits magnitude); wedge and tail are rejection
+    // sampled with further doubles.  Bit-exact on the fast path (99.2 %); the wedge/tail paths
+    // use CUDA's exp/log1p, which may differ from numpy's by an ulp.
+    __device__ __noinline__ double normal() {
+        for (;;) {
+            uint64_t r = next64();
+            int idx = (int)(r & 0xff);
+            r >>= 8;
+            int sign = (int)(r & 0x1);
+            uint64_t rabs = (r >> 1) & 0x000fffffffffffffULL;
+            double x = (double)rabs * __longlong_as_double((long long)k_wi_double_bits[idx]);
+            if (sign & 0x1) x = -x;
+            if (rabs < k_ki_double_bits[idx]) return x;
+            if (idx == 0) {
+                for (;;) {
+                    double xx = -kZigguratNorInvR * log1p(-next_double());
+                    double yy = -log1p(-next_double());
+                    if (yy + yy > xx * xx)
+                        return ((rabs >> 8) & 0x1) ? -(kZigguratNorR + xx) : kZigguratNorR + xx;
+                }
+            } else {
+                double f1 = __longlong_as_double((long long)k_fi_double_bits[idx - 1]);
+                double f0 = __longlong_as_double((long long)k_fi_double_bits[idx]);
+                if ((f1 - f0) * next_double() + f0 < exp(-0.5 * x * x)) return x;
+            }
+        }
     }
     // Generator.choice(n) / integers(0, n): Lemire rejection on buffered 32-bit draws
     __device__ __forceinline__ int choice(int n) {

@@ -784,6 +784,7 @@ network_step_kernel(const HwyNetParams P, const HwyNetGraph* __restrict__ graph,
 
 __global__ void __launch_bounds__(kBlockThreads)
 network_observe_kernel(const HwyNetParams P, const HwyNetGraph* __restrict__ graph, const HwyNetState S,
+                       const uint8_t* __restrict__ mask_a, const uint8_t* __restrict__ mask_b,
                        float* __restrict__ obs) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     GraphShared& g = *reinterpret_cast<GraphShared*>(smem_raw);
@@ -806,12 +807,93 @@ network_observe_kernel(const HwyNetParams P, const HwyNetGraph* __restrict__ gra
     st.lane[i] = meta_lane(r.meta);
     st.tgt[i] = meta_target(r.meta);
     group_sync();
+    const bool selected = (!mask_a && !mask_b) || (mask_a && mask_a[e]) || (mask_b && mask_b[e]);
     float* obs_env = obs + (size_t)e * obs_size(P);
     const int speed_index = S.speed_index[e];
+    if (!selected) return;  // whole group leaves together (selection is per env)
     if (P.obs_type == HWY_OBS_TTC)
         observe_ttc(P, g, st, P.n_vehicles, i, speed_index, obs_env);
     else
         observe_kinematics(P, g, st, P.n_vehicles, i, obs_env);
+}
+
+// RoundaboutEnv._make_vehicles (envs/roundabout_env.py:317-391), one env per thread (the draws
+// are a sequential chain on the env's numpy stream).
+__global__ void __launch_bounds__(128)
+roundabout_reset_kernel(const HwyNetParams P, const HwyNetGraph* __restrict__ graph, const HwyRoundaboutSpawn SP,
+                        const HwyNetState S, uint64_t* __restrict__ rng, const uint8_t* __restrict__ mask_a,
+                        const uint8_t* __restrict__ mask_b) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= S.n_envs) return;
+    if ((mask_a || mask_b) && !((mask_a && mask_a[e]) || (mask_b && mask_b[e]))) return;
+    const size_t n = (size_t)S.n_envs;
+    Pcg64 g;
+    g.s_hi = rng[0 * n + e];
+    g.s_lo = rng[1 * n + e];
+    g.i_hi = rng[2 * n + e];
+    g.i_lo = rng[3 * n + e];
+    uint64_t w4 = rng[4 * n + e];
+    g.has32 = (uint32_t)(w4 >> 32);
+    g.u32 = (uint32_t)w4;
+    double2* pos = reinterpret_cast<double2*>(S.pos);
+    double2* hs = reinterpret_cast<double2*>(S.hs);
+    double2* tt = reinterpret_cast<double2*>(S.tt);
+    double2* imp = reinterpret_cast<double2*>(S.imp);
+    const size_t base = (size_t)e * S.vp;
+    const int V = P.n_vehicles;
+    for (int v = 0; v < V; ++v) {
+        const bool is_ego = v == 0;
+        double px, py, heading, speed, delta = 4.0;
+        int dest = 3;
+        if (is_ego) {
+            const HwyNetLane& L = graph->lanes[SP.ego_lane];
+            lane_position(L, SP.ego_longitudinal, 0.0, px, py);
+            heading = lane_heading_at(L, SP.ego_heading_longitudinal);
+            speed = SP.ego_speed;
+        } else {
+            const int j = v - 1;
+            const HwyNetLane& L = graph->lanes[SP.spawn_lane[j]];
+            double lon = SP.base_longitudinal[j] + g.normal() * SP.position_deviation;
+            speed = SP.traffic_speed + g.normal() * SP.speed_deviation;
+            dest = (j == 0 && SP.fixed_destination >= 0) ? SP.fixed_destination : g.choice(3);
+            delta = g.uniform(SP.delta_lo, SP.delta_hi);
+            lane_position(L, lon, 0.0, px, py);  // make_on_lane (vehicle/objects.py:68-90)
+            heading = lane_heading_at(L, lon);
+        }
+        int lane = 0;  // RoadObject.__init__: closest lane (objects.py:46-50)
+        double bd = 0;
+        for (int l = 0; l < graph->n_lanes; ++l) {
+            double d = lane_distance_with_heading(graph->lanes[l], px, py, heading);
+            if (l == 0 || d < bd) {
+                bd = d;
+                lane = l;
+            }
+        }
+        double target_speed = speed, timer = 0.0;
+        int kind = HWY_KIND_IDM;
+        if (is_ego) {
+            kind = HWY_KIND_MDP;
+            target_speed = P.target_speeds[SP.ego_speed_index];
+        } else {
+            timer = py_mod_pos((px + py) * kPi, P.lane_change_delay);  // behavior.py:64
+        }
+        pos[base + v] = make_double2(px, py);
+        hs[base + v] = make_double2(heading, speed);
+        tt[base + v] = make_double2(target_speed, timer);
+        imp[base + v] = make_double2(0.0, 0.0);
+        S.delta[base + v] = delta;
+        S.meta[base + v] = (lane << HWY_META_LANE_SHIFT) | (lane << HWY_META_TARGET_SHIFT) |
+                           HWY_META_CHECK_COLLISIONS | (kind << HWY_META_KIND_SHIFT) | HWY_META_PRESENT;
+        const int* rsrc = SP.route_table + ((size_t)lane * 4 + dest) * R;
+        int* rdst = S.route + (base + v) * R;
+        for (int k = 0; k < R; ++k) rdst[k] = rsrc[k];
+        S.route_len[base + v] = SP.route_len[(size_t)lane * 4 + dest];
+    }
+    S.speed_index[e] = SP.ego_speed_index;
+    S.time[e] = 0.0;
+    rng[0 * n + e] = g.s_hi;
+    rng[1 * n + e] = g.s_lo;
+    rng[4 * n + e] = ((uint64_t)g.has32 << 32) | g.u32;
 }
 
 }  // namespace hwynet
@@ -882,8 +964,27 @@ int hwy_network_observe(const HwyNetParams* p, const HwyNetGraph* graph, const H
     if (configure_smem(hwynet::network_observe_kernel)) return 1;
     int blocks = (s->n_envs + hwynet::kBlockEnvs - 1) / hwynet::kBlockEnvs;
     hwynet::network_observe_kernel<<<blocks, hwynet::kBlockThreads, net_smem_bytes(), (cudaStream_t)stream>>>(
-        *p, graph, *s, obs);
+        *p, graph, *s, nullptr, nullptr, obs);
     return check_launch("network_observe_kernel");
+}
+
+int hwy_roundabout_reset(const HwyNetParams* p, const HwyNetGraph* graph, const HwyRoundaboutSpawn* spawn,
+                         const HwyNetState* s, uint64_t* rng, const uint8_t* mask_a, const uint8_t* mask_b,
+                         float* obs, void* stream) {
+    if (validate_net(p, graph, s)) return 1;
+    if (!spawn || !rng || !spawn->route_table || !spawn->route_len) return fail("%s", "null spawn / rng pointer");
+    if (p->n_vehicles != 5) return fail("%s", "roundabout spawn places exactly 5 vehicles");
+    cudaStream_t st = (cudaStream_t)stream;
+    hwynet::roundabout_reset_kernel<<<(s->n_envs + 127) / 128, 128, 0, st>>>(*p, graph, *spawn, *s, rng, mask_a, mask_b);
+    if (check_launch("roundabout_reset_kernel")) return 1;
+    if (obs) {
+        if (configure_smem(hwynet::network_observe_kernel)) return 1;
+        int blocks = (s->n_envs + hwynet::kBlockEnvs - 1) / hwynet::kBlockEnvs;
+        hwynet::network_observe_kernel<<<blocks, hwynet::kBlockThreads, net_smem_bytes(), st>>>(
+            *p, graph, *s, mask_a, mask_b, obs);
+        return check_launch("network_observe_kernel");
+    }
+    return 0;
 }
 
 }  // extern "C"

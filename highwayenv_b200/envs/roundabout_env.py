@@ -4,11 +4,16 @@ Host-side mirror of the reference's ``RoundaboutEnv`` (highway_env/envs/roundabo
 same config dictionary, road geometry and spawn procedure; stepping runs in
 ``hwy_network_step`` (include/hwyb200.h) for ``num_envs`` independent roundabouts.
 
-Reset is host-exact: every env owns the numpy ``Generator(PCG64)`` a reference env seeded with
-``seed + env_index_offset + i`` would own and ``_make_vehicles`` draws from it in the reference's
-order (normal, normal, choice, uniform per traffic vehicle); positions use the same numpy lane
-expressions as the reference.  Autoreset (SameStep) therefore goes through the host: the ended
-envs' states are rebuilt with numpy and uploaded.  (The highway family resets on the device.)
+Every env owns the numpy ``Generator(PCG64)`` stream a reference env seeded with
+``seed + env_index_offset + i`` would own; ``_make_vehicles`` draws from it in the reference's
+order (normal, normal, choice, uniform per traffic vehicle).  Two reset modes:
+
+* ``reset_mode="device"`` (default): ``hwy_roundabout_reset`` re-spawns on the GPU from the stream
+  (PCG64 + numpy's ziggurat normal restated on the device).  Draws, lanes and routes are identical
+  to the reference; spawn coordinates go through CUDA's sin/cos instead of numpy's and may differ
+  in the last ulp (~1e-15 m).  SameStep autoreset stays on the device.
+* ``reset_mode="host"``: the spawn is rebuilt with numpy (bit-identical to the reference) and
+  uploaded; autoreset round-trips through the host.
 """
 from __future__ import annotations
 
@@ -162,7 +167,8 @@ class BatchedRoundaboutEnv:
         return default_config(cls.ENV_ID)
 
     def __init__(self, config: Optional[dict] = None, render_mode: Optional[str] = None, num_envs: int = 1,
-                 device: Any = None, autoreset_mode: str = "SameStep", env_index_offset: int = 0) -> None:
+                 device: Any = None, autoreset_mode: str = "SameStep", env_index_offset: int = 0,
+                 reset_mode: str = "device") -> None:
         if render_mode is not None:
             raise NotImplementedError("rendering is out of scope of the accelerated path")
         if not torch.cuda.is_available():
@@ -173,6 +179,9 @@ class BatchedRoundaboutEnv:
         self.render_mode = None
         self.num_envs = int(num_envs)
         self.device = torch.device(device if device is not None else "cuda")
+        if reset_mode not in ("device", "host"):
+            raise ValueError("reset_mode must be 'device' or 'host'")
+        self.reset_mode = reset_mode
         self.autoreset_mode = autoreset_mode
         self.env_index_offset = int(env_index_offset)
         self.config = self.default_config()
@@ -271,6 +280,8 @@ class BatchedRoundaboutEnv:
         self._info_speed = z(n, dtype=torch.float64)
         self._info_crashed = z(n, dtype=torch.uint8)
         self._action_buf = z(n, dtype=torch.int32)
+        self._rng = z(5, n, dtype=torch.int64)  # numpy PCG64 words (device reset mode)
+        self._build_spawn_tables()
         st = N.HwyNetState()
         st.n_envs, st.vp = n, vp
         st.pos, st.hs, st.tt, st.imp = (t.data_ptr() for t in (self._pos, self._hs, self._tt, self._imp))
@@ -278,6 +289,39 @@ class BatchedRoundaboutEnv:
         st.route, st.route_len = self._route.data_ptr(), self._route_len.data_ptr()
         st.speed_index, st.time = self._speed_index.data_ptr(), self._time.data_ptr()
         self._state = st
+
+    def _build_spawn_tables(self) -> None:
+        """Host-planned routes for every (closest lane at spawn, destination) pair + spawn constants."""
+        net, sp = self.net, self.spawner
+        n_l = len(net.lanes)
+        table = np.zeros((n_l, 4, N.HWY_NET_MAX_ROUTE), dtype=np.int32)
+        lens = np.zeros((n_l, 4), dtype=np.int32)
+        for l in range(n_l):
+            for d, dest in enumerate(sp.DESTINATIONS + ["nxs"]):
+                table[l, d], lens[l, d] = sp._route_of(l, dest)
+        self._route_table = torch.from_numpy(table).to(self.device)
+        self._route_table_len = torch.from_numpy(lens).to(self.device)
+        s = N.HwyRoundaboutSpawn()
+        s.ego_lane = net.index[("ser", "ses", 0)]
+        for j, li in enumerate([("we", "sx", 1), ("we", "sx", 0), ("we", "sx", 0), ("eer", "ees", 0)]):
+            s.spawn_lane[j] = net.index[li]
+        fd = self.config["incoming_vehicle_destination"]
+        s.fixed_destination = -1 if fd is None else int(fd)
+        ts = self.action_type.target_speeds
+        s.ego_speed_index = int(np.clip(np.round((8.0 - ts[0]) / (ts[-1] - ts[0]) * (ts.size - 1)), 0, ts.size - 1))
+        for j, b in enumerate([5.0, 20.0, -20.0, 50.0]):
+            s.base_longitudinal[j] = b
+        s.ego_longitudinal, s.ego_heading_longitudinal, s.ego_speed = 125.0, 140.0, 8.0
+        s.position_deviation, s.speed_deviation, s.traffic_speed = 2.0, 2.0, 16.0
+        s.delta_lo, s.delta_hi = 3.5, 4.5
+        s.route_table, s.route_len = self._route_table.data_ptr(), self._route_table_len.data_ptr()
+        self._spawn_struct = s
+
+    def _device_reset(self, mask_a, mask_b, obs_ptr) -> None:
+        with torch.cuda.device(self.device):
+            N.check(self._lib.hwy_roundabout_reset(
+                C.byref(self._params), self._graph_dev.data_ptr(), C.byref(self._spawn_struct),
+                C.byref(self._state), self._rng.data_ptr(), mask_a, mask_b, obs_ptr, self._stream()))
 
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
@@ -314,6 +358,14 @@ class BatchedRoundaboutEnv:
             seeds = [int(s) for s in seed]
         self._rngs = [np.random.Generator(np.random.PCG64(np.random.SeedSequence(s))) for s in seeds]
         self.np_random_seed = seeds
+        if self.reset_mode == "device":
+            words = np.zeros((5, n), dtype=np.uint64)
+            m64 = (1 << 64) - 1
+            for i, g in enumerate(self._rngs):
+                st = g.bit_generator.state
+                sv, inc = st["state"]["state"], st["state"]["inc"]
+                words[:, i] = (sv >> 64, sv & m64, inc >> 64, inc & m64, (int(st["has_uint32"]) << 32) | int(st["uinteger"]))
+            self._rng.copy_(torch.from_numpy(words.view(np.int64)).to(self.device))
 
     # ------------------------------------------------------------------ gym API
     def reset(self, *, seed=None, options: Optional[dict] = None):
@@ -323,11 +375,19 @@ class BatchedRoundaboutEnv:
             self._allocate()
         if seed is not None or self._rngs is None:
             self._seed_streams(seed)
-        ids = np.arange(self.num_envs)
+        mask = None
         if options and options.get("reset_mask") is not None:
-            ids = np.nonzero(np.asarray(options["reset_mask"]))[0]
-        if len(ids):
-            self._upload(ids, self._spawn(ids))
+            mask = np.asarray(options["reset_mask"]).astype(bool)
+        if self.reset_mode == "device":
+            mt = None
+            if mask is not None:
+                mt = torch.from_numpy(mask.astype(np.uint8)).to(self.device)
+                self._mask_keepalive = mt
+            self._device_reset(None if mt is None else mt.data_ptr(), None, None)
+        else:
+            ids = np.arange(self.num_envs) if mask is None else np.nonzero(mask)[0]
+            if len(ids):
+                self._upload(ids, self._spawn(ids))
         self.observe()
         return self._obs, {"speed": self._hs[:, 0, 1], "crashed": (self._meta[:, 0] & N.META_CRASHED) != 0}
 
@@ -355,7 +415,11 @@ class BatchedRoundaboutEnv:
                 self._truncated.data_ptr(), self._info_speed.data_ptr(), self._info_crashed.data_ptr(),
                 self._stream()))
         info = {"speed": self._info_speed, "crashed": self._info_crashed.view(torch.bool), "action": act}
-        if self.autoreset_mode == "SameStep":
+        if self.autoreset_mode == "SameStep" and self.reset_mode == "device":
+            self._final_obs.copy_(self._obs)
+            info["final_obs"] = self._final_obs
+            self._device_reset(self._terminated.data_ptr(), self._truncated.data_ptr(), self._obs.data_ptr())
+        elif self.autoreset_mode == "SameStep":
             done = (self._terminated | self._truncated).cpu().numpy().astype(bool)
             if done.any():
                 self._final_obs.copy_(self._obs)

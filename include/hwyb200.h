@@ -235,6 +235,30 @@ int hwy_network_step(const HwyNetParams *p, const HwyNetGraph *graph, const HwyN
 int hwy_network_observe(const HwyNetParams *p, const HwyNetGraph *graph, const HwyNetState *s,
                         float *obs, void *stream);
 
+/* RoundaboutEnv._make_vehicles (envs/roundabout_env.py:317-391) on the device.  Per traffic
+ * vehicle the env's numpy stream yields normal (longitudinal), normal (speed),
+ * choice(destinations), uniform (DELTA); routes come from a host-built table of
+ * ControlledVehicle.plan_route_to results (vehicle/controller.py:71-87). */
+typedef struct HwyRoundaboutSpawn {
+    int32_t ego_lane;            /* table index of ("ser", "ses", 0) */
+    int32_t spawn_lane[4];       /* make_on_lane lanes: (we,sx,1), (we,sx,0), (we,sx,0), (eer,ees,0) */
+    int32_t fixed_destination;   /* config["incoming_vehicle_destination"], -1 = None */
+    int32_t ego_speed_index;
+    int32_t _pad;
+    double base_longitudinal[4]; /* 5, 20, -20, 50 */
+    double ego_longitudinal, ego_heading_longitudinal, ego_speed; /* 125, 140, 8 */
+    double position_deviation, speed_deviation, traffic_speed;    /* 2, 2, 16 */
+    double delta_lo, delta_hi;   /* IDMVehicle.DELTA_RANGE */
+    const int32_t *route_table;  /* DEVICE [n_lanes][4][HWY_NET_MAX_ROUTE]; destination 0..2 = exr, sxr, nxr; 3 = the ego's nxs */
+    const int32_t *route_len;    /* DEVICE [n_lanes][4] */
+} HwyRoundaboutSpawn;
+
+/* Re-spawn the envs selected by mask_a | mask_b (both NULL: all) from rng[5*n_envs] (layout as
+ * HwyHighwayState.rng); if obs != NULL also write their reset observation. */
+int hwy_roundabout_reset(const HwyNetParams *p, const HwyNetGraph *graph, const HwyRoundaboutSpawn *spawn,
+                         const HwyNetState *s, uint64_t *rng, const uint8_t *mask_a, const uint8_t *mask_b,
+                         float *obs, void *stream);
+
 /* Kernel launches issued by the calling thread through this library since load (the
  * `gpu_launches` claim of bench.py). */
 uint64_t hwy_launch_count(void);

@@ -59,7 +59,7 @@ def check_routes(st, got, ctx):
 @pytest.mark.parametrize("name", CASES)
 def test_reset_matches_reference(name):
     g = load_golden(name)
-    env = make_env(g["config"], len(g["seeds"]))
+    env = make_env(g["config"], len(g["seeds"]), reset_mode="host")
     obs, _ = env.reset(seed=[int(s) for s in g["seeds"]])
     sd = env.state_dict()
     for i in range(len(g["seeds"])):
@@ -146,9 +146,55 @@ def test_teacher_forced_vs_oracle_many_envs(name, n, T):
         assert np.max(np.abs(obs.cpu().numpy().reshape(n, -1) - o_obs)) <= 1e-6
 
 
+def test_device_reset_matches_host_reset():
+    """hwy_roundabout_reset (device PCG64 + ziggurat normal) against the numpy-exact host spawn:
+    identical draws / lanes / routes, coordinates within CUDA-vs-numpy sin/cos rounding."""
+    g = load_golden("roundabout_ttc")
+    n = 512
+    dev_env = make_env(g["config"], n, reset_mode="device")
+    host_env = make_env(g["config"], n, reset_mode="host")
+    o_d, _ = dev_env.reset(seed=777)
+    o_h, _ = host_env.reset(seed=777)
+    for rep in range(3):  # the streams keep advancing identically over repeated resets
+        a, b = dev_env.state_dict(), host_env.state_dict()
+        for k in ("x", "y", "heading", "timer"):
+            assert np.max(np.abs(a[k] - b[k])) <= 1e-12, (rep, k)
+        for k in ("speed", "delta", "target_speed"):
+            assert np.array_equal(a[k], b[k]), (rep, k)  # pure RNG arithmetic: bit-exact
+        for k in ("lane", "target_lane", "route", "route_len", "kind", "speed_index"):
+            assert np.array_equal(a[k], b[k]), (rep, k)
+        assert np.max(np.abs(o_d.cpu().numpy() - o_h.cpu().numpy())) <= 1e-6
+        # generator state after the spawn equals numpy's
+        words = dev_env._rng.cpu().numpy().view(np.uint64)
+        for i in (0, 1, n - 1):
+            st = host_env._rngs[i].bit_generator.state
+            sv = st["state"]["state"]
+            assert int(words[0, i]) == sv >> 64 and int(words[1, i]) == sv & ((1 << 64) - 1)
+            assert int(words[4, i]) >> 32 == int(st["has_uint32"])
+        o_d, _ = dev_env.reset()
+        o_h, _ = host_env.reset()
+
+
+def test_device_autoreset_same_step():
+    g = load_golden("roundabout_kin")
+    n = 64
+    env = make_env(g["config"], n)  # device reset, SameStep
+    env.reset(seed=9)
+    rng = np.random.default_rng(0)
+    resets = 0
+    for t in range(25):
+        obs, rew, term, trunc, info = env.step(rng.integers(0, 5, size=n).astype(np.int32))
+        done = (term | trunc).cpu().numpy()
+        resets += int(done.sum())
+        sd = env.state_dict()
+        assert np.all(sd["time"][done] == 0) and np.all(sd["x"][done, 0] == 2.0) and np.all(sd["y"][done, 0] == 45.0)
+        assert np.array_equal(info["final_obs"].cpu().numpy()[~done], obs.cpu().numpy()[~done])
+    assert resets >= 2 * n
+
+
 def test_autoreset_host_path():
     g = load_golden("roundabout_kin")
-    env = make_env(g["config"], 16)
+    env = make_env(g["config"], 16, reset_mode="host")
     env.reset(seed=5)
     for t in range(14):
         obs, rew, term, trunc, info = env.step(np.full(16, 1, dtype=np.int32))
