@@ -1,0 +1,83 @@
+"""Wider config coverage of the highway kernels against the C oracle: every thread mapping
+(32 / 64 / 128 threads per env) at its boundaries, lane counts, observation options, frequencies,
+reward options.  Teacher-forced each step + bit-exact resets."""
+import numpy as np
+import pytest
+
+import hwy_oracle as ho
+
+pytestmark = pytest.mark.gpu
+
+
+def run_case(env_id, over, n, T, seed):
+    import highwayenv_b200 as hb
+    from highwayenv_b200.config import default_config
+
+    cfg = default_config(env_id)
+    cfg.update(over)
+    env = hb.make(env_id, num_envs=n, config=over, autoreset_mode="Disabled")
+    ocfg = dict(cfg)
+    ocfg["_others_check_collisions"] = 0 if env_id == "highway-fast-v0" else 1
+    oc = ho.cfg_from_dict(ocfg)
+    ob = ho.OracleBatch(oc, n, seeds=range(seed, seed + n), threads=8)
+    obs, _ = env.reset(seed=seed)
+    assert np.array_equal(obs.cpu().numpy(), ob.reset()), "reset observation"
+    sd = env.state_dict()
+    for k in ("x", "y", "heading", "speed", "timer", "delta"):
+        assert np.array_equal(sd[k], ob.a[k]), f"reset {k}"
+    rng = np.random.default_rng(seed)
+    for t in range(T):
+        env.load_state_dict({k: ob.a[k].copy() for k in ob.a})
+        if oc.action_type == 0:
+            act = rng.integers(0, 5, size=n).astype(np.int32)
+        else:
+            act = rng.uniform(-1.2, 1.2, size=(n, 2)).astype(np.float32)  # exercises the clip
+        o_obs, o_rew, o_term, o_trunc = ob.step(act)
+        obs, rew, term, trunc, _ = env.step(act)
+        sd = env.state_dict()
+        for k in ("x", "y", "heading", "speed", "timer", "target_speed"):
+            assert np.max(np.abs(sd[k] - ob.a[k])) <= 1e-7, (t, k)
+        for k in ("lane", "target_lane", "crashed", "has_impact"):
+            assert np.array_equal(sd[k].astype(np.int32), ob.a[k].astype(np.int32)), (t, k)
+        assert np.max(np.abs(rew.cpu().numpy() - o_rew)) <= 1e-9
+        assert np.array_equal(term.cpu().numpy(), o_term.astype(bool))
+        assert np.array_equal(trunc.cpu().numpy(), o_trunc.astype(bool))
+        assert np.max(np.abs(obs.cpu().numpy() - o_obs)) <= 1e-6
+
+
+@pytest.mark.parametrize("vehicles", [1, 8, 31, 32, 63, 64, 100, 127])
+def test_vehicle_counts_fast(vehicles):
+    run_case("highway-fast-v0", {"vehicles_count": vehicles}, 24, 6, 100 + vehicles)
+
+
+@pytest.mark.parametrize("vehicles", [15, 40, 70])
+def test_vehicle_counts_all_pairs(vehicles):
+    run_case("highway-v0", {"vehicles_count": vehicles}, 12, 4, 300 + vehicles)
+
+
+@pytest.mark.parametrize("lanes", [1, 2, 5, 8])
+def test_lane_counts(lanes):
+    run_case("highway-fast-v0", {"vehicles_count": 30, "lanes_count": lanes}, 16, 6, 500 + lanes)
+
+
+@pytest.mark.parametrize("obs", [
+    {"type": "Kinematics", "vehicles_count": 3},
+    {"type": "Kinematics", "vehicles_count": 12, "see_behind": True},
+    {"type": "Kinematics", "absolute": True, "normalize": False},
+    {"type": "Kinematics", "clip": False},
+])
+def test_observation_options(obs):
+    run_case("highway-fast-v0", {"vehicles_count": 25, "observation": obs}, 16, 5, 700)
+
+
+@pytest.mark.parametrize("over", [
+    {"simulation_frequency": 10, "policy_frequency": 2, "duration": 4},
+    {"simulation_frequency": 15, "policy_frequency": 5},
+    {"normalize_reward": False, "collision_reward": -2.0, "right_lane_reward": 0.3, "high_speed_reward": 0.7,
+     "reward_speed_range": [15, 28]},
+    {"offroad_terminal": True, "initial_lane_id": 0, "ego_spacing": 1.0, "vehicles_density": 1.7},
+    {"action": {"type": "DiscreteMetaAction", "target_speeds": [10, 15, 20, 25, 30]}},
+    {"action": {"type": "ContinuousAction", "acceleration_range": [-3.0, 2.0], "steering_range": [-0.3, 0.3]}},
+])
+def test_misc_options(over):
+    run_case("highway-fast-v0", dict({"vehicles_count": 20}, **over), 16, 6, 900)
