@@ -42,6 +42,10 @@ CASES = {
     "roundabout_kin": ("roundabout-v0", None, list(range(400, 406)), 11, "discrete5"),
     "roundabout_ttc": ("roundabout-v0", {"observation": {"type": "TimeToCollision", "horizon": 10}},
                        list(range(500, 506)), 11, "discrete5"),
+    # intersection-v0 defaults (Kinematics, 7 features) and BASELINE configs[2] shape (OccupancyGrid)
+    "intersection_kin": ("intersection-v0", None, list(range(600, 606)), 13, "discrete3"),
+    "intersection_grid": ("intersection-v0", {"observation": {"type": "OccupancyGrid"}},
+                          list(range(700, 706)), 13, "discrete3"),
 }
 
 
@@ -57,9 +61,11 @@ def main() -> None:
         for seed in seeds:
             if akind == "discrete5":
                 actions = rng.integers(0, 5, size=T).astype(np.int64)
+            elif akind == "discrete3":
+                actions = rng.integers(0, 3, size=T).astype(np.int64)
             else:
                 actions = rng.uniform(-1, 1, size=(T, 2)).astype(np.float32)
-            per_seed.append(rh.rollout(env_id, over, seed, list(actions)))
+            per_seed.append(rh.rollout(env_id, over, seed, list(actions), pad=32 if env_id.startswith("intersection") else 0))
         out = {k: np.stack([p[k] for p in per_seed]) for k in per_seed[0].keys()}
         out["seeds"] = np.array(seeds, dtype=np.int64)
         env = rh.make_reference_env(env_id, over)

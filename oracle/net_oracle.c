@@ -264,6 +264,8 @@ typedef struct {
     int V;
 } World;
 
+static inline int world_count(const NetCfg *c, const NetState *s) { return s->count ? s->count[0] : c->n_vehicles; }
+
 #define RT_FROM(e) ((e)&0xff)
 #define RT_TO(e) (((e) >> 8) & 0xff)
 #define RT_ID(e) ((((e) >> 16) & 0xff) - 1) /* -1 = None */
@@ -558,6 +560,13 @@ static void mdp_act(World *w, int v, int action) {
     }
 }
 
+/* index of the controlled vehicle: first MDP vehicle of the list */
+static int ego_index(const World *w) {
+    for (int v = 0; v < w->V; v++)
+        if (w->s->kind[v] == NET_KIND_MDP) return v;
+    return 0;
+}
+
 static void road_act(World *w) {
     for (int v = 0; v < w->V; v++) {
         if (w->s->kind[v] == NET_KIND_IDM)
@@ -672,14 +681,14 @@ static void observe_ttc(const World *w, float *obs) {
     const NetCfg *c = w->c;
     const NetState *s = w->s;
     const NetGraph *g = w->g;
-    const int ego = 0;
+    const int ego = ego_index(w);
     const NetLane *EL = &g->lanes[s->lane[ego]];
     int n_speeds = c->n_target_speeds, n_lanes = EL->road_count;
     int n_t = (int)(c->ttc_horizon / (1.0 / c->policy_frequency));
     double tq = 1.0 / c->policy_frequency;
     double *grid = (double *)calloc((size_t)n_speeds * n_lanes * n_t, sizeof(double));
     double ce = cos(s->heading[ego]), se = sin(s->heading[ego]);
-    const int32_t *route = s->route; /* ego is slot 0 */
+    const int32_t *route = s->route + (size_t)ego * NET_MAX_ROUTE;
     for (int si = 0; si < n_speeds; si++) {
         double ego_speed = c->target_speeds[si];
         for (int o = 0; o < w->V; o++) {
@@ -741,21 +750,27 @@ static void observe_ttc(const World *w, float *obs) {
     free(grid);
 }
 
-/* envs/common/observation.py:234-276 with explicit features_range / absolute */
+/* envs/common/observation.py:234-276 with explicit features_range / absolute; optional
+ * cos_h, sin_h columns (vehicle/kinematics.py:247-248), which have no features_range entry */
 static void observe_kinematics(const World *w, float *obs) {
     const NetCfg *c = w->c;
     const NetState *s = w->s;
     int K = c->obs_vehicles_count, V = w->V;
-    double *rows = (double *)calloc((size_t)K * 5, sizeof(double));
-    const int ego = 0;
+    const int F = c->obs_features == 7 ? 7 : 5;
+    double *rows = (double *)calloc((size_t)K * F, sizeof(double));
+    const int ego = ego_index(w);
     double evx = s->speed[ego] * cos(s->heading[ego]), evy = s->speed[ego] * sin(s->heading[ego]);
     rows[0] = 1;
     rows[1] = s->x[ego];
     rows[2] = s->y[ego];
     rows[3] = evx;
     rows[4] = evy;
-    int *cand = (int *)malloc(sizeof(int) * V);
-    double *key = (double *)malloc(sizeof(double) * V);
+    if (F == 7) {
+        rows[5] = cos(s->heading[ego]);
+        rows[6] = sin(s->heading[ego]);
+    }
+    int *cand = (int *)malloc(sizeof(int) * (V > 0 ? V : 1));
+    double *key = (double *)malloc(sizeof(double) * (V > 0 ? V : 1));
     int nc = 0;
     for (int v = 0; v < V; v++) {
         if (!(norm2(s->x[v] - s->x[ego], s->y[v] - s->y[ego]) < c->perception_distance)) continue;
@@ -781,7 +796,7 @@ static void observe_kinematics(const World *w, float *obs) {
     int n_rows = 1;
     for (int k = 0; k < nc && k < K - 1; k++) {
         int v = cand[k];
-        double *r = rows + 5 * n_rows;
+        double *r = rows + F * n_rows;
         r[0] = 1;
         r[1] = s->x[v];
         r[2] = s->y[v];
@@ -793,11 +808,15 @@ static void observe_kinematics(const World *w, float *obs) {
             r[3] -= evx;
             r[4] -= evy;
         }
+        if (F == 7) {
+            r[5] = cos(s->heading[v]);
+            r[6] = sin(s->heading[v]);
+        }
         n_rows++;
     }
     if (c->obs_normalize) {
         for (int k = 0; k < n_rows; k++) {
-            double *r = rows + 5 * k;
+            double *r = rows + F * k;
             r[1] = lmap(r[1], c->obs_x_lo, c->obs_x_hi, -1, 1);
             r[2] = lmap(r[2], c->obs_y_lo, c->obs_y_hi, -1, 1);
             r[3] = lmap(r[3], c->obs_vx_lo, c->obs_vx_hi, -1, 1);
@@ -806,13 +825,69 @@ static void observe_kinematics(const World *w, float *obs) {
                 for (int f = 1; f < 5; f++) r[f] = clipd(r[f], -1, 1);
         }
     }
-    for (int k = 0; k < K * 5; k++) obs[k] = (float)rows[k];
+    for (int k = 0; k < K * F; k++) obs[k] = (float)rows[k];
     free(rows);
     free(cand);
     free(key);
 }
 
+/* envs/common/observation.py:354-484 OccupancyGridObservation.observe with the defaults of
+ * :282-284 (features presence, vx, vy, on_road; 11x11 cells of 5 m; world axes; relative) */
+static void observe_occupancy(const World *w, float *obs) {
+    const NetState *s = w->s;
+    const NetGraph *g = w->g;
+    const int ego = ego_index(w);
+    const int NX = 11, NY = 11;
+    const double lo = -5.5 * 5, step = 5;
+    double grid[4][11][11];
+    for (int l = 0; l < 4; l++)
+        for (int i = 0; i < NX; i++)
+            for (int j = 0; j < NY; j++) grid[l][i][j] = NAN;
+    double ex = s->x[ego], ey = s->y[ego];
+    double evx = s->speed[ego] * cos(s->heading[ego]), evy = s->speed[ego] * sin(s->heading[ego]);
+    /* vehicles in REVERSED list order (df[::-1]): the lowest index owns a shared cell */
+    for (int v = w->V - 1; v >= 0; v--) {
+        double x = s->x[v] - ex, y = s->y[v] - ey;
+        double vx = s->speed[v] * cos(s->heading[v]) - evx, vy = s->speed[v] * sin(s->heading[v]) - evy;
+        vx = lmap(vx, -2 * MAX_SPEED, 2 * MAX_SPEED, -1, 1);
+        vy = lmap(vy, -2 * MAX_SPEED, 2 * MAX_SPEED, -1, 1);
+        int ci = (int)floor((x - lo) / step), cj = (int)floor((y - lo) / step);
+        if (0 <= ci && ci < NX && 0 <= cj && cj < NY) {
+            grid[0][ci][cj] = 1;
+            grid[1][ci][cj] = vx;
+            grid[2][ci][cj] = vy;
+        }
+    }
+    /* fill_road_layer_by_lanes :446-484 */
+    for (int l = 0; l < g->n_lanes; l++) {
+        const NetLane *L = &g->lanes[l];
+        double origin = lane_s(L, ex, ey);
+        /* np.arange(origin - 100, origin + 100, 5): ceil((stop - start) / step) points start + k*step */
+        double start = origin - 100, stop = origin + 100;
+        int n = (int)ceil((stop - start) / 5.0);
+        for (int k = 0; k < n; k++) {
+            double wp = clipd(start + k * 5.0, 0, L->length);
+            double px, py;
+            net_lane_position(L, wp, 0, &px, &py);
+            px -= ex;
+            py -= ey;
+            int ci = (int)floor((px - lo) / step), cj = (int)floor((py - lo) / step);
+            if (0 <= ci && ci < NX && 0 <= cj && cj < NY) grid[3][ci][cj] = 1;
+        }
+    }
+    for (int l = 0; l < 4; l++)
+        for (int i = 0; i < NX; i++)
+            for (int j = 0; j < NY; j++) {
+                double val = grid[l][i][j];
+                val = clipd(val, -1, 1); /* np.clip keeps NaN */
+                if (isnan(grid[l][i][j])) val = 0; /* nan_to_num */
+                obs[(l * NX + i) * NY + j] = (float)val;
+            }
+}
+
 int net_obs_size(const NetCfg *c) {
+    if (c->obs_type == NET_OBS_OCCUPANCY) return 4 * 11 * 11;
+    if (c->obs_type == NET_OBS_KINEMATICS) return c->obs_vehicles_count * (c->obs_features == 7 ? 7 : 5);
     if (c->obs_type == NET_OBS_TTC) return 3 * 3 * (int)(c->ttc_horizon / (1.0 / c->policy_frequency));
     return c->obs_vehicles_count * 5;
 }
@@ -822,8 +897,10 @@ void net_observe(const NetGraph *g, const NetCfg *c, const NetState *s, float *o
     w.g = g;
     w.c = c;
     w.s = (NetState *)s;
-    w.V = c->n_vehicles;
-    if (c->obs_type == NET_OBS_TTC)
+    w.V = world_count(c, s);
+    if (c->obs_type == NET_OBS_OCCUPANCY)
+        observe_occupancy(&w, obs);
+    else if (c->obs_type == NET_OBS_TTC)
         observe_ttc(&w, obs);
     else
         observe_kinematics(&w, obs);
@@ -852,6 +929,123 @@ static void reward_done(const World *w, int action, double *reward, int32_t *ter
     *truncated = s->time[0] >= c->duration;
 }
 
+/* ------------------------------------------------------------------ road/regulation.py */
+
+/* road/road.py:323-362 position_heading_along_route(route, longitudinal, 0, current_lane_index) */
+static void position_heading_along_route(const World *w, int v, double longitudinal, double *px,
+                                         double *py, double *heading) {
+    const NetGraph *g = w->g;
+    const NetState *s = w->s;
+    const int32_t *route = s->route + (size_t)v * NET_MAX_ROUTE;
+    int rlen = s->route_len[v];
+    int cur = s->lane[v];
+    int own[1];
+    if (rlen == 0) { /* `self.route or [self.lane_index]` */
+        own[0] = NET_ROUTE(g->lanes[cur].from_node, g->lanes[cur].to_node, g->lanes[cur].lane_id);
+        route = own;
+        rlen = 1;
+    }
+    int k = 0;
+    for (;;) {
+        int first = road_first(g, RT_FROM(route[k]), RT_TO(route[k]));
+        int id = RT_ID(route[k]);
+        if (id < 0) id = g->lanes[cur].lane_id; /* always < len(graph[current road]) */
+        const NetLane *L = &g->lanes[first + id];
+        if (k < rlen - 1 && longitudinal > L->length) {
+            longitudinal -= L->length;
+            k++;
+            continue;
+        }
+        net_lane_position(L, longitudinal, 0, px, py);
+        *heading = net_lane_heading_at(L, longitudinal);
+        return;
+    }
+}
+
+/* regulation.py:85-111 is_conflict_possible (horizon 3, step 0.25) */
+static int is_conflict_possible(const World *w, int v1, int v2) {
+    const NetState *s = w->s;
+    double s1 = lane_s(LANE(w, s->lane[v1]), s->x[v1], s->y[v1]);
+    double s2 = lane_s(LANE(w, s->lane[v2]), s->x[v2], s->y[v2]);
+    for (int k = 1; k < 12; k++) {
+        double t = 0.25 * k; /* np.arange(0.25, 3, 0.25) */
+        double p1x, p1y, h1, p2x, p2y, h2;
+        position_heading_along_route(w, v1, s1 + s->speed[v1] * t, &p1x, &p1y, &h1);
+        position_heading_along_route(w, v2, s2 + s->speed[v2] * t, &p2x, &p2y, &h2);
+        if (norm2(p2x - p1x, p2y - p1y) > VEH_LENGTH) continue;
+        if (orc_rotated_rectangles_intersect(p1x, p1y, 1.5 * VEH_LENGTH, 0.9 * VEH_WIDTH, h1, p2x, p2y,
+                                             1.5 * VEH_LENGTH, 0.9 * VEH_WIDTH, h2))
+            return 1;
+    }
+    return 0;
+}
+
+/* regulation.py:42-83 enforce_road_rules + respect_priorities (YIELD_DURATION = 0) */
+static void enforce_road_rules(World *w) {
+    NetState *s = w->s;
+    for (int v = 0; v < w->V; v++)
+        if (s->is_yielding[v]) {
+            s->target_speed[v] = LANE(w, s->lane[v])->speed_limit;
+            s->is_yielding[v] = 0;
+        }
+    for (int i = 0; i < w->V - 1; i++)
+        for (int j = i + 1; j < w->V; j++) {
+            if (!is_conflict_possible(w, i, j)) continue;
+            int p1 = LANE(w, s->lane[i])->priority, p2 = LANE(w, s->lane[j])->priority;
+            int y;
+            if (p1 > p2)
+                y = j;
+            else if (p1 < p2)
+                y = i;
+            else {
+                double f12 = dot2(cos(s->heading[i]), sin(s->heading[i]), s->x[j] - s->x[i], s->y[j] - s->y[i]);
+                double f21 = dot2(cos(s->heading[j]), sin(s->heading[j]), s->x[i] - s->x[j], s->y[i] - s->y[j]);
+                y = f12 > f21 ? i : j;
+            }
+            if (s->kind[y] == NET_KIND_IDM) { /* ControlledVehicle and not MDPVehicle */
+                s->target_speed[y] = 0;
+                s->is_yielding[y] = 1;
+            }
+        }
+}
+
+/* regulation.py:36-40 RegulatedRoad.step prologue */
+static void regulated_pre_step(World *w, double dt) {
+    w->s->road_steps[0] += 1;
+    if (w->s->road_steps[0] % (int)(1 / dt / 2) == 0) enforce_road_rules(w);
+}
+
+/* envs/intersection_env.py:368-373 */
+int net_has_arrived(const NetGraph *g, const NetState *s, int v) {
+    const NetLane *L = &g->lanes[s->lane[v]];
+    return L->exit_lane && lane_s(L, s->x[v], s->y[v]) >= 25;
+}
+
+/* envs/intersection_env.py:79-117 (single controlled vehicle) */
+static void reward_done_intersection(const World *w, double *reward, int32_t *terminated,
+                                     int32_t *truncated) {
+    const NetCfg *c = w->c;
+    const NetState *s = w->s;
+    const int ego = ego_index(w);
+    const NetLane *L = LANE(w, s->lane[ego]);
+    double es, elat;
+    net_lane_local(L, s->x[ego], s->y[ego], &es, &elat);
+    int on_road = lane_on_lane(L, es, elat, 0.0);
+    int arrived = net_has_arrived(w->g, s, ego);
+    double scaled_speed = lmap(s->speed[ego], c->reward_speed_lo, c->reward_speed_hi, 0, 1);
+    double r = 0;
+    r = r + c->collision_reward * (double)(s->crashed[ego] != 0);
+    r = r + c->high_speed_reward * clipd(scaled_speed, 0, 1);
+    r = r + c->arrived_reward * (double)arrived;
+    r = r + 0 * (double)on_road;
+    if (arrived) r = c->arrived_reward;
+    r *= (double)on_road;
+    if (c->normalize_reward) r = lmap(r, c->collision_reward, c->arrived_reward, 0, 1);
+    *reward = r / 1; /* mean over the (single) controlled vehicle */
+    *terminated = s->crashed[ego] != 0 || arrived || (c->offroad_terminal && !on_road);
+    *truncated = s->time[0] >= c->duration;
+}
+
 /* envs/common/abstract.py:259-317 */
 void net_step(const NetGraph *g, const NetCfg *c, NetState *s, int action, float *obs, double *reward,
               int32_t *terminated, int32_t *truncated) {
@@ -859,19 +1053,45 @@ void net_step(const NetGraph *g, const NetCfg *c, NetState *s, int action, float
     w.g = g;
     w.c = c;
     w.s = s;
-    w.V = c->n_vehicles;
-    double *act_buf = (double *)calloc(2 * (size_t)c->n_vehicles, sizeof(double));
+    w.V = world_count(c, s);
+    double *act_buf = (double *)calloc(2 * (size_t)w.V, sizeof(double));
     w.act_steer = act_buf;
-    w.act_accel = act_buf + c->n_vehicles;
+    w.act_accel = act_buf + w.V;
     int frames = c->simulation_frequency / c->policy_frequency;
     double dt = 1.0 / c->simulation_frequency;
     s->time[0] += 1.0 / c->policy_frequency;
+    /* intersection: the ego is the LAST vehicle of the list (appended after the traffic) */
+    int ego = ego_index(&w);
+    int label = action;
+    if (c->action_mode == 1) label = action == 0 ? 4 : (action == 2 ? 3 : 1); /* SLOWER / IDLE / FASTER */
     for (int frame = 0; frame < frames; frame++) {
-        if (frame == 0) mdp_act(&w, 0, action);
+        if (frame == 0) mdp_act(&w, ego, label);
         road_act(&w);
+        if (c->regulated) regulated_pre_step(&w, dt);
         road_step(&w, dt);
     }
     if (obs) net_observe(g, c, s, obs);
-    reward_done(&w, action, reward, terminated, truncated);
+    if (c->reward_type == 1)
+        reward_done_intersection(&w, reward, terminated, truncated);
+    else
+        reward_done(&w, action, reward, terminated, truncated);
+    free(act_buf);
+}
+
+void net_substeps(const NetGraph *g, const NetCfg *c, NetState *s, int substeps) {
+    World w;
+    w.g = g;
+    w.c = c;
+    w.s = s;
+    w.V = world_count(c, s);
+    double *act_buf = (double *)calloc(2 * (size_t)(w.V > 0 ? w.V : 1), sizeof(double));
+    w.act_steer = act_buf;
+    w.act_accel = act_buf + w.V;
+    double dt = 1.0 / c->simulation_frequency;
+    for (int k = 0; k < substeps; k++) {
+        road_act(&w);
+        if (c->regulated) regulated_pre_step(&w, dt);
+        road_step(&w, dt);
+    }
     free(act_buf);
 }

@@ -29,6 +29,7 @@ extern "C" {
 #define NET_KIND_MDP 1
 
 #define NET_OBS_KINEMATICS 0 /* envs/common/observation.py:155 */
+#define NET_OBS_OCCUPANCY 1  /* envs/common/observation.py:279 */
 #define NET_OBS_TTC 2        /* envs/common/observation.py:115 */
 
 /* One lane of RoadNetwork.graph[from][to][lane_id]; table order = graph enumeration order
@@ -37,6 +38,7 @@ typedef struct NetLane {
     int32_t type, from_node, to_node, lane_id;
     int32_t road_first, road_count; /* table index of lane 0 of this road, lanes on the road */
     int32_t forbidden, priority;
+    int32_t exit_lane, _pad; /* intersection: "il" in from-node name and "o" in to-node name */
     double width, speed_limit, length;
     double sx, sy, ex, ey, dx, dy, lx, ly, heading; /* StraightLane fields (lane.py:183-194) */
     double amplitude, pulsation, phase;             /* SineLane */
@@ -66,6 +68,14 @@ typedef struct NetCfg {
     double acc_max, comfort_acc_max, comfort_acc_min, distance_wanted, time_wanted;
     double politeness, lane_change_min_acc_gain, lane_change_max_braking_imposed, lane_change_delay;
     double perception_distance;
+    /* intersection-v0 (envs/intersection_env.py) */
+    int32_t regulated;        /* RegulatedRoad (road/regulation.py) */
+    int32_t action_mode;      /* 0: LANE_LEFT/IDLE/LANE_RIGHT/FASTER/SLOWER, 1: SLOWER/IDLE/FASTER (action.py:206) */
+    int32_t reward_type;      /* 0 roundabout, 1 intersection */
+    int32_t obs_features;     /* Kinematics: 5, or 7 with cos_h, sin_h */
+    int32_t offroad_terminal;
+    int32_t _pad2;
+    double arrived_reward, reward_speed_lo, reward_speed_hi;
 } NetCfg;
 
 /* route entry: from | to << 8 | (lane_id + 1) << 16   (lane_id + 1 == 0: None) */
@@ -78,12 +88,19 @@ typedef struct NetState {
     int32_t *route_len; /* [V] */
     int32_t *speed_index; /* [1] */
     double *time;         /* [1] */
+    int32_t *count;       /* [1] current number of vehicles (dynamic population); NULL: cfg->n_vehicles */
+    int32_t *is_yielding; /* [V] RegulatedRoad yield flag */
+    int32_t *road_steps;  /* [1] RegulatedRoad.steps */
 } NetState;
 
 /* One AbstractEnv.step of a roundabout-v0 style env (MDPVehicle ego in slot 0). */
 void net_step(const NetGraph *g, const NetCfg *c, NetState *s, int action, float *obs,
               double *reward, int32_t *terminated, int32_t *truncated);
 void net_observe(const NetGraph *g, const NetCfg *c, const NetState *s, float *obs);
+/* Road.act() + Road.step(dt) `substeps` times without an ego action (intersection warm-up) */
+void net_substeps(const NetGraph *g, const NetCfg *c, NetState *s, int substeps);
+/* has_arrived(vehicle) of envs/intersection_env.py:368-373 */
+int net_has_arrived(const NetGraph *g, const NetState *s, int v);
 int net_obs_size(const NetCfg *c);
 
 /* geometry KATs */

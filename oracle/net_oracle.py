@@ -12,10 +12,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libnet_oracle.so")
 
 NET_MAX_LANES, NET_MAX_NODES, NET_MAX_SUCC, NET_MAX_ROUTE, NET_MAX_TARGET_SPEEDS = 64, 64, 6, 16, 8
-OBS_KINEMATICS, OBS_TTC = 0, 2
+OBS_KINEMATICS, OBS_OCCUPANCY, OBS_TTC = 0, 1, 2
 KIND_IDM, KIND_MDP = 0, 1
 
-_LANE_I = ("type", "from_node", "to_node", "lane_id", "road_first", "road_count", "forbidden", "priority")
+_LANE_I = ("type", "from_node", "to_node", "lane_id", "road_first", "road_count", "forbidden", "priority",
+           "exit_lane", "_pad")
 _LANE_F = ("width", "speed_limit", "length", "sx", "sy", "ex", "ey", "dx", "dy", "lx", "ly", "heading",
            "amplitude", "pulsation", "phase", "cx", "cy", "radius", "start_phase", "end_phase", "direction")
 
@@ -46,6 +47,9 @@ class NetCfg(C.Structure):
             "acc_max", "comfort_acc_max", "comfort_acc_min", "distance_wanted", "time_wanted",
             "politeness", "lane_change_min_acc_gain", "lane_change_max_braking_imposed", "lane_change_delay",
             "perception_distance")]
+        + [(k, C.c_int32) for k in ("regulated", "action_mode", "reward_type", "obs_features", "offroad_terminal",
+                                    "_pad2")]
+        + [(k, C.c_double) for k in ("arrived_reward", "reward_speed_lo", "reward_speed_hi")]
     )
 
 
@@ -56,7 +60,8 @@ _SI = ("lane", "target_lane", "kind", "crashed", "has_impact", "check_collisions
 class NetState(C.Structure):
     _fields_ = ([(k, C.c_void_p) for k in _SF] + [(k, C.c_void_p) for k in _SI]
                 + [("route", C.c_void_p), ("route_len", C.c_void_p), ("speed_index", C.c_void_p),
-                   ("time", C.c_void_p)])
+                   ("time", C.c_void_p), ("count", C.c_void_p), ("is_yielding", C.c_void_p),
+                   ("road_steps", C.c_void_p)])
 
 
 def build(force: bool = False) -> str:
@@ -81,6 +86,10 @@ def lib():
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.net_observe.restype = None
         _lib.net_observe.argtypes = [C.POINTER(NetGraph), C.POINTER(NetCfg), C.POINTER(NetState), C.c_void_p]
+        _lib.net_substeps.restype = None
+        _lib.net_substeps.argtypes = [C.POINTER(NetGraph), C.POINTER(NetCfg), C.POINTER(NetState), C.c_int]
+        _lib.net_has_arrived.restype = C.c_int
+        _lib.net_has_arrived.argtypes = [C.POINTER(NetGraph), C.POINTER(NetState), C.c_int]
         _lib.net_obs_size.restype = C.c_int
         _lib.net_obs_size.argtypes = [C.POINTER(NetCfg)]
         _lib.net_closest_lane.restype = C.c_int
@@ -102,7 +111,7 @@ def graph_from_arrays(d: dict) -> NetGraph:
     g.n_lanes, g.n_nodes = n, len(d["net_succ_count"])
     for k in range(n):
         for f in _LANE_I:
-            setattr(g.lanes[k], f, int(d["net_" + f][k]))
+            setattr(g.lanes[k], f, int(d["net_" + f][k]) if "net_" + f in d else 0)
         for f in _LANE_F:
             setattr(g.lanes[k], f, float(d["net_" + f][k]))
     for node in range(g.n_nodes):
@@ -113,8 +122,10 @@ def graph_from_arrays(d: dict) -> NetGraph:
 
 
 def cfg_from_dict(config: dict, n_vehicles: int = 5) -> NetCfg:
-    """roundabout-v0 config dict (envs/roundabout_env.py:13-42 over abstract.py:102-125)."""
+    """roundabout-v0 / intersection-v0 config dict (envs/roundabout_env.py:13-42,
+    envs/intersection_env.py:17-60 over abstract.py:102-125)."""
     c = NetCfg()
+    intersection = "spawn_probability" in config
     obs, act = config["observation"], config["action"]
     c.n_vehicles = n_vehicles
     c.simulation_frequency = int(config["simulation_frequency"])
@@ -124,7 +135,11 @@ def cfg_from_dict(config: dict, n_vehicles: int = 5) -> NetCfg:
     c.n_target_speeds = len(ts)
     for i, t in enumerate(ts):
         c.target_speeds[i] = t
-    if obs["type"] == "TimeToCollision":
+    c.obs_features = 5
+    if obs["type"] == "OccupancyGrid":
+        c.obs_type = OBS_OCCUPANCY
+        c.obs_vehicles_count = 5
+    elif obs["type"] == "TimeToCollision":
         c.obs_type = OBS_TTC
         c.ttc_horizon = int(obs.get("horizon", 10))
         c.obs_vehicles_count = 5
@@ -136,6 +151,9 @@ def cfg_from_dict(config: dict, n_vehicles: int = 5) -> NetCfg:
         c.obs_absolute = int(bool(obs.get("absolute", False)))
         c.obs_normalize = int(bool(obs.get("normalize", True)))
         c.obs_clip = int(bool(obs.get("clip", True)))
+        feats = obs.get("features") or ["presence", "x", "y", "vx", "vy"]
+        assert feats[:5] == ["presence", "x", "y", "vx", "vy"] and feats[5:] in ([], ["cos_h", "sin_h"]), feats
+        c.obs_features = len(feats)
         fr = obs.get("features_range")
         assert fr is not None, "roundabout gives explicit features_range"
         (c.obs_x_lo, c.obs_x_hi), (c.obs_y_lo, c.obs_y_hi) = map(lambda r: map(float, r), (fr["x"], fr["y"]))
@@ -144,9 +162,16 @@ def cfg_from_dict(config: dict, n_vehicles: int = 5) -> NetCfg:
     c.duration = float(config["duration"])
     c.collision_reward = float(config["collision_reward"])
     c.high_speed_reward = float(config["high_speed_reward"])
-    c.lane_change_reward = float(config["lane_change_reward"])
+    c.lane_change_reward = float(config.get("lane_change_reward", 0))
     c.acc_max, c.comfort_acc_max, c.comfort_acc_min = 6.0, 3.0, -5.0
     c.distance_wanted, c.time_wanted = 10.0, 1.5
+    if intersection:  # intersection_env.py:262-265 overrides + RegulatedRoad
+        c.distance_wanted, c.comfort_acc_max, c.comfort_acc_min = 7.0, 6.0, -3.0
+        c.regulated, c.reward_type = 1, 1
+        c.action_mode = 1 if (act.get("longitudinal", True) and not act.get("lateral", True)) else 0
+        c.arrived_reward = float(config["arrived_reward"])
+        c.reward_speed_lo, c.reward_speed_hi = (float(v) for v in config["reward_speed_range"])
+        c.offroad_terminal = int(bool(config["offroad_terminal"]))
     c.politeness, c.lane_change_min_acc_gain = 0.0, 0.2
     c.lane_change_max_braking_imposed, c.lane_change_delay = 2.0, 1.0
     c.perception_distance = 200.0
@@ -165,6 +190,9 @@ class NetOracleBatch:
         self.a["route_len"] = np.zeros((n, V), dtype=np.int32)
         self.a["speed_index"] = np.zeros(n, dtype=np.int32)
         self.a["time"] = np.zeros(n, dtype=np.float64)
+        self.a["count"] = np.full(n, V, dtype=np.int32)
+        self.a["is_yielding"] = np.zeros((n, V), dtype=np.int32)
+        self.a["road_steps"] = np.zeros(n, dtype=np.int32)
         self.obs_size = lib().net_obs_size(C.byref(cfg))
         self.obs = np.zeros((n, self.obs_size), dtype=np.float32)
         self.reward = np.zeros(n, dtype=np.float64)
@@ -173,10 +201,12 @@ class NetOracleBatch:
 
     def _state(self, e: int) -> NetState:
         st = NetState()
-        for k in list(_SF) + list(_SI) + ["route", "route_len"]:
+        for k in list(_SF) + list(_SI) + ["route", "route_len", "is_yielding"]:
             setattr(st, k, self.a[k][e].ctypes.data)
         st.speed_index = self.a["speed_index"][e:e + 1].ctypes.data
         st.time = self.a["time"][e:e + 1].ctypes.data
+        st.count = self.a["count"][e:e + 1].ctypes.data
+        st.road_steps = self.a["road_steps"][e:e + 1].ctypes.data
         return st
 
     def observe(self):
@@ -206,9 +236,180 @@ class NetOracleBatch:
         self.a["impact_x"][e] = np.where(has, st["impact"][:, 0], 0.0)
         self.a["impact_y"][e] = np.where(has, st["impact"][:, 1], 0.0)
         self.a["check_collisions"][e] = st["check_collisions"]
-        kind = np.full(self.V, KIND_IDM, dtype=np.int32)
-        kind[0] = KIND_MDP
-        self.a["kind"][e] = kind
+        if "kind" in st:
+            self.a["kind"][e] = st["kind"]
+            self.a["count"][e] = int(st["count"])
+            self.a["is_yielding"][e] = st["is_yielding"]
+            self.a["road_steps"][e] = int(st["road_steps"])
+        else:
+            kind = np.full(self.V, KIND_IDM, dtype=np.int32)
+            kind[0] = KIND_MDP
+            self.a["kind"][e] = kind
         self.a["route"][e], self.a["route_len"][e] = st["route"], st["route_len"]
         self.a["speed_index"][e] = st["speed_index"][0]
         self.a["time"][e] = float(st["time"])
+
+
+class IntersectionOracle(NetOracleBatch):
+    """intersection-v0: the C oracle for act/step/observe/reward plus the numpy restatement of the
+    dynamic population (envs/intersection_env.py:136-140,245-366): per-step _clear_vehicles /
+    _spawn_vehicle and the _make_vehicles warm-up, drawing from each env's numpy Generator."""
+
+    VMAX = 32
+
+    def __init__(self, graph: NetGraph, cfg: NetCfg, n_envs: int, net_arrays: dict, config: dict):
+        cfg.n_vehicles = self.VMAX
+        super().__init__(graph, cfg, n_envs)
+        self.config = config
+        self.net = net_arrays
+        names = [str(x) for x in net_arrays["net_node_names"]]
+        self.node = {nm: i for i, nm in enumerate(names)}
+        self.names = names
+        self.lane_of = {}
+        for k in range(len(net_arrays["net_type"])):
+            self.lane_of[(names[net_arrays["net_from_node"][k]], names[net_arrays["net_to_node"][k]],
+                          int(net_arrays["net_lane_id"][k]))] = k
+        self.succ = {nm: [] for nm in names}
+        for k in range(len(net_arrays["net_type"])):
+            f, t = names[net_arrays["net_from_node"][k]], names[net_arrays["net_to_node"][k]]
+            if t not in self.succ[f]:
+                self.succ[f].append(t)
+        self.rng = [np.random.Generator(np.random.PCG64(0)) for _ in range(n_envs)]
+        self.a["count"][:] = 0
+
+    # ---- helpers
+    def set_rng_words(self, e, w):
+        st = self.rng[e].bit_generator.state
+        st["state"]["state"] = (int(w[0]) << 64) | int(w[1])
+        st["state"]["inc"] = (int(w[2]) << 64) | int(w[3])
+        st["has_uint32"], st["uinteger"] = int(w[4]) >> 32, int(w[4]) & 0xFFFFFFFF
+        self.rng[e].bit_generator.state = st
+
+    def rng_words(self, e):
+        st = self.rng[e].bit_generator.state
+        m = (1 << 64) - 1
+        return np.array([st["state"]["state"] >> 64, st["state"]["state"] & m, st["state"]["inc"] >> 64,
+                         st["state"]["inc"] & m, (int(st["has_uint32"]) << 32) | int(st["uinteger"])], dtype=np.uint64)
+
+    def _lane_pos(self, lane, s):
+        x, y = C.c_double(), C.c_double()
+        lib().net_lane_position(C.byref(self.g.lanes[lane]), float(s), 0.0, C.byref(x), C.byref(y))
+        return x.value, y.value
+
+    def _shortest_path(self, start, goal):
+        queue = [(start, [start])]
+        while queue:
+            node, path = queue.pop(0)
+            for nxt in sorted(k for k in self.succ.get(node, []) if k not in path):
+                if nxt == goal:
+                    return path + [nxt]
+                if self.succ.get(nxt):
+                    queue.append((nxt, path + [nxt]))
+        return []
+
+    def _route(self, lane, destination):
+        f, t, lid = self.names[self.g.lanes[lane].from_node], self.names[self.g.lanes[lane].to_node], self.g.lanes[lane].lane_id
+        path = self._shortest_path(t, destination)
+        route = [(f, t, lid)] + [(path[i], path[i + 1], None) for i in range(len(path) - 1)]
+        enc = np.zeros(NET_MAX_ROUTE, dtype=np.int32)
+        for k, (a, b, l) in enumerate(route):
+            enc[k] = self.node[a] | (self.node[b] << 8) | (((-1 if l is None else l) + 1) << 16)
+        return enc, len(route)
+
+    def _append(self, e, x, y, heading, speed, kind, route, delta, target_speed=None, timer=None):
+        n = int(self.a["count"][e])
+        lane = lib().net_closest_lane(C.byref(self.g), x, y, heading)
+        a = self.a
+        a["x"][e, n], a["y"][e, n], a["heading"][e, n], a["speed"][e, n] = x, y, heading, speed
+        a["target_speed"][e, n] = speed if target_speed is None else target_speed
+        a["timer"][e, n] = ((x + y) * np.pi) % 1.0 if timer is None else timer
+        a["delta"][e, n] = delta
+        a["impact_x"][e, n] = a["impact_y"][e, n] = 0.0
+        a["lane"][e, n] = a["target_lane"][e, n] = lane
+        a["kind"][e, n], a["crashed"][e, n], a["has_impact"][e, n] = kind, 0, 0
+        a["check_collisions"][e, n], a["is_yielding"][e, n] = 1, 0
+        a["route"][e, n], a["route_len"][e, n] = self._route(lane, route)
+        a["count"][e] = n + 1
+        return n
+
+    # ---- envs/intersection_env.py:325-352
+    def _spawn_vehicle(self, e, longitudinal=0.0, position_deviation=1.0, speed_deviation=1.0,
+                       spawn_probability=0.6, go_straight=False):
+        g = self.rng[e]
+        if g.uniform() > spawn_probability:
+            return
+        route = g.choice(range(4), size=2, replace=False)
+        route[1] = (route[0] + 2) % 4 if go_straight else route[1]
+        lane = self.lane_of[("o" + str(route[0]), "ir" + str(route[0]), 0)]
+        lon = longitudinal + 5.0 + g.normal() * position_deviation
+        speed = 8.0 + g.normal() * speed_deviation
+        x, y = self._lane_pos(lane, lon)
+        heading = lib().net_lane_heading_at(C.byref(self.g.lanes[lane]), float(lon))
+        n = int(self.a["count"][e])
+        for v in range(n):
+            if np.linalg.norm(np.array([self.a["x"][e, v] - x, self.a["y"][e, v] - y])) < 15:
+                return
+        if n >= self.VMAX:
+            raise RuntimeError("vehicle capacity exceeded")
+        delta = None
+        idx = self._append(e, x, y, heading, speed, KIND_IDM, "o" + str(route[1]), 4.0)
+        self.a["delta"][e, idx] = g.uniform(low=3.5, high=4.5)
+
+    # ---- envs/intersection_env.py:354-366
+    def _clear_vehicles(self, e):
+        n = int(self.a["count"][e])
+        keep = []
+        for v in range(n):
+            L = self.g.lanes[int(self.a["lane"][e, v])]
+            s_, lat_ = C.c_double(), C.c_double()
+            lib().net_lane_local(C.byref(L), float(self.a["x"][e, v]), float(self.a["y"][e, v]), C.byref(s_), C.byref(lat_))
+            leaving = bool(L.exit_lane) and s_.value >= L.length - 4 * 5.0
+            if self.a["kind"][e, v] == KIND_MDP or not leaving:
+                keep.append(v)
+        if len(keep) != n:
+            for k in self.a:
+                if k in ("speed_index", "time", "count", "road_steps"):
+                    continue
+                self.a[k][e, :len(keep)] = self.a[k][e, keep]
+            self.a["count"][e] = len(keep)
+
+    # ---- envs/intersection_env.py:245-323
+    def reset_env(self, e, seed=None):
+        if seed is not None:
+            self.rng[e] = np.random.Generator(np.random.PCG64(np.random.SeedSequence(int(seed))))
+        g = self.rng[e]
+        self.a["count"][e] = 0
+        self.a["road_steps"][e] = 0
+        self.a["time"][e] = 0.0
+        n_vehicles = int(self.config["initial_vehicle_count"])
+        for t in range(n_vehicles - 1):
+            self._spawn_vehicle(e, np.linspace(0, 80, n_vehicles)[t])
+        st = self._state(e)
+        lib().net_substeps(C.byref(self.g), C.byref(self.cfg), C.byref(st), 3 * int(self.config["simulation_frequency"]))
+        self._spawn_vehicle(e, 60, spawn_probability=1.0, go_straight=True, position_deviation=0.1, speed_deviation=0.0)
+        ego_lane = self.lane_of[("o0", "ir0", 0)]
+        destination = self.config["destination"] or "o" + str(g.integers(1, 4))
+        x, y = self._lane_pos(ego_lane, 60.0 + 5.0 * g.normal(1.0))
+        heading = lib().net_lane_heading_at(C.byref(self.g.lanes[ego_lane]), 60.0)
+        speed_limit = self.g.lanes[ego_lane].speed_limit
+        ts = [self.cfg.target_speeds[i] for i in range(self.cfg.n_target_speeds)]
+        si = int(np.clip(np.round((speed_limit - ts[0]) / (ts[-1] - ts[0]) * (len(ts) - 1)), 0, len(ts) - 1))
+        idx = self._append(e, x, y, heading, speed_limit, KIND_MDP, destination, 4.0, target_speed=ts[si], timer=0.0)
+        self.a["speed_index"][e] = si
+        # prevent early collisions: drop traffic within 20 m of the ego
+        n = int(self.a["count"][e])
+        keep = [v for v in range(n) if v == idx or not (
+            np.linalg.norm(np.array([self.a["x"][e, v] - x, self.a["y"][e, v] - y])) < 20)]
+        for k in self.a:
+            if k in ("speed_index", "time", "count", "road_steps"):
+                continue
+            self.a[k][e, :len(keep)] = self.a[k][e, keep]
+        self.a["count"][e] = len(keep)
+
+    def step(self, actions):
+        out = super().step(actions)
+        p = float(self.config["spawn_probability"])
+        for e in range(self.n):
+            self._clear_vehicles(e)
+            self._spawn_vehicle(e, spawn_probability=p)
+        return out

@@ -99,12 +99,14 @@ def dump_network(env) -> dict:
         "width", "speed_limit", "length", "sx", "sy", "ex", "ey", "dx", "dy", "lx", "ly", "heading",
         "amplitude", "pulsation", "phase", "cx", "cy", "radius", "start_phase", "end_phase", "direction")}
     i = {k: np.zeros(n, dtype=np.int32) for k in (
-        "type", "from_node", "to_node", "lane_id", "road_first", "road_count", "forbidden", "priority")}
+        "type", "from_node", "to_node", "lane_id", "road_first", "road_count", "forbidden", "priority",
+        "exit_lane")}
     for k, ((fr, to, lid), lane) in enumerate(lanes):
         i["from_node"][k], i["to_node"][k], i["lane_id"][k] = ids[fr], ids[to], lid
         i["road_first"][k] = idx_of[(fr, to, 0)]
         i["road_count"][k] = len(env.road.network.graph[fr][to])
         i["forbidden"][k], i["priority"][k] = int(lane.forbidden), int(lane.priority)
+        i["exit_lane"][k] = int("il" in fr and "o" in to)  # intersection_env.py:354-373
         f["width"][k], f["speed_limit"][k], f["length"][k] = lane.width, lane.speed_limit, lane.length
         if isinstance(lane, CircularLane):
             i["type"][k] = 2
@@ -144,7 +146,7 @@ def encode_route(env, vehicle) -> tuple:
     return enc, len(route)
 
 
-def dump_state(env) -> dict:
+def dump_state(env, pad: int = 0) -> dict:
     """Snapshot the reference road in the SoA schema used by ``highwayenv_b200``.
 
     Fields (per vehicle, list order = ``road.vehicles`` order):
@@ -192,10 +194,23 @@ def dump_state(env) -> dict:
         enc = [encode_route(env, v) for v in vs]
         d["route"] = np.stack([e[0] for e in enc])
         d["route_len"] = np.array([e[1] for e in enc], dtype=np.int32)
+    if hasattr(env.road, "steps"):  # RegulatedRoad (road/regulation.py)
+        d["road_steps"] = np.int64(env.road.steps)
+        d["is_yielding"] = np.array([bool(getattr(v, "is_yielding", False)) for v in vs], dtype=np.bool_)
+        d["kind"] = np.array([1 if v in env.controlled_vehicles else 0 for v in vs], dtype=np.int32)
+    if pad:
+        assert n <= pad, n
+        d["count"] = np.int32(n)
+        for k, a in list(d.items()):
+            if isinstance(a, np.ndarray) and a.ndim >= 1 and a.shape[0] == n and k not in ("time",):
+                fill = np.nan if a.dtype.kind == "f" else 0
+                out = np.full((pad,) + a.shape[1:], fill, dtype=a.dtype)
+                out[:n] = a
+                d[k] = out
     return d
 
 
-def rollout(env_id: str, config: dict | None, seed: int, actions, record_substeps: bool = False):
+def rollout(env_id: str, config: dict | None, seed: int, actions, record_substeps: bool = False, pad: int = 0):
     """Reset with ``seed`` and apply ``actions``; returns dict of stacked arrays.
 
     Stepping continues after termination (the reference allows it), so trajectories have
@@ -203,11 +218,13 @@ def rollout(env_id: str, config: dict | None, seed: int, actions, record_substep
     """
     env = make_reference_env(env_id, config)
     obs0, _ = env.reset(seed=seed)
-    states = [dump_state(env)]
+    states = [dump_state(env, pad)]
+    rng_states = [env.np_random.bit_generator.state]
     obs, rew, term, trunc = [np.asarray(obs0)], [], [], []
     for a in actions:
         o, r, te, tr, _info = env.step(a)
-        states.append(dump_state(env))
+        states.append(dump_state(env, pad))
+        rng_states.append(env.np_random.bit_generator.state)
         obs.append(np.asarray(o))
         rew.append(float(r))
         term.append(bool(te))
@@ -219,4 +236,8 @@ def rollout(env_id: str, config: dict | None, seed: int, actions, record_substep
     out["terminated"] = np.array(term, dtype=np.bool_)
     out["truncated"] = np.array(trunc, dtype=np.bool_)
     out["actions"] = np.asarray(actions)
+    m64 = (1 << 64) - 1
+    out["rng_words"] = np.array([[st["state"]["state"] >> 64, st["state"]["state"] & m64, st["state"]["inc"] >> 64,
+                                  st["state"]["inc"] & m64, (int(st["has_uint32"]) << 32) | int(st["uinteger"])]
+                                 for st in rng_states], dtype=np.uint64)
     return out

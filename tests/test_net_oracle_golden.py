@@ -79,3 +79,66 @@ def test_free_running_prefix(name):
             assert np.max(np.abs(obs[i].reshape(g["obs"][i, t + 1].shape) - g["obs"][i, t + 1])) <= 1e-6
             compared += 1
     assert compared >= 3 * S
+
+
+# ------------------------------------------------------------------ intersection-v0
+INTER = ["intersection_kin", "intersection_grid"]
+_IKEYS = ("x", "y", "heading", "speed", "target_speed", "timer", "delta", "lane", "target_lane", "crashed",
+          "impact", "check_collisions", "speed_index", "time", "route", "route_len", "kind", "is_yielding",
+          "count", "road_steps")
+
+
+def inter_state(g, i, t):
+    return {k: g[k][i, t] for k in _IKEYS}
+
+
+def compare_inter(st, a, e, ctx, tol=1e-9):
+    """a: dict of arrays [n_envs, 32, ...] in the oracle's schema."""
+    n = int(st["count"])
+    assert n == int(a["count"][e]), f"{ctx} count {n} vs {a['count'][e]}"
+    for k in ("x", "y", "heading", "speed", "target_speed"):
+        d = np.max(np.abs(st[k][:n] - a[k][e][:n]))
+        assert d <= tol, f"{ctx} {k} {d}"
+    idm = st["kind"][:n] == 0
+    if idm.any():
+        assert np.max(np.abs(st["timer"][:n][idm] - a["timer"][e][:n][idm])) <= tol, f"{ctx} timer"
+        assert np.max(np.abs(st["delta"][:n][idm] - a["delta"][e][:n][idm])) <= tol, f"{ctx} delta"
+    for k in ("lane", "target_lane", "kind", "route_len"):
+        assert np.array_equal(st[k][:n], np.asarray(a[k][e][:n]).astype(st[k].dtype)), f"{ctx} {k}"
+    assert np.array_equal(st["crashed"][:n].astype(bool), np.asarray(a["crashed"][e][:n]).astype(bool)), f"{ctx} crashed"
+    assert np.array_equal(st["is_yielding"][:n].astype(bool), np.asarray(a["is_yielding"][e][:n]).astype(bool)), f"{ctx} yield"
+    has = ~np.isnan(st["impact"][:n, 0])
+    assert np.array_equal(has, np.asarray(a["has_impact"][e][:n]).astype(bool)), f"{ctx} has_impact"
+    for v in range(n):
+        m = st["route_len"][v]
+        assert np.array_equal(st["route"][v][:m], a["route"][e][v][:m]), f"{ctx} route {v}"
+    assert int(st["road_steps"]) == int(a["road_steps"][e]), f"{ctx} road_steps"
+
+
+@pytest.mark.parametrize("name", INTER)
+def test_intersection_reset_and_teacher_forced(name):
+    """_make_vehicles (9 spawns, 45 warm-up substeps under RegulatedRoad, challenger, ego, pruning) and
+    every step incl. regulation, _clear_vehicles/_spawn_vehicle and the numpy stream, vs the reference."""
+    g = load_golden(name)
+    graph = no.graph_from_arrays(g)
+    cfg = no.cfg_from_dict(g["config"])
+    S, T = g["actions"].shape[:2]
+    ob = no.IntersectionOracle(graph, cfg, S, g, g["config"])
+    for i in range(S):
+        ob.reset_env(i, seed=int(g["seeds"][i]))
+        compare_inter(inter_state(g, i, 0), ob.a, i, f"{name} reset#{i}")
+        assert np.array_equal(ob.rng_words(i), g["rng_words"][i, 0])
+    obs0 = ob.observe().reshape(g["obs"][:, 0].shape)
+    assert np.max(np.abs(obs0 - g["obs"][:, 0])) <= 1e-6
+    for t in range(T):
+        for i in range(S):
+            ob.load_state(i, inter_state(g, i, t))
+            ob.set_rng_words(i, g["rng_words"][i, t])
+        obs, rew, term, trunc = ob.step(g["actions"][:, t])
+        for i in range(S):
+            ctx = f"{name} #{i} t={t}"
+            compare_inter(inter_state(g, i, t + 1), ob.a, i, ctx)
+            assert abs(rew[i] - g["reward"][i, t]) <= 1e-9, ctx
+            assert bool(term[i]) == bool(g["terminated"][i, t]) and bool(trunc[i]) == bool(g["truncated"][i, t]), ctx
+            assert np.max(np.abs(obs[i].reshape(g["obs"][i, t + 1].shape) - g["obs"][i, t + 1])) <= 1e-6, ctx
+            assert np.array_equal(ob.rng_words(i), g["rng_words"][i, t + 1]), ctx
