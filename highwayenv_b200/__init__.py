@@ -24,6 +24,7 @@ REGISTRY = {
     "highway-v0": "highwayenv_b200.envs.highway_env:BatchedHighwayEnv",
     "highway-fast-v0": "highwayenv_b200.envs.highway_env:BatchedHighwayEnvFast",
     "roundabout-v0": "highwayenv_b200.envs.roundabout_env:BatchedRoundaboutEnv",
+    "intersection-v0": "highwayenv_b200.envs.intersection_env:BatchedIntersectionEnv",
 }
 
 

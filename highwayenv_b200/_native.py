@@ -61,11 +61,13 @@ class HwyHighwayState(C.Structure):
 
 # ---- general road networks (roundabout-v0)
 HWY_NET_MAX_LANES, HWY_NET_MAX_NODES, HWY_NET_MAX_SUCC, HWY_NET_MAX_ROUTE, HWY_NET_GROUP = 64, 64, 6, 16, 8
+HWY_NET_GROUP_LARGE = 32
 LANE_STRAIGHT, LANE_SINE, LANE_CIRCULAR = 0, 1, 2
-OBS_KINEMATICS, OBS_TTC = 0, 2
+OBS_KINEMATICS, OBS_OCCUPANCY, OBS_TTC = 0, 1, 2
+META_YIELDING = 1 << 22
 
 NET_LANE_INT_FIELDS = ("type", "from_node", "to_node", "lane_id", "road_first", "road_count", "forbidden",
-                       "priority")
+                       "priority", "exit_lane", "_pad")
 NET_LANE_F64_FIELDS = ("width", "speed_limit", "length", "sx", "sy", "ex", "ey", "dx", "dy", "lx", "ly",
                        "heading", "amplitude", "pulsation", "phase", "cx", "cy", "radius", "start_phase",
                        "end_phase", "direction")
@@ -97,6 +99,9 @@ class HwyNetParams(C.Structure):
             "comfort_acc_max", "comfort_acc_min", "distance_wanted", "time_wanted", "politeness",
             "lane_change_min_acc_gain", "lane_change_max_braking_imposed", "lane_change_delay",
             "perception_distance")]
+        + [(n, C.c_int32) for n in ("regulated", "action_mode", "reward_type", "obs_features", "offroad_terminal",
+                                    "dynamic_population")]
+        + [(n, C.c_double) for n in ("arrived_reward", "reward_speed_lo", "reward_speed_hi")]
     )
 
 
@@ -105,8 +110,14 @@ class HwyNetState(C.Structure):
         ("n_envs", C.c_int32), ("vp", C.c_int32),
         ("pos", C.c_void_p), ("hs", C.c_void_p), ("tt", C.c_void_p), ("imp", C.c_void_p),
         ("delta", C.c_void_p), ("meta", C.c_void_p), ("route", C.c_void_p), ("route_len", C.c_void_p),
-        ("speed_index", C.c_void_p), ("time", C.c_void_p),
+        ("speed_index", C.c_void_p), ("time", C.c_void_p), ("count", C.c_void_p), ("road_steps", C.c_void_p),
+        ("rng", C.c_void_p),
     ]
+
+
+class HwyIntersectionSpawn(C.Structure):
+    _fields_ = [("spawn_lane", C.c_int32 * 4), ("spawn_probability", C.c_double),
+                ("route_table", C.c_void_p), ("route_len", C.c_void_p)]
 
 
 class HwyRoundaboutSpawn(C.Structure):
@@ -125,6 +136,7 @@ EXPORTS = (
     "hwy_abi_version", "hwy_last_error", "hwy_highway_slot_stride", "hwy_highway_reset",
     "hwy_highway_observe", "hwy_highway_step", "hwy_highway_autoreset", "hwy_launch_count",
     "hwy_network_obs_size", "hwy_network_step", "hwy_network_observe", "hwy_roundabout_reset",
+    "hwy_intersection_step", "hwy_network_substeps",
 )
 
 _lib = None
@@ -165,6 +177,11 @@ def load():
                                      C.c_void_p, C.c_void_p, C.c_void_p]
     lib.hwy_network_observe.restype = C.c_int
     lib.hwy_network_observe.argtypes = [NP, NG, NS, C.c_void_p, C.c_void_p]
+    lib.hwy_intersection_step.restype = C.c_int
+    lib.hwy_intersection_step.argtypes = [NP, NG, C.POINTER(HwyIntersectionSpawn), NS, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.hwy_network_substeps.restype = C.c_int
+    lib.hwy_network_substeps.argtypes = [NP, NG, NS, C.c_void_p, C.c_int, C.c_void_p]
     lib.hwy_roundabout_reset.restype = C.c_int
     lib.hwy_roundabout_reset.argtypes = [NP, NG, C.POINTER(HwyRoundaboutSpawn), NS, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_void_p]

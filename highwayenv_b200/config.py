@@ -128,3 +128,40 @@ def roundabout_default_config() -> dict:
 
 
 DEFAULTS["roundabout-v0"] = roundabout_default_config
+
+
+def intersection_default_config() -> dict:
+    """IntersectionEnv.default_config (highway_env/envs/intersection_env.py:17-60)."""
+    config = abstract_default_config()
+    update_config(config, {
+        "observation": {
+            "type": "Kinematics",
+            "vehicles_count": 15,
+            "features": ["presence", "x", "y", "vx", "vy", "cos_h", "sin_h"],
+            "features_range": {"x": [-100, 100], "y": [-100, 100], "vx": [-20, 20], "vy": [-20, 20]},
+            "absolute": True,
+            "flatten": False,
+            "observe_intentions": False,
+        },
+        "action": {"type": "DiscreteMetaAction", "longitudinal": True, "lateral": False,
+                   "target_speeds": [0, 4.5, 9]},
+        "duration": 13,
+        "destination": "o1",
+        "controlled_vehicles": 1,
+        "initial_vehicle_count": 10,
+        "spawn_probability": 0.6,
+        "screen_width": 600,
+        "screen_height": 600,
+        "centering_position": [0.5, 0.6],
+        "scaling": 5.5 * 1.3,
+        "collision_reward": -5,
+        "high_speed_reward": 1,
+        "arrived_reward": 1,
+        "reward_speed_range": [7.0, 9.0],
+        "normalize_reward": False,
+        "offroad_terminal": False,
+    })
+    return config
+
+
+DEFAULTS["intersection-v0"] = intersection_default_config

@@ -25,10 +25,9 @@
 namespace hwynet {
 using namespace hwy;
 
-constexpr int G = HWY_NET_GROUP;
 constexpr int R = HWY_NET_MAX_ROUTE;
-constexpr int kBlockEnvs = 32;
-constexpr int kBlockThreads = kBlockEnvs * G;
+constexpr int kBlockThreads = 256;
+constexpr int kPred = 11;  // np.arange(0.25, 3, 0.25) prediction points of RegulatedRoad.is_conflict_possible
 
 struct GraphShared {
     int n_lanes, n_nodes;
@@ -37,13 +36,28 @@ struct GraphShared {
     int succ[HWY_NET_MAX_NODES][HWY_NET_MAX_SUCC];
 };
 
+// Per-env shared staging for G vehicle slots.  REG adds the RegulatedRoad prediction buffers.
+template <int G, bool REG>
 struct EnvStage {
     double x[G], y[G], heading[G], c[G], s[G], v[G], ts[G];
-    int lane[G], tgt[G];
+    int lane[G], tgt[G], kind[G];
     int route[G][R];
     int route_len[G];
-    double ttc[3][4][12];  // TimeToCollision grid [speed][lane on road][time]
+    int count, ego, speed_index, road_steps;
+    unsigned yield_mask;
+    // spawn record (dynamic population): written by the group's first thread, adopted by the new slot
+    double sp_x, sp_y, sp_h, sp_speed, sp_delta;
+    int sp_ok, sp_lane, sp_dest;
     double key[G];
+    union {
+        double ttc[3][4][12];  // TimeToCollision grid [speed][lane on road][time]
+        struct {
+            int owner[121];           // OccupancyGrid: lowest vehicle index in the cell
+            unsigned char road[121];  // on_road layer
+        } cells;
+    } o;
+    // RegulatedRoad: predicted (x, y, heading) of every vehicle at the 11 horizon points
+    double pred[REG ? G : 1][REG ? kPred : 1][3];
 };
 
 // ------------------------------------------------------------------ lanes (road/lane.py)
@@ -158,7 +172,8 @@ __device__ __forceinline__ int next_lane_given_next_road(const GraphShared& g, i
 }
 
 // road/road.py:73-136 next_lane: pops the vehicle's route in place
-__device__ __noinline__ int next_lane(const GraphShared& g, EnvStage& st, int v, int cur) {
+template <int G, bool REG>
+__device__ __noinline__ int next_lane(const GraphShared& g, EnvStage<G, REG>& st, int v, int cur) {
     const HwyNetLane& C = g.lanes[cur];
     int* route = st.route[v];
     int rlen = st.route_len[v];
@@ -199,14 +214,16 @@ __device__ __noinline__ int next_lane(const GraphShared& g, EnvStage& st, int v,
 }
 
 // vehicle/controller.py:135-143 follow_road
-__device__ __forceinline__ void follow_road(const GraphShared& g, EnvStage& st, int v) {
+template <int G, bool REG>
+__device__ __forceinline__ void follow_road(const GraphShared& g, EnvStage<G, REG>& st, int v) {
     const HwyNetLane& T = g.lanes[st.tgt[v]];
     if (lane_s_of(T, st.x[v], st.y[v]) > T.length - kLaneVehLength / 2)  // after_end (lane.py:120-125)
         st.tgt[v] = next_lane(g, st, v, st.tgt[v]);
 }
 
 // road/road.py:483-547 neighbour_vehicles, same-segment search
-__device__ __noinline__ void neighbours(const GraphShared& g, const EnvStage& st, int V, int veh,
+template <int G, bool REG>
+__device__ __noinline__ void neighbours(const GraphShared& g, const EnvStage<G, REG>& st, int V, int veh,
                                         int lane_idx, int& front, int& rear) {
     const HwyNetLane& L = g.lanes[lane_idx];
     double s = lane_s_of(L, st.x[veh], st.y[veh]);
@@ -229,13 +246,15 @@ __device__ __noinline__ void neighbours(const GraphShared& g, const EnvStage& st
     }
 }
 
-__device__ __forceinline__ double lane_distance_to(const GraphShared& g, const EnvStage& st, int self,
+template <int G, bool REG>
+__device__ __forceinline__ double lane_distance_to(const GraphShared& g, const EnvStage<G, REG>& st, int self,
                                                    int other) {
     const HwyNetLane& L = g.lanes[st.lane[self]];
     return lane_s_of(L, st.x[other], st.y[other]) - lane_s_of(L, st.x[self], st.y[self]);
 }
 // vehicle/behavior.py:192-217
-__device__ __forceinline__ double desired_gap(const HwyNetParams& P, const EnvStage& st, int ego, int front) {
+template <int G, bool REG>
+__device__ __forceinline__ double desired_gap(const HwyNetParams& P, const EnvStage<G, REG>& st, int ego, int front) {
     double ab = -P.comfort_acc_max * P.comfort_acc_min;
     double dvx = st.v[ego] * st.c[ego] - st.v[front] * st.c[front];
     double dvy = st.v[ego] * st.s[ego] - st.v[front] * st.s[front];
@@ -243,8 +262,9 @@ __device__ __forceinline__ double desired_gap(const HwyNetParams& P, const EnvSt
     return P.distance_wanted + st.v[ego] * P.time_wanted + st.v[ego] * dv / (2 * sqrt(ab));
 }
 // vehicle/behavior.py:150-190 with the caller's DELTA
+template <int G, bool REG>
 __device__ __noinline__ double idm_acceleration(const HwyNetParams& P, const GraphShared& g,
-                                                const EnvStage& st, double delta, int ego, int front) {
+                                                const EnvStage<G, REG>& st, double delta, int ego, int front) {
     if (ego < 0) return 0.0;
     double ego_target_speed = clipd(st.ts[ego], 0.0, g.lanes[st.lane[ego]].speed_limit);
     double acc = P.comfort_acc_max *
@@ -260,7 +280,8 @@ __device__ __noinline__ double idm_acceleration(const HwyNetParams& P, const Gra
 __device__ __forceinline__ int isign(int a) { return (a > 0) - (a < 0); }
 
 // vehicle/behavior.py:265-324 mobil(lane_index), incl. the planned-route branch
-__device__ __noinline__ bool mobil(const HwyNetParams& P, const GraphShared& g, const EnvStage& st, int V,
+template <int G, bool REG>
+__device__ __noinline__ bool mobil(const HwyNetParams& P, const GraphShared& g, const EnvStage<G, REG>& st, int V,
                                    int v, double delta, int lane_index) {
     int new_preceding, new_following;
     neighbours(g, st, V, v, lane_index, new_preceding, new_following);
@@ -289,8 +310,9 @@ __device__ __noinline__ bool mobil(const HwyNetParams& P, const GraphShared& g, 
 }
 
 // vehicle/behavior.py:219-263 change_lane_policy; returns the (possibly reset) timer
+template <int G, bool REG>
 __device__ __forceinline__ double change_lane_policy(const HwyNetParams& P, const GraphShared& g,
-                                                     EnvStage& st, int V, int v, double delta,
+                                                     EnvStage<G, REG>& st, int V, int v, double delta,
                                                      double timer) {
     const int lane = st.lane[v];
     if (lane != st.tgt[v]) {
@@ -342,16 +364,21 @@ __device__ __forceinline__ int speed_to_index(const HwyNetParams& P, double spee
 }
 
 // group-wide helpers (G consecutive lanes of a warp)
+template <int G>
 __device__ __forceinline__ unsigned group_mask() {
-    return ((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1));
+    return G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
 }
-__device__ __forceinline__ void group_sync() { __syncwarp(group_mask()); }
+template <int G>
+__device__ __forceinline__ void group_sync() {
+    __syncwarp(group_mask<G>());
+}
 
 // road/road.py:55-71 get_closest_lane_index for every vehicle, cooperatively: thread t scans lanes
 // t, t+G, ...; arg-min over (distance, lane index) keeps the first minimum like np.argmin.
-__device__ __forceinline__ int closest_lane_group(const GraphShared& g, const EnvStage& st, int V, int i) {
+template <int G, bool REG>
+__device__ __forceinline__ int closest_lane_group(const GraphShared& g, const EnvStage<G, REG>& st, int V, int i) {
     int mine = 0;
-    const unsigned mask = group_mask();
+    const unsigned mask = group_mask<G>();
     for (int v = 0; v < V; ++v) {
         double bd = INFINITY;
         int bl = 0x7fffffff;
@@ -415,22 +442,24 @@ __device__ __noinline__ bool is_connected_road(const GraphShared& g, int f1, int
 }
 
 // envs/common/finite_mdp.py:104-163 compute_ttc_grid + observation.py:128-152 (pad / crop)
-__device__ __forceinline__ void observe_ttc(const HwyNetParams& P, const GraphShared& g, EnvStage& st,
+template <int G, bool REG>
+__device__ __forceinline__ void observe_ttc(const HwyNetParams& P, const GraphShared& g, EnvStage<G, REG>& st,
                                             int V, int i, int speed_index, float* __restrict__ obs_env) {
-    const HwyNetLane& EL = g.lanes[st.lane[0]];
+    const int ego = st.ego;
+    const HwyNetLane& EL = g.lanes[st.lane[ego]];
     const int n_speeds = P.n_target_speeds, n_lanes = EL.road_count;
     const double tq = 1.0 / P.policy_frequency;
     const int n_t = (int)(P.ttc_horizon / tq);
-    for (int k = i; k < 3 * 4 * 12; k += G) (&st.ttc[0][0][0])[k] = 0.0;
-    group_sync();
-    if (i > 0 && i < V) {  // one thread per other vehicle; cells take the max cost (atomic on bits)
+    for (int k = i; k < 3 * 4 * 12; k += G) (&st.o.ttc[0][0][0])[k] = 0.0;
+    group_sync<G>();
+    if (i != ego && i < V) {  // one thread per other vehicle; cells take the max cost (atomic on bits)
         const int o = i;
         const HwyNetLane& OL = g.lanes[st.lane[o]];
         const bool connected = is_connected_road(g, EL.from_node, EL.to_node, OL.from_node, OL.to_node,
-                                                 st.route[0], st.route_len[0], 3);
+                                                 st.route[ego], st.route_len[ego], 3);
         const double margin = kVehLength / 2 + kVehLength / 2;
-        const double base = lane_distance_to(g, st, 0, o);
-        const double other_projected_speed = st.v[o] * dot2(st.c[o], st.s[o], st.c[0], st.s[0]);
+        const double base = lane_distance_to(g, st, ego, o);
+        const double other_projected_speed = st.v[o] * dot2(st.c[o], st.s[o], st.c[ego], st.s[ego]);
         for (int si = 0; si < n_speeds; ++si) {
             const double ego_speed = P.target_speeds[si];
             if (ego_speed == st.v[o]) continue;
@@ -449,13 +478,13 @@ __device__ __forceinline__ void observe_ttc(const HwyNetParams& P, const GraphSh
                     int t = times[q];
                     if (0 <= t && t < n_t)
                         for (int l = l0; l < l1; ++l)  // positive doubles order like their bit patterns
-                            atomicMax(reinterpret_cast<unsigned long long*>(&st.ttc[si][l][t]),
+                            atomicMax(reinterpret_cast<unsigned long long*>(&st.o.ttc[si][l][t]),
                                       (unsigned long long)__double_as_longlong(cost));
                 }
             }
         }
     }
-    group_sync();
+    group_sync<G>();
     const int ego_lane_id = EL.lane_id;
     for (int k = i; k < 9 * n_t; k += G) {
         int a = k / (3 * n_t), b = (k / n_t) % 3, t = k % n_t;
@@ -463,35 +492,39 @@ __device__ __forceinline__ void observe_ttc(const HwyNetParams& P, const GraphSh
         int src = vrow < 1 + n_speeds ? 0 : (vrow < 1 + n_speeds + (n_speeds - 2) ? 1 + (vrow - (1 + n_speeds)) : n_speeds - 1);
         if (n_speeds == 1) src = 0;
         int lcol = n_lanes + ego_lane_id - 1 + b;
-        double val = (lcol < n_lanes || lcol >= 2 * n_lanes) ? 1.0 : st.ttc[src][lcol - n_lanes][t];
+        double val = (lcol < n_lanes || lcol >= 2 * n_lanes) ? 1.0 : st.o.ttc[src][lcol - n_lanes][t];
         obs_env[k] = (float)val;
     }
 }
 
-// envs/common/observation.py:234-276 with explicit features_range (absolute or relative)
-__device__ __forceinline__ void observe_kinematics(const HwyNetParams& P, const GraphShared& g, EnvStage& st,
-                                                   int V, int i, float* __restrict__ obs_env) {
-    const int K = P.obs_vehicles_count;
-    const double ex = st.x[0], ey = st.y[0];
-    const double evx = st.v[0] * st.c[0], evy = st.v[0] * st.s[0];
+// envs/common/observation.py:234-276 with explicit features_range (absolute or relative);
+// F = 5 (presence, x, y, vx, vy) or 7 (+ cos_h, sin_h, vehicle/kinematics.py:247-248)
+template <int G, bool REG>
+__device__ __forceinline__ void observe_kinematics(const HwyNetParams& P, const GraphShared& g,
+                                                   EnvStage<G, REG>& st, int V, int i,
+                                                   float* __restrict__ obs_env) {
+    const int K = P.obs_vehicles_count, F = P.obs_features == 7 ? 7 : 5;
+    const int ego = st.ego;
+    const double ex = st.x[ego], ey = st.y[ego];
+    const double evx = st.v[ego] * st.c[ego], evy = st.v[ego] * st.s[ego];
     double key = INFINITY;
-    if (i > 0 && i < V) {
+    if (i != ego && i < V) {
         bool ok = norm2(st.x[i] - ex, st.y[i] - ey) < P.perception_distance;
-        double d = lane_distance_to(g, st, 0, i);
+        double d = lane_distance_to(g, st, ego, i);
         ok = ok && (P.obs_see_behind || -2 * kVehLength < d);
         if (ok) key = fabs(d);
     }
     st.key[i] = key;
-    group_sync();
+    group_sync<G>();
     int rank = 0, n_valid = 0;
-    for (int u = 1; u < V; ++u) {
+    for (int u = 0; u < V; ++u) {
         double ku = st.key[u];
         n_valid += ku < INFINITY;
         rank += (ku < key) || (ku == key && u < i);
     }
     int row = -1;
     double r1 = 0, r2 = 0, r3 = 0, r4 = 0;
-    if (i == 0) {
+    if (i == ego && i < V) {
         row = 0;
         r1 = ex;
         r2 = ey;
@@ -523,24 +556,97 @@ __device__ __forceinline__ void observe_kinematics(const HwyNetParams& P, const 
                 r4 = clipd(r4, -1.0, 1.0);
             }
         }
-        float* o = obs_env + 5 * row;
+        float* o = obs_env + F * row;
         o[0] = 1.0f;
         o[1] = (float)r1;
         o[2] = (float)r2;
         o[3] = (float)r3;
         o[4] = (float)r4;
+        if (F == 7) {
+            o[5] = (float)st.c[i];
+            o[6] = (float)st.s[i];
+        }
     }
     int filled = 1 + (n_valid < K - 1 ? n_valid : K - 1);
     for (int k = i; k < K; k += G)
-        if (k >= filled) {
-            float* o = obs_env + 5 * k;
-            o[0] = o[1] = o[2] = o[3] = o[4] = 0.0f;
+        if (k >= filled)
+            for (int f = 0; f < F; ++f) obs_env[F * k + f] = 0.0f;
+}
+
+// envs/common/observation.py:354-484 OccupancyGridObservation.observe with the defaults of :282-284
+// (presence, vx, vy, on_road; 11 x 11 cells of 5 m; world axes; relative to the observer)
+template <int G, bool REG>
+__device__ __forceinline__ void observe_occupancy(const HwyNetParams& P, const GraphShared& g,
+                                                  EnvStage<G, REG>& st, int V, int i,
+                                                  float* __restrict__ obs_env) {
+    const int ego = st.ego;
+    const double lo = -5.5 * 5, step = 5;
+    const double ex = st.x[ego], ey = st.y[ego];
+    const double evx = st.v[ego] * st.c[ego], evy = st.v[ego] * st.s[ego];
+    for (int k = i; k < 121; k += G) {
+        st.o.cells.owner[k] = 0x7fffffff;
+        st.o.cells.road[k] = 0;
+    }
+    group_sync<G>();
+    int cell = -1;
+    if (i < V) {  // vehicles are written in REVERSED list order: the lowest index owns a shared cell
+        double x = st.x[i] - ex, y = st.y[i] - ey;
+        int ci = (int)floor((x - lo) / step), cj = (int)floor((y - lo) / step);
+        if (0 <= ci && ci < 11 && 0 <= cj && cj < 11) {
+            cell = ci * 11 + cj;
+            atomicMin(&st.o.cells.owner[cell], i);
         }
+    }
+    // fill_road_layer_by_lanes (:446-484): waypoints every 5 m within +-100 m of the observer's
+    // longitudinal coordinate on each lane, clipped to the lane
+    for (int l = 0; l < g.n_lanes; ++l) {
+        const HwyNetLane& L = g.lanes[l];
+        const double origin = lane_s_of(L, ex, ey);
+        const double start = origin - 100, stop = origin + 100;
+        const int n = (int)ceil((stop - start) / 5.0);  // np.arange length
+        for (int k = i; k < n; k += G) {
+            double wp = clipd(start + k * 5.0, 0.0, L.length);
+            double px, py;
+            lane_position(L, wp, 0.0, px, py);
+            px -= ex;
+            py -= ey;
+            int ci = (int)floor((px - lo) / step), cj = (int)floor((py - lo) / step);
+            if (0 <= ci && ci < 11 && 0 <= cj && cj < 11) st.o.cells.road[ci * 11 + cj] = 1;
+        }
+    }
+    group_sync<G>();
+    for (int k = i; k < 121; k += G) {
+        obs_env[k] = 0.0f;        // nan_to_num of the untouched cells
+        obs_env[121 + k] = 0.0f;
+        obs_env[242 + k] = 0.0f;
+        obs_env[363 + k] = st.o.cells.road[k] ? 1.0f : 0.0f;
+    }
+    group_sync<G>();
+    if (cell >= 0 && st.o.cells.owner[cell] == i) {
+        double vx = st.v[i] * st.c[i] - evx, vy = st.v[i] * st.s[i] - evy;
+        vx = lmap(vx, -2 * kMaxSpeed, 2 * kMaxSpeed, -1.0, 1.0);  // normalize :340-352 (x, y not normalised)
+        vy = lmap(vy, -2 * kMaxSpeed, 2 * kMaxSpeed, -1.0, 1.0);
+        obs_env[cell] = 1.0f;
+        obs_env[121 + cell] = (float)clipd(vx, -1.0, 1.0);
+        obs_env[242 + cell] = (float)clipd(vy, -1.0, 1.0);
+    }
 }
 
 __device__ __forceinline__ int obs_size(const HwyNetParams& P) {
+    if (P.obs_type == HWY_OBS_OCCUPANCY) return 4 * 11 * 11;
     if (P.obs_type == HWY_OBS_TTC) return 9 * (int)(P.ttc_horizon / (1.0 / P.policy_frequency));
-    return P.obs_vehicles_count * 5;
+    return P.obs_vehicles_count * (P.obs_features == 7 ? 7 : 5);
+}
+
+template <int G, bool REG>
+__device__ __forceinline__ void observe_any(const HwyNetParams& P, const GraphShared& g, EnvStage<G, REG>& st,
+                                            int V, int i, float* __restrict__ obs_env) {
+    if (P.obs_type == HWY_OBS_TTC)
+        observe_ttc(P, g, st, V, i, st.speed_index, obs_env);
+    else if (P.obs_type == HWY_OBS_OCCUPANCY)
+        observe_occupancy(P, g, st, V, i, obs_env);
+    else
+        observe_kinematics(P, g, st, V, i, obs_env);
 }
 
 // ------------------------------------------------------------------ state I/O
@@ -569,9 +675,11 @@ __device__ __forceinline__ void store_regs(const HwyNetState& S, size_t slot, co
     reinterpret_cast<double2*>(S.hs)[slot] = make_double2(r.heading, r.speed);
     reinterpret_cast<double2*>(S.tt)[slot] = make_double2(r.target_speed, r.timer);
     reinterpret_cast<double2*>(S.imp)[slot] = make_double2(r.imp_x, r.imp_y);
+    S.delta[slot] = r.delta;
     S.meta[slot] = r.meta;
 }
-__device__ __forceinline__ void publish(EnvStage& st, int i, const Regs& r) {
+template <int G, bool REG>
+__device__ __forceinline__ void publish(EnvStage<G, REG>& st, int i, const Regs& r) {
     double sn, cs;
     m_sincos(r.heading, &sn, &cs);
     st.x[i] = r.x;
@@ -584,7 +692,6 @@ __device__ __forceinline__ void publish(EnvStage& st, int i, const Regs& r) {
 }
 
 __device__ __forceinline__ void stage_graph(GraphShared& gs, const HwyNetGraph* __restrict__ graph) {
-    // word-wise copy of the immutable lane table into shared memory
     static_assert(sizeof(GraphShared) == sizeof(HwyNetGraph), "layout");
     const int* src = reinterpret_cast<const int*>(graph);
     int* dst = reinterpret_cast<int*>(&gs);
@@ -592,229 +699,537 @@ __device__ __forceinline__ void stage_graph(GraphShared& gs, const HwyNetGraph* 
     __syncthreads();
 }
 
+
+// ------------------------------------------------------------------ RegulatedRoad (road/regulation.py)
+__device__ __forceinline__ int HwyNetLane_route(const HwyNetLane& L) {
+    return L.from_node | (L.to_node << 8) | ((L.lane_id + 1) << 16);
+}
+
+// road/road.py:323-362 position_heading_along_route(route, longitudinal, 0, current_lane_index)
+template <int G, bool REG>
+__device__ __noinline__ void position_heading_along_route(const GraphShared& g, const EnvStage<G, REG>& st, int v,
+                                                          double longitudinal, double& px, double& py,
+                                                          double& heading) {
+    const int cur = st.lane[v];
+    const int* route = st.route[v];
+    int rlen = st.route_len[v];
+    int own = HwyNetLane_route(g.lanes[cur]);
+    if (rlen == 0) {  // `self.route or [self.lane_index]`
+        route = &own;
+        rlen = 1;
+    }
+    int k = 0;
+    for (;;) {
+        int first = road_first(g, RT_FROM(route[k]), RT_TO(route[k]));
+        int id = RT_ID(route[k]);
+        if (id < 0) id = g.lanes[cur].lane_id;
+        const HwyNetLane& L = g.lanes[first + id];
+        if (k < rlen - 1 && longitudinal > L.length) {
+            longitudinal -= L.length;
+            ++k;
+            continue;
+        }
+        lane_position(L, longitudinal, 0.0, px, py);
+        heading = lane_heading_at(L, longitudinal);
+        return;
+    }
+}
+
+// utils.py:77-174 rotated_rectangles_intersect: 9 points (corners, centre, edge midpoints) of one
+// rectangle inside the other, both ways, with the reference's rotation convention
+__device__ __forceinline__ bool has_corner_inside(double c1x, double c1y, double l1, double w1, double a1,
+                                                  double c2x, double c2y, double l2, double w2, double a2) {
+    const double hl = l1 / 2, hw = w1 / 2;
+    const double pxs[9] = {-hl, -hl, hl, hl, 0, -hl, hl, 0, 0};
+    const double pys[9] = {-hw, hw, hw, -hw, 0, 0, 0, -hw, hw};
+    double s1, c1, s2, c2;
+    m_sincos(a1, &s1, &c1);
+    m_sincos(a2, &s2, &c2);
+    for (int k = 0; k < 9; ++k) {
+        double px = c1 * pxs[k] + (-s1) * pys[k] + c1x;
+        double py = s1 * pxs[k] + c1 * pys[k] + c1y;
+        double dx = px - c2x, dy = py - c2y;
+        double rx = c2 * dx + (-s2) * dy, ry = s2 * dx + c2 * dy;
+        if (-l2 / 2 <= rx && rx <= l2 / 2 && -w2 / 2 <= ry && ry <= w2 / 2) return true;
+    }
+    return false;
+}
+
+// regulation.py:42-111: enforce_road_rules with is_conflict_possible / respect_priorities.
+// All threads of the group call this; r is the caller's vehicle.
+template <int G, bool REG>
+__device__ __forceinline__ void enforce_road_rules(const HwyNetParams& P, const GraphShared& g,
+                                                   EnvStage<G, REG>& st, int V, int i, Regs& r) {
+    const bool active = i < V;
+    // un-freeze (YIELD_DURATION = 0: every yielding vehicle is released at the next regulation tick)
+    if (active && (r.meta & HWY_META_YIELDING)) {
+        r.target_speed = g.lanes[st.lane[i]].speed_limit;
+        r.meta &= ~HWY_META_YIELDING;
+        st.ts[i] = r.target_speed;
+    }
+    if (i == 0) st.yield_mask = 0;
+    // predict_trajectory_constant_speed (vehicle/controller.py:236-253) at t = 0.25 .. 2.75 s
+    if (active) {
+        const double s0 = lane_s_of(g.lanes[st.lane[i]], r.x, r.y);
+        for (int k = 0; k < kPred; ++k) {
+            double px, py, ph;
+            position_heading_along_route(g, st, i, s0 + r.speed * (0.25 * (k + 1)), px, py, ph);
+            st.pred[i][k][0] = px;
+            st.pred[i][k][1] = py;
+            st.pred[i][k][2] = ph;
+        }
+    }
+    group_sync<G>();
+    // every pair (a < b), dealt round-robin over the group
+    const int n_pairs = V * (V - 1) / 2;
+    for (int p = i; p < n_pairs; p += G) {
+        int a = 0, rem = p;  // p -> (a, b): row a has V-1-a pairs
+        while (rem >= V - 1 - a) {
+            rem -= V - 1 - a;
+            ++a;
+        }
+        const int b = a + 1 + rem;
+        bool conflict = false;
+        for (int k = 0; k < kPred && !conflict; ++k) {
+            double p1x = st.pred[a][k][0], p1y = st.pred[a][k][1], p2x = st.pred[b][k][0], p2y = st.pred[b][k][1];
+            if (norm2(p2x - p1x, p2y - p1y) > kVehLength) continue;
+            double h1 = st.pred[a][k][2], h2 = st.pred[b][k][2];
+            conflict = has_corner_inside(p1x, p1y, 1.5 * kVehLength, 0.9 * kVehWidth, h1, p2x, p2y,
+                                         1.5 * kVehLength, 0.9 * kVehWidth, h2) ||
+                       has_corner_inside(p2x, p2y, 1.5 * kVehLength, 0.9 * kVehWidth, h2, p1x, p1y,
+                                         1.5 * kVehLength, 0.9 * kVehWidth, h1);
+        }
+        if (!conflict) continue;
+        const int pa = g.lanes[st.lane[a]].priority, pb = g.lanes[st.lane[b]].priority;
+        int y;
+        if (pa > pb)
+            y = b;
+        else if (pa < pb)
+            y = a;
+        else {  // the vehicle behind yields (front_distance_to, vehicle/objects.py:205-206)
+            double fab = dot2(st.c[a], st.s[a], st.x[b] - st.x[a], st.y[b] - st.y[a]);
+            double fba = dot2(st.c[b], st.s[b], st.x[a] - st.x[b], st.y[a] - st.y[b]);
+            y = fab > fba ? a : b;
+        }
+        if (st.kind[y] == HWY_KIND_IDM) atomicOr(&st.yield_mask, 1u << y);  // never an MDPVehicle
+    }
+    group_sync<G>();
+    if (active && ((st.yield_mask >> i) & 1u)) {
+        r.target_speed = 0.0;
+        r.meta |= HWY_META_YIELDING;
+        st.ts[i] = 0.0;
+    }
+    group_sync<G>();
+}
+
+// ------------------------------------------------------------------ one simulation substep
+// Road.act() then [RegulatedRoad rules] Road.step(dt) for one env; all threads of the group call it.
+// `ego_label` >= 0 on the first frame of a policy step: the meta-action label of the controlled vehicle.
+template <int G, bool REG>
+__device__ __forceinline__ void substep(const HwyNetParams& P, const GraphShared& g, EnvStage<G, REG>& st, int i,
+                                        Regs& r, double& act_accel, double dt, int ego_label) {
+    const int V = st.count;
+    const bool active = i < V;
+    const int kind = meta_kind(r.meta);
+    // ---- action_type.act on the first frame: MDPVehicle.act (controller.py:295-315)
+    if (ego_label >= 0 && active && i == st.ego) {
+        follow_road(g, st, i);
+        if (ego_label == 3 || ego_label == 4) {
+            int idx = speed_to_index(P, r.speed) + (ego_label == 3 ? 1 : -1);
+            idx = max(0, min(idx, P.n_target_speeds - 1));
+            st.speed_index = idx;
+            r.target_speed = P.target_speeds[idx];
+            st.ts[i] = r.target_speed;
+        } else if (ego_label == 0 || ego_label == 2) {
+            const HwyNetLane& T = g.lanes[st.tgt[i]];
+            int id = max(0, min(T.lane_id + (ego_label == 2 ? 1 : -1), T.road_count - 1));
+            int cand = T.road_first + id;
+            if (lane_reachable(g.lanes[cand], r.x, r.y)) st.tgt[i] = cand;
+        }
+    }
+    group_sync<G>();
+    // ---- Road.act (road/road.py:464-467), ordered part: follow_road + lane-change policy in list order
+    const bool crashed = (r.meta & HWY_META_CRASHED) != 0;
+    for (int v = 0; v < V; ++v) {
+        if (i == v) {
+            if (kind == HWY_KIND_IDM) {
+                if (!crashed) {  // behavior.py:102-103
+                    follow_road(g, st, v);
+                    r.timer = change_lane_policy(P, g, st, V, v, r.delta, r.timer);
+                }
+            } else {
+                follow_road(g, st, v);  // ControlledVehicle.act(None) (controller.py:98)
+            }
+        }
+        group_sync<G>();
+    }
+    // ---- parallel part: steering + acceleration
+    double sin_beta = 0.0, cos_beta = 1.0;
+    if (active) {
+        const int lane = st.lane[i], tgt = st.tgt[i];
+        if (!crashed) {
+            double xs = steering_sin_slip(g.lanes[tgt], r.x, r.y, r.heading, r.speed);
+            beta_of_controlled(xs, sin_beta, cos_beta);
+        }
+        if (kind == HWY_KIND_IDM) {
+            if (!crashed) {
+                int f, rr;
+                neighbours(g, st, V, i, lane, f, rr);
+                double acc = idm_acceleration(P, g, st, r.delta, i, f);
+                if (lane != tgt) {
+                    neighbours(g, st, V, i, tgt, f, rr);
+                    acc = fmin(acc, idm_acceleration(P, g, st, r.delta, i, f));
+                }
+                act_accel = clipd(acc, -P.acc_max, P.acc_max);
+            }
+        } else {
+            act_accel = kKpA * (r.target_speed - r.speed);
+        }
+    }
+    // ---- RegulatedRoad.step (regulation.py:36-40): rules every int(1/dt/2) substeps, before Road.step
+    if (REG) {
+        if (i == 0) st.road_steps += 1;
+        group_sync<G>();
+        if (P.regulated && st.road_steps % (int)(1 / dt / 2) == 0) enforce_road_rules(P, g, st, V, i, r);
+    }
+    // ---- Road.step: Vehicle.step (kinematics.py:130-177), IDMVehicle.step timer (behavior.py:139-148)
+    if (active) {
+        if (kind == HWY_KIND_IDM) r.timer += dt;
+        if (crashed) act_accel = -1.0 * r.speed;
+        if (r.speed > kMaxSpeed)
+            act_accel = fmin(act_accel, 1.0 * (kMaxSpeed - r.speed));
+        else if (r.speed < kMinSpeed)
+            act_accel = fmax(act_accel, 1.0 * (kMinSpeed - r.speed));
+        const double ch = st.c[i], sh = st.s[i];
+        double cs = ch * cos_beta - sh * sin_beta, sn = sh * cos_beta + ch * sin_beta;
+        r.x += (r.speed * cs) * dt;
+        r.y += (r.speed * sn) * dt;
+        if (r.meta & HWY_META_HAS_IMPACT) {
+            r.x += r.imp_x;
+            r.y += r.imp_y;
+            r.meta = (r.meta | HWY_META_CRASHED) & ~HWY_META_HAS_IMPACT;
+        }
+        r.heading += r.speed * sin_beta / (kVehLength / 2) * dt;
+        r.speed += act_accel * dt;
+    }
+    group_sync<G>();  // everyone is done reading the pre-step staging
+    if (active) publish(st, i, r);
+    group_sync<G>();
+    int nl = closest_lane_group(g, st, V, i);  // on_state_update
+    if (active) st.lane[i] = nl;
+    group_sync<G>();
+    // ---- collision sweep (road/road.py:477-481): partners in ascending order => the surviving impact is
+    // the one of the largest partner index
+    if (active) {
+        const double diag = sqrt(kVehLength * kVehLength + kVehWidth * kVehWidth);
+        for (int j = 0; j < V; ++j) {
+            if (j == i) continue;
+            int a = i < j ? i : j, b = i < j ? j : i;
+            double dist = norm2(st.x[b] - st.x[a], st.y[b] - st.y[a]);
+            if (dist > (diag + diag) / 2 + st.v[a] * dt) continue;
+            Quad pa = make_polygon(st.x[a], st.y[a], st.c[a], st.s[a]);
+            Quad pb = make_polygon(st.x[b], st.y[b], st.c[b], st.s[b]);
+            bool inter, will;
+            double trx, try_;
+            polygons_intersecting(pa, pb, st.v[a] * st.c[a] * dt, st.v[a] * st.s[a] * dt, st.v[b] * st.c[b] * dt,
+                                  st.v[b] * st.s[b] * dt, inter, will, trx, try_);
+            if (will) {
+                r.imp_x = i == a ? trx / 2 : -trx / 2;
+                r.imp_y = i == a ? try_ / 2 : -try_ / 2;
+                r.meta |= HWY_META_HAS_IMPACT;
+            }
+            if (inter) r.meta |= HWY_META_CRASHED;
+        }
+    }
+}
+
+// load one env into the group's stage (count, ego, routes, staged kinematics)
+template <int G, bool REG>
+__device__ __forceinline__ void load_env(const HwyNetParams& P, const HwyNetState& S, EnvStage<G, REG>& st, int e,
+                                         int i, Regs& r) {
+    const size_t slot = (size_t)e * S.vp + i;
+    load_regs(S, slot, r);
+    const int* src = S.route + slot * R;
+    for (int k = 0; k < R; ++k) st.route[i][k] = src[k];
+    st.route_len[i] = S.route_len[slot];
+    const int count = S.count ? S.count[e] : P.n_vehicles;
+    if (i == 0) {
+        st.count = count;
+        st.speed_index = S.speed_index[e];
+        st.road_steps = S.road_steps ? S.road_steps[e] : 0;
+    }
+    publish(st, i, r);
+    st.lane[i] = meta_lane(r.meta);
+    st.tgt[i] = meta_target(r.meta);
+    st.kind[i] = meta_kind(r.meta);
+    // the controlled vehicle: first MDPVehicle of the list
+    unsigned is_mdp = __ballot_sync(group_mask<G>(), i < count && meta_kind(r.meta) == HWY_KIND_MDP);
+    is_mdp >>= ((threadIdx.x & 31) & ~(G - 1));
+    if (i == 0) st.ego = is_mdp ? __ffs(is_mdp) - 1 : 0;
+    group_sync<G>();
+}
+
+template <int G, bool REG>
+__device__ __forceinline__ void store_env(const HwyNetState& S, EnvStage<G, REG>& st, int e, int i, int dst,
+                                          Regs& r) {
+    // dst: destination slot of this vehicle (-1: dropped)
+    if (dst >= 0) {
+        r.meta = meta_set_target(meta_set_lane(r.meta, st.lane[i]), st.tgt[i]);
+        const size_t slot = (size_t)e * S.vp + dst;
+        store_regs(S, slot, r);
+        int* d = S.route + slot * R;
+        for (int k = 0; k < R; ++k) d[k] = st.route[i][k];
+        S.route_len[slot] = st.route_len[i];
+    }
+}
+
+// ------------------------------------------------------------------ intersection population
+// envs/intersection_env.py:325-352 _spawn_vehicle, executed by ONE thread: consumes the env's numpy
+// stream (uniform; choice(range(4), size=2, replace=False) = Floyd's algorithm + tail shuffle;
+// normal; normal; uniform) and leaves the accepted vehicle in the stage's spawn record.
+template <int G, bool REG>
+__device__ __noinline__ void spawn_vehicle(const HwyNetParams& P, const HwyIntersectionSpawn& SP,
+                                           const GraphShared& g, EnvStage<G, REG>& st, Pcg64& rng,
+                                           unsigned keep_mask, double longitudinal, double position_deviation,
+                                           double speed_deviation, double spawn_probability, bool go_straight) {
+    st.sp_ok = 0;
+    if (rng.next_double() > spawn_probability) return;  // np_random.uniform()
+    int a = rng.choice(3), b = rng.choice(4);            // Floyd: j = 2, 3
+    if (b == a) b = 3;
+    int route2[2] = {a, b};
+    int j = rng.choice(2);                               // _shuffle_int(n = 2): swap [1] <-> [j]
+    int tmp = route2[1];
+    route2[1] = route2[j];
+    route2[j] = tmp;
+    const int r0 = route2[0];
+    const int r1 = go_straight ? (r0 + 2) % 4 : route2[1];
+    const int lane = SP.spawn_lane[r0];
+    const double lon = longitudinal + 5.0 + rng.normal() * position_deviation;
+    const double speed = 8.0 + rng.normal() * speed_deviation;
+    double px, py;
+    lane_position(g.lanes[lane], lon, 0.0, px, py);  // make_on_lane (vehicle/objects.py:68-90)
+    const double heading = lane_heading_at(g.lanes[lane], lon);
+    for (int v = 0; v < st.count; ++v) {
+        if (!((keep_mask >> v) & 1u)) continue;
+        if (norm2(st.x[v] - px, st.y[v] - py) < 15) return;
+    }
+    st.sp_delta = rng.uniform(3.5, 4.5);  // randomize_behavior
+    st.sp_x = px;
+    st.sp_y = py;
+    st.sp_h = heading;
+    st.sp_speed = speed;
+    int cl = 0;
+    double bd = 0;
+    for (int l = 0; l < g.n_lanes; ++l) {
+        double d = lane_distance_with_heading(g.lanes[l], px, py, heading);
+        if (l == 0 || d < bd) {
+            bd = d;
+            cl = l;
+        }
+    }
+    st.sp_lane = cl;
+    st.sp_dest = r1;
+    st.sp_ok = 1;
+}
+
+// the thread owning slot `dst` adopts the spawn record as an IDMVehicle
+template <int G, bool REG>
+__device__ __forceinline__ void adopt_spawn(const HwyNetParams& P, const HwyIntersectionSpawn& SP,
+                                            EnvStage<G, REG>& st, int i, Regs& r) {
+    r.x = st.sp_x;
+    r.y = st.sp_y;
+    r.heading = st.sp_h;
+    r.speed = st.sp_speed;
+    r.target_speed = st.sp_speed;
+    r.timer = py_mod_pos((st.sp_x + st.sp_y) * kPi, P.lane_change_delay);
+    r.delta = st.sp_delta;
+    r.imp_x = r.imp_y = 0.0;
+    r.meta = (st.sp_lane << HWY_META_LANE_SHIFT) | (st.sp_lane << HWY_META_TARGET_SHIFT) | HWY_META_CHECK_COLLISIONS |
+             (HWY_KIND_IDM << HWY_META_KIND_SHIFT) | HWY_META_PRESENT;
+    const int* rs = SP.route_table + ((size_t)st.sp_lane * 4 + st.sp_dest) * R;
+    for (int k = 0; k < R; ++k) st.route[i][k] = rs[k];
+    st.route_len[i] = SP.route_len[(size_t)st.sp_lane * 4 + st.sp_dest];
+    st.lane[i] = st.tgt[i] = st.sp_lane;
+    st.kind[i] = HWY_KIND_IDM;
+    publish(st, i, r);
+}
+
+__device__ __forceinline__ Pcg64 load_rng(const uint64_t* rng, size_t n, int e) {
+    Pcg64 g;
+    g.s_hi = rng[0 * n + e];
+    g.s_lo = rng[1 * n + e];
+    g.i_hi = rng[2 * n + e];
+    g.i_lo = rng[3 * n + e];
+    uint64_t w4 = rng[4 * n + e];
+    g.has32 = (uint32_t)(w4 >> 32);
+    g.u32 = (uint32_t)w4;
+    return g;
+}
+__device__ __forceinline__ void store_rng(uint64_t* rng, size_t n, int e, const Pcg64& g) {
+    rng[0 * n + e] = g.s_hi;
+    rng[1 * n + e] = g.s_lo;
+    rng[4 * n + e] = ((uint64_t)g.has32 << 32) | g.u32;
+}
+
 // ------------------------------------------------------------------ the step kernel
+template <int G, bool REG>
 __global__ void __launch_bounds__(kBlockThreads)
 network_step_kernel(const HwyNetParams P, const HwyNetGraph* __restrict__ graph, const HwyNetState S,
-                    const int32_t* __restrict__ action, float* __restrict__ obs,
+                    const HwyIntersectionSpawn SP, const int32_t* __restrict__ action, float* __restrict__ obs,
                     double* __restrict__ reward, uint8_t* __restrict__ terminated,
                     uint8_t* __restrict__ truncated, double* __restrict__ info_speed,
                     uint8_t* __restrict__ info_crashed) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     GraphShared& g = *reinterpret_cast<GraphShared*>(smem_raw);
-    EnvStage* stages = reinterpret_cast<EnvStage*>(smem_raw + ((sizeof(GraphShared) + 15) & ~size_t(15)));
+    EnvStage<G, REG>* stages =
+        reinterpret_cast<EnvStage<G, REG>*>(smem_raw + ((sizeof(GraphShared) + 15) & ~size_t(15)));
     stage_graph(g, graph);
 
+    constexpr int kEnvs = kBlockThreads / G;
     const int sub = threadIdx.x / G, i = threadIdx.x % G;
-    const int env = blockIdx.x * kBlockEnvs + sub;
+    const int env = blockIdx.x * kEnvs + sub;
     const bool env_ok = env < S.n_envs;
     const int e = env_ok ? env : S.n_envs - 1;
-    EnvStage& st = stages[sub];
-    const int V = P.n_vehicles;
-    const bool active = i < V;
-    const size_t slot = (size_t)e * S.vp + i;
+    EnvStage<G, REG>& st = stages[sub];
 
     Regs r;
-    load_regs(S, slot, r);
-    const int kind = meta_kind(r.meta);
-    int speed_index = i == 0 ? S.speed_index[e] : 0;
-    {
-        const int* src = S.route + slot * R;
-        for (int k = 0; k < R; ++k) st.route[i][k] = src[k];
-        st.route_len[i] = S.route_len[slot];
-    }
+    load_env(P, S, st, e, i, r);
     const int frames = P.simulation_frequency / P.policy_frequency;
     const double dt = 1.0 / P.simulation_frequency;
     const int act = action[e];
-    double sin_beta = 0.0, cos_beta = 1.0, act_accel = 0.0;
+    // action label: DiscreteMetaAction.ACTIONS_ALL, or ACTIONS_LONGI {0 SLOWER, 1 IDLE, 2 FASTER} (action.py:204-206)
+    const int label = P.action_mode == 1 ? (act == 0 ? 4 : (act == 2 ? 3 : 1)) : act;
+    double act_accel = 0.0;
 
-    publish(st, i, r);
-    st.lane[i] = meta_lane(r.meta);
-    st.tgt[i] = meta_target(r.meta);
-    group_sync();
+    for (int frame = 0; frame < frames; ++frame) substep(P, g, st, i, r, act_accel, dt, frame == 0 ? label : -1);
+    group_sync<G>();
 
-    for (int frame = 0; frame < frames; ++frame) {
-        // ---- Road.act (road/road.py:464-467), ordered part: follow_road + lane-change policy,
-        // one vehicle at a time in list order (later vehicles read earlier vehicles' new targets).
-        if (frame == 0 && i == 0) {
-            // action_type.act: MDPVehicle.act (controller.py:295-315) -> ControlledVehicle.act
-            follow_road(g, st, 0);
-            if (act == 3 || act == 4) {
-                int idx = speed_to_index(P, r.speed) + (act == 3 ? 1 : -1);
-                idx = max(0, min(idx, P.n_target_speeds - 1));
-                speed_index = idx;
-                r.target_speed = P.target_speeds[idx];
-                st.ts[0] = r.target_speed;
-            } else if (act == 0 || act == 2) {
-                const HwyNetLane& T = g.lanes[st.tgt[0]];
-                int id = max(0, min(T.lane_id + (act == 2 ? 1 : -1), T.road_count - 1));
-                int cand = T.road_first + id;
-                if (lane_reachable(g.lanes[cand], r.x, r.y)) st.tgt[0] = cand;
-            }
-        }
-        group_sync();
-        const bool crashed = (r.meta & HWY_META_CRASHED) != 0;
-        for (int v = 0; v < V; ++v) {
-            if (i == v) {
-                if (kind == HWY_KIND_IDM) {
-                    if (!crashed) {  // behavior.py:102-103
-                        follow_road(g, st, v);
-                        r.timer = change_lane_policy(P, g, st, V, v, r.delta, r.timer);
-                    }
-                } else {
-                    follow_road(g, st, v);  // ControlledVehicle.act(None) (controller.py:98)
-                }
-            }
-            group_sync();
-        }
-        // ---- parallel part: steering + acceleration, then Vehicle.step
-        if (active) {
-            const int lane = st.lane[i], tgt = st.tgt[i];
-            sin_beta = 0.0;
-            cos_beta = 1.0;
-            if (!crashed) {
-                double xs = steering_sin_slip(g.lanes[tgt], r.x, r.y, r.heading, r.speed);
-                beta_of_controlled(xs, sin_beta, cos_beta);
-            }
-            if (kind == HWY_KIND_IDM) {
-                if (!crashed) {
-                    int f, rr;
-                    neighbours(g, st, V, i, lane, f, rr);
-                    double acc = idm_acceleration(P, g, st, r.delta, i, f);
-                    if (lane != tgt) {
-                        neighbours(g, st, V, i, tgt, f, rr);
-                        acc = fmin(acc, idm_acceleration(P, g, st, r.delta, i, f));
-                    }
-                    act_accel = clipd(acc, -P.acc_max, P.acc_max);
-                }
-            } else {
-                act_accel = kKpA * (r.target_speed - r.speed);
-            }
-            // Vehicle.step (kinematics.py:130-177), IDMVehicle.step timer (behavior.py:139-148)
-            if (kind == HWY_KIND_IDM) r.timer += dt;
-            if (crashed) act_accel = -1.0 * r.speed;
-            if (r.speed > kMaxSpeed)
-                act_accel = fmin(act_accel, 1.0 * (kMaxSpeed - r.speed));
-            else if (r.speed < kMinSpeed)
-                act_accel = fmax(act_accel, 1.0 * (kMinSpeed - r.speed));
-            const double ch = st.c[i], sh = st.s[i];
-            double cs = ch * cos_beta - sh * sin_beta, sn = sh * cos_beta + ch * sin_beta;
-            r.x += (r.speed * cs) * dt;
-            r.y += (r.speed * sn) * dt;
-            if (r.meta & HWY_META_HAS_IMPACT) {
-                r.x += r.imp_x;
-                r.y += r.imp_y;
-                r.meta = (r.meta | HWY_META_CRASHED) & ~HWY_META_HAS_IMPACT;
-            }
-            r.heading += r.speed * sin_beta / (kVehLength / 2) * dt;
-            r.speed += act_accel * dt;
-        }
-        group_sync();  // everyone is done reading the pre-step staging
-        if (active) publish(st, i, r);
-        group_sync();
-        // ---- on_state_update: closest lane of every vehicle, cooperatively
-        int nl = closest_lane_group(g, st, V, i);
-        if (active) st.lane[i] = nl;
-        group_sync();
-        // ---- Road.step collision sweep (road/road.py:477-481): partners in ascending order, so
-        // the surviving impact is the one of the largest partner index
-        if (active) {
-            const double diag = sqrt(kVehLength * kVehLength + kVehWidth * kVehWidth);
-            for (int j = 0; j < V; ++j) {
-                if (j == i) continue;
-                int a = i < j ? i : j, b = i < j ? j : i;
-                double dist = norm2(st.x[b] - st.x[a], st.y[b] - st.y[a]);
-                if (dist > (diag + diag) / 2 + st.v[a] * dt) continue;
-                Quad pa = make_polygon(st.x[a], st.y[a], st.c[a], st.s[a]);
-                Quad pb = make_polygon(st.x[b], st.y[b], st.c[b], st.s[b]);
-                bool inter, will;
-                double trx, try_;
-                polygons_intersecting(pa, pb, st.v[a] * st.c[a] * dt, st.v[a] * st.s[a] * dt,
-                                      st.v[b] * st.c[b] * dt, st.v[b] * st.s[b] * dt, inter, will, trx, try_);
-                if (will) {
-                    r.imp_x = i == a ? trx / 2 : -trx / 2;
-                    r.imp_y = i == a ? try_ / 2 : -try_ / 2;
-                    r.meta |= HWY_META_HAS_IMPACT;
-                }
-                if (inter) r.meta |= HWY_META_CRASHED;
-            }
-        }
-    }
-
-    // ---- epilogue
-    if (active) {
-        r.meta = meta_set_target(meta_set_lane(r.meta, st.lane[i]), st.tgt[i]);
-        if (env_ok) {
-            store_regs(S, slot, r);
-            int* dst = S.route + slot * R;
-            for (int k = 0; k < R; ++k) dst[k] = st.route[i][k];
-            S.route_len[slot] = st.route_len[i];
-        }
-    }
+    // ---- epilogue: observation, reward, termination (before any population change)
+    const int V = st.count, ego = st.ego;
     float* obs_env = obs + (size_t)e * obs_size(P);
-    // the ego's thread owns speed_index: broadcast it to the group for the observation crop
-    speed_index = __shfl_sync(group_mask(), speed_index, 0, G);
-    if (P.obs_type == HWY_OBS_TTC)
-        observe_ttc(P, g, st, V, i, speed_index, obs_env);
-    else
-        observe_kinematics(P, g, st, V, i, obs_env);
-    if (i == 0 && env_ok) {
-        // envs/roundabout_env.py:44-71
-        const HwyNetLane& L = g.lanes[st.lane[0]];
+    observe_any(P, g, st, V, i, obs_env);
+    if (i == ego && i < V && env_ok) {
+        const HwyNetLane& L = g.lanes[st.lane[i]];
         double es, elat;
         lane_local(L, r.x, r.y, es, elat);
-        bool on_road = lane_on(L, es, elat, 0.0);
-        bool is_crashed = (r.meta & HWY_META_CRASHED) != 0;
+        const bool on_road = lane_on(L, es, elat, 0.0);
+        const bool is_crashed = (r.meta & HWY_META_CRASHED) != 0;
         double rew = 0.0;
-        rew = rew + P.collision_reward * (is_crashed ? 1.0 : 0.0);
-        rew = rew + P.high_speed_reward * ((double)speed_index / (double)(3 - 1));
-        rew = rew + P.lane_change_reward * ((act == 0 || act == 2) ? 1.0 : 0.0);
-        rew = rew + 0.0 * (on_road ? 1.0 : 0.0);
-        if (P.normalize_reward) rew = lmap(rew, P.collision_reward, P.high_speed_reward, 0.0, 1.0);
-        rew *= on_road ? 1.0 : 0.0;
+        bool term;
+        if (P.reward_type == 1) {
+            // envs/intersection_env.py:79-117,368-373 (one controlled vehicle)
+            const bool arrived = L.exit_lane && es >= 25;
+            double scaled_speed = lmap(r.speed, P.reward_speed_lo, P.reward_speed_hi, 0.0, 1.0);
+            rew = rew + P.collision_reward * (is_crashed ? 1.0 : 0.0);
+            rew = rew + P.high_speed_reward * clipd(scaled_speed, 0.0, 1.0);
+            rew = rew + P.arrived_reward * (arrived ? 1.0 : 0.0);
+            rew = rew + 0.0 * (on_road ? 1.0 : 0.0);
+            if (arrived) rew = P.arrived_reward;
+            rew *= on_road ? 1.0 : 0.0;
+            if (P.normalize_reward) rew = lmap(rew, P.collision_reward, P.arrived_reward, 0.0, 1.0);
+            term = is_crashed || arrived || (P.offroad_terminal && !on_road);
+        } else {
+            // envs/roundabout_env.py:44-71
+            rew = rew + P.collision_reward * (is_crashed ? 1.0 : 0.0);
+            rew = rew + P.high_speed_reward * ((double)st.speed_index / (double)(3 - 1));
+            rew = rew + P.lane_change_reward * ((act == 0 || act == 2) ? 1.0 : 0.0);
+            rew = rew + 0.0 * (on_road ? 1.0 : 0.0);
+            if (P.normalize_reward) rew = lmap(rew, P.collision_reward, P.high_speed_reward, 0.0, 1.0);
+            rew *= on_road ? 1.0 : 0.0;
+            term = is_crashed;
+        }
         double t = S.time[e] + 1.0 / P.policy_frequency;
         S.time[e] = t;
-        S.speed_index[e] = speed_index;
+        S.speed_index[e] = st.speed_index;
         reward[e] = rew;
-        terminated[e] = (uint8_t)is_crashed;
+        terminated[e] = (uint8_t)term;
         truncated[e] = (uint8_t)(t >= P.duration);
         if (info_speed) info_speed[e] = r.speed;
         if (info_crashed) info_crashed[e] = (uint8_t)is_crashed;
     }
+    group_sync<G>();
+
+    // ---- IntersectionEnv.step (intersection_env.py:136-140): _clear_vehicles, then _spawn_vehicle(p)
+    int dst = i < V ? i : -1;
+    if (REG && P.dynamic_population) {
+        bool keep = i < V;
+        if (keep && meta_kind(r.meta) != HWY_KIND_MDP) {  // _clear_vehicles :354-366
+            const HwyNetLane& L = g.lanes[st.lane[i]];
+            if (L.exit_lane && lane_s_of(L, r.x, r.y) >= L.length - 4 * kVehLength) keep = false;
+        }
+        unsigned keep_mask = __ballot_sync(group_mask<G>(), keep) >> ((threadIdx.x & 31) & ~(G - 1));
+        const int n_keep = __popc(keep_mask);
+        dst = keep ? __popc(keep_mask & ((1u << i) - 1u)) : -1;
+        if (i == 0) {
+            Pcg64 rng = load_rng(S.rng, (size_t)S.n_envs, e);
+            spawn_vehicle(P, SP, g, st, rng, keep_mask, 0.0, 1.0, 1.0, SP.spawn_probability, false);
+            if (n_keep >= G) st.sp_ok = 0;  // slot capacity (never reached: the reference peaks at ~15)
+            if (env_ok) store_rng(S.rng, (size_t)S.n_envs, e, rng);
+        }
+        group_sync<G>();
+        if (env_ok) store_env(S, st, e, i, dst, r);
+        group_sync<G>();
+        if (st.sp_ok && i == n_keep) {
+            adopt_spawn(P, SP, st, i, r);
+            if (env_ok) store_env(S, st, e, i, i, r);
+        }
+        if (i == 0 && env_ok) {
+            S.count[e] = n_keep + st.sp_ok;
+            S.road_steps[e] = st.road_steps;
+        }
+    } else {
+        if (env_ok) store_env(S, st, e, i, dst, r);
+        if (REG && i == 0 && env_ok && S.road_steps) S.road_steps[e] = st.road_steps;
+    }
 }
 
+template <int G, bool REG>
 __global__ void __launch_bounds__(kBlockThreads)
 network_observe_kernel(const HwyNetParams P, const HwyNetGraph* __restrict__ graph, const HwyNetState S,
                        const uint8_t* __restrict__ mask_a, const uint8_t* __restrict__ mask_b,
                        float* __restrict__ obs) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     GraphShared& g = *reinterpret_cast<GraphShared*>(smem_raw);
-    EnvStage* stages = reinterpret_cast<EnvStage*>(smem_raw + ((sizeof(GraphShared) + 15) & ~size_t(15)));
+    EnvStage<G, REG>* stages =
+        reinterpret_cast<EnvStage<G, REG>*>(smem_raw + ((sizeof(GraphShared) + 15) & ~size_t(15)));
     stage_graph(g, graph);
+    constexpr int kEnvs = kBlockThreads / G;
     const int sub = threadIdx.x / G, i = threadIdx.x % G;
-    const int env = blockIdx.x * kBlockEnvs + sub;
+    const int env = blockIdx.x * kEnvs + sub;
     const bool env_ok = env < S.n_envs;
     const int e = env_ok ? env : S.n_envs - 1;
-    EnvStage& st = stages[sub];
-    const size_t slot = (size_t)e * S.vp + i;
+    EnvStage<G, REG>& st = stages[sub];
     Regs r;
-    load_regs(S, slot, r);
-    {
-        const int* src = S.route + slot * R;
-        for (int k = 0; k < R; ++k) st.route[i][k] = src[k];
-        st.route_len[i] = S.route_len[slot];
-    }
-    publish(st, i, r);
-    st.lane[i] = meta_lane(r.meta);
-    st.tgt[i] = meta_target(r.meta);
-    group_sync();
+    load_env(P, S, st, e, i, r);
     const bool selected = (!mask_a && !mask_b) || (mask_a && mask_a[e]) || (mask_b && mask_b[e]);
-    float* obs_env = obs + (size_t)e * obs_size(P);
-    const int speed_index = S.speed_index[e];
     if (!selected) return;  // whole group leaves together (selection is per env)
-    if (P.obs_type == HWY_OBS_TTC)
-        observe_ttc(P, g, st, P.n_vehicles, i, speed_index, obs_env);
-    else
-        observe_kinematics(P, g, st, P.n_vehicles, i, obs_env);
+    observe_any(P, g, st, st.count, i, obs + (size_t)e * obs_size(P));
+}
+
+// Road.act + Road.step `n_substeps` times with no ego action (IntersectionEnv._make_vehicles warm-up)
+template <int G, bool REG>
+__global__ void __launch_bounds__(kBlockThreads)
+network_substeps_kernel(const HwyNetParams P, const HwyNetGraph* __restrict__ graph, const HwyNetState S,
+                        const uint8_t* __restrict__ mask, int n_substeps) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    GraphShared& g = *reinterpret_cast<GraphShared*>(smem_raw);
+    EnvStage<G, REG>* stages =
+        reinterpret_cast<EnvStage<G, REG>*>(smem_raw + ((sizeof(GraphShared) + 15) & ~size_t(15)));
+    stage_graph(g, graph);
+    constexpr int kEnvs = kBlockThreads / G;
+    const int sub = threadIdx.x / G, i = threadIdx.x % G;
+    const int env = blockIdx.x * kEnvs + sub;
+    if (env >= S.n_envs) return;
+    if (mask && !mask[env]) return;
+    EnvStage<G, REG>& st = stages[sub];
+    Regs r;
+    load_env(P, S, st, env, i, r);
+    const double dt = 1.0 / P.simulation_frequency;
+    double act_accel = 0.0;
+    for (int k = 0; k < n_substeps; ++k) substep(P, g, st, i, r, act_accel, dt, -1);
+    group_sync<G>();
+    store_env(S, st, env, i, i < st.count ? i : -1, r);
+    if (i == 0 && S.road_steps) S.road_steps[env] = st.road_steps;
 }
 
 // RoundaboutEnv._make_vehicles (envs/roundabout_env.py:317-391), one env per thread (the draws
@@ -905,19 +1320,22 @@ using hwy_abi::fail;
 
 int validate_net(const HwyNetParams* p, const HwyNetGraph* graph, const HwyNetState* s) {
     if (!p || !graph || !s) return fail("%s", "null params/graph/state");
-    if (p->n_vehicles < 1 || p->n_vehicles > HWY_NET_GROUP) return fail("%s", "n_vehicles out of range for the network kernels");
+    if (s->vp != HWY_NET_GROUP && s->vp != HWY_NET_GROUP_LARGE) return fail("%s", "slot stride must be 8 or 32");
+    if (p->n_vehicles < 1 || p->n_vehicles > s->vp) return fail("%s", "n_vehicles out of range for the network kernels");
     if (p->n_target_speeds < 1 || p->n_target_speeds > 3) return fail("%s", "network kernels support up to 3 target speeds");
-    if (p->obs_type != HWY_OBS_KINEMATICS && p->obs_type != HWY_OBS_TTC) return fail("%s", "unknown obs_type");
+    if (p->obs_type != HWY_OBS_KINEMATICS && p->obs_type != HWY_OBS_TTC && p->obs_type != HWY_OBS_OCCUPANCY)
+        return fail("%s", "unknown obs_type");
     if (p->obs_type == HWY_OBS_TTC && (p->ttc_horizon * p->policy_frequency < 1 || p->ttc_horizon * p->policy_frequency > 12))
         return fail("%s", "ttc horizon out of range");
-    if (p->obs_type == HWY_OBS_KINEMATICS && (p->obs_vehicles_count < 1 || p->obs_vehicles_count > HWY_MAX_OBS_VEHICLES))
+    if (p->obs_type == HWY_OBS_KINEMATICS && (p->obs_vehicles_count < 1 || p->obs_vehicles_count > 32))
         return fail("%s", "obs_vehicles_count out of range");
     if (p->simulation_frequency < 1 || p->policy_frequency < 1 || p->simulation_frequency < p->policy_frequency)
         return fail("%s", "bad simulation/policy frequency");
-    if (s->n_envs < 1 || s->vp != HWY_NET_GROUP) return fail("%s", "bad n_envs / slot stride");
+    if (s->n_envs < 1) return fail("%s", "n_envs < 1");
     if (!s->pos || !s->hs || !s->tt || !s->imp || !s->delta || !s->meta || !s->route || !s->route_len ||
         !s->speed_index || !s->time)
         return fail("%s", "null state pointer");
+    if (s->vp == HWY_NET_GROUP_LARGE && (!s->count || !s->road_steps)) return fail("%s", "count / road_steps required");
     int dev_count = 0;
     if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count < 1) {
         cudaGetLastError();
@@ -926,14 +1344,45 @@ int validate_net(const HwyNetParams* p, const HwyNetGraph* graph, const HwyNetSt
     return 0;
 }
 
+template <int G, bool REG>
 size_t net_smem_bytes() {
-    return ((sizeof(hwynet::GraphShared) + 15) & ~size_t(15)) + hwynet::kBlockEnvs * sizeof(hwynet::EnvStage);
+    return ((sizeof(hwynet::GraphShared) + 15) & ~size_t(15)) +
+           (hwynet::kBlockThreads / G) * sizeof(hwynet::EnvStage<G, REG>);
 }
 template <typename K>
-int configure_smem(K kernel) {
-    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)net_smem_bytes());
+int configure_smem(K kernel, size_t bytes) {
+    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (err != cudaSuccess) return fail("cudaFuncSetAttribute: %s", cudaGetErrorString(err));
     return 0;
+}
+int blocks_for(int n_envs, int g) {
+    int per = hwynet::kBlockThreads / g;
+    return (n_envs + per - 1) / per;
+}
+
+template <int G, bool REG>
+int launch_step(const HwyNetParams* p, const HwyNetGraph* graph, const HwyIntersectionSpawn& sp, const HwyNetState* s,
+                const int32_t* action, float* obs, double* reward, uint8_t* terminated, uint8_t* truncated,
+                double* info_speed, uint8_t* info_crashed, cudaStream_t st) {
+    const size_t smem = net_smem_bytes<G, REG>();
+    if (configure_smem(hwynet::network_step_kernel<G, REG>, smem)) return 1;
+    hwynet::network_step_kernel<G, REG><<<blocks_for(s->n_envs, G), hwynet::kBlockThreads, smem, st>>>(
+        *p, graph, *s, sp, action, obs, reward, terminated, truncated, info_speed, info_crashed);
+    return check_launch("network_step_kernel");
+}
+template <int G, bool REG>
+int launch_observe(const HwyNetParams* p, const HwyNetGraph* graph, const HwyNetState* s, const uint8_t* mask_a,
+                   const uint8_t* mask_b, float* obs, cudaStream_t st) {
+    const size_t smem = net_smem_bytes<G, REG>();
+    if (configure_smem(hwynet::network_observe_kernel<G, REG>, smem)) return 1;
+    hwynet::network_observe_kernel<G, REG><<<blocks_for(s->n_envs, G), hwynet::kBlockThreads, smem, st>>>(
+        *p, graph, *s, mask_a, mask_b, obs);
+    return check_launch("network_observe_kernel");
+}
+int observe_dispatch(const HwyNetParams* p, const HwyNetGraph* graph, const HwyNetState* s, const uint8_t* mask_a,
+                     const uint8_t* mask_b, float* obs, cudaStream_t st) {
+    if (s->vp == HWY_NET_GROUP) return launch_observe<HWY_NET_GROUP, false>(p, graph, s, mask_a, mask_b, obs, st);
+    return launch_observe<HWY_NET_GROUP_LARGE, true>(p, graph, s, mask_a, mask_b, obs, st);
 }
 }  // namespace
 
@@ -941,8 +1390,9 @@ extern "C" {
 
 int hwy_network_obs_size(const HwyNetParams* p) {
     if (!p) return 0;
+    if (p->obs_type == HWY_OBS_OCCUPANCY) return 4 * 11 * 11;
     if (p->obs_type == HWY_OBS_TTC) return 9 * (int)(p->ttc_horizon / (1.0 / p->policy_frequency));
-    return p->obs_vehicles_count * 5;
+    return p->obs_vehicles_count * (p->obs_features == 7 ? 7 : 5);
 }
 
 int hwy_network_step(const HwyNetParams* p, const HwyNetGraph* graph, const HwyNetState* s,
@@ -950,22 +1400,51 @@ int hwy_network_step(const HwyNetParams* p, const HwyNetGraph* graph, const HwyN
                      uint8_t* truncated, double* info_speed, uint8_t* info_crashed, void* stream) {
     if (validate_net(p, graph, s)) return 1;
     if (!action || !obs || !reward || !terminated || !truncated) return fail("%s", "null pointer");
-    if (configure_smem(hwynet::network_step_kernel)) return 1;
-    int blocks = (s->n_envs + hwynet::kBlockEnvs - 1) / hwynet::kBlockEnvs;
-    hwynet::network_step_kernel<<<blocks, hwynet::kBlockThreads, net_smem_bytes(), (cudaStream_t)stream>>>(
-        *p, graph, *s, action, obs, reward, terminated, truncated, info_speed, info_crashed);
-    return check_launch("network_step_kernel");
+    if (s->vp != HWY_NET_GROUP) return fail("%s", "hwy_network_step expects slot stride 8 (use hwy_intersection_step)");
+    HwyIntersectionSpawn none = {};
+    return launch_step<HWY_NET_GROUP, false>(p, graph, none, s, action, obs, reward, terminated, truncated,
+                                             info_speed, info_crashed, (cudaStream_t)stream);
+}
+
+int hwy_intersection_step(const HwyNetParams* p, const HwyNetGraph* graph, const HwyIntersectionSpawn* spawn,
+                          const HwyNetState* s, const int32_t* action, float* obs, double* reward,
+                          uint8_t* terminated, uint8_t* truncated, double* info_speed, uint8_t* info_crashed,
+                          void* stream) {
+    if (validate_net(p, graph, s)) return 1;
+    if (!action || !obs || !reward || !terminated || !truncated) return fail("%s", "null pointer");
+    if (s->vp != HWY_NET_GROUP_LARGE) return fail("%s", "hwy_intersection_step expects slot stride 32");
+    if (p->dynamic_population && (!spawn || !spawn->route_table || !spawn->route_len || !s->rng))
+        return fail("%s", "dynamic population needs the spawn tables and the rng words");
+    HwyIntersectionSpawn none = {};
+    return launch_step<HWY_NET_GROUP_LARGE, true>(p, graph, spawn ? *spawn : none, s, action, obs, reward, terminated,
+                                                  truncated, info_speed, info_crashed, (cudaStream_t)stream);
+}
+
+int hwy_network_substeps(const HwyNetParams* p, const HwyNetGraph* graph, const HwyNetState* s, const uint8_t* mask,
+                         int n_substeps, void* stream) {
+    if (validate_net(p, graph, s)) return 1;
+    if (n_substeps < 0) return fail("%s", "n_substeps < 0");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (s->vp == HWY_NET_GROUP) {
+        const size_t smem = net_smem_bytes<HWY_NET_GROUP, false>();
+        if (configure_smem(hwynet::network_substeps_kernel<HWY_NET_GROUP, false>, smem)) return 1;
+        hwynet::network_substeps_kernel<HWY_NET_GROUP, false>
+            <<<blocks_for(s->n_envs, HWY_NET_GROUP), hwynet::kBlockThreads, smem, st>>>(*p, graph, *s, mask, n_substeps);
+    } else {
+        const size_t smem = net_smem_bytes<HWY_NET_GROUP_LARGE, true>();
+        if (configure_smem(hwynet::network_substeps_kernel<HWY_NET_GROUP_LARGE, true>, smem)) return 1;
+        hwynet::network_substeps_kernel<HWY_NET_GROUP_LARGE, true>
+            <<<blocks_for(s->n_envs, HWY_NET_GROUP_LARGE), hwynet::kBlockThreads, smem, st>>>(*p, graph, *s, mask,
+                                                                                             n_substeps);
+    }
+    return check_launch("network_substeps_kernel");
 }
 
 int hwy_network_observe(const HwyNetParams* p, const HwyNetGraph* graph, const HwyNetState* s, float* obs,
                         void* stream) {
     if (validate_net(p, graph, s)) return 1;
     if (!obs) return fail("%s", "obs is null");
-    if (configure_smem(hwynet::network_observe_kernel)) return 1;
-    int blocks = (s->n_envs + hwynet::kBlockEnvs - 1) / hwynet::kBlockEnvs;
-    hwynet::network_observe_kernel<<<blocks, hwynet::kBlockThreads, net_smem_bytes(), (cudaStream_t)stream>>>(
-        *p, graph, *s, nullptr, nullptr, obs);
-    return check_launch("network_observe_kernel");
+    return observe_dispatch(p, graph, s, nullptr, nullptr, obs, (cudaStream_t)stream);
 }
 
 int hwy_roundabout_reset(const HwyNetParams* p, const HwyNetGraph* graph, const HwyRoundaboutSpawn* spawn,
@@ -973,17 +1452,11 @@ int hwy_roundabout_reset(const HwyNetParams* p, const HwyNetGraph* graph, const 
                          float* obs, void* stream) {
     if (validate_net(p, graph, s)) return 1;
     if (!spawn || !rng || !spawn->route_table || !spawn->route_len) return fail("%s", "null spawn / rng pointer");
-    if (p->n_vehicles != 5) return fail("%s", "roundabout spawn places exactly 5 vehicles");
+    if (p->n_vehicles != 5 || s->vp != HWY_NET_GROUP) return fail("%s", "roundabout spawn places exactly 5 vehicles in 8 slots");
     cudaStream_t st = (cudaStream_t)stream;
     hwynet::roundabout_reset_kernel<<<(s->n_envs + 127) / 128, 128, 0, st>>>(*p, graph, *spawn, *s, rng, mask_a, mask_b);
     if (check_launch("roundabout_reset_kernel")) return 1;
-    if (obs) {
-        if (configure_smem(hwynet::network_observe_kernel)) return 1;
-        int blocks = (s->n_envs + hwynet::kBlockEnvs - 1) / hwynet::kBlockEnvs;
-        hwynet::network_observe_kernel<<<blocks, hwynet::kBlockThreads, net_smem_bytes(), st>>>(
-            *p, graph, *s, mask_a, mask_b, obs);
-        return check_launch("network_observe_kernel");
-    }
+    if (obs) return observe_dispatch(p, graph, s, mask_a, mask_b, obs, st);
     return 0;
 }
 

@@ -74,7 +74,9 @@ class NetworkTable:
                 first = len(self.lanes)
                 for lid, lane in enumerate(lanes):
                     lane = dict(lane, from_node=self.node_id[f], to_node=self.node_id[t], lane_id=lid,
-                                road_first=first, road_count=len(lanes))
+                                road_first=first, road_count=len(lanes),
+                                # intersection_env.py:354-373 tests node NAMES: ("il" in from) and ("o" in to)
+                                exit_lane=int("il" in f and "o" in t))
                     self.index[(f, t, lid)] = len(self.lanes)
                     self.lanes.append(lane)
         if len(self.lanes) > N.HWY_NET_MAX_LANES or len(self.node_id) > N.HWY_NET_MAX_NODES:

@@ -163,14 +163,18 @@ int hwy_highway_autoreset(const HwyHighwayParams *p, const HwyHighwayState *s,
 #define HWY_NET_MAX_NODES 64
 #define HWY_NET_MAX_SUCC 6
 #define HWY_NET_MAX_ROUTE 16
-#define HWY_NET_GROUP 8 /* vehicle slots per env (threads per env) */
+#define HWY_NET_GROUP 8        /* vehicle slots per env (threads per env): roundabout-v0 */
+#define HWY_NET_GROUP_LARGE 32 /* intersection-v0 (dynamic population, at most 32 vehicles) */
 
 #define HWY_LANE_STRAIGHT 0
 #define HWY_LANE_SINE 1
 #define HWY_LANE_CIRCULAR 2
 
 #define HWY_OBS_KINEMATICS 0
+#define HWY_OBS_OCCUPANCY 1 /* envs/common/observation.py:279-499, default 4 x 11 x 11 grid */
 #define HWY_OBS_TTC 2
+
+#define HWY_META_YIELDING (1 << 22) /* RegulatedRoad: vehicle.is_yielding (road/regulation.py:42-83) */
 
 /* One lane of RoadNetwork.graph[from][to][lane_id]; table order = graph enumeration order
  * (road/road.py:65-71: from-node insertion order, to-node insertion order, lane id). */
@@ -178,6 +182,7 @@ typedef struct HwyNetLane {
     int32_t type, from_node, to_node, lane_id;
     int32_t road_first, road_count; /* table index of lane 0 of this road; lanes on the road */
     int32_t forbidden, priority;
+    int32_t exit_lane, _pad; /* intersection: "il" in the from-node and "o" in the to-node name (intersection_env.py:354-373) */
     double width, speed_limit, length;
     double sx, sy, ex, ey, dx, dy, lx, ly, heading;            /* StraightLane / SineLane base */
     double amplitude, pulsation, phase;                         /* SineLane */
@@ -207,6 +212,14 @@ typedef struct HwyNetParams {
     double acc_max, comfort_acc_max, comfort_acc_min, distance_wanted, time_wanted;
     double politeness, lane_change_min_acc_gain, lane_change_max_braking_imposed, lane_change_delay;
     double perception_distance;
+    /* intersection-v0 (envs/intersection_env.py) */
+    int32_t regulated;          /* RegulatedRoad (road/regulation.py:12-111) */
+    int32_t action_mode;        /* 0: LANE_LEFT/IDLE/LANE_RIGHT/FASTER/SLOWER; 1: SLOWER/IDLE/FASTER (action.py:204-206) */
+    int32_t reward_type;        /* 0 roundabout_env.py:44-71, 1 intersection_env.py:79-117 */
+    int32_t obs_features;       /* Kinematics columns: 5, or 7 with cos_h, sin_h */
+    int32_t offroad_terminal;
+    int32_t dynamic_population; /* per-step _clear_vehicles / _spawn_vehicle (intersection_env.py:136-140) */
+    double arrived_reward, reward_speed_lo, reward_speed_hi;
 } HwyNetParams;
 
 /* route entry: from_node | to_node << 8 | (lane_id + 1) << 16  (lane_id + 1 == 0: None) */
@@ -220,7 +233,18 @@ typedef struct HwyNetState {
     int32_t *route_len;          /* [n_envs*vp] */
     int32_t *speed_index;        /* [n_envs] */
     double *time;                /* [n_envs] */
+    int32_t *count;              /* [n_envs] vehicles currently on the road; NULL: always n_vehicles */
+    int32_t *road_steps;         /* [n_envs] RegulatedRoad.steps; NULL when not regulated */
+    uint64_t *rng;               /* [5*n_envs] numpy PCG64 stream (layout as HwyHighwayState.rng); NULL if unused */
 } HwyNetState;
+
+/* IntersectionEnv._spawn_vehicle constants (envs/intersection_env.py:325-352). */
+typedef struct HwyIntersectionSpawn {
+    int32_t spawn_lane[4];      /* table index of ("o"+k, "ir"+k, 0) */
+    double spawn_probability;   /* config["spawn_probability"] */
+    const int32_t *route_table; /* DEVICE [n_lanes][4][HWY_NET_MAX_ROUTE]: plan_route_to(lane, "o"+k) */
+    const int32_t *route_len;   /* DEVICE [n_lanes][4] */
+} HwyIntersectionSpawn;
 
 /* observation size in floats: Kinematics K*5, TimeToCollision 3*3*(horizon*policy_frequency) */
 int hwy_network_obs_size(const HwyNetParams *p);
@@ -230,6 +254,19 @@ int hwy_network_obs_size(const HwyNetParams *p);
 int hwy_network_step(const HwyNetParams *p, const HwyNetGraph *graph, const HwyNetState *s,
                      const int32_t *action, float *obs, double *reward, uint8_t *terminated,
                      uint8_t *truncated, double *info_speed, uint8_t *info_crashed, void *stream);
+
+/* Same for intersection-v0 (s->vp == HWY_NET_GROUP_LARGE): RegulatedRoad rules every
+ * int(simulation_frequency / 2) substeps, and after the observation the step's _clear_vehicles and
+ * _spawn_vehicle(spawn_probability) drawing from s->rng (IntersectionEnv.step, :136-140). */
+int hwy_intersection_step(const HwyNetParams *p, const HwyNetGraph *graph, const HwyIntersectionSpawn *spawn,
+                          const HwyNetState *s, const int32_t *action, float *obs, double *reward,
+                          uint8_t *terminated, uint8_t *truncated, double *info_speed,
+                          uint8_t *info_crashed, void *stream);
+
+/* Road.act() + Road.step(dt) n_substeps times without an ego action, for the envs whose mask byte is
+ * set (NULL: all): the 3 s warm-up of IntersectionEnv._make_vehicles (:271-278). */
+int hwy_network_substeps(const HwyNetParams *p, const HwyNetGraph *graph, const HwyNetState *s,
+                         const uint8_t *mask, int n_substeps, void *stream);
 
 /* observation_type.observe() of the current state */
 int hwy_network_observe(const HwyNetParams *p, const HwyNetGraph *graph, const HwyNetState *s,

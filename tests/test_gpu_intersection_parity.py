@@ -1,0 +1,149 @@
+"""GPU parity of intersection-v0 (RegulatedRoad, dynamic population, OccupancyGrid / 7-feature
+Kinematics) through the C ABI: against golden rollouts of the unmodified reference (state, obs,
+reward, flags AND the numpy generator words after every step) and against the oracle on more seeds."""
+import numpy as np
+import pytest
+
+import net_oracle as no
+from parity_utils import load_golden
+from test_net_oracle_golden import compare_inter, inter_state
+
+pytestmark = pytest.mark.gpu
+CASES = ["intersection_kin", "intersection_grid"]
+V = 32
+
+
+def make_env(cfg, n, **kw):
+    import highwayenv_b200 as hb
+
+    cfg = dict(cfg)
+    env_id = cfg.pop("_env_id")
+    cfg.pop("_others_check_collisions", None)
+    return hb.make(env_id, num_envs=n, config=cfg, **kw)
+
+
+def to_sd(states, rng_words=None):
+    """golden schema (NaN / -1 padded beyond `count`) -> env.load_state_dict schema"""
+    out = {}
+    live = np.stack([np.arange(V) < int(s["count"]) for s in states])
+    for k in ("x", "y", "heading", "speed", "target_speed", "timer"):
+        out[k] = np.where(live, np.nan_to_num(np.stack([s[k] for s in states])), 0.0)
+    out["delta"] = np.where(live, np.nan_to_num(np.stack([s["delta"] for s in states]), nan=4.0), 4.0)
+    lane = np.where(live, np.stack([s["lane"] for s in states]), 0)
+    tgt = np.stack([s["target_lane"] for s in states])
+    out["lane"], out["target_lane"] = lane, np.where(live & (tgt >= 0), tgt, lane)
+    imp = np.stack([s["impact"] for s in states])
+    has = live & ~np.isnan(imp[..., 0])
+    out["has_impact"] = has
+    out["impact_x"], out["impact_y"] = np.where(has, imp[..., 0], 0.0), np.where(has, imp[..., 1], 0.0)
+    for k in ("kind", "crashed", "is_yielding", "route_len"):
+        out[k] = np.where(live, np.stack([s[k] for s in states]), 0)
+    out["route"] = np.stack([s["route"] for s in states]).astype(np.int32)
+    out["speed_index"] = np.array([np.ravel(s["speed_index"])[0] for s in states], dtype=np.int32)
+    out["time"] = np.array([float(s["time"]) for s in states])
+    out["count"] = np.array([int(s["count"]) for s in states], dtype=np.int32)
+    out["road_steps"] = np.array([int(s["road_steps"]) for s in states], dtype=np.int32)
+    if rng_words is not None:
+        out["rng"] = np.ascontiguousarray(np.asarray(rng_words, dtype=np.uint64).T)
+    return out
+
+
+def oracle_view(sd):
+    a = dict(sd)
+    a["has_impact"] = sd["has_impact"]
+    return a
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_reset_matches_reference(name):
+    """host numpy spawns + 45 warm-up substeps on the device + challenger / ego / pruning"""
+    g = load_golden(name)
+    S = len(g["seeds"])
+    env = make_env(g["config"], S, autoreset_mode="Disabled")
+    obs, _ = env.reset(seed=[int(s) for s in g["seeds"]])
+    sd = env.state_dict()
+    for i in range(S):
+        compare_inter(inter_state(g, i, 0), oracle_view(sd), i, f"{name} reset#{i}", tol=1e-8)
+        assert np.array_equal(sd["rng"][:, i], g["rng_words"][i, 0]), i
+    assert np.max(np.abs(obs.cpu().numpy() - g["obs"][:, 0])) <= 1e-6
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_teacher_forced_vs_reference(name):
+    g = load_golden(name)
+    S, T = g["actions"].shape[:2]
+    env = make_env(g["config"], S, autoreset_mode="Disabled")
+    env.reset(seed=0)
+    for t in range(T):
+        env.load_state_dict(to_sd([inter_state(g, i, t) for i in range(S)], g["rng_words"][:, t]))
+        obs, rew, term, trunc, _ = env.step(g["actions"][:, t].astype(np.int32))
+        sd = env.state_dict()
+        obs, rew, term, trunc = obs.cpu().numpy(), rew.cpu().numpy(), term.cpu().numpy(), trunc.cpu().numpy()
+        for i in range(S):
+            ctx = f"{name} #{i} t={t}"
+            compare_inter(inter_state(g, i, t + 1), oracle_view(sd), i, ctx, tol=1e-8)
+            assert abs(rew[i] - g["reward"][i, t]) <= 1e-9, ctx
+            assert bool(term[i]) == bool(g["terminated"][i, t]) and bool(trunc[i]) == bool(g["truncated"][i, t]), ctx
+            assert np.max(np.abs(obs[i] - g["obs"][i, t + 1])) <= 1e-6, ctx
+            assert np.array_equal(sd["rng"][:, i], g["rng_words"][i, t + 1]), ctx  # device PCG64 == numpy stream
+
+
+@pytest.mark.parametrize("name,n,T", [("intersection_kin", 96, 10), ("intersection_grid", 64, 10)])
+def test_teacher_forced_vs_oracle_many_envs(name, n, T):
+    g = load_golden(name)
+    ob = no.IntersectionOracle(no.graph_from_arrays(g), no.cfg_from_dict(g["config"]), n, g, g["config"])
+    env = make_env(g["config"], n, autoreset_mode="Disabled")
+    env.reset(seed=4200)
+    for e in range(n):
+        ob.reset_env(e, seed=4200 + e)
+    sd = env.state_dict()
+    # reset: same draws, same population; coordinates within the warm-up's accumulated rounding
+    assert np.array_equal(sd["count"], ob.a["count"])
+    for e in range(n):
+        assert np.array_equal(sd["rng"][:, e], ob.rng_words(e)), e
+    rng = np.random.default_rng(3)
+    n_act = 3
+    for t in range(T):
+        state = {k: ob.a[k].copy() for k in ob.a}
+        state["rng"] = np.stack([ob.rng_words(e) for e in range(n)], axis=1)
+        env.load_state_dict(state)
+        act = rng.integers(0, n_act, size=n).astype(np.int32)
+        o_obs, o_rew, o_term, o_trunc = ob.step(act)
+        obs, rew, term, trunc, _ = env.step(act)
+        sd = env.state_dict()
+        assert np.array_equal(sd["count"], ob.a["count"]), t
+        live = np.arange(V)[None, :] < sd["count"][:, None]
+        for k in ("x", "y", "heading", "speed", "timer", "target_speed", "delta"):
+            assert np.max(np.abs(np.where(live, sd[k] - ob.a[k], 0.0))) <= 1e-7, (t, k)
+        for k in ("lane", "target_lane", "crashed", "has_impact", "route_len", "kind", "is_yielding"):
+            assert np.array_equal(np.where(live, sd[k], 0).astype(np.int32), np.where(live, ob.a[k], 0).astype(np.int32)), (t, k)
+        assert np.array_equal(sd["speed_index"], ob.a["speed_index"])
+        assert np.array_equal(sd["road_steps"], ob.a["road_steps"])
+        for e in range(n):
+            assert np.array_equal(sd["rng"][:, e], ob.rng_words(e)), (t, e)
+        assert np.max(np.abs(rew.cpu().numpy() - o_rew)) <= 1e-9
+        assert np.array_equal(term.cpu().numpy(), o_term.astype(bool))
+        assert np.array_equal(trunc.cpu().numpy(), o_trunc.astype(bool))
+        assert np.max(np.abs(obs.cpu().numpy().reshape(n, -1) - o_obs.reshape(n, -1))) <= 1e-6
+
+
+def test_free_running_rollout_and_autoreset():
+    """free-running episodes with SameStep autoreset: population stays within the slots, every
+    finished env is replaced by a fresh `_make_vehicles` population, observations stay finite."""
+    g = load_golden("intersection_kin")
+    n = 48
+    env = make_env(g["config"], n)
+    env.reset(seed=11)
+    rng = np.random.default_rng(1)
+    resets = 0
+    for t in range(30):
+        obs, rew, term, trunc, info = env.step(rng.integers(0, 3, size=n).astype(np.int32))
+        done = (term | trunc).cpu().numpy()
+        resets += int(done.sum())
+        sd = env.state_dict()
+        assert np.all(sd["time"][done] == 0)
+        assert np.all((sd["count"] >= 1) & (sd["count"] <= V))
+        assert np.isfinite(obs.cpu().numpy()).all() and np.isfinite(rew.cpu().numpy()).all()
+        if done.any():
+            assert "final_obs" in info
+    assert resets >= n

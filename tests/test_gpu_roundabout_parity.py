@@ -127,7 +127,8 @@ def test_teacher_forced_vs_oracle_many_envs(name, n, T):
     env.reset(seed=31000)
     sd0 = env.state_dict()
     for k in ob.a:
-        ob.a[k][...] = sd0[k]
+        if k in sd0:  # count / is_yielding / road_steps are intersection-only
+            ob.a[k][...] = sd0[k]
     rng = np.random.default_rng(7)
     for t in range(T):
         env.load_state_dict({k: ob.a[k].copy() for k in ob.a})

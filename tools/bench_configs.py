@@ -27,23 +27,31 @@ CONFIGS = [
     ("cfg3 roundabout-v0 TimeToCollision", "roundabout-v0",
      {"observation": {"type": "TimeToCollision", "horizon": 10}}, 8192, "SameStep", "discrete"),
     ("roundabout-v0 defaults (Kinematics)", "roundabout-v0", None, 8192, "SameStep", "discrete"),
+    ("cfg2 intersection-v0 OccupancyGrid", "intersection-v0", {"observation": {"type": "OccupancyGrid"}}, 8192,
+     "SameStep", "discrete3"),
+    ("intersection-v0 defaults (Kinematics 15x7)", "intersection-v0", None, 8192, "SameStep", "discrete3"),
+    ("cfg2 intersection-v0 OccupancyGrid, step kernel only", "intersection-v0",
+     {"observation": {"type": "OccupancyGrid"}}, 8192, "Disabled", "discrete3"),
 ]
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--only", default=None, help="substring filter on the config name")
     args = ap.parse_args()
     dev = torch.device("cuda")
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     for name, env_id, cfg, n, mode, akind in CONFIGS:
+        if args.only and args.only not in name:
+            continue
         env = hb.make(env_id, num_envs=n, config=cfg, autoreset_mode=mode)
         env.reset(seed=0)
         g = torch.Generator(device=dev)
         g.manual_seed(1234)
         K, W = args.steps, 5
-        if akind == "discrete":
-            acts = torch.randint(0, 5, (K + W, n), generator=g, device=dev, dtype=torch.int32)
+        if akind.startswith("discrete"):
+            acts = torch.randint(0, 3 if akind == "discrete3" else 5, (K + W, n), generator=g, device=dev, dtype=torch.int32)
         else:
             acts = (torch.rand((K + W, n, 2), generator=g, device=dev, dtype=torch.float32) * 2 - 1)
         for t in range(W):
