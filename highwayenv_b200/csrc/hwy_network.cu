@@ -36,11 +36,17 @@ struct GraphShared {
     int succ[HWY_NET_MAX_NODES][HWY_NET_MAX_SUCC];
 };
 
+template <int G>
+__host__ __device__ constexpr int kCand() {
+    return G >= 32 ? 96 : 40;
+}
+
 // Per-env shared staging for G vehicle slots.  REG adds the RegulatedRoad prediction buffers.
 template <int G, bool REG>
 struct EnvStage {
     double x[G], y[G], heading[G], c[G], s[G], v[G], ts[G];
     int lane[G], tgt[G], kind[G];
+    int tgt_prev[G];  // target lanes before the current Road.act (Gauss-Seidel view of later vehicles)
     int route[G][R];
     int route_len[G];
     int count, ego, speed_index, road_steps;
@@ -49,12 +55,20 @@ struct EnvStage {
     double sp_x, sp_y, sp_h, sp_speed, sp_delta;
     int sp_ok, sp_lane, sp_dest;
     double key[G];
+    // local coordinates of every vehicle on its OWN lane (st.lane), refreshed together with the lane index:
+    // what local_coordinates() returns for (vehicle.lane, vehicle.position), reused by every query on that lane
+    double own_s[G], own_lat[G];
+    int n_cand;
     union {
         double ttc[3][4][12];  // TimeToCollision grid [speed][lane on road][time]
         struct {
             int owner[121];           // OccupancyGrid: lowest vehicle index in the cell
             unsigned char road[121];  // on_road layer
         } cells;
+        struct {  // closest-lane search: (vehicle, lane) pairs that survive the lateral lower bound
+            double d[kCand<G>()], s[kCand<G>()], lat[kCand<G>()];
+            unsigned short vl[kCand<G>()];
+        } cand;
     } o;
     // RegulatedRoad: predicted (x, y, heading) of every vehicle at the 11 horizon points
     double pred[REG ? G : 1][REG ? kPred : 1][3];
@@ -62,22 +76,35 @@ struct EnvStage {
 
 // ------------------------------------------------------------------ lanes (road/lane.py)
 // local_coordinates: StraightLane :205-209, SineLane :285-289, CircularLane :351-358
-__device__ __noinline__ void lane_local(const HwyNetLane& L, double x, double y, double& s, double& lat) {
+// `gate`: callers that go on to test on_lane(.., margin) (lane.py:100-118) pass width/2 + margin; the lateral
+// offset is computed first and the longitudinal one (an atan2 on a CircularLane) only when |lat| <= gate.
+// Returns false (s untouched) when the lateral test already fails.  gate = +inf: plain local_coordinates.
+__device__ __noinline__ bool lane_local_gated(const HwyNetLane& L, double x, double y, double gate, double& s,
+                                              double& lat) {
     if (L.type == HWY_LANE_CIRCULAR) {
         double ddx = x - L.cx, ddy = y - L.cy;
+        double r = norm2(ddx, ddy);
+        lat = L.direction * (L.radius - r);
+        if (!(fabs(lat) <= gate)) return false;
         double phi = atan2(ddy, ddx);
         phi = L.start_phase + wrap_to_pi(phi - L.start_phase);
-        double r = norm2(ddx, ddy);
         s = L.direction * (phi - L.start_phase) * L.radius;
-        lat = L.direction * (L.radius - r);
-        return;
+        return true;
     }
     double ddx = x - L.sx, ddy = y - L.sy;
-    double lon = dot2(ddx, ddy, L.dx, L.dy);
     double la = dot2(ddx, ddy, L.lx, L.ly);
+    if (L.type != HWY_LANE_SINE && !(fabs(la) <= gate)) {
+        lat = la;
+        return false;
+    }
+    double lon = dot2(ddx, ddy, L.dx, L.dy);
     if (L.type == HWY_LANE_SINE) la = la - L.amplitude * m_sin(L.pulsation * lon + L.phase);
     s = lon;
     lat = la;
+    return fabs(la) <= gate;
+}
+__device__ __forceinline__ void lane_local(const HwyNetLane& L, double x, double y, double& s, double& lat) {
+    lane_local_gated(L, x, y, INFINITY, s, lat);
 }
 // position: StraightLane :192-197, SineLane :268-273, CircularLane :338-342
 __device__ __noinline__ void lane_position(const HwyNetLane& L, double s, double lat, double& x, double& y) {
@@ -128,9 +155,8 @@ __device__ __forceinline__ double lane_distance(const HwyNetLane& L, double x, d
     return fabs(r) + fmax(s - L.length, 0.0) + fmax(0.0 - s, 0.0);
 }
 // :132-147 distance_with_heading
-__device__ __forceinline__ double lane_distance_with_heading(const HwyNetLane& L, double x, double y,
-                                                             double h) {
-    double s, r;
+__device__ __forceinline__ double lane_distance_with_heading(const HwyNetLane& L, double x, double y, double h,
+                                                             double& s, double& r) {
     lane_local(L, x, y, s, r);
     double angle = fabs(wrap_to_pi(h - lane_heading_at(L, s)));
     return fabs(r) + fmax(s - L.length, 0.0) + fmax(0.0 - s, 0.0) + 1.0 * angle;
@@ -146,6 +172,12 @@ __device__ __forceinline__ int road_first(const GraphShared& g, int from, int to
         if (g.lanes[f].to_node == to) return f;
     }
     return -1;
+}
+
+__device__ __forceinline__ double lane_distance_with_heading(const HwyNetLane& L, double x, double y,
+                                                             double h) {
+    double s, r;
+    return lane_distance_with_heading(L, x, y, h, s, r);
 }
 
 // road/road.py:138-157 next_lane_given_next_road (next_id < 0 == None)
@@ -217,7 +249,8 @@ __device__ __noinline__ int next_lane(const GraphShared& g, EnvStage<G, REG>& st
 template <int G, bool REG>
 __device__ __forceinline__ void follow_road(const GraphShared& g, EnvStage<G, REG>& st, int v) {
     const HwyNetLane& T = g.lanes[st.tgt[v]];
-    if (lane_s_of(T, st.x[v], st.y[v]) > T.length - kLaneVehLength / 2)  // after_end (lane.py:120-125)
+    const double s = st.tgt[v] == st.lane[v] ? st.own_s[v] : lane_s_of(T, st.x[v], st.y[v]);
+    if (s > T.length - kLaneVehLength / 2)  // after_end (lane.py:120-125)
         st.tgt[v] = next_lane(g, st, v, st.tgt[v]);
 }
 
@@ -226,14 +259,20 @@ template <int G, bool REG>
 __device__ __noinline__ void neighbours(const GraphShared& g, const EnvStage<G, REG>& st, int V, int veh,
                                         int lane_idx, int& front, int& rear) {
     const HwyNetLane& L = g.lanes[lane_idx];
-    double s = lane_s_of(L, st.x[veh], st.y[veh]);
+    const double s = lane_idx == st.lane[veh] ? st.own_s[veh] : lane_s_of(L, st.x[veh], st.y[veh]);
+    const double gate = L.width / 2 + 1.0;  // the lateral half of on_lane(margin=1)
     double s_front = 0, s_rear = 0;
     front = -1;
     rear = -1;
     for (int v = 0; v < V; ++v) {
         if (v == veh) continue;
         double s_v, lat_v;
-        lane_local(L, st.x[v], st.y[v], s_v, lat_v);
+        if (st.lane[v] == lane_idx) {
+            s_v = st.own_s[v];
+            lat_v = st.own_lat[v];
+        } else if (!lane_local_gated(L, st.x[v], st.y[v], gate, s_v, lat_v)) {
+            continue;
+        }
         if (!lane_on(L, s_v, lat_v, 1.0)) continue;
         if (s <= s_v && (front < 0 || s_v <= s_front)) {
             s_front = s_v;
@@ -250,7 +289,8 @@ template <int G, bool REG>
 __device__ __forceinline__ double lane_distance_to(const GraphShared& g, const EnvStage<G, REG>& st, int self,
                                                    int other) {
     const HwyNetLane& L = g.lanes[st.lane[self]];
-    return lane_s_of(L, st.x[other], st.y[other]) - lane_s_of(L, st.x[self], st.y[self]);
+    const double s_other = st.lane[other] == st.lane[self] ? st.own_s[other] : lane_s_of(L, st.x[other], st.y[other]);
+    return s_other - st.own_s[self];
 }
 // vehicle/behavior.py:192-217
 template <int G, bool REG>
@@ -319,7 +359,9 @@ __device__ __forceinline__ double change_lane_policy(const HwyNetParams& P, cons
         const HwyNetLane &A = g.lanes[lane], &B = g.lanes[st.tgt[v]];
         if (A.from_node == B.from_node && A.to_node == B.to_node) {
             for (int o = 0; o < V; ++o) {
-                if (o != v && st.lane[o] != st.tgt[v] && st.tgt[o] == st.tgt[v]) {
+                // vehicles later in the list have not acted yet: their target lane of before this Road.act
+                const int tgt_o = o < v ? st.tgt[o] : st.tgt_prev[o];
+                if (o != v && st.lane[o] != st.tgt[v] && tgt_o == st.tgt[v]) {
                     double d = lane_distance_to(g, st, v, o);
                     double d_star = desired_gap(P, st, v, o);
                     if (0 < d && d < d_star) {
@@ -345,10 +387,8 @@ __device__ __forceinline__ double change_lane_policy(const HwyNetParams& P, cons
 }
 
 // vehicle/controller.py:145-187 steering_control up to the argument of the last arcsin
-__device__ __noinline__ double steering_sin_slip(const HwyNetLane& L, double x, double y, double heading,
+__device__ __noinline__ double steering_sin_slip(const HwyNetLane& L, double lc_s, double lc_lat, double heading,
                                                  double speed) {
-    double lc_s, lc_lat;
-    lane_local(L, x, y, lc_s, lc_lat);
     double lane_future_heading = lane_heading_at(L, lc_s + speed * kTauPursuit);
     double lateral_speed_command = -kKpLateral * lc_lat;
     double heading_command = m_asin(clipd(lateral_speed_command / not_zero(speed), -1.0, 1.0));
@@ -372,36 +412,94 @@ template <int G>
 __device__ __forceinline__ void group_sync() {
     __syncwarp(group_mask<G>());
 }
+// Block-wide variant for the unconditional phase boundaries of a substep.  Only the G threads of an env exchange
+// data, but the kernels' code is several times the 32 KB instruction cache: keeping the block's warps in the same
+// phase lets them share the fetched lines instead of each streaming the whole body (stall_no_instruction).
+template <int G>
+__device__ __forceinline__ void phase_sync() {
+#ifdef HWY_NET_WARP_PHASES
+    __syncwarp(group_mask<G>());
+#else
+    // NOT __syncthreads(): that is barrier.sync.ALIGNED, which requires the whole warp to arrive converged — the
+    // compiler does not guarantee that here (per-vehicle branches around the call sites; synccheck flagged it).
+    // The unaligned form counts threads individually and is also the intra-group memory fence the callers need.
+    asm volatile("barrier.sync 0;" ::: "memory");
+#endif
+}
 
-// road/road.py:55-71 get_closest_lane_index for every vehicle, cooperatively: thread t scans lanes
-// t, t+G, ...; arg-min over (distance, lane index) keeps the first minimum like np.argmin.
+// road/road.py:55-71 get_closest_lane_index for every vehicle of the group; also refreshes the own-lane
+// coordinate cache.  np.argmin over distance_with_heading of all lanes keeps the FIRST minimum.  Exact pruning:
+// the distance to the lane the vehicle was on is an upper bound of the minimum, and
+// distance_with_heading >= |lateral offset| (all its terms are >= 0 and rounding is monotone), so a lane whose
+// |lateral| — no atan2 needed — exceeds that bound can never win.  The surviving (vehicle, lane) pairs go to a
+// shared work list that the whole group evaluates, then every vehicle reduces its own entries by (d, lane).
 template <int G, bool REG>
-__device__ __forceinline__ int closest_lane_group(const GraphShared& g, const EnvStage<G, REG>& st, int V, int i) {
-    int mine = 0;
-    const unsigned mask = group_mask<G>();
-    for (int v = 0; v < V; ++v) {
-        double bd = INFINITY;
-        int bl = 0x7fffffff;
-        const double x = st.x[v], y = st.y[v], h = st.heading[v];
-        for (int l = i; l < g.n_lanes; l += G) {
-            double d = lane_distance_with_heading(g.lanes[l], x, y, h);
-            if (d < bd) {
+__device__ __forceinline__ void closest_lane_group(const GraphShared& g, EnvStage<G, REG>& st, int V, int i) {
+    const bool active = i < V;
+    constexpr int K = kCand<G>();
+    double x = 0, y = 0, h = 0, bd = 0, bs = 0, blat = 0;
+    int bl = 0;
+    if (i == 0) st.n_cand = 0;
+    if (active) {
+        x = st.x[i];
+        y = st.y[i];
+        h = st.heading[i];
+        bl = st.lane[i];
+        bd = lane_distance_with_heading(g.lanes[bl], x, y, h, bs, blat);
+    }
+    phase_sync<G>();
+    if (active) {
+        const int hint = bl;
+        for (int l = 0; l < g.n_lanes; ++l) {
+            if (l == hint) continue;
+            const HwyNetLane& L = g.lanes[l];
+            double lb = 0.0;
+            if (L.type == HWY_LANE_CIRCULAR)
+                lb = fabs(L.direction * (L.radius - norm2(x - L.cx, y - L.cy)));
+            else if (L.type == HWY_LANE_STRAIGHT)
+                lb = fabs(dot2(x - L.sx, y - L.sy, L.lx, L.ly));
+            if (lb > bd) continue;
+            int slot = atomicAdd(&st.n_cand, 1);
+            if (slot < K) {
+                st.o.cand.vl[slot] = (unsigned short)((i << 8) | l);
+            } else {  // list full: evaluate in place
+                double s_, r_;
+                double d = lane_distance_with_heading(L, x, y, h, s_, r_);
+                if (d < bd || (d == bd && l < bl)) {
+                    bd = d;
+                    bl = l;
+                    bs = s_;
+                    blat = r_;
+                }
+            }
+        }
+    }
+    phase_sync<G>();
+    const int n = min(st.n_cand, K);
+    for (int p = i; p < n; p += G) {
+        const int v = st.o.cand.vl[p] >> 8, l = st.o.cand.vl[p] & 0xff;
+        st.o.cand.d[p] = lane_distance_with_heading(g.lanes[l], st.x[v], st.y[v], st.heading[v], st.o.cand.s[p],
+                                                    st.o.cand.lat[p]);
+    }
+    phase_sync<G>();
+    if (active) {
+        for (int p = 0; p < n; ++p) {
+            const int vl = st.o.cand.vl[p];
+            if ((vl >> 8) != i) continue;
+            const int l = vl & 0xff;
+            const double d = st.o.cand.d[p];
+            if (d < bd || (d == bd && l < bl)) {
                 bd = d;
                 bl = l;
+                bs = st.o.cand.s[p];
+                blat = st.o.cand.lat[p];
             }
         }
-#pragma unroll
-        for (int off = G / 2; off > 0; off >>= 1) {
-            double od = __shfl_xor_sync(mask, bd, off, G);
-            int ol = __shfl_xor_sync(mask, bl, off, G);
-            if (od < bd || (od == bd && ol < bl)) {
-                bd = od;
-                bl = ol;
-            }
-        }
-        if (v == i) mine = bl;
+        st.lane[i] = bl;
+        st.own_s[i] = bs;
+        st.own_lat[i] = blat;
     }
-    return mine;
+    phase_sync<G>();
 }
 
 // ------------------------------------------------------------------ observations
@@ -770,7 +868,7 @@ __device__ __forceinline__ void enforce_road_rules(const HwyNetParams& P, const 
     if (i == 0) st.yield_mask = 0;
     // predict_trajectory_constant_speed (vehicle/controller.py:236-253) at t = 0.25 .. 2.75 s
     if (active) {
-        const double s0 = lane_s_of(g.lanes[st.lane[i]], r.x, r.y);
+        const double s0 = st.own_s[i];
         for (int k = 0; k < kPred; ++k) {
             double px, py, ph;
             position_heading_along_route(g, st, i, s0 + r.speed * (0.25 * (k + 1)), px, py, ph);
@@ -847,20 +945,36 @@ __device__ __forceinline__ void substep(const HwyNetParams& P, const GraphShared
             if (lane_reachable(g.lanes[cand], r.x, r.y)) st.tgt[i] = cand;
         }
     }
-    group_sync<G>();
-    // ---- Road.act (road/road.py:464-467), ordered part: follow_road + lane-change policy in list order
+    phase_sync<G>();
+    // ---- Road.act (road/road.py:464-467): vehicle.act() in list order.  follow_road only touches the vehicle's
+    // own target lane and route, so all of them run at once; what must stay ordered is the lane-change policy of the
+    // vehicles whose policy can read another vehicle's target lane or move their own (a pending change on the same
+    // road, or a decision tick on a multi-lane road).  Those take turns; when it is u's turn it sees the final
+    // target lanes of the vehicles before it and the pre-act ones (tgt_prev) of the vehicles after it.
     const bool crashed = (r.meta & HWY_META_CRASHED) != 0;
-    for (int v = 0; v < V; ++v) {
-        if (i == v) {
-            if (kind == HWY_KIND_IDM) {
-                if (!crashed) {  // behavior.py:102-103
-                    follow_road(g, st, v);
-                    r.timer = change_lane_policy(P, g, st, V, v, r.delta, r.timer);
-                }
-            } else {
-                follow_road(g, st, v);  // ControlledVehicle.act(None) (controller.py:98)
+    bool ordered = false;
+    if (active) {
+        st.tgt_prev[i] = st.tgt[i];
+        if (kind != HWY_KIND_IDM || !crashed) follow_road(g, st, i);  // behavior.py:102-103, controller.py:98
+        if (kind == HWY_KIND_IDM && !crashed) {
+            const int lane = st.lane[i], tgt = st.tgt[i];
+            const HwyNetLane &A = g.lanes[lane], &B = g.lanes[tgt];
+            if (lane != tgt) {
+                ordered = A.from_node == B.from_node && A.to_node == B.to_node;
+            } else if (P.lane_change_delay < r.timer) {  // do_every (utils.py:16-17)
+                if (A.road_count > 1)
+                    ordered = true;
+                else
+                    r.timer = 0.0;  // decision tick with no side lane
             }
         }
+    }
+    phase_sync<G>();
+    unsigned turn = __ballot_sync(group_mask<G>(), ordered) >> ((threadIdx.x & 31) & ~(G - 1));
+    while (turn) {
+        const int v = __ffs(turn) - 1;
+        turn &= turn - 1;
+        if (i == v) r.timer = change_lane_policy(P, g, st, V, v, r.delta, r.timer);
         group_sync<G>();
     }
     // ---- parallel part: steering + acceleration
@@ -868,7 +982,9 @@ __device__ __forceinline__ void substep(const HwyNetParams& P, const GraphShared
     if (active) {
         const int lane = st.lane[i], tgt = st.tgt[i];
         if (!crashed) {
-            double xs = steering_sin_slip(g.lanes[tgt], r.x, r.y, r.heading, r.speed);
+            double lc_s = st.own_s[i], lc_lat = st.own_lat[i];
+            if (tgt != lane) lane_local(g.lanes[tgt], r.x, r.y, lc_s, lc_lat);
+            double xs = steering_sin_slip(g.lanes[tgt], lc_s, lc_lat, r.heading, r.speed);
             beta_of_controlled(xs, sin_beta, cos_beta);
         }
         if (kind == HWY_KIND_IDM) {
@@ -912,12 +1028,10 @@ __device__ __forceinline__ void substep(const HwyNetParams& P, const GraphShared
         r.heading += r.speed * sin_beta / (kVehLength / 2) * dt;
         r.speed += act_accel * dt;
     }
-    group_sync<G>();  // everyone is done reading the pre-step staging
+    phase_sync<G>();  // everyone is done reading the pre-step staging
     if (active) publish(st, i, r);
-    group_sync<G>();
-    int nl = closest_lane_group(g, st, V, i);  // on_state_update
-    if (active) st.lane[i] = nl;
-    group_sync<G>();
+    phase_sync<G>();
+    closest_lane_group(g, st, V, i);  // on_state_update
     // ---- collision sweep (road/road.py:477-481): partners in ascending order => the surviving impact is
     // the one of the largest partner index
     if (active) {
@@ -945,8 +1059,8 @@ __device__ __forceinline__ void substep(const HwyNetParams& P, const GraphShared
 
 // load one env into the group's stage (count, ego, routes, staged kinematics)
 template <int G, bool REG>
-__device__ __forceinline__ void load_env(const HwyNetParams& P, const HwyNetState& S, EnvStage<G, REG>& st, int e,
-                                         int i, Regs& r) {
+__device__ __forceinline__ void load_env(const HwyNetParams& P, const GraphShared& g, const HwyNetState& S,
+                                         EnvStage<G, REG>& st, int e, int i, Regs& r) {
     const size_t slot = (size_t)e * S.vp + i;
     load_regs(S, slot, r);
     const int* src = S.route + slot * R;
@@ -962,6 +1076,7 @@ __device__ __forceinline__ void load_env(const HwyNetParams& P, const HwyNetStat
     st.lane[i] = meta_lane(r.meta);
     st.tgt[i] = meta_target(r.meta);
     st.kind[i] = meta_kind(r.meta);
+    if (i < count) lane_local(g.lanes[st.lane[i]], r.x, r.y, st.own_s[i], st.own_lat[i]);
     // the controlled vehicle: first MDPVehicle of the list
     unsigned is_mdp = __ballot_sync(group_mask<G>(), i < count && meta_kind(r.meta) == HWY_KIND_MDP);
     is_mdp >>= ((threadIdx.x & 31) & ~(G - 1));
@@ -1093,7 +1208,7 @@ network_step_kernel(const HwyNetParams P, const HwyNetGraph* __restrict__ graph,
     EnvStage<G, REG>& st = stages[sub];
 
     Regs r;
-    load_env(P, S, st, e, i, r);
+    load_env(P, g, S, st, e, i, r);
     const int frames = P.simulation_frequency / P.policy_frequency;
     const double dt = 1.0 / P.simulation_frequency;
     const int act = action[e];
@@ -1110,8 +1225,7 @@ network_step_kernel(const HwyNetParams P, const HwyNetGraph* __restrict__ graph,
     observe_any(P, g, st, V, i, obs_env);
     if (i == ego && i < V && env_ok) {
         const HwyNetLane& L = g.lanes[st.lane[i]];
-        double es, elat;
-        lane_local(L, r.x, r.y, es, elat);
+        const double es = st.own_s[i], elat = st.own_lat[i];
         const bool on_road = lane_on(L, es, elat, 0.0);
         const bool is_crashed = (r.meta & HWY_META_CRASHED) != 0;
         double rew = 0.0;
@@ -1155,7 +1269,7 @@ network_step_kernel(const HwyNetParams P, const HwyNetGraph* __restrict__ graph,
         bool keep = i < V;
         if (keep && meta_kind(r.meta) != HWY_KIND_MDP) {  // _clear_vehicles :354-366
             const HwyNetLane& L = g.lanes[st.lane[i]];
-            if (L.exit_lane && lane_s_of(L, r.x, r.y) >= L.length - 4 * kVehLength) keep = false;
+            if (L.exit_lane && st.own_s[i] >= L.length - 4 * kVehLength) keep = false;
         }
         unsigned keep_mask = __ballot_sync(group_mask<G>(), keep) >> ((threadIdx.x & 31) & ~(G - 1));
         const int n_keep = __popc(keep_mask);
@@ -1200,7 +1314,7 @@ network_observe_kernel(const HwyNetParams P, const HwyNetGraph* __restrict__ gra
     const int e = env_ok ? env : S.n_envs - 1;
     EnvStage<G, REG>& st = stages[sub];
     Regs r;
-    load_env(P, S, st, e, i, r);
+    load_env(P, g, S, st, e, i, r);
     const bool selected = (!mask_a && !mask_b) || (mask_a && mask_a[e]) || (mask_b && mask_b[e]);
     if (!selected) return;  // whole group leaves together (selection is per env)
     observe_any(P, g, st, st.count, i, obs + (size_t)e * obs_size(P));
@@ -1218,16 +1332,20 @@ network_substeps_kernel(const HwyNetParams P, const HwyNetGraph* __restrict__ gr
     stage_graph(g, graph);
     constexpr int kEnvs = kBlockThreads / G;
     const int sub = threadIdx.x / G, i = threadIdx.x % G;
-    const int env = blockIdx.x * kEnvs + sub;
-    if (env >= S.n_envs) return;
-    if (mask && !mask[env]) return;
+    const int env_raw = blockIdx.x * kEnvs + sub;
+    // substep() has block-wide phase barriers: a block leaves only as a whole; envs that are not selected ride
+    // along (on a valid env's data) and store nothing
+    const bool selected = env_raw < S.n_envs && (!mask || mask[env_raw]);
+    if (!__syncthreads_or(selected)) return;
+    const int env = env_raw < S.n_envs ? env_raw : S.n_envs - 1;
     EnvStage<G, REG>& st = stages[sub];
     Regs r;
-    load_env(P, S, st, env, i, r);
+    load_env(P, g, S, st, env, i, r);
     const double dt = 1.0 / P.simulation_frequency;
     double act_accel = 0.0;
     for (int k = 0; k < n_substeps; ++k) substep(P, g, st, i, r, act_accel, dt, -1);
     group_sync<G>();
+    if (!selected) return;
     store_env(S, st, env, i, i < st.count ? i : -1, r);
     if (i == 0 && S.road_steps) S.road_steps[env] = st.road_steps;
 }

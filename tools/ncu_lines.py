@@ -1,0 +1,32 @@
+"""Aggregate an `ncu --page source --print-source cuda,sass --csv` dump per CUDA source line.
+    python tools/ncu_lines.py dump.csv [top]"""
+import csv
+import sys
+
+rows = csv.reader(open(sys.argv[1]))
+top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+cur_file, fn, hdr, out = None, None, None, []
+for r in rows:
+    if not r:
+        continue
+    if r[0] == "File Path":
+        cur_file = r[1].split("/")[-1]
+    elif r[0] == "Function Name":
+        fn = r[1][:60]
+    elif r[0] == "Line No":
+        hdr = r
+    elif r[0].isdigit() and hdr:
+        d = dict(zip(hdr[4:], r[4:]))
+        try:
+            out.append((int(d["Instructions Executed"]), int(d["# Samples"]), cur_file, int(r[0]), r[1].strip()[:90],
+                        float(d["Avg. Threads Executed"] or 0), fn))
+        except (ValueError, KeyError):
+            pass
+ti, ts = sum(o[0] for o in out), sum(o[1] for o in out)
+print("total inst", ti, "samples", ts)
+print("== by instructions")
+for o in sorted(out, reverse=True)[:top]:
+    print(f"{o[0]/ti*100:5.1f}% i {o[1]/ts*100:5.1f}% s thr {o[5]:4.0f} {o[2]}:{o[3]} | {o[4]}")
+print("== by stall samples")
+for o in sorted(out, key=lambda o: -o[1])[:top]:
+    print(f"{o[0]/ti*100:5.1f}% i {o[1]/ts*100:5.1f}% s thr {o[5]:4.0f} {o[2]}:{o[3]} | {o[4]}")
