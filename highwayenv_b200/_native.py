@@ -117,7 +117,9 @@ class HwyNetState(C.Structure):
 
 class HwyIntersectionSpawn(C.Structure):
     _fields_ = [("spawn_lane", C.c_int32 * 4), ("spawn_probability", C.c_double),
-                ("route_table", C.c_void_p), ("route_len", C.c_void_p)]
+                ("route_table", C.c_void_p), ("route_len", C.c_void_p),
+                ("ego_lane", C.c_int32), ("ego_destination", C.c_int32), ("initial_vehicle_count", C.c_int32),
+                ("_pad", C.c_int32), ("scratch", C.c_void_p)]
 
 
 class HwyRoundaboutSpawn(C.Structure):
@@ -136,7 +138,7 @@ EXPORTS = (
     "hwy_abi_version", "hwy_last_error", "hwy_highway_slot_stride", "hwy_highway_reset",
     "hwy_highway_observe", "hwy_highway_step", "hwy_highway_autoreset", "hwy_launch_count",
     "hwy_network_obs_size", "hwy_network_step", "hwy_network_observe", "hwy_roundabout_reset",
-    "hwy_intersection_step", "hwy_network_substeps",
+    "hwy_intersection_step", "hwy_network_substeps", "hwy_intersection_reset",
 )
 
 _lib = None
@@ -180,6 +182,9 @@ def load():
     lib.hwy_intersection_step.restype = C.c_int
     lib.hwy_intersection_step.argtypes = [NP, NG, C.POINTER(HwyIntersectionSpawn), NS, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.hwy_intersection_reset.restype = C.c_int
+    lib.hwy_intersection_reset.argtypes = [NP, NG, C.POINTER(HwyIntersectionSpawn), NS, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_void_p]
     lib.hwy_network_substeps.restype = C.c_int
     lib.hwy_network_substeps.argtypes = [NP, NG, NS, C.c_void_p, C.c_int, C.c_void_p]
     lib.hwy_roundabout_reset.restype = C.c_int

@@ -52,8 +52,8 @@ struct EnvStage {
     int count, ego, speed_index, road_steps;
     unsigned yield_mask;
     // spawn record (dynamic population): written by the group's first thread, adopted by the new slot
-    double sp_x, sp_y, sp_h, sp_speed, sp_delta;
-    int sp_ok, sp_lane, sp_dest;
+    double sp_x, sp_y, sp_h, sp_speed, sp_delta, sp_ts;
+    int sp_ok, sp_lane, sp_dest, sp_kind;
     double key[G];
     // local coordinates of every vehicle on its OWN lane (st.lane), refreshed together with the lane index:
     // what local_coordinates() returns for (vehicle.lane, vehicle.position), reused by every query on that lane
@@ -1147,25 +1147,33 @@ __device__ __noinline__ void spawn_vehicle(const HwyNetParams& P, const HwyInter
     st.sp_ok = 1;
 }
 
-// the thread owning slot `dst` adopts the spawn record as an IDMVehicle
+// the thread owning the new slot adopts the spawn record: an IDMVehicle, or the MDPVehicle of _make_vehicles
 template <int G, bool REG>
 __device__ __forceinline__ void adopt_spawn(const HwyNetParams& P, const HwyIntersectionSpawn& SP,
-                                            EnvStage<G, REG>& st, int i, Regs& r) {
+                                            const GraphShared& g, EnvStage<G, REG>& st, int i, Regs& r,
+                                            int kind = HWY_KIND_IDM) {
     r.x = st.sp_x;
     r.y = st.sp_y;
     r.heading = st.sp_h;
     r.speed = st.sp_speed;
-    r.target_speed = st.sp_speed;
-    r.timer = py_mod_pos((st.sp_x + st.sp_y) * kPi, P.lane_change_delay);
-    r.delta = st.sp_delta;
+    if (kind == HWY_KIND_IDM) {
+        r.target_speed = st.sp_speed;
+        r.timer = py_mod_pos((st.sp_x + st.sp_y) * kPi, P.lane_change_delay);  // behavior.py:59
+        r.delta = st.sp_delta;
+    } else {
+        r.target_speed = st.sp_ts;
+        r.timer = 0.0;
+        r.delta = 4.0;
+    }
     r.imp_x = r.imp_y = 0.0;
     r.meta = (st.sp_lane << HWY_META_LANE_SHIFT) | (st.sp_lane << HWY_META_TARGET_SHIFT) | HWY_META_CHECK_COLLISIONS |
-             (HWY_KIND_IDM << HWY_META_KIND_SHIFT) | HWY_META_PRESENT;
+             (kind << HWY_META_KIND_SHIFT) | HWY_META_PRESENT;
     const int* rs = SP.route_table + ((size_t)st.sp_lane * 4 + st.sp_dest) * R;
     for (int k = 0; k < R; ++k) st.route[i][k] = rs[k];
     st.route_len[i] = SP.route_len[(size_t)st.sp_lane * 4 + st.sp_dest];
     st.lane[i] = st.tgt[i] = st.sp_lane;
-    st.kind[i] = HWY_KIND_IDM;
+    st.kind[i] = kind;
+    lane_local(g.lanes[st.sp_lane], r.x, r.y, st.own_s[i], st.own_lat[i]);
     publish(st, i, r);
 }
 
@@ -1284,7 +1292,7 @@ network_step_kernel(const HwyNetParams P, const HwyNetGraph* __restrict__ graph,
         if (env_ok) store_env(S, st, e, i, dst, r);
         group_sync<G>();
         if (st.sp_ok && i == n_keep) {
-            adopt_spawn(P, SP, st, i, r);
+            adopt_spawn(P, SP, g, st, i, r);
             if (env_ok) store_env(S, st, e, i, i, r);
         }
         if (i == 0 && env_ok) {
@@ -1348,6 +1356,135 @@ network_substeps_kernel(const HwyNetParams P, const HwyNetGraph* __restrict__ gr
     if (!selected) return;
     store_env(S, st, env, i, i < st.count ? i : -1, r);
     if (i == 0 && S.road_steps) S.road_steps[env] = st.road_steps;
+}
+
+// work list of the envs to reset: list[0] = how many, list[1..] = env ids (any order)
+__global__ void compact_envs_kernel(const uint8_t* __restrict__ mask_a, const uint8_t* __restrict__ mask_b, int n_envs,
+                                    int* __restrict__ list) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool sel = e < n_envs && ((!mask_a && !mask_b) || (mask_a && mask_a[e]) || (mask_b && mask_b[e]));
+    const unsigned m = __ballot_sync(0xffffffffu, sel);
+    if (!m) return;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd(&list[0], __popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (sel) list[1 + base + __popc(m & ((1u << lane) - 1u))] = e;
+}
+
+// IntersectionEnv._make_vehicles (envs/intersection_env.py:245-323) for the listed envs, one 32-slot group each:
+// n-1 _spawn_vehicle draws along the access roads, the 3 s warm-up simulation, the straight-going challenger, the
+// controlled vehicle, and the 20 m pruning around it; then the fresh observation.  Dense over the work list: block
+// b serves entries [8b, 8b+8) and leaves as a whole when there are none.
+template <int G, bool REG>
+__global__ void __launch_bounds__(kBlockThreads)
+intersection_reset_kernel(const HwyNetParams P, const HwyNetGraph* __restrict__ graph, const HwyNetState S,
+                          const HwyIntersectionSpawn SP, const int* __restrict__ list, float* __restrict__ obs) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    GraphShared& g = *reinterpret_cast<GraphShared*>(smem_raw);
+    EnvStage<G, REG>* stages =
+        reinterpret_cast<EnvStage<G, REG>*>(smem_raw + ((sizeof(GraphShared) + 15) & ~size_t(15)));
+    constexpr int kEnvs = kBlockThreads / G;
+    const int n_sel = list[0];
+    if (blockIdx.x * kEnvs >= n_sel) return;  // uniform per block
+    stage_graph(g, graph);
+    const int sub = threadIdx.x / G, i = threadIdx.x % G;
+    const int idx = blockIdx.x * kEnvs + sub;
+    const bool selected = idx < n_sel;  // the others ride along on the last entry and store nothing
+    const int e = list[1 + (selected ? idx : n_sel - 1)];
+    EnvStage<G, REG>& st = stages[sub];
+
+    Regs r = {};
+    st.x[i] = st.y[i] = st.heading[i] = st.s[i] = st.v[i] = st.ts[i] = 0.0;
+    st.c[i] = 1.0;
+    st.lane[i] = st.tgt[i] = st.tgt_prev[i] = 0;
+    st.kind[i] = HWY_KIND_IDM;
+    st.route_len[i] = 0;
+    st.own_s[i] = st.own_lat[i] = 0.0;
+    Pcg64 rng;
+    if (i == 0) {
+        st.count = 0;
+        st.ego = 0;
+        st.speed_index = 0;
+        st.road_steps = 0;
+        st.sp_ok = 0;
+        rng = load_rng(S.rng, (size_t)S.n_envs, e);
+    }
+    group_sync<G>();
+    auto commit = [&](int kind) {  // the spawn record (if accepted) becomes vehicle number `count`
+        group_sync<G>();
+        if (st.sp_ok && i == st.count) adopt_spawn(P, SP, g, st, i, r, kind);
+        group_sync<G>();
+        if (i == 0 && st.sp_ok) st.count += 1;
+        group_sync<G>();
+    };
+    // ---- :266-270  n_vehicles - 1 draws at np.linspace(0, 80, n_vehicles)[t]
+    const int n0 = SP.initial_vehicle_count;
+    for (int t = 0; t < n0 - 1; ++t) {
+        if (i == 0) {
+            const unsigned present = st.count >= 32 ? 0xffffffffu : ((1u << st.count) - 1u);
+            spawn_vehicle(P, SP, g, st, rng, present, (double)t * (80.0 / (double)(n0 - 1)), 1.0, 1.0,
+                          SP.spawn_probability, false);
+            if (st.count >= G) st.sp_ok = 0;
+        }
+        commit(HWY_KIND_IDM);
+    }
+    // ---- :271-278  3 s of simulation under the RegulatedRoad rules
+    const double dt = 1.0 / P.simulation_frequency;
+    double act_accel = 0.0;
+    for (int k = 0; k < 3 * P.simulation_frequency; ++k) substep(P, g, st, i, r, act_accel, dt, -1);
+    group_sync<G>();
+    // ---- :281-288  the challenger: certain, going straight, tight deviations
+    if (i == 0) {
+        const unsigned present = st.count >= 32 ? 0xffffffffu : ((1u << st.count) - 1u);
+        spawn_vehicle(P, SP, g, st, rng, present, 60.0, 0.1, 0.0, 1.0, true);
+        if (st.count >= G) st.sp_ok = 0;
+    }
+    commit(HWY_KIND_IDM);
+    // ---- :291-315  the controlled vehicle on ("o0", "ir0", 0)
+    if (i == 0) {
+        const int dest = SP.ego_destination >= 0 ? SP.ego_destination : 1 + rng.choice(3);  // "o" + integers(1, 4)
+        const HwyNetLane& EL = g.lanes[SP.ego_lane];
+        const double lon = 60.0 + 5.0 * (1.0 + 1.0 * rng.normal());  // 60 + 5 * np_random.normal(1)
+        lane_position(EL, lon, 0.0, st.sp_x, st.sp_y);
+        st.sp_h = lane_heading_at(EL, 60.0);
+        st.sp_speed = EL.speed_limit;
+        int cl = 0;
+        double bd = 0;
+        for (int l = 0; l < g.n_lanes; ++l) {
+            double d = lane_distance_with_heading(g.lanes[l], st.sp_x, st.sp_y, st.sp_h);
+            if (l == 0 || d < bd) {
+                bd = d;
+                cl = l;
+            }
+        }
+        st.sp_lane = cl;
+        st.sp_dest = dest;
+        st.speed_index = speed_to_index(P, st.sp_speed);  // MDPVehicle.__init__ (controller.py:283-293)
+        st.sp_ts = P.target_speeds[st.speed_index];
+        st.sp_ok = st.count < G ? 1 : 0;
+        st.ego = st.count;
+    }
+    commit(HWY_KIND_MDP);
+    // ---- :317-323  drop the traffic within 20 m of the controlled vehicle
+    const int V = st.count, ego = st.ego;
+    bool keep = i < V;
+    if (keep && i != ego && norm2(st.x[i] - st.x[ego], st.y[i] - st.y[ego]) < 20) keep = false;
+    const unsigned keep_mask = __ballot_sync(group_mask<G>(), keep) >> ((threadIdx.x & 31) & ~(G - 1));
+    const int dst = keep ? __popc(keep_mask & ((1u << i) - 1u)) : -1;
+    if (!selected) return;  // no block-wide barrier below this line
+    store_env(S, st, e, i, dst, r);
+    if (i == 0) {
+        S.count[e] = __popc(keep_mask);
+        S.road_steps[e] = st.road_steps;
+        S.speed_index[e] = st.speed_index;
+        S.time[e] = 0.0;
+        store_rng(S.rng, (size_t)S.n_envs, e, rng);
+    }
+    if (!obs) return;
+    group_sync<G>();  // the stored state is re-read by other threads of the group
+    load_env(P, g, S, st, e, i, r);
+    observe_any(P, g, st, st.count, i, obs + (size_t)e * obs_size(P));
 }
 
 // RoundaboutEnv._make_vehicles (envs/roundabout_env.py:317-391), one env per thread (the draws
@@ -1536,6 +1673,31 @@ int hwy_intersection_step(const HwyNetParams* p, const HwyNetGraph* graph, const
     HwyIntersectionSpawn none = {};
     return launch_step<HWY_NET_GROUP_LARGE, true>(p, graph, spawn ? *spawn : none, s, action, obs, reward, terminated,
                                                   truncated, info_speed, info_crashed, (cudaStream_t)stream);
+}
+
+int hwy_intersection_reset(const HwyNetParams* p, const HwyNetGraph* graph, const HwyIntersectionSpawn* spawn,
+                           const HwyNetState* s, const uint8_t* mask_a, const uint8_t* mask_b, float* obs,
+                           float* final_obs, void* stream) {
+    if (validate_net(p, graph, s)) return 1;
+    if (s->vp != HWY_NET_GROUP_LARGE) return fail("%s", "hwy_intersection_reset expects slot stride 32");
+    if (!spawn || !spawn->route_table || !spawn->route_len || !spawn->scratch || !s->rng)
+        return fail("%s", "reset needs the spawn tables, the scratch list and the rng words");
+    if (spawn->initial_vehicle_count < 1 || spawn->initial_vehicle_count > HWY_NET_GROUP_LARGE - 2)
+        return fail("%s", "initial_vehicle_count out of range");
+    if (final_obs && !obs) return fail("%s", "final_obs without obs");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(spawn->scratch, 0, sizeof(int), st);
+    hwynet::compact_envs_kernel<<<(s->n_envs + 255) / 256, 256, 0, st>>>(mask_a, mask_b, s->n_envs, spawn->scratch);
+    if (final_obs)
+        cudaMemcpyAsync(final_obs, obs, (size_t)s->n_envs * hwy_network_obs_size(p) * sizeof(float),
+                        cudaMemcpyDeviceToDevice, st);
+    const size_t smem = net_smem_bytes<HWY_NET_GROUP_LARGE, true>();
+    if (configure_smem(hwynet::intersection_reset_kernel<HWY_NET_GROUP_LARGE, true>, smem)) return 1;
+    hwynet::intersection_reset_kernel<HWY_NET_GROUP_LARGE, true>
+        <<<blocks_for(s->n_envs, HWY_NET_GROUP_LARGE), hwynet::kBlockThreads, smem, st>>>(*p, graph, *s, *spawn,
+                                                                                         spawn->scratch, obs);
+    if (check_launch("compact_envs_kernel")) return 1;
+    return check_launch("intersection_reset_kernel");
 }
 
 int hwy_network_substeps(const HwyNetParams* p, const HwyNetGraph* graph, const HwyNetState* s, const uint8_t* mask,

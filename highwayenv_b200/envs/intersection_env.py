@@ -6,10 +6,17 @@ changes every step (``_clear_vehicles`` / ``_spawn_vehicle``), Kinematics (7 fea
 OccupancyGrid observation, 3 longitudinal meta-actions.
 
 Stepping — including the RegulatedRoad rules and the per-step clear/spawn with the env's numpy
-stream — runs in ``hwy_intersection_step``.  ``reset`` replays ``_make_vehicles``
-(:245-323) on the host with numpy generators (bit-identical draws) and runs its 3 s warm-up
-simulation on the device (``hwy_network_substeps``); the generator state is then handed to the
-device for the per-step spawns.  SameStep autoreset goes through that host path.
+stream — runs in ``hwy_intersection_step``.  ``reset`` has two implementations of
+``_make_vehicles`` (:245-323):
+
+* ``reset_mode="device"`` (default): ``hwy_intersection_reset`` — draws, warm-up simulation,
+  challenger, controlled vehicle and pruning in one kernel over the envs that finished; this is
+  what the SameStep autoreset uses, so a step never leaves the GPU.
+* ``reset_mode="host"``: the same sequence with numpy generators on the host (bit-identical to
+  the reference's draws and lane arithmetic) and only the 3 s warm-up on the device
+  (``hwy_network_substeps``); used by the parity tests against the reference's reset states.
+
+Both consume the env's PCG64 stream identically (checked word for word in the tests).
 """
 from __future__ import annotations
 
@@ -72,13 +79,17 @@ class BatchedIntersectionEnv:
         return default_config(cls.ENV_ID)
 
     def __init__(self, config: Optional[dict] = None, render_mode: Optional[str] = None, num_envs: int = 1,
-                 device: Any = None, autoreset_mode: str = "SameStep", env_index_offset: int = 0) -> None:
+                 device: Any = None, autoreset_mode: str = "SameStep", env_index_offset: int = 0,
+                 reset_mode: str = "device") -> None:
         if render_mode is not None:
             raise NotImplementedError("rendering is out of scope of the accelerated path")
         if not torch.cuda.is_available():
             raise RuntimeError("highwayenv_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         if autoreset_mode not in ("SameStep", "Disabled"):
             raise NotImplementedError(autoreset_mode)
+        if reset_mode not in ("device", "host"):
+            raise ValueError(reset_mode)
+        self.reset_mode = reset_mode
         self._lib = N.load()
         self.render_mode = None
         self.num_envs = int(num_envs)
@@ -219,6 +230,14 @@ class BatchedIntersectionEnv:
             sp.spawn_lane[k] = self.net.index[("o" + str(k), "ir" + str(k), 0)]
         sp.spawn_probability = float(self.config["spawn_probability"])
         sp.route_table, sp.route_len = self._route_table.data_ptr(), self._route_table_len.data_ptr()
+        sp.ego_lane = self.net.index[("o0", "ir0", 0)]
+        dest = self.config["destination"]
+        if dest is not None and (not isinstance(dest, str) or dest not in ("o0", "o1", "o2", "o3")):
+            raise ValueError(f"destination {dest!r}")
+        sp.ego_destination = -1 if dest is None else int(dest[1:])
+        sp.initial_vehicle_count = int(self.config["initial_vehicle_count"])
+        self._scratch = z(n + 1, dtype=torch.int32)
+        sp.scratch = self._scratch.data_ptr()
         self._spawn_struct = sp
 
     def _stream(self) -> int:
@@ -378,6 +397,12 @@ class BatchedIntersectionEnv:
         sd["rng"] = words
         self.load_state_dict(sd, ids)
 
+    def _device_reset(self, mask_a, mask_b, obs_ptr, final_obs_ptr) -> None:
+        with torch.cuda.device(self.device):
+            N.check(self._lib.hwy_intersection_reset(
+                C.byref(self._params), self._graph_dev.data_ptr(), C.byref(self._spawn_struct), C.byref(self._state),
+                mask_a, mask_b, obs_ptr, final_obs_ptr, self._stream()))
+
     def _sync_host_rngs(self, ids) -> None:
         """The device advanced the streams (per-step spawns): mirror them into the host generators."""
         words = self._rng.cpu().numpy().view(np.uint64)
@@ -400,7 +425,14 @@ class BatchedIntersectionEnv:
             seeds = [int(s) for s in seed]
         self._rngs = [np.random.Generator(np.random.PCG64(np.random.SeedSequence(s))) for s in seeds]
         self.np_random_seed = seeds
-        self._fresh = True
+        if self.reset_mode == "device":
+            words = np.zeros((5, n), dtype=np.uint64)
+            m64 = (1 << 64) - 1
+            for i, g in enumerate(self._rngs):
+                st = g.bit_generator.state
+                sv, inc = st["state"]["state"], st["state"]["inc"]
+                words[:, i] = (sv >> 64, sv & m64, inc >> 64, inc & m64, (int(st["has_uint32"]) << 32) | int(st["uinteger"]))
+            self._rng.copy_(torch.from_numpy(words.view(np.int64)).to(self.device))
 
     # ------------------------------------------------------------------ gym API
     def reset(self, *, seed=None, options: Optional[dict] = None):
@@ -411,13 +443,18 @@ class BatchedIntersectionEnv:
         fresh = seed is not None or self._rngs is None or any(g is None for g in self._rngs)
         if fresh:
             self._seed_streams(seed)
-        ids = np.arange(self.num_envs)
+        mask = None
         if options and options.get("reset_mask") is not None:
-            ids = np.nonzero(np.asarray(options["reset_mask"]))[0]
-        if not fresh:
-            self._sync_host_rngs(ids)
-        if len(ids):
-            self._reset_envs(ids)
+            mask = np.asarray(options["reset_mask"]).astype(bool)
+        if self.reset_mode == "device":
+            mt = None if mask is None else torch.from_numpy(mask.astype(np.uint8)).to(self.device)
+            self._device_reset(None if mt is None else mt.data_ptr(), None, None, None)
+        else:
+            ids = np.arange(self.num_envs) if mask is None else np.nonzero(mask)[0]
+            if not fresh:
+                self._sync_host_rngs(ids)
+            if len(ids):
+                self._reset_envs(ids)
         self.observe()
         return self._obs, {"speed": self._info_speed, "crashed": self._info_crashed.view(torch.bool)}
 
@@ -444,7 +481,11 @@ class BatchedIntersectionEnv:
                 act.data_ptr(), self._obs.data_ptr(), self._reward.data_ptr(), self._terminated.data_ptr(),
                 self._truncated.data_ptr(), self._info_speed.data_ptr(), self._info_crashed.data_ptr(), self._stream()))
         info = {"speed": self._info_speed, "crashed": self._info_crashed.view(torch.bool), "action": act}
-        if self.autoreset_mode == "SameStep":
+        if self.autoreset_mode == "SameStep" and self.reset_mode == "device":
+            info["final_obs"] = self._final_obs
+            self._device_reset(self._terminated.data_ptr(), self._truncated.data_ptr(), self._obs.data_ptr(),
+                               self._final_obs.data_ptr())
+        elif self.autoreset_mode == "SameStep":
             done = (self._terminated | self._truncated).cpu().numpy().astype(bool)
             if done.any():
                 self._final_obs.copy_(self._obs)

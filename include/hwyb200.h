@@ -244,6 +244,12 @@ typedef struct HwyIntersectionSpawn {
     double spawn_probability;   /* config["spawn_probability"] */
     const int32_t *route_table; /* DEVICE [n_lanes][4][HWY_NET_MAX_ROUTE]: plan_route_to(lane, "o"+k) */
     const int32_t *route_len;   /* DEVICE [n_lanes][4] */
+    /* _make_vehicles (:245-323), used by hwy_intersection_reset */
+    int32_t ego_lane;              /* table index of ("o0", "ir0", 0) */
+    int32_t ego_destination;       /* k of config["destination"] == "o"+k; -1 (None): "o" + integers(1, 4) */
+    int32_t initial_vehicle_count; /* config["initial_vehicle_count"] */
+    int32_t _pad;
+    int32_t *scratch;              /* DEVICE [n_envs + 1] int32: work list of the envs being reset */
 } HwyIntersectionSpawn;
 
 /* observation size in floats: Kinematics K*5, TimeToCollision 3*3*(horizon*policy_frequency) */
@@ -262,6 +268,15 @@ int hwy_intersection_step(const HwyNetParams *p, const HwyNetGraph *graph, const
                           const HwyNetState *s, const int32_t *action, float *obs, double *reward,
                           uint8_t *terminated, uint8_t *truncated, double *info_speed,
                           uint8_t *info_crashed, void *stream);
+
+/* IntersectionEnv._reset / _make_vehicles (envs/intersection_env.py:119-122,245-323) on the device for the
+ * envs with mask_a[e] | mask_b[e] (both NULL: every env): n-1 _spawn_vehicle draws, 3 s of warm-up simulation,
+ * the challenger, the controlled vehicle (MDPVehicle on ("o0","ir0",0) at 60 + 5*normal(1)), the 20 m pruning;
+ * all draws come from s->rng in the reference's order.  With final_obs, obs is first copied there (the
+ * SameStep autoreset's info["final_obs"]); the fresh observation of the reset envs is written to obs. */
+int hwy_intersection_reset(const HwyNetParams *p, const HwyNetGraph *graph, const HwyIntersectionSpawn *spawn,
+                           const HwyNetState *s, const uint8_t *mask_a, const uint8_t *mask_b, float *obs,
+                           float *final_obs, void *stream);
 
 /* Road.act() + Road.step(dt) n_substeps times without an ego action, for the envs whose mask byte is
  * set (NULL: all): the 3 s warm-up of IntersectionEnv._make_vehicles (:271-278). */

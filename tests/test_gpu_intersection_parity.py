@@ -59,7 +59,7 @@ def test_reset_matches_reference(name):
     """host numpy spawns + 45 warm-up substeps on the device + challenger / ego / pruning"""
     g = load_golden(name)
     S = len(g["seeds"])
-    env = make_env(g["config"], S, autoreset_mode="Disabled")
+    env = make_env(g["config"], S, autoreset_mode="Disabled", reset_mode="host")
     obs, _ = env.reset(seed=[int(s) for s in g["seeds"]])
     sd = env.state_dict()
     for i in range(S):
@@ -92,7 +92,7 @@ def test_teacher_forced_vs_reference(name):
 def test_teacher_forced_vs_oracle_many_envs(name, n, T):
     g = load_golden(name)
     ob = no.IntersectionOracle(no.graph_from_arrays(g), no.cfg_from_dict(g["config"]), n, g, g["config"])
-    env = make_env(g["config"], n, autoreset_mode="Disabled")
+    env = make_env(g["config"], n, autoreset_mode="Disabled", reset_mode="host")
     env.reset(seed=4200)
     for e in range(n):
         ob.reset_env(e, seed=4200 + e)
@@ -147,3 +147,54 @@ def test_free_running_rollout_and_autoreset():
         if done.any():
             assert "final_obs" in info
     assert resets >= n
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_device_reset_matches_host_reset(name):
+    """hwy_intersection_reset (all of _make_vehicles in one kernel) against the numpy-exact host sequence:
+    the same draws word for word, the same population, lanes and routes; coordinates within the rounding
+    of CUDA-vs-numpy sin/cos carried through the 45 warm-up substeps."""
+    g = load_golden(name)
+    n = 192
+    dev_env = make_env(g["config"], n, autoreset_mode="Disabled", reset_mode="device")
+    host_env = make_env(g["config"], n, autoreset_mode="Disabled", reset_mode="host")
+    o_d, _ = dev_env.reset(seed=900)
+    o_h, _ = host_env.reset(seed=900)
+    a, b = dev_env.state_dict(), host_env.state_dict()
+    assert np.array_equal(a["rng"], b["rng"])
+    assert np.array_equal(a["count"], b["count"])
+    live = np.arange(V)[None, :] < a["count"][:, None]
+    for k in ("lane", "target_lane", "kind", "route_len", "is_yielding", "crashed"):
+        assert np.array_equal(np.where(live, a[k], 0), np.where(live, b[k], 0)), k
+    assert np.array_equal(a["speed_index"], b["speed_index"]) and np.array_equal(a["road_steps"], b["road_steps"])
+    for k in ("x", "y", "heading", "speed", "target_speed", "timer", "delta"):
+        assert np.max(np.abs(np.where(live, a[k] - b[k], 0.0))) <= 1e-7, k
+    assert np.max(np.abs(o_d.cpu().numpy() - o_h.cpu().numpy())) <= 1e-6
+    # reference reset states: the device path reproduces the golden resets as well
+    S = len(g["seeds"])
+    env = make_env(g["config"], S, autoreset_mode="Disabled")
+    obs, _ = env.reset(seed=[int(s) for s in g["seeds"]])
+    sd = env.state_dict()
+    for i in range(S):
+        compare_inter(inter_state(g, i, 0), oracle_view(sd), i, f"{name} device reset#{i}", tol=1e-7)
+        assert np.array_equal(sd["rng"][:, i], g["rng_words"][i, 0]), i
+    assert np.max(np.abs(obs.cpu().numpy() - g["obs"][:, 0])) <= 1e-6
+
+
+def test_device_autoreset_masks_only_finished_envs():
+    g = load_golden("intersection_kin")
+    n = 64
+    env = make_env(g["config"], n)
+    env.reset(seed=21)
+    rng = np.random.default_rng(5)
+    for t in range(20):
+        before = env.state_dict()
+        obs, rew, term, trunc, info = env.step(rng.integers(0, 3, size=n).astype(np.int32))
+        done = (term | trunc).cpu().numpy()
+        sd = env.state_dict()
+        assert np.all(sd["time"][done] == 0) and np.all(sd["time"][~done] > 0)
+        assert np.all(sd["road_steps"][done] == 45)
+        # envs that go on keep their own generator stream: one step consumes at most a few draws,
+        # a reset consumes dozens — and the inc half of the state never changes
+        assert np.array_equal(sd["rng"][2:4], before["rng"][2:4])
+        assert np.array_equal(info["final_obs"].cpu().numpy()[~done], obs.cpu().numpy()[~done])
