@@ -238,7 +238,7 @@ def run_gpu_arm(args) -> None:
     # ---- e2e through the public API with host buffers
     h_actions = torch.empty(E, dtype=torch.int32).pin_memory()
     host_pool = torch.randint(0, 5, (K, E), dtype=torch.int32)
-    h_obs = torch.empty((E, env.K, 5), dtype=torch.float32).pin_memory()
+    h_obs = torch.empty(tuple(env._obs.shape), dtype=torch.float32).pin_memory()
     h_rew = torch.empty(E, dtype=torch.float64).pin_memory()
     h_term = torch.empty(E, dtype=torch.bool).pin_memory()
     h_trunc = torch.empty(E, dtype=torch.bool).pin_memory()

@@ -31,6 +31,11 @@ class HwyStraightLane(C.Structure):
         "speed_limit")]
 
 
+HWY_MAX_OBS_FEATURES = 16
+FEATURE_CODES = {"presence": 0, "x": 1, "y": 2, "vx": 3, "vy": 4, "heading": 5, "cos_h": 6, "sin_h": 7,
+                 "cos_d": 8, "sin_d": 9, "long_off": 10, "lat_off": 11, "ang_off": 12}
+
+
 class HwyHighwayParams(C.Structure):
     _fields_ = (
         [(n, C.c_int32) for n in (
@@ -47,6 +52,9 @@ class HwyHighwayParams(C.Structure):
             "lane_change_min_acc_gain", "lane_change_max_braking_imposed", "lane_change_delay",
             "delta_lo", "delta_hi", "perception_distance")]
         + [("lanes", HwyStraightLane * HWY_MAX_LANES)]
+        + [("obs_n_features", C.c_int32), ("_pad_obs", C.c_int32),
+           ("obs_feature", C.c_int32 * HWY_MAX_OBS_FEATURES), ("obs_feature_ranged", C.c_int32 * HWY_MAX_OBS_FEATURES),
+           ("obs_feature_lo", C.c_double * HWY_MAX_OBS_FEATURES), ("obs_feature_hi", C.c_double * HWY_MAX_OBS_FEATURES)]
     )
 
 

@@ -208,9 +208,47 @@ __device__ __forceinline__ double idm_acceleration_of(const HwyHighwayParams& P,
 // ------------------------------------------------------------------ observation
 // envs/common/observation.py:234-276 KinematicObservation.observe (presence,x,y,vx,vy; order
 // "sorted") with road/road.py:421-450 close_objects_to and kinematics.py:237-261 to_dict.
+__device__ __forceinline__ int obs_columns(const HwyHighwayParams& P) {
+    return P.obs_n_features > 0 ? P.obs_n_features : 5;
+}
+
+// One observation row with a configured feature list (Vehicle.to_dict, vehicle/kinematics.py:237-261;
+// normalize_obs, observation.py:207-232).  Out of line: the default five columns never come here.
+__device__ __noinline__ void kinematics_row_features(const HwyHighwayParams& P, int lane, double x, double y,
+                                                     double heading, double c, double s, double dx, double dy,
+                                                     double dvx, double dvy, float* __restrict__ o,
+                                                     float* __restrict__ o2) {
+    const HwyStraightLane L = P.lanes[lane];
+    double lon, lat;
+    lane_local(L, x, y, lon, lat);  // Vehicle.lane_offset :228-235
+    for (int col = 0; col < P.obs_n_features; ++col) {
+        double v = 0.0;
+        switch (P.obs_feature[col]) {
+            case HWY_FEAT_PRESENCE: v = 1.0; break;
+            case HWY_FEAT_X: v = dx; break;
+            case HWY_FEAT_Y: v = dy; break;
+            case HWY_FEAT_VX: v = dvx; break;
+            case HWY_FEAT_VY: v = dvy; break;
+            case HWY_FEAT_HEADING: v = heading; break;
+            case HWY_FEAT_COS_H: v = c; break;
+            case HWY_FEAT_SIN_H: v = s; break;
+            case HWY_FEAT_LONG_OFF: v = lon; break;
+            case HWY_FEAT_LAT_OFF: v = lat; break;
+            case HWY_FEAT_ANG_OFF: v = wrap_to_pi(heading - L.heading); break;  // lane.local_angle (lane.py:145-147)
+            default: v = 0.0; break;  // cos_d / sin_d: no route on this road family => destination == position
+        }
+        if (P.obs_normalize && P.obs_feature_ranged[col]) {
+            v = lmap(v, P.obs_feature_lo[col], P.obs_feature_hi[col], -1.0, 1.0);
+            if (P.obs_clip) v = clipd(v, -1.0, 1.0);
+        }
+        o[col] = (float)v;
+        if (o2) o2[col] = (float)v;
+    }
+}
+
 template <int TPE>
 __device__ __forceinline__ void kinematics_observe(const HwyHighwayParams& P, const Frame<TPE>& F,
-                                                   double* key_scratch, int i,
+                                                   double* key_scratch, int i, double heading,
                                                    float* __restrict__ obs_env,
                                                    float* __restrict__ obs_env2 = nullptr) {
     const int V = P.n_vehicles, K = P.obs_vehicles_count;
@@ -255,7 +293,11 @@ __device__ __forceinline__ void kinematics_observe(const HwyHighwayParams& P, co
             r4 -= evy;
         }
     }
-    if (row >= 0) {
+    const int NF = obs_columns(P);
+    if (row >= 0 && P.obs_n_features > 0) {
+        kinematics_row_features(P, F.lane[i], F.x[i], F.y[i], heading, F.c[i], F.s[i], r1, r2, r3, r4,
+                                obs_env + NF * row, obs_env2 ? obs_env2 + NF * row : nullptr);
+    } else if (row >= 0) {
         if (P.obs_normalize) {  // normalize_obs :207-232
             r1 = lmap(r1, -xr, xr, -1.0, 1.0);
             r2 = lmap(r2, -yr, yr, -1.0, 1.0);
@@ -285,11 +327,9 @@ __device__ __forceinline__ void kinematics_observe(const HwyHighwayParams& P, co
     }
     int filled = 1 + (n_valid < K - 1 ? n_valid : K - 1);  // zero padding of missing rows
     if (i < K && i >= filled) {
-        float* o = obs_env + 5 * i;
-        o[0] = o[1] = o[2] = o[3] = o[4] = 0.0f;
-        if (obs_env2) {
-            o = obs_env2 + 5 * i;
-            o[0] = o[1] = o[2] = o[3] = o[4] = 0.0f;
+        for (int col = 0; col < NF; ++col) {
+            obs_env[NF * i + col] = 0.0f;
+            if (obs_env2) obs_env2[NF * i + col] = 0.0f;
         }
     }
 }
@@ -756,7 +796,7 @@ constexpr int kMaxBlockThreads = 512;  // 128 registers/thread => one full regis
 // blockDim.x = TPE * (envs per block); dynamic shared memory = envs per block * sizeof(EnvShared).
 template <int TPE>
 __global__ void __launch_bounds__(kMaxBlockThreads, 1)
-highway_step_kernel(const HwyHighwayParams P, const HwyHighwayState S,
+highway_step_kernel(const __grid_constant__ HwyHighwayParams P, const HwyHighwayState S,
                     const int32_t* __restrict__ action_i, const float* __restrict__ action_f,
                     float* __restrict__ obs, double* __restrict__ reward,
                     uint8_t* __restrict__ terminated, uint8_t* __restrict__ truncated,
@@ -1076,10 +1116,11 @@ highway_step_kernel(const HwyHighwayParams P, const HwyHighwayState S,
     PHASE_MARK(11);
     // ---- epilogue: state back to HBM, observation, reward, termination
     const Frame<TPE>& F = sm.f[p];
-    const size_t obs_off = (size_t)e * P.obs_vehicles_count * 5;
+    const size_t obs_off = (size_t)e * P.obs_vehicles_count * obs_columns(P);
     float* obs_env = obs + obs_off;
     if (env_ok)
-        kinematics_observe(P, F, sm.key, i, obs_env, (autoreset && final_obs) ? final_obs + obs_off : nullptr);
+        kinematics_observe(P, F, sm.key, i, r.heading, obs_env,
+                           (autoreset && final_obs) ? final_obs + obs_off : nullptr);
     else
         env_sync<TPE>();
     if (i == 0) {
@@ -1127,7 +1168,7 @@ highway_step_kernel(const HwyHighwayParams P, const HwyHighwayState S,
         if (do_reset) publish(P, G, i, active, r);
         env_sync<TPE>();
         if (do_reset) {
-            kinematics_observe(P, G, sm.key, i, obs_env);
+            kinematics_observe(P, G, sm.key, i, r.heading, obs_env);
             if (i == 0) {
                 S.time[e] = 0.0;
                 S.speed_index[e] = speed_index;
@@ -1150,7 +1191,7 @@ struct ObsShared {
 
 template <int TPE>
 __global__ void __launch_bounds__(TPE == 32 ? 128 : TPE)
-highway_observe_kernel(const HwyHighwayParams P, const HwyHighwayState S,
+highway_observe_kernel(const __grid_constant__ HwyHighwayParams P, const HwyHighwayState S,
                        const uint8_t* __restrict__ mask_a, const uint8_t* __restrict__ mask_b,
                        int use_mask, float* __restrict__ obs) {
     constexpr int EPB = TPE == 32 ? 4 : 1;
@@ -1167,7 +1208,7 @@ highway_observe_kernel(const HwyHighwayParams P, const HwyHighwayState S,
     env_sync<TPE>();
     const bool wanted = env_ok && (!use_mask || (mask_a && mask_a[e]) || (mask_b && mask_b[e]));
     if (wanted)
-        kinematics_observe(P, sm.f, sm.key, i, obs + (size_t)e * P.obs_vehicles_count * 5);
+        kinematics_observe(P, sm.f, sm.key, i, r.heading, obs + (size_t)e * P.obs_vehicles_count * obs_columns(P));
     else
         env_sync<TPE>();
 }
@@ -1178,7 +1219,7 @@ highway_observe_kernel(const HwyHighwayParams P, const HwyHighwayState S,
 // randomize_behavior (behavior.py:64-69), MDPVehicle.__init__ (controller.py:284-293).
 // The spawn is a sequential chain on the env's PCG64 stream => one thread per env.
 __global__ void __launch_bounds__(128)
-highway_reset_kernel(const HwyHighwayParams P, const HwyHighwayState S,
+highway_reset_kernel(const __grid_constant__ HwyHighwayParams P, const HwyHighwayState S,
                      const uint8_t* __restrict__ mask_a, const uint8_t* __restrict__ mask_b,
                      int use_mask) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1304,6 +1345,11 @@ int validate(const HwyHighwayParams* p, const HwyHighwayState* s) {
     if (p->lanes_count < 1 || p->lanes_count > HWY_MAX_LANES) return fail("%s", "lanes_count out of range");
     if (p->obs_vehicles_count < 1 || p->obs_vehicles_count > HWY_MAX_OBS_VEHICLES)
         return fail("%s", "obs_vehicles_count out of range");
+    if (p->obs_n_features < 0 || p->obs_n_features > HWY_MAX_OBS_FEATURES)
+        return fail("%s", "obs_n_features out of range");
+    for (int c = 0; c < p->obs_n_features; ++c)
+        if (p->obs_feature[c] < HWY_FEAT_PRESENCE || p->obs_feature[c] > HWY_FEAT_ANG_OFF)
+            return fail("%s", "unknown observation feature code");
     if (p->n_target_speeds < 1 || p->n_target_speeds > HWY_MAX_TARGET_SPEEDS)
         return fail("%s", "n_target_speeds out of range");
     if (p->simulation_frequency < 1 || p->policy_frequency < 1 ||

@@ -1197,8 +1197,8 @@ __device__ __forceinline__ void store_rng(uint64_t* rng, size_t n, int e, const 
 // ------------------------------------------------------------------ the step kernel
 template <int G, bool REG>
 __global__ void __launch_bounds__(kBlockThreads)
-network_step_kernel(const HwyNetParams P, const HwyNetGraph* __restrict__ graph, const HwyNetState S,
-                    const HwyIntersectionSpawn SP, const int32_t* __restrict__ action, float* __restrict__ obs,
+network_step_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGraph* __restrict__ graph, const __grid_constant__ HwyNetState S,
+                    const __grid_constant__ HwyIntersectionSpawn SP, const int32_t* __restrict__ action, float* __restrict__ obs,
                     double* __restrict__ reward, uint8_t* __restrict__ terminated,
                     uint8_t* __restrict__ truncated, double* __restrict__ info_speed,
                     uint8_t* __restrict__ info_crashed) {
@@ -1307,7 +1307,7 @@ network_step_kernel(const HwyNetParams P, const HwyNetGraph* __restrict__ graph,
 
 template <int G, bool REG>
 __global__ void __launch_bounds__(kBlockThreads)
-network_observe_kernel(const HwyNetParams P, const HwyNetGraph* __restrict__ graph, const HwyNetState S,
+network_observe_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGraph* __restrict__ graph, const __grid_constant__ HwyNetState S,
                        const uint8_t* __restrict__ mask_a, const uint8_t* __restrict__ mask_b,
                        float* __restrict__ obs) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1331,7 +1331,7 @@ network_observe_kernel(const HwyNetParams P, const HwyNetGraph* __restrict__ gra
 // Road.act + Road.step `n_substeps` times with no ego action (IntersectionEnv._make_vehicles warm-up)
 template <int G, bool REG>
 __global__ void __launch_bounds__(kBlockThreads)
-network_substeps_kernel(const HwyNetParams P, const HwyNetGraph* __restrict__ graph, const HwyNetState S,
+network_substeps_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGraph* __restrict__ graph, const __grid_constant__ HwyNetState S,
                         const uint8_t* __restrict__ mask, int n_substeps) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     GraphShared& g = *reinterpret_cast<GraphShared*>(smem_raw);
@@ -1378,8 +1378,8 @@ __global__ void compact_envs_kernel(const uint8_t* __restrict__ mask_a, const ui
 // b serves entries [8b, 8b+8) and leaves as a whole when there are none.
 template <int G, bool REG>
 __global__ void __launch_bounds__(kBlockThreads)
-intersection_reset_kernel(const HwyNetParams P, const HwyNetGraph* __restrict__ graph, const HwyNetState S,
-                          const HwyIntersectionSpawn SP, const int* __restrict__ list, float* __restrict__ obs) {
+intersection_reset_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGraph* __restrict__ graph, const __grid_constant__ HwyNetState S,
+                          const __grid_constant__ HwyIntersectionSpawn SP, const int* __restrict__ list, float* __restrict__ obs) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     GraphShared& g = *reinterpret_cast<GraphShared*>(smem_raw);
     EnvStage<G, REG>* stages =
@@ -1490,8 +1490,8 @@ intersection_reset_kernel(const HwyNetParams P, const HwyNetGraph* __restrict__ 
 // RoundaboutEnv._make_vehicles (envs/roundabout_env.py:317-391), one env per thread (the draws
 // are a sequential chain on the env's numpy stream).
 __global__ void __launch_bounds__(128)
-roundabout_reset_kernel(const HwyNetParams P, const HwyNetGraph* __restrict__ graph, const HwyRoundaboutSpawn SP,
-                        const HwyNetState S, uint64_t* __restrict__ rng, const uint8_t* __restrict__ mask_a,
+roundabout_reset_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGraph* __restrict__ graph, const __grid_constant__ HwyRoundaboutSpawn SP,
+                        const __grid_constant__ HwyNetState S, uint64_t* __restrict__ rng, const uint8_t* __restrict__ mask_a,
                         const uint8_t* __restrict__ mask_b) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= S.n_envs) return;

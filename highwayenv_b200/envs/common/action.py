@@ -8,6 +8,8 @@ device in the first substep of ``hwy_highway_step``.
 """
 from __future__ import annotations
 
+import itertools
+
 import numpy as np
 
 from ... import _native as N
@@ -100,9 +102,29 @@ class ContinuousAction(ActionType):
         p.steer_lo, p.steer_hi = float(self.steering_range[0]), float(self.steering_range[1])
 
 
+class DiscreteAction(ContinuousAction):
+    """A uniform quantisation of ContinuousAction (reference action.py:165-196): action k selects
+    `itertools.product(*np.linspace(low, high, actions_per_axis).T)[k]`, which then goes through
+    ContinuousAction.act.  The float32 table is built with the reference's expressions; the
+    lookup is a device gather in front of the continuous-action kernel path."""
+
+    def __init__(self, actions_per_axis: int = 3, **kwargs):
+        super().__init__(**kwargs)
+        self.actions_per_axis = int(actions_per_axis)
+        if self.actions_per_axis < 1:
+            raise ValueError("actions_per_axis must be >= 1")
+        cont = super().space()
+        axes = np.linspace(cont.low, cont.high, self.actions_per_axis).T
+        self.table = np.array(list(itertools.product(*axes)), dtype=np.float32)
+
+    def space(self):
+        return Discrete(self.actions_per_axis ** 2)
+
+
 ACTION_TYPES = {
     "DiscreteMetaAction": DiscreteMetaAction,
     "ContinuousAction": ContinuousAction,
+    "DiscreteAction": DiscreteAction,
 }
 
 
@@ -111,6 +133,6 @@ def action_factory(env, config: dict) -> ActionType:
     kind = config["type"]
     if kind in ACTION_TYPES:
         return ACTION_TYPES[kind](**config)
-    if kind in ("DiscreteAction", "MultiAgentAction"):
+    if kind in ("MultiAgentAction",):
         raise NotImplementedError(f"action type {kind!r} is not on the accelerated path yet")
     raise ValueError("Unknown action type")

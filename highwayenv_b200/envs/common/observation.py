@@ -22,8 +22,10 @@ class ObservationType:
 
 class KinematicObservation(ObservationType):
     """Kinematics of the ego and its nearest vehicles (reference observation.py:155-276):
-    rows (presence, x, y, vx, vy); row 0 is the ego, the others the closest vehicles by
-    |longitudinal distance on the ego's lane| within PERCEPTION_DISTANCE."""
+    row 0 is the ego, the others the closest vehicles by |longitudinal distance on the ego's lane|
+    within PERCEPTION_DISTANCE; columns are any of `Vehicle.to_dict`'s keys (vehicle/kinematics.py:237-261):
+    presence, x, y, vx, vy, heading, cos_h, sin_h, cos_d, sin_d, long_off, lat_off, ang_off, with an
+    optional `features_range` (every listed feature present in the table is mapped to [-1, 1])."""
 
     FEATURES = ["presence", "x", "y", "vx", "vy"]
 
@@ -32,10 +34,16 @@ class KinematicObservation(ObservationType):
                  clip: bool = True, see_behind: bool = False, observe_intentions: bool = False,
                  include_obstacles: bool = True, **kwargs):
         self.features = list(features) if features else list(self.FEATURES)
-        if self.features != self.FEATURES:
-            raise NotImplementedError(f"Kinematics features {self.features} (only {self.FEATURES})")
-        if features_range is not None:
-            raise NotImplementedError("custom features_range")
+        unknown = [f for f in self.features if f not in N.FEATURE_CODES]
+        if unknown:
+            raise KeyError(f"{unknown} not in index")  # what `df[self.features]` raises in the reference
+        if len(self.features) > N.HWY_MAX_OBS_FEATURES:
+            raise ValueError(f"at most {N.HWY_MAX_OBS_FEATURES} features")
+        if observe_intentions and ("cos_d" in self.features or "sin_d" in self.features):
+            # vehicles of this road family have no route: destination == position, the direction is (0, 0)
+            pass
+        self.features_range = None if features_range is None else {k: [float(v[0]), float(v[1])]
+                                                                   for k, v in features_range.items()}
         if order != "sorted":
             raise NotImplementedError("order='shuffled' draws from env.np_random on the host")
         if not 1 <= int(vehicles_count) <= N.HWY_MAX_OBS_VEHICLES:
@@ -54,6 +62,19 @@ class KinematicObservation(ObservationType):
         p.obs_absolute = int(self.absolute)
         p.obs_normalize = int(self.normalize)
         p.obs_clip = int(self.clip)
+        if self.features == self.FEATURES and self.features_range is None:
+            p.obs_n_features = 0  # default columns and ranges: the specialised epilogue
+            return
+        ranges = self.features_range
+        if ranges is None:  # normalize_obs (observation.py:214-226): side lanes of the straight road = lanes_count
+            ranges = {"x": [-5.0 * 40.0, 5.0 * 40.0], "y": [-4.0 * p.lanes_count, 4.0 * p.lanes_count],
+                      "vx": [-2 * 40.0, 2 * 40.0], "vy": [-2 * 40.0, 2 * 40.0]}
+        p.obs_n_features = len(self.features)
+        for c, f in enumerate(self.features):
+            p.obs_feature[c] = N.FEATURE_CODES[f]
+            p.obs_feature_ranged[c] = int(f in ranges)
+            if f in ranges:
+                p.obs_feature_lo[c], p.obs_feature_hi[c] = ranges[f]
 
 
 OBSERVATION_TYPES = {"Kinematics": KinematicObservation}

@@ -163,7 +163,8 @@ class BatchedHighwayEnv:
         V = int(self._params.n_vehicles)
         vp = int(self._lib.hwy_highway_slot_stride(V))
         K = int(self._params.obs_vehicles_count)
-        key = (n, vp, K, int(self._params.action_type))
+        F = int(self._params.obs_n_features) or 5
+        key = (n, vp, K, F, int(self._params.action_type))
         if self._allocated_for == key:
             return
         z = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, device=dev)  # noqa: E731
@@ -177,8 +178,8 @@ class BatchedHighwayEnv:
         self._speed_index = z(n, dtype=torch.int32)
         self._time = z(n, dtype=torch.float64)
         self._rng = z(5, n, dtype=torch.int64)  # uint64 words, bit-cast
-        self._obs = z(n, K, 5, dtype=torch.float32)
-        self._final_obs = z(n, K, 5, dtype=torch.float32)
+        self._obs = z(n, K, F, dtype=torch.float32)
+        self._final_obs = z(n, K, F, dtype=torch.float32)
         self._reward = z(n, dtype=torch.float64)
         self._terminated = z(n, dtype=torch.uint8)
         self._truncated = z(n, dtype=torch.uint8)
@@ -240,6 +241,18 @@ class BatchedHighwayEnv:
 
     def _stage_actions(self, actions) -> torch.Tensor:
         buf = self._action_buf
+        table = getattr(self.action_type, "table", None)
+        if table is not None:  # DiscreteAction (action.py:165-196): index -> (throttle, steering), then ContinuousAction
+            if getattr(self, "_action_table", None) is None or self._action_table.device != buf.device:
+                self._action_table = torch.from_numpy(table).to(buf.device)
+            idx = actions if isinstance(actions, torch.Tensor) else torch.from_numpy(np.asarray(actions))
+            idx = idx.to(device=buf.device, dtype=torch.long).reshape(-1)
+            if idx.numel() != buf.shape[0]:
+                raise ValueError("one action per env")
+            if bool(((idx < 0) | (idx >= table.shape[0])).any()):
+                raise IndexError("list index out of range")  # all_actions[action] in the reference
+            torch.index_select(self._action_table, 0, idx, out=buf)
+            return buf
         if isinstance(actions, torch.Tensor):
             if actions.device == buf.device and actions.dtype == buf.dtype and actions.is_contiguous() \
                     and actions.shape == buf.shape:
@@ -256,7 +269,7 @@ class BatchedHighwayEnv:
 
         ``actions``: [N] integers (DiscreteMetaAction) or [N, 2] float32 (ContinuousAction);
         device tensors are used in place.  Returns device tensors
-        ``(obs [N,K,5] f32, reward [N] f64, terminated [N] bool, truncated [N] bool, info)``;
+        ``(obs [N,K,F] f32, reward [N] f64, terminated [N] bool, truncated [N] bool, info)``;
         the buffers are reused by the next call.
         """
         if not self._seeded:

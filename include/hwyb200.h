@@ -46,6 +46,22 @@ extern "C" {
 #define HWY_META_KIND_SHIFT 19        /* 2 bits */
 #define HWY_META_PRESENT (1 << 21)
 
+/* Kinematics feature columns (Vehicle.to_dict keys, vehicle/kinematics.py:240-254) */
+#define HWY_MAX_OBS_FEATURES 16
+#define HWY_FEAT_PRESENCE 0
+#define HWY_FEAT_X 1
+#define HWY_FEAT_Y 2
+#define HWY_FEAT_VX 3
+#define HWY_FEAT_VY 4
+#define HWY_FEAT_HEADING 5
+#define HWY_FEAT_COS_H 6
+#define HWY_FEAT_SIN_H 7
+#define HWY_FEAT_COS_D 8
+#define HWY_FEAT_SIN_D 9
+#define HWY_FEAT_LONG_OFF 10
+#define HWY_FEAT_LAT_OFF 11
+#define HWY_FEAT_ANG_OFF 12
+
 /* autoreset modes of hwy_highway_step (gymnasium.vector.AutoresetMode) */
 #define HWY_AUTORESET_DISABLED 0
 #define HWY_AUTORESET_SAME_STEP 1 /* reset inside the step that ended; obs = reset obs */
@@ -91,6 +107,15 @@ typedef struct HwyHighwayParams {
     double delta_lo, delta_hi;
     double perception_distance;      /* abstract.py:56 */
     HwyStraightLane lanes[HWY_MAX_LANES];
+    /* KinematicObservation.features / features_range (observation.py:160-232; Vehicle.to_dict,
+     * vehicle/kinematics.py:237-261).  obs_n_features == 0: the default columns (presence, x, y, vx, vy)
+     * with the default ranges.  Otherwise column c holds feature obs_feature[c] (HWY_FEAT_*), mapped
+     * from [obs_feature_lo, obs_feature_hi] to [-1, 1] when obs_normalize and obs_feature_ranged[c]. */
+    int32_t obs_n_features;
+    int32_t _pad_obs;
+    int32_t obs_feature[HWY_MAX_OBS_FEATURES];
+    int32_t obs_feature_ranged[HWY_MAX_OBS_FEATURES];
+    double obs_feature_lo[HWY_MAX_OBS_FEATURES], obs_feature_hi[HWY_MAX_OBS_FEATURES];
 } HwyHighwayParams;
 
 /* Device-resident state of n_envs independent roads, structure of arrays over
@@ -122,7 +147,7 @@ int hwy_highway_slot_stride(int n_vehicles);
  * all): HighwayEnv._create_road/_create_vehicles (highway_env.py:55-98,177-182) with
  * Vehicle.create_random (kinematics.py:50-104), drawing from each env's PCG64 stream in
  * the reference's order.  If obs != NULL also writes the reset observation
- * [n_envs][obs_vehicles_count][5] float32 of those envs. */
+ * [n_envs][obs_vehicles_count][n columns] float32 of those envs. */
 int hwy_highway_reset(const HwyHighwayParams *p, const HwyHighwayState *s, const uint8_t *mask,
                       float *obs, void *stream);
 

@@ -38,6 +38,22 @@ CASES = {
         12,
         "box2",
     ),
+    # (f)2 plugins on the same path: DiscreteAction (action.py:165-196) and the full Kinematics feature list
+    "highway_discrete_action": ("highway-v0", {"vehicles_count": 20, "action": {"type": "DiscreteAction"}},
+                                list(range(800, 804)), 15, "discrete9"),
+    "highway_fast_features": (
+        "highway-fast-v0",
+        {"observation": {"type": "Kinematics", "vehicles_count": 7, "see_behind": True,
+                         "features": ["presence", "x", "y", "vx", "vy", "heading", "cos_h", "sin_h", "cos_d", "sin_d",
+                                      "long_off", "lat_off", "ang_off"]}},
+        list(range(810, 814)), 20, "discrete5"),
+    "highway_fast_features_range": (
+        "highway-fast-v0",
+        {"observation": {"type": "Kinematics", "vehicles_count": 4, "absolute": True, "clip": False,
+                         "features": ["x", "lat_off", "presence", "vx", "heading", "long_off"],
+                         "features_range": {"x": [-100, 1500], "vx": [0, 45], "long_off": [0, 2000],
+                                            "heading": [-1, 1], "vy": [-3, 3]}}},
+        list(range(820, 824)), 20, "discrete5"),
     # roundabout-v0 defaults (Kinematics absolute) and BASELINE configs[3] shape (TimeToCollision)
     "roundabout_kin": ("roundabout-v0", None, list(range(400, 406)), 11, "discrete5"),
     "roundabout_ttc": ("roundabout-v0", {"observation": {"type": "TimeToCollision", "horizon": 10}},
@@ -61,6 +77,8 @@ def main() -> None:
         for seed in seeds:
             if akind == "discrete5":
                 actions = rng.integers(0, 5, size=T).astype(np.int64)
+            elif akind == "discrete9":
+                actions = rng.integers(0, 9, size=T).astype(np.int64)
             elif akind == "discrete3":
                 actions = rng.integers(0, 3, size=T).astype(np.int64)
             else:

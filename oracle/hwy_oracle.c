@@ -642,6 +642,49 @@ static void world_init(World *w, const OrcHighwayCfg *c, OrcHighwayState *s, dou
     memset(act_buf, 0, sizeof(double) * 2 * c->n_vehicles); /* kinematics.py:44 */
 }
 
+int orc_highway_obs_columns(const OrcHighwayCfg *c) { return c->obs_n_features > 0 ? c->obs_n_features : 5; }
+
+/* vehicle/kinematics.py:237-261 Vehicle.to_dict(origin_vehicle, observe_intentions=False) restricted to
+ * the configured columns, then normalize_obs (observation.py:207-232) with the configured ranges */
+static void observe_row_features(const World *w, int v, int origin, float *out) {
+    const OrcHighwayCfg *c = w->c;
+    const OrcHighwayState *s = w->s;
+    double ch = cos(s->heading[v]), sh = sin(s->heading[v]);
+    double x = s->x[v], y = s->y[v], vx = s->speed[v] * ch, vy = s->speed[v] * sh;
+    if (origin >= 0) { /* :257-260: only x, y, vx, vy are made relative */
+        double co = cos(s->heading[origin]), so = sin(s->heading[origin]);
+        x -= s->x[origin];
+        y -= s->y[origin];
+        vx -= s->speed[origin] * co;
+        vy -= s->speed[origin] * so;
+    }
+    const Lane *L = &w->lanes[s->lane[v]];
+    double lon, lat;
+    lane_local(L, s->x[v], s->y[v], &lon, &lat); /* lane_offset :228-235 */
+    for (int col = 0; col < c->obs_n_features; col++) {
+        double val = 0;
+        switch (c->obs_feature[col]) {
+            case 0: val = 1; break;
+            case 1: val = x; break;
+            case 2: val = y; break;
+            case 3: val = vx; break;
+            case 4: val = vy; break;
+            case 5: val = s->heading[v]; break;
+            case 6: val = ch; break;
+            case 7: val = sh; break;
+            case 10: val = lon; break;
+            case 11: val = lat; break;
+            case 12: val = orc_wrap_to_pi(s->heading[v] - L->heading); break; /* lane.py:145-147 */
+            default: val = 0; break; /* cos_d, sin_d: no route => destination == position (kinematics.py:205-226) */
+        }
+        if (c->obs_normalize && c->obs_feature_ranged[col]) {
+            val = lmap(val, c->obs_feature_lo[col], c->obs_feature_hi[col], -1, 1);
+            if (c->obs_clip) val = clipd(val, -1, 1);
+        }
+        out[col] = (float)val;
+    }
+}
+
 /* envs/common/observation.py:234-276 KinematicObservation.observe (features presence,x,y,vx,vy;
  * order "sorted"); road/road.py:421-450 close_objects_to; kinematics.py:237-261 to_dict */
 void orc_highway_observe(const OrcHighwayCfg *c, const OrcHighwayState *s, float *obs) {
@@ -685,6 +728,17 @@ void orc_highway_observe(const OrcHighwayCfg *c, const OrcHighwayState *s, float
         }
         cand[j + 1] = cv;
         key[j + 1] = ck;
+    }
+    if (c->obs_n_features > 0) { /* configured feature list */
+        const int NF = c->obs_n_features;
+        for (int k = 0; k < K * NF; k++) obs[k] = 0.0f;
+        observe_row_features(&w, ego, -1, obs);
+        for (int k = 0; k < nc && k < K - 1; k++)
+            observe_row_features(&w, cand[k], c->obs_absolute ? -1 : ego, obs + NF * (k + 1));
+        free(rows);
+        free(cand);
+        free(key);
+        return;
     }
     int n_rows = 1;
     for (int k = 0; k < nc && k < K - 1; k++) {
@@ -892,7 +946,7 @@ typedef struct {
 static void *job_run(void *arg) {
     Job *j = (Job *)arg;
     const OrcHighwayCfg *c = j->c;
-    size_t obs_sz = (size_t)c->obs_vehicles_count * 5;
+    size_t obs_sz = (size_t)c->obs_vehicles_count * orc_highway_obs_columns(c);
     for (int e = j->e0; e < j->e1; e++) {
         OrcHighwayState s;
         bind_env(c, j->b, e, &s);

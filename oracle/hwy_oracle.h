@@ -27,6 +27,7 @@ extern "C" {
 #define ORC_MAX_TARGET_SPEEDS 8
 
 /* vehicle kinds */
+#define ORC_MAX_OBS_FEATURES 16
 #define ORC_KIND_IDM 0      /* highway_env/vehicle/behavior.py:12  IDMVehicle */
 #define ORC_KIND_MDP 1      /* highway_env/vehicle/controller.py:256 MDPVehicle (DiscreteMetaAction ego) */
 #define ORC_KIND_VEHICLE 2  /* highway_env/vehicle/kinematics.py:13 Vehicle (ContinuousAction ego) */
@@ -65,6 +66,13 @@ typedef struct OrcHighwayCfg {
     double politeness, lane_change_min_acc_gain, lane_change_max_braking_imposed, lane_change_delay;
     double delta_lo, delta_hi; /* DELTA_RANGE */
     double perception_distance; /* abstract.py:56 */
+    /* KinematicObservation.features / features_range (observation.py:160-232): 0 = the default
+     * (presence, x, y, vx, vy) with default ranges; else the Vehicle.to_dict keys (kinematics.py:240-254)
+     * by code: 0 presence 1 x 2 y 3 vx 4 vy 5 heading 6 cos_h 7 sin_h 8 cos_d 9 sin_d 10 long_off
+     * 11 lat_off 12 ang_off; a column is normalised iff obs_feature_ranged */
+    int32_t obs_n_features, _pad_obs;
+    int32_t obs_feature[ORC_MAX_OBS_FEATURES], obs_feature_ranged[ORC_MAX_OBS_FEATURES];
+    double obs_feature_lo[ORC_MAX_OBS_FEATURES], obs_feature_hi[ORC_MAX_OBS_FEATURES];
 } OrcHighwayCfg;
 
 /* One env's state, structure of arrays over vehicles (list order = road.vehicles). */

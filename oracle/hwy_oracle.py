@@ -66,6 +66,9 @@ class OrcHighwayCfg(C.Structure):
         ("delta_lo", C.c_double),
         ("delta_hi", C.c_double),
         ("perception_distance", C.c_double),
+        ("obs_n_features", C.c_int32), ("_pad_obs", C.c_int32),
+        ("obs_feature", C.c_int32 * 16), ("obs_feature_ranged", C.c_int32 * 16),
+        ("obs_feature_lo", C.c_double * 16), ("obs_feature_hi", C.c_double * 16),
     ]
 
 
@@ -179,7 +182,7 @@ def cfg_from_dict(config: dict) -> OrcHighwayCfg:
     c.n_vehicles = int(config["vehicles_count"]) + 1
     c.simulation_frequency = int(config["simulation_frequency"])
     c.policy_frequency = int(config["policy_frequency"])
-    c.action_type = {"DiscreteMetaAction": 0, "ContinuousAction": 1}[act["type"]]
+    c.action_type = {"DiscreteMetaAction": 0, "ContinuousAction": 1, "DiscreteAction": 1}[act["type"]]
     c.others_check_collisions = int(config.get("_others_check_collisions", 1))
     c.normalize_reward = int(bool(config["normalize_reward"]))
     c.offroad_terminal = int(bool(config["offroad_terminal"]))
@@ -188,6 +191,20 @@ def cfg_from_dict(config: dict) -> OrcHighwayCfg:
     c.obs_absolute = int(bool(obs.get("absolute", False)))
     c.obs_normalize = int(bool(obs.get("normalize", True)))
     c.obs_clip = int(bool(obs.get("clip", True)))
+    feats, fr = obs.get("features"), obs.get("features_range")
+    if (feats and list(feats) != ["presence", "x", "y", "vx", "vy"]) or fr is not None:
+        feats = list(feats) if feats else ["presence", "x", "y", "vx", "vy"]
+        codes = ["presence", "x", "y", "vx", "vy", "heading", "cos_h", "sin_h", "cos_d", "sin_d", "long_off",
+                 "lat_off", "ang_off"]
+        if fr is None:  # observation.py:214-226
+            lanes = int(config["lanes_count"])
+            fr = {"x": [-200.0, 200.0], "y": [-4.0 * lanes, 4.0 * lanes], "vx": [-80.0, 80.0], "vy": [-80.0, 80.0]}
+        c.obs_n_features = len(feats)
+        for k, f in enumerate(feats):
+            c.obs_feature[k] = codes.index(f)
+            c.obs_feature_ranged[k] = int(f in fr)
+            if f in fr:
+                c.obs_feature_lo[k], c.obs_feature_hi[k] = float(fr[f][0]), float(fr[f][1])
     ts = act.get("target_speeds")
     ts = list(np.linspace(20, 30, 3)) if ts is None else [float(t) for t in ts]
     c.n_target_speeds = len(ts)
@@ -222,6 +239,15 @@ def cfg_from_dict(config: dict) -> OrcHighwayCfg:
     return c
 
 
+def discrete_action_table(actions_per_axis: int = 3) -> np.ndarray:
+    """DiscreteAction.act (action.py:188-196): all_actions = product of linspace(low, high, k) per axis"""
+    import itertools
+
+    low, high = np.full(2, -1.0, dtype=np.float32), np.full(2, 1.0, dtype=np.float32)
+    axes = np.linspace(low, high, actions_per_axis).T
+    return np.array(list(itertools.product(*axes)), dtype=np.float32)
+
+
 class OracleBatch:
     """n_envs highway envs stepped by the C oracle (SoA numpy buffers [n_envs, V])."""
 
@@ -241,7 +267,7 @@ class OracleBatch:
         for k in list(_F64) + list(_I32) + ["speed_index", "time"]:
             setattr(self._b, k, self.a[k].ctypes.data)
         self._b.rng = self.rng.ctypes.data
-        self.obs = np.zeros((self.n, self.K, 5), dtype=np.float32)
+        self.obs = np.zeros((self.n, self.K, int(cfg.obs_n_features) or 5), dtype=np.float32)
         self.reward = np.zeros(self.n, dtype=np.float64)
         self.terminated = np.zeros(self.n, dtype=np.uint8)
         self.truncated = np.zeros(self.n, dtype=np.uint8)

@@ -12,7 +12,8 @@ from parity_utils import compare_state, golden_state, load_golden, well_conditio
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["highway_fast_v20", "highway_fast_v50", "highway_v50", "highway_v100_continuous"]
+CASES = ["highway_fast_v20", "highway_fast_v50", "highway_v50", "highway_v100_continuous",
+         "highway_discrete_action", "highway_fast_features", "highway_fast_features_range"]
 
 
 def make_env(g_or_cfg, n, **kw):
@@ -125,7 +126,8 @@ def _oracle_pair(name, n, seed0):
 
 
 @pytest.mark.parametrize("name,n,T", [("highway_fast_v50", 512, 30), ("highway_fast_v20", 256, 30),
-                                      ("highway_v50", 64, 12), ("highway_v100_continuous", 32, 8)])
+                                      ("highway_v50", 64, 12), ("highway_v100_continuous", 32, 8),
+                                      ("highway_fast_features", 128, 12), ("highway_fast_features_range", 128, 12)])
 def test_teacher_forced_vs_oracle_many_envs(name, n, T):
     """Every step: inject the oracle's state, step both, compare everything."""
     g, cfg, oc, ob = _oracle_pair(name, n, 5000)

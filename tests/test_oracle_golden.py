@@ -6,7 +6,16 @@ import pytest
 import hwy_oracle as ho
 from parity_utils import compare_state, golden_state, load_golden, well_conditioned
 
-CASES = ["highway_fast_v20", "highway_fast_v50", "highway_v50", "highway_v100_continuous"]
+CASES = ["highway_fast_v20", "highway_fast_v50", "highway_v50", "highway_v100_continuous",
+         "highway_discrete_action", "highway_fast_features", "highway_fast_features_range"]
+
+
+def _actions(g, t):
+    """DiscreteAction (action.py:165-196): index -> float32 (throttle, steering) pair"""
+    a = g["actions"][:, t]
+    if g["config"]["action"]["type"] == "DiscreteAction":
+        return ho.discrete_action_table(g["config"]["action"].get("actions_per_axis", 3))[a]
+    return a
 
 
 def _got(ob, e=0):
@@ -38,7 +47,7 @@ def test_teacher_forced_steps(name):
     for t in range(T):
         for i in range(S):
             ob.load_state(i, golden_state(g, i, t))
-        obs, rew, term, trunc = ob.step(g["actions"][:, t])
+        obs, rew, term, trunc = ob.step(_actions(g, t))
         for i in range(S):
             ctx = f"{name} seed#{i} t={t}"
             worst = max(worst, compare_state(golden_state(g, i, t + 1), _got(ob, i), ctx=ctx))
@@ -59,7 +68,7 @@ def test_free_running_prefix(name):
     alive = np.ones(S, dtype=bool)
     compared = 0
     for t in range(T):
-        obs, rew, term, trunc = ob.step(g["actions"][:, t])
+        obs, rew, term, trunc = ob.step(_actions(g, t))
         for i in range(S):
             st = golden_state(g, i, t + 1)
             alive[i] &= well_conditioned(st)
