@@ -68,7 +68,7 @@ class HwyHighwayState(C.Structure):
 
 
 # ---- general road networks (roundabout-v0)
-HWY_NET_MAX_LANES, HWY_NET_MAX_NODES, HWY_NET_MAX_SUCC, HWY_NET_MAX_ROUTE, HWY_NET_GROUP = 64, 64, 6, 16, 8
+HWY_NET_MAX_LANES, HWY_NET_MAX_NODES, HWY_NET_MAX_SUCC, HWY_NET_MAX_ROUTE, HWY_NET_GROUP = 32, 64, 6, 16, 8
 HWY_NET_GROUP_LARGE = 32
 LANE_STRAIGHT, LANE_SINE, LANE_CIRCULAR = 0, 1, 2
 OBS_KINEMATICS, OBS_OCCUPANCY, OBS_TTC = 0, 1, 2

@@ -28,6 +28,7 @@ using namespace hwy;
 constexpr int R = HWY_NET_MAX_ROUTE;
 constexpr int kBlockThreads = 256;
 constexpr int kPred = 11;  // np.arange(0.25, 3, 0.25) prediction points of RegulatedRoad.is_conflict_possible
+constexpr int kPredChunk = 4;  // horizon points staged in shared memory at a time
 
 struct GraphShared {
     int n_lanes, n_nodes;
@@ -38,7 +39,7 @@ struct GraphShared {
 
 template <int G>
 __host__ __device__ constexpr int kCand() {
-    return G >= 32 ? 96 : 40;
+    return G >= 32 ? 48 : 40;
 }
 
 // Per-env shared staging for G vehicle slots.  REG adds the RegulatedRoad prediction buffers.
@@ -70,8 +71,8 @@ struct EnvStage {
             unsigned short vl[kCand<G>()];
         } cand;
     } o;
-    // RegulatedRoad: predicted (x, y, heading) of every vehicle at the 11 horizon points
-    double pred[REG ? G : 1][REG ? kPred : 1][3];
+    // RegulatedRoad: predicted (x, y, heading) of every vehicle at kPredChunk horizon points at a time
+    double pred[REG ? G : 1][REG ? kPredChunk : 1][3];
 };
 
 // ------------------------------------------------------------------ lanes (road/lane.py)
@@ -866,38 +867,57 @@ __device__ __forceinline__ void enforce_road_rules(const HwyNetParams& P, const 
         st.ts[i] = r.target_speed;
     }
     if (i == 0) st.yield_mask = 0;
-    // predict_trajectory_constant_speed (vehicle/controller.py:236-253) at t = 0.25 .. 2.75 s
-    if (active) {
-        const double s0 = st.own_s[i];
-        for (int k = 0; k < kPred; ++k) {
-            double px, py, ph;
-            position_heading_along_route(g, st, i, s0 + r.speed * (0.25 * (k + 1)), px, py, ph);
-            st.pred[i][k][0] = px;
-            st.pred[i][k][1] = py;
-            st.pred[i][k][2] = ph;
-        }
-    }
-    group_sync<G>();
-    // every pair (a < b), dealt round-robin over the group
+    // Pairs (a < b) are dealt round-robin over the group: this thread owns pairs i, i + G, ... (<= 16 of the
+    // 32 * 31 / 2); bit q of `conflict` = its q-th pair conflicts at some horizon point.  The horizon
+    // (predict_trajectory_constant_speed, vehicle/controller.py:236-253, t = 0.25 .. 2.75 s) is staged
+    // kPredChunk points at a time.
     const int n_pairs = V * (V - 1) / 2;
-    for (int p = i; p < n_pairs; p += G) {
-        int a = 0, rem = p;  // p -> (a, b): row a has V-1-a pairs
-        while (rem >= V - 1 - a) {
-            rem -= V - 1 - a;
-            ++a;
+    auto row_start = [V](int a) { return a * (2 * V - a - 1) / 2; };
+    auto decode = [&](int p, int& a, int& b) {
+        const int w = 2 * V - 1;
+        a = (int)(((float)w - sqrtf((float)(w * w - 8 * p))) * 0.5f);
+        a = max(0, min(a, V - 2));
+        while (a > 0 && row_start(a) > p) --a;
+        while (row_start(a + 1) <= p) ++a;
+        b = a + 1 + (p - row_start(a));
+    };
+    unsigned conflict = 0;
+    const double s0 = active ? st.own_s[i] : 0.0;
+    for (int k0 = 0; k0 < kPred; k0 += kPredChunk) {
+        const int nk = min(kPredChunk, kPred - k0);
+        if (active) {
+            for (int k = 0; k < nk; ++k) {
+                double px, py, ph;
+                position_heading_along_route(g, st, i, s0 + r.speed * (0.25 * (k0 + k + 1)), px, py, ph);
+                st.pred[i][k][0] = px;
+                st.pred[i][k][1] = py;
+                st.pred[i][k][2] = ph;
+            }
         }
-        const int b = a + 1 + rem;
-        bool conflict = false;
-        for (int k = 0; k < kPred && !conflict; ++k) {
-            double p1x = st.pred[a][k][0], p1y = st.pred[a][k][1], p2x = st.pred[b][k][0], p2y = st.pred[b][k][1];
-            if (norm2(p2x - p1x, p2y - p1y) > kVehLength) continue;
-            double h1 = st.pred[a][k][2], h2 = st.pred[b][k][2];
-            conflict = has_corner_inside(p1x, p1y, 1.5 * kVehLength, 0.9 * kVehWidth, h1, p2x, p2y,
-                                         1.5 * kVehLength, 0.9 * kVehWidth, h2) ||
-                       has_corner_inside(p2x, p2y, 1.5 * kVehLength, 0.9 * kVehWidth, h2, p1x, p1y,
-                                         1.5 * kVehLength, 0.9 * kVehWidth, h1);
+        group_sync<G>();
+        int q = 0;
+        for (int p = i; p < n_pairs; p += G, ++q) {
+            if ((conflict >> q) & 1u) continue;
+            int a, b;
+            decode(p, a, b);
+            bool hit = false;
+            for (int k = 0; k < nk && !hit; ++k) {
+                double p1x = st.pred[a][k][0], p1y = st.pred[a][k][1], p2x = st.pred[b][k][0], p2y = st.pred[b][k][1];
+                if (norm2(p2x - p1x, p2y - p1y) > kVehLength) continue;
+                double h1 = st.pred[a][k][2], h2 = st.pred[b][k][2];
+                hit = has_corner_inside(p1x, p1y, 1.5 * kVehLength, 0.9 * kVehWidth, h1, p2x, p2y, 1.5 * kVehLength,
+                                        0.9 * kVehWidth, h2) ||
+                      has_corner_inside(p2x, p2y, 1.5 * kVehLength, 0.9 * kVehWidth, h2, p1x, p1y, 1.5 * kVehLength,
+                                        0.9 * kVehWidth, h1);
+            }
+            if (hit) conflict |= 1u << q;
         }
-        if (!conflict) continue;
+        group_sync<G>();
+    }
+    for (int q = 0; conflict >> q; ++q) {
+        if (!((conflict >> q) & 1u)) continue;
+        int a, b;
+        decode(i + q * G, a, b);
         const int pa = g.lanes[st.lane[a]].priority, pb = g.lanes[st.lane[b]].priority;
         int y;
         if (pa > pb)
@@ -1201,18 +1221,23 @@ network_step_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGraph* _
                     const __grid_constant__ HwyIntersectionSpawn SP, const int32_t* __restrict__ action, float* __restrict__ obs,
                     double* __restrict__ reward, uint8_t* __restrict__ terminated,
                     uint8_t* __restrict__ truncated, double* __restrict__ info_speed,
-                    uint8_t* __restrict__ info_crashed) {
+                    uint8_t* __restrict__ info_crashed, const int* __restrict__ list) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     GraphShared& g = *reinterpret_cast<GraphShared*>(smem_raw);
     EnvStage<G, REG>* stages =
         reinterpret_cast<EnvStage<G, REG>*>(smem_raw + ((sizeof(GraphShared) + 15) & ~size_t(15)));
+    constexpr int kEnvs = kBlockThreads / G;
+    // with a work list (list[0] = how many, list[1..] = env ids) the grid is dense over the list and the
+    // blocks past its end leave as a whole; partial blocks let the spare groups ride along on the last entry
+    const int n_work = list ? list[0] : S.n_envs;
+    if (blockIdx.x * kEnvs >= n_work) return;
     stage_graph(g, graph);
 
-    constexpr int kEnvs = kBlockThreads / G;
     const int sub = threadIdx.x / G, i = threadIdx.x % G;
-    const int env = blockIdx.x * kEnvs + sub;
-    const bool env_ok = env < S.n_envs;
-    const int e = env_ok ? env : S.n_envs - 1;
+    const int idx = blockIdx.x * kEnvs + sub;
+    const bool env_ok = idx < n_work;
+    const int pick = env_ok ? idx : n_work - 1;
+    const int e = list ? list[1 + pick] : pick;
     EnvStage<G, REG>& st = stages[sub];
 
     Regs r;
@@ -1370,6 +1395,26 @@ __global__ void compact_envs_kernel(const uint8_t* __restrict__ mask_a, const ui
     if (lane == __ffs(m) - 1) base = atomicAdd(&list[0], __popc(m));
     base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
     if (sel) list[1 + base + __popc(m & ((1u << lane) - 1u))] = e;
+}
+
+// Two work lists for the step: envs whose population fits 16 slots even after this step's spawn (count <= 15)
+// run two per warp; the rest use 32 slots.  small / large: [n_envs + 1] each, [0] = count (zeroed by the caller).
+__global__ void classify_envs_kernel(const int* __restrict__ count, int n_envs, int* __restrict__ small,
+                                     int* __restrict__ large) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ok = e < n_envs;
+    const bool is_small = ok && count[e] <= 15;
+    const int lane = threadIdx.x & 31;
+    for (int pass = 0; pass < 2; ++pass) {
+        const bool sel = ok && (pass == 0 ? is_small : !is_small);
+        int* list = pass == 0 ? small : large;
+        const unsigned m = __ballot_sync(0xffffffffu, sel);
+        if (!m) continue;
+        int base = 0;
+        if (lane == __ffs(m) - 1) base = atomicAdd(&list[0], __popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (sel) list[1 + base + __popc(m & ((1u << lane) - 1u))] = e;
+    }
 }
 
 // IntersectionEnv._make_vehicles (envs/intersection_env.py:245-323) for the listed envs, one 32-slot group each:
@@ -1618,11 +1663,11 @@ int blocks_for(int n_envs, int g) {
 template <int G, bool REG>
 int launch_step(const HwyNetParams* p, const HwyNetGraph* graph, const HwyIntersectionSpawn& sp, const HwyNetState* s,
                 const int32_t* action, float* obs, double* reward, uint8_t* terminated, uint8_t* truncated,
-                double* info_speed, uint8_t* info_crashed, cudaStream_t st) {
+                double* info_speed, uint8_t* info_crashed, cudaStream_t st, const int* list = nullptr) {
     const size_t smem = net_smem_bytes<G, REG>();
     if (configure_smem(hwynet::network_step_kernel<G, REG>, smem)) return 1;
     hwynet::network_step_kernel<G, REG><<<blocks_for(s->n_envs, G), hwynet::kBlockThreads, smem, st>>>(
-        *p, graph, *s, sp, action, obs, reward, terminated, truncated, info_speed, info_crashed);
+        *p, graph, *s, sp, action, obs, reward, terminated, truncated, info_speed, info_crashed, list);
     return check_launch("network_step_kernel");
 }
 template <int G, bool REG>
@@ -1671,8 +1716,23 @@ int hwy_intersection_step(const HwyNetParams* p, const HwyNetGraph* graph, const
     if (p->dynamic_population && (!spawn || !spawn->route_table || !spawn->route_len || !s->rng))
         return fail("%s", "dynamic population needs the spawn tables and the rng words");
     HwyIntersectionSpawn none = {};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (spawn && spawn->scratch && s->count) {
+        // populations of <= 15 vehicles (nearly all envs) step two per warp on 16 slots, the others on 32
+        int* small = spawn->scratch;
+        int* large = spawn->scratch + (s->n_envs + 1);
+        cudaMemsetAsync(small, 0, sizeof(int), st);
+        cudaMemsetAsync(large, 0, sizeof(int), st);
+        hwynet::classify_envs_kernel<<<(s->n_envs + 255) / 256, 256, 0, st>>>(s->count, s->n_envs, small, large);
+        if (check_launch("classify_envs_kernel")) return 1;
+        if (launch_step<16, true>(p, graph, *spawn, s, action, obs, reward, terminated, truncated, info_speed,
+                                  info_crashed, st, small))
+            return 1;
+        return launch_step<HWY_NET_GROUP_LARGE, true>(p, graph, *spawn, s, action, obs, reward, terminated, truncated,
+                                                      info_speed, info_crashed, st, large);
+    }
     return launch_step<HWY_NET_GROUP_LARGE, true>(p, graph, spawn ? *spawn : none, s, action, obs, reward, terminated,
-                                                  truncated, info_speed, info_crashed, (cudaStream_t)stream);
+                                                  truncated, info_speed, info_crashed, st);
 }
 
 int hwy_intersection_reset(const HwyNetParams* p, const HwyNetGraph* graph, const HwyIntersectionSpawn* spawn,
@@ -1691,12 +1751,19 @@ int hwy_intersection_reset(const HwyNetParams* p, const HwyNetGraph* graph, cons
     if (final_obs)
         cudaMemcpyAsync(final_obs, obs, (size_t)s->n_envs * hwy_network_obs_size(p) * sizeof(float),
                         cudaMemcpyDeviceToDevice, st);
-    const size_t smem = net_smem_bytes<HWY_NET_GROUP_LARGE, true>();
-    if (configure_smem(hwynet::intersection_reset_kernel<HWY_NET_GROUP_LARGE, true>, smem)) return 1;
-    hwynet::intersection_reset_kernel<HWY_NET_GROUP_LARGE, true>
-        <<<blocks_for(s->n_envs, HWY_NET_GROUP_LARGE), hwynet::kBlockThreads, smem, st>>>(*p, graph, *s, *spawn,
-                                                                                         spawn->scratch, obs);
     if (check_launch("compact_envs_kernel")) return 1;
+    if (spawn->initial_vehicle_count + 1 <= 16) {  // n-1 draws + challenger + controlled vehicle fit 16 slots
+        const size_t smem = net_smem_bytes<16, true>();
+        if (configure_smem(hwynet::intersection_reset_kernel<16, true>, smem)) return 1;
+        hwynet::intersection_reset_kernel<16, true>
+            <<<blocks_for(s->n_envs, 16), hwynet::kBlockThreads, smem, st>>>(*p, graph, *s, *spawn, spawn->scratch, obs);
+    } else {
+        const size_t smem = net_smem_bytes<HWY_NET_GROUP_LARGE, true>();
+        if (configure_smem(hwynet::intersection_reset_kernel<HWY_NET_GROUP_LARGE, true>, smem)) return 1;
+        hwynet::intersection_reset_kernel<HWY_NET_GROUP_LARGE, true>
+            <<<blocks_for(s->n_envs, HWY_NET_GROUP_LARGE), hwynet::kBlockThreads, smem, st>>>(*p, graph, *s, *spawn,
+                                                                                             spawn->scratch, obs);
+    }
     return check_launch("intersection_reset_kernel");
 }
 

@@ -236,7 +236,7 @@ class BatchedIntersectionEnv:
             raise ValueError(f"destination {dest!r}")
         sp.ego_destination = -1 if dest is None else int(dest[1:])
         sp.initial_vehicle_count = int(self.config["initial_vehicle_count"])
-        self._scratch = z(n + 1, dtype=torch.int32)
+        self._scratch = z(2 * (n + 1), dtype=torch.int32)
         sp.scratch = self._scratch.data_ptr()
         self._spawn_struct = sp
 

@@ -184,7 +184,7 @@ int hwy_highway_autoreset(const HwyHighwayParams *p, const HwyHighwayState *s,
  * roundabout-v0 (envs/roundabout_env.py): Straight / Sine / Circular lanes (road/lane.py:159-384),
  * planned routes and RoadNetwork.next_lane (road/road.py:73-157), TimeToCollision or absolute
  * Kinematics observation.  Same conventions as the highway entry points above. */
-#define HWY_NET_MAX_LANES 64
+#define HWY_NET_MAX_LANES 32
 #define HWY_NET_MAX_NODES 64
 #define HWY_NET_MAX_SUCC 6
 #define HWY_NET_MAX_ROUTE 16
@@ -274,7 +274,9 @@ typedef struct HwyIntersectionSpawn {
     int32_t ego_destination;       /* k of config["destination"] == "o"+k; -1 (None): "o" + integers(1, 4) */
     int32_t initial_vehicle_count; /* config["initial_vehicle_count"] */
     int32_t _pad;
-    int32_t *scratch;              /* DEVICE [n_envs + 1] int32: work list of the envs being reset */
+    int32_t *scratch;              /* DEVICE [2 * (n_envs + 1)] int32: work lists (envs being reset; the
+                                    * step's 16-slot / 32-slot populations).  NULL: hwy_intersection_step
+                                    * runs every env on 32 slots and hwy_intersection_reset is unavailable */
 } HwyIntersectionSpawn;
 
 /* observation size in floats: Kinematics K*5, TimeToCollision 3*3*(horizon*policy_frequency) */

@@ -198,3 +198,36 @@ def test_device_autoreset_masks_only_finished_envs():
         # a reset consumes dozens — and the inc half of the state never changes
         assert np.array_equal(sd["rng"][2:4], before["rng"][2:4])
         assert np.array_equal(info["final_obs"].cpu().numpy()[~done], obs.cpu().numpy()[~done])
+
+
+def test_16_slot_and_32_slot_paths_agree():
+    """hwy_intersection_step runs populations of <= 15 vehicles two per warp on 16 slots and the others on 32
+    (work lists in spawn.scratch); without scratch every env takes the 32-slot kernel.  Same results bit for bit."""
+    g = load_golden("intersection_grid")
+    n = 256
+    a = make_env(g["config"], n, autoreset_mode="Disabled")
+    b = make_env(g["config"], n, autoreset_mode="Disabled")
+    a.reset(seed=77)
+    b.reset(seed=77)
+    b._spawn_struct.scratch = None
+    rng = np.random.default_rng(9)
+    small = large = 0
+    for t in range(16):  # runs past the 13 s horizon: populations keep growing, some beyond 15
+        counts = a.state_dict()["count"]
+        small += int((counts <= 15).sum())
+        large += int((counts > 15).sum())
+        act = rng.integers(0, 3, size=n).astype(np.int32)
+        oa, ra, ta, ua, _ = a.step(act)
+        ob, rb, tb, ub, _ = b.step(act)
+        assert np.array_equal(oa.cpu().numpy(), ob.cpu().numpy()), t
+        assert np.array_equal(ra.cpu().numpy(), rb.cpu().numpy()), t
+        assert np.array_equal(ta.cpu().numpy(), tb.cpu().numpy()) and np.array_equal(ua.cpu().numpy(), ub.cpu().numpy())
+        sa, sb = a.state_dict(), b.state_dict()
+        live = np.arange(V)[None, :] < sa["count"][:, None]
+        for k in sa:
+            x, y = sa[k], sb[k]
+            if x.ndim >= 2 and x.shape[:2] == (n, V):
+                m = live.reshape(live.shape + (1,) * (x.ndim - 2))
+                x, y = np.where(m, x, 0), np.where(m, y, 0)
+            assert np.array_equal(x, y), (t, k)
+    assert small > 0 and large > 0, (small, large)
