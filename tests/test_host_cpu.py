@@ -33,13 +33,18 @@ def test_struct_layout_matches_header():
 
     from highwayenv_b200 import _native as N
 
-    src = '#include <stdio.h>\n#include "hwyb200.h"\nint main(){printf("%zu %zu %zu\\n", sizeof(HwyHighwayParams), sizeof(HwyHighwayState), sizeof(HwyStraightLane));return 0;}\n'
+    src = ('#include <stdio.h>\n#include "hwyb200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", '
+           'sizeof(HwyHighwayParams), sizeof(HwyHighwayState), sizeof(HwyStraightLane), sizeof(HwyNetLane), '
+           'sizeof(HwyNetGraph), sizeof(HwyNetParams), sizeof(HwyNetState), sizeof(HwyIntersectionSpawn), '
+           'sizeof(HwyRoundaboutSpawn));return 0;}\n')
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "t.c"), "w").write(src)
         exe = os.path.join(d, "t")
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", exe])
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
-    assert sizes == [C.sizeof(N.HwyHighwayParams), C.sizeof(N.HwyHighwayState), C.sizeof(N.HwyStraightLane)]
+    assert sizes == [C.sizeof(t) for t in (N.HwyHighwayParams, N.HwyHighwayState, N.HwyStraightLane, N.HwyNetLane,
+                                           N.HwyNetGraph, N.HwyNetParams, N.HwyNetState, N.HwyIntersectionSpawn,
+                                           N.HwyRoundaboutSpawn)]
 
 
 def test_abi_validation_without_gpu():
@@ -113,6 +118,54 @@ def test_plugin_factories():
         observation_factory(None, {"type": "Nope"})
     with pytest.raises(NotImplementedError):
         observation_factory(None, {"type": "OccupancyGrid"})
+    # DiscreteAction (action.py:165-196): 3 x 3 grid over [-1, 1]^2 in itertools.product order, float32
+    d = action_factory(None, {"type": "DiscreteAction"})
+    assert d.space().n == 9 and d.table.dtype == np.float32
+    assert d.table.tolist() == [[x, y] for x in (-1.0, 0.0, 1.0) for y in (-1.0, 0.0, 1.0)]
+    assert action_factory(None, {"type": "DiscreteAction", "actions_per_axis": 5}).space().n == 25
+    # Kinematics feature lists / ranges end up in the kernel parameters
+    from highwayenv_b200 import _native as N
+    k = observation_factory(None, {"type": "Kinematics", "features": ["presence", "x", "cos_h", "lat_off"],
+                                   "features_range": {"x": [-10, 10]}})
+    p = N.HwyHighwayParams()
+    p.lanes_count = 4
+    k.fill_params(p)
+    assert k.space().shape == (5, 4) and p.obs_n_features == 4
+    assert list(p.obs_feature[:4]) == [0, 1, 6, 11] and list(p.obs_feature_ranged[:4]) == [0, 1, 0, 0]
+    assert (p.obs_feature_lo[1], p.obs_feature_hi[1]) == (-10.0, 10.0)
+    with pytest.raises(KeyError):
+        observation_factory(None, {"type": "Kinematics", "features": ["presence", "nope"]})
+
+
+def test_network_tables_match_the_reference_dump():
+    """road/network.py + the scenario builders against the lane tables dumped from the reference's
+    RoadNetwork (graph enumeration order, lane constructor arithmetic, successor lists, priorities)."""
+    from highwayenv_b200.envs.intersection_env import make_intersection_network
+    from highwayenv_b200.envs.roundabout_env import make_roundabout_network
+    from parity_utils import load_golden
+
+    for name, build in (("intersection_kin", make_intersection_network), ("roundabout_kin", make_roundabout_network)):
+        g, ex = load_golden(name), build().export_arrays()
+        assert list(ex["net_node_names"]) == list(g["net_node_names"]), name
+        for key, val in ex.items():
+            if key != "net_node_names" and key in g:
+                assert np.array_equal(val, g[key]), (name, key)
+    net = make_intersection_network()
+    # plan_route_to (controller.py:71-87): from the south access road to the west exit = right turn
+    route = net.plan_route(("o0", "ir0", 0), "o1")
+    assert [r[:2] for r in route] == [("o0", "ir0"), ("ir0", "il1"), ("il1", "o1")]
+    assert sum(l["exit_lane"] for l in net.lanes) == 4 and sorted({l["priority"] for l in net.lanes}) == [0, 1, 2, 3]
+
+
+def test_intersection_defaults_match_reference_config():
+    from highwayenv_b200.config import default_config
+    from parity_utils import load_golden
+
+    ref = dict(load_golden("intersection_kin")["config"])
+    ref.pop("_env_id"), ref.pop("_others_check_collisions")
+    ours = default_config("intersection-v0")
+    ours["offscreen_rendering"] = ref["offscreen_rendering"]
+    assert ours == ref
 
 
 def test_no_silent_cpu_fallback():
