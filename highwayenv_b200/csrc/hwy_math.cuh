@@ -48,7 +48,47 @@ static __device__ __noinline__ double m_asin(double x) { return asin(x); }
 static __device__ __noinline__ double m_tan(double x) { return tan(x); }
 static __device__ __noinline__ double m_atan(double x) { return atan(x); }
 static __device__ __noinline__ double m_sin(double x) { return sin(x); }
-static __device__ __noinline__ void m_sincos(double x, double* s, double* c) { sincos(x, s, c); }
+// sin and cos together.  Headings and lane phases are almost always within +-pi/4 (a vehicle following its lane),
+// where no argument reduction is needed: the fdlibm kernel polynomials (__kernel_sin / __kernel_cos, < 1 ulp, the
+// same accuracy class as numpy's and CUDA's own routines) cost ~30 fp64 operations instead of the ~300 issued
+// instructions of the general sincos(), which had become the largest single item of the step kernel (14 % of its
+// instructions, profiles/r1_step_kernel_history.md).  Larger arguments take the library routine.  Returned by
+// value: pointer results through a non-inlined call would live in local memory.
+static __device__ __noinline__ double2 m_sincos_impl(double x) {
+    const double ax = fabs(x);
+    if (ax <= 0.7853981633974483) {
+        const double z = x * x;
+        double r = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+        r = fma(z, r, 2.75573137070700676789e-06);
+        r = fma(z, r, -1.98412698298579493134e-04);
+        r = fma(z, r, 8.33333333332248946124e-03);
+        const double v = z * x;
+        const double sn = fma(v, fma(z, r, -1.66666666666666324348e-01), x);
+        double q = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+        q = fma(z, q, -2.75573143513906633035e-07);
+        q = fma(z, q, 2.48015872894767294178e-05);
+        q = fma(z, q, -1.38888888888741095749e-03);
+        q = fma(z, q, 4.16666666666666019037e-02);
+        const double zr = z * (z * q);
+        double cs;
+        if (ax < 0.3) {
+            cs = 1.0 - (0.5 * z - zr);
+        } else {  // split 1 - z/2 around qx ~ |x|/4 so that the subtraction from 1 is exact
+            const double qx = ax > 0.78125 ? 0.28125 : __hiloint2double(__double2hiint(ax) - 0x00200000, 0);
+            const double hz = 0.5 * z - qx;
+            cs = (1.0 - qx) - (hz - zr);
+        }
+        return make_double2(sn, cs);
+    }
+    double sn, cs;
+    sincos(x, &sn, &cs);
+    return make_double2(sn, cs);
+}
+__device__ __forceinline__ void m_sincos(double x, double* s, double* c) {
+    const double2 r = m_sincos_impl(x);
+    *s = r.x;
+    *c = r.y;
+}
 static __device__ __noinline__ double m_pow(double x, double y) { return pow(x, y); }
 static __device__ __noinline__ double m_fmod(double a, double b) { return fmod(a, b); }
 
