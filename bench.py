@@ -259,13 +259,32 @@ def run_gpu_arm(args) -> None:
         h_trunc.copy_(trunc, non_blocking=True)
         torch.cuda.synchronize(dev)  # the caller reads the results before acting again
     barrier()
-    e2e_s = time.perf_counter() - t0
+    e2e_eager_s = time.perf_counter() - t0
+    # the same loop through env.host_stepper(): upload + kernel + downloads replayed as one CUDA graph
+    e2e_s, e2e_api = e2e_eager_s, "env.step + explicit pinned copies"
+    try:
+        hs = env.host_stepper()
+        pool_np = host_pool.numpy()
+        for k in range(min(3, K)):
+            hs.actions[:] = pool_np[k]
+            hs.step()
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(K):
+            hs.actions[:] = pool_np[k]  # the policy's host-side output
+            o, r_, te, tr = hs.step()   # returns after the results are in host memory
+        barrier()
+        e2e_graph_s = time.perf_counter() - t0
+        if e2e_graph_s < e2e_s:
+            e2e_s, e2e_api = e2e_graph_s, "env.host_stepper().step() (one CUDA graph: H2D + step kernel + D2H)"
+    except Exception as exc:  # graph capture unavailable: keep the eager number, say why
+        e2e_api += f" (host_stepper unavailable: {type(exc).__name__})"
 
     # ---- max over ranks
-    t = torch.tensor([total_ms, e2e_s, kern_ms_avg], dtype=torch.float64, device=dev)
+    t = torch.tensor([total_ms, e2e_s, kern_ms_avg, e2e_eager_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_s, kern_ms_avg = (float(x) for x in t.cpu())
+    total_ms, e2e_s, kern_ms_avg, e2e_eager = (float(x) for x in t.cpu())
     total_launches = torch.tensor([launches], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(total_launches)
@@ -299,13 +318,17 @@ def run_gpu_arm(args) -> None:
                 "value": n_total * K / e2e_s, "unit": UNIT,
                 "h2d_bytes_per_step": E * 4,
                 "d2h_bytes_per_step": E * (env.K * 5 * 4 + 8 + 1 + 1),
-                "note": "per GPU; pinned host actions -> device, public env.step, obs/reward/terminated/truncated -> pinned host, sync every step",
+                "api": e2e_api, "eager_value": n_total * K / e2e_eager,
+                "note": "per GPU; pinned host actions -> device, public API, obs/reward/terminated/truncated -> pinned host, sync every step",
             },
             "gpu_launches": int(total_launches.item()),
             "roofline": {
                 "bound": "hbm", "kernel": "highway_step_kernel<64>",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": _ncu_traffic(), "peak_source": peak_src,
+                "traffic_source": "profiles/r1_ncu_highway_step.json (dram__bytes_read.sum + dram__bytes_write.sum, "
+                                  "one ncu --set full capture of this kernel at this size; ncu replays without the L2 "
+                                  "flush, so the state stays L2-resident)",
                 "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * E,
                 "kernel_ms": kern_ms_avg,
                 "note": "fp64 compute/latency bound: see DESIGN.md roofline discussion",
@@ -320,6 +343,17 @@ def run_gpu_arm(args) -> None:
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def _ncu_traffic():
+    """DRAM bytes per launch of the step kernel from the committed ncu capture summary (None if absent)."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_ncu_highway_step.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"])
+    except (OSError, KeyError, ValueError):
+        return None
 
 
 def main() -> None:

@@ -272,3 +272,25 @@ def test_longitudinal_ties_take_the_exact_path():
         for k in ("lane", "target_lane", "crashed", "has_impact"):
             assert np.array_equal(sd[k].astype(np.int32), ob.a[k].astype(np.int32)), (t, k)
         assert np.array_equal(term.cpu().numpy(), o_term.astype(bool))
+
+
+def test_host_stepper_graph_matches_env_step():
+    """env.host_stepper(): upload + step kernel + downloads in one CUDA graph == env.step, through resets."""
+    g = load_golden("highway_fast_v20")
+    n = 96
+    a = make_env(g["config"], n)
+    b = make_env(g["config"], n)
+    a.reset(seed=123)
+    b.reset(seed=123)
+    hs = b.host_stepper()
+    rng = np.random.default_rng(4)
+    for t in range(35):
+        act = rng.integers(0, 5, size=n).astype(np.int32)
+        oa, ra, ta, ua, _ = a.step(act)
+        hs.actions[:] = act
+        ob, rb, tb, ub = hs.step()
+        assert np.array_equal(oa.cpu().numpy(), ob) and np.array_equal(ra.cpu().numpy(), rb), t
+        assert np.array_equal(ta.cpu().numpy(), tb) and np.array_equal(ua.cpu().numpy(), ub), t
+    sa, sb = a.state_dict(), b.state_dict()
+    for k in sa:
+        assert np.array_equal(sa[k], sb[k]), k
