@@ -25,6 +25,9 @@ REGISTRY = {
     "highway-fast-v0": "highwayenv_b200.envs.highway_env:BatchedHighwayEnvFast",
     "roundabout-v0": "highwayenv_b200.envs.roundabout_env:BatchedRoundaboutEnv",
     "intersection-v0": "highwayenv_b200.envs.intersection_env:BatchedIntersectionEnv",
+    # ConnectedLaneNeighboursMixin variants (neighbour search across lane segments)
+    "roundabout-v1": "highwayenv_b200.envs.roundabout_env:BatchedConnectedLaneRoundaboutEnv",
+    "intersection-v2": "highwayenv_b200.envs.intersection_env:BatchedConnectedLaneIntersectionEnv",
 }
 
 

@@ -108,7 +108,7 @@ class HwyNetParams(C.Structure):
             "lane_change_min_acc_gain", "lane_change_max_braking_imposed", "lane_change_delay",
             "perception_distance")]
         + [(n, C.c_int32) for n in ("regulated", "action_mode", "reward_type", "obs_features", "offroad_terminal",
-                                    "dynamic_population")]
+                                    "dynamic_population", "connected_lanes", "_pad_net")]
         + [(n, C.c_double) for n in ("arrived_reward", "reward_speed_lo", "reward_speed_hi")]
     )
 

@@ -165,3 +165,16 @@ def intersection_default_config() -> dict:
 
 
 DEFAULTS["intersection-v0"] = intersection_default_config
+
+
+def _connected(base):
+    """ConnectedLaneNeighboursMixin.default_config (envs/common/abstract.py:26-37)."""
+    def make() -> dict:
+        config = base()
+        update_config(config, {"neighbour_vehicles_connected_lanes": True})
+        return config
+    return make
+
+
+DEFAULTS["roundabout-v1"] = _connected(roundabout_default_config)
+DEFAULTS["intersection-v2"] = _connected(intersection_default_config)

@@ -255,33 +255,59 @@ __device__ __forceinline__ void follow_road(const GraphShared& g, EnvStage<G, RE
         st.tgt[v] = next_lane(g, st, v, st.tgt[v]);
 }
 
-// road/road.py:483-547 neighbour_vehicles, same-segment search
+// road/road.py:483-547 neighbour_vehicles.  `connected` = config["neighbour_vehicles_connected_lanes"]
+// (ConnectedLaneNeighboursMixin, abstract.py:26-37; road.py:509-529): the lanes continuing `lane_idx` (every road
+// leaving its end node: lane _id, or lane 0 when that road has fewer lanes) are searched with offset +length and
+// the lanes leading into its start node (from-nodes in graph order = table order) with offset -their length; a
+// vehicle counts on the FIRST lane of that list it is on.
 template <int G, bool REG>
 __device__ __noinline__ void neighbours(const GraphShared& g, const EnvStage<G, REG>& st, int V, int veh,
-                                        int lane_idx, int& front, int& rear) {
+                                        int lane_idx, bool connected, int& front, int& rear) {
+    constexpr int kMaxSearch = 16;
     const HwyNetLane& L = g.lanes[lane_idx];
     const double s = lane_idx == st.lane[veh] ? st.own_s[veh] : lane_s_of(L, st.x[veh], st.y[veh]);
-    const double gate = L.width / 2 + 1.0;  // the lateral half of on_lane(margin=1)
+    unsigned char lanes[kMaxSearch];
+    int n_l = 1;
+    lanes[0] = (unsigned char)lane_idx;
+    int n_next = 0;
+    if (connected) {
+        for (int k = 0; k < g.succ_count[L.to_node] && n_l < kMaxSearch; ++k) {
+            const int f = g.succ[L.to_node][k];
+            lanes[n_l++] = (unsigned char)(f + (L.lane_id < g.lanes[f].road_count ? L.lane_id : 0));
+        }
+        n_next = n_l - 1;
+        for (int l = 0; l < g.n_lanes && n_l < kMaxSearch; ++l) {
+            const HwyNetLane& P0 = g.lanes[l];
+            if (P0.lane_id != 0 || P0.to_node != L.from_node) continue;
+            lanes[n_l++] = (unsigned char)(l + (L.lane_id < P0.road_count ? L.lane_id : 0));
+        }
+    }
     double s_front = 0, s_rear = 0;
     front = -1;
     rear = -1;
     for (int v = 0; v < V; ++v) {
         if (v == veh) continue;
-        double s_v, lat_v;
-        if (st.lane[v] == lane_idx) {
-            s_v = st.own_s[v];
-            lat_v = st.own_lat[v];
-        } else if (!lane_local_gated(L, st.x[v], st.y[v], gate, s_v, lat_v)) {
-            continue;
-        }
-        if (!lane_on(L, s_v, lat_v, 1.0)) continue;
-        if (s <= s_v && (front < 0 || s_v <= s_front)) {
-            s_front = s_v;
-            front = v;
-        }
-        if (s_v < s && (rear < 0 || s_v > s_rear)) {
-            s_rear = s_v;
-            rear = v;
+        for (int k = 0; k < n_l; ++k) {
+            const int sl = lanes[k];
+            const HwyNetLane& SL = g.lanes[sl];
+            double s_v, lat_v;
+            if (st.lane[v] == sl) {
+                s_v = st.own_s[v];
+                lat_v = st.own_lat[v];
+            } else if (!lane_local_gated(SL, st.x[v], st.y[v], SL.width / 2 + 1.0, s_v, lat_v)) {
+                continue;  // the lateral half of on_lane(margin=1) already fails
+            }
+            if (!lane_on(SL, s_v, lat_v, 1.0)) continue;
+            if (k > 0) s_v += k <= n_next ? L.length : -SL.length;
+            if (s <= s_v && (front < 0 || s_v <= s_front)) {
+                s_front = s_v;
+                front = v;
+            }
+            if (s_v < s && (rear < 0 || s_v > s_rear)) {
+                s_rear = s_v;
+                rear = v;
+            }
+            break;  // matched on this lane
         }
     }
 }
@@ -325,11 +351,11 @@ template <int G, bool REG>
 __device__ __noinline__ bool mobil(const HwyNetParams& P, const GraphShared& g, const EnvStage<G, REG>& st, int V,
                                    int v, double delta, int lane_index) {
     int new_preceding, new_following;
-    neighbours(g, st, V, v, lane_index, new_preceding, new_following);
+    neighbours(g, st, V, v, lane_index, P.connected_lanes != 0, new_preceding, new_following);
     double new_following_pred_a = idm_acceleration(P, g, st, delta, new_following, v);
     if (new_following_pred_a < -P.lane_change_max_braking_imposed) return false;
     int old_preceding, old_following;
-    neighbours(g, st, V, v, st.lane[v], old_preceding, old_following);
+    neighbours(g, st, V, v, st.lane[v], P.connected_lanes != 0, old_preceding, old_following);
     double self_pred_a = idm_acceleration(P, g, st, delta, v, new_preceding);
     if (st.route_len[v] > 0 && RT_ID(st.route[v][0]) >= 0) {
         int tid = g.lanes[st.tgt[v]].lane_id, cid = g.lanes[lane_index].lane_id;
@@ -1010,10 +1036,10 @@ __device__ __forceinline__ void substep(const HwyNetParams& P, const GraphShared
         if (kind == HWY_KIND_IDM) {
             if (!crashed) {
                 int f, rr;
-                neighbours(g, st, V, i, lane, f, rr);
+                neighbours(g, st, V, i, lane, P.connected_lanes != 0, f, rr);
                 double acc = idm_acceleration(P, g, st, r.delta, i, f);
                 if (lane != tgt) {
-                    neighbours(g, st, V, i, tgt, f, rr);
+                    neighbours(g, st, V, i, tgt, P.connected_lanes != 0, f, rr);
                     acc = fmin(acc, idm_acceleration(P, g, st, r.delta, i, f));
                 }
                 act_accel = clipd(acc, -P.acc_max, P.acc_max);

@@ -183,6 +183,7 @@ class BatchedIntersectionEnv:
         p.lane_change_max_braking_imposed, p.lane_change_delay = 2.0, 1.0
         p.perception_distance = 200.0
         p.regulated, p.reward_type, p.dynamic_population = 1, 1, 1
+        p.connected_lanes = int(bool(cfg.get("neighbour_vehicles_connected_lanes", False)))
         self._params = p
         self.observation_space = batch_space(self.single_observation_space, self.num_envs)
         self.action_space = batch_space(self.single_action_space, self.num_envs)
@@ -502,3 +503,10 @@ class BatchedIntersectionEnv:
     @property
     def unwrapped(self):
         return self
+
+
+class BatchedConnectedLaneIntersectionEnv(BatchedIntersectionEnv):
+    """`intersection-v2`: ConnectedLaneNeighboursMixin (envs/common/abstract.py:26-37) — `neighbour_vehicles` also
+    searches the lane segments connected to the queried lane (road/road.py:509-529)."""
+
+    ENV_ID = "intersection-v2"

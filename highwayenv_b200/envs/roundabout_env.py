@@ -254,6 +254,7 @@ class BatchedRoundaboutEnv:
         p.politeness, p.lane_change_min_acc_gain = 0.0, 0.2
         p.lane_change_max_braking_imposed, p.lane_change_delay = 2.0, 1.0
         p.perception_distance = 200.0
+        p.connected_lanes = int(bool(cfg.get("neighbour_vehicles_connected_lanes", False)))
         self._params = p
         self.single_action_space = Discrete(5)
         self.spawner = RoundaboutSpawner(self.net, self.config, self.action_type.target_speeds)
@@ -474,3 +475,10 @@ class BatchedRoundaboutEnv:
         self._time.copy_(torch.from_numpy(np.asarray(sd["time"], dtype=np.float64).reshape(n)))
         if self._rngs is None:
             self._seed_streams(0)
+
+
+class BatchedConnectedLaneRoundaboutEnv(BatchedRoundaboutEnv):
+    """`roundabout-v1`: ConnectedLaneNeighboursMixin (envs/common/abstract.py:26-37) — `neighbour_vehicles` also
+    searches the lane segments connected to the queried lane (road/road.py:509-529)."""
+
+    ENV_ID = "roundabout-v1"

@@ -244,6 +244,9 @@ typedef struct HwyNetParams {
     int32_t obs_features;       /* Kinematics columns: 5, or 7 with cos_h, sin_h */
     int32_t offroad_terminal;
     int32_t dynamic_population; /* per-step _clear_vehicles / _spawn_vehicle (intersection_env.py:136-140) */
+    int32_t connected_lanes;    /* config["neighbour_vehicles_connected_lanes"]: roundabout-v1, intersection-v2
+                                 * (abstract.py:26-37, road/road.py:509-529) */
+    int32_t _pad_net;
     double arrived_reward, reward_speed_lo, reward_speed_hi;
 } HwyNetParams;
 

@@ -62,6 +62,9 @@ CASES = {
     "intersection_kin": ("intersection-v0", None, list(range(600, 606)), 13, "discrete3"),
     "intersection_grid": ("intersection-v0", {"observation": {"type": "OccupancyGrid"}},
                           list(range(700, 706)), 13, "discrete3"),
+    # (f)3 connected-lane neighbour search (ConnectedLaneNeighboursMixin, abstract.py:26-37; road.py:509-529)
+    "roundabout_v1_kin": ("roundabout-v1", None, list(range(900, 906)), 11, "discrete5"),
+    "intersection_v2_kin": ("intersection-v2", None, list(range(910, 916)), 13, "discrete3"),
 }
 
 

@@ -287,24 +287,52 @@ static inline double lane_distance_to(const World *w, int self, int other) {
     return lane_s(L, w->s->x[other], w->s->y[other]) - lane_s(L, w->s->x[self], w->s->y[self]);
 }
 
-/* road/road.py:483-547 neighbour_vehicles (same-segment search) */
+/* road/road.py:483-547 neighbour_vehicles.  With neighbour_vehicles_connected_lanes (:509-529) the lanes
+ * that continue `lane_index` (every road leaving its end node: lane _id, or lane 0 when that road has fewer
+ * lanes) are searched with offset +length, and the lanes leading into its start node (from-nodes in graph
+ * insertion order) with offset -their length; a vehicle is counted on the FIRST lane of that list it is on. */
 static void neighbour_vehicles(const World *w, int veh, int lane_idx, int *front, int *rear) {
     const NetLane *L = LANE(w, lane_idx);
     double s = lane_s(L, w->s->x[veh], w->s->y[veh]);
     double s_front = 0, s_rear = 0;
     int v_front = -1, v_rear = -1;
+    int lanes[1 + NET_MAX_SUCC + NET_MAX_NODES];
+    double offsets[1 + NET_MAX_SUCC + NET_MAX_NODES];
+    int n_l = 0;
+    lanes[n_l] = lane_idx;
+    offsets[n_l++] = 0.0;
+    if (w->c->connected_lanes) {
+        const NetGraph *g = w->g;
+        for (int k = 0; k < g->succ_count[L->to_node]; k++) {
+            const NetLane *N0 = &g->lanes[g->succ[L->to_node][k]];
+            lanes[n_l] = g->succ[L->to_node][k] + (L->lane_id < N0->road_count ? L->lane_id : 0);
+            offsets[n_l++] = L->length;
+        }
+        for (int l = 0; l < g->n_lanes; l++) { /* table order == graph.values() order of the from-nodes */
+            const NetLane *P0 = &g->lanes[l];
+            if (P0->lane_id != 0 || P0->to_node != L->from_node) continue;
+            int pl = l + (L->lane_id < P0->road_count ? L->lane_id : 0);
+            lanes[n_l] = pl;
+            offsets[n_l++] = -g->lanes[pl].length;
+        }
+    }
     for (int v = 0; v < w->V; v++) {
         if (v == veh) continue;
-        double s_v, lat_v;
-        net_lane_local(L, w->s->x[v], w->s->y[v], &s_v, &lat_v);
-        if (!lane_on_lane(L, s_v, lat_v, 1.0)) continue;
-        if (s <= s_v && (v_front < 0 || s_v <= s_front)) {
-            s_front = s_v;
-            v_front = v;
-        }
-        if (s_v < s && (v_rear < 0 || s_v > s_rear)) {
-            s_rear = s_v;
-            v_rear = v;
+        for (int k = 0; k < n_l; k++) {
+            const NetLane *SL = LANE(w, lanes[k]);
+            double s_v, lat_v;
+            net_lane_local(SL, w->s->x[v], w->s->y[v], &s_v, &lat_v);
+            if (!lane_on_lane(SL, s_v, lat_v, 1.0)) continue;
+            s_v += offsets[k];
+            if (s <= s_v && (v_front < 0 || s_v <= s_front)) {
+                s_front = s_v;
+                v_front = v;
+            }
+            if (s_v < s && (v_rear < 0 || s_v > s_rear)) {
+                s_rear = s_v;
+                v_rear = v;
+            }
+            break; /* matched on this lane */
         }
     }
     *front = v_front;

@@ -74,7 +74,7 @@ typedef struct NetCfg {
     int32_t reward_type;      /* 0 roundabout, 1 intersection */
     int32_t obs_features;     /* Kinematics: 5, or 7 with cos_h, sin_h */
     int32_t offroad_terminal;
-    int32_t _pad2;
+    int32_t connected_lanes;  /* config["neighbour_vehicles_connected_lanes"] (abstract.py:26-37, road.py:509-529) */
     double arrived_reward, reward_speed_lo, reward_speed_hi;
 } NetCfg;
 

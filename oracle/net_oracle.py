@@ -48,7 +48,7 @@ class NetCfg(C.Structure):
             "politeness", "lane_change_min_acc_gain", "lane_change_max_braking_imposed", "lane_change_delay",
             "perception_distance")]
         + [(k, C.c_int32) for k in ("regulated", "action_mode", "reward_type", "obs_features", "offroad_terminal",
-                                    "_pad2")]
+                                    "connected_lanes")]
         + [(k, C.c_double) for k in ("arrived_reward", "reward_speed_lo", "reward_speed_hi")]
     )
 
@@ -172,6 +172,7 @@ def cfg_from_dict(config: dict, n_vehicles: int = 5) -> NetCfg:
         c.arrived_reward = float(config["arrived_reward"])
         c.reward_speed_lo, c.reward_speed_hi = (float(v) for v in config["reward_speed_range"])
         c.offroad_terminal = int(bool(config["offroad_terminal"]))
+    c.connected_lanes = int(bool(config.get("neighbour_vehicles_connected_lanes", False)))
     c.politeness, c.lane_change_min_acc_gain = 0.0, 0.2
     c.lane_change_max_braking_imposed, c.lane_change_delay = 2.0, 1.0
     c.perception_distance = 200.0

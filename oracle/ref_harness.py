@@ -52,6 +52,8 @@ ENV_CLASSES = {
     "highway-fast-v0": ("highway_env.envs.highway_env", "HighwayEnvFast"),
     "intersection-v0": ("highway_env.envs.intersection_env", "IntersectionEnv"),
     "roundabout-v0": ("highway_env.envs.roundabout_env", "RoundaboutEnv"),
+    "roundabout-v1": ("highway_env.envs.roundabout_env", "ConnectedLaneRoundaboutEnv"),
+    "intersection-v2": ("highway_env.envs.intersection_env", "ConnectedLaneIntersectionEnv"),
 }
 
 

@@ -9,7 +9,7 @@ from parity_utils import load_golden
 from test_net_oracle_golden import compare_inter, inter_state
 
 pytestmark = pytest.mark.gpu
-CASES = ["intersection_kin", "intersection_grid"]
+CASES = ["intersection_kin", "intersection_grid", "intersection_v2_kin"]
 V = 32
 
 
@@ -88,7 +88,7 @@ def test_teacher_forced_vs_reference(name):
             assert np.array_equal(sd["rng"][:, i], g["rng_words"][i, t + 1]), ctx  # device PCG64 == numpy stream
 
 
-@pytest.mark.parametrize("name,n,T", [("intersection_kin", 96, 10), ("intersection_grid", 64, 10)])
+@pytest.mark.parametrize("name,n,T", [("intersection_kin", 96, 10), ("intersection_grid", 64, 10), ("intersection_v2_kin", 96, 10)])
 def test_teacher_forced_vs_oracle_many_envs(name, n, T):
     g = load_golden(name)
     ob = no.IntersectionOracle(no.graph_from_arrays(g), no.cfg_from_dict(g["config"]), n, g, g["config"])

@@ -7,7 +7,7 @@ import net_oracle as no
 from parity_utils import compare_state, golden_state, load_golden, well_conditioned
 
 pytestmark = pytest.mark.gpu
-CASES = ["roundabout_kin", "roundabout_ttc"]
+CASES = ["roundabout_kin", "roundabout_ttc", "roundabout_v1_kin"]
 
 
 def make_env(cfg, n, **kw):
@@ -117,7 +117,7 @@ def test_free_running_vs_reference(name):
     assert compared >= 3 * S
 
 
-@pytest.mark.parametrize("name,n,T", [("roundabout_ttc", 256, 11), ("roundabout_kin", 128, 11)])
+@pytest.mark.parametrize("name,n,T", [("roundabout_ttc", 256, 11), ("roundabout_kin", 128, 11), ("roundabout_v1_kin", 128, 11)])
 def test_teacher_forced_vs_oracle_many_envs(name, n, T):
     g = load_golden(name)
     graph = no.graph_from_arrays(g)

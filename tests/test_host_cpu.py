@@ -157,15 +157,21 @@ def test_network_tables_match_the_reference_dump():
     assert sum(l["exit_lane"] for l in net.lanes) == 4 and sorted({l["priority"] for l in net.lanes}) == [0, 1, 2, 3]
 
 
-def test_intersection_defaults_match_reference_config():
+def test_network_env_defaults_match_reference_config():
+    """intersection-v0/v2, roundabout-v0/v1 (the v1/v2 ids = ConnectedLaneNeighboursMixin defaults)"""
+    import highwayenv_b200 as hb
     from highwayenv_b200.config import default_config
     from parity_utils import load_golden
 
-    ref = dict(load_golden("intersection_kin")["config"])
-    ref.pop("_env_id"), ref.pop("_others_check_collisions")
-    ours = default_config("intersection-v0")
-    ours["offscreen_rendering"] = ref["offscreen_rendering"]
-    assert ours == ref
+    for name in ("intersection_kin", "intersection_v2_kin", "roundabout_kin", "roundabout_v1_kin"):
+        ref = dict(load_golden(name)["config"])
+        env_id = ref.pop("_env_id")
+        ref.pop("_others_check_collisions")
+        assert env_id in hb.REGISTRY
+        ours = default_config(env_id)
+        ours["offscreen_rendering"] = ref["offscreen_rendering"]
+        assert ours == ref, name
+    assert default_config("roundabout-v1")["neighbour_vehicles_connected_lanes"] is True
 
 
 def test_no_silent_cpu_fallback():

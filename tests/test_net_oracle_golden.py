@@ -6,7 +6,7 @@ import pytest
 import net_oracle as no
 from parity_utils import compare_state, golden_state, load_golden, well_conditioned
 
-CASES = ["roundabout_kin", "roundabout_ttc"]
+CASES = ["roundabout_kin", "roundabout_ttc", "roundabout_v1_kin"]
 
 
 def golden_net_state(g, i, t):
@@ -82,7 +82,7 @@ def test_free_running_prefix(name):
 
 
 # ------------------------------------------------------------------ intersection-v0
-INTER = ["intersection_kin", "intersection_grid"]
+INTER = ["intersection_kin", "intersection_grid", "intersection_v2_kin"]
 _IKEYS = ("x", "y", "heading", "speed", "target_speed", "timer", "delta", "lane", "target_lane", "crashed",
           "impact", "check_collisions", "speed_index", "time", "route", "route_len", "kind", "is_yielding",
           "count", "road_steps")
