@@ -70,8 +70,8 @@ class BatchedHighwayEnv:
         self.device = torch.device(device if device is not None else "cuda")
         if self.device.type != "cuda":
             raise RuntimeError("highwayenv_b200 only runs on CUDA devices")
-        if autoreset_mode not in ("SameStep", "Disabled"):
-            raise NotImplementedError(f"autoreset_mode {autoreset_mode!r} (SameStep and Disabled are implemented)")
+        if autoreset_mode not in ("SameStep", "NextStep", "Disabled"):
+            raise ValueError(f"autoreset_mode {autoreset_mode!r} (SameStep, NextStep, Disabled)")
         self.autoreset_mode = autoreset_mode
         self.env_index_offset = int(env_index_offset)
         self.config = self.default_config()
@@ -236,6 +236,7 @@ class BatchedHighwayEnv:
         with torch.cuda.device(self.device):
             N.check(self._lib.hwy_highway_reset(C.byref(self._params), C.byref(self._state), mask_ptr,
                                                 self._obs.data_ptr(), self._stream()))
+        self._autoreset_envs = None
         info = {"speed": self._hs[:, 0, 1], "crashed": (self._meta[:, 0] & N.META_CRASHED) != 0}
         return self._obs, info
 
@@ -288,8 +289,26 @@ class BatchedHighwayEnv:
         info = {"speed": self._info_speed, "crashed": self._info_crashed.view(torch.bool), "action": act}
         if same_step:
             info["final_obs"] = self._final_obs
+        elif self.autoreset_mode == "NextStep":
+            self._next_step_autoreset()
         return (self._obs, self._reward, self._terminated.view(torch.bool),
                 self._truncated.view(torch.bool), info)
+
+    def _next_step_autoreset(self) -> None:
+        """gymnasium AutoresetMode.NEXT_STEP (the vector default): an env that ended in the previous step is
+        reset by this call instead of stepped — reset observation, reward 0, both flags False.  The step
+        kernel has already advanced those envs; their state is simply replaced by the masked device reset
+        (stepping draws nothing from the env's generator on this road family)."""
+        prev = getattr(self, "_autoreset_envs", None)
+        if prev is not None:
+            with torch.cuda.device(self.device):
+                N.check(self._lib.hwy_highway_reset(C.byref(self._params), C.byref(self._state), prev.data_ptr(),
+                                                    self._obs.data_ptr(), self._stream()))
+            keep = prev == 0
+            self._reward.mul_(keep)
+            self._terminated.mul_(keep)
+            self._truncated.mul_(keep)
+        self._autoreset_envs = (self._terminated | self._truncated).contiguous()
 
     def host_stepper(self) -> "HostStepper":
         """Host-buffer stepping through one CUDA graph (see HostStepper)."""

@@ -85,8 +85,10 @@ class BatchedIntersectionEnv:
             raise NotImplementedError("rendering is out of scope of the accelerated path")
         if not torch.cuda.is_available():
             raise RuntimeError("highwayenv_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
-        if autoreset_mode not in ("SameStep", "Disabled"):
-            raise NotImplementedError(autoreset_mode)
+        if autoreset_mode not in ("SameStep", "NextStep", "Disabled"):
+            raise ValueError(autoreset_mode)
+        if autoreset_mode == "NextStep" and reset_mode != "device":
+            raise NotImplementedError("NextStep autoreset uses the device reset")
         if reset_mode not in ("device", "host"):
             raise ValueError(reset_mode)
         self.reset_mode = reset_mode
@@ -456,6 +458,7 @@ class BatchedIntersectionEnv:
                 self._sync_host_rngs(ids)
             if len(ids):
                 self._reset_envs(ids)
+        self._autoreset_envs = None
         self.observe()
         return self._obs, {"speed": self._info_speed, "crashed": self._info_crashed.view(torch.bool)}
 
@@ -476,6 +479,8 @@ class BatchedIntersectionEnv:
             a = actions.cpu().numpy() if isinstance(actions, torch.Tensor) else np.asarray(actions)
             buf.copy_(torch.from_numpy(np.ascontiguousarray(a.reshape(tuple(buf.shape)))).to(buf.dtype), non_blocking=True)
             act = buf
+        prev = getattr(self, "_autoreset_envs", None) if self.autoreset_mode == "NextStep" else None
+        rng_before = self._rng.clone() if prev is not None else None  # a step draws from the env's generator
         with torch.cuda.device(self.device):
             N.check(self._lib.hwy_intersection_step(
                 C.byref(self._params), self._graph_dev.data_ptr(), C.byref(self._spawn_struct), C.byref(self._state),
@@ -486,6 +491,17 @@ class BatchedIntersectionEnv:
             info["final_obs"] = self._final_obs
             self._device_reset(self._terminated.data_ptr(), self._truncated.data_ptr(), self._obs.data_ptr(),
                                self._final_obs.data_ptr())
+        elif self.autoreset_mode == "NextStep":
+            # gymnasium NEXT_STEP: envs that ended in the previous step are reset by this call instead of stepped;
+            # their generator is rewound to where the episode ended, then _make_vehicles runs on the device
+            if prev is not None:
+                self._rng.copy_(torch.where(prev.bool().unsqueeze(0), rng_before, self._rng))
+                self._device_reset(prev.data_ptr(), None, self._obs.data_ptr(), None)
+                keep = prev == 0
+                self._reward.mul_(keep)
+                self._terminated.mul_(keep)
+                self._truncated.mul_(keep)
+            self._autoreset_envs = (self._terminated | self._truncated).contiguous()
         elif self.autoreset_mode == "SameStep":
             done = (self._terminated | self._truncated).cpu().numpy().astype(bool)
             if done.any():

@@ -173,8 +173,10 @@ class BatchedRoundaboutEnv:
             raise NotImplementedError("rendering is out of scope of the accelerated path")
         if not torch.cuda.is_available():
             raise RuntimeError("highwayenv_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
-        if autoreset_mode not in ("SameStep", "Disabled"):
-            raise NotImplementedError(autoreset_mode)
+        if autoreset_mode not in ("SameStep", "NextStep", "Disabled"):
+            raise ValueError(autoreset_mode)
+        if autoreset_mode == "NextStep" and reset_mode != "device":
+            raise NotImplementedError("NextStep autoreset uses the device reset")
         self._lib = N.load()
         self.render_mode = None
         self.num_envs = int(num_envs)
@@ -389,6 +391,7 @@ class BatchedRoundaboutEnv:
             ids = np.arange(self.num_envs) if mask is None else np.nonzero(mask)[0]
             if len(ids):
                 self._upload(ids, self._spawn(ids))
+        self._autoreset_envs = None
         self.observe()
         return self._obs, {"speed": self._hs[:, 0, 1], "crashed": (self._meta[:, 0] & N.META_CRASHED) != 0}
 
@@ -420,6 +423,15 @@ class BatchedRoundaboutEnv:
             self._final_obs.copy_(self._obs)
             info["final_obs"] = self._final_obs
             self._device_reset(self._terminated.data_ptr(), self._truncated.data_ptr(), self._obs.data_ptr())
+        elif self.autoreset_mode == "NextStep":  # see BatchedHighwayEnv._next_step_autoreset
+            prev = getattr(self, "_autoreset_envs", None)
+            if prev is not None:
+                self._device_reset(prev.data_ptr(), None, self._obs.data_ptr())
+                keep = prev == 0
+                self._reward.mul_(keep)
+                self._terminated.mul_(keep)
+                self._truncated.mul_(keep)
+            self._autoreset_envs = (self._terminated | self._truncated).contiguous()
         elif self.autoreset_mode == "SameStep":
             done = (self._terminated | self._truncated).cpu().numpy().astype(bool)
             if done.any():

@@ -294,3 +294,47 @@ def test_host_stepper_graph_matches_env_step():
     sa, sb = a.state_dict(), b.state_dict()
     for k in sa:
         assert np.array_equal(sa[k], sb[k]), k
+
+
+def test_next_step_autoreset_matches_gymnasium_semantics():
+    """AutoresetMode.NEXT_STEP (gymnasium's vector default): an env that ended is RESET by the next step call
+    (reset obs, reward 0, flags False) instead of being stepped.  Emulated with the oracle exactly as
+    SyncVectorEnv does it, teacher-forced every step; spawns and generator streams must stay bit-identical."""
+    name, n, T = "highway_fast_v20", 96, 45
+    g, cfg, oc, ob = _oracle_pair(name, n, 13000)
+    cfg = dict(cfg)
+    cfg["duration"] = 6
+    oc = ho.cfg_from_dict(cfg)
+    ob = ho.OracleBatch(oc, n, seeds=range(13000, 13000 + n), threads=8)
+    env = make_env(cfg, n, autoreset_mode="NextStep")
+    obs0, _ = env.reset(seed=13000)
+    assert np.array_equal(obs0.cpu().numpy(), ob.reset())
+    rng = np.random.default_rng(8)
+    pending = np.zeros(n, dtype=bool)
+    n_resets = 0
+    for t in range(T):
+        env.load_state_dict({k: ob.a[k].copy() for k in ob.a})
+        act = rng.integers(0, 5, size=n).astype(np.int32)
+        snap = {k: ob.a[k].copy() for k in ob.a}
+        snap_rng = ob.rng.copy()
+        o_obs, o_rew, o_term, o_trunc = (x.copy() for x in ob.step(act))
+        if pending.any():  # those envs are reset instead of stepped
+            for k in ob.a:
+                ob.a[k][pending] = snap[k][pending]
+            ob.rng[pending] = snap_rng[pending]
+            o_obs[pending] = ob.reset(mask=pending.astype(np.uint8))[pending]
+            o_rew[pending], o_term[pending], o_trunc[pending] = 0.0, 0, 0
+            n_resets += int(pending.sum())
+        obs, rew, term, trunc, _ = env.step(act)
+        sd = env.state_dict()
+        assert np.array_equal(term.cpu().numpy(), o_term.astype(bool)) and np.array_equal(trunc.cpu().numpy(), o_trunc.astype(bool)), t
+        assert np.max(np.abs(rew.cpu().numpy() - o_rew)) <= 1e-9, t
+        assert np.all(rew.cpu().numpy()[pending] == 0.0)
+        assert np.array_equal(obs.cpu().numpy()[pending], o_obs[pending]), t      # reset observations: bit-exact
+        assert np.max(np.abs(obs.cpu().numpy() - o_obs)) <= 1e-6, t
+        for k in ("x", "y", "speed", "delta", "timer"):
+            assert np.array_equal(sd[k][pending], ob.a[k][pending]), (t, k)
+        assert np.array_equal(sd["time"], ob.a["time"])
+        assert np.array_equal(sd["rng"][0], ob.rng["state_hi"]) and np.array_equal(sd["rng"][1], ob.rng["state_lo"])
+        pending = (o_term | o_trunc).astype(bool)
+    assert n_resets > n

@@ -231,3 +231,43 @@ def test_16_slot_and_32_slot_paths_agree():
                 x, y = np.where(m, x, 0), np.where(m, y, 0)
             assert np.array_equal(x, y), (t, k)
     assert small > 0 and large > 0, (small, large)
+
+
+@pytest.mark.parametrize("env_name", ["intersection_kin", "roundabout_kin"])
+def test_next_step_autoreset_bookkeeping(env_name):
+    """NEXT_STEP on the network envs: the call after an episode end returns the reset observation with reward 0
+    and clear flags, the env restarts at time 0, and (intersection) the reset continues the env's generator from
+    where the episode ended — the same stream the SameStep twin consumes."""
+    g = load_golden(env_name)
+    n = 64
+    a = make_env(g["config"], n, autoreset_mode="NextStep")
+    b = make_env(g["config"], n, autoreset_mode="SameStep")
+    a.reset(seed=31)
+    b.reset(seed=31)
+    n_act = 3 if env_name.startswith("intersection") else 5
+    rng = np.random.default_rng(6)
+    pending = np.zeros(n, dtype=bool)
+    first_done_checked = 0
+    for t in range(30):
+        act = rng.integers(0, n_act, size=n).astype(np.int32)
+        obs, rew, term, trunc, _ = a.step(act)
+        sd = a.state_dict()
+        rew, term, trunc = rew.cpu().numpy(), term.cpu().numpy(), trunc.cpu().numpy()
+        assert np.all(rew[pending] == 0) and not term[pending].any() and not trunc[pending].any()
+        assert np.all(sd["time"][pending] == 0) and np.all(sd["time"][~pending] > 0)
+        if t < 14:
+            # until an env's first episode end both twins see identical histories; SameStep resets in the
+            # ending step, NextStep one call later — from the same generator state, so the fresh populations match
+            ob_, rb, tb, ub, _ = b.step(act)
+            sb = b.state_dict()
+            fresh = pending & (first_seen == t - 1) if t else pending
+            for k in ("x", "y", "speed"):
+                if fresh.any():
+                    live = (np.arange(sd[k].shape[1])[None, :] < sd["count"][:, None]) if "count" in sd else np.ones_like(sd[k], bool)
+                    assert np.allclose(np.where(live, sd[k], 0)[fresh], np.where(live, snap[k], 0)[fresh], rtol=0, atol=1e-9), (t, k)
+            first_done_checked += int(fresh.sum())
+            done_b = (tb | ub).cpu().numpy()
+            snap = sb
+            first_seen = np.where(done_b & (first_seen < 0), t, first_seen) if t else np.where(done_b, 0, -1)
+        pending = term | trunc
+    assert first_done_checked > 0
