@@ -108,7 +108,7 @@ class HwyNetParams(C.Structure):
             "lane_change_min_acc_gain", "lane_change_max_braking_imposed", "lane_change_delay",
             "perception_distance")]
         + [(n, C.c_int32) for n in ("regulated", "action_mode", "reward_type", "obs_features", "offroad_terminal",
-                                    "dynamic_population", "connected_lanes", "_pad_net")]
+                                    "dynamic_population", "connected_lanes", "n_agents")]
         + [(n, C.c_double) for n in ("arrived_reward", "reward_speed_lo", "reward_speed_hi")]
     )
 
@@ -146,7 +146,7 @@ EXPORTS = (
     "hwy_abi_version", "hwy_last_error", "hwy_highway_slot_stride", "hwy_highway_reset",
     "hwy_highway_observe", "hwy_highway_step", "hwy_highway_autoreset", "hwy_launch_count",
     "hwy_network_obs_size", "hwy_network_step", "hwy_network_observe", "hwy_roundabout_reset",
-    "hwy_intersection_step", "hwy_network_substeps", "hwy_intersection_reset",
+    "hwy_intersection_step", "hwy_network_substeps", "hwy_intersection_reset", "hwy_intersection_step_agents",
 )
 
 _lib = None
@@ -190,6 +190,8 @@ def load():
     lib.hwy_intersection_step.restype = C.c_int
     lib.hwy_intersection_step.argtypes = [NP, NG, C.POINTER(HwyIntersectionSpawn), NS, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.hwy_intersection_step_agents.restype = C.c_int
+    lib.hwy_intersection_step_agents.argtypes = [NP, NG, C.POINTER(HwyIntersectionSpawn), NS] + [C.c_void_p] * 10
     lib.hwy_intersection_reset.restype = C.c_int
     lib.hwy_intersection_reset.argtypes = [NP, NG, C.POINTER(HwyIntersectionSpawn), NS, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_void_p]

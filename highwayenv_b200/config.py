@@ -178,3 +178,34 @@ def _connected(base):
 
 DEFAULTS["roundabout-v1"] = _connected(roundabout_default_config)
 DEFAULTS["intersection-v2"] = _connected(intersection_default_config)
+
+
+def multi_agent_intersection_default_config() -> dict:
+    """MultiAgentIntersectionEnv.default_config (envs/intersection_env.py:376-420)."""
+    config = intersection_default_config()
+    update_config(config, {
+        "action": {
+            "type": "MultiAgentAction",
+            "action_config": {"type": "DiscreteMetaAction", "lateral": False, "longitudinal": True,
+                              "target_speeds": [0, 4.5, 9]},
+        },
+        "observation": {
+            "type": "MultiAgentObservation",
+            "observation_config": {
+                "type": "Kinematics",
+                "vehicles_count": 15,
+                "features": ["presence", "x", "y", "vx", "vy", "cos_h", "sin_h"],
+                "features_range": {"x": [-100, 100], "y": [-100, 100], "vx": [-20, 20], "vy": [-20, 20]},
+                "absolute": True,
+                "flatten": False,
+                "observe_intentions": False,
+            },
+        },
+        "controlled_vehicles": 2,
+    })
+    return config
+
+
+DEFAULTS["intersection-multi-agent-v0"] = multi_agent_intersection_default_config
+DEFAULTS["intersection-multi-agent-v1"] = multi_agent_intersection_default_config
+DEFAULTS["intersection-multi-agent-v2"] = _connected(multi_agent_intersection_default_config)

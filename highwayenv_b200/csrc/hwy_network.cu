@@ -51,6 +51,8 @@ struct EnvStage {
     int route[G][R];
     int route_len[G];
     int count, ego, speed_index, road_steps;
+    unsigned agent_mask;    // the controlled (MDP) vehicles among the first `count` slots, list order = agent order
+    double agent_reward[4];  // per-agent rewards of the step (MultiAgent: summed in agent order)
     unsigned yield_mask;
     // spawn record (dynamic population): written by the group's first thread, adopted by the new slot
     double sp_x, sp_y, sp_h, sp_speed, sp_delta, sp_ts;
@@ -966,22 +968,52 @@ __device__ __forceinline__ void enforce_road_rules(const HwyNetParams& P, const 
     group_sync<G>();
 }
 
+__device__ __forceinline__ int n_agents_of(const HwyNetParams& P) { return P.n_agents > 1 ? P.n_agents : 1; }
+// slot of the a-th controlled vehicle (-1: none)
+__device__ __forceinline__ int agent_slot(unsigned agent_mask, int a) {
+    for (int k = 0; k < a; ++k) agent_mask &= agent_mask - 1;
+    return agent_mask ? __ffs(agent_mask) - 1 : -1;
+}
+// observation_type.observe(): one observation per controlled vehicle (MultiAgentObservation, observation.py:588-604)
+template <int G, bool REG>
+__device__ __forceinline__ void observe_agents(const HwyNetParams& P, const GraphShared& g, EnvStage<G, REG>& st, int i,
+                                               float* __restrict__ obs_env) {
+    const int A = n_agents_of(P);
+    if (A == 1) {
+        observe_any(P, g, st, st.count, i, obs_env);
+        return;
+    }
+    const int first = st.ego;
+    for (int a = 0; a < A; ++a) {
+        group_sync<G>();
+        if (i == 0) st.ego = max(agent_slot(st.agent_mask, a), 0);
+        group_sync<G>();
+        observe_any(P, g, st, st.count, i, obs_env + (size_t)a * obs_size(P));
+    }
+    group_sync<G>();
+    if (i == 0) st.ego = first;
+    group_sync<G>();
+}
+
 // ------------------------------------------------------------------ one simulation substep
 // Road.act() then [RegulatedRoad rules] Road.step(dt) for one env; all threads of the group call it.
 // `ego_label` >= 0 on the first frame of a policy step: the meta-action label of the controlled vehicle.
 template <int G, bool REG>
 __device__ __forceinline__ void substep(const HwyNetParams& P, const GraphShared& g, EnvStage<G, REG>& st, int i,
-                                        Regs& r, double& act_accel, double dt, int ego_label) {
+                                        Regs& r, double& act_accel, double dt, int ego_label,
+                                        int* my_speed_index = nullptr) {
     const int V = st.count;
     const bool active = i < V;
     const int kind = meta_kind(r.meta);
     // ---- action_type.act on the first frame: MDPVehicle.act (controller.py:295-315)
-    if (ego_label >= 0 && active && i == st.ego) {
+    // (every controlled vehicle has its own label: MultiAgentAction.act, action.py:316-321)
+    if (ego_label >= 0 && active && kind == HWY_KIND_MDP) {
         follow_road(g, st, i);
         if (ego_label == 3 || ego_label == 4) {
             int idx = speed_to_index(P, r.speed) + (ego_label == 3 ? 1 : -1);
             idx = max(0, min(idx, P.n_target_speeds - 1));
-            st.speed_index = idx;
+            if (i == st.ego) st.speed_index = idx;
+            if (my_speed_index) *my_speed_index = idx;
             r.target_speed = P.target_speeds[idx];
             st.ts[i] = r.target_speed;
         } else if (ego_label == 0 || ego_label == 2) {
@@ -1126,7 +1158,10 @@ __device__ __forceinline__ void load_env(const HwyNetParams& P, const GraphShare
     // the controlled vehicle: first MDPVehicle of the list
     unsigned is_mdp = __ballot_sync(group_mask<G>(), i < count && meta_kind(r.meta) == HWY_KIND_MDP);
     is_mdp >>= ((threadIdx.x & 31) & ~(G - 1));
-    if (i == 0) st.ego = is_mdp ? __ffs(is_mdp) - 1 : 0;
+    if (i == 0) {
+        st.ego = is_mdp ? __ffs(is_mdp) - 1 : 0;
+        st.agent_mask = is_mdp;
+    }
     group_sync<G>();
 }
 
@@ -1247,7 +1282,8 @@ network_step_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGraph* _
                     const __grid_constant__ HwyIntersectionSpawn SP, const int32_t* __restrict__ action, float* __restrict__ obs,
                     double* __restrict__ reward, uint8_t* __restrict__ terminated,
                     uint8_t* __restrict__ truncated, double* __restrict__ info_speed,
-                    uint8_t* __restrict__ info_crashed, const int* __restrict__ list) {
+                    uint8_t* __restrict__ info_crashed, const int* __restrict__ list,
+                    double* __restrict__ agents_reward, uint8_t* __restrict__ agents_terminated) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     GraphShared& g = *reinterpret_cast<GraphShared*>(smem_raw);
     EnvStage<G, REG>* stages =
@@ -1270,19 +1306,66 @@ network_step_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGraph* _
     load_env(P, g, S, st, e, i, r);
     const int frames = P.simulation_frequency / P.policy_frequency;
     const double dt = 1.0 / P.simulation_frequency;
-    const int act = action[e];
+    const int A = n_agents_of(P);
+    // this thread's agent number (controlled vehicles in list order), its action and its MDPVehicle.speed_index
+    const bool is_agent = i < st.count && meta_kind(r.meta) == HWY_KIND_MDP;
+    const int my_agent = is_agent ? min(__popc(st.agent_mask & ((1u << i) - 1u)), A - 1) : 0;
+    const int act = action[(size_t)e * A + my_agent];
     // action label: DiscreteMetaAction.ACTIONS_ALL, or ACTIONS_LONGI {0 SLOWER, 1 IDLE, 2 FASTER} (action.py:204-206)
     const int label = P.action_mode == 1 ? (act == 0 ? 4 : (act == 2 ? 3 : 1)) : act;
+    int my_speed_index = is_agent ? S.speed_index[(size_t)e * A + my_agent] : 0;
     double act_accel = 0.0;
 
-    for (int frame = 0; frame < frames; ++frame) substep(P, g, st, i, r, act_accel, dt, frame == 0 ? label : -1);
+    for (int frame = 0; frame < frames; ++frame)
+        substep(P, g, st, i, r, act_accel, dt, frame == 0 ? label : -1, &my_speed_index);
     group_sync<G>();
 
     // ---- epilogue: observation, reward, termination (before any population change)
     const int V = st.count, ego = st.ego;
-    float* obs_env = obs + (size_t)e * obs_size(P);
-    observe_any(P, g, st, V, i, obs_env);
-    if (i == ego && i < V && env_ok) {
+    float* obs_env = obs + (size_t)e * A * obs_size(P);
+    observe_agents(P, g, st, i, obs_env);
+    if (A > 1) {
+        // ---- several controlled vehicles (envs/intersection_env.py:62-134): mean of the agents' rewards, terminated
+        // when ANY crashed or ALL arrived; per-agent rewards / terminal flags for _info
+        bool is_crashed = false, arrived = false, on_road = true;
+        if (is_agent) {
+            const HwyNetLane& L = g.lanes[st.lane[i]];
+            const double es = st.own_s[i], elat = st.own_lat[i];
+            on_road = lane_on(L, es, elat, 0.0);
+            is_crashed = (r.meta & HWY_META_CRASHED) != 0;
+            arrived = L.exit_lane && es >= 25;
+            double scaled_speed = lmap(r.speed, P.reward_speed_lo, P.reward_speed_hi, 0.0, 1.0);
+            double rew = 0.0;
+            rew = rew + P.collision_reward * (is_crashed ? 1.0 : 0.0);
+            rew = rew + P.high_speed_reward * clipd(scaled_speed, 0.0, 1.0);
+            rew = rew + P.arrived_reward * (arrived ? 1.0 : 0.0);
+            rew = rew + 0.0 * (on_road ? 1.0 : 0.0);
+            if (arrived) rew = P.arrived_reward;
+            rew *= on_road ? 1.0 : 0.0;
+            if (P.normalize_reward) rew = lmap(rew, P.collision_reward, P.arrived_reward, 0.0, 1.0);
+            st.agent_reward[my_agent] = rew;
+            if (env_ok) {
+                if (agents_reward) agents_reward[(size_t)e * A + my_agent] = rew;
+                if (agents_terminated) agents_terminated[(size_t)e * A + my_agent] = (uint8_t)(is_crashed || arrived);
+                S.speed_index[(size_t)e * A + my_agent] = my_speed_index;
+            }
+        }
+        const unsigned gm = group_mask<G>();
+        const bool any_crashed = __ballot_sync(gm, is_agent && is_crashed) != 0;
+        const bool all_arrived = __ballot_sync(gm, is_agent && !arrived) == 0;
+        group_sync<G>();
+        if (i == ego && env_ok) {
+            double sum = 0.0;
+            for (int a = 0; a < A; ++a) sum = sum + st.agent_reward[a];
+            double t = S.time[e] + 1.0 / P.policy_frequency;
+            S.time[e] = t;
+            reward[e] = sum / (double)A;
+            terminated[e] = (uint8_t)(any_crashed || all_arrived || (P.offroad_terminal && !on_road));
+            truncated[e] = (uint8_t)(t >= P.duration);
+            if (info_speed) info_speed[e] = r.speed;
+            if (info_crashed) info_crashed[e] = (uint8_t)is_crashed;
+        }
+    } else if (i == ego && i < V && env_ok) {
         const HwyNetLane& L = g.lanes[st.lane[i]];
         const double es = st.own_s[i], elat = st.own_lat[i];
         const bool on_road = lane_on(L, es, elat, 0.0);
@@ -1376,7 +1459,7 @@ network_observe_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGraph
     load_env(P, g, S, st, e, i, r);
     const bool selected = (!mask_a && !mask_b) || (mask_a && mask_a[e]) || (mask_b && mask_b[e]);
     if (!selected) return;  // whole group leaves together (selection is per env)
-    observe_any(P, g, st, st.count, i, obs + (size_t)e * obs_size(P));
+    observe_agents(P, g, st, i, obs + (size_t)e * n_agents_of(P) * obs_size(P));
 }
 
 // Road.act + Road.step `n_substeps` times with no ego action (IntersectionEnv._make_vehicles warm-up)
@@ -1512,35 +1595,42 @@ intersection_reset_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGr
         if (st.count >= G) st.sp_ok = 0;
     }
     commit(HWY_KIND_IDM);
-    // ---- :291-315  the controlled vehicle on ("o0", "ir0", 0)
-    if (i == 0) {
-        const int dest = SP.ego_destination >= 0 ? SP.ego_destination : 1 + rng.choice(3);  // "o" + integers(1, 4)
-        const HwyNetLane& EL = g.lanes[SP.ego_lane];
-        const double lon = 60.0 + 5.0 * (1.0 + 1.0 * rng.normal());  // 60 + 5 * np_random.normal(1)
-        lane_position(EL, lon, 0.0, st.sp_x, st.sp_y);
-        st.sp_h = lane_heading_at(EL, 60.0);
-        st.sp_speed = EL.speed_limit;
-        int cl = 0;
-        double bd = 0;
-        for (int l = 0; l < g.n_lanes; ++l) {
-            double d = lane_distance_with_heading(g.lanes[l], st.sp_x, st.sp_y, st.sp_h);
-            if (l == 0 || d < bd) {
-                bd = d;
-                cl = l;
+    // ---- :291-315  the controlled vehicles, one per access road ("o{k}", "ir{k}", 0), k = agent % 4
+    const int A = n_agents_of(P);
+    for (int agent = 0; agent < A; ++agent) {
+        if (i == 0) {
+            const int dest = SP.ego_destination >= 0 ? SP.ego_destination : 1 + rng.choice(3);  // "o" + integers(1, 4)
+            const HwyNetLane& EL = g.lanes[SP.spawn_lane[agent % 4]];
+            const double lon = 60.0 + 5.0 * (1.0 + 1.0 * rng.normal());  // 60 + 5 * np_random.normal(1)
+            lane_position(EL, lon, 0.0, st.sp_x, st.sp_y);
+            st.sp_h = lane_heading_at(EL, 60.0);
+            st.sp_speed = EL.speed_limit;
+            int cl = 0;
+            double bd = 0;
+            for (int l = 0; l < g.n_lanes; ++l) {
+                double d = lane_distance_with_heading(g.lanes[l], st.sp_x, st.sp_y, st.sp_h);
+                if (l == 0 || d < bd) {
+                    bd = d;
+                    cl = l;
+                }
             }
+            st.sp_lane = cl;
+            st.sp_dest = dest;
+            st.speed_index = speed_to_index(P, st.sp_speed);  // MDPVehicle.__init__ (controller.py:283-293)
+            st.sp_ts = P.target_speeds[st.speed_index];
+            st.sp_ok = st.count < G ? 1 : 0;
+            if (agent == 0) st.ego = st.count;
         }
-        st.sp_lane = cl;
-        st.sp_dest = dest;
-        st.speed_index = speed_to_index(P, st.sp_speed);  // MDPVehicle.__init__ (controller.py:283-293)
-        st.sp_ts = P.target_speeds[st.speed_index];
-        st.sp_ok = st.count < G ? 1 : 0;
-        st.ego = st.count;
+        commit(HWY_KIND_MDP);
     }
-    commit(HWY_KIND_MDP);
-    // ---- :317-323  drop the traffic within 20 m of the controlled vehicle
-    const int V = st.count, ego = st.ego;
+    // ---- :317-323  after each controlled vehicle the TRAFFIC within 20 m of it is dropped; controlled vehicles are
+    // never dropped and their creation does not look at the others, so all prunings can run at the end
+    const int V = st.count;
     bool keep = i < V;
-    if (keep && i != ego && norm2(st.x[i] - st.x[ego], st.y[i] - st.y[ego]) < 20) keep = false;
+    if (keep && st.kind[i] != HWY_KIND_MDP) {
+        for (int v = 0; v < V; ++v)
+            if (st.kind[v] == HWY_KIND_MDP && norm2(st.x[i] - st.x[v], st.y[i] - st.y[v]) < 20) keep = false;
+    }
     const unsigned keep_mask = __ballot_sync(group_mask<G>(), keep) >> ((threadIdx.x & 31) & ~(G - 1));
     const int dst = keep ? __popc(keep_mask & ((1u << i) - 1u)) : -1;
     if (!selected) return;  // no block-wide barrier below this line
@@ -1548,14 +1638,14 @@ intersection_reset_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGr
     if (i == 0) {
         S.count[e] = __popc(keep_mask);
         S.road_steps[e] = st.road_steps;
-        S.speed_index[e] = st.speed_index;
+        for (int agent = 0; agent < A; ++agent) S.speed_index[(size_t)e * A + agent] = st.speed_index;
         S.time[e] = 0.0;
         store_rng(S.rng, (size_t)S.n_envs, e, rng);
     }
     if (!obs) return;
     group_sync<G>();  // the stored state is re-read by other threads of the group
     load_env(P, g, S, st, e, i, r);
-    observe_any(P, g, st, st.count, i, obs + (size_t)e * obs_size(P));
+    observe_agents(P, g, st, i, obs + (size_t)e * A * obs_size(P));
 }
 
 // RoundaboutEnv._make_vehicles (envs/roundabout_env.py:317-391), one env per thread (the draws
@@ -1662,6 +1752,7 @@ int validate_net(const HwyNetParams* p, const HwyNetGraph* graph, const HwyNetSt
         !s->speed_index || !s->time)
         return fail("%s", "null state pointer");
     if (s->vp == HWY_NET_GROUP_LARGE && (!s->count || !s->road_steps)) return fail("%s", "count / road_steps required");
+    if (p->n_agents < 0 || p->n_agents > 4) return fail("%s", "n_agents out of range (0..4)");
     int dev_count = 0;
     if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count < 1) {
         cudaGetLastError();
@@ -1689,11 +1780,13 @@ int blocks_for(int n_envs, int g) {
 template <int G, bool REG>
 int launch_step(const HwyNetParams* p, const HwyNetGraph* graph, const HwyIntersectionSpawn& sp, const HwyNetState* s,
                 const int32_t* action, float* obs, double* reward, uint8_t* terminated, uint8_t* truncated,
-                double* info_speed, uint8_t* info_crashed, cudaStream_t st, const int* list = nullptr) {
+                double* info_speed, uint8_t* info_crashed, cudaStream_t st, const int* list = nullptr,
+                double* agents_reward = nullptr, uint8_t* agents_terminated = nullptr) {
     const size_t smem = net_smem_bytes<G, REG>();
     if (configure_smem(hwynet::network_step_kernel<G, REG>, smem)) return 1;
     hwynet::network_step_kernel<G, REG><<<blocks_for(s->n_envs, G), hwynet::kBlockThreads, smem, st>>>(
-        *p, graph, *s, sp, action, obs, reward, terminated, truncated, info_speed, info_crashed, list);
+        *p, graph, *s, sp, action, obs, reward, terminated, truncated, info_speed, info_crashed, list, agents_reward,
+        agents_terminated);
     return check_launch("network_step_kernel");
 }
 template <int G, bool REG>
@@ -1716,9 +1809,10 @@ extern "C" {
 
 int hwy_network_obs_size(const HwyNetParams* p) {
     if (!p) return 0;
-    if (p->obs_type == HWY_OBS_OCCUPANCY) return 4 * 11 * 11;
-    if (p->obs_type == HWY_OBS_TTC) return 9 * (int)(p->ttc_horizon / (1.0 / p->policy_frequency));
-    return p->obs_vehicles_count * (p->obs_features == 7 ? 7 : 5);
+    const int agents = p->n_agents > 1 ? p->n_agents : 1;  // one observation per controlled vehicle
+    if (p->obs_type == HWY_OBS_OCCUPANCY) return agents * 4 * 11 * 11;
+    if (p->obs_type == HWY_OBS_TTC) return agents * 9 * (int)(p->ttc_horizon / (1.0 / p->policy_frequency));
+    return agents * p->obs_vehicles_count * (p->obs_features == 7 ? 7 : 5);
 }
 
 int hwy_network_step(const HwyNetParams* p, const HwyNetGraph* graph, const HwyNetState* s,
@@ -1736,7 +1830,17 @@ int hwy_intersection_step(const HwyNetParams* p, const HwyNetGraph* graph, const
                           const HwyNetState* s, const int32_t* action, float* obs, double* reward,
                           uint8_t* terminated, uint8_t* truncated, double* info_speed, uint8_t* info_crashed,
                           void* stream) {
+    return hwy_intersection_step_agents(p, graph, spawn, s, action, obs, reward, terminated, truncated, info_speed,
+                                        info_crashed, nullptr, nullptr, stream);
+}
+
+int hwy_intersection_step_agents(const HwyNetParams* p, const HwyNetGraph* graph, const HwyIntersectionSpawn* spawn,
+                                 const HwyNetState* s, const int32_t* action, float* obs, double* reward,
+                                 uint8_t* terminated, uint8_t* truncated, double* info_speed, uint8_t* info_crashed,
+                                 double* agents_reward, uint8_t* agents_terminated, void* stream) {
     if (validate_net(p, graph, s)) return 1;
+    if (p->n_agents > 1 && (p->obs_type != HWY_OBS_KINEMATICS || p->reward_type != 1))
+        return fail("%s", "several controlled vehicles: Kinematics observation on intersection envs only");
     if (!action || !obs || !reward || !terminated || !truncated) return fail("%s", "null pointer");
     if (s->vp != HWY_NET_GROUP_LARGE) return fail("%s", "hwy_intersection_step expects slot stride 32");
     if (p->dynamic_population && (!spawn || !spawn->route_table || !spawn->route_len || !s->rng))
@@ -1752,13 +1856,15 @@ int hwy_intersection_step(const HwyNetParams* p, const HwyNetGraph* graph, const
         hwynet::classify_envs_kernel<<<(s->n_envs + 255) / 256, 256, 0, st>>>(s->count, s->n_envs, small, large);
         if (check_launch("classify_envs_kernel")) return 1;
         if (launch_step<16, true>(p, graph, *spawn, s, action, obs, reward, terminated, truncated, info_speed,
-                                  info_crashed, st, small))
+                                  info_crashed, st, small, agents_reward, agents_terminated))
             return 1;
         return launch_step<HWY_NET_GROUP_LARGE, true>(p, graph, *spawn, s, action, obs, reward, terminated, truncated,
-                                                      info_speed, info_crashed, st, large);
+                                                      info_speed, info_crashed, st, large, agents_reward,
+                                                      agents_terminated);
     }
     return launch_step<HWY_NET_GROUP_LARGE, true>(p, graph, spawn ? *spawn : none, s, action, obs, reward, terminated,
-                                                  truncated, info_speed, info_crashed, st);
+                                                  truncated, info_speed, info_crashed, st, nullptr, agents_reward,
+                                                  agents_terminated);
 }
 
 int hwy_intersection_reset(const HwyNetParams* p, const HwyNetGraph* graph, const HwyIntersectionSpawn* spawn,

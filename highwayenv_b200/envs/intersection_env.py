@@ -72,6 +72,7 @@ _F64 = ("x", "y", "heading", "speed", "target_speed", "timer", "delta", "impact_
 
 class BatchedIntersectionEnv:
     ENV_ID = "intersection-v0"
+    MULTI_AGENT_WRAPPER = False
     metadata = {"render_modes": [], "autoreset_mode": "SameStep"}
 
     @classmethod
@@ -116,6 +117,19 @@ class BatchedIntersectionEnv:
     def define_spaces(self) -> None:
         cfg = self.config
         act, obs = cfg["action"], cfg["observation"]
+        # MultiAgentAction / MultiAgentObservation (action.py:301-333, observation.py:588-604): the same plugin per
+        # controlled vehicle; tuples of the reference become a leading agent axis here
+        self.n_agents = int(cfg.get("controlled_vehicles", 1))
+        multi = act["type"] == "MultiAgentAction" or obs["type"] == "MultiAgentObservation"
+        if multi:
+            if act["type"] != "MultiAgentAction" or obs["type"] != "MultiAgentObservation":
+                raise NotImplementedError("MultiAgentAction and MultiAgentObservation go together here")
+            act, obs = act["action_config"], obs["observation_config"]
+        elif self.n_agents != 1:
+            raise NotImplementedError("controlled_vehicles > 1 needs MultiAgentAction / MultiAgentObservation")
+        if not 1 <= self.n_agents <= 4:
+            raise ValueError("controlled_vehicles must be in 1..4")
+        self.multi_agent = multi
         if act["type"] != "DiscreteMetaAction":
             if act["type"] in ("ContinuousAction", "DiscreteAction", "MultiAgentAction"):
                 raise NotImplementedError(f"action type {act['type']!r} on intersection-v0")
@@ -123,8 +137,8 @@ class BatchedIntersectionEnv:
         longi, lat = act.get("longitudinal", True), act.get("lateral", True)
         if not longi:
             raise NotImplementedError("lateral-only meta-actions")
-        if cfg.get("controlled_vehicles", 1) != 1:
-            raise NotImplementedError("multi-agent intersection")
+        if multi and obs["type"] != "Kinematics":
+            raise NotImplementedError("MultiAgentObservation over Kinematics only")
         ts = act.get("target_speeds")
         self.target_speeds = np.linspace(20, 30, 3) if ts is None else np.array(ts, dtype=np.float64)
         if self.target_speeds.size > 3:
@@ -189,6 +203,17 @@ class BatchedIntersectionEnv:
         self._params = p
         self.observation_space = batch_space(self.single_observation_space, self.num_envs)
         self.action_space = batch_space(self.single_action_space, self.num_envs)
+        p.n_agents = self.n_agents if multi else 0
+        self._params = p
+        if multi:  # Tuple spaces of the reference -> one leading agent axis
+            per = self.single_observation_space
+            self.single_observation_space = Box(low=-np.inf, high=np.inf, shape=(self.n_agents,) + tuple(per.shape),
+                                                dtype=np.float32)
+            self.agent_action_space = self.single_action_space
+            self.single_action_space = Box(low=0, high=self.agent_action_space.n - 1, shape=(self.n_agents,),
+                                           dtype=np.int64)
+            self.observation_space = batch_space(self.single_observation_space, self.num_envs)
+            self.action_space = batch_space(self.single_action_space, self.num_envs)
         self.obs_shape = tuple(self.single_observation_space.shape)
 
     def _allocate(self) -> None:
@@ -200,7 +225,10 @@ class BatchedIntersectionEnv:
         self._meta = z(n, vp, dtype=torch.int32)
         self._route = z(n, vp, N.HWY_NET_MAX_ROUTE, dtype=torch.int32)
         self._route_len = z(n, vp, dtype=torch.int32)
-        self._speed_index = z(n, dtype=torch.int32)
+        A = self.n_agents
+        self._speed_index = z(n * A, dtype=torch.int32)
+        self._agents_reward = z(n, A, dtype=torch.float64)
+        self._agents_terminated = z(n, A, dtype=torch.uint8)
         self._time = z(n, dtype=torch.float64)
         self._count = z(n, dtype=torch.int32)
         self._road_steps = z(n, dtype=torch.int32)
@@ -210,7 +238,7 @@ class BatchedIntersectionEnv:
         self._reward = z(n, dtype=torch.float64)
         self._terminated, self._truncated = z(n, dtype=torch.uint8), z(n, dtype=torch.uint8)
         self._info_speed, self._info_crashed = z(n, dtype=torch.float64), z(n, dtype=torch.uint8)
-        self._action_buf = z(n, dtype=torch.int32)
+        self._action_buf = z(n, A, dtype=torch.int32) if self.multi_agent else z(n, dtype=torch.int32)
         st = N.HwyNetState()
         st.n_envs, st.vp = n, vp
         st.pos, st.hs, st.tt, st.imp = (t.data_ptr() for t in (self._pos, self._hs, self._tt, self._imp))
@@ -266,7 +294,9 @@ class BatchedIntersectionEnv:
             "has_impact": (meta & N.META_HAS_IMPACT) != 0, "check_collisions": (meta & N.META_CHECK_COLLISIONS) != 0,
             "is_yielding": (meta & N.META_YIELDING) != 0,
             "route": self._route.cpu().numpy(), "route_len": self._route_len.cpu().numpy(),
-            "speed_index": self._speed_index.cpu().numpy(), "time": self._time.cpu().numpy(),
+            "speed_index": (self._speed_index.cpu().numpy().reshape(self.num_envs, self.n_agents)
+                            if self.multi_agent else self._speed_index.cpu().numpy()),
+            "time": self._time.cpu().numpy(),
             "count": self._count.cpu().numpy(), "road_steps": self._road_steps.cpu().numpy(),
             "rng": self._rng.cpu().numpy().view(np.uint64),
         }
@@ -290,7 +320,8 @@ class BatchedIntersectionEnv:
         self._meta[idx] = torch.from_numpy(meta).to(dev)
         self._route[idx] = torch.from_numpy(np.ascontiguousarray(sd["route"], dtype=np.int32)).to(dev)
         self._route_len[idx] = torch.from_numpy(np.ascontiguousarray(sd["route_len"], dtype=np.int32)).to(dev)
-        self._speed_index[idx] = torch.from_numpy(np.asarray(sd["speed_index"], dtype=np.int32).reshape(-1)).to(dev)
+        si = torch.from_numpy(np.ascontiguousarray(np.asarray(sd["speed_index"], dtype=np.int32)).reshape(-1, self.n_agents)).to(dev)
+        self._speed_index.view(self.num_envs, self.n_agents)[idx] = si
         self._time[idx] = torch.from_numpy(np.asarray(sd["time"], dtype=np.float64).reshape(-1)).to(dev)
         self._count[idx] = torch.from_numpy(np.asarray(sd["count"], dtype=np.int32).reshape(-1)).to(dev)
         self._road_steps[idx] = torch.from_numpy(np.asarray(sd["road_steps"], dtype=np.int32).reshape(-1)).to(dev)
@@ -310,7 +341,7 @@ class BatchedIntersectionEnv:
         for k in ("lane", "target_lane", "kind", "crashed", "has_impact", "is_yielding", "route_len"):
             sd[k] = np.zeros((m, VMAX), dtype=np.int64)
         sd["route"] = np.zeros((m, VMAX, N.HWY_NET_MAX_ROUTE), dtype=np.int32)
-        sd["speed_index"] = np.zeros(m, dtype=np.int32)
+        sd["speed_index"] = np.zeros((m, self.n_agents), dtype=np.int32)
         sd["time"] = np.zeros(m)
         sd["count"] = np.zeros(m, dtype=np.int32)
         sd["road_steps"] = np.zeros(m, dtype=np.int32)
@@ -369,27 +400,29 @@ class BatchedIntersectionEnv:
         full = self.state_dict()
         sd = {k: (v[ids].copy() if k != "rng" else None) for k, v in full.items()}
         sd.pop("rng")
-        ego_lane = self.net.index[("o0", "ir0", 0)]
         ts = self.target_speeds
+        sd["speed_index"] = np.asarray(sd["speed_index"]).reshape(m, self.n_agents)
         for k, e in enumerate(ids):
             g = self._rngs[e]
             self._spawn_vehicle(sd, k, g, 60, spawn_probability=1.0, go_straight=True, position_deviation=0.1,
                                 speed_deviation=0.0)
-            destination = cfg["destination"] or "o" + str(g.integers(1, 4))
-            px, py = self.net.position(ego_lane, 60.0 + 5.0 * g.normal(1.0), 0.0)
-            x, y, h = float(px), float(py), float(self.net.heading_at(ego_lane, 60.0))
-            speed_limit = self.net.lanes[ego_lane]["speed_limit"]
-            si = int(np.clip(np.round((speed_limit - ts[0]) / (ts[-1] - ts[0]) * (ts.size - 1)), 0, ts.size - 1))
-            idx = self._append(sd, k, x, y, h, speed_limit, N.KIND_MDP, destination, 4.0, target_speed=ts[si], timer=0.0)
-            sd["speed_index"][k] = si
-            n = int(sd["count"][k])
-            keep = [v for v in range(n) if v == idx or not (
-                np.linalg.norm(np.array([sd["x"][k, v] - x, sd["y"][k, v] - y])) < 20)]
-            for name, arr in sd.items():
-                if name in ("speed_index", "time", "count", "road_steps"):
-                    continue
-                arr[k, :len(keep)] = arr[k, keep]
-            sd["count"][k] = len(keep)
+            for agent in range(self.n_agents):  # :291-323, one controlled vehicle per access road
+                ego_lane = self.net.index[("o%d" % (agent % 4), "ir%d" % (agent % 4), 0)]
+                destination = cfg["destination"] or "o" + str(g.integers(1, 4))
+                px, py = self.net.position(ego_lane, 60.0 + 5.0 * g.normal(1.0), 0.0)
+                x, y, h = float(px), float(py), float(self.net.heading_at(ego_lane, 60.0))
+                speed_limit = self.net.lanes[ego_lane]["speed_limit"]
+                si = int(np.clip(np.round((speed_limit - ts[0]) / (ts[-1] - ts[0]) * (ts.size - 1)), 0, ts.size - 1))
+                self._append(sd, k, x, y, h, speed_limit, N.KIND_MDP, destination, 4.0, target_speed=ts[si], timer=0.0)
+                sd["speed_index"][k, agent] = si
+                n = int(sd["count"][k])
+                keep = [v for v in range(n) if sd["kind"][k, v] == N.KIND_MDP or not (
+                    np.linalg.norm(np.array([sd["x"][k, v] - x, sd["y"][k, v] - y])) < 20)]
+                for name, arr in sd.items():
+                    if name in ("speed_index", "time", "count", "road_steps"):
+                        continue
+                    arr[k, :len(keep)] = arr[k, keep]
+                sd["count"][k] = len(keep)
             sd["time"][k] = 0.0
         words = np.zeros((5, m), dtype=np.uint64)
         m64 = (1 << 64) - 1
@@ -482,11 +515,16 @@ class BatchedIntersectionEnv:
         prev = getattr(self, "_autoreset_envs", None) if self.autoreset_mode == "NextStep" else None
         rng_before = self._rng.clone() if prev is not None else None  # a step draws from the env's generator
         with torch.cuda.device(self.device):
-            N.check(self._lib.hwy_intersection_step(
+            N.check(self._lib.hwy_intersection_step_agents(
                 C.byref(self._params), self._graph_dev.data_ptr(), C.byref(self._spawn_struct), C.byref(self._state),
                 act.data_ptr(), self._obs.data_ptr(), self._reward.data_ptr(), self._terminated.data_ptr(),
-                self._truncated.data_ptr(), self._info_speed.data_ptr(), self._info_crashed.data_ptr(), self._stream()))
+                self._truncated.data_ptr(), self._info_speed.data_ptr(), self._info_crashed.data_ptr(),
+                self._agents_reward.data_ptr() if self.multi_agent else None,
+                self._agents_terminated.data_ptr() if self.multi_agent else None, self._stream()))
         info = {"speed": self._info_speed, "crashed": self._info_crashed.view(torch.bool), "action": act}
+        if self.multi_agent:  # IntersectionEnv._info (:124-132)
+            info["agents_rewards"] = self._agents_reward
+            info["agents_terminated"] = self._agents_terminated.view(torch.bool)
         if self.autoreset_mode == "SameStep" and self.reset_mode == "device":
             info["final_obs"] = self._final_obs
             self._device_reset(self._terminated.data_ptr(), self._truncated.data_ptr(), self._obs.data_ptr(),
@@ -511,6 +549,10 @@ class BatchedIntersectionEnv:
                 self._sync_host_rngs(ids)
                 self._reset_envs(ids)
                 self.observe()
+        if self.multi_agent and self.MULTI_AGENT_WRAPPER:
+            # MultiAgentWrapper.step (envs/common/abstract.py:468-477): per-agent rewards and terminal flags
+            return (self._obs, self._agents_reward, self._agents_terminated.view(torch.bool),
+                    self._truncated.view(torch.bool), info)
         return (self._obs, self._reward, self._terminated.view(torch.bool), self._truncated.view(torch.bool), info)
 
     def close(self) -> None:
@@ -526,3 +568,25 @@ class BatchedConnectedLaneIntersectionEnv(BatchedIntersectionEnv):
     searches the lane segments connected to the queried lane (road/road.py:509-529)."""
 
     ENV_ID = "intersection-v2"
+
+
+class BatchedMultiAgentIntersectionEnv(BatchedIntersectionEnv):
+    """`intersection-multi-agent-v0` (MultiAgentIntersectionEnv, envs/intersection_env.py:376-420): two controlled
+    vehicles, tuple actions / observations as a leading agent axis, mean reward, any-crashed / all-arrived
+    termination, `info["agents_rewards"]`, `info["agents_terminated"]`."""
+
+    ENV_ID = "intersection-multi-agent-v0"
+
+
+class BatchedMultiAgentWrappedIntersectionEnv(BatchedMultiAgentIntersectionEnv):
+    """`intersection-multi-agent-v1`: the same behind MultiAgentWrapper (abstract.py:468-477) — `step` returns the
+    per-agent rewards and terminal flags [N, agents] in place of the scalar ones."""
+
+    ENV_ID = "intersection-multi-agent-v1"
+    MULTI_AGENT_WRAPPER = True
+
+
+class BatchedConnectedLaneMultiAgentIntersectionEnv(BatchedMultiAgentWrappedIntersectionEnv):
+    """`intersection-multi-agent-v2`: + ConnectedLaneNeighboursMixin."""
+
+    ENV_ID = "intersection-multi-agent-v2"

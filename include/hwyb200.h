@@ -132,7 +132,7 @@ typedef struct HwyHighwayState {
     double *pos, *hs, *tt, *imp; /* [n_envs*vp*2] */
     double *delta;               /* [n_envs*vp]   IDMVehicle.DELTA */
     int32_t *meta;               /* [n_envs*vp] */
-    int32_t *speed_index;        /* [n_envs] */
+    int32_t *speed_index;        /* [n_envs * max(1, n_agents)] MDPVehicle.speed_index of each controlled vehicle */
     double *time;                /* [n_envs] */
     uint64_t *rng;               /* [5*n_envs] */
 } HwyHighwayState;
@@ -246,7 +246,9 @@ typedef struct HwyNetParams {
     int32_t dynamic_population; /* per-step _clear_vehicles / _spawn_vehicle (intersection_env.py:136-140) */
     int32_t connected_lanes;    /* config["neighbour_vehicles_connected_lanes"]: roundabout-v1, intersection-v2
                                  * (abstract.py:26-37, road/road.py:509-529) */
-    int32_t _pad_net;
+    int32_t n_agents;           /* config["controlled_vehicles"] (0 or 1: one).  > 1 = MultiAgentAction /
+                                 * MultiAgentObservation (action.py:301-333, observation.py:588-604): actions, obs and
+                                 * speed_index carry n_agents entries per env, controlled vehicles in list order */
     double arrived_reward, reward_speed_lo, reward_speed_hi;
 } HwyNetParams;
 
@@ -259,7 +261,7 @@ typedef struct HwyNetState {
     int32_t *meta;               /* [n_envs*vp] lane(8) | target lane(8) | flags, as above */
     int32_t *route;              /* [n_envs*vp*HWY_NET_MAX_ROUTE] ControlledVehicle.route */
     int32_t *route_len;          /* [n_envs*vp] */
-    int32_t *speed_index;        /* [n_envs] */
+    int32_t *speed_index;        /* [n_envs * max(1, n_agents)] MDPVehicle.speed_index of each controlled vehicle */
     double *time;                /* [n_envs] */
     int32_t *count;              /* [n_envs] vehicles currently on the road; NULL: always n_vehicles */
     int32_t *road_steps;         /* [n_envs] RegulatedRoad.steps; NULL when not regulated */
@@ -282,7 +284,8 @@ typedef struct HwyIntersectionSpawn {
                                     * runs every env on 32 slots and hwy_intersection_reset is unavailable */
 } HwyIntersectionSpawn;
 
-/* observation size in floats: Kinematics K*5, TimeToCollision 3*3*(horizon*policy_frequency) */
+/* observation size in floats PER ENV: Kinematics K*F, TimeToCollision 3*3*(horizon*policy_frequency),
+ * OccupancyGrid 4*11*11; times n_agents when several vehicles are controlled */
 int hwy_network_obs_size(const HwyNetParams *p);
 
 /* AbstractEnv.step (abstract.py:259-285) on a general network: action [n_envs] int32
@@ -298,6 +301,17 @@ int hwy_intersection_step(const HwyNetParams *p, const HwyNetGraph *graph, const
                           const HwyNetState *s, const int32_t *action, float *obs, double *reward,
                           uint8_t *terminated, uint8_t *truncated, double *info_speed,
                           uint8_t *info_crashed, void *stream);
+
+/* The same with config["controlled_vehicles"] = p->n_agents > 1 (intersection-multi-agent-v0,
+ * envs/intersection_env.py:376-420): action [n_envs][n_agents], obs [n_envs][n_agents][K][F]; reward is the mean
+ * of the agents' rewards, terminated = any crashed or all arrived (:62-134); agents_reward / agents_terminated
+ * [n_envs][n_agents] (optional) are _info's per-agent entries, which MultiAgentWrapper (abstract.py:468-477)
+ * returns in place of the scalar reward / terminated. */
+int hwy_intersection_step_agents(const HwyNetParams *p, const HwyNetGraph *graph, const HwyIntersectionSpawn *spawn,
+                                 const HwyNetState *s, const int32_t *action, float *obs, double *reward,
+                                 uint8_t *terminated, uint8_t *truncated, double *info_speed,
+                                 uint8_t *info_crashed, double *agents_reward, uint8_t *agents_terminated,
+                                 void *stream);
 
 /* IntersectionEnv._reset / _make_vehicles (envs/intersection_env.py:119-122,245-323) on the device for the
  * envs with mask_a[e] | mask_b[e] (both NULL: every env): n-1 _spawn_vehicle draws, 3 s of warm-up simulation,

@@ -65,6 +65,8 @@ CASES = {
     # (f)3 connected-lane neighbour search (ConnectedLaneNeighboursMixin, abstract.py:26-37; road.py:509-529)
     "roundabout_v1_kin": ("roundabout-v1", None, list(range(900, 906)), 11, "discrete5"),
     "intersection_v2_kin": ("intersection-v2", None, list(range(910, 916)), 13, "discrete3"),
+    # (f)2 MultiAgentAction / MultiAgentObservation: two controlled vehicles
+    "intersection_multi_agent": ("intersection-multi-agent-v0", None, list(range(920, 926)), 13, "discrete3x2"),
 }
 
 
@@ -82,6 +84,8 @@ def main() -> None:
                 actions = rng.integers(0, 5, size=T).astype(np.int64)
             elif akind == "discrete9":
                 actions = rng.integers(0, 9, size=T).astype(np.int64)
+            elif akind == "discrete3x2":
+                actions = rng.integers(0, 3, size=(T, 2)).astype(np.int64)
             elif akind == "discrete3":
                 actions = rng.integers(0, 3, size=T).astype(np.int64)
             else:

@@ -573,19 +573,28 @@ static int speed_to_index(const NetCfg *c, double speed) {
 }
 
 /* vehicle/controller.py:295-315; action.py:204 labels */
-static void mdp_act(World *w, int v, int action) {
+static void mdp_act_agent(World *w, int v, int action, int agent) {
     const NetCfg *c = w->c;
     NetState *s = w->s;
     if (action == 3 || action == 4) {
         int idx = speed_to_index(c, s->speed[v]) + (action == 3 ? 1 : -1);
         if (idx < 0) idx = 0;
         if (idx > c->n_target_speeds - 1) idx = c->n_target_speeds - 1;
-        s->speed_index[0] = idx;
+        s->speed_index[agent] = idx;
         s->target_speed[v] = c->target_speeds[idx];
         controlled_act(w, v, -1);
     } else {
         controlled_act(w, v, action);
     }
+}
+
+static void mdp_act(World *w, int v, int action) { mdp_act_agent(w, v, action, 0); }
+
+/* the k-th controlled vehicle (env.controlled_vehicles order == list order of the MDP vehicles); -1: none */
+static int agent_vehicle(const World *w, int k) {
+    for (int v = 0; v < w->V; v++)
+        if (w->s->kind[v] == NET_KIND_MDP && k-- == 0) return v;
+    return -1;
 }
 
 /* index of the controlled vehicle: first MDP vehicle of the list */
@@ -780,13 +789,14 @@ static void observe_ttc(const World *w, float *obs) {
 
 /* envs/common/observation.py:234-276 with explicit features_range / absolute; optional
  * cos_h, sin_h columns (vehicle/kinematics.py:247-248), which have no features_range entry */
-static void observe_kinematics(const World *w, float *obs) {
+static void observe_kinematics_from(const World *w, int ego, float *obs);
+static void observe_kinematics(const World *w, float *obs) { observe_kinematics_from(w, ego_index(w), obs); }
+static void observe_kinematics_from(const World *w, int ego, float *obs) {
     const NetCfg *c = w->c;
     const NetState *s = w->s;
     int K = c->obs_vehicles_count, V = w->V;
     const int F = c->obs_features == 7 ? 7 : 5;
     double *rows = (double *)calloc((size_t)K * F, sizeof(double));
-    const int ego = ego_index(w);
     double evx = s->speed[ego] * cos(s->heading[ego]), evy = s->speed[ego] * sin(s->heading[ego]);
     rows[0] = 1;
     rows[1] = s->x[ego];
@@ -1049,6 +1059,29 @@ int net_has_arrived(const NetGraph *g, const NetState *s, int v) {
     return L->exit_lane && lane_s(L, s->x[v], s->y[v]) >= 25;
 }
 
+/* envs/intersection_env.py:93-117 _agent_reward / _agent_rewards of one controlled vehicle */
+static double agent_reward_intersection(const World *w, int ego, int *arrived_out, int *on_road_out) {
+    const NetCfg *c = w->c;
+    const NetState *s = w->s;
+    const NetLane *L = LANE(w, s->lane[ego]);
+    double es, elat;
+    net_lane_local(L, s->x[ego], s->y[ego], &es, &elat);
+    int on_road = lane_on_lane(L, es, elat, 0.0);
+    int arrived = net_has_arrived(w->g, s, ego);
+    double scaled_speed = lmap(s->speed[ego], c->reward_speed_lo, c->reward_speed_hi, 0, 1);
+    double r = 0;
+    r = r + c->collision_reward * (double)(s->crashed[ego] != 0);
+    r = r + c->high_speed_reward * clipd(scaled_speed, 0, 1);
+    r = r + c->arrived_reward * (double)arrived;
+    r = r + 0 * (double)on_road;
+    if (arrived) r = c->arrived_reward;
+    r *= (double)on_road;
+    if (c->normalize_reward) r = lmap(r, c->collision_reward, c->arrived_reward, 0, 1);
+    *arrived_out = arrived;
+    *on_road_out = on_road;
+    return r;
+}
+
 /* envs/intersection_env.py:79-117 (single controlled vehicle) */
 static void reward_done_intersection(const World *w, double *reward, int32_t *terminated,
                                      int32_t *truncated) {
@@ -1104,6 +1137,66 @@ void net_step(const NetGraph *g, const NetCfg *c, NetState *s, int action, float
     else
         reward_done(&w, action, reward, terminated, truncated);
     free(act_buf);
+}
+
+/* The same step with several controlled vehicles: MultiAgentAction.act (envs/common/action.py:301-333) applies
+ * actions[k] to controlled vehicle k in order; MultiAgentObservation (observation.py:588-604) stacks one
+ * observation per agent; _reward is the mean of the agents' rewards, the episode terminates when ANY agent crashed
+ * or ALL arrived (intersection_env.py:79-134); info carries the per-agent rewards and terminal flags. */
+void net_step_agents(const NetGraph *g, const NetCfg *c, NetState *s, const int32_t *actions, int n_agents,
+                     float *obs, double *reward, int32_t *terminated, int32_t *truncated, double *agents_reward,
+                     int32_t *agents_terminated) {
+    World w;
+    w.g = g;
+    w.c = c;
+    w.s = s;
+    w.V = world_count(c, s);
+    double *act_buf = (double *)calloc(2 * (size_t)w.V, sizeof(double));
+    w.act_steer = act_buf;
+    w.act_accel = act_buf + w.V;
+    int frames = c->simulation_frequency / c->policy_frequency;
+    double dt = 1.0 / c->simulation_frequency;
+    s->time[0] += 1.0 / c->policy_frequency;
+    for (int frame = 0; frame < frames; frame++) {
+        if (frame == 0)
+            for (int k = 0; k < n_agents; k++) {
+                int v = agent_vehicle(&w, k);
+                int label = actions[k];
+                if (c->action_mode == 1) label = actions[k] == 0 ? 4 : (actions[k] == 2 ? 3 : 1);
+                if (v >= 0) mdp_act_agent(&w, v, label, k);
+            }
+        road_act(&w);
+        if (c->regulated) regulated_pre_step(&w, dt);
+        road_step(&w, dt);
+    }
+    const int per = net_obs_size(c);
+    double sum = 0;
+    int any_crashed = 0, all_arrived = 1, first_on_road = 1;
+    for (int k = 0; k < n_agents; k++) {
+        int v = agent_vehicle(&w, k);
+        if (obs) observe_kinematics_from(&w, v, obs + (size_t)k * per);
+        int arrived, on_road;
+        double r = agent_reward_intersection(&w, v, &arrived, &on_road);
+        sum += r;
+        any_crashed |= s->crashed[v] != 0;
+        all_arrived &= arrived;
+        if (k == 0) first_on_road = on_road;
+        if (agents_reward) agents_reward[k] = r;
+        if (agents_terminated) agents_terminated[k] = s->crashed[v] != 0 || arrived;
+    }
+    *reward = sum / n_agents;
+    *terminated = any_crashed || all_arrived || (c->offroad_terminal && !first_on_road);
+    *truncated = s->time[0] >= c->duration;
+    free(act_buf);
+}
+
+void net_observe_agents(const NetGraph *g, const NetCfg *c, const NetState *s, int n_agents, float *obs) {
+    World w;
+    w.g = g;
+    w.c = c;
+    w.s = (NetState *)s;
+    w.V = world_count(c, s);
+    for (int k = 0; k < n_agents; k++) observe_kinematics_from(&w, agent_vehicle(&w, k), obs + (size_t)k * net_obs_size(c));
 }
 
 void net_substeps(const NetGraph *g, const NetCfg *c, NetState *s, int substeps) {

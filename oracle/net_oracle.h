@@ -97,6 +97,12 @@ typedef struct NetState {
 void net_step(const NetGraph *g, const NetCfg *c, NetState *s, int action, float *obs,
               double *reward, int32_t *terminated, int32_t *truncated);
 void net_observe(const NetGraph *g, const NetCfg *c, const NetState *s, float *obs);
+/* several controlled vehicles (MultiAgentAction / MultiAgentObservation, intersection-multi-agent-v0):
+ * actions [n_agents], obs [n_agents][net_obs_size], speed_index [n_agents] in the state */
+void net_step_agents(const NetGraph *g, const NetCfg *c, NetState *s, const int32_t *actions, int n_agents,
+                     float *obs, double *reward, int32_t *terminated, int32_t *truncated, double *agents_reward,
+                     int32_t *agents_terminated);
+void net_observe_agents(const NetGraph *g, const NetCfg *c, const NetState *s, int n_agents, float *obs);
 /* Road.act() + Road.step(dt) `substeps` times without an ego action (intersection warm-up) */
 void net_substeps(const NetGraph *g, const NetCfg *c, NetState *s, int substeps);
 /* has_arrived(vehicle) of envs/intersection_env.py:368-373 */

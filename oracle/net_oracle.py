@@ -86,6 +86,13 @@ def lib():
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.net_observe.restype = None
         _lib.net_observe.argtypes = [C.POINTER(NetGraph), C.POINTER(NetCfg), C.POINTER(NetState), C.c_void_p]
+        _lib.net_step_agents.restype = None
+        _lib.net_step_agents.argtypes = [C.POINTER(NetGraph), C.POINTER(NetCfg), C.POINTER(NetState), C.c_void_p,
+                                         C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p]
+        _lib.net_observe_agents.restype = None
+        _lib.net_observe_agents.argtypes = [C.POINTER(NetGraph), C.POINTER(NetCfg), C.POINTER(NetState), C.c_int,
+                                            C.c_void_p]
         _lib.net_substeps.restype = None
         _lib.net_substeps.argtypes = [C.POINTER(NetGraph), C.POINTER(NetCfg), C.POINTER(NetState), C.c_int]
         _lib.net_has_arrived.restype = C.c_int
@@ -127,6 +134,10 @@ def cfg_from_dict(config: dict, n_vehicles: int = 5) -> NetCfg:
     c = NetCfg()
     intersection = "spawn_probability" in config
     obs, act = config["observation"], config["action"]
+    if obs["type"] == "MultiAgentObservation":  # observation.py:588-604: one observation per controlled vehicle
+        obs = obs["observation_config"]
+    if act["type"] == "MultiAgentAction":  # action.py:301-333
+        act = act["action_config"]
     c.n_vehicles = n_vehicles
     c.simulation_frequency = int(config["simulation_frequency"])
     c.policy_frequency = int(config["policy_frequency"])
@@ -247,7 +258,11 @@ class NetOracleBatch:
             kind[0] = KIND_MDP
             self.a["kind"][e] = kind
         self.a["route"][e], self.a["route_len"][e] = st["route"], st["route_len"]
-        self.a["speed_index"][e] = st["speed_index"][0]
+        if self.a["speed_index"].ndim == 2:  # one entry per controlled vehicle, in list order
+            si = np.asarray(st["speed_index"])[np.asarray(st["kind"]) == KIND_MDP]
+            self.a["speed_index"][e, :len(si)] = si
+        else:
+            self.a["speed_index"][e] = st["speed_index"][0]
         self.a["time"][e] = float(st["time"])
 
 
@@ -277,6 +292,13 @@ class IntersectionOracle(NetOracleBatch):
                 self.succ[f].append(t)
         self.rng = [np.random.Generator(np.random.PCG64(0)) for _ in range(n_envs)]
         self.a["count"][:] = 0
+        # several controlled vehicles: MultiAgentAction / MultiAgentObservation (intersection-multi-agent-v0)
+        self.A = int(config.get("controlled_vehicles", 1))
+        if self.A > 1:
+            self.a["speed_index"] = np.zeros((n_envs, self.A), dtype=np.int32)
+            self.obs = np.zeros((n_envs, self.A * self.obs_size), dtype=np.float32)
+            self.agents_reward = np.zeros((n_envs, self.A), dtype=np.float64)
+            self.agents_terminated = np.zeros((n_envs, self.A), dtype=np.int32)
 
     # ---- helpers
     def set_rng_words(self, e, w):
@@ -388,27 +410,49 @@ class IntersectionOracle(NetOracleBatch):
         st = self._state(e)
         lib().net_substeps(C.byref(self.g), C.byref(self.cfg), C.byref(st), 3 * int(self.config["simulation_frequency"]))
         self._spawn_vehicle(e, 60, spawn_probability=1.0, go_straight=True, position_deviation=0.1, speed_deviation=0.0)
-        ego_lane = self.lane_of[("o0", "ir0", 0)]
-        destination = self.config["destination"] or "o" + str(g.integers(1, 4))
-        x, y = self._lane_pos(ego_lane, 60.0 + 5.0 * g.normal(1.0))
-        heading = lib().net_lane_heading_at(C.byref(self.g.lanes[ego_lane]), 60.0)
-        speed_limit = self.g.lanes[ego_lane].speed_limit
-        ts = [self.cfg.target_speeds[i] for i in range(self.cfg.n_target_speeds)]
-        si = int(np.clip(np.round((speed_limit - ts[0]) / (ts[-1] - ts[0]) * (len(ts) - 1)), 0, len(ts) - 1))
-        idx = self._append(e, x, y, heading, speed_limit, KIND_MDP, destination, 4.0, target_speed=ts[si], timer=0.0)
-        self.a["speed_index"][e] = si
-        # prevent early collisions: drop traffic within 20 m of the ego
-        n = int(self.a["count"][e])
-        keep = [v for v in range(n) if v == idx or not (
-            np.linalg.norm(np.array([self.a["x"][e, v] - x, self.a["y"][e, v] - y])) < 20)]
-        for k in self.a:
-            if k in ("speed_index", "time", "count", "road_steps"):
-                continue
-            self.a[k][e, :len(keep)] = self.a[k][e, keep]
-        self.a["count"][e] = len(keep)
+        for ego_id in range(self.A):  # :291-315, one controlled vehicle per access road
+            ego_lane = self.lane_of[("o%d" % (ego_id % 4), "ir%d" % (ego_id % 4), 0)]
+            destination = self.config["destination"] or "o" + str(g.integers(1, 4))
+            x, y = self._lane_pos(ego_lane, 60.0 + 5.0 * g.normal(1.0))
+            heading = lib().net_lane_heading_at(C.byref(self.g.lanes[ego_lane]), 60.0)
+            speed_limit = self.g.lanes[ego_lane].speed_limit
+            ts = [self.cfg.target_speeds[i] for i in range(self.cfg.n_target_speeds)]
+            si = int(np.clip(np.round((speed_limit - ts[0]) / (ts[-1] - ts[0]) * (len(ts) - 1)), 0, len(ts) - 1))
+            self._append(e, x, y, heading, speed_limit, KIND_MDP, destination, 4.0, target_speed=ts[si], timer=0.0)
+            if self.A > 1:
+                self.a["speed_index"][e, ego_id] = si
+            else:
+                self.a["speed_index"][e] = si
+            # prevent early collisions: drop the TRAFFIC within 20 m of this controlled vehicle (:317-323)
+            n = int(self.a["count"][e])
+            keep = [v for v in range(n) if self.a["kind"][e, v] == KIND_MDP or not (
+                np.linalg.norm(np.array([self.a["x"][e, v] - x, self.a["y"][e, v] - y])) < 20)]
+            for k in self.a:
+                if k in ("speed_index", "time", "count", "road_steps"):
+                    continue
+                self.a[k][e, :len(keep)] = self.a[k][e, keep]
+            self.a["count"][e] = len(keep)
+
+    def observe(self):
+        if self.A == 1:
+            return super().observe()
+        for e in range(self.n):
+            st = self._state(e)
+            lib().net_observe_agents(C.byref(self.g), C.byref(self.cfg), C.byref(st), self.A, self.obs[e].ctypes.data)
+        return self.obs
+
+    def _step_agents(self, actions):
+        acts = np.ascontiguousarray(actions, dtype=np.int32).reshape(self.n, self.A)
+        for e in range(self.n):
+            st = self._state(e)
+            lib().net_step_agents(C.byref(self.g), C.byref(self.cfg), C.byref(st), acts[e].ctypes.data, self.A,
+                                  self.obs[e].ctypes.data, self.reward[e:e + 1].ctypes.data,
+                                  self.terminated[e:e + 1].ctypes.data, self.truncated[e:e + 1].ctypes.data,
+                                  self.agents_reward[e].ctypes.data, self.agents_terminated[e].ctypes.data)
+        return self.obs, self.reward, self.terminated, self.truncated
 
     def step(self, actions):
-        out = super().step(actions)
+        out = super().step(actions) if self.A == 1 else self._step_agents(actions)
         p = float(self.config["spawn_probability"])
         for e in range(self.n):
             self._clear_vehicles(e)

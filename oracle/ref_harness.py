@@ -54,6 +54,7 @@ ENV_CLASSES = {
     "roundabout-v0": ("highway_env.envs.roundabout_env", "RoundaboutEnv"),
     "roundabout-v1": ("highway_env.envs.roundabout_env", "ConnectedLaneRoundaboutEnv"),
     "intersection-v2": ("highway_env.envs.intersection_env", "ConnectedLaneIntersectionEnv"),
+    "intersection-multi-agent-v0": ("highway_env.envs.intersection_env", "MultiAgentIntersectionEnv"),
 }
 
 
@@ -223,8 +224,14 @@ def rollout(env_id: str, config: dict | None, seed: int, actions, record_substep
     states = [dump_state(env, pad)]
     rng_states = [env.np_random.bit_generator.state]
     obs, rew, term, trunc = [np.asarray(obs0)], [], [], []
+    agents_rewards, agents_terminated = [], []
     for a in actions:
+        if isinstance(a, np.ndarray) and a.ndim == 1 and a.dtype.kind == "i":
+            a = tuple(int(x) for x in a)  # MultiAgentAction takes a tuple (action.py:316-321)
         o, r, te, tr, _info = env.step(a)
+        if "agents_rewards" in _info:
+            agents_rewards.append(np.array(_info["agents_rewards"], dtype=np.float64))
+            agents_terminated.append(np.array(_info["agents_terminated"], dtype=np.bool_))
         states.append(dump_state(env, pad))
         rng_states.append(env.np_random.bit_generator.state)
         obs.append(np.asarray(o))
@@ -238,6 +245,8 @@ def rollout(env_id: str, config: dict | None, seed: int, actions, record_substep
     out["terminated"] = np.array(term, dtype=np.bool_)
     out["truncated"] = np.array(trunc, dtype=np.bool_)
     out["actions"] = np.asarray(actions)
+    if agents_rewards:
+        out["agents_rewards"], out["agents_terminated"] = np.stack(agents_rewards), np.stack(agents_terminated)
     m64 = (1 << 64) - 1
     out["rng_words"] = np.array([[st["state"]["state"] >> 64, st["state"]["state"] & m64, st["state"]["inc"] >> 64,
                                   st["state"]["inc"] & m64, (int(st["has_uint32"]) << 32) | int(st["uinteger"])]

@@ -271,3 +271,84 @@ def test_next_step_autoreset_bookkeeping(env_name):
             first_seen = np.where(done_b & (first_seen < 0), t, first_seen) if t else np.where(done_b, 0, -1)
         pending = term | trunc
     assert first_done_checked > 0
+
+
+# ------------------------------------------------------------------ several controlled vehicles
+def test_multi_agent_reset_and_teacher_forced_vs_reference():
+    """intersection-multi-agent-v0 (two MDPVehicles, MultiAgentAction / MultiAgentObservation) against the
+    reference: reset population, every step's state, stacked observations, mean reward, flags, per-agent info,
+    generator words."""
+    name = "intersection_multi_agent"
+    g = load_golden(name)
+    S, T = g["actions"].shape[:2]
+    for mode in ("host", "device"):
+        env = make_env(g["config"], S, autoreset_mode="Disabled", reset_mode=mode)
+        obs, _ = env.reset(seed=[int(s) for s in g["seeds"]])
+        sd = env.state_dict()
+        for i in range(S):
+            compare_inter(inter_state(g, i, 0), oracle_view(sd), i, f"{name} {mode} reset#{i}", tol=1e-7)
+            assert np.array_equal(sd["rng"][:, i], g["rng_words"][i, 0]), i
+        assert obs.shape == (S, 2, 15, 7)
+        assert np.max(np.abs(obs.cpu().numpy() - g["obs"][:, 0])) <= 1e-6
+    for t in range(T):
+        st = to_sd([inter_state(g, i, t) for i in range(S)], g["rng_words"][:, t])
+        st["speed_index"] = np.stack([np.asarray(g["speed_index"][i, t])[np.asarray(g["kind"][i, t]) == 1][:2]
+                                      for i in range(S)])
+        env.load_state_dict(st)
+        obs, rew, term, trunc, info = env.step(g["actions"][:, t].astype(np.int32))
+        sd = env.state_dict()
+        obs, rew, term, trunc = obs.cpu().numpy(), rew.cpu().numpy(), term.cpu().numpy(), trunc.cpu().numpy()
+        ar, at = info["agents_rewards"].cpu().numpy(), info["agents_terminated"].cpu().numpy()
+        for i in range(S):
+            ctx = f"{name} #{i} t={t}"
+            compare_inter(inter_state(g, i, t + 1), oracle_view(sd), i, ctx, tol=1e-8)
+            assert abs(rew[i] - g["reward"][i, t]) <= 1e-9, ctx
+            assert bool(term[i]) == bool(g["terminated"][i, t]) and bool(trunc[i]) == bool(g["truncated"][i, t]), ctx
+            assert np.max(np.abs(obs[i] - g["obs"][i, t + 1])) <= 1e-6, ctx
+            assert np.max(np.abs(ar[i] - g["agents_rewards"][i, t])) <= 1e-9, ctx
+            assert np.array_equal(at[i], g["agents_terminated"][i, t]), ctx
+            assert np.array_equal(sd["rng"][:, i], g["rng_words"][i, t + 1]), ctx
+
+
+def test_multi_agent_many_envs_vs_oracle_and_wrapper_ids():
+    g = load_golden("intersection_multi_agent")
+    n = 96
+    ob = no.IntersectionOracle(no.graph_from_arrays(g), no.cfg_from_dict(g["config"]), n, g, g["config"])
+    env = make_env(g["config"], n, autoreset_mode="Disabled", reset_mode="host")
+    env.reset(seed=5100)
+    for e in range(n):
+        ob.reset_env(e, seed=5100 + e)
+    rng = np.random.default_rng(12)
+    for t in range(10):
+        state = {k: ob.a[k].copy() for k in ob.a}
+        state["rng"] = np.stack([ob.rng_words(e) for e in range(n)], axis=1)
+        env.load_state_dict(state)
+        act = rng.integers(0, 3, size=(n, 2)).astype(np.int32)
+        o_obs, o_rew, o_term, o_trunc = ob.step(act)
+        obs, rew, term, trunc, info = env.step(act)
+        sd = env.state_dict()
+        assert np.array_equal(sd["count"], ob.a["count"]), t
+        live = np.arange(V)[None, :] < sd["count"][:, None]
+        # controlled vehicles told to stop crawl at |v| < 1 m/s, where the reference's steering law divides by
+        # not_zero(speed) and amplifies 1-ulp differences by ~1e6 per step (DESIGN.md section 4): 1e-5 is the bar
+        for k in ("x", "y", "heading", "speed", "target_speed"):
+            assert np.max(np.abs(np.where(live, sd[k] - ob.a[k], 0.0))) <= 1e-5, (t, k)
+        for k in ("lane", "target_lane", "crashed", "kind", "is_yielding"):
+            assert np.array_equal(np.where(live, sd[k], 0).astype(np.int32), np.where(live, ob.a[k], 0).astype(np.int32)), (t, k)
+        assert np.array_equal(sd["speed_index"], ob.a["speed_index"])
+        assert np.max(np.abs(rew.cpu().numpy() - o_rew)) <= 1e-9
+        assert np.max(np.abs(info["agents_rewards"].cpu().numpy() - ob.agents_reward)) <= 1e-9
+        assert np.array_equal(info["agents_terminated"].cpu().numpy(), ob.agents_terminated.astype(bool))
+        assert np.array_equal(term.cpu().numpy(), o_term.astype(bool)) and np.array_equal(trunc.cpu().numpy(), o_trunc.astype(bool))
+        assert np.max(np.abs(obs.cpu().numpy().reshape(n, -1) - o_obs.reshape(n, -1))) <= 1e-6
+    # the wrapper ids return the per-agent entries; v2 adds the connected-lane search; SameStep autoreset on device
+    import highwayenv_b200 as hb
+    for env_id in ("intersection-multi-agent-v1", "intersection-multi-agent-v2"):
+        w = hb.make(env_id, num_envs=32)
+        o, _ = w.reset(seed=3)
+        assert o.shape == (32, 2, 15, 7)
+        for t in range(16):
+            o, r, te, tr, info = w.step(rng.integers(0, 3, size=(32, 2)).astype(np.int32))
+            assert r.shape == (32, 2) and te.shape == (32, 2) and tr.shape == (32,)
+            assert np.isfinite(o.cpu().numpy()).all()
+        assert bool(w.config["neighbour_vehicles_connected_lanes"]) == env_id.endswith("v2")

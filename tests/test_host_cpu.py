@@ -163,7 +163,8 @@ def test_network_env_defaults_match_reference_config():
     from highwayenv_b200.config import default_config
     from parity_utils import load_golden
 
-    for name in ("intersection_kin", "intersection_v2_kin", "roundabout_kin", "roundabout_v1_kin"):
+    for name in ("intersection_kin", "intersection_v2_kin", "roundabout_kin", "roundabout_v1_kin",
+                 "intersection_multi_agent"):
         ref = dict(load_golden(name)["config"])
         env_id = ref.pop("_env_id")
         ref.pop("_others_check_collisions")

@@ -142,3 +142,35 @@ def test_intersection_reset_and_teacher_forced(name):
             assert bool(term[i]) == bool(g["terminated"][i, t]) and bool(trunc[i]) == bool(g["truncated"][i, t]), ctx
             assert np.max(np.abs(obs[i].reshape(g["obs"][i, t + 1].shape) - g["obs"][i, t + 1])) <= 1e-6, ctx
             assert np.array_equal(ob.rng_words(i), g["rng_words"][i, t + 1]), ctx
+
+
+def test_intersection_multi_agent_reset_and_teacher_forced():
+    """intersection-multi-agent-v0: two controlled vehicles (MultiAgentAction tuple actions, stacked
+    observations, mean reward, any-crashed / all-arrived termination, per-agent info) vs the reference."""
+    name = "intersection_multi_agent"
+    g = load_golden(name)
+    graph = no.graph_from_arrays(g)
+    cfg = no.cfg_from_dict(g["config"])
+    S, T = g["actions"].shape[:2]
+    ob = no.IntersectionOracle(graph, cfg, S, g, g["config"])
+    assert ob.A == 2
+    for i in range(S):
+        ob.reset_env(i, seed=int(g["seeds"][i]))
+        compare_inter(inter_state(g, i, 0), ob.a, i, f"{name} reset#{i}")
+        assert np.array_equal(ob.rng_words(i), g["rng_words"][i, 0])
+    obs0 = ob.observe().reshape(g["obs"][:, 0].shape)
+    assert np.max(np.abs(obs0 - g["obs"][:, 0])) <= 1e-6
+    for t in range(T):
+        for i in range(S):
+            ob.load_state(i, inter_state(g, i, t))
+            ob.set_rng_words(i, g["rng_words"][i, t])
+        obs, rew, term, trunc = ob.step(g["actions"][:, t])
+        for i in range(S):
+            ctx = f"{name} #{i} t={t}"
+            compare_inter(inter_state(g, i, t + 1), ob.a, i, ctx)
+            assert abs(rew[i] - g["reward"][i, t]) <= 1e-9, ctx
+            assert bool(term[i]) == bool(g["terminated"][i, t]) and bool(trunc[i]) == bool(g["truncated"][i, t]), ctx
+            assert np.max(np.abs(obs[i].reshape(g["obs"][i, t + 1].shape) - g["obs"][i, t + 1])) <= 1e-6, ctx
+            assert np.max(np.abs(ob.agents_reward[i] - g["agents_rewards"][i, t])) <= 1e-9, ctx
+            assert np.array_equal(ob.agents_terminated[i].astype(bool), g["agents_terminated"][i, t]), ctx
+            assert np.array_equal(ob.rng_words(i), g["rng_words"][i, t + 1]), ctx
