@@ -147,6 +147,7 @@ EXPORTS = (
     "hwy_highway_observe", "hwy_highway_step", "hwy_highway_autoreset", "hwy_launch_count",
     "hwy_network_obs_size", "hwy_network_step", "hwy_network_observe", "hwy_roundabout_reset",
     "hwy_intersection_step", "hwy_network_substeps", "hwy_intersection_reset", "hwy_intersection_step_agents",
+    "hwy_debug_network_neighbours", "hwy_debug_rotated_rectangles_intersect",
 )
 
 _lib = None
@@ -192,6 +193,10 @@ def load():
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.hwy_intersection_step_agents.restype = C.c_int
     lib.hwy_intersection_step_agents.argtypes = [NP, NG, C.POINTER(HwyIntersectionSpawn), NS] + [C.c_void_p] * 10
+    lib.hwy_debug_network_neighbours.restype = C.c_int
+    lib.hwy_debug_network_neighbours.argtypes = [NP, NG, NS, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.hwy_debug_rotated_rectangles_intersect.restype = C.c_int
+    lib.hwy_debug_rotated_rectangles_intersect.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.hwy_intersection_reset.restype = C.c_int
     lib.hwy_intersection_reset.argtypes = [NP, NG, C.POINTER(HwyIntersectionSpawn), NS, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_void_p]

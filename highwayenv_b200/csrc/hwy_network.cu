@@ -1462,6 +1462,42 @@ network_observe_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGraph
     observe_agents(P, g, st, i, obs + (size_t)e * n_agents_of(P) * obs_size(P));
 }
 
+// Test entries for the reference's own known-answer tests: Road.neighbour_vehicles(vehicle, lane) of every vehicle
+// (tests/road/test_neighbour_vehicles.py) and utils.rotated_rectangles_intersect (tests/test_utils.py:19-27).
+template <int G, bool REG>
+__global__ void __launch_bounds__(kBlockThreads)
+debug_neighbours_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGraph* __restrict__ graph,
+                        const __grid_constant__ HwyNetState S, const int32_t* __restrict__ query_lane,
+                        int32_t* __restrict__ front, int32_t* __restrict__ rear) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    GraphShared& g = *reinterpret_cast<GraphShared*>(smem_raw);
+    EnvStage<G, REG>* stages =
+        reinterpret_cast<EnvStage<G, REG>*>(smem_raw + ((sizeof(GraphShared) + 15) & ~size_t(15)));
+    stage_graph(g, graph);
+    constexpr int kEnvs = kBlockThreads / G;
+    const int sub = threadIdx.x / G, i = threadIdx.x % G;
+    const int env = blockIdx.x * kEnvs + sub;
+    const bool env_ok = env < S.n_envs;
+    const int e = env_ok ? env : S.n_envs - 1;
+    EnvStage<G, REG>& st = stages[sub];
+    Regs r;
+    load_env(P, g, S, st, e, i, r);
+    int f = -1, rr = -1;
+    const size_t slot = (size_t)e * S.vp + i;
+    if (i < st.count) neighbours(g, st, st.count, i, query_lane ? query_lane[slot] : st.lane[i], P.connected_lanes != 0, f, rr);
+    if (env_ok) {
+        front[slot] = f;
+        rear[slot] = rr;
+    }
+}
+__global__ void debug_rectangles_kernel(const double* __restrict__ rects, int n, int32_t* __restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const double* q = rects + 10 * k;
+    out[k] = has_corner_inside(q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7], q[8], q[9]) ||
+             has_corner_inside(q[5], q[6], q[7], q[8], q[9], q[0], q[1], q[2], q[3], q[4]);
+}
+
 // Road.act + Road.step `n_substeps` times with no ego action (IntersectionEnv._make_vehicles warm-up)
 template <int G, bool REG>
 __global__ void __launch_bounds__(kBlockThreads)
@@ -1897,6 +1933,34 @@ int hwy_intersection_reset(const HwyNetParams* p, const HwyNetGraph* graph, cons
                                                                                              spawn->scratch, obs);
     }
     return check_launch("intersection_reset_kernel");
+}
+
+int hwy_debug_network_neighbours(const HwyNetParams* p, const HwyNetGraph* graph, const HwyNetState* s,
+                                 const int32_t* query_lane, int32_t* front, int32_t* rear, void* stream) {
+    if (validate_net(p, graph, s)) return 1;
+    if (!front || !rear) return fail("%s", "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (s->vp == HWY_NET_GROUP) {
+        const size_t smem = net_smem_bytes<HWY_NET_GROUP, false>();
+        if (configure_smem(hwynet::debug_neighbours_kernel<HWY_NET_GROUP, false>, smem)) return 1;
+        hwynet::debug_neighbours_kernel<HWY_NET_GROUP, false>
+            <<<blocks_for(s->n_envs, HWY_NET_GROUP), hwynet::kBlockThreads, smem, st>>>(*p, graph, *s, query_lane, front,
+                                                                                       rear);
+    } else {
+        const size_t smem = net_smem_bytes<HWY_NET_GROUP_LARGE, true>();
+        if (configure_smem(hwynet::debug_neighbours_kernel<HWY_NET_GROUP_LARGE, true>, smem)) return 1;
+        hwynet::debug_neighbours_kernel<HWY_NET_GROUP_LARGE, true>
+            <<<blocks_for(s->n_envs, HWY_NET_GROUP_LARGE), hwynet::kBlockThreads, smem, st>>>(*p, graph, *s, query_lane,
+                                                                                             front, rear);
+    }
+    return check_launch("debug_neighbours_kernel");
+}
+
+int hwy_debug_rotated_rectangles_intersect(const double* rects, int n, int32_t* out, void* stream) {
+    if (!rects || !out || n < 0) return fail("%s", "bad arguments");
+    if (n == 0) return 0;
+    hwynet::debug_rectangles_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rects, n, out);
+    return check_launch("debug_rectangles_kernel");
 }
 
 int hwy_network_substeps(const HwyNetParams* p, const HwyNetGraph* graph, const HwyNetState* s, const uint8_t* mask,

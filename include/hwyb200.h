@@ -322,6 +322,15 @@ int hwy_intersection_reset(const HwyNetParams *p, const HwyNetGraph *graph, cons
                            const HwyNetState *s, const uint8_t *mask_a, const uint8_t *mask_b, float *obs,
                            float *final_obs, void *stream);
 
+/* Test entries (the reference's own known-answer tests run against the device functions):
+ * Road.neighbour_vehicles(v, lane) (road/road.py:483-547) for every vehicle v of every env — lane = query_lane
+ * [n_envs*vp] or, when NULL, v's own lane — into front / rear [n_envs*vp] (slot index, -1 = None);
+ * utils.rotated_rectangles_intersect (utils.py:115-125) for n pairs, rects [n][10] =
+ * (cx, cy, length, width, angle) x 2 on the DEVICE. */
+int hwy_debug_network_neighbours(const HwyNetParams *p, const HwyNetGraph *graph, const HwyNetState *s,
+                                 const int32_t *query_lane, int32_t *front, int32_t *rear, void *stream);
+int hwy_debug_rotated_rectangles_intersect(const double *rects, int n, int32_t *out, void *stream);
+
 /* Road.act() + Road.step(dt) n_substeps times without an ego action, for the envs whose mask byte is
  * set (NULL: all): the 3 s warm-up of IntersectionEnv._make_vehicles (:271-278). */
 int hwy_network_substeps(const HwyNetParams *p, const HwyNetGraph *graph, const HwyNetState *s,

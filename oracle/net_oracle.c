@@ -90,6 +90,12 @@ static int orc_rotated_rectangles_intersect(double c1x, double c1y, double l1, d
            has_corner_inside(c2x, c2y, l2, w2, a2, c1x, c1y, l1, w1, a1);
 }
 
+/* test entry for the reference's known-answer test (tests/test_utils.py:19-27) */
+int net_rotated_rectangles_intersect(double c1x, double c1y, double l1, double w1, double a1, double c2x, double c2y,
+                                     double l2, double w2, double a2) {
+    return orc_rotated_rectangles_intersect(c1x, c1y, l1, w1, a1, c2x, c2y, l2, w2, a2);
+}
+
 /* utils.py:177-185 */
 static void project_polygon(const double p[5][2], double ax, double ay, double *mn, double *mx) {
     double lo = 0, hi = 0;
@@ -337,6 +343,21 @@ static void neighbour_vehicles(const World *w, int veh, int lane_idx, int *front
     }
     *front = v_front;
     *rear = v_rear;
+}
+
+/* test entry: Road.neighbour_vehicles(vehicle, lane_index) for the reference's own known-answer tests
+ * (tests/road/test_neighbour_vehicles.py) */
+void net_neighbours(const NetGraph *g, const NetCfg *c, const NetState *s, int veh, int lane_idx, int32_t *front,
+                    int32_t *rear) {
+    World w;
+    w.g = g;
+    w.c = c;
+    w.s = (NetState *)s;
+    w.V = world_count(c, s);
+    int f, r;
+    neighbour_vehicles(&w, veh, lane_idx, &f, &r);
+    *front = f;
+    *rear = r;
 }
 
 /* vehicle/behavior.py:192-217 */

@@ -109,6 +109,12 @@ void net_substeps(const NetGraph *g, const NetCfg *c, NetState *s, int substeps)
 int net_has_arrived(const NetGraph *g, const NetState *s, int v);
 int net_obs_size(const NetCfg *c);
 
+/* entries for the reference's own known-answer tests */
+void net_neighbours(const NetGraph *g, const NetCfg *c, const NetState *s, int veh, int lane_idx, int32_t *front,
+                    int32_t *rear);
+int net_rotated_rectangles_intersect(double c1x, double c1y, double l1, double w1, double a1, double c2x, double c2y,
+                                     double l2, double w2, double a2);
+
 /* geometry KATs */
 void net_lane_local(const NetLane *L, double x, double y, double *s, double *lat);
 void net_lane_position(const NetLane *L, double s, double lat, double *x, double *y);

@@ -93,6 +93,11 @@ def lib():
         _lib.net_observe_agents.restype = None
         _lib.net_observe_agents.argtypes = [C.POINTER(NetGraph), C.POINTER(NetCfg), C.POINTER(NetState), C.c_int,
                                             C.c_void_p]
+        _lib.net_neighbours.restype = None
+        _lib.net_neighbours.argtypes = [C.POINTER(NetGraph), C.POINTER(NetCfg), C.POINTER(NetState), C.c_int, C.c_int,
+                                        C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        _lib.net_rotated_rectangles_intersect.restype = C.c_int
+        _lib.net_rotated_rectangles_intersect.argtypes = [C.c_double] * 10
         _lib.net_substeps.restype = None
         _lib.net_substeps.argtypes = [C.POINTER(NetGraph), C.POINTER(NetCfg), C.POINTER(NetState), C.c_int]
         _lib.net_has_arrived.restype = C.c_int
