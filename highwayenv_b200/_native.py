@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("HWYB200_LIB") or os.path.join(_HERE, "csrc", "libhwyb200.so")
 
-HWY_ABI_VERSION = 1
+HWY_ABI_VERSION = 3  # bump with every change of a struct or signature: a stale libhwyb200.so then fails to load
 HWY_MAX_LANES = 8
 HWY_MAX_TARGET_SPEEDS = 8
 HWY_MAX_VEHICLES = 128
@@ -109,7 +109,9 @@ class HwyNetParams(C.Structure):
             "perception_distance")]
         + [(n, C.c_int32) for n in ("regulated", "action_mode", "reward_type", "obs_features", "offroad_terminal",
                                     "dynamic_population", "connected_lanes", "n_agents")]
-        + [(n, C.c_double) for n in ("arrived_reward", "reward_speed_lo", "reward_speed_hi")]
+        + [(n, C.c_double) for n in ("arrived_reward", "reward_speed_lo", "reward_speed_hi", "right_lane_reward",
+                                     "merging_speed_reward")]
+        + [("merge_lane", C.c_int32), ("_pad_merge", C.c_int32)]
     )
 
 
@@ -130,6 +132,14 @@ class HwyIntersectionSpawn(C.Structure):
                 ("_pad", C.c_int32), ("scratch", C.c_void_p)]
 
 
+class HwyMergeSpawn(C.Structure):
+    _fields_ = [("lane_ab", C.c_int32 * 2), ("lane_jk", C.c_int32), ("ego_speed_index", C.c_int32),
+                ("obstacle_x", C.c_double), ("obstacle_y", C.c_double)]
+
+
+KIND_OBSTACLE = 3
+
+
 class HwyRoundaboutSpawn(C.Structure):
     _fields_ = [
         ("ego_lane", C.c_int32), ("spawn_lane", C.c_int32 * 4), ("fixed_destination", C.c_int32),
@@ -147,7 +157,7 @@ EXPORTS = (
     "hwy_highway_observe", "hwy_highway_step", "hwy_highway_autoreset", "hwy_launch_count",
     "hwy_network_obs_size", "hwy_network_step", "hwy_network_observe", "hwy_roundabout_reset",
     "hwy_intersection_step", "hwy_network_substeps", "hwy_intersection_reset", "hwy_intersection_step_agents",
-    "hwy_debug_network_neighbours", "hwy_debug_rotated_rectangles_intersect",
+    "hwy_debug_network_neighbours", "hwy_debug_rotated_rectangles_intersect", "hwy_merge_reset",
 )
 
 _lib = None
@@ -197,6 +207,9 @@ def load():
     lib.hwy_debug_network_neighbours.argtypes = [NP, NG, NS, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.hwy_debug_rotated_rectangles_intersect.restype = C.c_int
     lib.hwy_debug_rotated_rectangles_intersect.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.hwy_merge_reset.restype = C.c_int
+    lib.hwy_merge_reset.argtypes = [NP, NG, C.POINTER(HwyMergeSpawn), NS, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p]
     lib.hwy_intersection_reset.restype = C.c_int
     lib.hwy_intersection_reset.argtypes = [NP, NG, C.POINTER(HwyIntersectionSpawn), NS, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_void_p]

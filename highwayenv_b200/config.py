@@ -209,3 +209,21 @@ def multi_agent_intersection_default_config() -> dict:
 DEFAULTS["intersection-multi-agent-v0"] = multi_agent_intersection_default_config
 DEFAULTS["intersection-multi-agent-v1"] = multi_agent_intersection_default_config
 DEFAULTS["intersection-multi-agent-v2"] = _connected(multi_agent_intersection_default_config)
+
+
+def merge_default_config() -> dict:
+    """MergeEnv.default_config (highway_env/envs/merge_env.py:24-37) over AbstractEnv's."""
+    config = abstract_default_config()
+    update_config(config, {
+        "collision_reward": -1,
+        "right_lane_reward": 0.1,
+        "high_speed_reward": 0.2,
+        "reward_speed_range": [20, 30],
+        "merging_speed_reward": -0.5,
+        "lane_change_reward": -0.05,
+    })
+    return config
+
+
+DEFAULTS["merge-v0"] = merge_default_config
+DEFAULTS["merge-v1"] = _connected(merge_default_config)

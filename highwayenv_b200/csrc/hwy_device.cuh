@@ -115,8 +115,8 @@ __device__ __forceinline__ int speed_to_index(const HwyHighwayParams& P, double 
 struct Quad {
     double x[4], y[4];
 };
-__device__ __forceinline__ Quad make_polygon(double px, double py, double c, double s) {
-    const double hl = kVehLength / 2, hw = kVehWidth / 2;
+__device__ __forceinline__ Quad make_polygon(double px, double py, double c, double s, double length = kVehLength) {
+    const double hl = length / 2, hw = kVehWidth / 2;
     const double lx[4] = {-hl, -hl, +hl, +hl};
     const double ly[4] = {-hw, +hw, +hw, -hw};
     Quad q;

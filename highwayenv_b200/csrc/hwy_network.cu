@@ -334,7 +334,7 @@ __device__ __forceinline__ double desired_gap(const HwyNetParams& P, const EnvSt
 template <int G, bool REG>
 __device__ __noinline__ double idm_acceleration(const HwyNetParams& P, const GraphShared& g,
                                                 const EnvStage<G, REG>& st, double delta, int ego, int front) {
-    if (ego < 0) return 0.0;
+    if (ego < 0 || st.kind[ego] == HWY_KIND_OBSTACLE) return 0.0;  // `not isinstance(ego_vehicle, Vehicle)`
     double ego_target_speed = clipd(st.ts[ego], 0.0, g.lanes[st.lane[ego]].speed_limit);
     double acc = P.comfort_acc_max *
                  (1 - m_pow(fmax(st.v[ego], 0.0) / fabs(not_zero(ego_target_speed)), delta));
@@ -463,8 +463,9 @@ __device__ __forceinline__ void phase_sync() {
 // |lateral| — no atan2 needed — exceeds that bound can never win.  The surviving (vehicle, lane) pairs go to a
 // shared work list that the whole group evaluates, then every vehicle reduces its own entries by (d, lane).
 template <int G, bool REG>
-__device__ __forceinline__ void closest_lane_group(const GraphShared& g, EnvStage<G, REG>& st, int V, int i) {
-    const bool active = i < V;
+__device__ __forceinline__ void closest_lane_group(const GraphShared& g, EnvStage<G, REG>& st, int V, int i,
+                                                   bool mobile) {
+    const bool active = i < V && mobile;  // a road object keeps the lane it was created on
     constexpr int K = kCand<G>();
     double x = 0, y = 0, h = 0, bd = 0, bs = 0, blat = 0;
     int bl = 0;
@@ -579,7 +580,7 @@ __device__ __forceinline__ void observe_ttc(const HwyNetParams& P, const GraphSh
     const int n_t = (int)(P.ttc_horizon / tq);
     for (int k = i; k < 3 * 4 * 12; k += G) (&st.o.ttc[0][0][0])[k] = 0.0;
     group_sync<G>();
-    if (i != ego && i < V) {  // one thread per other vehicle; cells take the max cost (atomic on bits)
+    if (i != ego && i < V && st.kind[i] != HWY_KIND_OBSTACLE) {  // one thread per other VEHICLE; cells take the max cost
         const int o = i;
         const HwyNetLane& OL = g.lanes[st.lane[o]];
         const bool connected = is_connected_road(g, EL.from_node, EL.to_node, OL.from_node, OL.to_node,
@@ -638,7 +639,8 @@ __device__ __forceinline__ void observe_kinematics(const HwyNetParams& P, const 
     if (i != ego && i < V) {
         bool ok = norm2(st.x[i] - ex, st.y[i] - ey) < P.perception_distance;
         double d = lane_distance_to(g, st, ego, i);
-        ok = ok && (P.obs_see_behind || -2 * kVehLength < d);
+        // close_objects_to (road/road.py:421-450): obstacles are always filtered like see_behind=False
+        ok = ok && ((P.obs_see_behind && st.kind[i] != HWY_KIND_OBSTACLE) || -2 * kVehLength < d);
         if (ok) key = fabs(d);
     }
     st.key[i] = key;
@@ -1033,7 +1035,9 @@ __device__ __forceinline__ void substep(const HwyNetParams& P, const GraphShared
     bool ordered = false;
     if (active) {
         st.tgt_prev[i] = st.tgt[i];
-        if (kind != HWY_KIND_IDM || !crashed) follow_road(g, st, i);  // behavior.py:102-103, controller.py:98
+        // road.objects neither act nor step (road/road.py:464-476)
+        if (kind != HWY_KIND_OBSTACLE && (kind != HWY_KIND_IDM || !crashed))
+            follow_road(g, st, i);  // behavior.py:102-103, controller.py:98
         if (kind == HWY_KIND_IDM && !crashed) {
             const int lane = st.lane[i], tgt = st.tgt[i];
             const HwyNetLane &A = g.lanes[lane], &B = g.lanes[tgt];
@@ -1056,8 +1060,9 @@ __device__ __forceinline__ void substep(const HwyNetParams& P, const GraphShared
         group_sync<G>();
     }
     // ---- parallel part: steering + acceleration
+    const bool mobile = active && kind != HWY_KIND_OBSTACLE;  // road.objects neither act nor step
     double sin_beta = 0.0, cos_beta = 1.0;
-    if (active) {
+    if (mobile) {
         const int lane = st.lane[i], tgt = st.tgt[i];
         if (!crashed) {
             double lc_s = st.own_s[i], lc_lat = st.own_lat[i];
@@ -1087,7 +1092,7 @@ __device__ __forceinline__ void substep(const HwyNetParams& P, const GraphShared
         if (P.regulated && st.road_steps % (int)(1 / dt / 2) == 0) enforce_road_rules(P, g, st, V, i, r);
     }
     // ---- Road.step: Vehicle.step (kinematics.py:130-177), IDMVehicle.step timer (behavior.py:139-148)
-    if (active) {
+    if (mobile) {
         if (kind == HWY_KIND_IDM) r.timer += dt;
         if (crashed) act_accel = -1.0 * r.speed;
         if (r.speed > kMaxSpeed)
@@ -1109,25 +1114,33 @@ __device__ __forceinline__ void substep(const HwyNetParams& P, const GraphShared
     phase_sync<G>();  // everyone is done reading the pre-step staging
     if (active) publish(st, i, r);
     phase_sync<G>();
-    closest_lane_group(g, st, V, i);  // on_state_update
+    closest_lane_group(g, st, V, i, mobile);  // on_state_update
     // ---- collision sweep (road/road.py:477-481): partners in ascending order => the surviving impact is
     // the one of the largest partner index
+    // Road objects (Obstacle: 2 x 2 m, kind 3) sit in the slots after the vehicles, so vehicle i meets its vehicle
+    // partners first and the objects last, as in the reference; only vehicles call handle_collisions; against an
+    // Obstacle the vehicle takes the WHOLE transition (vehicle/objects.py:104-107).
     if (active) {
-        const double diag = sqrt(kVehLength * kVehLength + kVehWidth * kVehWidth);
         for (int j = 0; j < V; ++j) {
             if (j == i) continue;
             int a = i < j ? i : j, b = i < j ? j : i;
+            if (st.kind[a] == HWY_KIND_OBSTACLE) continue;
+            const bool b_object = st.kind[b] == HWY_KIND_OBSTACLE;
+            const double len_b = b_object ? 2.0 : kVehLength;
+            const double diag_a = sqrt(kVehLength * kVehLength + kVehWidth * kVehWidth);
+            const double diag_b = sqrt(len_b * len_b + kVehWidth * kVehWidth);
             double dist = norm2(st.x[b] - st.x[a], st.y[b] - st.y[a]);
-            if (dist > (diag + diag) / 2 + st.v[a] * dt) continue;
+            if (dist > (diag_a + diag_b) / 2 + st.v[a] * dt) continue;
             Quad pa = make_polygon(st.x[a], st.y[a], st.c[a], st.s[a]);
-            Quad pb = make_polygon(st.x[b], st.y[b], st.c[b], st.s[b]);
+            Quad pb = make_polygon(st.x[b], st.y[b], st.c[b], st.s[b], len_b);
             bool inter, will;
             double trx, try_;
             polygons_intersecting(pa, pb, st.v[a] * st.c[a] * dt, st.v[a] * st.s[a] * dt, st.v[b] * st.c[b] * dt,
                                   st.v[b] * st.s[b] * dt, inter, will, trx, try_);
-            if (will) {
-                r.imp_x = i == a ? trx / 2 : -trx / 2;
-                r.imp_y = i == a ? try_ / 2 : -try_ / 2;
+            if (will && !(b_object && i == b)) {
+                const double share = b_object ? 1.0 : 0.5;
+                r.imp_x = i == a ? trx * share : -trx * share;
+                r.imp_y = i == a ? try_ * share : -try_ * share;
                 r.meta |= HWY_META_HAS_IMPACT;
             }
             if (inter) r.meta |= HWY_META_CRASHED;
@@ -1384,6 +1397,22 @@ network_step_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGraph* _
             rew *= on_road ? 1.0 : 0.0;
             if (P.normalize_reward) rew = lmap(rew, P.collision_reward, P.arrived_reward, 0.0, 1.0);
             term = is_crashed || arrived || (P.offroad_terminal && !on_road);
+        } else if (P.reward_type == 2) {
+            // envs/merge_env.py:39-84: unclipped speed term, lane id of the CURRENT lane, altruistic penalty over the
+            // ControlledVehicles on the merging lane ("b", "c", 2); never truncated, terminated past x = 370
+            double scaled_speed = lmap(r.speed, P.reward_speed_lo, P.reward_speed_hi, 0.0, 1.0);
+            double merging = 0.0;
+            for (int v = 0; v < V; ++v)
+                if (st.lane[v] == P.merge_lane && st.kind[v] != HWY_KIND_OBSTACLE)
+                    merging = merging + (st.ts[v] - st.v[v]) / st.ts[v];
+            rew = rew + P.collision_reward * (is_crashed ? 1.0 : 0.0);
+            rew = rew + P.right_lane_reward * ((double)L.lane_id / 1.0);
+            rew = rew + P.high_speed_reward * scaled_speed;
+            rew = rew + P.lane_change_reward * ((act == 0 || act == 2) ? 1.0 : 0.0);
+            rew = rew + P.merging_speed_reward * merging;
+            rew = lmap(rew, P.collision_reward + P.merging_speed_reward, P.high_speed_reward + P.right_lane_reward, 0.0,
+                       1.0);
+            term = is_crashed || r.x > 370;
         } else {
             // envs/roundabout_env.py:44-71
             rew = rew + P.collision_reward * (is_crashed ? 1.0 : 0.0);
@@ -1763,6 +1792,68 @@ roundabout_reset_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGrap
     rng[4 * n + e] = ((uint64_t)g.has32 << 32) | g.u32;
 }
 
+// MergeEnv._make_vehicles and the ramp's Obstacle (envs/merge_env.py:150-190), one env per thread
+__global__ void __launch_bounds__(128)
+merge_reset_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGraph* __restrict__ graph,
+                   const __grid_constant__ HwyMergeSpawn SP, const __grid_constant__ HwyNetState S,
+                   uint64_t* __restrict__ rng, const uint8_t* __restrict__ mask_a, const uint8_t* __restrict__ mask_b) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= S.n_envs) return;
+    if ((mask_a || mask_b) && !((mask_a && mask_a[e]) || (mask_b && mask_b[e]))) return;
+    Pcg64 g = load_rng(rng, (size_t)S.n_envs, e);
+    double2* pos = reinterpret_cast<double2*>(S.pos);
+    double2* hs = reinterpret_cast<double2*>(S.hs);
+    double2* tt = reinterpret_cast<double2*>(S.tt);
+    double2* imp = reinterpret_cast<double2*>(S.imp);
+    const size_t base = (size_t)e * S.vp;
+    const double base_position[3] = {90.0, 70.0, 5.0}, base_speed[3] = {29.0, 31.0, 31.5};
+    for (int v = 0; v < 6; ++v) {
+        double px, py, speed, target_speed, timer = 0.0;
+        int kind = HWY_KIND_IDM;
+        if (v == 0) {  // :158-161 ego = action_type.vehicle_class(road, ("a","b",1).position(30, 0), speed=30)
+            lane_position(graph->lanes[SP.lane_ab[1]], 30.0, 0.0, px, py);
+            speed = 30.0;
+            kind = HWY_KIND_MDP;
+            target_speed = P.target_speeds[SP.ego_speed_index];
+        } else if (v <= 3) {  // :165-169
+            const HwyNetLane& L = graph->lanes[SP.lane_ab[g.choice(2)]];  // np_random.integers(2)
+            lane_position(L, base_position[v - 1] + g.uniform(-5.0, 5.0), 0.0, px, py);
+            speed = base_speed[v - 1] + g.uniform(-1.0, 1.0);
+            target_speed = speed;
+        } else if (v == 4) {  // :171-175 the merging vehicle
+            lane_position(graph->lanes[SP.lane_jk], 110.0, 0.0, px, py);
+            speed = 20.0;
+            target_speed = 30.0;
+        } else {  // _make_road :147: Obstacle(road, lbc.position(ends[2], 0))
+            px = SP.obstacle_x;
+            py = SP.obstacle_y;
+            speed = target_speed = 0.0;
+            kind = HWY_KIND_OBSTACLE;
+        }
+        int lane = 0;  // RoadObject.__init__: closest lane at heading 0 (objects.py:46-50)
+        double bd = 0;
+        for (int l = 0; l < graph->n_lanes; ++l) {
+            double d = lane_distance_with_heading(graph->lanes[l], px, py, 0.0);
+            if (l == 0 || d < bd) {
+                bd = d;
+                lane = l;
+            }
+        }
+        if (kind == HWY_KIND_IDM) timer = py_mod_pos((px + py) * kPi, P.lane_change_delay);  // behavior.py:64
+        pos[base + v] = make_double2(px, py);
+        hs[base + v] = make_double2(0.0, speed);
+        tt[base + v] = make_double2(target_speed, timer);
+        imp[base + v] = make_double2(0.0, 0.0);
+        S.delta[base + v] = 4.0;  // IDMVehicle.DELTA: randomize_behavior is not called here
+        S.meta[base + v] = (lane << HWY_META_LANE_SHIFT) | (lane << HWY_META_TARGET_SHIFT) | HWY_META_CHECK_COLLISIONS |
+                           (kind << HWY_META_KIND_SHIFT) | HWY_META_PRESENT;
+        S.route_len[base + v] = 0;
+    }
+    S.speed_index[e] = SP.ego_speed_index;
+    S.time[e] = 0.0;
+    store_rng(rng, (size_t)S.n_envs, e, g);
+}
+
 }  // namespace hwynet
 
 // ====================================================================== C ABI
@@ -1961,6 +2052,18 @@ int hwy_debug_rotated_rectangles_intersect(const double* rects, int n, int32_t* 
     if (n == 0) return 0;
     hwynet::debug_rectangles_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rects, n, out);
     return check_launch("debug_rectangles_kernel");
+}
+
+int hwy_merge_reset(const HwyNetParams* p, const HwyNetGraph* graph, const HwyMergeSpawn* spawn, const HwyNetState* s,
+                    uint64_t* rng, const uint8_t* mask_a, const uint8_t* mask_b, float* obs, void* stream) {
+    if (validate_net(p, graph, s)) return 1;
+    if (!spawn || !rng) return fail("%s", "null spawn / rng");
+    if (s->vp != HWY_NET_GROUP || p->n_vehicles != 6) return fail("%s", "merge-v0: 5 vehicles + 1 obstacle on 8 slots");
+    cudaStream_t st = (cudaStream_t)stream;
+    hwynet::merge_reset_kernel<<<(s->n_envs + 127) / 128, 128, 0, st>>>(*p, graph, *spawn, *s, rng, mask_a, mask_b);
+    if (check_launch("merge_reset_kernel")) return 1;
+    if (obs) return observe_dispatch(p, graph, s, mask_a, mask_b, obs, st);
+    return 0;
 }
 
 int hwy_network_substeps(const HwyNetParams* p, const HwyNetGraph* graph, const HwyNetState* s, const uint8_t* mask,

@@ -189,12 +189,15 @@ class BatchedRoundaboutEnv:
         self.config = self.default_config()
         if config:
             self.config.update(config)
-        self.net = make_roundabout_network()
+        self.net = self._make_network()
         self._graph_dev = torch.from_numpy(
             np.frombuffer(bytes(self.net.to_struct()), dtype=np.uint8).copy()).to(self.device)
         self._rngs = None
         self.define_spaces()
         self._allocate()
+
+    def _make_network(self) -> NetworkTable:
+        return make_roundabout_network()
 
     # ------------------------------------------------------------------ configuration
     def configure(self, config: Optional[dict]) -> None:
@@ -259,7 +262,7 @@ class BatchedRoundaboutEnv:
         p.connected_lanes = int(bool(cfg.get("neighbour_vehicles_connected_lanes", False)))
         self._params = p
         self.single_action_space = Discrete(5)
-        self.spawner = RoundaboutSpawner(self.net, self.config, self.action_type.target_speeds)
+        self.spawner = RoundaboutSpawner(self.net, self.config, self.action_type.target_speeds) if self.ENV_ID.startswith("roundabout") else None
         self.observation_space = batch_space(self.single_observation_space, self.num_envs)
         self.action_space = batch_space(self.single_action_space, self.num_envs)
         self.obs_shape = tuple(self.single_observation_space.shape)

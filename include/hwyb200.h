@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define HWY_ABI_VERSION 1
+#define HWY_ABI_VERSION 3
 #define HWY_MAX_LANES 8
 #define HWY_MAX_TARGET_SPEEDS 8
 #define HWY_MAX_VEHICLES 128 /* per env, incl. the ego */
@@ -45,6 +45,9 @@ extern "C" {
 #define HWY_META_CHECK_COLLISIONS (1 << 18)
 #define HWY_META_KIND_SHIFT 19        /* 2 bits */
 #define HWY_META_PRESENT (1 << 21)
+/* kinds (2 bits): 0 IDMVehicle, 1 MDPVehicle, 2 plain Vehicle (ContinuousAction ego), 3 Obstacle — a static 2 x 2 m
+ * road object (vehicle/objects.py:213-220); road.objects occupy the slots after the vehicles */
+#define HWY_KIND_OBSTACLE 3
 
 /* Kinematics feature columns (Vehicle.to_dict keys, vehicle/kinematics.py:240-254) */
 #define HWY_MAX_OBS_FEATURES 16
@@ -250,6 +253,10 @@ typedef struct HwyNetParams {
                                  * MultiAgentObservation (action.py:301-333, observation.py:588-604): actions, obs and
                                  * speed_index carry n_agents entries per env, controlled vehicles in list order */
     double arrived_reward, reward_speed_lo, reward_speed_hi;
+    /* merge-v0 (envs/merge_env.py:24-84): reward_type 2 */
+    double right_lane_reward, merging_speed_reward;
+    int32_t merge_lane;         /* table index of ("b", "c", 2): slow ControlledVehicles there are penalised */
+    int32_t _pad_merge;
 } HwyNetParams;
 
 /* route entry: from_node | to_node << 8 | (lane_id + 1) << 16  (lane_id + 1 == 0: None) */
@@ -339,6 +346,21 @@ int hwy_network_substeps(const HwyNetParams *p, const HwyNetGraph *graph, const 
 /* observation_type.observe() of the current state */
 int hwy_network_observe(const HwyNetParams *p, const HwyNetGraph *graph, const HwyNetState *s,
                         float *obs, void *stream);
+
+/* MergeEnv._make_vehicles + the Obstacle of _make_road (envs/merge_env.py:150-190) on the device: the MDPVehicle on
+ * ("a","b",1) at s = 30, speed 30; three IDM vehicles on ("a","b", integers(2)) at position + uniform(-5, 5) with
+ * speed + uniform(-1, 1); the merging vehicle on ("j","k",0) at s = 110, speed 20, target speed 30; and, in the
+ * slot after the vehicles, the Obstacle (kind HWY_KIND_OBSTACLE) at the end of the ramp.  mask_a | mask_b select
+ * the envs (both NULL: all); with obs, the fresh observation of those envs is written. */
+typedef struct HwyMergeSpawn {
+    int32_t lane_ab[2];      /* table indices of ("a","b",0), ("a","b",1) */
+    int32_t lane_jk;         /* ("j","k",0) */
+    int32_t ego_speed_index; /* MDPVehicle.speed_to_index(30) */
+    double obstacle_x, obstacle_y;
+} HwyMergeSpawn;
+int hwy_merge_reset(const HwyNetParams *p, const HwyNetGraph *graph, const HwyMergeSpawn *spawn,
+                    const HwyNetState *s, uint64_t *rng, const uint8_t *mask_a, const uint8_t *mask_b,
+                    float *obs, void *stream);
 
 /* RoundaboutEnv._make_vehicles (envs/roundabout_env.py:317-391) on the device.  Per traffic
  * vehicle the env's numpy stream yields normal (longitudinal), normal (speed),

@@ -67,7 +67,25 @@ CASES = {
     "intersection_v2_kin": ("intersection-v2", None, list(range(910, 916)), 13, "discrete3"),
     # (f)2 MultiAgentAction / MultiAgentObservation: two controlled vehicles
     "intersection_multi_agent": ("intersection-multi-agent-v0", None, list(range(920, 926)), 13, "discrete3x2"),
+    # (f)3 scenario builders on the same kernels: merge-v0 (straight + sine lanes, an Obstacle at the ramp's end)
+    "merge_kin": ("merge-v0", None, list(range(930, 938)), 18, "discrete5"),
+    "merge_v1_kin": ("merge-v1", None, list(range(940, 944)), 18, "discrete5"),
+    # the merging vehicle is moved onto the end of the ramp at speed: it runs into the Obstacle (objects.py:104-107)
+    "merge_obstacle_hit": ("merge-v0", None, list(range(950, 954)), 6, "discrete5"),
 }
+
+
+def _ram_the_obstacle(env):
+    lane = env.road.network.get_lane(("b", "c", 2))
+    v = env.road.vehicles[4]
+    v.position = lane.position(58.0 + 3.0 * (env.np_random.uniform()), 0.0)
+    v.heading = lane.heading_at(60.0)
+    v.speed, v.target_speed = 28.0, 30.0
+    v.lane_index = v.target_lane_index = ("b", "c", 2)
+    v.lane = lane
+
+
+MUTATE = {"merge_obstacle_hit": _ram_the_obstacle}
 
 
 def main() -> None:
@@ -90,7 +108,8 @@ def main() -> None:
                 actions = rng.integers(0, 3, size=T).astype(np.int64)
             else:
                 actions = rng.uniform(-1, 1, size=(T, 2)).astype(np.float32)
-            per_seed.append(rh.rollout(env_id, over, seed, list(actions), pad=32 if env_id.startswith("intersection") else 0))
+            per_seed.append(rh.rollout(env_id, over, seed, list(actions), pad=32 if env_id.startswith("intersection") else 0,
+                                       mutate=MUTATE.get(name)))
         out = {k: np.stack([p[k] for p in per_seed]) for k in per_seed[0].keys()}
         out["seeds"] = np.array(seeds, dtype=np.int64)
         env = rh.make_reference_env(env_id, over)
@@ -102,6 +121,10 @@ def main() -> None:
             out.update(rh.dump_network(env))
         cfg["_others_check_collisions"] = 0 if env_id == "highway-fast-v0" else 1
         cfg["_env_id"] = env_id
+        if env_id.startswith("merge"):
+            lanes = [li for li, _ in rh.lane_list(env)]
+            cfg["_merge_lane"] = lanes.index(("b", "c", 2))
+            cfg["_default_side_lanes"] = len(env.road.network.all_side_lanes(env.vehicle.lane_index))
         out["config_json"] = np.array(json.dumps(cfg))
         path = os.path.join(OUT, name + ".npz")
         np.savez_compressed(path, **out)

@@ -377,7 +377,7 @@ static double desired_gap(const World *w, int ego, int front) {
 static double idm_acceleration(const World *w, int self_, int ego, int front) {
     const NetCfg *c = w->c;
     const NetState *s = w->s;
-    if (ego < 0) return 0;
+    if (ego < 0 || s->kind[ego] == NET_KIND_OBSTACLE) return 0; /* `not isinstance(ego_vehicle, Vehicle)` (behavior.py:171) */
     double ego_target_speed = clipd(s->target_speed[ego], 0, LANE(w, s->lane[ego])->speed_limit);
     double acceleration =
         c->comfort_acc_max *
@@ -627,6 +627,7 @@ static int ego_index(const World *w) {
 
 static void road_act(World *w) {
     for (int v = 0; v < w->V; v++) {
+        if (w->s->kind[v] == NET_KIND_OBSTACLE) continue; /* road.objects do not act (road.py:464-467) */
         if (w->s->kind[v] == NET_KIND_IDM)
             idm_act(w, v);
         else
@@ -637,6 +638,7 @@ static void road_act(World *w) {
 /* vehicle/kinematics.py:130-177 (+ behavior.py:139-148) */
 static void vehicle_step(World *w, int v, double dt) {
     NetState *s = w->s;
+    if (s->kind[v] == NET_KIND_OBSTACLE) return; /* only road.vehicles step (road.py:475-476) */
     if (s->kind[v] == NET_KIND_IDM) s->timer[v] += dt;
     if (s->crashed[v]) {
         w->act_steer[v] = 0;
@@ -662,11 +664,15 @@ static void vehicle_step(World *w, int v, double dt) {
     s->lane[v] = net_closest_lane(w->g, s->x[v], s->y[v], s->heading[v]);
 }
 
+static double object_length(const NetState *s, int v) { /* RoadObject.LENGTH 2 (objects.py:25), Vehicle 5 */
+    return s->kind[v] == NET_KIND_OBSTACLE ? 2.0 : VEH_LENGTH;
+}
 static void polygon(const NetState *s, int v, double p[5][2]) {
-    static const double loc[4][2] = {{-VEH_LENGTH / 2, -VEH_WIDTH / 2},
-                                     {-VEH_LENGTH / 2, +VEH_WIDTH / 2},
-                                     {+VEH_LENGTH / 2, +VEH_WIDTH / 2},
-                                     {+VEH_LENGTH / 2, -VEH_WIDTH / 2}};
+    const double len = object_length(s, v);
+    const double loc[4][2] = {{-len / 2, -VEH_WIDTH / 2},
+                              {-len / 2, +VEH_WIDTH / 2},
+                              {+len / 2, +VEH_WIDTH / 2},
+                              {+len / 2, -VEH_WIDTH / 2}};
     double c = cos(s->heading[v]), sn = sin(s->heading[v]);
     for (int k = 0; k < 4; k++) {
         p[k][0] = (c * loc[k][0] + (-sn) * loc[k][1]) + s->x[v];
@@ -680,9 +686,11 @@ static void polygon(const NetState *s, int v, double p[5][2]) {
 static void handle_collisions(World *w, int a, int b, double dt) {
     NetState *s = w->s;
     if (!(s->check_collisions[a] || s->check_collisions[b])) return;
-    double diag = sqrt(VEH_LENGTH * VEH_LENGTH + VEH_WIDTH * VEH_WIDTH);
+    if (s->kind[a] == NET_KIND_OBSTACLE) return; /* Road.step: only vehicles call handle_collisions (road.py:477-481) */
+    double la = object_length(s, a), lb = object_length(s, b);
+    double diag_a = sqrt(la * la + VEH_WIDTH * VEH_WIDTH), diag_b = sqrt(lb * lb + VEH_WIDTH * VEH_WIDTH);
     double dist = norm2(s->x[b] - s->x[a], s->y[b] - s->y[a]);
-    if (dist > (diag + diag) / 2 + s->speed[a] * dt) return;
+    if (dist > (diag_a + diag_b) / 2 + s->speed[a] * dt) return;
     double pa[5][2], pb[5][2], tr[2];
     polygon(s, a, pa);
     polygon(s, b, pb);
@@ -692,12 +700,18 @@ static void handle_collisions(World *w, int a, int b, double dt) {
     orc_polygons_intersecting(pa, pb, s->speed[a] * ca * dt, s->speed[a] * sa * dt,
                               s->speed[b] * cb * dt, s->speed[b] * sb * dt, &inter, &will, tr);
     if (will) {
-        s->impact_x[a] = tr[0] / 2;
-        s->impact_y[a] = tr[1] / 2;
-        s->has_impact[a] = 1;
-        s->impact_x[b] = -tr[0] / 2;
-        s->impact_y[b] = -tr[1] / 2;
-        s->has_impact[b] = 1;
+        if (s->kind[b] == NET_KIND_OBSTACLE) { /* objects.py:106-107: the whole transition goes to the vehicle */
+            s->impact_x[a] = tr[0];
+            s->impact_y[a] = tr[1];
+            s->has_impact[a] = 1;
+        } else {
+            s->impact_x[a] = tr[0] / 2;
+            s->impact_y[a] = tr[1] / 2;
+            s->has_impact[a] = 1;
+            s->impact_x[b] = -tr[0] / 2;
+            s->impact_y[b] = -tr[1] / 2;
+            s->has_impact[b] = 1;
+        }
     }
     if (inter) {
         s->crashed[a] = 1;
@@ -750,7 +764,7 @@ static void observe_ttc(const World *w, float *obs) {
     for (int si = 0; si < n_speeds; si++) {
         double ego_speed = c->target_speeds[si];
         for (int o = 0; o < w->V; o++) {
-            if (o == ego || ego_speed == s->speed[o]) continue;
+            if (o == ego || ego_speed == s->speed[o] || s->kind[o] == NET_KIND_OBSTACLE) continue;
             double margin = VEH_LENGTH / 2 + VEH_LENGTH / 2;
             const double ms[3] = {0, -margin, margin}, costs[3] = {1, 0.5, 0.5};
             const NetLane *OL = &g->lanes[s->lane[o]];
@@ -835,7 +849,8 @@ static void observe_kinematics_from(const World *w, int ego, float *obs) {
         if (!(norm2(s->x[v] - s->x[ego], s->y[v] - s->y[ego]) < c->perception_distance)) continue;
         if (v == ego) continue;
         double d = lane_distance_to(w, ego, v);
-        if (!(c->obs_see_behind || -2 * VEH_LENGTH < d)) continue;
+        /* road.py:421-450 close_objects_to: obstacles are always filtered like see_behind=False */
+        if (!((c->obs_see_behind && s->kind[v] != NET_KIND_OBSTACLE) || -2 * VEH_LENGTH < d)) continue;
         cand[nc] = v;
         key[nc] = fabs(d);
         nc++;
@@ -986,6 +1001,27 @@ static void reward_done(const World *w, int action, double *reward, int32_t *ter
     *reward = r;
     *terminated = s->crashed[ego] != 0;
     *truncated = s->time[0] >= c->duration;
+}
+
+/* envs/merge_env.py:39-84 */
+static void reward_done_merge(const World *w, int action, double *reward, int32_t *terminated, int32_t *truncated) {
+    const NetCfg *c = w->c;
+    const NetState *s = w->s;
+    const int ego = 0;
+    double scaled_speed = lmap(s->speed[ego], c->reward_speed_lo, c->reward_speed_hi, 0, 1);
+    double merging = 0; /* altruistic penalty: ControlledVehicles on the merging lane ("b", "c", 2) */
+    for (int v = 0; v < w->V; v++)
+        if (s->lane[v] == c->merge_lane && s->kind[v] != NET_KIND_OBSTACLE)
+            merging = merging + (s->target_speed[v] - s->speed[v]) / s->target_speed[v];
+    double r = 0;
+    r = r + c->collision_reward * (double)(s->crashed[ego] != 0);
+    r = r + c->right_lane_reward * ((double)LANE(w, s->lane[ego])->lane_id / 1);
+    r = r + c->high_speed_reward * scaled_speed;
+    r = r + c->lane_change_reward * (double)(action == 0 || action == 2);
+    r = r + c->merging_speed_reward * merging;
+    *reward = lmap(r, c->collision_reward + c->merging_speed_reward, c->high_speed_reward + c->right_lane_reward, 0, 1);
+    *terminated = s->crashed[ego] != 0 || s->x[ego] > 370;
+    *truncated = 0;
 }
 
 /* ------------------------------------------------------------------ road/regulation.py */
@@ -1155,6 +1191,8 @@ void net_step(const NetGraph *g, const NetCfg *c, NetState *s, int action, float
     if (obs) net_observe(g, c, s, obs);
     if (c->reward_type == 1)
         reward_done_intersection(&w, reward, terminated, truncated);
+    else if (c->reward_type == 2)
+        reward_done_merge(&w, action, reward, terminated, truncated);
     else
         reward_done(&w, action, reward, terminated, truncated);
     free(act_buf);

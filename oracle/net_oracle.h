@@ -27,6 +27,8 @@ extern "C" {
 
 #define NET_KIND_IDM 0
 #define NET_KIND_MDP 1
+#define NET_KIND_OBSTACLE 3 /* vehicle/objects.py:213-220 Obstacle: a static 2 x 2 m road object (road.objects);
+                             * objects occupy the slots AFTER the vehicles */
 
 #define NET_OBS_KINEMATICS 0 /* envs/common/observation.py:155 */
 #define NET_OBS_OCCUPANCY 1  /* envs/common/observation.py:279 */
@@ -76,6 +78,10 @@ typedef struct NetCfg {
     int32_t offroad_terminal;
     int32_t connected_lanes;  /* config["neighbour_vehicles_connected_lanes"] (abstract.py:26-37, road.py:509-529) */
     double arrived_reward, reward_speed_lo, reward_speed_hi;
+    /* merge-v0 (envs/merge_env.py): reward_type 2 */
+    double right_lane_reward, merging_speed_reward;
+    int32_t merge_lane; /* table index of ("b", "c", 2), the lane whose slow vehicles are penalised */
+    int32_t _pad3;
 } NetCfg;
 
 /* route entry: from | to << 8 | (lane_id + 1) << 16   (lane_id + 1 == 0: None) */

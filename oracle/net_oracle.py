@@ -49,7 +49,9 @@ class NetCfg(C.Structure):
             "perception_distance")]
         + [(k, C.c_int32) for k in ("regulated", "action_mode", "reward_type", "obs_features", "offroad_terminal",
                                     "connected_lanes")]
-        + [(k, C.c_double) for k in ("arrived_reward", "reward_speed_lo", "reward_speed_hi")]
+        + [(k, C.c_double) for k in ("arrived_reward", "reward_speed_lo", "reward_speed_hi", "right_lane_reward",
+                                     "merging_speed_reward")]
+        + [("merge_lane", C.c_int32), ("_pad3", C.c_int32)]
     )
 
 
@@ -171,11 +173,14 @@ def cfg_from_dict(config: dict, n_vehicles: int = 5) -> NetCfg:
         assert feats[:5] == ["presence", "x", "y", "vx", "vy"] and feats[5:] in ([], ["cos_h", "sin_h"]), feats
         c.obs_features = len(feats)
         fr = obs.get("features_range")
-        assert fr is not None, "roundabout gives explicit features_range"
+        if fr is None:  # observation.py:214-226, computed once at the first observe: ego on ("a","b",1), 2 side lanes
+            assert "_default_side_lanes" in config, "no features_range: the fixture records the side-lane count"
+            w = 4.0 * int(config["_default_side_lanes"])
+            fr = {"x": [-200.0, 200.0], "y": [-w, w], "vx": [-80.0, 80.0], "vy": [-80.0, 80.0]}
         (c.obs_x_lo, c.obs_x_hi), (c.obs_y_lo, c.obs_y_hi) = map(lambda r: map(float, r), (fr["x"], fr["y"]))
         (c.obs_vx_lo, c.obs_vx_hi), (c.obs_vy_lo, c.obs_vy_hi) = map(lambda r: map(float, r), (fr["vx"], fr["vy"]))
-    c.normalize_reward = int(bool(config["normalize_reward"]))
-    c.duration = float(config["duration"])
+    c.normalize_reward = int(bool(config.get("normalize_reward", False)))  # merge-v0 has no such key
+    c.duration = float(config.get("duration", float("inf")))  # AbstractEnv has no duration; merge never truncates
     c.collision_reward = float(config["collision_reward"])
     c.high_speed_reward = float(config["high_speed_reward"])
     c.lane_change_reward = float(config.get("lane_change_reward", 0))
@@ -188,6 +193,12 @@ def cfg_from_dict(config: dict, n_vehicles: int = 5) -> NetCfg:
         c.arrived_reward = float(config["arrived_reward"])
         c.reward_speed_lo, c.reward_speed_hi = (float(v) for v in config["reward_speed_range"])
         c.offroad_terminal = int(bool(config["offroad_terminal"]))
+    if "merging_speed_reward" in config:  # merge-v0 (envs/merge_env.py:24-37)
+        c.reward_type = 2
+        c.right_lane_reward = float(config["right_lane_reward"])
+        c.merging_speed_reward = float(config["merging_speed_reward"])
+        c.reward_speed_lo, c.reward_speed_hi = (float(v) for v in config["reward_speed_range"])
+        c.merge_lane = int(config["_merge_lane"])
     c.connected_lanes = int(bool(config.get("neighbour_vehicles_connected_lanes", False)))
     c.politeness, c.lane_change_min_acc_gain = 0.0, 0.2
     c.lane_change_max_braking_imposed, c.lane_change_delay = 2.0, 1.0

@@ -55,6 +55,8 @@ ENV_CLASSES = {
     "roundabout-v1": ("highway_env.envs.roundabout_env", "ConnectedLaneRoundaboutEnv"),
     "intersection-v2": ("highway_env.envs.intersection_env", "ConnectedLaneIntersectionEnv"),
     "intersection-multi-agent-v0": ("highway_env.envs.intersection_env", "MultiAgentIntersectionEnv"),
+    "merge-v0": ("highway_env.envs.merge_env", "MergeEnv"),
+    "merge-v1": ("highway_env.envs.merge_env", "ConnectedLaneMergeEnv"),
 }
 
 
@@ -158,7 +160,8 @@ def dump_state(env, pad: int = 0) -> dict:
       crashed (bool); impact (f64[2], NaN when ``None``); speed_index (ego MDPVehicle).
     """
     idx_of = {li: k for k, (li, _) in enumerate(lane_list(env))}
-    vs = env.road.vehicles
+    objects = [o for o in getattr(env.road, "objects", [])]
+    vs = list(env.road.vehicles) + objects  # road.objects (Obstacles) occupy the slots after the vehicles
     n = len(vs)
     d = {
         "x": np.array([v.position[0] for v in vs], dtype=np.float64),
@@ -201,6 +204,11 @@ def dump_state(env, pad: int = 0) -> dict:
         d["road_steps"] = np.int64(env.road.steps)
         d["is_yielding"] = np.array([bool(getattr(v, "is_yielding", False)) for v in vs], dtype=np.bool_)
         d["kind"] = np.array([1 if v in env.controlled_vehicles else 0 for v in vs], dtype=np.int32)
+    if objects and "kind" not in d:
+        d["kind"] = np.array([3 if v in objects else (1 if v in env.controlled_vehicles else 0) for v in vs], dtype=np.int32)
+        d["is_yielding"] = np.zeros(n, dtype=np.bool_)
+        d["road_steps"] = np.int64(0)
+        d["count"] = np.int32(n)
     if pad:
         assert n <= pad, n
         d["count"] = np.int32(n)
@@ -213,7 +221,8 @@ def dump_state(env, pad: int = 0) -> dict:
     return d
 
 
-def rollout(env_id: str, config: dict | None, seed: int, actions, record_substeps: bool = False, pad: int = 0):
+def rollout(env_id: str, config: dict | None, seed: int, actions, record_substeps: bool = False, pad: int = 0,
+            mutate=None):
     """Reset with ``seed`` and apply ``actions``; returns dict of stacked arrays.
 
     Stepping continues after termination (the reference allows it), so trajectories have
@@ -221,6 +230,9 @@ def rollout(env_id: str, config: dict | None, seed: int, actions, record_substep
     """
     env = make_reference_env(env_id, config)
     obs0, _ = env.reset(seed=seed)
+    if mutate is not None:  # scripted edit of the reset state (to reach rare events within a short fixture)
+        mutate(env)
+        obs0 = env.observation_type.observe()
     states = [dump_state(env, pad)]
     rng_states = [env.np_random.bit_generator.state]
     obs, rew, term, trunc = [np.asarray(obs0)], [], [], []

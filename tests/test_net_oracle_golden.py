@@ -174,3 +174,51 @@ def test_intersection_multi_agent_reset_and_teacher_forced():
             assert np.max(np.abs(ob.agents_reward[i] - g["agents_rewards"][i, t])) <= 1e-9, ctx
             assert np.array_equal(ob.agents_terminated[i].astype(bool), g["agents_terminated"][i, t]), ctx
             assert np.array_equal(ob.rng_words(i), g["rng_words"][i, t + 1]), ctx
+
+
+# ------------------------------------------------------------------ merge-v0 (road objects, sine ramp)
+MERGE = ["merge_kin", "merge_v1_kin", "merge_obstacle_hit"]
+
+
+def merge_state(g, i, t):
+    """golden state with the Obstacle in the slot after the vehicles (kind 3)"""
+    st = golden_state(g, i, t)
+    V = len(st["x"])
+    st["target_lane"] = np.where(st["target_lane"] < 0, st["lane"], st["target_lane"])
+    st["route"], st["route_len"] = np.zeros((V, no.NET_MAX_ROUTE), dtype=np.int32), np.zeros(V, dtype=np.int32)
+    st["kind"], st["count"] = g["kind"][i, t], V
+    # RoadObject.__init__ gives objects impact = zeros (objects.py:66); it is inert (objects never step)
+    st["impact"] = np.where((st["kind"] == 3)[:, None], np.nan, st["impact"])
+    st["is_yielding"], st["road_steps"] = np.zeros(V, dtype=np.int32), 0
+    return st
+
+
+@pytest.mark.parametrize("name", MERGE)
+def test_merge_teacher_forced(name):
+    """merge-v0 / merge-v1: IDM traffic + a merging vehicle on the sine ramp, an Obstacle at the ramp's end
+    (neighbour search, IDM, collisions with the full impact, Kinematics rows), merge reward, x > 370 termination."""
+    g = load_golden(name)
+    graph = no.graph_from_arrays(g)
+    V = g["x"].shape[2]
+    assert V == 6 and list(g["kind"][0, 0]) == [1, 0, 0, 0, 0, 3]
+    cfg = no.cfg_from_dict(g["config"], n_vehicles=V)
+    S, T = g["actions"].shape[:2]
+    ob = no.NetOracleBatch(graph, cfg, S)
+    for i in range(S):
+        ob.load_state(i, merge_state(g, i, 0))
+    obs0 = ob.observe().reshape(g["obs"][:, 0].shape)
+    assert np.max(np.abs(obs0 - g["obs"][:, 0])) <= 1e-6
+    worst, crashes = 0.0, 0
+    for t in range(T):
+        for i in range(S):
+            ob.load_state(i, merge_state(g, i, t))
+        obs, rew, term, trunc = ob.step(g["actions"][:, t])
+        for i in range(S):
+            ctx = f"{name} seed#{i} t={t}"
+            st1 = merge_state(g, i, t + 1)
+            worst = max(worst, compare_state(st1, got_state(ob, i), ctx=ctx))
+            assert abs(rew[i] - g["reward"][i, t]) <= 1e-9, ctx
+            assert bool(term[i]) == bool(g["terminated"][i, t]) and not trunc[i] and not g["truncated"][i, t], ctx
+            assert np.max(np.abs(obs[i].reshape(g["obs"][i, t + 1].shape) - g["obs"][i, t + 1])) <= 1e-6, ctx
+            crashes += int(st1["crashed"].any())
+    assert worst < 1e-9
