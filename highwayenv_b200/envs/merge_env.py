@@ -57,6 +57,8 @@ class BatchedMergeEnv(BatchedRoundaboutEnv):
         return make_merge_network()
 
     def define_spaces(self) -> None:
+        if self.reset_mode != "device":
+            raise NotImplementedError("merge envs reset on the device (hwy_merge_reset)")
         cfg = self.config
         obs = dict(cfg["observation"])
         if obs["type"] != "Kinematics":

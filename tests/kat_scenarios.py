@@ -120,3 +120,13 @@ def diamond_network():
     net.add_straight("3", "0", [5, -5], [0, 0])
     net.finalize()
     return net
+
+
+def single_lane_road():
+    """RoadNetwork.straight_road_network(lanes=1) (road/road.py:291-321): one 10 km lane "0" -> "1\""""
+    from highwayenv_b200.road.network import NetworkTable
+
+    net = NetworkTable()
+    net.add_straight("0", "1", [0, 0], [10000, 0], speed_limit=30.0)
+    net.finalize()
+    return net

@@ -232,3 +232,54 @@ def test_env_step_until_done(env_id):
         if done.all():
             break
     assert done.all(), "every episode ends by the time limit"
+
+
+def _single_lane_device(x, speed, kinds):
+    """vehicles / objects on RoadNetwork.straight_road_network(1), as raw device state for hwy_network_substeps"""
+    from highwayenv_b200 import _native as N
+
+    net = K.single_lane_road()
+    n, vp, dev, V = 2, 8, "cuda", len(x)
+    graph = torch.from_numpy(np.frombuffer(bytes(net.to_struct()), dtype=np.uint8).copy()).to(dev)
+    z = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, device=dev)  # noqa: E731
+    t = {k: z(n, vp, 2, dtype=torch.float64) for k in ("pos", "hs", "tt", "imp")}
+    t["pos"][:, :V, 0] = torch.tensor(x, dtype=torch.float64, device=dev)
+    t["hs"][:, :V, 1] = torch.tensor(speed, dtype=torch.float64, device=dev)
+    t["tt"][:, :V, 0] = torch.tensor(speed, dtype=torch.float64, device=dev)
+    t["delta"] = torch.full((n, vp), 4.0, dtype=torch.float64, device=dev)
+    t["meta"] = z(n, vp, dtype=torch.int32)
+    t["meta"][:, :V] = torch.tensor([(k << N.META_KIND_SHIFT) | N.META_PRESENT | N.META_CHECK_COLLISIONS for k in kinds],
+                                    dtype=torch.int32, device=dev)
+    t["route"], t["route_len"] = z(n, vp, N.HWY_NET_MAX_ROUTE, dtype=torch.int32), z(n, vp, dtype=torch.int32)
+    t["speed_index"], t["time"] = z(n, dtype=torch.int32), z(n, dtype=torch.float64)
+    st = N.HwyNetState()
+    st.n_envs, st.vp = n, vp
+    for k in ("pos", "hs", "tt", "imp", "delta", "meta", "route", "route_len", "speed_index", "time"):
+        setattr(st, k, t[k].data_ptr())
+    p = N.HwyNetParams()
+    p.n_vehicles, p.simulation_frequency, p.policy_frequency, p.n_target_speeds = V, 15, 1, 3
+    p.obs_vehicles_count, p.obs_features = 5, 5
+    p.acc_max, p.comfort_acc_max, p.comfort_acc_min = 6.0, 3.0, -5.0
+    p.distance_wanted, p.time_wanted, p.lane_change_delay = 10.0, 1.5, 1.0
+    p.lane_change_min_acc_gain, p.lane_change_max_braking_imposed = 0.2, 2.0
+    return N, p, graph, st, t
+
+
+def test_behavior_stop_before_obstacle():
+    """vehicle/test_behavior.py:13-27 on the device"""
+    N, p, graph, st, t = _single_lane_device([0.0, 80.0], [20.0, 0.0], [0, 3])
+    N.check(N.load().hwy_network_substeps(C.byref(p), graph.data_ptr(), C.byref(st), None, 10 * K.FPS, None))
+    torch.cuda.synchronize()
+    x, y = float(t["pos"][1, 0, 0]), float(t["pos"][1, 0, 1])
+    assert not (int(t["meta"][1, 0]) & N.META_CRASHED)
+    assert x == pytest.approx(70.0, abs=1) and y == pytest.approx(0)
+    assert float(t["hs"][1, 0, 1]) == pytest.approx(0, abs=1) and float(t["hs"][1, 0, 0]) == pytest.approx(0)
+    assert float(t["pos"][1, 1, 0]) == 80.0  # the object never moves
+
+
+def test_dynamics_collision_with_obstacle():
+    """vehicle/test_dynamics.py:56-60 on the device"""
+    N, p, graph, st, t = _single_lane_device([20.0, 23.0], [10.0, 0.0], [0, 3])
+    N.check(N.load().hwy_network_substeps(C.byref(p), graph.data_ptr(), C.byref(st), None, 1, None))
+    torch.cuda.synchronize()
+    assert int(t["meta"][1, 0]) & N.META_CRASHED and int(t["meta"][1, 1]) & N.META_CRASHED

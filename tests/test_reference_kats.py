@@ -154,3 +154,41 @@ def test_road_network_follow_road():
         if int(a["target_lane"][0, 0]) != lane:
             lane, changes = int(a["target_lane"][0, 0]), changes + 1
     assert changes >= 3
+
+
+def _single_lane_oracle(n_slots):
+    net = K.single_lane_road()
+    graph = no.graph_from_arrays(net.export_arrays())
+    cfg = no.NetCfg()
+    cfg.n_vehicles, cfg.simulation_frequency, cfg.policy_frequency = n_slots, 15, 1
+    cfg.acc_max, cfg.comfort_acc_max, cfg.comfort_acc_min = 6.0, 3.0, -5.0  # IDMVehicle class constants
+    cfg.distance_wanted, cfg.time_wanted, cfg.lane_change_delay = 10.0, 1.5, 1.0
+    cfg.lane_change_min_acc_gain, cfg.lane_change_max_braking_imposed = 0.2, 2.0
+    return graph, cfg, no.NetOracleBatch(graph, cfg, 1)
+
+
+def test_behavior_stop_before_obstacle():
+    """vehicle/test_behavior.py:13-27 (IDMVehicle): a vehicle at 20 m/s stops DISTANCE_WANTED before an Obstacle
+    80 m ahead, without crashing"""
+    graph, cfg, ob = _single_lane_oracle(2)
+    a = ob.a
+    a["speed"][0, 0], a["target_speed"][0, 0], a["delta"][0, 0] = 20.0, 20.0, 4.0
+    a["x"][0, 1], a["kind"][0, 1] = 80.0, 3
+    a["check_collisions"][0] = 1
+    st = ob._state(0)
+    no.lib().net_substeps(C.byref(graph), C.byref(cfg), C.byref(st), 10 * K.FPS)
+    assert not a["crashed"][0, 0]
+    assert a["x"][0, 0] == pytest.approx(80.0 - 10.0, abs=1) and a["y"][0, 0] == pytest.approx(0)
+    assert a["speed"][0, 0] == pytest.approx(0, abs=1) and a["heading"][0, 0] == pytest.approx(0)
+
+
+def test_dynamics_collision_with_obstacle():
+    """vehicle/test_dynamics.py:56-60: a vehicle at [20, 0] and an Obstacle at [23, 0] -> both crashed"""
+    graph, cfg, ob = _single_lane_oracle(2)
+    a = ob.a
+    a["x"][0, 0], a["speed"][0, 0], a["target_speed"][0, 0], a["delta"][0, 0] = 20.0, 10.0, 10.0, 4.0
+    a["x"][0, 1], a["kind"][0, 1] = 23.0, 3
+    a["check_collisions"][0] = 1
+    st = ob._state(0)
+    no.lib().net_substeps(C.byref(graph), C.byref(cfg), C.byref(st), 1)
+    assert a["crashed"][0, 0] and a["crashed"][0, 1]
