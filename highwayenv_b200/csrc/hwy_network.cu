@@ -268,6 +268,32 @@ __device__ __noinline__ void neighbours(const GraphShared& g, const EnvStage<G, 
     constexpr int kMaxSearch = 16;
     const HwyNetLane& L = g.lanes[lane_idx];
     const double s = lane_idx == st.lane[veh] ? st.own_s[veh] : lane_s_of(L, st.x[veh], st.y[veh]);
+    if (!connected) {  // same-segment search: one lane, no list
+        const double gate = L.width / 2 + 1.0;  // the lateral half of on_lane(margin=1)
+        double s_front = 0, s_rear = 0;
+        front = -1;
+        rear = -1;
+        for (int v = 0; v < V; ++v) {
+            if (v == veh) continue;
+            double s_v, lat_v;
+            if (st.lane[v] == lane_idx) {
+                s_v = st.own_s[v];
+                lat_v = st.own_lat[v];
+            } else if (!lane_local_gated(L, st.x[v], st.y[v], gate, s_v, lat_v)) {
+                continue;
+            }
+            if (!lane_on(L, s_v, lat_v, 1.0)) continue;
+            if (s <= s_v && (front < 0 || s_v <= s_front)) {
+                s_front = s_v;
+                front = v;
+            }
+            if (s_v < s && (rear < 0 || s_v > s_rear)) {
+                s_rear = s_v;
+                rear = v;
+            }
+        }
+        return;
+    }
     unsigned char lanes[kMaxSearch];
     int n_l = 1;
     lanes[0] = (unsigned char)lane_idx;
@@ -1127,8 +1153,9 @@ __device__ __forceinline__ void substep(const HwyNetParams& P, const GraphShared
             if (st.kind[a] == HWY_KIND_OBSTACLE) continue;
             const bool b_object = st.kind[b] == HWY_KIND_OBSTACLE;
             const double len_b = b_object ? 2.0 : kVehLength;
-            const double diag_a = sqrt(kVehLength * kVehLength + kVehWidth * kVehWidth);
-            const double diag_b = sqrt(len_b * len_b + kVehWidth * kVehWidth);
+            // RoadObject.diagonal = sqrt(LENGTH^2 + WIDTH^2) (objects.py:63): sqrt(29) and sqrt(8), correctly rounded
+            const double diag_a = 0x1.58a68a4a8d9f3p+2;
+            const double diag_b = b_object ? 0x1.6a09e667f3bcdp+1 : 0x1.58a68a4a8d9f3p+2;
             double dist = norm2(st.x[b] - st.x[a], st.y[b] - st.y[a]);
             if (dist > (diag_a + diag_b) / 2 + st.v[a] * dt) continue;
             Quad pa = make_polygon(st.x[a], st.y[a], st.c[a], st.s[a]);
