@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("HWYB200_LIB") or os.path.join(_HERE, "csrc", "libhwyb200.so")
 
-HWY_ABI_VERSION = 3  # bump with every change of a struct or signature: a stale libhwyb200.so then fails to load
+HWY_ABI_VERSION = 4  # bump with every change of a struct or signature: a stale libhwyb200.so then fails to load
 HWY_MAX_LANES = 8
 HWY_MAX_TARGET_SPEEDS = 8
 HWY_MAX_VEHICLES = 128
@@ -111,7 +111,7 @@ class HwyNetParams(C.Structure):
                                     "dynamic_population", "connected_lanes", "n_agents")]
         + [(n, C.c_double) for n in ("arrived_reward", "reward_speed_lo", "reward_speed_hi", "right_lane_reward",
                                      "merging_speed_reward")]
-        + [("merge_lane", C.c_int32), ("_pad_merge", C.c_int32)]
+        + [("merge_lane", C.c_int32), ("_pad_merge", C.c_int32), ("left_lane_reward", C.c_double)]
     )
 
 
@@ -138,6 +138,11 @@ class HwyMergeSpawn(C.Structure):
 
 
 KIND_OBSTACLE = 3
+META_NO_LANE_CHANGE = 1 << 23
+
+
+class HwyTwoWaySpawn(C.Structure):
+    _fields_ = [("lane_ab1", C.c_int32), ("lane_ba0", C.c_int32), ("ego_speed_index", C.c_int32), ("_pad", C.c_int32)]
 
 
 class HwyRoundaboutSpawn(C.Structure):
@@ -158,6 +163,7 @@ EXPORTS = (
     "hwy_network_obs_size", "hwy_network_step", "hwy_network_observe", "hwy_roundabout_reset",
     "hwy_intersection_step", "hwy_network_substeps", "hwy_intersection_reset", "hwy_intersection_step_agents",
     "hwy_debug_network_neighbours", "hwy_debug_rotated_rectangles_intersect", "hwy_merge_reset",
+    "hwy_two_way_reset",
 )
 
 _lib = None
@@ -207,6 +213,9 @@ def load():
     lib.hwy_debug_network_neighbours.argtypes = [NP, NG, NS, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.hwy_debug_rotated_rectangles_intersect.restype = C.c_int
     lib.hwy_debug_rotated_rectangles_intersect.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.hwy_two_way_reset.restype = C.c_int
+    lib.hwy_two_way_reset.argtypes = [NP, NG, C.POINTER(HwyTwoWaySpawn), NS, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p]
     lib.hwy_merge_reset.restype = C.c_int
     lib.hwy_merge_reset.argtypes = [NP, NG, C.POINTER(HwyMergeSpawn), NS, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p]

@@ -227,3 +227,20 @@ def merge_default_config() -> dict:
 
 DEFAULTS["merge-v0"] = merge_default_config
 DEFAULTS["merge-v1"] = _connected(merge_default_config)
+
+
+def two_way_default_config() -> dict:
+    """TwoWayEnv.default_config (highway_env/envs/two_way_env.py:17-33) over AbstractEnv's."""
+    config = abstract_default_config()
+    update_config(config, {
+        "observation": {"type": "TimeToCollision", "horizon": 5},
+        "action": {"type": "DiscreteMetaAction"},
+        "collision_reward": 0,
+        "left_lane_constraint": 1,
+        "left_lane_reward": 0.2,
+        "high_speed_reward": 0.8,
+    })
+    return config
+
+
+DEFAULTS["two-way-v0"] = two_way_default_config

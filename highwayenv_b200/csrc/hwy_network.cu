@@ -1064,7 +1064,8 @@ __device__ __forceinline__ void substep(const HwyNetParams& P, const GraphShared
         // road.objects neither act nor step (road/road.py:464-476)
         if (kind != HWY_KIND_OBSTACLE && (kind != HWY_KIND_IDM || !crashed))
             follow_road(g, st, i);  // behavior.py:102-103, controller.py:98
-        if (kind == HWY_KIND_IDM && !crashed) {
+        // IDMVehicle(enable_lane_change=False) never runs change_lane_policy (behavior.py:104-105)
+        if (kind == HWY_KIND_IDM && !crashed && !(r.meta & HWY_META_NO_LANE_CHANGE)) {
             const int lane = st.lane[i], tgt = st.tgt[i];
             const HwyNetLane &A = g.lanes[lane], &B = g.lanes[tgt];
             if (lane != tgt) {
@@ -1440,6 +1441,13 @@ network_step_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGraph* _
             rew = lmap(rew, P.collision_reward + P.merging_speed_reward, P.high_speed_reward + P.right_lane_reward, 0.0,
                        1.0);
             term = is_crashed || r.x > 370;
+        } else if (P.reward_type == 3) {
+            // envs/two_way_env.py:35-62: speed index and how far left the TARGET lane is; never truncated
+            const int n_side = L.road_count;  // all_side_lanes(vehicle.lane_index)
+            rew = rew + P.high_speed_reward * ((double)st.speed_index / (double)(P.n_target_speeds - 1));
+            rew = rew + P.left_lane_reward *
+                            ((double)(n_side - 1 - g.lanes[st.tgt[i]].lane_id) / (double)(n_side - 1));
+            term = is_crashed;
         } else {
             // envs/roundabout_env.py:44-71
             rew = rew + P.collision_reward * (is_crashed ? 1.0 : 0.0);
@@ -1881,6 +1889,71 @@ merge_reset_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGraph* __
     store_rng(rng, (size_t)S.n_envs, e, g);
 }
 
+// TwoWayEnv._make_vehicles (envs/two_way_env.py:113-158), one env per thread
+__global__ void __launch_bounds__(128)
+two_way_reset_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGraph* __restrict__ graph,
+                     const __grid_constant__ HwyTwoWaySpawn SP, const __grid_constant__ HwyNetState S,
+                     uint64_t* __restrict__ rng, const uint8_t* __restrict__ mask_a, const uint8_t* __restrict__ mask_b) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= S.n_envs) return;
+    if ((mask_a || mask_b) && !((mask_a && mask_a[e]) || (mask_b && mask_b[e]))) return;
+    Pcg64 g = load_rng(rng, (size_t)S.n_envs, e);
+    double2* pos = reinterpret_cast<double2*>(S.pos);
+    double2* hs = reinterpret_cast<double2*>(S.hs);
+    double2* tt = reinterpret_cast<double2*>(S.tt);
+    double2* imp = reinterpret_cast<double2*>(S.imp);
+    const size_t base = (size_t)e * S.vp;
+    for (int v = 0; v < 6; ++v) {
+        double px, py, heading, speed, target_speed, timer = 0.0;
+        int kind = HWY_KIND_IDM, flags = HWY_META_NO_LANE_CHANGE;
+        if (v == 0) {  // :120-123 ego on ("a","b",1) at s = 30, speed 30
+            const HwyNetLane& L = graph->lanes[SP.lane_ab1];
+            lane_position(L, 30.0, 0.0, px, py);
+            heading = 0.0;
+            speed = 30.0;
+            kind = HWY_KIND_MDP;
+            flags = 0;
+            target_speed = P.target_speeds[SP.ego_speed_index];
+        } else if (v <= 3) {  // :126-144 three vehicles ahead on the same lane
+            const HwyNetLane& L = graph->lanes[SP.lane_ab1];
+            const double i = (double)(v - 1);
+            lane_position(L, 70.0 + 40.0 * i + 10.0 * g.normal(), 0.0, px, py);
+            heading = lane_heading_at(L, 70.0 + 40.0 * i);
+            speed = 24.0 + 2.0 * g.normal();
+            target_speed = speed;
+        } else {  // :145-158 two oncoming vehicles on ("b","a",0)
+            const HwyNetLane& L = graph->lanes[SP.lane_ba0];
+            const double i = (double)(v - 4);
+            lane_position(L, 200.0 + 100.0 * i + 10.0 * g.normal(), 0.0, px, py);
+            heading = lane_heading_at(L, 200.0 + 100.0 * i);
+            speed = 20.0 + 5.0 * g.normal();
+            target_speed = speed;
+        }
+        int lane = 0;  // RoadObject.__init__: closest lane (objects.py:46-50)
+        double bd = 0;
+        for (int l = 0; l < graph->n_lanes; ++l) {
+            double d = lane_distance_with_heading(graph->lanes[l], px, py, heading);
+            if (l == 0 || d < bd) {
+                bd = d;
+                lane = l;
+            }
+        }
+        const int target = v >= 4 ? SP.lane_ba0 : lane;  // :157 v.target_lane_index = ("b", "a", 0)
+        if (kind == HWY_KIND_IDM) timer = py_mod_pos((px + py) * kPi, P.lane_change_delay);  // behavior.py:64
+        pos[base + v] = make_double2(px, py);
+        hs[base + v] = make_double2(heading, speed);
+        tt[base + v] = make_double2(target_speed, timer);
+        imp[base + v] = make_double2(0.0, 0.0);
+        S.delta[base + v] = 4.0;
+        S.meta[base + v] = (lane << HWY_META_LANE_SHIFT) | (target << HWY_META_TARGET_SHIFT) | HWY_META_CHECK_COLLISIONS |
+                           (kind << HWY_META_KIND_SHIFT) | HWY_META_PRESENT | flags;
+        S.route_len[base + v] = 0;
+    }
+    S.speed_index[e] = SP.ego_speed_index;
+    S.time[e] = 0.0;
+    store_rng(rng, (size_t)S.n_envs, e, g);
+}
+
 }  // namespace hwynet
 
 // ====================================================================== C ABI
@@ -2089,6 +2162,18 @@ int hwy_merge_reset(const HwyNetParams* p, const HwyNetGraph* graph, const HwyMe
     cudaStream_t st = (cudaStream_t)stream;
     hwynet::merge_reset_kernel<<<(s->n_envs + 127) / 128, 128, 0, st>>>(*p, graph, *spawn, *s, rng, mask_a, mask_b);
     if (check_launch("merge_reset_kernel")) return 1;
+    if (obs) return observe_dispatch(p, graph, s, mask_a, mask_b, obs, st);
+    return 0;
+}
+
+int hwy_two_way_reset(const HwyNetParams* p, const HwyNetGraph* graph, const HwyTwoWaySpawn* spawn, const HwyNetState* s,
+                      uint64_t* rng, const uint8_t* mask_a, const uint8_t* mask_b, float* obs, void* stream) {
+    if (validate_net(p, graph, s)) return 1;
+    if (!spawn || !rng) return fail("%s", "null spawn / rng");
+    if (s->vp != HWY_NET_GROUP || p->n_vehicles != 6) return fail("%s", "two-way-v0: 6 vehicles on 8 slots");
+    cudaStream_t st = (cudaStream_t)stream;
+    hwynet::two_way_reset_kernel<<<(s->n_envs + 127) / 128, 128, 0, st>>>(*p, graph, *spawn, *s, rng, mask_a, mask_b);
+    if (check_launch("two_way_reset_kernel")) return 1;
     if (obs) return observe_dispatch(p, graph, s, mask_a, mask_b, obs, st);
     return 0;
 }

@@ -463,6 +463,7 @@ class BatchedRoundaboutEnv:
             "delta": self._delta[:, :V].cpu().numpy(), "impact_x": imp[..., 0].copy(), "impact_y": imp[..., 1].copy(),
             "lane": (meta >> N.META_LANE_SHIFT) & 0xFF, "target_lane": (meta >> N.META_TARGET_SHIFT) & 0xFF,
             "kind": (meta >> N.META_KIND_SHIFT) & 3, "crashed": (meta & N.META_CRASHED) != 0,
+            "no_lane_change": (meta & N.META_NO_LANE_CHANGE) != 0,
             "has_impact": (meta & N.META_HAS_IMPACT) != 0, "check_collisions": (meta & N.META_CHECK_COLLISIONS) != 0,
             "route": self._route[:, :V].cpu().numpy(), "route_len": self._route_len[:, :V].cpu().numpy(),
             "speed_index": self._speed_index.cpu().numpy(), "time": self._time.cpu().numpy(),
@@ -482,6 +483,8 @@ class BatchedRoundaboutEnv:
                 | np.where(np.asarray(sd["crashed"], dtype=bool), N.META_CRASHED, 0)
                 | np.where(np.asarray(sd["has_impact"], dtype=bool), N.META_HAS_IMPACT, 0)
                 | np.where(np.asarray(sd["check_collisions"], dtype=bool), N.META_CHECK_COLLISIONS, 0)
+                | (np.where(np.asarray(sd["no_lane_change"], dtype=bool), N.META_NO_LANE_CHANGE, 0)
+                   if "no_lane_change" in sd else 0)
                 | N.META_PRESENT).astype(np.int32)
         self._meta[:, :V] = torch.from_numpy(meta.reshape(n, V)).to(dev)
         self._route[:, :V] = torch.from_numpy(np.ascontiguousarray(sd["route"], dtype=np.int32)).to(dev)

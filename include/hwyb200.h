@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define HWY_ABI_VERSION 3
+#define HWY_ABI_VERSION 4
 #define HWY_MAX_LANES 8
 #define HWY_MAX_TARGET_SPEEDS 8
 #define HWY_MAX_VEHICLES 128 /* per env, incl. the ego */
@@ -202,7 +202,8 @@ int hwy_highway_autoreset(const HwyHighwayParams *p, const HwyHighwayState *s,
 #define HWY_OBS_OCCUPANCY 1 /* envs/common/observation.py:279-499, default 4 x 11 x 11 grid */
 #define HWY_OBS_TTC 2
 
-#define HWY_META_YIELDING (1 << 22) /* RegulatedRoad: vehicle.is_yielding (road/regulation.py:42-83) */
+#define HWY_META_YIELDING (1 << 22)
+#define HWY_META_NO_LANE_CHANGE (1 << 23) /* IDMVehicle(enable_lane_change=False) (vehicle/behavior.py:48-62,104-105) */ /* RegulatedRoad: vehicle.is_yielding (road/regulation.py:42-83) */
 
 /* One lane of RoadNetwork.graph[from][to][lane_id]; table order = graph enumeration order
  * (road/road.py:65-71: from-node insertion order, to-node insertion order, lane id). */
@@ -257,6 +258,7 @@ typedef struct HwyNetParams {
     double right_lane_reward, merging_speed_reward;
     int32_t merge_lane;         /* table index of ("b", "c", 2): slow ControlledVehicles there are penalised */
     int32_t _pad_merge;
+    double left_lane_reward;    /* two-way-v0 (envs/two_way_env.py:17-62): reward_type 3 */
 } HwyNetParams;
 
 /* route entry: from_node | to_node << 8 | (lane_id + 1) << 16  (lane_id + 1 == 0: None) */
@@ -361,6 +363,17 @@ typedef struct HwyMergeSpawn {
 int hwy_merge_reset(const HwyNetParams *p, const HwyNetGraph *graph, const HwyMergeSpawn *spawn,
                     const HwyNetState *s, uint64_t *rng, const uint8_t *mask_a, const uint8_t *mask_b,
                     float *obs, void *stream);
+
+/* TwoWayEnv._make_vehicles (envs/two_way_env.py:113-158) on the device: the MDPVehicle on ("a","b",1) at s = 30,
+ * three IDM vehicles ahead at 70 + 40 i + 10 normal() with speed 24 + 2 normal(), two oncoming ones on ("b","a",0)
+ * at 200 + 100 i + 10 normal() with speed 20 + 5 normal(); all traffic has enable_lane_change=False. */
+typedef struct HwyTwoWaySpawn {
+    int32_t lane_ab1, lane_ba0; /* table indices of ("a","b",1) and ("b","a",0) */
+    int32_t ego_speed_index, _pad;
+} HwyTwoWaySpawn;
+int hwy_two_way_reset(const HwyNetParams *p, const HwyNetGraph *graph, const HwyTwoWaySpawn *spawn,
+                      const HwyNetState *s, uint64_t *rng, const uint8_t *mask_a, const uint8_t *mask_b,
+                      float *obs, void *stream);
 
 /* RoundaboutEnv._make_vehicles (envs/roundabout_env.py:317-391) on the device.  Per traffic
  * vehicle the env's numpy stream yields normal (longitudinal), normal (speed),

@@ -554,7 +554,7 @@ static void idm_act(World *w, int v) {
     NetState *s = w->s;
     if (s->crashed[v]) return;
     follow_road(w, v);
-    change_lane_policy(w, v);
+    if (!(s->no_lane_change && s->no_lane_change[v])) change_lane_policy(w, v); /* behavior.py:104-105 */
     double steering = steering_control(w, v, s->target_lane[v]);
     steering = clipd(steering, -MAX_STEERING_ANGLE, MAX_STEERING_ANGLE);
     int front, rear;
@@ -1024,6 +1024,21 @@ static void reward_done_merge(const World *w, int action, double *reward, int32_
     *truncated = 0;
 }
 
+/* envs/two_way_env.py:35-62 */
+static void reward_done_two_way(const World *w, double *reward, int32_t *terminated, int32_t *truncated) {
+    const NetCfg *c = w->c;
+    const NetState *s = w->s;
+    const int ego = 0;
+    const int n_side = LANE(w, s->lane[ego])->road_count; /* all_side_lanes(vehicle.lane_index) */
+    double r = 0;
+    r = r + c->high_speed_reward * ((double)s->speed_index[0] / (double)(c->n_target_speeds - 1));
+    r = r + c->left_lane_reward *
+                ((double)(n_side - 1 - LANE(w, s->target_lane[ego])->lane_id) / (double)(n_side - 1));
+    *reward = r;
+    *terminated = s->crashed[ego] != 0;
+    *truncated = 0;
+}
+
 /* ------------------------------------------------------------------ road/regulation.py */
 
 /* road/road.py:323-362 position_heading_along_route(route, longitudinal, 0, current_lane_index) */
@@ -1193,6 +1208,8 @@ void net_step(const NetGraph *g, const NetCfg *c, NetState *s, int action, float
         reward_done_intersection(&w, reward, terminated, truncated);
     else if (c->reward_type == 2)
         reward_done_merge(&w, action, reward, terminated, truncated);
+    else if (c->reward_type == 3)
+        reward_done_two_way(&w, reward, terminated, truncated);
     else
         reward_done(&w, action, reward, terminated, truncated);
     free(act_buf);

@@ -82,6 +82,8 @@ typedef struct NetCfg {
     double right_lane_reward, merging_speed_reward;
     int32_t merge_lane; /* table index of ("b", "c", 2), the lane whose slow vehicles are penalised */
     int32_t _pad3;
+    /* two-way-v0 (envs/two_way_env.py): reward_type 3 */
+    double left_lane_reward;
 } NetCfg;
 
 /* route entry: from | to << 8 | (lane_id + 1) << 16   (lane_id + 1 == 0: None) */
@@ -97,6 +99,7 @@ typedef struct NetState {
     int32_t *count;       /* [1] current number of vehicles (dynamic population); NULL: cfg->n_vehicles */
     int32_t *is_yielding; /* [V] RegulatedRoad yield flag */
     int32_t *road_steps;  /* [1] RegulatedRoad.steps */
+    int32_t *no_lane_change; /* [V] IDMVehicle(enable_lane_change=False) (behavior.py:48-62,104-105); NULL: all enabled */
 } NetState;
 
 /* One AbstractEnv.step of a roundabout-v0 style env (MDPVehicle ego in slot 0). */

@@ -51,7 +51,7 @@ class NetCfg(C.Structure):
                                     "connected_lanes")]
         + [(k, C.c_double) for k in ("arrived_reward", "reward_speed_lo", "reward_speed_hi", "right_lane_reward",
                                      "merging_speed_reward")]
-        + [("merge_lane", C.c_int32), ("_pad3", C.c_int32)]
+        + [("merge_lane", C.c_int32), ("_pad3", C.c_int32), ("left_lane_reward", C.c_double)]
     )
 
 
@@ -63,7 +63,7 @@ class NetState(C.Structure):
     _fields_ = ([(k, C.c_void_p) for k in _SF] + [(k, C.c_void_p) for k in _SI]
                 + [("route", C.c_void_p), ("route_len", C.c_void_p), ("speed_index", C.c_void_p),
                    ("time", C.c_void_p), ("count", C.c_void_p), ("is_yielding", C.c_void_p),
-                   ("road_steps", C.c_void_p)])
+                   ("road_steps", C.c_void_p), ("no_lane_change", C.c_void_p)])
 
 
 def build(force: bool = False) -> str:
@@ -199,6 +199,9 @@ def cfg_from_dict(config: dict, n_vehicles: int = 5) -> NetCfg:
         c.merging_speed_reward = float(config["merging_speed_reward"])
         c.reward_speed_lo, c.reward_speed_hi = (float(v) for v in config["reward_speed_range"])
         c.merge_lane = int(config["_merge_lane"])
+    if "left_lane_reward" in config:  # two-way-v0 (envs/two_way_env.py:17-33)
+        c.reward_type = 3
+        c.left_lane_reward = float(config["left_lane_reward"])
     c.connected_lanes = int(bool(config.get("neighbour_vehicles_connected_lanes", False)))
     c.politeness, c.lane_change_min_acc_gain = 0.0, 0.2
     c.lane_change_max_braking_imposed, c.lane_change_delay = 2.0, 1.0
@@ -221,6 +224,7 @@ class NetOracleBatch:
         self.a["count"] = np.full(n, V, dtype=np.int32)
         self.a["is_yielding"] = np.zeros((n, V), dtype=np.int32)
         self.a["road_steps"] = np.zeros(n, dtype=np.int32)
+        self.a["no_lane_change"] = np.zeros((n, V), dtype=np.int32)
         self.obs_size = lib().net_obs_size(C.byref(cfg))
         self.obs = np.zeros((n, self.obs_size), dtype=np.float32)
         self.reward = np.zeros(n, dtype=np.float64)
@@ -235,6 +239,7 @@ class NetOracleBatch:
         st.time = self.a["time"][e:e + 1].ctypes.data
         st.count = self.a["count"][e:e + 1].ctypes.data
         st.road_steps = self.a["road_steps"][e:e + 1].ctypes.data
+        st.no_lane_change = self.a["no_lane_change"][e].ctypes.data
         return st
 
     def observe(self):
@@ -273,6 +278,7 @@ class NetOracleBatch:
             kind = np.full(self.V, KIND_IDM, dtype=np.int32)
             kind[0] = KIND_MDP
             self.a["kind"][e] = kind
+        self.a["no_lane_change"][e] = st["no_lane_change"] if "no_lane_change" in st else 0
         self.a["route"][e], self.a["route_len"][e] = st["route"], st["route_len"]
         if self.a["speed_index"].ndim == 2:  # one entry per controlled vehicle, in list order
             si = np.asarray(st["speed_index"])[np.asarray(st["kind"]) == KIND_MDP]

@@ -55,6 +55,7 @@ ENV_CLASSES = {
     "roundabout-v1": ("highway_env.envs.roundabout_env", "ConnectedLaneRoundaboutEnv"),
     "intersection-v2": ("highway_env.envs.intersection_env", "ConnectedLaneIntersectionEnv"),
     "intersection-multi-agent-v0": ("highway_env.envs.intersection_env", "MultiAgentIntersectionEnv"),
+    "two-way-v0": ("highway_env.envs.two_way_env", "TwoWayEnv"),
     "merge-v0": ("highway_env.envs.merge_env", "MergeEnv"),
     "merge-v1": ("highway_env.envs.merge_env", "ConnectedLaneMergeEnv"),
 }
@@ -196,6 +197,8 @@ def dump_state(env, pad: int = 0) -> dict:
         "time": np.float64(env.time),
         "steps": np.int64(env.steps),
     }
+    if any(getattr(v, "enable_lane_change", True) is False for v in vs):  # IDMVehicle(enable_lane_change=False)
+        d["no_lane_change"] = np.array([getattr(v, "enable_lane_change", True) is False for v in vs], dtype=np.int32)
     if any(getattr(v, "route", None) for v in vs):
         enc = [encode_route(env, v) for v in vs]
         d["route"] = np.stack([e[0] for e in enc])

@@ -222,3 +222,44 @@ def test_merge_teacher_forced(name):
             assert np.max(np.abs(obs[i].reshape(g["obs"][i, t + 1].shape) - g["obs"][i, t + 1])) <= 1e-6, ctx
             crashes += int(st1["crashed"].any())
     assert worst < 1e-9
+
+
+# ------------------------------------------------------------------ two-way-v0 (oncoming lane, no lane changes)
+def two_way_state(g, i, t):
+    st = golden_state(g, i, t)
+    V = len(st["x"])
+    st["target_lane"] = np.where(st["target_lane"] < 0, st["lane"], st["target_lane"])
+    st["route"], st["route_len"] = np.zeros((V, no.NET_MAX_ROUTE), dtype=np.int32), np.zeros(V, dtype=np.int32)
+    st["kind"] = np.array([1] + [0] * (V - 1), dtype=np.int32)
+    st["count"], st["is_yielding"], st["road_steps"] = V, np.zeros(V, dtype=np.int32), 0
+    st["no_lane_change"] = g["no_lane_change"][i, t]
+    return st
+
+
+def test_two_way_teacher_forced():
+    """two-way-v0: IDMVehicle(enable_lane_change=False) traffic incl. two oncoming vehicles on ("b","a",0),
+    TimeToCollision horizon 5, reward = 0.8 speed_index / 2 + 0.2 (1 - target lane id), never truncated"""
+    name = "two_way_ttc"
+    g = load_golden(name)
+    graph = no.graph_from_arrays(g)
+    V = g["x"].shape[2]
+    cfg = no.cfg_from_dict(g["config"], n_vehicles=V)
+    assert cfg.reward_type == 3 and cfg.obs_type == no.OBS_TTC
+    S, T = g["actions"].shape[:2]
+    ob = no.NetOracleBatch(graph, cfg, S)
+    for i in range(S):
+        ob.load_state(i, two_way_state(g, i, 0))
+    obs0 = ob.observe().reshape(g["obs"][:, 0].shape)
+    assert np.max(np.abs(obs0 - g["obs"][:, 0])) <= 1e-6
+    worst = 0.0
+    for t in range(T):
+        for i in range(S):
+            ob.load_state(i, two_way_state(g, i, t))
+        obs, rew, term, trunc = ob.step(g["actions"][:, t])
+        for i in range(S):
+            ctx = f"{name} seed#{i} t={t}"
+            worst = max(worst, compare_state(two_way_state(g, i, t + 1), got_state(ob, i), ctx=ctx))
+            assert abs(rew[i] - g["reward"][i, t]) <= 1e-9, ctx
+            assert bool(term[i]) == bool(g["terminated"][i, t]) and not trunc[i] and not g["truncated"][i, t], ctx
+            assert np.max(np.abs(obs[i].reshape(g["obs"][i, t + 1].shape) - g["obs"][i, t + 1])) <= 1e-6, ctx
+    assert worst < 1e-9
