@@ -28,6 +28,7 @@ CONFIGS = [
      {"observation": {"type": "TimeToCollision", "horizon": 10}}, 8192, "SameStep", "discrete"),
     ("roundabout-v0 defaults (Kinematics)", "roundabout-v0", None, 8192, "SameStep", "discrete"),
     ("merge-v0 defaults (Kinematics, 5 vehicles + obstacle)", "merge-v0", None, 8192, "SameStep", "discrete"),
+    ("two-way-v0 defaults (TimeToCollision, 6 vehicles)", "two-way-v0", None, 8192, "SameStep", "discrete"),
     ("cfg2 intersection-v0 OccupancyGrid", "intersection-v0", {"observation": {"type": "OccupancyGrid"}}, 8192,
      "SameStep", "discrete3"),
     ("intersection-v0 defaults (Kinematics 15x7)", "intersection-v0", None, 8192, "SameStep", "discrete3"),
