@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("HWYB200_LIB") or os.path.join(_HERE, "csrc", "libhwyb200.so")
 
-HWY_ABI_VERSION = 4  # bump with every change of a struct or signature: a stale libhwyb200.so then fails to load
+HWY_ABI_VERSION = 5  # bump with every change of a struct or signature: a stale libhwyb200.so then fails to load
 HWY_MAX_LANES = 8
 HWY_MAX_TARGET_SPEEDS = 8
 HWY_MAX_VEHICLES = 128
@@ -141,6 +141,11 @@ KIND_OBSTACLE = 3
 META_NO_LANE_CHANGE = 1 << 23
 
 
+class HwyUTurnSpawn(C.Structure):
+    _fields_ = [("lane", C.c_int32 * 8), ("longitudinal", C.c_double * 8), ("speed", C.c_double * 8),
+                ("ego_speed_index", C.c_int32), ("_pad", C.c_int32), ("route_table", C.c_void_p), ("route_len", C.c_void_p)]
+
+
 class HwyTwoWaySpawn(C.Structure):
     _fields_ = [("lane_ab1", C.c_int32), ("lane_ba0", C.c_int32), ("ego_speed_index", C.c_int32), ("_pad", C.c_int32)]
 
@@ -163,7 +168,7 @@ EXPORTS = (
     "hwy_network_obs_size", "hwy_network_step", "hwy_network_observe", "hwy_roundabout_reset",
     "hwy_intersection_step", "hwy_network_substeps", "hwy_intersection_reset", "hwy_intersection_step_agents",
     "hwy_debug_network_neighbours", "hwy_debug_rotated_rectangles_intersect", "hwy_merge_reset",
-    "hwy_two_way_reset",
+    "hwy_two_way_reset", "hwy_u_turn_reset",
 )
 
 _lib = None
@@ -213,6 +218,9 @@ def load():
     lib.hwy_debug_network_neighbours.argtypes = [NP, NG, NS, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.hwy_debug_rotated_rectangles_intersect.restype = C.c_int
     lib.hwy_debug_rotated_rectangles_intersect.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.hwy_u_turn_reset.restype = C.c_int
+    lib.hwy_u_turn_reset.argtypes = [NP, NG, C.POINTER(HwyUTurnSpawn), NS, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p]
     lib.hwy_two_way_reset.restype = C.c_int
     lib.hwy_two_way_reset.argtypes = [NP, NG, C.POINTER(HwyTwoWaySpawn), NS, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p]

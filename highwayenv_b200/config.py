@@ -244,3 +244,25 @@ def two_way_default_config() -> dict:
 
 
 DEFAULTS["two-way-v0"] = two_way_default_config
+
+
+def u_turn_default_config() -> dict:
+    """UTurnEnv.default_config (highway_env/envs/u_turn_env.py:14-33) over AbstractEnv's."""
+    config = abstract_default_config()
+    update_config(config, {
+        "observation": {"type": "TimeToCollision", "horizon": 16},
+        "action": {"type": "DiscreteMetaAction", "target_speeds": [8, 16, 24]},
+        "screen_width": 789,
+        "screen_height": 289,
+        "duration": 10,
+        "collision_reward": -1.0,
+        "left_lane_reward": 0.1,
+        "high_speed_reward": 0.4,
+        "reward_speed_range": [8, 24],
+        "normalize_reward": True,
+        "offroad_terminal": False,
+    })
+    return config
+
+
+DEFAULTS["u-turn-v0"] = u_turn_default_config

@@ -63,7 +63,7 @@ struct EnvStage {
     double own_s[G], own_lat[G];
     int n_cand;
     union {
-        double ttc[3][4][12];  // TimeToCollision grid [speed][lane on road][time]
+        double ttc[3][4][16];  // TimeToCollision grid [speed][lane on road][time] (u-turn-v0: 16 s horizon)
         struct {
             int owner[121];           // OccupancyGrid: lowest vehicle index in the cell
             unsigned char road[121];  // on_road layer
@@ -604,7 +604,7 @@ __device__ __forceinline__ void observe_ttc(const HwyNetParams& P, const GraphSh
     const int n_speeds = P.n_target_speeds, n_lanes = EL.road_count;
     const double tq = 1.0 / P.policy_frequency;
     const int n_t = (int)(P.ttc_horizon / tq);
-    for (int k = i; k < 3 * 4 * 12; k += G) (&st.o.ttc[0][0][0])[k] = 0.0;
+    for (int k = i; k < 3 * 4 * 16; k += G) (&st.o.ttc[0][0][0])[k] = 0.0;
     group_sync<G>();
     if (i != ego && i < V && st.kind[i] != HWY_KIND_OBSTACLE) {  // one thread per other VEHICLE; cells take the max cost
         const int o = i;
@@ -1441,6 +1441,19 @@ network_step_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGraph* _
             rew = lmap(rew, P.collision_reward + P.merging_speed_reward, P.high_speed_reward + P.right_lane_reward, 0.0,
                        1.0);
             term = is_crashed || r.x > 370;
+        } else if (P.reward_type == 4) {
+            // envs/u_turn_env.py:36-82: collision, current lane id (left-most = highest), clipped speed term;
+            // normalised, then multiplied by on_road; truncated at `duration`
+            const int n1 = L.road_count - 1 > 1 ? L.road_count - 1 : 1;
+            double scaled_speed = lmap(r.speed, P.reward_speed_lo, P.reward_speed_hi, 0.0, 1.0);
+            rew = rew + P.collision_reward * (is_crashed ? 1.0 : 0.0);
+            rew = rew + P.left_lane_reward * ((double)L.lane_id / (double)n1);
+            rew = rew + P.high_speed_reward * clipd(scaled_speed, 0.0, 1.0);
+            rew = rew + 0.0 * (on_road ? 1.0 : 0.0);
+            if (P.normalize_reward)
+                rew = lmap(rew, P.collision_reward, P.high_speed_reward + P.left_lane_reward, 0.0, 1.0);
+            rew *= on_road ? 1.0 : 0.0;
+            term = is_crashed;
         } else if (P.reward_type == 3) {
             // envs/two_way_env.py:35-62: speed index and how far left the TARGET lane is; never truncated
             const int n_side = L.road_count;  // all_side_lanes(vehicle.lane_index)
@@ -1889,6 +1902,66 @@ merge_reset_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGraph* __
     store_rng(rng, (size_t)S.n_envs, e, g);
 }
 
+// UTurnEnv._make_vehicles (envs/u_turn_env.py:179-275), one env per thread: the MDPVehicle at the start of
+// ("a","b",0) and six IDM vehicles made on fixed lanes with normal-jittered longitudinal / speed, all routed to "d"
+__global__ void __launch_bounds__(128)
+u_turn_reset_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGraph* __restrict__ graph,
+                    const __grid_constant__ HwyUTurnSpawn SP, const __grid_constant__ HwyNetState S,
+                    uint64_t* __restrict__ rng, const uint8_t* __restrict__ mask_a, const uint8_t* __restrict__ mask_b) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= S.n_envs) return;
+    if ((mask_a || mask_b) && !((mask_a && mask_a[e]) || (mask_b && mask_b[e]))) return;
+    Pcg64 g = load_rng(rng, (size_t)S.n_envs, e);
+    double2* pos = reinterpret_cast<double2*>(S.pos);
+    double2* hs = reinterpret_cast<double2*>(S.hs);
+    double2* tt = reinterpret_cast<double2*>(S.tt);
+    double2* imp = reinterpret_cast<double2*>(S.imp);
+    const size_t base = (size_t)e * S.vp;
+    for (int v = 0; v < 7; ++v) {
+        double px, py, heading, speed, target_speed, timer = 0.0, delta = 4.0;
+        int kind = HWY_KIND_IDM;
+        if (v == 0) {  // :189-201 ego = vehicle_class(road, ("a","b",0).position(0, 0), speed=16)
+            lane_position(graph->lanes[SP.lane[0]], 0.0, 0.0, px, py);
+            heading = 0.0;
+            speed = 16.0;
+            kind = HWY_KIND_MDP;
+            target_speed = P.target_speeds[SP.ego_speed_index];
+        } else {  // make_on_lane (vehicle/objects.py:68-90) with longitudinal + normal * 2, speed + normal * 2
+            const HwyNetLane& L = graph->lanes[SP.lane[v]];
+            const double lon = SP.longitudinal[v] + g.normal() * 2.0;
+            speed = SP.speed[v] + g.normal() * 2.0;
+            lane_position(L, lon, 0.0, px, py);
+            heading = lane_heading_at(L, lon);
+            target_speed = speed;
+            if (v == 1) delta = g.uniform(3.5, 4.5);  // only vehicle 1 calls randomize_behavior (:218)
+        }
+        int lane = 0;  // RoadObject.__init__: closest lane (objects.py:46-50)
+        double bd = 0;
+        for (int l = 0; l < graph->n_lanes; ++l) {
+            double d = lane_distance_with_heading(graph->lanes[l], px, py, heading);
+            if (l == 0 || d < bd) {
+                bd = d;
+                lane = l;
+            }
+        }
+        if (kind == HWY_KIND_IDM) timer = py_mod_pos((px + py) * kPi, P.lane_change_delay);  // behavior.py:64
+        pos[base + v] = make_double2(px, py);
+        hs[base + v] = make_double2(heading, speed);
+        tt[base + v] = make_double2(target_speed, timer);
+        imp[base + v] = make_double2(0.0, 0.0);
+        S.delta[base + v] = delta;
+        S.meta[base + v] = (lane << HWY_META_LANE_SHIFT) | (lane << HWY_META_TARGET_SHIFT) | HWY_META_CHECK_COLLISIONS |
+                           (kind << HWY_META_KIND_SHIFT) | HWY_META_PRESENT;
+        const int* rsrc = SP.route_table + (size_t)lane * R;  // plan_route_to("d") from the closest lane
+        int* rdst = S.route + (base + v) * R;
+        for (int k = 0; k < R; ++k) rdst[k] = rsrc[k];
+        S.route_len[base + v] = SP.route_len[lane];
+    }
+    S.speed_index[e] = SP.ego_speed_index;
+    S.time[e] = 0.0;
+    store_rng(rng, (size_t)S.n_envs, e, g);
+}
+
 // TwoWayEnv._make_vehicles (envs/two_way_env.py:113-158), one env per thread
 __global__ void __launch_bounds__(128)
 two_way_reset_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGraph* __restrict__ graph,
@@ -1968,7 +2041,7 @@ int validate_net(const HwyNetParams* p, const HwyNetGraph* graph, const HwyNetSt
     if (p->n_target_speeds < 1 || p->n_target_speeds > 3) return fail("%s", "network kernels support up to 3 target speeds");
     if (p->obs_type != HWY_OBS_KINEMATICS && p->obs_type != HWY_OBS_TTC && p->obs_type != HWY_OBS_OCCUPANCY)
         return fail("%s", "unknown obs_type");
-    if (p->obs_type == HWY_OBS_TTC && (p->ttc_horizon * p->policy_frequency < 1 || p->ttc_horizon * p->policy_frequency > 12))
+    if (p->obs_type == HWY_OBS_TTC && (p->ttc_horizon * p->policy_frequency < 1 || p->ttc_horizon * p->policy_frequency > 16))
         return fail("%s", "ttc horizon out of range");
     if (p->obs_type == HWY_OBS_KINEMATICS && (p->obs_vehicles_count < 1 || p->obs_vehicles_count > 32))
         return fail("%s", "obs_vehicles_count out of range");
@@ -2162,6 +2235,18 @@ int hwy_merge_reset(const HwyNetParams* p, const HwyNetGraph* graph, const HwyMe
     cudaStream_t st = (cudaStream_t)stream;
     hwynet::merge_reset_kernel<<<(s->n_envs + 127) / 128, 128, 0, st>>>(*p, graph, *spawn, *s, rng, mask_a, mask_b);
     if (check_launch("merge_reset_kernel")) return 1;
+    if (obs) return observe_dispatch(p, graph, s, mask_a, mask_b, obs, st);
+    return 0;
+}
+
+int hwy_u_turn_reset(const HwyNetParams* p, const HwyNetGraph* graph, const HwyUTurnSpawn* spawn, const HwyNetState* s,
+                     uint64_t* rng, const uint8_t* mask_a, const uint8_t* mask_b, float* obs, void* stream) {
+    if (validate_net(p, graph, s)) return 1;
+    if (!spawn || !rng || !spawn->route_table || !spawn->route_len) return fail("%s", "null spawn / rng / route table");
+    if (s->vp != HWY_NET_GROUP || p->n_vehicles != 7) return fail("%s", "u-turn-v0: 7 vehicles on 8 slots");
+    cudaStream_t st = (cudaStream_t)stream;
+    hwynet::u_turn_reset_kernel<<<(s->n_envs + 127) / 128, 128, 0, st>>>(*p, graph, *spawn, *s, rng, mask_a, mask_b);
+    if (check_launch("u_turn_reset_kernel")) return 1;
     if (obs) return observe_dispatch(p, graph, s, mask_a, mask_b, obs, st);
     return 0;
 }

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define HWY_ABI_VERSION 4
+#define HWY_ABI_VERSION 5
 #define HWY_MAX_LANES 8
 #define HWY_MAX_TARGET_SPEEDS 8
 #define HWY_MAX_VEHICLES 128 /* per env, incl. the ego */
@@ -258,7 +258,8 @@ typedef struct HwyNetParams {
     double right_lane_reward, merging_speed_reward;
     int32_t merge_lane;         /* table index of ("b", "c", 2): slow ControlledVehicles there are penalised */
     int32_t _pad_merge;
-    double left_lane_reward;    /* two-way-v0 (envs/two_way_env.py:17-62): reward_type 3 */
+    double left_lane_reward;    /* two-way-v0 (envs/two_way_env.py:17-62): reward_type 3; u-turn-v0
+                                 * (envs/u_turn_env.py:14-82): reward_type 4 */
 } HwyNetParams;
 
 /* route entry: from_node | to_node << 8 | (lane_id + 1) << 16  (lane_id + 1 == 0: None) */
@@ -363,6 +364,22 @@ typedef struct HwyMergeSpawn {
 int hwy_merge_reset(const HwyNetParams *p, const HwyNetGraph *graph, const HwyMergeSpawn *spawn,
                     const HwyNetState *s, uint64_t *rng, const uint8_t *mask_a, const uint8_t *mask_b,
                     float *obs, void *stream);
+
+/* UTurnEnv._make_vehicles (envs/u_turn_env.py:179-275) on the device: the MDPVehicle at the start of ("a","b",0),
+ * speed 16, and six IDM vehicles made with make_on_lane(lane[v], longitudinal[v] + 2 normal(), speed[v] + 2 normal());
+ * vehicle 1 also draws its DELTA (randomize_behavior); every vehicle gets plan_route_to("d") from a host-built
+ * table indexed by the closest lane.  (The reference also sets ego.PURSUIT_TAU, an attribute nothing reads —
+ * steering_control uses TAU_PURSUIT, vehicle/controller.py:28,159 — so there is nothing to restate.) */
+typedef struct HwyUTurnSpawn {
+    int32_t lane[8];             /* [0] ego lane ("a","b",0); [1..6] make_on_lane lanes */
+    double longitudinal[8], speed[8];
+    int32_t ego_speed_index, _pad;
+    const int32_t *route_table;  /* DEVICE [n_lanes][HWY_NET_MAX_ROUTE]: plan_route_to("d") from each lane */
+    const int32_t *route_len;    /* DEVICE [n_lanes] */
+} HwyUTurnSpawn;
+int hwy_u_turn_reset(const HwyNetParams *p, const HwyNetGraph *graph, const HwyUTurnSpawn *spawn,
+                     const HwyNetState *s, uint64_t *rng, const uint8_t *mask_a, const uint8_t *mask_b,
+                     float *obs, void *stream);
 
 /* TwoWayEnv._make_vehicles (envs/two_way_env.py:113-158) on the device: the MDPVehicle on ("a","b",1) at s = 30,
  * three IDM vehicles ahead at 70 + 40 i + 10 normal() with speed 24 + 2 normal(), two oncoming ones on ("b","a",0)

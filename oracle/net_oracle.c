@@ -396,7 +396,8 @@ static double steering_control(const World *w, int v, int target_lane) {
     const NetLane *L = LANE(w, target_lane);
     double lc_s, lc_lat;
     net_lane_local(L, s->x[v], s->y[v], &lc_s, &lc_lat);
-    double lane_next_coords = lc_s + s->speed[v] * TAU_PURSUIT;
+    double tau = (s->kind[v] == NET_KIND_MDP && w->c->ego_pursuit_tau > 0) ? w->c->ego_pursuit_tau : TAU_PURSUIT;
+    double lane_next_coords = lc_s + s->speed[v] * tau;
     double lane_future_heading = net_lane_heading_at(L, lane_next_coords);
     double lateral_speed_command = -KP_LATERAL * lc_lat;
     double heading_command = asin(clipd(lateral_speed_command / orc_not_zero(s->speed[v]), -1, 1));
@@ -1039,6 +1040,29 @@ static void reward_done_two_way(const World *w, double *reward, int32_t *termina
     *truncated = 0;
 }
 
+/* envs/u_turn_env.py:36-82 */
+static void reward_done_u_turn(const World *w, double *reward, int32_t *terminated, int32_t *truncated) {
+    const NetCfg *c = w->c;
+    const NetState *s = w->s;
+    const int ego = 0;
+    const NetLane *L = LANE(w, s->lane[ego]);
+    double es, elat;
+    net_lane_local(L, s->x[ego], s->y[ego], &es, &elat);
+    int on_road = lane_on_lane(L, es, elat, 0.0);
+    int n1 = L->road_count - 1 > 1 ? L->road_count - 1 : 1;
+    double scaled_speed = lmap(s->speed[ego], c->reward_speed_lo, c->reward_speed_hi, 0, 1);
+    double r = 0;
+    r = r + c->collision_reward * (double)(s->crashed[ego] != 0);
+    r = r + c->left_lane_reward * ((double)L->lane_id / (double)n1);
+    r = r + c->high_speed_reward * clipd(scaled_speed, 0, 1);
+    r = r + 0 * (double)on_road;
+    if (c->normalize_reward) r = lmap(r, c->collision_reward, c->high_speed_reward + c->left_lane_reward, 0, 1);
+    r *= (double)on_road;
+    *reward = r;
+    *terminated = s->crashed[ego] != 0;
+    *truncated = s->time[0] >= c->duration;
+}
+
 /* ------------------------------------------------------------------ road/regulation.py */
 
 /* road/road.py:323-362 position_heading_along_route(route, longitudinal, 0, current_lane_index) */
@@ -1210,6 +1234,8 @@ void net_step(const NetGraph *g, const NetCfg *c, NetState *s, int action, float
         reward_done_merge(&w, action, reward, terminated, truncated);
     else if (c->reward_type == 3)
         reward_done_two_way(&w, reward, terminated, truncated);
+    else if (c->reward_type == 4)
+        reward_done_u_turn(&w, reward, terminated, truncated);
     else
         reward_done(&w, action, reward, terminated, truncated);
     free(act_buf);

@@ -82,8 +82,9 @@ typedef struct NetCfg {
     double right_lane_reward, merging_speed_reward;
     int32_t merge_lane; /* table index of ("b", "c", 2), the lane whose slow vehicles are penalised */
     int32_t _pad3;
-    /* two-way-v0 (envs/two_way_env.py): reward_type 3 */
+    /* two-way-v0 (envs/two_way_env.py): reward_type 3; u-turn-v0 (envs/u_turn_env.py): reward_type 4 */
     double left_lane_reward;
+    double ego_pursuit_tau; /* u_turn_env.py:193 ego.PURSUIT_TAU = TAU_HEADING; 0: the class default */
 } NetCfg;
 
 /* route entry: from | to << 8 | (lane_id + 1) << 16   (lane_id + 1 == 0: None) */

@@ -51,7 +51,8 @@ class NetCfg(C.Structure):
                                     "connected_lanes")]
         + [(k, C.c_double) for k in ("arrived_reward", "reward_speed_lo", "reward_speed_hi", "right_lane_reward",
                                      "merging_speed_reward")]
-        + [("merge_lane", C.c_int32), ("_pad3", C.c_int32), ("left_lane_reward", C.c_double)]
+        + [("merge_lane", C.c_int32), ("_pad3", C.c_int32), ("left_lane_reward", C.c_double),
+           ("ego_pursuit_tau", C.c_double)]
     )
 
 
@@ -199,9 +200,15 @@ def cfg_from_dict(config: dict, n_vehicles: int = 5) -> NetCfg:
         c.merging_speed_reward = float(config["merging_speed_reward"])
         c.reward_speed_lo, c.reward_speed_hi = (float(v) for v in config["reward_speed_range"])
         c.merge_lane = int(config["_merge_lane"])
-    if "left_lane_reward" in config:  # two-way-v0 (envs/two_way_env.py:17-33)
+    if "left_lane_reward" in config:  # two-way-v0 (envs/two_way_env.py:17-33) / u-turn-v0 (envs/u_turn_env.py:14-33)
         c.reward_type = 3
         c.left_lane_reward = float(config["left_lane_reward"])
+        if "reward_speed_range" in config:  # u-turn
+            c.reward_type = 4
+            c.reward_speed_lo, c.reward_speed_hi = (float(v) for v in config["reward_speed_range"])
+            # u_turn_env.py:196 sets ego.PURSUIT_TAU, but steering_control reads self.TAU_PURSUIT
+            # (controller.py:28,159): the assignment is inert in the reference, so the default tau applies
+            c.ego_pursuit_tau = 0.0
     c.connected_lanes = int(bool(config.get("neighbour_vehicles_connected_lanes", False)))
     c.politeness, c.lane_change_min_acc_gain = 0.0, 0.2
     c.lane_change_max_braking_imposed, c.lane_change_delay = 2.0, 1.0

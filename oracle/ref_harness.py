@@ -56,6 +56,7 @@ ENV_CLASSES = {
     "intersection-v2": ("highway_env.envs.intersection_env", "ConnectedLaneIntersectionEnv"),
     "intersection-multi-agent-v0": ("highway_env.envs.intersection_env", "MultiAgentIntersectionEnv"),
     "two-way-v0": ("highway_env.envs.two_way_env", "TwoWayEnv"),
+    "u-turn-v0": ("highway_env.envs.u_turn_env", "UTurnEnv"),
     "merge-v0": ("highway_env.envs.merge_env", "MergeEnv"),
     "merge-v1": ("highway_env.envs.merge_env", "ConnectedLaneMergeEnv"),
 }

@@ -207,7 +207,7 @@ def test_road_network_follow_road():
 
 @pytest.mark.parametrize("env_id", ["highway-v0", "highway-fast-v0", "roundabout-v0", "roundabout-v1", "intersection-v0",
                                     "intersection-v2", "intersection-multi-agent-v0", "intersection-multi-agent-v1",
-                                    "merge-v0", "merge-v1", "two-way-v0"])
+                                    "merge-v0", "merge-v1", "two-way-v0", "u-turn-v0"])
 def test_env_step_until_done(env_id):
     """envs/test_gym.py:65-90 test_env_step: reset, random actions until the episode ends, observations stay in
     the observation space (shape, dtype, finite; [-1, 1] where the reference normalises and clips)."""

@@ -146,9 +146,11 @@ def test_network_tables_match_the_reference_dump():
 
     from highwayenv_b200.envs.merge_env import make_merge_network
     from highwayenv_b200.envs.two_way_env import make_two_way_network
+    from highwayenv_b200.envs.u_turn_env import make_u_turn_network
 
     for name, build in (("intersection_kin", make_intersection_network), ("roundabout_kin", make_roundabout_network),
-                        ("merge_kin", make_merge_network), ("two_way_ttc", make_two_way_network)):
+                        ("merge_kin", make_merge_network), ("two_way_ttc", make_two_way_network),
+                        ("u_turn_ttc", make_u_turn_network)):
         g, ex = load_golden(name), build().export_arrays()
         assert list(ex["net_node_names"]) == list(g["net_node_names"]), name
         for key, val in ex.items():
@@ -168,7 +170,7 @@ def test_network_env_defaults_match_reference_config():
     from parity_utils import load_golden
 
     for name in ("intersection_kin", "intersection_v2_kin", "roundabout_kin", "roundabout_v1_kin",
-                 "intersection_multi_agent", "merge_kin", "merge_v1_kin", "two_way_ttc"):
+                 "intersection_multi_agent", "merge_kin", "merge_v1_kin", "two_way_ttc", "u_turn_ttc"):
         ref = {k: v for k, v in load_golden(name)["config"].items() if not k.startswith("_") or k == "_env_id"}
         env_id = ref.pop("_env_id")
         assert env_id in hb.REGISTRY

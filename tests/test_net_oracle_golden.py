@@ -263,3 +263,41 @@ def test_two_way_teacher_forced():
             assert bool(term[i]) == bool(g["terminated"][i, t]) and not trunc[i] and not g["truncated"][i, t], ctx
             assert np.max(np.abs(obs[i].reshape(g["obs"][i, t + 1].shape) - g["obs"][i, t + 1])) <= 1e-6, ctx
     assert worst < 1e-9
+
+
+# ------------------------------------------------------------------ u-turn-v0 (circular U-turn, routed traffic)
+def u_turn_state(g, i, t):
+    st = golden_net_state(g, i, t)
+    st["target_lane"] = np.where(st["target_lane"] < 0, st["lane"], st["target_lane"])
+    return st
+
+
+def test_u_turn_teacher_forced():
+    """u-turn-v0: routes to "d" through the circular lanes, ego PURSUIT_TAU = TAU_HEADING, TimeToCollision with a
+    16 s horizon, left-lane / speed reward with on_road factor, truncation at 10 s"""
+    name = "u_turn_ttc"
+    g = load_golden(name)
+    graph = no.graph_from_arrays(g)
+    V = g["x"].shape[2]
+    cfg = no.cfg_from_dict(g["config"], n_vehicles=V)
+    assert cfg.reward_type == 4 and cfg.ttc_horizon == 16 and V == 7
+    S, T = g["actions"].shape[:2]
+    ob = no.NetOracleBatch(graph, cfg, S)
+    for i in range(S):
+        ob.load_state(i, u_turn_state(g, i, 0))
+    obs0 = ob.observe().reshape(g["obs"][:, 0].shape)
+    assert np.max(np.abs(obs0 - g["obs"][:, 0])) <= 1e-6
+    worst = 0.0
+    for t in range(T):
+        for i in range(S):
+            ob.load_state(i, u_turn_state(g, i, t))
+        obs, rew, term, trunc = ob.step(g["actions"][:, t])
+        for i in range(S):
+            ctx = f"{name} seed#{i} t={t}"
+            st1 = u_turn_state(g, i, t + 1)
+            worst = max(worst, compare_state(st1, got_state(ob, i), ctx=ctx))
+            check_routes(st1, got_state(ob, i), ctx)
+            assert abs(rew[i] - g["reward"][i, t]) <= 1e-9, ctx
+            assert bool(term[i]) == bool(g["terminated"][i, t]) and bool(trunc[i]) == bool(g["truncated"][i, t]), ctx
+            assert np.max(np.abs(obs[i].reshape(g["obs"][i, t + 1].shape) - g["obs"][i, t + 1])) <= 1e-6, ctx
+    assert worst < 1e-9

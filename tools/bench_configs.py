@@ -29,6 +29,7 @@ CONFIGS = [
     ("roundabout-v0 defaults (Kinematics)", "roundabout-v0", None, 8192, "SameStep", "discrete"),
     ("merge-v0 defaults (Kinematics, 5 vehicles + obstacle)", "merge-v0", None, 8192, "SameStep", "discrete"),
     ("two-way-v0 defaults (TimeToCollision, 6 vehicles)", "two-way-v0", None, 8192, "SameStep", "discrete"),
+    ("u-turn-v0 defaults (TimeToCollision 16 s, 7 vehicles)", "u-turn-v0", None, 8192, "SameStep", "discrete"),
     ("cfg2 intersection-v0 OccupancyGrid", "intersection-v0", {"observation": {"type": "OccupancyGrid"}}, 8192,
      "SameStep", "discrete3"),
     ("intersection-v0 defaults (Kinematics 15x7)", "intersection-v0", None, 8192, "SameStep", "discrete3"),
