@@ -266,3 +266,4 @@ def u_turn_default_config() -> dict:
 
 
 DEFAULTS["u-turn-v0"] = u_turn_default_config
+DEFAULTS["u-turn-v1"] = _connected(u_turn_default_config)

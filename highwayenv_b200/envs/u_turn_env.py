@@ -81,3 +81,9 @@ class BatchedUTurnEnv(BatchedRoundaboutEnv):
             N.check(self._lib.hwy_u_turn_reset(
                 C.byref(self._params), self._graph_dev.data_ptr(), C.byref(self._spawn_struct), C.byref(self._state),
                 self._rng.data_ptr(), mask_a, mask_b, obs_ptr, self._stream()))
+
+
+class BatchedConnectedLaneUTurnEnv(BatchedUTurnEnv):
+    """`u-turn-v1`: ConnectedLaneNeighboursMixin (envs/common/abstract.py:26-37)."""
+
+    ENV_ID = "u-turn-v1"

@@ -74,6 +74,7 @@ CASES = {
     "two_way_ttc": ("two-way-v0", None, list(range(960, 968)), 15, "discrete5"),
     # u-turn-v0: circular U-turn, routed traffic, ego with PURSUIT_TAU = TAU_HEADING, TimeToCollision horizon 16
     "u_turn_ttc": ("u-turn-v0", None, list(range(970, 978)), 10, "discrete5"),
+    "u_turn_v1_ttc": ("u-turn-v1", None, list(range(980, 984)), 10, "discrete5"),
     # the merging vehicle is moved onto the end of the ramp at speed: it runs into the Obstacle (objects.py:104-107)
     "merge_obstacle_hit": ("merge-v0", None, list(range(950, 954)), 6, "discrete5"),
 }

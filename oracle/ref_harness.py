@@ -57,6 +57,7 @@ ENV_CLASSES = {
     "intersection-multi-agent-v0": ("highway_env.envs.intersection_env", "MultiAgentIntersectionEnv"),
     "two-way-v0": ("highway_env.envs.two_way_env", "TwoWayEnv"),
     "u-turn-v0": ("highway_env.envs.u_turn_env", "UTurnEnv"),
+    "u-turn-v1": ("highway_env.envs.u_turn_env", "ConnectedLaneUTurnEnv"),
     "merge-v0": ("highway_env.envs.merge_env", "MergeEnv"),
     "merge-v1": ("highway_env.envs.merge_env", "ConnectedLaneMergeEnv"),
 }

@@ -15,7 +15,7 @@ NAME = "u_turn_ttc"
 def make_env(cfg, n, **kw):
     import highwayenv_b200 as hb
 
-    return hb.make("u-turn-v0", num_envs=n, config={k: v for k, v in cfg.items() if not k.startswith("_")}, **kw)
+    return hb.make(cfg["_env_id"], num_envs=n, config={k: v for k, v in cfg.items() if not k.startswith("_")}, **kw)
 
 
 def sd_of(g, i, t):
@@ -39,7 +39,8 @@ def test_reset_matches_reference():
     assert np.max(np.abs(obs.cpu().numpy() - g["obs"][:, 0])) <= 1e-6
 
 
-def test_teacher_forced_vs_reference():
+@pytest.mark.parametrize("NAME", ["u_turn_ttc", "u_turn_v1_ttc"])
+def test_teacher_forced_vs_reference(NAME):
     g = load_golden(NAME)
     S, T = g["actions"].shape[:2]
     env = make_env(g["config"], S, autoreset_mode="Disabled")

@@ -170,7 +170,7 @@ def test_network_env_defaults_match_reference_config():
     from parity_utils import load_golden
 
     for name in ("intersection_kin", "intersection_v2_kin", "roundabout_kin", "roundabout_v1_kin",
-                 "intersection_multi_agent", "merge_kin", "merge_v1_kin", "two_way_ttc", "u_turn_ttc"):
+                 "intersection_multi_agent", "merge_kin", "merge_v1_kin", "two_way_ttc", "u_turn_ttc", "u_turn_v1_ttc"):
         ref = {k: v for k, v in load_golden(name)["config"].items() if not k.startswith("_") or k == "_env_id"}
         env_id = ref.pop("_env_id")
         assert env_id in hb.REGISTRY

@@ -272,10 +272,10 @@ def u_turn_state(g, i, t):
     return st
 
 
-def test_u_turn_teacher_forced():
-    """u-turn-v0: routes to "d" through the circular lanes, ego PURSUIT_TAU = TAU_HEADING, TimeToCollision with a
+@pytest.mark.parametrize("name", ["u_turn_ttc", "u_turn_v1_ttc"])
+def test_u_turn_teacher_forced(name):
+    """u-turn-v0 / v1 (connected-lane neighbour search): routes to "d" through the circular lanes, ego PURSUIT_TAU = TAU_HEADING, TimeToCollision with a
     16 s horizon, left-lane / speed reward with on_road factor, truncation at 10 s"""
-    name = "u_turn_ttc"
     g = load_golden(name)
     graph = no.graph_from_arrays(g)
     V = g["x"].shape[2]
