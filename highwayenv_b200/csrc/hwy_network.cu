@@ -1690,8 +1690,9 @@ intersection_reset_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGr
     for (int t = 0; t < n0 - 1; ++t) {
         if (i == 0) {
             const unsigned present = st.count >= 32 ? 0xffffffffu : ((1u << st.count) - 1u);
-            spawn_vehicle(P, SP, g, st, rng, present, (double)t * (80.0 / (double)(n0 - 1)), 1.0, 1.0,
-                          SP.spawn_probability, false);
+            // _make_vehicles calls _spawn_vehicle(longitudinal) with the FUNCTION default spawn_probability = 0.6
+            // (intersection_env.py:268,331), not config["spawn_probability"] (used by the per-step spawn, :139)
+            spawn_vehicle(P, SP, g, st, rng, present, (double)t * (80.0 / (double)(n0 - 1)), 1.0, 1.0, 0.6, false);
             if (st.count >= G) st.sp_ok = 0;
         }
         commit(HWY_KIND_IDM);
