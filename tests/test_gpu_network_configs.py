@@ -115,3 +115,48 @@ def test_intersection_options_reset_and_steps_vs_oracle(over):
         assert np.max(np.abs(rew.cpu().numpy() - o_rew)) <= 1e-9
         assert np.array_equal(term.cpu().numpy(), o_term.astype(bool)) and np.array_equal(trunc.cpu().numpy(), o_trunc.astype(bool))
         assert np.max(np.abs(obs.cpu().numpy().reshape(n, -1) - o_obs.reshape(n, -1))) <= 1e-6
+
+
+@pytest.mark.parametrize("over", [
+    {"controlled_vehicles": 3},
+    {"controlled_vehicles": 4, "destination": None},
+], ids=lambda o: "-".join(f"{k}" for k in o))
+def test_multi_agent_options_reset_and_steps_vs_oracle(over):
+    """more controlled vehicles than the default two (one per access road), random destinations"""
+    g, cfg = _cfg("intersection_multi_agent", over)
+    n, A = 48, int(cfg["controlled_vehicles"])
+    ob = no.IntersectionOracle(no.graph_from_arrays(g), no.cfg_from_dict(cfg), n, g, cfg)
+    for e in range(n):
+        ob.reset_env(e, seed=4500 + e)
+    for mode in ("device", "host"):
+        env = _make(cfg, n, autoreset_mode="Disabled", reset_mode=mode)
+        obs, _ = env.reset(seed=4500)
+        assert obs.shape == (n, A, 15, 7)
+        sd = env.state_dict()
+        assert np.array_equal(sd["count"], ob.a["count"]), mode
+        live = np.arange(V32)[None, :] < sd["count"][:, None]
+        for k in ("lane", "kind", "route_len"):
+            assert np.array_equal(np.where(live, sd[k], 0), np.where(live, ob.a[k], 0)), (mode, k)
+        assert np.all((np.where(live, sd["kind"], 0) == 1).sum(axis=1) == A)
+        for k in ("x", "y", "speed"):
+            assert np.max(np.abs(np.where(live, sd[k] - ob.a[k], 0.0))) <= 1e-6, (mode, k)
+        for e in range(n):
+            assert np.array_equal(sd["rng"][:, e], ob.rng_words(e)), (mode, e)
+        assert np.max(np.abs(obs.cpu().numpy().reshape(n, -1) - ob.observe().reshape(n, -1))) <= 1e-6
+    rng = np.random.default_rng(3)
+    for t in range(6):
+        state = {k: ob.a[k].copy() for k in ob.a}
+        state["rng"] = np.stack([ob.rng_words(e) for e in range(n)], axis=1)
+        env.load_state_dict(state)
+        act = rng.integers(0, 3, size=(n, A)).astype(np.int32)
+        o_obs, o_rew, o_term, o_trunc = ob.step(act)
+        obs, rew, term, trunc, info = env.step(act)
+        sd = env.state_dict()
+        assert np.array_equal(sd["count"], ob.a["count"]), t
+        assert np.max(np.abs(rew.cpu().numpy() - o_rew)) <= 1e-9
+        assert np.max(np.abs(info["agents_rewards"].cpu().numpy() - ob.agents_reward)) <= 1e-9
+        assert np.array_equal(info["agents_terminated"].cpu().numpy(), ob.agents_terminated.astype(bool))
+        assert np.array_equal(term.cpu().numpy(), o_term.astype(bool)) and np.array_equal(trunc.cpu().numpy(), o_trunc.astype(bool))
+        assert np.max(np.abs(obs.cpu().numpy().reshape(n, -1) - o_obs.reshape(n, -1))) <= 1e-6
+        for e in range(n):
+            assert np.array_equal(sd["rng"][:, e], ob.rng_words(e)), (t, e)
