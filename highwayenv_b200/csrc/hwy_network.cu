@@ -1,17 +1,20 @@
-// hwy_network.cu — sm_100a kernels + C ABI for envs on a GENERAL road network (roundabout-v0):
-// StraightLane / SineLane / CircularLane geometry, planned routes with RoadNetwork.next_lane,
-// IDM + MOBIL with the route branch, all-pairs SAT collisions, absolute Kinematics or
-// TimeToCollision observation, roundabout reward.
+// hwy_network.cu — sm_100a kernels + C ABI for envs on a GENERAL road network: roundabout-v0|v1, merge-v0|v1,
+// two-way-v0, u-turn-v0|v1 (8 vehicle slots per env) and intersection-v0|v2, intersection-multi-agent-v0|v1|v2
+// (16 / 32 slots, RegulatedRoad, a population that changes every step).
+// StraightLane / SineLane / CircularLane geometry, planned routes with RoadNetwork.next_lane, IDM + MOBIL with the
+// route branch, all-pairs SAT collisions incl. road objects (Obstacle), connected-lane neighbour search, Kinematics /
+// TimeToCollision / OccupancyGrid observations, the scenarios' rewards, and their resets on the env's numpy stream.
 //
-// Thread mapping: G = 8 threads per env (vehicle slot = thread; roundabout has 5 vehicles), 32
-// envs per 256-thread block.  The per-vehicle work is branchy; the one regular O(V*L) piece —
-// Vehicle.on_state_update's get_closest_lane_index over ALL lanes (47 % of the reference's step
-// on networks) — is spread over the group: thread t evaluates lanes t, t+G, ... for each
-// vehicle and a shuffle arg-min (first minimum wins, as np.argmin) picks the lane.
-// Road.act's Gauss-Seidel part (follow_road + change_lane_policy mutate target lanes / routes that
-// later vehicles read) runs in list order, one vehicle at a time, exactly like the reference;
-// steering, IDM acceleration, integration and the collision sweep run one vehicle per thread.
-// The lane table lives in HBM (HwyNetGraph) and is staged into shared memory once per block.
+// Thread mapping: template <int G, bool REG> — G threads per env (vehicle slot = thread), 256-thread blocks; the
+// groups of a block advance through the phases of a substep together (block-wide `barrier.sync`): the kernels are
+// several times the instruction cache, and warps left to drift apart stalled on instruction fetch.
+//  * Each vehicle's local coordinates on its own lane are computed once per substep and reused by every query.
+//  * Vehicle.on_state_update's get_closest_lane_index over ALL lanes (47 % of the reference's step on networks) is
+//    pruned exactly by a lateral lower bound; the surviving (vehicle, lane) pairs form a work list for the group.
+//  * Road.act's Gauss-Seidel part: follow_road runs for all vehicles at once; only vehicles whose lane-change
+//    policy can read or move a target lane take turns in list order.
+//  * Steering, IDM acceleration, integration and the collision sweep run one vehicle per thread.
+// The lane table lives in HBM (HwyNetGraph) and is staged into shared memory once per block.  DESIGN.md 3.5-3.9.
 //
 // Reference paths are relative to /root/reference/highway_env.
 #include <cstdio>
