@@ -310,6 +310,20 @@ class BatchedHighwayEnv:
             self._truncated.mul_(keep)
         self._autoreset_envs = (self._terminated | self._truncated).contiguous()
 
+    def get_available_actions(self) -> torch.Tensor:
+        """DiscreteMetaAction.get_available_actions (envs/common/action.py:262-299, AbstractEnv.get_available_actions
+        abstract.py:357-358) for every env at once: a bool mask [N, 5] over (LANE_LEFT, IDLE, LANE_RIGHT, FASTER,
+        SLOWER).  A lane change is available when the side lane exists and `is_reachable_from` the ego's position
+        (road/lane.py:104-118); FASTER / SLOWER unless the speed index sits at the end of `target_speeds`."""
+        if self._params.action_type != 0:
+            raise AttributeError("available actions are defined for DiscreteMetaAction only")
+        lanes = [self._params.lanes[k] for k in range(int(self._params.lanes_count))]
+        table = torch.tensor([[L.start_x, L.start_y, L.dir_x, L.dir_y, L.lat_x, L.lat_y, L.length, L.width] for L in lanes],
+                             dtype=torch.float64, device=self._pos.device)
+        lane = ((self._meta[:, 0] >> N.META_LANE_SHIFT) & 0xFF).long()
+        return available_actions_mask(self._pos[:, 0, 0], self._pos[:, 0, 1], lane, self._speed_index.long(), table,
+                                      int(self._params.n_target_speeds))
+
     def host_stepper(self) -> "HostStepper":
         """Host-buffer stepping through one CUDA graph (see HostStepper)."""
         return HostStepper(self)
@@ -386,6 +400,27 @@ class BatchedHighwayEnvFast(BatchedHighwayEnv):
 
     ENV_ID = "highway-fast-v0"
     OTHERS_CHECK_COLLISIONS = False
+
+
+def available_actions_mask(x, y, lane, speed_index, lane_table, n_speeds: int, vehicle_length: float = 5.0):
+    """Pure tensor form of DiscreteMetaAction.get_available_actions on a straight multi-lane road (any device).
+
+    lane_table: [L, 8] = (start_x, start_y, dir_x, dir_y, lat_x, lat_y, length, width) per lane; returns bool [N, 5]
+    in label order LANE_LEFT, IDLE, LANE_RIGHT, FASTER, SLOWER (action.py:204)."""
+    n_lanes = lane_table.shape[0]
+    out = torch.zeros((x.shape[0], 5), dtype=torch.bool, device=x.device)
+    out[:, 1] = True  # IDLE
+    for col, step in ((0, -1), (2, +1)):  # side_lanes: id - 1, id + 1 on the same road (road/road.py:200-211)
+        side = lane + step
+        exists = (side >= 0) & (side < n_lanes)
+        t = lane_table[side.clamp(0, n_lanes - 1)]
+        dx, dy = x - t[:, 0], y - t[:, 1]
+        lon = dx * t[:, 2] + dy * t[:, 3]
+        lat = dx * t[:, 4] + dy * t[:, 5]
+        out[:, col] = exists & (lat.abs() <= 2 * t[:, 7]) & (lon >= 0) & (lon < t[:, 6] + vehicle_length)
+    out[:, 3] = speed_index < n_speeds - 1
+    out[:, 4] = speed_index > 0
+    return out
 
 
 class HostStepper:

@@ -241,3 +241,24 @@ def test_gloo_world_size_2_gather(tmp_path):
     outs = [p.communicate(timeout=120)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "ok 0" in outs[0] and "ok 1" in outs[1]
+
+
+def test_available_actions_mask_matches_reference_rule():
+    """DiscreteMetaAction.get_available_actions (action.py:262-299) in tensor form, on CPU tensors"""
+    import torch
+
+    from highwayenv_b200.envs.highway_env import available_actions_mask
+
+    table = torch.tensor([[0.0, 4.0 * l, 1.0, 0.0, -0.0, 1.0, 10000.0, 4.0] for l in range(3)], dtype=torch.float64)
+    x = torch.tensor([100.0, 100.0, 100.0, -1.0, 10004.9, 10005.0], dtype=torch.float64)
+    y = torch.tensor([0.0, 4.0, 8.0, 4.0, 4.0, 4.0], dtype=torch.float64)
+    lane = torch.tensor([0, 1, 2, 1, 1, 1])
+    si = torch.tensor([0, 1, 2, 1, 1, 1])
+    m = available_actions_mask(x, y, lane, si, table, 3).numpy()
+    # columns: LANE_LEFT, IDLE, LANE_RIGHT, FASTER, SLOWER
+    assert m[0].tolist() == [False, True, True, True, False]   # leftmost lane, lowest speed
+    assert m[1].tolist() == [True, True, True, True, True]
+    assert m[2].tolist() == [True, True, False, False, True]   # rightmost lane, highest speed
+    assert m[3].tolist() == [False, True, False, True, True]   # before the lane start: 0 <= longitudinal fails
+    assert m[4].tolist() == [True, True, True, True, True]     # longitudinal < length + VEHICLE_LENGTH
+    assert m[5].tolist() == [False, True, False, True, True]

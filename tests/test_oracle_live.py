@@ -39,3 +39,26 @@ def test_oracle_matches_live_reference(env_id, over, T, seed):
         assert compare_state(rh.dump_state(env), got, ctx=f"{env_id} t={t}") < 1e-9
         assert abs(r - ro[0]) < 1e-12 and te == bool(teo[0]) and tr == bool(tro[0])
         assert np.max(np.abs(o - oo[0])) <= 1e-6
+
+
+def test_available_actions_mask_matches_live_reference():
+    """DiscreteMetaAction.get_available_actions (action.py:262-299) vs the product's tensor form (CPU tensors)"""
+    import torch
+
+    from highwayenv_b200.envs.highway_env import available_actions_mask
+
+    env = rh.make_reference_env("highway-fast-v0", {"lanes_count": 3})
+    env.reset(seed=0)
+    table = torch.tensor([[0.0, 4.0 * l, 1.0, 0.0, -0.0, 1.0, 10000.0, 4.0] for l in range(3)], dtype=torch.float64)
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        v = env.vehicle
+        lane, si = int(rng.integers(3)), int(rng.integers(3))
+        x = float(rng.choice([-3.0, 0.0, 50.0, 9999.0, 10004.99, 10005.0, 10010.0]))
+        y = 4.0 * lane + float(rng.uniform(-2, 2))
+        v.position, v.lane_index, v.speed_index = np.array([x, y]), ("0", "1", lane), si
+        v.lane = env.road.network.get_lane(v.lane_index)
+        ref = sorted(set(env.action_type.get_available_actions()))
+        m = available_actions_mask(torch.tensor([x], dtype=torch.float64), torch.tensor([y], dtype=torch.float64),
+                                   torch.tensor([lane]), torch.tensor([si]), table, 3)[0].numpy()
+        assert sorted(np.nonzero(m)[0].tolist()) == ref, (lane, x, y, si)
