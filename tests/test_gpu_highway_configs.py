@@ -81,3 +81,24 @@ def test_observation_options(obs):
 ])
 def test_misc_options(over):
     run_case("highway-fast-v0", dict({"vehicles_count": 20}, **over), 16, 6, 900)
+
+
+def test_get_available_actions_on_device_state():
+    """env.get_available_actions(): bool [N, 5] from the device state (action.py:262-299)"""
+    import highwayenv_b200 as hb
+
+    env = hb.make("highway-fast-v0", num_envs=32, config={"lanes_count": 3})
+    env.reset(seed=0)
+    m = env.get_available_actions().cpu().numpy()
+    sd = env.state_dict()
+    lane, si = sd["lane"][:, 0], sd["speed_index"]
+    assert m.shape == (32, 5) and m[:, 1].all()
+    assert np.array_equal(m[:, 0], lane > 0) and np.array_equal(m[:, 2], lane < 2)
+    assert np.array_equal(m[:, 3], si < 2) and np.array_equal(m[:, 4], si > 0)
+    for _ in range(3):
+        env.step(np.full(32, 3, dtype=np.int32))  # FASTER (envs that crash meanwhile are reset: SameStep)
+    m = env.get_available_actions().cpu().numpy()
+    sd = env.state_dict()
+    lane, si = sd["lane"][:, 0], sd["speed_index"]
+    assert np.array_equal(m[:, 0], lane > 0) and np.array_equal(m[:, 2], lane < 2)
+    assert np.array_equal(m[:, 3], si < 2) and np.array_equal(m[:, 4], si > 0) and (si == 2).any()
