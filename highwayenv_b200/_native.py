@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("HWYB200_LIB") or os.path.join(_HERE, "csrc", "libhwyb200.so")
 
-HWY_ABI_VERSION = 5  # bump with every change of a struct or signature: a stale libhwyb200.so then fails to load
+HWY_ABI_VERSION = 7  # bump with every change of a struct or signature: a stale libhwyb200.so then fails to load
 HWY_MAX_LANES = 8
 HWY_MAX_TARGET_SPEEDS = 8
 HWY_MAX_VEHICLES = 128
@@ -121,7 +121,7 @@ class HwyNetState(C.Structure):
         ("pos", C.c_void_p), ("hs", C.c_void_p), ("tt", C.c_void_p), ("imp", C.c_void_p),
         ("delta", C.c_void_p), ("meta", C.c_void_p), ("route", C.c_void_p), ("route_len", C.c_void_p),
         ("speed_index", C.c_void_p), ("time", C.c_void_p), ("count", C.c_void_p), ("road_steps", C.c_void_p),
-        ("rng", C.c_void_p),
+        ("rng", C.c_void_p), ("overflow", C.c_void_p),
     ]
 
 
@@ -162,7 +162,39 @@ class HwyRoundaboutSpawn(C.Structure):
     ]
 
 
+FEAT_ON_ROAD, FEAT_UNKNOWN = 13, 14
+HWY_NET_MAX_ROUTE = 16
+
+
+class HwyObsView(C.Structure):
+    """Read-only view of a state of either family for the observation plugins (include/hwyb200.h)."""
+    _fields_ = [("n_envs", C.c_int32), ("vp", C.c_int32), ("n_vehicles", C.c_int32), ("n_agents", C.c_int32),
+                ("pos", C.c_void_p), ("hs", C.c_void_p), ("meta", C.c_void_p), ("count", C.c_void_p),
+                ("route", C.c_void_p), ("route_len", C.c_void_p), ("speed_index", C.c_void_p)]
+
+
+class HwyGridParams(C.Structure):
+    _fields_ = [("n_features", C.c_int32), ("features", C.c_int32 * HWY_MAX_OBS_FEATURES),
+                ("ranged", C.c_int32 * HWY_MAX_OBS_FEATURES),
+                ("range_lo", C.c_double * HWY_MAX_OBS_FEATURES), ("range_hi", C.c_double * HWY_MAX_OBS_FEATURES),
+                ("x_ranged", C.c_int32), ("y_ranged", C.c_int32),
+                ("x_lo", C.c_double), ("x_hi", C.c_double), ("y_lo", C.c_double), ("y_hi", C.c_double),
+                ("grid_lo", C.c_double * 2), ("grid_step", C.c_double * 2), ("shape", C.c_int32 * 2),
+                ("align_to_vehicle_axes", C.c_int32), ("clip", C.c_int32), ("as_image", C.c_int32),
+                ("observe_intentions", C.c_int32)]
+
+
+class HwyTtcParams(C.Structure):
+    _fields_ = [("horizon", C.c_int32), ("policy_frequency", C.c_int32), ("n_target_speeds", C.c_int32),
+                ("_pad", C.c_int32), ("target_speeds", C.c_double * HWY_MAX_TARGET_SPEEDS)]
+
+
+class HwyLidarParams(C.Structure):
+    _fields_ = [("cells", C.c_int32), ("normalize", C.c_int32), ("maximum_range", C.c_double)]
+
+
 EXPORTS = (
+    "hwy_observe_grid", "hwy_observe_ttc", "hwy_observe_lidar",
     "hwy_abi_version", "hwy_last_error", "hwy_highway_slot_stride", "hwy_highway_reset",
     "hwy_highway_observe", "hwy_highway_step", "hwy_highway_autoreset", "hwy_launch_count",
     "hwy_network_obs_size", "hwy_network_step", "hwy_network_observe", "hwy_roundabout_reset",
@@ -235,6 +267,13 @@ def load():
     lib.hwy_roundabout_reset.restype = C.c_int
     lib.hwy_roundabout_reset.argtypes = [NP, NG, C.POINTER(HwyRoundaboutSpawn), NS, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_void_p]
+    OV = C.POINTER(HwyObsView)
+    lib.hwy_observe_grid.restype = C.c_int
+    lib.hwy_observe_grid.argtypes = [NG, OV, C.POINTER(HwyGridParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.hwy_observe_ttc.restype = C.c_int
+    lib.hwy_observe_ttc.argtypes = [NG, OV, C.POINTER(HwyTtcParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.hwy_observe_lidar.restype = C.c_int
+    lib.hwy_observe_lidar.argtypes = [OV, C.POINTER(HwyLidarParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     if lib.hwy_abi_version() != HWY_ABI_VERSION:
         raise RuntimeError("libhwyb200.so ABI version mismatch; rebuild")
     _lib = lib

@@ -10,8 +10,8 @@ import subprocess
 import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = [os.path.join(_HERE, "csrc", "hwy_highway.cu"), os.path.join(_HERE, "csrc", "hwy_network.cu")]
-DEPS = SRC + [os.path.join(_HERE, "csrc", h) for h in ("hwy_math.cuh", "hwy_device.cuh", "hwy_abi.h")] + [
+SRC = [os.path.join(_HERE, "csrc", f) for f in ("hwy_highway.cu", "hwy_network.cu", "hwy_observe.cu")]
+DEPS = SRC + [os.path.join(_HERE, "csrc", h) for h in ("hwy_math.cuh", "hwy_device.cuh", "hwy_lanes.cuh", "hwy_abi.h")] + [
     os.path.join(os.path.dirname(_HERE), "include", "hwyb200.h")]
 OUT = os.path.join(_HERE, "csrc", "libhwyb200.so")
 

@@ -21,6 +21,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <mutex>
+
 #include <cuda_runtime.h>
 
 #include "../../include/hwyb200.h"
@@ -58,6 +61,7 @@ struct Frame {
     uint32_t fired[NW];                      // IDM vehicles whose lane-change timer will fire
     unsigned char lane[TPE], tgt[TPE], perm[TPE], rank[TPE];
     int slow;                                // ties in ls or unaligned lanes: use the linear scans
+    unsigned vmax_bits;                      // max(0, max speed) of the env, float bits rounded up (pruned sweep bound)
 };
 
 template <int TPE>
@@ -387,7 +391,10 @@ __device__ __forceinline__ void publish(const HwyHighwayParams& P, Frame<TPE>& F
         F.tgt[i] = (unsigned char)meta_target(r.meta);
     }
     if (i < HWY_MAX_LANES * NW) (&F.smask[0][0])[i] = 0;
-    if (i == 0) F.slow = 0;
+    if (i == 0) {
+        F.slow = 0;
+        F.vmax_bits = 0u;
+    }
 }
 
 // Collision test of the pair a < b on the staged positions (vehicle/objects.py:92-138):
@@ -442,7 +449,7 @@ __device__ __noinline__ void pair_sat(const Frame<TPE>& F, int a, int b, double 
 template <int TPE>
 __device__ __forceinline__ void build_frame(const HwyHighwayParams& P, EnvShared<TPE>& sm, Frame<TPE>& F,
                                             int i, bool active, bool aligned, const VehicleRegs& r,
-                                            double dt, bool do_sweep) {
+                                            double dt, bool do_sweep, bool pruned) {
     const int V = P.n_vehicles;
     const int wie = i >> 5;  // warp within the env
     const int lane = meta_lane(r.meta), tgt = meta_target(r.meta);
@@ -505,7 +512,14 @@ __device__ __forceinline__ void build_frame(const HwyHighwayParams& P, EnvShared
     // -- collision sweep, pass 1: every gated pair once.  A pair with exactly one
     // check_collisions side is taken by the other side's thread (so the controlled vehicle's
     // pairs are spread over the block); pairs of two checking vehicles are dealt round-robin.
-    if (active && do_sweep) {
+    if (do_sweep && pruned) {
+        // many checking vehicles (highway-v0: all of them): the sweep runs after the next barrier over the
+        // rank-neighbours only (sweep_pruned); here just the env's speed bound.  Non-negative floats order
+        // like their bit patterns.
+        unsigned vb = __float_as_uint(active ? fmaxf(__double2float_ru(r.speed), 0.0f) : 0.0f);
+        vb = __reduce_max_sync(0xffffffffu, vb);
+        if ((i & 31) == 0) atomicMax(&F.vmax_bits, vb);
+    } else if (active && do_sweep) {
         const bool cc_i = test_bit(sm.cc, i);
         auto do_pair = [&](int a, int b) {
             if (!pair_precheck(F, a, b, dt)) return;
@@ -536,6 +550,37 @@ __device__ __forceinline__ void build_frame(const HwyHighwayParams& P, EnvShared
                 do_pair(i < j ? i : j, i < j ? j : i);
             }
         }
+    }
+}
+
+// Collision sweep, pass 1, rank-pruned form (after the barrier that follows build_frame).  The frame holds every
+// vehicle's rank along the road (s = projection on lane 0's unit direction, ties broken by slot), and
+// |s_b - s_a| <= ||p_b - p_a||, so a pair whose s-gap exceeds the largest possible reject threshold
+// diag + max(v) dt of vehicle/objects.py:122-138 fails that sphere pre-check too: scanning the rank-neighbours
+// upwards until the gap exceeds the bound visits exactly the pairs the all-pairs sweep can accept (plus a few it
+// rejects itself).  Every unordered pair is met once, from its lower-ranked member.
+template <int TPE>
+__device__ __forceinline__ void sweep_pruned(EnvShared<TPE>& sm, const Frame<TPE>& F, int V, int i, bool active,
+                                             double dt) {
+    if (!active) return;
+    const double diag = sqrt(kVehLength * kVehLength + kVehWidth * kVehWidth);
+    const double bound = diag + (double)__uint_as_float(F.vmax_bits) * dt + 1e-6;  // >= thr of any pair, + rounding of s
+    const bool cc_i = test_bit(sm.cc, i);
+    const double si = F.ls[i];
+    for (int q = F.rank[i] + 1; q < V; ++q) {
+        const int j = F.perm[q];
+        if (F.ls[j] - si > bound) break;
+        if (!(cc_i || test_bit(sm.cc, j))) continue;  // handle_collisions' gate (objects.py:99-100)
+        const int a = i < j ? i : j, b = i < j ? j : i;
+        if (!pair_precheck(F, a, b, dt)) continue;
+        bool inter, will;
+        double trx, try_;
+        pair_sat(F, a, b, dt, inter, will, trx, try_);
+        if (will) {
+            atomicMax(&sm.last_will[a], b);
+            atomicMax(&sm.last_will[b], a);
+        }
+        if (inter) sm.crash_hit[a] = sm.crash_hit[b] = 1;
     }
 }
 
@@ -583,18 +628,6 @@ __device__ __forceinline__ U128 add128(U128 a, U128 b) {
     r.lo = a.lo + b.lo;
     r.hi = a.hi + b.hi + (r.lo < a.lo ? 1 : 0);
     return r;
-}
-__global__ void pcg_jump_init_kernel() {
-    const U128 A = {0x2360ed051fc65da4ULL, 0x4385df649fccf645ULL};
-    U128 an = {0, 1}, gn = {0, 0};
-    for (int n = 0; n < kPcgJumpN; ++n) {
-        g_pcg_jump[n][0] = an.hi;
-        g_pcg_jump[n][1] = an.lo;
-        g_pcg_jump[n][2] = gn.hi;
-        g_pcg_jump[n][3] = gn.lo;
-        gn = add128(mul128(gn, A), U128{0, 1});  // G_{n+1} = G_n * A + 1
-        an = mul128(an, A);
-    }
 }
 // generator positioned so that its next next64() returns output number n of the stream `g0`
 __device__ __forceinline__ Pcg64 pcg_at(const Pcg64& g0, int n) {
@@ -841,6 +874,9 @@ highway_step_kernel(const __grid_constant__ HwyHighwayParams P, const HwyHighway
         if (active) sm.delta[i] = r.delta;
     }
     const IdmK K = make_idm(P);
+    // all-pairs gate (every vehicle checks collisions): rank-pruned sweep; a single checking vehicle (highway-fast)
+    // already costs one pre-check per thread
+    const bool pruned = P.others_check_collisions != 0;
     int p = 1;
     PHASE_INIT();
     PHASE_MARK(0);  // load + static masks
@@ -858,8 +894,12 @@ highway_step_kernel(const __grid_constant__ HwyHighwayParams P, const HwyHighway
         if (i == 0) sm.n_items = 0;
         // frame 0: masks only — the sweep of the stored state ran at the end of the substep that
         // produced it (previous launch).  Later: Road.step's sweep (road/road.py:477-481).
-        build_frame(P, sm, F, i, active, aligned, r, dt, frame > 0);
+        build_frame(P, sm, F, i, active, aligned, r, dt, frame > 0, pruned);
         PHASE_MARK(3);  // ranks, masks, sweep pass 1
+        if (pruned && frame > 0) {  // uniform over the grid
+            env_sync<TPE>();
+            sweep_pruned(sm, F, V, i, active, dt);
+        }
         env_sync<TPE>();
         PHASE_MARK(4);  // barrier after build
         if (active && frame > 0) apply_collisions(sm, F, i, r, dt);
@@ -1396,16 +1436,36 @@ int step_envs_per_block(int tpe, int n_envs) {
     return epb;
 }
 
-// One-time (per device) fill of the PCG64 jump table used by the fused autoreset.
+// One-time (per device) fill of the PCG64 jump table used by the fused autoreset.  The table is computed on
+// the host and copied with a synchronous cudaMemcpyToSymbol under a mutex, so it is complete before any kernel
+// of any stream that is launched afterwards; hwy_highway_reset calls this too, i.e. the table exists before the
+// first step.  A first call from a capturing stream is refused (the copy cannot be captured).
 int ensure_pcg_jump(cudaStream_t st) {
+    static std::mutex mu;
     static bool ready[64] = {false};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return fail("%s", "cudaGetDevice failed");
-    if (!ready[dev]) {
-        hwy::pcg_jump_init_kernel<<<1, 1, 0, st>>>();
-        if (check_launch("pcg_jump_init_kernel")) return 1;
-        ready[dev] = true;
+    std::lock_guard<std::mutex> lock(mu);
+    if (ready[dev]) return 0;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (st && cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone)
+        return fail("%s", "PCG64 jump table not initialised on this device: call hwy_highway_reset (or one eager "
+                          "step) before capturing a step into a CUDA graph");
+    static uint64_t table[hwy::kPcgJumpN][4];
+    typedef unsigned __int128 u128;
+    const u128 A = ((u128)0x2360ed051fc65da4ULL << 64) | 0x4385df649fccf645ULL;
+    u128 an = 1, gn = 0;
+    for (int n = 0; n < hwy::kPcgJumpN; ++n) {
+        table[n][0] = (uint64_t)(an >> 64);
+        table[n][1] = (uint64_t)an;
+        table[n][2] = (uint64_t)(gn >> 64);
+        table[n][3] = (uint64_t)gn;
+        gn = gn * A + 1;  // G_{n+1} = G_n * A + 1
+        an = an * A;
     }
+    cudaError_t err = cudaMemcpyToSymbol(hwy::g_pcg_jump, table, sizeof(table));
+    if (err != cudaSuccess) return fail("cudaMemcpyToSymbol(g_pcg_jump): %s", cudaGetErrorString(err));
+    ready[dev] = true;
     return 0;
 }
 
@@ -1416,12 +1476,15 @@ int launch_step(const HwyHighwayParams* p, const HwyHighwayState* s, const int32
                 float* final_obs, int blocks, int epb, cudaStream_t st) {
     if (autoreset && ensure_pcg_jump(st)) return 1;
     size_t smem = (size_t)epb * sizeof(hwy::EnvShared<TPE>);
-    static thread_local size_t configured = 0;
-    if (smem > configured) {
+    // the attribute is per device (and per template instance): cache it by device ordinal
+    static std::atomic<size_t> configured[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return fail("%s", "cudaGetDevice failed");
+    if (smem > configured[dev].load(std::memory_order_relaxed)) {
         cudaError_t err = cudaFuncSetAttribute(hwy::highway_step_kernel<TPE>,
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return fail("cudaFuncSetAttribute: %s", cudaGetErrorString(err));
-        configured = smem;
+        configured[dev].store(smem, std::memory_order_relaxed);
     }
     hwy::highway_step_kernel<TPE><<<blocks, TPE * epb, smem, st>>>(
         *p, *s, action_i, action_f, obs, reward, terminated, truncated, info_speed, info_crashed,
@@ -1468,6 +1531,7 @@ int hwy_highway_reset(const HwyHighwayParams* p, const HwyHighwayState* s, const
     if (validate(p, s)) return 1;
     cudaStream_t st = (cudaStream_t)stream;
     int use_mask = mask != nullptr;
+    if (ensure_pcg_jump(st)) return 1;  // the fused autoreset of later steps reads the table
     if (launch_reset(p, s, mask, nullptr, use_mask, st)) return 1;
     if (obs) return launch_observe(p, s, mask, nullptr, use_mask, obs, st);
     return 0;

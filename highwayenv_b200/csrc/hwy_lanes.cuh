@@ -1,0 +1,135 @@
+// hwy_lanes.cuh — lane geometry of a general road network (road/lane.py: StraightLane, SineLane, CircularLane) and the
+// shared-memory copy of the lane table, shared by the step kernels (hwy_network.cu) and the observation plugins
+// (hwy_observe.cu).  Reference paths are relative to /root/reference/highway_env.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/hwyb200.h"
+#include "hwy_device.cuh"
+#include "hwy_math.cuh"
+
+namespace hwynet {
+using namespace hwy;
+
+struct GraphShared {
+    int n_lanes, n_nodes;
+    HwyNetLane lanes[HWY_NET_MAX_LANES];
+    int succ_count[HWY_NET_MAX_NODES];
+    int succ[HWY_NET_MAX_NODES][HWY_NET_MAX_SUCC];
+};
+
+// ------------------------------------------------------------------ lanes (road/lane.py)
+// local_coordinates: StraightLane :205-209, SineLane :285-289, CircularLane :351-358
+// `gate`: callers that go on to test on_lane(.., margin) (lane.py:100-118) pass width/2 + margin; the lateral
+// offset is computed first and the longitudinal one (an atan2 on a CircularLane) only when |lat| <= gate.
+// Returns false (s untouched) when the lateral test already fails.  gate = +inf: plain local_coordinates.
+static __device__ __noinline__ bool lane_local_gated(const HwyNetLane& L, double x, double y, double gate, double& s,
+                                              double& lat) {
+    if (L.type == HWY_LANE_CIRCULAR) {
+        double ddx = x - L.cx, ddy = y - L.cy;
+        double r = norm2(ddx, ddy);
+        lat = L.direction * (L.radius - r);
+        if (!(fabs(lat) <= gate)) return false;
+        double phi = atan2(ddy, ddx);
+        phi = L.start_phase + wrap_to_pi(phi - L.start_phase);
+        s = L.direction * (phi - L.start_phase) * L.radius;
+        return true;
+    }
+    double ddx = x - L.sx, ddy = y - L.sy;
+    double la = dot2(ddx, ddy, L.lx, L.ly);
+    if (L.type != HWY_LANE_SINE && !(fabs(la) <= gate)) {
+        lat = la;
+        return false;
+    }
+    double lon = dot2(ddx, ddy, L.dx, L.dy);
+    if (L.type == HWY_LANE_SINE) la = la - L.amplitude * m_sin(L.pulsation * lon + L.phase);
+    s = lon;
+    lat = la;
+    return fabs(la) <= gate;
+}
+__device__ __forceinline__ void lane_local(const HwyNetLane& L, double x, double y, double& s, double& lat) {
+    lane_local_gated(L, x, y, INFINITY, s, lat);
+}
+// position: StraightLane :192-197, SineLane :268-273, CircularLane :338-342
+static __device__ __noinline__ void lane_position(const HwyNetLane& L, double s, double lat, double& x, double& y) {
+    if (L.type == HWY_LANE_CIRCULAR) {
+        double phi = L.direction * s / L.radius + L.start_phase;
+        double rr = L.radius - lat * L.direction;
+        double sn, cs;
+        m_sincos(phi, &sn, &cs);
+        x = L.cx + rr * cs;
+        y = L.cy + rr * sn;
+        return;
+    }
+    if (L.type == HWY_LANE_SINE) lat = lat + L.amplitude * m_sin(L.pulsation * s + L.phase);
+    x = (L.sx + s * L.dx) + lat * L.lx;
+    y = (L.sy + s * L.dy) + lat * L.ly;
+}
+// heading_at: StraightLane :199-200, SineLane :275-280, CircularLane :344-347
+static __device__ __noinline__ double lane_heading_at(const HwyNetLane& L, double s) {
+    if (L.type == HWY_LANE_CIRCULAR) {
+        double phi = L.direction * s / L.radius + L.start_phase;
+        return phi + kPi / 2 * L.direction;
+    }
+    if (L.type == HWY_LANE_SINE) {
+        double sn, cs;
+        m_sincos(L.pulsation * s + L.phase, &sn, &cs);
+        return L.heading + m_atan(L.amplitude * L.pulsation * cs);
+    }
+    return L.heading;
+}
+__device__ __forceinline__ double lane_s_of(const HwyNetLane& L, double x, double y) {
+    double s, lat;
+    lane_local(L, x, y, s, lat);
+    return s;
+}
+__device__ __forceinline__ bool lane_on(const HwyNetLane& L, double s, double lat, double margin) {
+    return fabs(lat) <= L.width / 2 + margin && -kLaneVehLength <= s && s < L.length + kLaneVehLength;
+}
+__device__ __forceinline__ bool lane_reachable(const HwyNetLane& L, double x, double y) {
+    if (L.forbidden) return false;
+    double s, lat;
+    lane_local(L, x, y, s, lat);
+    return fabs(lat) <= 2 * L.width && 0 <= s && s < L.length + kLaneVehLength;
+}
+// :127-130 distance
+__device__ __forceinline__ double lane_distance(const HwyNetLane& L, double x, double y) {
+    double s, r;
+    lane_local(L, x, y, s, r);
+    return fabs(r) + fmax(s - L.length, 0.0) + fmax(0.0 - s, 0.0);
+}
+// :132-147 distance_with_heading
+__device__ __forceinline__ double lane_distance_with_heading(const HwyNetLane& L, double x, double y, double h,
+                                                             double& s, double& r) {
+    lane_local(L, x, y, s, r);
+    double angle = fabs(wrap_to_pi(h - lane_heading_at(L, s)));
+    return fabs(r) + fmax(s - L.length, 0.0) + fmax(0.0 - s, 0.0) + 1.0 * angle;
+}
+
+#define RT_FROM(e) ((e)&0xff)
+#define RT_TO(e) (((e) >> 8) & 0xff)
+#define RT_ID(e) ((((e) >> 16) & 0xff) - 1)
+
+__device__ __forceinline__ int road_first(const GraphShared& g, int from, int to) {
+    for (int k = 0; k < g.succ_count[from]; ++k) {
+        int f = g.succ[from][k];
+        if (g.lanes[f].to_node == to) return f;
+    }
+    return -1;
+}
+
+__device__ __forceinline__ double lane_distance_with_heading(const HwyNetLane& L, double x, double y,
+                                                             double h) {
+    double s, r;
+    return lane_distance_with_heading(L, x, y, h, s, r);
+}
+
+__device__ __forceinline__ void stage_graph(GraphShared& gs, const HwyNetGraph* __restrict__ graph) {
+    static_assert(sizeof(GraphShared) == sizeof(HwyNetGraph), "layout");
+    const int* src = reinterpret_cast<const int*>(graph);
+    int* dst = reinterpret_cast<int*>(&gs);
+    for (int k = threadIdx.x; k < (int)(sizeof(HwyNetGraph) / sizeof(int)); k += blockDim.x) dst[k] = src[k];
+    __syncthreads();
+}
+
+}  // namespace hwynet

@@ -24,6 +24,7 @@
 #include "hwy_abi.h"
 #include "hwy_device.cuh"
 #include "hwy_math.cuh"
+#include "hwy_lanes.cuh"
 
 namespace hwynet {
 using namespace hwy;
@@ -32,13 +33,6 @@ constexpr int R = HWY_NET_MAX_ROUTE;
 constexpr int kBlockThreads = 256;
 constexpr int kPred = 11;  // np.arange(0.25, 3, 0.25) prediction points of RegulatedRoad.is_conflict_possible
 constexpr int kPredChunk = 4;  // horizon points staged in shared memory at a time
-
-struct GraphShared {
-    int n_lanes, n_nodes;
-    HwyNetLane lanes[HWY_NET_MAX_LANES];
-    int succ_count[HWY_NET_MAX_NODES];
-    int succ[HWY_NET_MAX_NODES][HWY_NET_MAX_SUCC];
-};
 
 template <int G>
 __host__ __device__ constexpr int kCand() {
@@ -79,112 +73,6 @@ struct EnvStage {
     // RegulatedRoad: predicted (x, y, heading) of every vehicle at kPredChunk horizon points at a time
     double pred[REG ? G : 1][REG ? kPredChunk : 1][3];
 };
-
-// ------------------------------------------------------------------ lanes (road/lane.py)
-// local_coordinates: StraightLane :205-209, SineLane :285-289, CircularLane :351-358
-// `gate`: callers that go on to test on_lane(.., margin) (lane.py:100-118) pass width/2 + margin; the lateral
-// offset is computed first and the longitudinal one (an atan2 on a CircularLane) only when |lat| <= gate.
-// Returns false (s untouched) when the lateral test already fails.  gate = +inf: plain local_coordinates.
-__device__ __noinline__ bool lane_local_gated(const HwyNetLane& L, double x, double y, double gate, double& s,
-                                              double& lat) {
-    if (L.type == HWY_LANE_CIRCULAR) {
-        double ddx = x - L.cx, ddy = y - L.cy;
-        double r = norm2(ddx, ddy);
-        lat = L.direction * (L.radius - r);
-        if (!(fabs(lat) <= gate)) return false;
-        double phi = atan2(ddy, ddx);
-        phi = L.start_phase + wrap_to_pi(phi - L.start_phase);
-        s = L.direction * (phi - L.start_phase) * L.radius;
-        return true;
-    }
-    double ddx = x - L.sx, ddy = y - L.sy;
-    double la = dot2(ddx, ddy, L.lx, L.ly);
-    if (L.type != HWY_LANE_SINE && !(fabs(la) <= gate)) {
-        lat = la;
-        return false;
-    }
-    double lon = dot2(ddx, ddy, L.dx, L.dy);
-    if (L.type == HWY_LANE_SINE) la = la - L.amplitude * m_sin(L.pulsation * lon + L.phase);
-    s = lon;
-    lat = la;
-    return fabs(la) <= gate;
-}
-__device__ __forceinline__ void lane_local(const HwyNetLane& L, double x, double y, double& s, double& lat) {
-    lane_local_gated(L, x, y, INFINITY, s, lat);
-}
-// position: StraightLane :192-197, SineLane :268-273, CircularLane :338-342
-__device__ __noinline__ void lane_position(const HwyNetLane& L, double s, double lat, double& x, double& y) {
-    if (L.type == HWY_LANE_CIRCULAR) {
-        double phi = L.direction * s / L.radius + L.start_phase;
-        double rr = L.radius - lat * L.direction;
-        double sn, cs;
-        m_sincos(phi, &sn, &cs);
-        x = L.cx + rr * cs;
-        y = L.cy + rr * sn;
-        return;
-    }
-    if (L.type == HWY_LANE_SINE) lat = lat + L.amplitude * m_sin(L.pulsation * s + L.phase);
-    x = (L.sx + s * L.dx) + lat * L.lx;
-    y = (L.sy + s * L.dy) + lat * L.ly;
-}
-// heading_at: StraightLane :199-200, SineLane :275-280, CircularLane :344-347
-__device__ __noinline__ double lane_heading_at(const HwyNetLane& L, double s) {
-    if (L.type == HWY_LANE_CIRCULAR) {
-        double phi = L.direction * s / L.radius + L.start_phase;
-        return phi + kPi / 2 * L.direction;
-    }
-    if (L.type == HWY_LANE_SINE) {
-        double sn, cs;
-        m_sincos(L.pulsation * s + L.phase, &sn, &cs);
-        return L.heading + m_atan(L.amplitude * L.pulsation * cs);
-    }
-    return L.heading;
-}
-__device__ __forceinline__ double lane_s_of(const HwyNetLane& L, double x, double y) {
-    double s, lat;
-    lane_local(L, x, y, s, lat);
-    return s;
-}
-__device__ __forceinline__ bool lane_on(const HwyNetLane& L, double s, double lat, double margin) {
-    return fabs(lat) <= L.width / 2 + margin && -kLaneVehLength <= s && s < L.length + kLaneVehLength;
-}
-__device__ __forceinline__ bool lane_reachable(const HwyNetLane& L, double x, double y) {
-    if (L.forbidden) return false;
-    double s, lat;
-    lane_local(L, x, y, s, lat);
-    return fabs(lat) <= 2 * L.width && 0 <= s && s < L.length + kLaneVehLength;
-}
-// :127-130 distance
-__device__ __forceinline__ double lane_distance(const HwyNetLane& L, double x, double y) {
-    double s, r;
-    lane_local(L, x, y, s, r);
-    return fabs(r) + fmax(s - L.length, 0.0) + fmax(0.0 - s, 0.0);
-}
-// :132-147 distance_with_heading
-__device__ __forceinline__ double lane_distance_with_heading(const HwyNetLane& L, double x, double y, double h,
-                                                             double& s, double& r) {
-    lane_local(L, x, y, s, r);
-    double angle = fabs(wrap_to_pi(h - lane_heading_at(L, s)));
-    return fabs(r) + fmax(s - L.length, 0.0) + fmax(0.0 - s, 0.0) + 1.0 * angle;
-}
-
-#define RT_FROM(e) ((e)&0xff)
-#define RT_TO(e) (((e) >> 8) & 0xff)
-#define RT_ID(e) ((((e) >> 16) & 0xff) - 1)
-
-__device__ __forceinline__ int road_first(const GraphShared& g, int from, int to) {
-    for (int k = 0; k < g.succ_count[from]; ++k) {
-        int f = g.succ[from][k];
-        if (g.lanes[f].to_node == to) return f;
-    }
-    return -1;
-}
-
-__device__ __forceinline__ double lane_distance_with_heading(const HwyNetLane& L, double x, double y,
-                                                             double h) {
-    double s, r;
-    return lane_distance_with_heading(L, x, y, h, s, r);
-}
 
 // road/road.py:138-157 next_lane_given_next_road (next_id < 0 == None)
 __device__ __forceinline__ int next_lane_given_next_road(const GraphShared& g, int cur, int next_first,
@@ -849,14 +737,6 @@ __device__ __forceinline__ void publish(EnvStage<G, REG>& st, int i, const Regs&
     st.ts[i] = r.target_speed;
 }
 
-__device__ __forceinline__ void stage_graph(GraphShared& gs, const HwyNetGraph* __restrict__ graph) {
-    static_assert(sizeof(GraphShared) == sizeof(HwyNetGraph), "layout");
-    const int* src = reinterpret_cast<const int*>(graph);
-    int* dst = reinterpret_cast<int*>(&gs);
-    for (int k = threadIdx.x; k < (int)(sizeof(HwyNetGraph) / sizeof(int)); k += blockDim.x) dst[k] = src[k];
-    __syncthreads();
-}
-
 
 // ------------------------------------------------------------------ RegulatedRoad (road/regulation.py)
 __device__ __forceinline__ int HwyNetLane_route(const HwyNetLane& L) {
@@ -1499,7 +1379,10 @@ network_step_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGraph* _
         if (i == 0) {
             Pcg64 rng = load_rng(S.rng, (size_t)S.n_envs, e);
             spawn_vehicle(P, SP, g, st, rng, keep_mask, 0.0, 1.0, 1.0, SP.spawn_probability, false);
-            if (n_keep >= G) st.sp_ok = 0;  // slot capacity (never reached: the reference peaks at ~15)
+            if (n_keep >= G && st.sp_ok) {  // every slot taken: the spawn is dropped, LOUDLY (the reference's list
+                st.sp_ok = 0;               // is unbounded; it peaks at ~15-23 vehicles within the default 13 s)
+                if (env_ok && S.overflow) S.overflow[e] += 1;
+            }
             if (env_ok) store_rng(S.rng, (size_t)S.n_envs, e, rng);
         }
         group_sync<G>();
@@ -1696,7 +1579,10 @@ intersection_reset_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGr
             // _make_vehicles calls _spawn_vehicle(longitudinal) with the FUNCTION default spawn_probability = 0.6
             // (intersection_env.py:268,331), not config["spawn_probability"] (used by the per-step spawn, :139)
             spawn_vehicle(P, SP, g, st, rng, present, (double)t * (80.0 / (double)(n0 - 1)), 1.0, 1.0, 0.6, false);
-            if (st.count >= G) st.sp_ok = 0;
+            if (st.count >= G && st.sp_ok) {
+                st.sp_ok = 0;
+                if (selected && S.overflow) S.overflow[e] += 1;
+            }
         }
         commit(HWY_KIND_IDM);
     }
@@ -1709,7 +1595,10 @@ intersection_reset_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGr
     if (i == 0) {
         const unsigned present = st.count >= 32 ? 0xffffffffu : ((1u << st.count) - 1u);
         spawn_vehicle(P, SP, g, st, rng, present, 60.0, 0.1, 0.0, 1.0, true);
-        if (st.count >= G) st.sp_ok = 0;
+        if (st.count >= G && st.sp_ok) {
+            st.sp_ok = 0;
+            if (selected && S.overflow) S.overflow[e] += 1;
+        }
     }
     commit(HWY_KIND_IDM);
     // ---- :291-315  the controlled vehicles, one per access road ("o{k}", "ir{k}", 0), k = agent % 4
@@ -1736,6 +1625,7 @@ intersection_reset_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGr
             st.speed_index = speed_to_index(P, st.sp_speed);  // MDPVehicle.__init__ (controller.py:283-293)
             st.sp_ts = P.target_speeds[st.speed_index];
             st.sp_ok = st.count < G ? 1 : 0;
+            if (!st.sp_ok && selected && S.overflow) S.overflow[e] += 1;
             if (agent == 0) st.ego = st.count;
         }
         commit(HWY_KIND_MDP);

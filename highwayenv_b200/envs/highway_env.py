@@ -50,6 +50,7 @@ class BatchedHighwayEnv:
     metadata = {"render_modes": [], "autoreset_mode": "SameStep"}
 
     PERCEPTION_DISTANCE = 5.0 * 40.0  # abstract.py:56
+    _kernel_events = None  # bench.py hook: list of (start, end) CUDA events around the step kernels
 
     @classmethod
     def default_config(cls) -> dict:
@@ -279,6 +280,10 @@ class BatchedHighwayEnv:
         ai = act.data_ptr() if self._params.action_type == 0 else None
         af = act.data_ptr() if self._params.action_type == 1 else None
         same_step = self.autoreset_mode == "SameStep"
+        kev = self._kernel_events
+        if kev is not None:  # bench.py: CUDA events around the step kernel(s) alone
+            kev.append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
+            kev[-1][0].record(torch.cuda.current_stream(self.device))
         with torch.cuda.device(self.device):
             N.check(self._lib.hwy_highway_step(
                 C.byref(self._params), C.byref(self._state), ai, af, self._obs.data_ptr(),
@@ -286,6 +291,8 @@ class BatchedHighwayEnv:
                 self._info_speed.data_ptr(), self._info_crashed.data_ptr(),
                 N.AUTORESET_SAME_STEP if same_step else N.AUTORESET_DISABLED,
                 self._final_obs.data_ptr() if same_step else None, self._stream()))
+        if kev is not None:
+            kev[-1][1].record(torch.cuda.current_stream(self.device))
         info = {"speed": self._info_speed, "crashed": self._info_crashed.view(torch.bool), "action": act}
         if same_step:
             info["final_obs"] = self._final_obs
@@ -443,6 +450,10 @@ class HostStepper:
         table = getattr(env.action_type, "table", None)
         if table is not None:
             raise NotImplementedError("host_stepper with DiscreteAction (index gather) — use env.step")
+        if env.autoreset_mode == "NextStep":
+            # NextStep runs host-side control flow per call (which envs ended last time); a captured graph would
+            # replay one frozen decision
+            raise NotImplementedError("host_stepper with autoreset_mode='NextStep' — use SameStep or Disabled")
         pin = lambda t: torch.empty(tuple(t.shape), dtype=t.dtype).pin_memory()  # noqa: E731
         self._h_actions = pin(env._action_buf)
         self._h_obs, self._h_reward = pin(env._obs), pin(env._reward)

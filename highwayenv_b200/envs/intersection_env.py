@@ -73,6 +73,7 @@ _F64 = ("x", "y", "heading", "speed", "target_speed", "timer", "delta", "impact_
 class BatchedIntersectionEnv:
     ENV_ID = "intersection-v0"
     MULTI_AGENT_WRAPPER = False
+    _kernel_events = None  # bench.py hook: list of (start, end) CUDA events around the step kernels
     metadata = {"render_modes": [], "autoreset_mode": "SameStep"}
 
     @classmethod
@@ -232,7 +233,11 @@ class BatchedIntersectionEnv:
         self._time = z(n, dtype=torch.float64)
         self._count = z(n, dtype=torch.int32)
         self._road_steps = z(n, dtype=torch.int32)
+        self._overflow = z(n, dtype=torch.int32)  # spawns dropped because all 32 slots were taken (loud, see step())
+        old_rng = getattr(self, "_rng", None)  # keep the env's numpy stream across a re-allocation
         self._rng = z(5, n, dtype=torch.int64)
+        if old_rng is not None and old_rng.shape == self._rng.shape:
+            self._rng.copy_(old_rng)
         self._obs = z(n, *self.obs_shape, dtype=torch.float32)
         self._final_obs = z(n, *self.obs_shape, dtype=torch.float32)
         self._reward = z(n, dtype=torch.float64)
@@ -246,6 +251,7 @@ class BatchedIntersectionEnv:
         st.route, st.route_len = self._route.data_ptr(), self._route_len.data_ptr()
         st.speed_index, st.time = self._speed_index.data_ptr(), self._time.data_ptr()
         st.count, st.road_steps, st.rng = self._count.data_ptr(), self._road_steps.data_ptr(), self._rng.data_ptr()
+        st.overflow = self._overflow.data_ptr()
         self._state = st
         # plan_route_to(lane, "o"+k) for every lane (vehicle/controller.py:71-87)
         n_l = len(self.net.lanes)
@@ -508,12 +514,19 @@ class BatchedIntersectionEnv:
         if isinstance(actions, torch.Tensor) and actions.device == buf.device and actions.dtype == buf.dtype \
                 and actions.shape == buf.shape and actions.is_contiguous():
             act = actions
+        elif isinstance(actions, torch.Tensor):  # dtype / device conversion without a host round trip
+            buf.copy_(actions.reshape(buf.shape), non_blocking=True)
+            act = buf
         else:
-            a = actions.cpu().numpy() if isinstance(actions, torch.Tensor) else np.asarray(actions)
+            a = np.asarray(actions)
             buf.copy_(torch.from_numpy(np.ascontiguousarray(a.reshape(tuple(buf.shape)))).to(buf.dtype), non_blocking=True)
             act = buf
         prev = getattr(self, "_autoreset_envs", None) if self.autoreset_mode == "NextStep" else None
         rng_before = self._rng.clone() if prev is not None else None  # a step draws from the env's generator
+        kev = self._kernel_events
+        if kev is not None:  # bench.py: CUDA events around the step kernel(s) alone
+            kev.append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
+            kev[-1][0].record(torch.cuda.current_stream(self.device))
         with torch.cuda.device(self.device):
             N.check(self._lib.hwy_intersection_step_agents(
                 C.byref(self._params), self._graph_dev.data_ptr(), C.byref(self._spawn_struct), C.byref(self._state),
@@ -521,7 +534,13 @@ class BatchedIntersectionEnv:
                 self._truncated.data_ptr(), self._info_speed.data_ptr(), self._info_crashed.data_ptr(),
                 self._agents_reward.data_ptr() if self.multi_agent else None,
                 self._agents_terminated.data_ptr() if self.multi_agent else None, self._stream()))
-        info = {"speed": self._info_speed, "crashed": self._info_crashed.view(torch.bool), "action": act}
+        if kev is not None:
+            kev[-1][1].record(torch.cuda.current_stream(self.device))
+        # "spawn_overflow" [N] int32: how many accepted spawns found all 32 vehicle slots of the env taken since the env
+        # was constructed.  The reference's vehicle list is unbounded; a non-zero entry means that env no longer
+        # follows the reference (reachable only with `duration` >> 13 s or a high spawn_probability).
+        info = {"speed": self._info_speed, "crashed": self._info_crashed.view(torch.bool), "action": act,
+                "spawn_overflow": self._overflow}
         if self.multi_agent:  # IntersectionEnv._info (:124-132)
             info["agents_rewards"] = self._agents_reward
             info["agents_terminated"] = self._agents_terminated.view(torch.bool)

@@ -160,6 +160,7 @@ class TimeToCollisionObservation:
 class BatchedRoundaboutEnv:
     ENV_ID = "roundabout-v0"
     N_VEHICLES = 5
+    _kernel_events = None  # bench.py hook: list of (start, end) CUDA events around the step kernels
     metadata = {"render_modes": [], "autoreset_mode": "SameStep"}
 
     @classmethod
@@ -286,7 +287,12 @@ class BatchedRoundaboutEnv:
         self._info_speed = z(n, dtype=torch.float64)
         self._info_crashed = z(n, dtype=torch.uint8)
         self._action_buf = z(n, dtype=torch.int32)
-        self._rng = z(5, n, dtype=torch.int64)  # numpy PCG64 words (device reset mode)
+        # numpy PCG64 words (device reset mode).  A re-allocation (reset(options={"config": ...})) must keep the
+        # env's stream: the reference's np_random survives a reset without a seed (abstract.py:219-249)
+        old_rng = getattr(self, "_rng", None)
+        self._rng = z(5, n, dtype=torch.int64)
+        if old_rng is not None and old_rng.shape == self._rng.shape:
+            self._rng.copy_(old_rng)
         self._build_spawn_tables()
         st = N.HwyNetState()
         st.n_envs, st.vp = n, vp
@@ -411,16 +417,25 @@ class BatchedRoundaboutEnv:
         if isinstance(actions, torch.Tensor) and actions.device == buf.device and actions.dtype == buf.dtype \
                 and actions.shape == buf.shape and actions.is_contiguous():
             act = actions
-        else:
-            buf.copy_(torch.as_tensor(np.asarray(actions.cpu() if isinstance(actions, torch.Tensor) else actions))
-                      .reshape(buf.shape).to(buf.dtype), non_blocking=True)
+        elif isinstance(actions, torch.Tensor):  # dtype / device conversion without a host round trip
+            buf.copy_(actions.reshape(buf.shape), non_blocking=True)
             act = buf
+        else:
+            buf.copy_(torch.from_numpy(np.ascontiguousarray(np.asarray(actions).reshape(tuple(buf.shape))))
+                      .to(buf.dtype), non_blocking=True)
+            act = buf
+        kev = self._kernel_events
+        if kev is not None:  # bench.py: CUDA events around the step kernel(s) alone
+            kev.append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
+            kev[-1][0].record(torch.cuda.current_stream(self.device))
         with torch.cuda.device(self.device):
             N.check(self._lib.hwy_network_step(
                 C.byref(self._params), self._graph_dev.data_ptr(), C.byref(self._state), act.data_ptr(),
                 self._obs.data_ptr(), self._reward.data_ptr(), self._terminated.data_ptr(),
                 self._truncated.data_ptr(), self._info_speed.data_ptr(), self._info_crashed.data_ptr(),
                 self._stream()))
+        if kev is not None:
+            kev[-1][1].record(torch.cuda.current_stream(self.device))
         info = {"speed": self._info_speed, "crashed": self._info_crashed.view(torch.bool), "action": act}
         if self.autoreset_mode == "SameStep" and self.reset_mode == "device":
             self._final_obs.copy_(self._obs)

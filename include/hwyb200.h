@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define HWY_ABI_VERSION 5
+#define HWY_ABI_VERSION 7
 #define HWY_MAX_LANES 8
 #define HWY_MAX_TARGET_SPEEDS 8
 #define HWY_MAX_VEHICLES 128 /* per env, incl. the ego */
@@ -276,6 +276,10 @@ typedef struct HwyNetState {
     int32_t *count;              /* [n_envs] vehicles currently on the road; NULL: always n_vehicles */
     int32_t *road_steps;         /* [n_envs] RegulatedRoad.steps; NULL when not regulated */
     uint64_t *rng;               /* [5*n_envs] numpy PCG64 stream (layout as HwyHighwayState.rng); NULL if unused */
+    int32_t *overflow;           /* [n_envs] or NULL: vehicles that _spawn_vehicle accepted but that found every slot of
+                                  * the env taken (the reference's list is unbounded; HWY_NET_GROUP_LARGE slots here).
+                                  * Incremented by the step / reset kernels, never cleared by them: a non-zero entry
+                                  * means the env has left the reference's trajectory (info["spawn_overflow"]) */
 } HwyNetState;
 
 /* IntersectionEnv._spawn_vehicle constants (envs/intersection_env.py:325-352). */
@@ -415,6 +419,59 @@ typedef struct HwyRoundaboutSpawn {
 int hwy_roundabout_reset(const HwyNetParams *p, const HwyNetGraph *graph, const HwyRoundaboutSpawn *spawn,
                          const HwyNetState *s, uint64_t *rng, const uint8_t *mask_a, const uint8_t *mask_b,
                          float *obs, void *stream);
+
+/* ====================================================================== observation plugins on ANY road family
+ * The reference's observation_factory (envs/common/observation.py:772-794) builds any ObservationType on any env; these
+ * entry points are that registry on the device: they read a state of either family through a HwyObsView (the highway
+ * family passes the lane table of RoadNetwork.straight_road_network as a HwyNetGraph) and write the observation of
+ * every controlled vehicle, obs[n_envs][max(1, n_agents)][...].  mask_a | mask_b select envs (both NULL: all). */
+#define HWY_FEAT_ON_ROAD 13 /* OccupancyGrid layer (observation.py:412-413) */
+#define HWY_FEAT_UNKNOWN 14 /* a feature no Vehicle.to_dict key matches: the layer stays NaN -> 0 */
+
+typedef struct HwyObsView {
+    int32_t n_envs, vp;         /* slot stride of the state arrays */
+    int32_t n_vehicles;         /* slots in use when count == NULL */
+    int32_t n_agents;           /* controlled vehicles observed per env (0 or 1: the first one) */
+    const double *pos, *hs;     /* [n_envs*vp*2] position, (heading, speed) */
+    const int32_t *meta;        /* [n_envs*vp] lane | kind | ... (HWY_META_*) */
+    const int32_t *count;       /* [n_envs] or NULL */
+    const int32_t *route;       /* [n_envs*vp*HWY_NET_MAX_ROUTE] or NULL (no planned routes: cos_d = sin_d = 0) */
+    const int32_t *route_len;   /* [n_envs*vp] or NULL */
+    const int32_t *speed_index; /* [n_envs*max(1, n_agents)] MDPVehicle.speed_index (TimeToCollision) or NULL */
+} HwyObsView;
+
+/* OccupancyGridObservation.__init__ (observation.py:286-333) */
+typedef struct HwyGridParams {
+    int32_t n_features;
+    int32_t features[HWY_MAX_OBS_FEATURES];  /* HWY_FEAT_* */
+    int32_t ranged[HWY_MAX_OBS_FEATURES];    /* the feature has a features_range entry: lmap to [-1, 1] */
+    double range_lo[HWY_MAX_OBS_FEATURES], range_hi[HWY_MAX_OBS_FEATURES];
+    int32_t x_ranged, y_ranged;              /* "x" / "y" in features_range (cell index un-maps them, :383-400) */
+    double x_lo, x_hi, y_lo, y_hi;
+    double grid_lo[2], grid_step[2];
+    int32_t shape[2];                        /* floor((grid_size[:,1] - grid_size[:,0]) / grid_step) */
+    int32_t align_to_vehicle_axes, clip, as_image, observe_intentions;
+} HwyGridParams;
+/* obs [n_envs][agents][n_features][shape0][shape1] float32 (as_image: the uint8 values as floats) */
+int hwy_observe_grid(const HwyNetGraph *graph, const HwyObsView *view, const HwyGridParams *p, const uint8_t *mask_a,
+                     const uint8_t *mask_b, float *obs, void *stream);
+
+/* TimeToCollisionObservation (observation.py:115-152; finite_mdp.py:104-163 compute_ttc_grid): obs
+ * [n_envs][agents][3][3][horizon * policy_frequency] */
+typedef struct HwyTtcParams {
+    int32_t horizon, policy_frequency, n_target_speeds, _pad;
+    double target_speeds[HWY_MAX_TARGET_SPEEDS];
+} HwyTtcParams;
+int hwy_observe_ttc(const HwyNetGraph *graph, const HwyObsView *view, const HwyTtcParams *p, const uint8_t *mask_a,
+                    const uint8_t *mask_b, float *obs, void *stream);
+
+/* LidarObservation (observation.py:678-769): obs [n_envs][agents][cells][2] float32 (distance, relative radial speed) */
+typedef struct HwyLidarParams {
+    int32_t cells, normalize;
+    double maximum_range;
+} HwyLidarParams;
+int hwy_observe_lidar(const HwyObsView *view, const HwyLidarParams *p, const uint8_t *mask_a, const uint8_t *mask_b,
+                      float *obs, void *stream);
 
 /* Kernel launches issued by the calling thread through this library since load (the
  * `gpu_launches` claim of bench.py). */

@@ -160,7 +160,88 @@ def main() -> None:
         print(f"{name}: -> {path} ({os.path.getsize(path)/1e3:.0f} kB)")
 
 
+# ------------------------------------------------------------------ observation plugins on every env family
+# One short rollout per env id; on every visited state the reference builds each listed observation type with its own
+# observation_factory (envs/common/observation.py:772-794) and observes — the plugin registry is orthogonal to the env.
+GRID_RICH = {"type": "OccupancyGrid",
+             "features": ["presence", "x", "y", "vx", "vy", "cos_h", "sin_h", "long_off", "lat_off", "ang_off", "heading",
+                          "cos_d", "sin_d", "on_road"],
+             "features_range": {"x": [-100, 100], "y": [-100, 100], "vx": [-20, 20], "vy": [-20, 20]},
+             "grid_size": [[-32, 32], [-18, 18]], "grid_step": [4, 3], "align_to_vehicle_axes": True, "clip": False}
+OBS_PLUGIN_CASES = {
+    "obs_plugins_highway": ("highway-v0", {"vehicles_count": 30}, list(range(2000, 2004)), 8, "discrete5", [
+        {"type": "TimeToCollision", "horizon": 10},
+        {"type": "OccupancyGrid"},
+        {"type": "OccupancyGrid", "grid_size": [[-300, 300], [-10, 10]], "grid_step": [2, 2]},  # the reference's own test
+        GRID_RICH,
+        {"type": "LidarObservation"},
+        {"type": "LidarObservation", "cells": 36, "maximum_range": 90, "normalize": False},
+    ]),
+    "obs_plugins_intersection": ("intersection-v0", None, list(range(2010, 2014)), 8, "discrete3", [
+        {"type": "TimeToCollision", "horizon": 5},
+        {"type": "OccupancyGrid", "align_to_vehicle_axes": True, "grid_size": [[-32, 32], [-32, 32]], "grid_step": [4, 4]},
+        GRID_RICH,
+        {"type": "LidarObservation"},
+    ]),
+    "obs_plugins_roundabout": ("roundabout-v0", None, list(range(2020, 2024)), 8, "discrete5", [
+        {"type": "OccupancyGrid"},
+        GRID_RICH,
+        {"type": "LidarObservation", "cells": 24},
+        {"type": "TimeToCollision", "horizon": 7},
+    ]),
+    "obs_plugins_merge": ("merge-v0", None, list(range(2030, 2034)), 8, "discrete5", [
+        {"type": "LidarObservation", "maximum_range": 120},
+        {"type": "OccupancyGrid", "grid_size": [[-60, 60], [-12, 12]], "grid_step": [3, 2]},
+        {"type": "TimeToCollision", "horizon": 6},
+    ]),
+}
+
+
+def gen_obs_plugins(only) -> None:
+    import json
+
+    from highway_env.envs.common.observation import observation_factory
+
+    for name, (env_id, over, seeds, T, akind, obs_cfgs) in OBS_PLUGIN_CASES.items():
+        if only and name not in only:
+            continue
+        rng = np.random.default_rng(sum(map(ord, name)))
+        pad = 32 if env_id.startswith("intersection") else 0
+        states, obs = [], [[] for _ in obs_cfgs]
+        for seed in seeds:
+            env = rh.make_reference_env(env_id, over)
+            env.reset(seed=seed)
+            observers = [observation_factory(env, dict(c)) for c in obs_cfgs]
+            hi = 3 if akind == "discrete3" else 5
+            for t in range(T + 1):
+                states.append(rh.dump_state(env, pad))
+                for k, ob in enumerate(observers):
+                    obs[k].append(np.asarray(ob.observe()).copy())
+                if t < T:
+                    env.step(int(rng.integers(0, hi)))
+        keys = [k for k in states[0].keys() if all(k in s for s in states)]
+        out = {k: np.stack([s[k] for s in states]) for k in keys}
+        for k in range(len(obs_cfgs)):
+            out[f"obs_{k}"] = np.stack(obs[k])
+        env = rh.make_reference_env(env_id, over)
+        env.reset(seed=0)
+        out.update(rh.dump_network(env))
+        cfg = dict(env.config)
+        cfg["_env_id"] = env_id
+        cfg["_target_speeds"] = [float(x) for x in env.vehicle.target_speeds]
+        out["config_json"] = np.array(json.dumps(cfg))
+        out["obs_cfgs_json"] = np.array(json.dumps(obs_cfgs))
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, **out)
+        print(f"{name}: {len(states)} states x {len(obs_cfgs)} observation types -> {path} ({os.path.getsize(path)/1e3:.0f} kB)")
+
+
 if __name__ == "__main__":
     if not rh.reference_available():
         raise SystemExit("reference not mounted; golden fixtures can only be generated in the build container")
-    main()
+    args = sys.argv[1:]
+    if args and args[0] == "obs_plugins":
+        rh._ensure_imports()
+        gen_obs_plugins(args[1:])
+    else:
+        main()

@@ -750,11 +750,10 @@ static int is_connected_road(const NetGraph *g, int f1, int t1, int f2, int t2, 
 }
 
 /* envs/common/finite_mdp.py:104-163 compute_ttc_grid + observation.py:128-152 */
-static void observe_ttc(const World *w, float *obs) {
+static void observe_ttc_from(const World *w, int ego, int si_e, float *obs) {
     const NetCfg *c = w->c;
     const NetState *s = w->s;
     const NetGraph *g = w->g;
-    const int ego = ego_index(w);
     const NetLane *EL = &g->lanes[s->lane[ego]];
     int n_speeds = c->n_target_speeds, n_lanes = EL->road_count;
     int n_t = (int)(c->ttc_horizon / (1.0 / c->policy_frequency));
@@ -796,7 +795,7 @@ static void observe_ttc(const World *w, float *obs) {
         }
     }
     /* pad lanes with ones, crop 3 around the ego lane; repeat first/last speed rows, crop 3 */
-    int ego_lane_id = EL->lane_id, si_e = s->speed_index[0];
+    int ego_lane_id = EL->lane_id;
     for (int a = 0; a < 3; a++) {
         int vrow = n_speeds + si_e - 1 + a; /* index into the repeated array */
         /* repeated rows: row0 x (1+n_speeds), middle rows x1, last x (1+n_speeds) */
@@ -821,6 +820,17 @@ static void observe_ttc(const World *w, float *obs) {
         }
     }
     free(grid);
+}
+
+static void observe_ttc(const World *w, float *obs) { observe_ttc_from(w, ego_index(w), w->s->speed_index[0], obs); }
+void net_observe_ttc_from(const NetGraph *g, const NetCfg *c, const NetState *s, int V, int ego, int speed_index,
+                          float *obs) {
+    World w;
+    w.g = g;
+    w.c = c;
+    w.s = (NetState *)s;
+    w.V = V;
+    observe_ttc_from(&w, ego, speed_index, obs);
 }
 
 /* envs/common/observation.py:234-276 with explicit features_range / absolute; optional
@@ -1317,4 +1327,212 @@ void net_substeps(const NetGraph *g, const NetCfg *c, NetState *s, int substeps)
         road_step(&w, dt);
     }
     free(act_buf);
+}
+
+
+/* ====================================================================== observation plugins, general form
+ * Vehicle.to_dict (vehicle/kinematics.py:237-261) relative to `origin` (< 0: absolute); road objects
+ * (vehicle/objects.py:141-159) have no heading / offsets columns (NaN in the DataFrame). */
+static double vehicle_feature(const NetGraph *g, const NetState *s, int v, int origin, int feat, int observe_intentions) {
+    const int is_object = s->kind[v] == NET_KIND_OBSTACLE;
+    const double ch = cos(s->heading[v]), sh = sin(s->heading[v]);
+    switch (feat) {
+        case NET_FEAT_PRESENCE: return 1.0;
+        case NET_FEAT_X: return origin >= 0 ? s->x[v] - s->x[origin] : s->x[v];
+        case NET_FEAT_Y: return origin >= 0 ? s->y[v] - s->y[origin] : s->y[v];
+        case NET_FEAT_VX: {
+            double vx = is_object ? 0.0 : s->speed[v] * ch;
+            return origin >= 0 ? vx - s->speed[origin] * cos(s->heading[origin]) : vx;
+        }
+        case NET_FEAT_VY: {
+            double vy = is_object ? 0.0 : s->speed[v] * sh;
+            return origin >= 0 ? vy - s->speed[origin] * sin(s->heading[origin]) : vy;
+        }
+        case NET_FEAT_HEADING: return is_object ? NAN : s->heading[v];
+        case NET_FEAT_COS_H: return ch;
+        case NET_FEAT_SIN_H: return sh;
+        case NET_FEAT_COS_D:
+        case NET_FEAT_SIN_D: {
+            /* destination (:203-215): end of the last route lane (lane id None -> 0); no route: the position */
+            int rl = s->route_len ? s->route_len[v] : 0;
+            if (!observe_intentions || is_object || rl == 0) return 0.0;
+            int e = s->route[(size_t)v * NET_MAX_ROUTE + rl - 1];
+            int first = road_first(g, RT_FROM(e), RT_TO(e));
+            int id = RT_ID(e) < 0 ? 0 : RT_ID(e);
+            const NetLane *L = &g->lanes[first + id];
+            double dx, dy;
+            net_lane_position(L, L->length, 0, &dx, &dy);
+            dx -= s->x[v];
+            dy -= s->y[v];
+            if (dx == 0.0 && dy == 0.0) return 0.0;
+            double n = sqrt(dx * dx + dy * dy); /* np.linalg.norm of a 2-vector */
+            return feat == NET_FEAT_COS_D ? dx / n : dy / n;
+        }
+        case NET_FEAT_LONG_OFF:
+        case NET_FEAT_LAT_OFF:
+        case NET_FEAT_ANG_OFF: {
+            if (is_object) return NAN;
+            const NetLane *L = &g->lanes[s->lane[v]];
+            double lon, lat;
+            net_lane_local(L, s->x[v], s->y[v], &lon, &lat);
+            if (feat == NET_FEAT_LONG_OFF) return lon;
+            if (feat == NET_FEAT_LAT_OFF) return lat;
+            return orc_wrap_to_pi(s->heading[v] - net_lane_heading_at(L, lon)); /* lane.local_angle :145-147 */
+        }
+        default: return NAN;
+    }
+}
+
+/* OccupancyGridObservation.pos_to_index (:422-444); the position is relative to the observer */
+static void grid_index(const NetGridCfg *gc, double px, double py, double ce, double se, int *ci, int *cj) {
+    if (gc->align_to_vehicle_axes) { /* [[c, s], [-s, c]] @ position */
+        double rx = ce * px + se * py, ry = -se * px + ce * py;
+        px = rx;
+        py = ry;
+    }
+    *ci = (int)floor((px - gc->grid_lo[0]) / gc->grid_step[0]);
+    *cj = (int)floor((py - gc->grid_lo[1]) / gc->grid_step[1]);
+}
+
+/* OccupancyGridObservation.observe (:354-420) with every constructor option */
+void net_observe_grid(const NetGraph *g, const NetState *s, int V, int ego, const NetGridCfg *gc, float *obs) {
+    const int NX = gc->shape[0], NY = gc->shape[1], F = gc->n_features;
+    const size_t cells = (size_t)NX * NY;
+    double *grid = (double *)malloc(sizeof(double) * cells * F);
+    for (size_t k = 0; k < cells * F; k++) grid[k] = NAN;
+    const double ex = s->x[ego], ey = s->y[ego];
+    const double ce = cos(s->heading[ego]), se = sin(s->heading[ego]);
+    for (int layer = 0; layer < F; layer++) {
+        const int feat = gc->features[layer];
+        if (feat == NET_FEAT_ON_ROAD) {
+            /* fill_road_layer_by_lanes (:466-499) */
+            const double spacing = fmin(gc->grid_step[0], gc->grid_step[1]);
+            for (int l = 0; l < g->n_lanes; l++) {
+                const NetLane *L = &g->lanes[l];
+                double origin = lane_s(L, ex, ey);
+                double start = origin - 100, stop = origin + 100;
+                int n = (int)ceil((stop - start) / spacing); /* np.arange length */
+                for (int k = 0; k < n; k++) {
+                    double wp = clipd(start + k * spacing, 0, L->length);
+                    double px, py;
+                    net_lane_position(L, wp, 0, &px, &py);
+                    int ci, cj;
+                    grid_index(gc, px - ex, py - ey, ce, se, &ci, &cj);
+                    if (0 <= ci && ci < NX && 0 <= cj && cj < NY) grid[(size_t)layer * cells + (size_t)ci * NY + cj] = 1;
+                }
+            }
+            continue;
+        }
+        if (feat == NET_FEAT_UNKNOWN) continue;
+        for (int v = V - 1; v >= 0; v--) { /* df[::-1]: the lowest index is written last */
+            if (s->kind[v] == NET_KIND_OBSTACLE) continue; /* road.vehicles only */
+            double x = vehicle_feature(g, s, v, ego, NET_FEAT_X, 1), y = vehicle_feature(g, s, v, ego, NET_FEAT_Y, 1);
+            /* normalize() maps x / y when they have a range; the cell index un-maps them (:383-400) */
+            if (gc->x_ranged) x = lmap(lmap(x, gc->x_lo, gc->x_hi, -1, 1), -1, 1, gc->x_lo, gc->x_hi);
+            if (gc->y_ranged) y = lmap(lmap(y, gc->y_lo, gc->y_hi, -1, 1), -1, 1, gc->y_lo, gc->y_hi);
+            int ci, cj;
+            grid_index(gc, x, y, ce, se, &ci, &cj);
+            if (!(0 <= ci && ci < NX && 0 <= cj && cj < NY)) continue;
+            double val = vehicle_feature(g, s, v, ego, feat, gc->observe_intentions);
+            if (gc->ranged[layer]) val = lmap(val, gc->range_lo[layer], gc->range_hi[layer], -1, 1);
+            grid[(size_t)layer * cells + (size_t)ci * NY + cj] = val;
+        }
+    }
+    for (size_t k = 0; k < cells * F; k++) {
+        double val = grid[k];
+        if (isnan(val)) { /* np.clip keeps NaN; astype(uint8) of NaN and nan_to_num both give 0 */
+            obs[k] = 0.0f;
+            continue;
+        }
+        if (gc->clip) val = clipd(val, -1, 1);
+        if (gc->as_image) val = (double)(unsigned char)(long)((clipd(val, -1, 1) + 1) / 2 * 255); /* .astype(np.uint8) */
+        obs[k] = (float)val;
+    }
+    free(grid);
+}
+
+/* utils.distance_to_rect (utils.py:388-416): ray [r, q] against the rectangle (a, b, c, d) */
+static double lidar_distance_to_rect(const double r[2], const double q[2], double corners[4][2]) {
+    const double *a = corners[0], *b = corners[1], *d = corners[3];
+    double ux = b[0] - a[0], uy = b[1] - a[1], vx = d[0] - a[0], vy = d[1] - a[1];
+    double un = norm2(ux, uy), vn = norm2(vx, vy);
+    ux /= un;
+    uy /= un;
+    vx /= vn;
+    vy /= vn;
+    double rqu = dot2(q[0] - r[0], q[1] - r[1], ux, uy), rqv = dot2(q[0] - r[0], q[1] - r[1], vx, vy);
+    double i1[2] = {dot2(a[0] - r[0], a[1] - r[1], ux, uy) / rqu, dot2(b[0] - r[0], b[1] - r[1], ux, uy) / rqu};
+    double i2[2] = {dot2(a[0] - r[0], a[1] - r[1], vx, vy) / rqv, dot2(d[0] - r[0], d[1] - r[1], vx, vy) / rqv};
+    if (!(rqu >= 0)) {
+        double t = i1[0];
+        i1[0] = i1[1];
+        i1[1] = t;
+    }
+    if (!(rqv >= 0)) {
+        double t = i2[0];
+        i2[0] = i2[1];
+        i2[1] = t;
+    }
+    if (interval_distance(i1[0], i1[1], i2[0], i2[1]) <= 0 && interval_distance(0, 1, i1[0], i1[1]) <= 0 &&
+        interval_distance(0, 1, i2[0], i2[1]) <= 0)
+        return fmax(i1[0], i2[0]) * norm2(q[0] - r[0], q[1] - r[1]);
+    return INFINITY;
+}
+
+/* LidarObservation.trace / observe (observation.py:703-769).  The grid is float32: every store rounds, and the
+ * `<=` comparisons read the rounded values back. */
+void net_observe_lidar(const NetState *s, int V, int ego, int cells, double maximum_range, int normalize, float *obs) {
+    const double angle = 2 * M_PI / cells;
+    float *grid = obs;
+    for (int k = 0; k < cells; k++) grid[2 * k] = grid[2 * k + 1] = (float)maximum_range;
+    const double ox = s->x[ego], oy = s->y[ego];
+    const double ovx = s->speed[ego] * cos(s->heading[ego]), ovy = s->speed[ego] * sin(s->heading[ego]);
+#define ANGLE_TO_INDEX(a) ((int)py_mod(floor((a) / angle), (double)cells))
+    for (int o = 0; o < V; o++) { /* road.vehicles + road.objects: objects sit after the vehicles */
+        if (o == ego) continue;
+        const int is_object = s->kind[o] == NET_KIND_OBSTACLE;
+        const double len = is_object ? 2.0 : VEH_LENGTH, wid = 2.0;
+        const double ch = cos(s->heading[o]), sh = sin(s->heading[o]);
+        const double vx = is_object ? 0.0 : s->speed[o] * ch, vy = is_object ? 0.0 : s->speed[o] * sh;
+        double center_distance = norm2(s->x[o] - ox, s->y[o] - oy);
+        if (center_distance > maximum_range) continue;
+        double center_angle = atan2(s->y[o] - oy, s->x[o] - ox) + angle / 2;
+        int center_index = ANGLE_TO_INDEX(center_angle);
+        double distance = center_distance - wid / 2;
+        if (distance <= grid[2 * center_index]) {
+            double dx = cos(center_index * angle), dy = sin(center_index * angle);
+            grid[2 * center_index] = (float)distance;
+            grid[2 * center_index + 1] = (float)dot2(vx - ovx, vy - ovy, dx, dy);
+        }
+        /* utils.rect_corners (utils.py:128-157): rotation @ corner + centre */
+        const double cl[4][2] = {{-len / 2, -wid / 2}, {-len / 2, wid / 2}, {len / 2, wid / 2}, {len / 2, -wid / 2}};
+        double corners[4][2], amin = 0, amax = 0;
+        for (int k = 0; k < 4; k++) {
+            corners[k][0] = (ch * cl[k][0] + (-sh) * cl[k][1]) + s->x[o];
+            corners[k][1] = (sh * cl[k][0] + ch * cl[k][1]) + s->y[o];
+            double a = atan2(corners[k][1] - oy, corners[k][0] - ox) + angle / 2;
+            if (k == 0 || a < amin) amin = a;
+            if (k == 0 || a > amax) amax = a;
+        }
+        if (amin < -M_PI / 2 && M_PI / 2 < amax) { /* corners wrap around +pi */
+            double t = amin;
+            amin = amax;
+            amax = t + 2 * M_PI;
+        }
+        int start = ANGLE_TO_INDEX(amin), end = ANGLE_TO_INDEX(amax);
+        int n_idx = start < end ? end - start + 1 : (cells - start) + (end + 1);
+        for (int q = 0; q < n_idx; q++) {
+            int index = start < end ? start + q : (q < cells - start ? start + q : q - (cells - start));
+            double dx = cos(index * angle), dy = sin(index * angle);
+            double r[2] = {ox, oy}, qq[2] = {ox + maximum_range * dx, oy + maximum_range * dy};
+            double dist = lidar_distance_to_rect(r, qq, corners);
+            if (dist <= grid[2 * index]) {
+                grid[2 * index] = (float)dist;
+                grid[2 * index + 1] = (float)dot2(vx - ovx, vy - ovy, dx, dy);
+            }
+        }
+    }
+#undef ANGLE_TO_INDEX
+    if (normalize) /* obs /= maximum_range on the float32 array */
+        for (int k = 0; k < 2 * cells; k++) grid[k] = grid[k] / (float)maximum_range;
 }

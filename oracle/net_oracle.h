@@ -125,6 +125,47 @@ void net_neighbours(const NetGraph *g, const NetCfg *c, const NetState *s, int v
 int net_rotated_rectangles_intersect(double c1x, double c1y, double l1, double w1, double a1, double c2x, double c2y,
                                      double l2, double w2, double a2);
 
+/* ------------------------------------------------------------------ observation plugins on ANY road family
+ * (envs/common/observation.py:772-794 observation_factory: every observation type works on every env).  The state
+ * is the per-env NetState with V vehicles/objects; `ego` is the observer's slot. */
+#define NET_FEAT_PRESENCE 0
+#define NET_FEAT_X 1
+#define NET_FEAT_Y 2
+#define NET_FEAT_VX 3
+#define NET_FEAT_VY 4
+#define NET_FEAT_HEADING 5
+#define NET_FEAT_COS_H 6
+#define NET_FEAT_SIN_H 7
+#define NET_FEAT_COS_D 8
+#define NET_FEAT_SIN_D 9
+#define NET_FEAT_LONG_OFF 10
+#define NET_FEAT_LAT_OFF 11
+#define NET_FEAT_ANG_OFF 12
+#define NET_FEAT_ON_ROAD 13  /* OccupancyGrid only */
+#define NET_FEAT_UNKNOWN 14  /* a feature name no Vehicle.to_dict key matches: the layer stays NaN -> 0 */
+#define NET_MAX_FEATURES 16
+
+/* OccupancyGridObservation.__init__ arguments (observation.py:286-333) */
+typedef struct NetGridCfg {
+    int32_t n_features;
+    int32_t features[NET_MAX_FEATURES];
+    int32_t ranged[NET_MAX_FEATURES]; /* feature has a features_range entry */
+    double range_lo[NET_MAX_FEATURES], range_hi[NET_MAX_FEATURES];
+    int32_t x_ranged, y_ranged;       /* "x" / "y" in features_range: cell coordinates are un-normalised (:383-400) */
+    double x_lo, x_hi, y_lo, y_hi;
+    double grid_lo[2], grid_step[2];  /* grid_size[:, 0], grid_step */
+    int32_t shape[2];                 /* floor((size[:,1] - size[:,0]) / step) */
+    int32_t align_to_vehicle_axes, clip, as_image, observe_intentions;
+} NetGridCfg;
+/* obs [n_features][shape0][shape1] float32 (as_image: the uint8 values, stored as floats) */
+void net_observe_grid(const NetGraph *g, const NetState *s, int V, int ego, const NetGridCfg *gc, float *obs);
+/* TimeToCollisionObservation.observe (observation.py:115-152) for observer `ego` with speed index `speed_index`:
+ * obs [3][3][horizon * policy_frequency] */
+void net_observe_ttc_from(const NetGraph *g, const NetCfg *c, const NetState *s, int V, int ego, int speed_index,
+                          float *obs);
+/* LidarObservation.observe (observation.py:678-769): obs [cells][2] float32 */
+void net_observe_lidar(const NetState *s, int V, int ego, int cells, double maximum_range, int normalize, float *obs);
+
 /* geometry KATs */
 void net_lane_local(const NetLane *L, double x, double y, double *s, double *lat);
 void net_lane_position(const NetLane *L, double s, double lat, double *x, double *y);

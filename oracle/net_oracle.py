@@ -60,6 +60,49 @@ _SF = ("x", "y", "heading", "speed", "target_speed", "timer", "delta", "impact_x
 _SI = ("lane", "target_lane", "kind", "crashed", "has_impact", "check_collisions")
 
 
+NET_MAX_FEATURES = 16
+FEATURE_CODES = {"presence": 0, "x": 1, "y": 2, "vx": 3, "vy": 4, "heading": 5, "cos_h": 6, "sin_h": 7, "cos_d": 8,
+                 "sin_d": 9, "long_off": 10, "lat_off": 11, "ang_off": 12, "on_road": 13}
+FEAT_UNKNOWN = 14
+
+
+class NetGridCfg(C.Structure):
+    _fields_ = [("n_features", C.c_int32), ("features", C.c_int32 * NET_MAX_FEATURES),
+                ("ranged", C.c_int32 * NET_MAX_FEATURES),
+                ("range_lo", C.c_double * NET_MAX_FEATURES), ("range_hi", C.c_double * NET_MAX_FEATURES),
+                ("x_ranged", C.c_int32), ("y_ranged", C.c_int32),
+                ("x_lo", C.c_double), ("x_hi", C.c_double), ("y_lo", C.c_double), ("y_hi", C.c_double),
+                ("grid_lo", C.c_double * 2), ("grid_step", C.c_double * 2), ("shape", C.c_int32 * 2),
+                ("align_to_vehicle_axes", C.c_int32), ("clip", C.c_int32), ("as_image", C.c_int32),
+                ("observe_intentions", C.c_int32)]
+
+
+def grid_cfg(features=None, grid_size=None, grid_step=None, features_range=None, absolute=False,
+             align_to_vehicle_axes=False, clip=True, as_image=False, **_):
+    """OccupancyGridObservation.__init__ (envs/common/observation.py:286-333) -> NetGridCfg"""
+    gc = NetGridCfg()
+    features = list(features) if features is not None else ["presence", "vx", "vy", "on_road"]
+    size = np.array(grid_size if grid_size is not None else [[-5.5 * 5, 5.5 * 5], [-5.5 * 5, 5.5 * 5]], dtype=np.float64)
+    step = np.array(grid_step if grid_step is not None else [5, 5], dtype=np.float64)
+    shape = np.asarray(np.floor((size[:, 1] - size[:, 0]) / step), dtype=np.intp)
+    fr = features_range or {"vx": [-80.0, 80.0], "vy": [-80.0, 80.0]}
+    gc.n_features = len(features)
+    for k, f in enumerate(features):
+        gc.features[k] = FEATURE_CODES.get(f, FEAT_UNKNOWN)
+        if f in fr and f != "on_road":
+            gc.ranged[k], gc.range_lo[k], gc.range_hi[k] = 1, float(fr[f][0]), float(fr[f][1])
+    if "x" in fr:
+        gc.x_ranged, gc.x_lo, gc.x_hi = 1, float(fr["x"][0]), float(fr["x"][1])
+    if "y" in fr:
+        gc.y_ranged, gc.y_lo, gc.y_hi = 1, float(fr["y"][0]), float(fr["y"][1])
+    gc.grid_lo[0], gc.grid_lo[1] = float(size[0, 0]), float(size[1, 0])
+    gc.grid_step[0], gc.grid_step[1] = float(step[0]), float(step[1])
+    gc.shape[0], gc.shape[1] = int(shape[0]), int(shape[1])
+    gc.align_to_vehicle_axes, gc.clip, gc.as_image = int(bool(align_to_vehicle_axes)), int(bool(clip)), int(bool(as_image))
+    gc.observe_intentions = 1
+    return gc
+
+
 class NetState(C.Structure):
     _fields_ = ([(k, C.c_void_p) for k in _SF] + [(k, C.c_void_p) for k in _SI]
                 + [("route", C.c_void_p), ("route_len", C.c_void_p), ("speed_index", C.c_void_p),
@@ -109,6 +152,15 @@ def lib():
         _lib.net_obs_size.argtypes = [C.POINTER(NetCfg)]
         _lib.net_closest_lane.restype = C.c_int
         _lib.net_closest_lane.argtypes = [C.POINTER(NetGraph), C.c_double, C.c_double, C.c_double]
+        _lib.net_observe_grid.restype = None
+        _lib.net_observe_grid.argtypes = [C.POINTER(NetGraph), C.POINTER(NetState), C.c_int, C.c_int,
+                                          C.POINTER(NetGridCfg), C.c_void_p]
+        _lib.net_observe_ttc_from.restype = None
+        _lib.net_observe_ttc_from.argtypes = [C.POINTER(NetGraph), C.POINTER(NetCfg), C.POINTER(NetState), C.c_int,
+                                              C.c_int, C.c_int, C.c_void_p]
+        _lib.net_observe_lidar.restype = None
+        _lib.net_observe_lidar.argtypes = [C.POINTER(NetState), C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
+                                           C.c_void_p]
         for name in ("net_lane_local", "net_lane_position"):
             getattr(_lib, name).restype = None
             getattr(_lib, name).argtypes = [C.POINTER(NetLane), C.c_double, C.c_double,
@@ -254,6 +306,38 @@ class NetOracleBatch:
             st = self._state(e)
             lib().net_observe(C.byref(self.g), C.byref(self.cfg), C.byref(st), self.obs[e].ctypes.data)
         return self.obs
+
+    # ---- observation plugins on any road family (net_oracle.h "observation plugins")
+    def _ego(self, e: int) -> int:
+        cnt = int(self.a["count"][e])
+        k = np.nonzero(np.isin(self.a["kind"][e, :cnt], (KIND_MDP, 2)))[0]
+        return int(k[0]) if len(k) else 0
+
+    def observe_grid(self, gc: "NetGridCfg", egos=None):
+        out = np.zeros((self.n, gc.n_features, gc.shape[0], gc.shape[1]), dtype=np.float32)
+        for e in range(self.n):
+            st = self._state(e)
+            lib().net_observe_grid(C.byref(self.g), C.byref(st), int(self.a["count"][e]),
+                                   self._ego(e) if egos is None else int(egos[e]), C.byref(gc), out[e].ctypes.data)
+        return out
+
+    def observe_ttc(self, egos=None):
+        n_t = int(self.cfg.ttc_horizon * self.cfg.policy_frequency)
+        out = np.zeros((self.n, 3, 3, n_t), dtype=np.float32)
+        for e in range(self.n):
+            st = self._state(e)
+            si = int(np.ravel(self.a["speed_index"][e])[0])
+            lib().net_observe_ttc_from(C.byref(self.g), C.byref(self.cfg), C.byref(st), int(self.a["count"][e]),
+                                       self._ego(e) if egos is None else int(egos[e]), si, out[e].ctypes.data)
+        return out
+
+    def observe_lidar(self, cells=16, maximum_range=60.0, normalize=True, egos=None):
+        out = np.zeros((self.n, cells, 2), dtype=np.float32)
+        for e in range(self.n):
+            st = self._state(e)
+            lib().net_observe_lidar(C.byref(st), int(self.a["count"][e]), self._ego(e) if egos is None else int(egos[e]),
+                                    int(cells), float(maximum_range), int(bool(normalize)), out[e].ctypes.data)
+        return out
 
     def step(self, actions):
         for e in range(self.n):

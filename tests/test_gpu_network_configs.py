@@ -160,3 +160,79 @@ def test_multi_agent_options_reset_and_steps_vs_oracle(over):
         assert np.max(np.abs(obs.cpu().numpy().reshape(n, -1) - o_obs.reshape(n, -1))) <= 1e-6
         for e in range(n):
             assert np.array_equal(sd["rng"][:, e], ob.rng_words(e)), (t, e)
+
+
+# ------------------------------------------------------------------ round-2 regressions
+@pytest.mark.parametrize("name", ["roundabout_kin", "intersection_kin", "merge_kin"])
+def test_reset_with_config_option_keeps_the_numpy_stream(name):
+    """reset(options={"config": ...}) re-allocates the device buffers; like the reference (seed=None keeps
+    np_random, abstract.py:219-249) the env's generator must go on, not restart from zeroed words."""
+    g, cfg = _cfg(name, {})
+    n = 16
+    a, b = _make(cfg, n), _make(cfg, n)
+    a.reset(seed=321)
+    b.reset(seed=321)
+    a.reset()
+    b.reset(options={"config": {"duration": cfg.get("duration", 11)}})
+    wa, wb = a._rng.cpu().numpy(), b._rng.cpu().numpy()
+    assert np.any(wb != 0) and np.array_equal(wa, wb)
+    sa, sb = a.state_dict(), b.state_dict()
+    for k in ("x", "y", "speed", "lane"):
+        assert np.array_equal(sa[k], sb[k]), k
+
+
+def test_device_int64_actions_are_staged_on_the_device():
+    """torch.randint / argmax produce int64 CUDA tensors: they must be converted on the device (no host round trip)
+    and give the same step as int32 actions."""
+    import torch
+
+    g, cfg = _cfg("roundabout_kin", {})
+    a, b = _make(cfg, 32, autoreset_mode="Disabled"), _make(cfg, 32, autoreset_mode="Disabled")
+    a.reset(seed=5)
+    b.reset(seed=5)
+    act = torch.randint(0, 5, (32,), device="cuda")
+    assert act.dtype == torch.int64
+    oa = a.step(act)[0].clone()
+    ob_ = b.step(act.to(torch.int32))[0]
+    assert torch.equal(oa, ob_)
+
+
+def test_intersection_full_slots_spawn_is_reported():
+    """A spawn accepted by _spawn_vehicle while all 32 slots are taken cannot be stored (the reference's list is
+    unbounded): the drop is counted in info["spawn_overflow"] instead of passing silently."""
+    g, cfg = _cfg("intersection_kin", {"spawn_probability": 1.0})
+    n = 8
+    env = _make(cfg, n, autoreset_mode="Disabled")
+    env.reset(seed=77)
+    sd = env.state_dict()
+    exit_lane = int(np.nonzero(np.asarray(g["net_exit_lane"]))[0][0])
+    for e in range(n):
+        ego = int(np.nonzero(sd["kind"][e, :sd["count"][e]] == 1)[0][0])
+        src = 0 if ego != 0 else 1
+        for v in range(V32):
+            if v == ego:
+                continue
+            for k in sd:
+                if sd[k].ndim >= 2 and sd[k].shape[:2] == (n, V32) and k != "rng":
+                    sd[k][e, v] = sd[k][e, src]
+            sd["kind"][e, v], sd["lane"][e, v], sd["target_lane"][e, v] = 0, exit_lane, exit_lane
+            sd["route_len"][e, v] = 0
+            sd["speed"][e, v] = sd["target_speed"][e, v] = 0.0
+        sd["count"][e] = V32
+    # park the fillers along the exit lane (before the point where _clear_vehicles removes them), far from the spawn points
+    L = {k[4:]: np.asarray(g[k])[exit_lane] for k in g if k.startswith("net_") and np.ndim(g[k]) == 1 and len(g[k]) > exit_lane}
+    for e in range(n):
+        for v in range(V32):
+            if sd["kind"][e, v] == 1:
+                continue
+            s = 5.0 + 2.0 * v
+            sd["x"][e, v] = L["sx"] + s * L["dx"]
+            sd["y"][e, v] = L["sy"] + s * L["dy"]
+            sd["heading"][e, v] = L["heading"]
+    env.load_state_dict(sd)
+    total = 0
+    for t in range(3):
+        _, _, _, _, info = env.step(np.ones(n, dtype=np.int32))
+        total = int(info["spawn_overflow"].sum().item())
+        assert np.all(env.state_dict()["count"] <= V32)
+    assert total > 0
