@@ -12,11 +12,12 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("HWYB200_LIB") or os.path.join(_HERE, "csrc", "libhwyb200.so")
 
-HWY_ABI_VERSION = 7  # bump with every change of a struct or signature: a stale libhwyb200.so then fails to load
+HWY_ABI_VERSION = 8  # bump with every change of a struct or signature: a stale libhwyb200.so then fails to load
 HWY_MAX_LANES = 8
 HWY_MAX_TARGET_SPEEDS = 8
 HWY_MAX_VEHICLES = 128
 HWY_MAX_OBS_VEHICLES = 16
+HWY_REWARD_TERMS = 5
 
 KIND_IDM, KIND_MDP, KIND_VEHICLE = 0, 1, 2
 META_LANE_SHIFT, META_TARGET_SHIFT = 0, 8
@@ -63,8 +64,9 @@ class HwyHighwayState(C.Structure):
         ("n_envs", C.c_int32), ("vp", C.c_int32),
         ("pos", C.c_void_p), ("hs", C.c_void_p), ("tt", C.c_void_p), ("imp", C.c_void_p),
         ("delta", C.c_void_p), ("meta", C.c_void_p), ("speed_index", C.c_void_p),
-        ("time", C.c_void_p), ("rng", C.c_void_p),
+        ("time", C.c_void_p), ("rng", C.c_void_p), ("reward_terms", C.c_void_p),
     ]
+
 
 
 # ---- general road networks (roundabout-v0)
@@ -121,7 +123,7 @@ class HwyNetState(C.Structure):
         ("pos", C.c_void_p), ("hs", C.c_void_p), ("tt", C.c_void_p), ("imp", C.c_void_p),
         ("delta", C.c_void_p), ("meta", C.c_void_p), ("route", C.c_void_p), ("route_len", C.c_void_p),
         ("speed_index", C.c_void_p), ("time", C.c_void_p), ("count", C.c_void_p), ("road_steps", C.c_void_p),
-        ("rng", C.c_void_p), ("overflow", C.c_void_p),
+        ("rng", C.c_void_p), ("reward_terms", C.c_void_p), ("overflow", C.c_void_p),
     ]
 
 

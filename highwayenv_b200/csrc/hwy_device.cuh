@@ -32,9 +32,28 @@ __device__ __forceinline__ bool lane_reachable(const HwyStraightLane& L, double 
 }
 // road/road.py:55-71 get_closest_lane_index with lane.py:132-143 distance_with_heading:
 // first minimum in graph-enumeration order.
-__device__ __forceinline__ int closest_lane(const HwyHighwayParams& P, double x, double y, double h) {
+// `aligned` (lanes_aligned below, uniform): every lane has the direction, origin-x, heading and length of lane 0, so
+// s, the two longitudinal terms and the angle term are bitwise the same for every lane and only the lateral offset
+// (dy of the lane origin; dir = (1, 0), lat = (-0, 1) make both dot products exact) is per lane.
+__device__ __forceinline__ int closest_lane(const HwyHighwayParams& P, double x, double y, double h, bool aligned = false) {
     int best = 0;
     double bd = 0;
+    if (aligned) {
+        const HwyStraightLane& L0 = P.lanes[0];
+        const double s = dot2(x - L0.start_x, y - L0.start_y, L0.dir_x, L0.dir_y);
+        const double t1 = fmax(s - L0.length, 0.0), t2 = fmax(0.0 - s, 0.0);
+        const double angle = 1.0 * fabs(wrap_to_pi(h - L0.heading));
+        for (int l = 0; l < P.lanes_count; ++l) {
+            const HwyStraightLane& L = P.lanes[l];
+            const double r = dot2(x - L.start_x, y - L.start_y, L.lat_x, L.lat_y);
+            const double d = fabs(r) + t1 + t2 + angle;
+            if (l == 0 || d < bd) {
+                bd = d;
+                best = l;
+            }
+        }
+        return best;
+    }
     for (int l = 0; l < P.lanes_count; ++l) {
         const HwyStraightLane& L = P.lanes[l];
         double s, r;
@@ -50,6 +69,16 @@ __device__ __forceinline__ int closest_lane(const HwyHighwayParams& P, double x,
 }
 // All lanes share origin-x and an x-aligned direction (RoadNetwork.straight_road_network with
 // angle 0, road/road.py:291-321): the longitudinal coordinate is then bitwise lane independent.
+// stricter: also the same heading, length and lateral direction (what closest_lane's shared terms need)
+__device__ __forceinline__ bool lanes_congruent(const HwyHighwayParams& P) {
+    bool ok = P.lanes[0].dir_y == 0.0;
+    for (int l = 1; l < P.lanes_count; ++l)
+        ok = ok && P.lanes[l].start_x == P.lanes[0].start_x && P.lanes[l].dir_x == P.lanes[0].dir_x &&
+             P.lanes[l].dir_y == 0.0 && P.lanes[l].heading == P.lanes[0].heading &&
+             P.lanes[l].length == P.lanes[0].length && P.lanes[l].lat_x == P.lanes[0].lat_x &&
+             P.lanes[l].lat_y == P.lanes[0].lat_y;
+    return ok;
+}
 __device__ __forceinline__ bool lanes_aligned(const HwyHighwayParams& P) {
     bool ok = P.lanes[0].dir_y == 0.0;
     for (int l = 1; l < P.lanes_count; ++l)

@@ -825,10 +825,18 @@ __device__ __forceinline__ void spawn_fused(const HwyHighwayParams& P, const Hwy
 
 // ------------------------------------------------------------------ the step kernel
 constexpr int kMaxBlockThreads = 512;  // 128 registers/thread => one full register file
+// Register budget of the step kernel = 65536 / (HWY_STEP_BOUND_THREADS * HWY_STEP_BOUND_BLOCKS); the launcher never
+// uses more than HWY_STEP_BOUND_THREADS threads per block.  (512, 1): 128 registers, two 256-thread blocks per SM.
+#ifndef HWY_STEP_BOUND_THREADS
+#define HWY_STEP_BOUND_THREADS 512
+#endif
+#ifndef HWY_STEP_BOUND_BLOCKS
+#define HWY_STEP_BOUND_BLOCKS 1
+#endif
 
 // blockDim.x = TPE * (envs per block); dynamic shared memory = envs per block * sizeof(EnvShared).
 template <int TPE>
-__global__ void __launch_bounds__(kMaxBlockThreads, 1)
+__global__ void __launch_bounds__(HWY_STEP_BOUND_THREADS, HWY_STEP_BOUND_BLOCKS)
 highway_step_kernel(const __grid_constant__ HwyHighwayParams P, const HwyHighwayState S,
                     const int32_t* __restrict__ action_i, const float* __restrict__ action_f,
                     float* __restrict__ obs, double* __restrict__ reward,
@@ -849,6 +857,7 @@ highway_step_kernel(const __grid_constant__ HwyHighwayParams P, const HwyHighway
     const bool active = i < V;
     const size_t slot = (size_t)e * S.vp + (active ? i : 0);
     const bool aligned = lanes_aligned(P);
+    const bool congruent = lanes_congruent(P);
 
     VehicleRegs r;
     load_vehicle(S, slot, r);
@@ -1146,7 +1155,7 @@ highway_step_kernel(const __grid_constant__ HwyHighwayParams P, const HwyHighway
             }
             r.heading += r.speed * sin_beta / (kVehLength / 2) * dt;
             r.speed += act_accel * dt;
-            int nl = closest_lane(P, r.x, r.y, r.heading);  // on_state_update :170-177
+            int nl = closest_lane(P, r.x, r.y, r.heading, congruent);  // on_state_update :170-177
             r.meta = meta_set_lane(r.meta, nl);
             if (kind == HWY_KIND_VEHICLE) r.meta = meta_set_target(r.meta, nl);  // schema: mirrors lane
         }
@@ -1195,6 +1204,14 @@ highway_step_kernel(const __grid_constant__ HwyHighwayParams P, const HwyHighway
         truncated[e] = (uint8_t)(t >= P.duration);
         if (info_speed) info_speed[e] = r.speed;  // abstract.py:200-217 _info
         if (info_crashed) info_crashed[e] = (uint8_t)is_crashed;
+        if (S.reward_terms) {  // _rewards (highway_env.py:118-137): info["rewards"]
+            double* rt = S.reward_terms + (size_t)e * HWY_REWARD_TERMS;
+            rt[0] = is_crashed ? 1.0 : 0.0;
+            rt[1] = (double)rl / (double)nl1;
+            rt[2] = clipd(scaled_speed, 0.0, 1.0);
+            rt[3] = on_road ? 1.0 : 0.0;
+            rt[4] = 0.0;
+        }
         sm.done = autoreset && (is_crashed || (P.offroad_terminal && !on_road) || t >= P.duration);
     }
     if (autoreset) {
@@ -1420,7 +1437,8 @@ Grid grid_for(int tpe, int n_envs) {
 // Envs per block of the step kernel: as many as fit 512 threads (lock-step, see env_sync),
 // reduced when that leaves the last wave of blocks mostly empty.  HWYB200_EPB overrides.
 int step_envs_per_block(int tpe, int n_envs) {
-    int max_epb = hwy::kMaxBlockThreads / tpe;
+    int max_epb = (hwy::kMaxBlockThreads < HWY_STEP_BOUND_THREADS ? hwy::kMaxBlockThreads : HWY_STEP_BOUND_THREADS) / tpe;
+    if (max_epb < 1) max_epb = 1;
     if (const char* e = getenv("HWYB200_EPB")) {
         int v = atoi(e);
         if (v >= 1 && v <= max_epb) return v;

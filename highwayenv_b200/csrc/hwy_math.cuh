@@ -92,9 +92,14 @@ __device__ __forceinline__ void m_sincos(double x, double* s, double* c) {
 static __device__ __noinline__ double m_pow(double x, double y) { return pow(x, y); }
 static __device__ __noinline__ double m_fmod(double a, double b) { return fmod(a, b); }
 
-// Python floored float modulo (b > 0 here); fast path when 0 <= a < b (fmod is exact: a).
-__device__ __forceinline__ double py_mod_pos(double a, double b) {
-    if (a >= 0.0 && a < b) return a;
+// Python floored float modulo (b > 0 here).  fmod() is exact, so the cases around the principal range need no call:
+//   0 <= a < b      -> a
+//   b <= a < 2b     -> a - b        (exact by Sterbenz: b <= a <= 2b)
+//   -b <= a < 0     -> fmod = a, then the sign fix-up `+= b` (one rounded add, as CPython's float_rem does)
+//   b == 1          -> a - floor(a) (exact) for a >= 0
+// Everything else takes the library fmod (a bit-serial loop: it was 11 % of the step kernel's instructions when
+// every wrap_to_pi went through it, profiles/r2_step_kernel_history.md).
+static __device__ __noinline__ double py_mod_slow(double a, double b) {
     double m = m_fmod(a, b);
     if (m != 0.0) {
         if (m < 0) m += b;
@@ -102,6 +107,16 @@ __device__ __forceinline__ double py_mod_pos(double a, double b) {
         m = 0.0;
     }
     return m;
+}
+__device__ __forceinline__ double py_mod_pos(double a, double b) {
+    if (a >= 0.0) {
+        if (a < b) return a;
+        if (a < b + b) return a - b;
+        if (b == 1.0 && a < 4503599627370496.0) return a - floor(a);
+    } else if (a >= -b) {
+        return a + b;
+    }
+    return py_mod_slow(a, b);
 }
 // utils.py:59-60
 __device__ __forceinline__ double wrap_to_pi(double x) { return py_mod_pos(x + kPi, kTwoPi) - kPi; }

@@ -50,6 +50,7 @@ struct EnvStage {
     int count, ego, speed_index, road_steps;
     unsigned agent_mask;    // the controlled (MDP) vehicles among the first `count` slots, list order = agent order
     double agent_reward[4];  // per-agent rewards of the step (MultiAgent: summed in agent order)
+    double agent_terms[4][4];  // per-agent _agent_rewards terms (collision, high_speed, arrived, on_road)
     unsigned yield_mask;
     // spawn record (dynamic population): written by the group's first thread, adopted by the new slot
     double sp_x, sp_y, sp_h, sp_speed, sp_delta, sp_ts;
@@ -400,11 +401,14 @@ __device__ __forceinline__ void closest_lane_group(const GraphShared& g, EnvStag
         for (int l = 0; l < g.n_lanes; ++l) {
             if (l == hint) continue;
             const HwyNetLane& L = g.lanes[l];
-            double lb = 0.0;
+            double lb;
             if (L.type == HWY_LANE_CIRCULAR)
                 lb = fabs(L.direction * (L.radius - norm2(x - L.cx, y - L.cy)));
             else if (L.type == HWY_LANE_STRAIGHT)
                 lb = fabs(dot2(x - L.sx, y - L.sy, L.lx, L.ly));
+            else  // SineLane: lateral = straight lateral - amplitude * sin(..), so |lateral| >= |straight lateral| -
+                  // |amplitude|; 1e-9 m covers the rounding of that subtraction (the other bounds are exact)
+                lb = fabs(dot2(x - L.sx, y - L.sy, L.lx, L.ly)) - fabs(L.amplitude) - 1e-9;
             if (lb > bd) continue;
             int slot = atomicAdd(&st.n_cand, 1);
             if (slot < K) {
@@ -1268,6 +1272,10 @@ network_step_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGraph* _
             rew *= on_road ? 1.0 : 0.0;
             if (P.normalize_reward) rew = lmap(rew, P.collision_reward, P.arrived_reward, 0.0, 1.0);
             st.agent_reward[my_agent] = rew;
+            st.agent_terms[my_agent][0] = is_crashed ? 1.0 : 0.0;
+            st.agent_terms[my_agent][1] = clipd(scaled_speed, 0.0, 1.0);
+            st.agent_terms[my_agent][2] = arrived ? 1.0 : 0.0;
+            st.agent_terms[my_agent][3] = on_road ? 1.0 : 0.0;
             if (env_ok) {
                 if (agents_reward) agents_reward[(size_t)e * A + my_agent] = rew;
                 if (agents_terminated) agents_terminated[(size_t)e * A + my_agent] = (uint8_t)(is_crashed || arrived);
@@ -1284,6 +1292,14 @@ network_step_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGraph* _
             double t = S.time[e] + 1.0 / P.policy_frequency;
             S.time[e] = t;
             reward[e] = sum / (double)A;
+            if (S.reward_terms) {  // _rewards (intersection_env.py:67-77): every term averaged over the agents
+                for (int k = 0; k < 4; ++k) {
+                    double tk = 0.0;
+                    for (int a = 0; a < A; ++a) tk = tk + st.agent_terms[a][k];
+                    S.reward_terms[(size_t)e * HWY_REWARD_TERMS + k] = tk / (double)A;
+                }
+                S.reward_terms[(size_t)e * HWY_REWARD_TERMS + 4] = 0.0;
+            }
             terminated[e] = (uint8_t)(any_crashed || all_arrived || (P.offroad_terminal && !on_road));
             truncated[e] = (uint8_t)(t >= P.duration);
             if (info_speed) info_speed[e] = r.speed;
@@ -1296,6 +1312,7 @@ network_step_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGraph* _
         const bool is_crashed = (r.meta & HWY_META_CRASHED) != 0;
         double rew = 0.0;
         bool term;
+        double rt[HWY_REWARD_TERMS] = {0.0, 0.0, 0.0, 0.0, 0.0};  // un-weighted terms of _rewards (info["rewards"])
         if (P.reward_type == 1) {
             // envs/intersection_env.py:79-117,368-373 (one controlled vehicle)
             const bool arrived = L.exit_lane && es >= 25;
@@ -1308,6 +1325,10 @@ network_step_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGraph* _
             rew *= on_road ? 1.0 : 0.0;
             if (P.normalize_reward) rew = lmap(rew, P.collision_reward, P.arrived_reward, 0.0, 1.0);
             term = is_crashed || arrived || (P.offroad_terminal && !on_road);
+            rt[0] = is_crashed ? 1.0 : 0.0;
+            rt[1] = clipd(scaled_speed, 0.0, 1.0);
+            rt[2] = arrived ? 1.0 : 0.0;
+            rt[3] = on_road ? 1.0 : 0.0;
         } else if (P.reward_type == 2) {
             // envs/merge_env.py:39-84: unclipped speed term, lane id of the CURRENT lane, altruistic penalty over the
             // ControlledVehicles on the merging lane ("b", "c", 2); never truncated, terminated past x = 370
@@ -1324,6 +1345,11 @@ network_step_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGraph* _
             rew = lmap(rew, P.collision_reward + P.merging_speed_reward, P.high_speed_reward + P.right_lane_reward, 0.0,
                        1.0);
             term = is_crashed || r.x > 370;
+            rt[0] = is_crashed ? 1.0 : 0.0;
+            rt[1] = (double)L.lane_id / 1.0;
+            rt[2] = scaled_speed;
+            rt[3] = (act == 0 || act == 2) ? 1.0 : 0.0;
+            rt[4] = merging;
         } else if (P.reward_type == 4) {
             // envs/u_turn_env.py:36-82: collision, current lane id (left-most = highest), clipped speed term;
             // normalised, then multiplied by on_road; truncated at `duration`
@@ -1337,6 +1363,10 @@ network_step_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGraph* _
                 rew = lmap(rew, P.collision_reward, P.high_speed_reward + P.left_lane_reward, 0.0, 1.0);
             rew *= on_road ? 1.0 : 0.0;
             term = is_crashed;
+            rt[0] = is_crashed ? 1.0 : 0.0;
+            rt[1] = (double)L.lane_id / (double)n1;
+            rt[2] = clipd(scaled_speed, 0.0, 1.0);
+            rt[3] = on_road ? 1.0 : 0.0;
         } else if (P.reward_type == 3) {
             // envs/two_way_env.py:35-62: speed index and how far left the TARGET lane is; never truncated
             const int n_side = L.road_count;  // all_side_lanes(vehicle.lane_index)
@@ -1344,6 +1374,8 @@ network_step_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGraph* _
             rew = rew + P.left_lane_reward *
                             ((double)(n_side - 1 - g.lanes[st.tgt[i]].lane_id) / (double)(n_side - 1));
             term = is_crashed;
+            rt[0] = (double)st.speed_index / (double)(P.n_target_speeds - 1);
+            rt[1] = (double)(n_side - 1 - g.lanes[st.tgt[i]].lane_id) / (double)(n_side - 1);
         } else {
             // envs/roundabout_env.py:44-71
             rew = rew + P.collision_reward * (is_crashed ? 1.0 : 0.0);
@@ -1353,7 +1385,13 @@ network_step_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGraph* _
             if (P.normalize_reward) rew = lmap(rew, P.collision_reward, P.high_speed_reward, 0.0, 1.0);
             rew *= on_road ? 1.0 : 0.0;
             term = is_crashed;
+            rt[0] = is_crashed ? 1.0 : 0.0;
+            rt[1] = (double)st.speed_index / (double)(3 - 1);
+            rt[2] = (act == 0 || act == 2) ? 1.0 : 0.0;
+            rt[3] = on_road ? 1.0 : 0.0;
         }
+        if (S.reward_terms)
+            for (int k = 0; k < HWY_REWARD_TERMS; ++k) S.reward_terms[(size_t)e * HWY_REWARD_TERMS + k] = rt[k];
         double t = S.time[e] + 1.0 / P.policy_frequency;
         S.time[e] = t;
         S.speed_index[e] = st.speed_index;

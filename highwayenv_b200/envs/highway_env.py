@@ -26,7 +26,8 @@ from .. import _native as N
 from ..config import default_config
 from ..spaces import batch_space
 from .common.action import action_factory
-from .common.observation import observation_factory
+from .common.observation import KinematicObservation, ObservationHost, observation_factory
+from ..road.network import NetworkTable
 
 
 def _pcg64_words(seeds: Sequence[int]) -> np.ndarray:
@@ -42,7 +43,7 @@ def _pcg64_words(seeds: Sequence[int]) -> np.ndarray:
     return out
 
 
-class BatchedHighwayEnv:
+class BatchedHighwayEnv(ObservationHost):
     """``num_envs`` independent highway roads stepped by the sm_100a kernels."""
 
     ENV_ID = "highway-v0"
@@ -50,6 +51,7 @@ class BatchedHighwayEnv:
     metadata = {"render_modes": [], "autoreset_mode": "SameStep"}
 
     PERCEPTION_DISTANCE = 5.0 * 40.0  # abstract.py:56
+    REWARD_NAMES = ("collision_reward", "right_lane_reward", "high_speed_reward", "on_road_reward")  # _rewards :118-137
     _kernel_events = None  # bench.py hook: list of (start, end) CUDA events around the step kernels
 
     @classmethod
@@ -92,6 +94,14 @@ class BatchedHighwayEnv:
         """Plugin selection by ``config[...]["type"]`` (abstract.py:154-161)."""
         self.observation_type = observation_factory(self, self.config["observation"])
         self.action_type = action_factory(self, self.config["action"])
+        # the step kernel's own epilogue is Kinematics; any other plugin runs its standalone kernel after the step
+        # (envs/common/observation.py) while the kernel writes default Kinematics rows into a scratch buffer
+        self._fused_obs = KinematicObservation() if self.observation_type.standalone else self.observation_type
+        if hasattr(self.observation_type, "bind"):  # TimeToCollision: the observer's target speeds
+            if not hasattr(self.action_type, "target_speeds"):
+                raise ValueError("TimeToCollision needs an MDPVehicle observer (DiscreteMetaAction): "
+                                 "compute_ttc_grid reads vehicle.target_speeds (finite_mdp.py:104-163)")
+            self.observation_type.bind(self.config["policy_frequency"], self.action_type.target_speeds)
         self.single_observation_space = self.observation_type.space()
         self.single_action_space = self.action_type.space()
         self.observation_space = batch_space(self.single_observation_space, self.num_envs)
@@ -139,7 +149,7 @@ class BatchedHighwayEnv:
         p.lane_change_max_braking_imposed, p.lane_change_delay = 2.0, 1.0
         p.delta_lo, p.delta_hi = 3.5, 4.5
         p.perception_distance = self.PERCEPTION_DISTANCE
-        self.observation_type.fill_params(p)
+        self._fused_obs.fill_params(p)
         self.action_type.fill_params(p)
         # RoadNetwork.straight_road_network(lanes, speed_limit=30) (road/road.py:291-321) with
         # StraightLane.__init__ arithmetic (road/lane.py:183-194)
@@ -165,7 +175,8 @@ class BatchedHighwayEnv:
         vp = int(self._lib.hwy_highway_slot_stride(V))
         K = int(self._params.obs_vehicles_count)
         F = int(self._params.obs_n_features) or 5
-        key = (n, vp, K, F, int(self._params.action_type))
+        plugin_shape = tuple(self.single_observation_space.shape) if self.observation_type.standalone else None
+        key = (n, vp, K, F, int(self._params.action_type), plugin_shape)
         if self._allocated_for == key:
             return
         z = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, device=dev)  # noqa: E731
@@ -179,13 +190,20 @@ class BatchedHighwayEnv:
         self._speed_index = z(n, dtype=torch.int32)
         self._time = z(n, dtype=torch.float64)
         self._rng = z(5, n, dtype=torch.int64)  # uint64 words, bit-cast
-        self._obs = z(n, K, F, dtype=torch.float32)
-        self._final_obs = z(n, K, F, dtype=torch.float32)
+        self._fused_out = z(n, K, F, dtype=torch.float32)  # what the step / reset kernels write
+        if plugin_shape is None:
+            self._obs = self._fused_out
+            self._final_obs = z(n, K, F, dtype=torch.float32)
+        else:
+            self._obs = z(n, *plugin_shape, dtype=torch.float32)
+            self._final_obs = z(n, *plugin_shape, dtype=torch.float32)
+        self._plugin_view = None
         self._reward = z(n, dtype=torch.float64)
         self._terminated = z(n, dtype=torch.uint8)
         self._truncated = z(n, dtype=torch.uint8)
         self._info_speed = z(n, dtype=torch.float64)
         self._info_crashed = z(n, dtype=torch.uint8)
+        self._reward_terms = z(n, N.HWY_REWARD_TERMS, dtype=torch.float64)
         if self._params.action_type == 0:
             self._action_buf = z(n, dtype=torch.int32)
         else:
@@ -196,6 +214,7 @@ class BatchedHighwayEnv:
         st.delta, st.meta = self._delta.data_ptr(), self._meta.data_ptr()
         st.speed_index, st.time, st.rng = (
             self._speed_index.data_ptr(), self._time.data_ptr(), self._rng.data_ptr())
+        st.reward_terms = self._reward_terms.data_ptr()
         self._state = st
         self._allocated_for = key
         self._seeded = False
@@ -236,10 +255,12 @@ class BatchedHighwayEnv:
             mask_ptr = mask.data_ptr()
         with torch.cuda.device(self.device):
             N.check(self._lib.hwy_highway_reset(C.byref(self._params), C.byref(self._state), mask_ptr,
-                                                self._obs.data_ptr(), self._stream()))
+                                                self._fused_out.data_ptr(), self._stream()))
+        if self.observation_type.standalone:
+            self._observe_plugin(self._obs, None if mask_ptr is None else self._mask_keepalive)
         self._autoreset_envs = None
         info = {"speed": self._hs[:, 0, 1], "crashed": (self._meta[:, 0] & N.META_CRASHED) != 0}
-        return self._obs, info
+        return self._out_obs(), info
 
     def _stage_actions(self, actions) -> torch.Tensor:
         buf = self._action_buf
@@ -280,26 +301,64 @@ class BatchedHighwayEnv:
         ai = act.data_ptr() if self._params.action_type == 0 else None
         af = act.data_ptr() if self._params.action_type == 1 else None
         same_step = self.autoreset_mode == "SameStep"
+        plugin = self.observation_type.standalone
+        fused_reset = same_step and not plugin  # a standalone plugin must observe the final state before the reset
         kev = self._kernel_events
         if kev is not None:  # bench.py: CUDA events around the step kernel(s) alone
             kev.append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
             kev[-1][0].record(torch.cuda.current_stream(self.device))
         with torch.cuda.device(self.device):
             N.check(self._lib.hwy_highway_step(
-                C.byref(self._params), C.byref(self._state), ai, af, self._obs.data_ptr(),
+                C.byref(self._params), C.byref(self._state), ai, af, self._fused_out.data_ptr(),
                 self._reward.data_ptr(), self._terminated.data_ptr(), self._truncated.data_ptr(),
                 self._info_speed.data_ptr(), self._info_crashed.data_ptr(),
-                N.AUTORESET_SAME_STEP if same_step else N.AUTORESET_DISABLED,
-                self._final_obs.data_ptr() if same_step else None, self._stream()))
+                N.AUTORESET_SAME_STEP if fused_reset else N.AUTORESET_DISABLED,
+                self._final_obs.data_ptr() if fused_reset else None, self._stream()))
         if kev is not None:
             kev[-1][1].record(torch.cuda.current_stream(self.device))
-        info = {"speed": self._info_speed, "crashed": self._info_crashed.view(torch.bool), "action": act}
+        # AbstractEnv._info (abstract.py:200-217): speed, crashed, action and the un-weighted reward terms of _rewards
+        info = {"speed": self._info_speed, "crashed": self._info_crashed.view(torch.bool), "action": act,
+                "rewards": {name: self._reward_terms[:, k] for k, name in enumerate(self.REWARD_NAMES)}}
+        if plugin:
+            self._observe_plugin(self._obs)
+            if same_step:  # observe, keep as final_obs, re-spawn the finished envs, observe those again
+                self._final_obs.copy_(self._obs)
+                with torch.cuda.device(self.device):
+                    N.check(self._lib.hwy_highway_autoreset(
+                        C.byref(self._params), C.byref(self._state), self._terminated.data_ptr(),
+                        self._truncated.data_ptr(), self._fused_out.data_ptr(), self._stream()))
+                self._observe_plugin(self._obs, self._terminated, self._truncated)
         if same_step:
             info["final_obs"] = self._final_obs
         elif self.autoreset_mode == "NextStep":
             self._next_step_autoreset()
-        return (self._obs, self._reward, self._terminated.view(torch.bool),
+        return (self._out_obs(), self._reward, self._terminated.view(torch.bool),
                 self._truncated.view(torch.bool), info)
+
+    def _out_obs(self) -> torch.Tensor:
+        if getattr(self.observation_type, "as_image", False):  # OccupancyGrid(as_image=True): uint8 (observation.py:336-338)
+            return self._obs.to(torch.uint8)
+        return self._obs
+
+    def _obs_view(self):
+        """ObservationHost: the state as a HwyObsView + the lane table of RoadNetwork.straight_road_network
+        (road/road.py:291-321) as a device HwyNetGraph."""
+        if self._plugin_view is None:
+            net = NetworkTable()
+            for l in range(int(self._params.lanes_count)):
+                L = self._params.lanes[l]
+                net.add_straight("0", "1", [L.start_x, L.start_y],
+                                 [L.start_x + L.length * L.dir_x, L.start_y + L.length * L.dir_y], width=L.width,
+                                 speed_limit=L.speed_limit)
+            net.finalize()
+            self._plugin_graph = torch.from_numpy(
+                np.frombuffer(bytes(net.to_struct()), dtype=np.uint8).copy()).to(self.device)
+            v = N.HwyObsView()
+            v.n_envs, v.vp, v.n_vehicles, v.n_agents = self.num_envs, self.vp, self.V, 0
+            v.pos, v.hs, v.meta = self._pos.data_ptr(), self._hs.data_ptr(), self._meta.data_ptr()
+            v.speed_index = self._speed_index.data_ptr()
+            self._plugin_view = v
+        return self._plugin_view, self._plugin_graph.data_ptr()
 
     def _next_step_autoreset(self) -> None:
         """gymnasium AutoresetMode.NEXT_STEP (the vector default): an env that ended in the previous step is
@@ -310,7 +369,9 @@ class BatchedHighwayEnv:
         if prev is not None:
             with torch.cuda.device(self.device):
                 N.check(self._lib.hwy_highway_reset(C.byref(self._params), C.byref(self._state), prev.data_ptr(),
-                                                    self._obs.data_ptr(), self._stream()))
+                                                    self._fused_out.data_ptr(), self._stream()))
+            if self.observation_type.standalone:
+                self._observe_plugin(self._obs, prev)
             keep = prev == 0
             self._reward.mul_(keep)
             self._terminated.mul_(keep)
@@ -338,8 +399,10 @@ class BatchedHighwayEnv:
     def observe(self) -> torch.Tensor:
         with torch.cuda.device(self.device):
             N.check(self._lib.hwy_highway_observe(C.byref(self._params), C.byref(self._state),
-                                                  self._obs.data_ptr(), self._stream()))
-        return self._obs
+                                                  self._fused_out.data_ptr(), self._stream()))
+        if self.observation_type.standalone:
+            self._observe_plugin(self._obs)
+        return self._out_obs()
 
     def close(self) -> None:
         pass
@@ -430,51 +493,4 @@ def available_actions_mask(x, y, lane, speed_index, lane_table, n_speeds: int, v
     return out
 
 
-class HostStepper:
-    """`env.step` for callers that live on the host (a CPU policy, a gymnasium wrapper stack): pinned host
-    buffers for the actions and the results, and ONE CUDA graph holding the action upload, the step kernel
-    and the result downloads, so a step costs one graph launch + one stream sync instead of six API calls.
-
-        hs = env.host_stepper()
-        hs.actions[:] = policy(hs.obs)            # numpy views of pinned memory
-        obs, reward, terminated, truncated = hs.step()
-
-    The arrays returned are the stepper's own pinned buffers (overwritten by the next step).  State, RNG
-    streams and autoreset behave exactly as with `env.step` (same kernel, same buffers)."""
-
-    def __init__(self, env: "BatchedHighwayEnv") -> None:
-        if not env._seeded:
-            raise RuntimeError("call reset() before host_stepper()")
-        self.env = env
-        dev = env.device
-        table = getattr(env.action_type, "table", None)
-        if table is not None:
-            raise NotImplementedError("host_stepper with DiscreteAction (index gather) — use env.step")
-        if env.autoreset_mode == "NextStep":
-            # NextStep runs host-side control flow per call (which envs ended last time); a captured graph would
-            # replay one frozen decision
-            raise NotImplementedError("host_stepper with autoreset_mode='NextStep' — use SameStep or Disabled")
-        pin = lambda t: torch.empty(tuple(t.shape), dtype=t.dtype).pin_memory()  # noqa: E731
-        self._h_actions = pin(env._action_buf)
-        self._h_obs, self._h_reward = pin(env._obs), pin(env._reward)
-        self._h_term, self._h_trunc = pin(env._terminated), pin(env._truncated)
-        self.actions = self._h_actions.numpy()
-        self.obs, self.reward = self._h_obs.numpy(), self._h_reward.numpy()
-        self.terminated, self.truncated = self._h_term.numpy().view(np.bool_), self._h_trunc.numpy().view(np.bool_)
-        self._h_obs.copy_(env._obs)
-        self._stream = torch.cuda.Stream(device=dev)
-        self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.device(dev):
-            torch.cuda.synchronize(dev)
-            with torch.cuda.graph(self._graph, stream=self._stream):
-                env._action_buf.copy_(self._h_actions, non_blocking=True)
-                obs, reward, term, trunc, _ = env.step(env._action_buf)
-                self._h_obs.copy_(env._obs, non_blocking=True)
-                self._h_reward.copy_(env._reward, non_blocking=True)
-                self._h_term.copy_(env._terminated, non_blocking=True)
-                self._h_trunc.copy_(env._truncated, non_blocking=True)
-
-    def step(self):
-        self._graph.replay()
-        self._stream.synchronize()
-        return self.obs, self.reward, self.terminated, self.truncated
+from .common.host_stepper import HostStepper  # noqa: E402,F401  (re-export: the stepper serves every env family)

@@ -30,6 +30,8 @@ from .. import _native as N
 from ..config import default_config
 from ..road.network import NetworkTable
 from ..spaces import Box, Discrete, batch_space
+from .common.observation import (KinematicObservation, ObservationHost, OccupancyGridObservation,
+                                 observation_factory)
 
 VMAX = N.HWY_NET_GROUP_LARGE
 
@@ -70,9 +72,10 @@ def make_intersection_network() -> NetworkTable:
 _F64 = ("x", "y", "heading", "speed", "target_speed", "timer", "delta", "impact_x", "impact_y")
 
 
-class BatchedIntersectionEnv:
+class BatchedIntersectionEnv(ObservationHost):
     ENV_ID = "intersection-v0"
     MULTI_AGENT_WRAPPER = False
+    REWARD_NAMES = ("collision_reward", "high_speed_reward", "arrived_reward", "on_road_reward")  # _agent_rewards :95-105
     _kernel_events = None  # bench.py hook: list of (start, end) CUDA events around the step kernels
     metadata = {"render_modes": [], "autoreset_mode": "SameStep"}
 
@@ -138,8 +141,6 @@ class BatchedIntersectionEnv:
         longi, lat = act.get("longitudinal", True), act.get("lateral", True)
         if not longi:
             raise NotImplementedError("lateral-only meta-actions")
-        if multi and obs["type"] != "Kinematics":
-            raise NotImplementedError("MultiAgentObservation over Kinematics only")
         ts = act.get("target_speeds")
         self.target_speeds = np.linspace(20, 30, 3) if ts is None else np.array(ts, dtype=np.float64)
         if self.target_speeds.size > 3:
@@ -153,40 +154,38 @@ class BatchedIntersectionEnv:
         p.action_mode = 1 if not lat else 0
         self.single_action_space = Discrete(3 if not lat else 5)
         p.obs_features = 5
-        if obs["type"] == "OccupancyGrid":
-            for k in ("features", "grid_size", "grid_step", "features_range"):
-                if obs.get(k) is not None:
-                    raise NotImplementedError(f"OccupancyGrid option {k!r} (defaults only)")
-            if obs.get("absolute") or obs.get("align_to_vehicle_axes") or obs.get("as_image") or obs.get("clip", True) is not True:
-                raise NotImplementedError("OccupancyGrid options (defaults only)")
-            p.obs_type = N.OBS_OCCUPANCY
-            p.obs_vehicles_count = 5
-            self.single_observation_space = Box(low=-np.inf, high=np.inf, shape=(4, 11, 11), dtype=np.float32)
-        elif obs["type"] == "Kinematics":
-            feats = obs.get("features") or ["presence", "x", "y", "vx", "vy"]
+        # ---- observation plugin: the reference's factory rule (one registry, envs/common/observation.py); the step
+        # kernel writes Kinematics (5 / 7 columns) and the default OccupancyGrid itself, any other plugin observes
+        # with its standalone kernel after the step
+        plugin = observation_factory(self, obs)
+        self.observation_type = plugin
+        fused = False
+        if isinstance(plugin, OccupancyGridObservation) and plugin.is_default and not multi:
+            p.obs_type, p.obs_vehicles_count, fused = N.OBS_OCCUPANCY, 5, True
+        elif isinstance(plugin, KinematicObservation):
+            feats = plugin.features
             if feats[:5] != ["presence", "x", "y", "vx", "vy"] or feats[5:] not in ([], ["cos_h", "sin_h"]):
                 raise NotImplementedError(f"Kinematics features {feats}")
-            fr = obs.get("features_range")
-            if fr is None:
-                raise NotImplementedError("Kinematics without features_range on intersection-v0")
-            if obs.get("order", "sorted") != "sorted" or obs.get("observe_intentions"):
-                raise NotImplementedError("Kinematics order / observe_intentions")
+            if obs.get("observe_intentions"):
+                raise NotImplementedError("Kinematics observe_intentions")
+            fr = plugin.features_range
+            if fr is None:  # normalize_obs (observation.py:214-226): the controlled vehicle spawns on a one-lane road
+                fr = {"x": [-5.0 * 40.0, 5.0 * 40.0], "y": [-4.0, 4.0], "vx": [-2 * 40.0, 2 * 40.0], "vy": [-2 * 40.0, 2 * 40.0]}
             p.obs_type, p.obs_features = N.OBS_KINEMATICS, len(feats)
-            p.obs_vehicles_count = int(obs.get("vehicles_count", 5))
-            if p.obs_vehicles_count > 32:
-                raise ValueError("vehicles_count must be <= 32")
-            p.obs_see_behind = int(bool(obs.get("see_behind", False)))
-            p.obs_absolute = int(bool(obs.get("absolute", False)))
-            p.obs_normalize = int(bool(obs.get("normalize", True)))
-            p.obs_clip = int(bool(obs.get("clip", True)))
+            p.obs_vehicles_count = plugin.vehicles_count
+            p.obs_see_behind, p.obs_absolute = int(plugin.see_behind), int(plugin.absolute)
+            p.obs_normalize, p.obs_clip = int(plugin.normalize), int(plugin.clip)
             (p.obs_x_lo, p.obs_x_hi), (p.obs_y_lo, p.obs_y_hi) = (map(float, fr["x"]), map(float, fr["y"]))
             (p.obs_vx_lo, p.obs_vx_hi), (p.obs_vy_lo, p.obs_vy_hi) = (map(float, fr["vx"]), map(float, fr["vy"]))
-            shape = (p.obs_vehicles_count, len(feats))
-            self.single_observation_space = Box(low=-np.inf, high=np.inf, shape=shape, dtype=np.float32)
-        elif obs["type"] in ("TimeToCollision", "KinematicsGoal", "GrayscaleObservation", "LidarObservation"):
-            raise NotImplementedError(f"observation type {obs['type']!r} on intersection-v0")
-        else:
-            raise ValueError("Unknown observation type")
+            fused = True
+        if hasattr(plugin, "bind"):  # TimeToCollision
+            plugin.bind(p.policy_frequency, self.target_speeds)
+        self._plugin_standalone = not fused
+        if not fused:  # scratch row for the kernels' own epilogue
+            p.obs_type, p.obs_features, p.obs_vehicles_count = N.OBS_KINEMATICS, 5, 1
+            p.obs_x_lo = p.obs_y_lo = p.obs_vx_lo = p.obs_vy_lo = -1.0
+            p.obs_x_hi = p.obs_y_hi = p.obs_vx_hi = p.obs_vy_hi = 1.0
+        self.single_observation_space = plugin.space()
         p.normalize_reward = int(bool(cfg["normalize_reward"]))
         p.duration = float(cfg["duration"])
         p.collision_reward, p.high_speed_reward = float(cfg["collision_reward"]), float(cfg["high_speed_reward"])
@@ -233,6 +232,7 @@ class BatchedIntersectionEnv:
         self._time = z(n, dtype=torch.float64)
         self._count = z(n, dtype=torch.int32)
         self._road_steps = z(n, dtype=torch.int32)
+        self._reward_terms = z(n, N.HWY_REWARD_TERMS, dtype=torch.float64)
         self._overflow = z(n, dtype=torch.int32)  # spawns dropped because all 32 slots were taken (loud, see step())
         old_rng = getattr(self, "_rng", None)  # keep the env's numpy stream across a re-allocation
         self._rng = z(5, n, dtype=torch.int64)
@@ -240,6 +240,8 @@ class BatchedIntersectionEnv:
             self._rng.copy_(old_rng)
         self._obs = z(n, *self.obs_shape, dtype=torch.float32)
         self._final_obs = z(n, *self.obs_shape, dtype=torch.float32)
+        self._fused_out = z(n, A, 5, dtype=torch.float32) if self._plugin_standalone else self._obs
+        self._plugin_view = None
         self._reward = z(n, dtype=torch.float64)
         self._terminated, self._truncated = z(n, dtype=torch.uint8), z(n, dtype=torch.uint8)
         self._info_speed, self._info_crashed = z(n, dtype=torch.float64), z(n, dtype=torch.uint8)
@@ -252,6 +254,7 @@ class BatchedIntersectionEnv:
         st.speed_index, st.time = self._speed_index.data_ptr(), self._time.data_ptr()
         st.count, st.road_steps, st.rng = self._count.data_ptr(), self._road_steps.data_ptr(), self._rng.data_ptr()
         st.overflow = self._overflow.data_ptr()
+        st.reward_terms = self._reward_terms.data_ptr()
         self._state = st
         # plan_route_to(lane, "o"+k) for every lane (vehicle/controller.py:71-87)
         n_l = len(self.net.lanes)
@@ -499,13 +502,31 @@ class BatchedIntersectionEnv:
                 self._reset_envs(ids)
         self._autoreset_envs = None
         self.observe()
-        return self._obs, {"speed": self._info_speed, "crashed": self._info_crashed.view(torch.bool)}
+        return self._out_obs(), {"speed": self._info_speed, "crashed": self._info_crashed.view(torch.bool)}
 
     def observe(self) -> torch.Tensor:
         with torch.cuda.device(self.device):
             N.check(self._lib.hwy_network_observe(C.byref(self._params), self._graph_dev.data_ptr(),
-                                                  C.byref(self._state), self._obs.data_ptr(), self._stream()))
+                                                  C.byref(self._state), self._fused_out.data_ptr(), self._stream()))
+        if self._plugin_standalone:
+            self._observe_plugin(self._obs)
+        return self._out_obs()
+
+    def _out_obs(self) -> torch.Tensor:
+        if getattr(self.observation_type, "as_image", False):
+            return self._obs.to(torch.uint8)
         return self._obs
+
+    def _obs_view(self):
+        if self._plugin_view is None:
+            v = N.HwyObsView()
+            v.n_envs, v.vp, v.n_vehicles, v.n_agents = self.num_envs, self.vp, VMAX, (self.n_agents if self.multi_agent else 0)
+            v.pos, v.hs, v.meta = self._pos.data_ptr(), self._hs.data_ptr(), self._meta.data_ptr()
+            v.count = self._count.data_ptr()
+            v.route, v.route_len = self._route.data_ptr(), self._route_len.data_ptr()
+            v.speed_index = self._speed_index.data_ptr()
+            self._plugin_view = v
+        return self._plugin_view, self._graph_dev.data_ptr()
 
     def step(self, actions):
         if self._rngs is None:
@@ -530,7 +551,7 @@ class BatchedIntersectionEnv:
         with torch.cuda.device(self.device):
             N.check(self._lib.hwy_intersection_step_agents(
                 C.byref(self._params), self._graph_dev.data_ptr(), C.byref(self._spawn_struct), C.byref(self._state),
-                act.data_ptr(), self._obs.data_ptr(), self._reward.data_ptr(), self._terminated.data_ptr(),
+                act.data_ptr(), self._fused_out.data_ptr(), self._reward.data_ptr(), self._terminated.data_ptr(),
                 self._truncated.data_ptr(), self._info_speed.data_ptr(), self._info_crashed.data_ptr(),
                 self._agents_reward.data_ptr() if self.multi_agent else None,
                 self._agents_terminated.data_ptr() if self.multi_agent else None, self._stream()))
@@ -540,20 +561,31 @@ class BatchedIntersectionEnv:
         # was constructed.  The reference's vehicle list is unbounded; a non-zero entry means that env no longer
         # follows the reference (reachable only with `duration` >> 13 s or a high spawn_probability).
         info = {"speed": self._info_speed, "crashed": self._info_crashed.view(torch.bool), "action": act,
-                "spawn_overflow": self._overflow}
+                "spawn_overflow": self._overflow,
+                "rewards": {name: self._reward_terms[:, k] for k, name in enumerate(self.REWARD_NAMES)}}
         if self.multi_agent:  # IntersectionEnv._info (:124-132)
             info["agents_rewards"] = self._agents_reward
             info["agents_terminated"] = self._agents_terminated.view(torch.bool)
+        plugin = self._plugin_standalone
+        if plugin:
+            self._observe_plugin(self._obs)
         if self.autoreset_mode == "SameStep" and self.reset_mode == "device":
             info["final_obs"] = self._final_obs
-            self._device_reset(self._terminated.data_ptr(), self._truncated.data_ptr(), self._obs.data_ptr(),
-                               self._final_obs.data_ptr())
+            if plugin:
+                self._final_obs.copy_(self._obs)
+                self._device_reset(self._terminated.data_ptr(), self._truncated.data_ptr(), self._fused_out.data_ptr(), None)
+                self._observe_plugin(self._obs, self._terminated, self._truncated)
+            else:
+                self._device_reset(self._terminated.data_ptr(), self._truncated.data_ptr(), self._obs.data_ptr(),
+                                   self._final_obs.data_ptr())
         elif self.autoreset_mode == "NextStep":
             # gymnasium NEXT_STEP: envs that ended in the previous step are reset by this call instead of stepped;
             # their generator is rewound to where the episode ended, then _make_vehicles runs on the device
             if prev is not None:
                 self._rng.copy_(torch.where(prev.bool().unsqueeze(0), rng_before, self._rng))
-                self._device_reset(prev.data_ptr(), None, self._obs.data_ptr(), None)
+                self._device_reset(prev.data_ptr(), None, self._fused_out.data_ptr(), None)
+                if plugin:
+                    self._observe_plugin(self._obs, prev)
                 keep = prev == 0
                 self._reward.mul_(keep)
                 self._terminated.mul_(keep)
@@ -570,9 +602,15 @@ class BatchedIntersectionEnv:
                 self.observe()
         if self.multi_agent and self.MULTI_AGENT_WRAPPER:
             # MultiAgentWrapper.step (envs/common/abstract.py:468-477): per-agent rewards and terminal flags
-            return (self._obs, self._agents_reward, self._agents_terminated.view(torch.bool),
+            return (self._out_obs(), self._agents_reward, self._agents_terminated.view(torch.bool),
                     self._truncated.view(torch.bool), info)
-        return (self._obs, self._reward, self._terminated.view(torch.bool), self._truncated.view(torch.bool), info)
+        return (self._out_obs(), self._reward, self._terminated.view(torch.bool), self._truncated.view(torch.bool), info)
+
+    def host_stepper(self):
+        """Host-buffer stepping through one CUDA graph (envs/common/host_stepper.py)."""
+        from .common.host_stepper import HostStepper
+
+        return HostStepper(self)
 
     def close(self) -> None:
         pass

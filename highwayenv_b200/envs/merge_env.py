@@ -52,6 +52,8 @@ def make_merge_network() -> NetworkTable:
 class BatchedMergeEnv(BatchedRoundaboutEnv):
     ENV_ID = "merge-v0"
     N_VEHICLES = 6  # five vehicles + the Obstacle
+    EGO_SIDE_LANES = 2  # the controlled vehicle spawns on ("a", "b", 1): normalize_obs' default y-range (observation.py:214-226)
+    REWARD_NAMES = ("collision_reward", "right_lane_reward", "high_speed_reward", "lane_change_reward", "merging_speed_reward")  # _rewards :62-77
 
     def _make_network(self) -> NetworkTable:
         return make_merge_network()
@@ -60,24 +62,9 @@ class BatchedMergeEnv(BatchedRoundaboutEnv):
         if self.reset_mode != "device":
             raise NotImplementedError("merge envs reset on the device (hwy_merge_reset)")
         cfg = self.config
-        obs = dict(cfg["observation"])
-        if obs["type"] != "Kinematics":
-            if obs["type"] in ("TimeToCollision", "OccupancyGrid", "KinematicsGoal", "GrayscaleObservation", "LidarObservation"):
-                raise NotImplementedError(f"observation type {obs['type']!r} on {self.ENV_ID}")
-            raise ValueError("Unknown observation type")
-        if obs.get("features_range") is None:
-            # normalize_obs (observation.py:214-226) computes the ranges once, at the first observation: the
-            # controlled vehicle sits on ("a", "b", 1), a road with two side lanes
-            obs["features_range"] = {"x": [-5.0 * 40, 5.0 * 40], "y": [-4.0 * 2, 4.0 * 2],
-                                     "vx": [-2 * 40.0, 2 * 40.0], "vy": [-2 * 40.0, 2 * 40.0]}
-        saved = cfg["observation"]
-        cfg["observation"] = obs
         cfg.setdefault("normalize_reward", False)
         cfg.setdefault("duration", float("inf"))  # AbstractEnv has no duration; MergeEnv never truncates
-        try:
-            super().define_spaces()
-        finally:
-            cfg["observation"] = saved
+        super().define_spaces()
         p = self._params
         p.reward_type = 2
         p.right_lane_reward = float(cfg["right_lane_reward"])

@@ -28,6 +28,8 @@ from ..config import default_config
 from ..road.network import NetworkTable
 from ..spaces import Box, Discrete, batch_space
 from .common.action import DiscreteMetaAction
+from .common.observation import (KinematicObservation, LidarObservation, ObservationHost, OccupancyGridObservation,
+                                 TimeToCollisionObservation, observation_factory)
 
 
 def make_roundabout_network() -> NetworkTable:
@@ -147,19 +149,11 @@ class RoundaboutSpawner:
 
 
 
-class TimeToCollisionObservation:
-    """TimeToCollisionObservation (reference envs/common/observation.py:115-152): [3, 3, horizon]."""
-
-    def __init__(self, horizon: int = 10, **kwargs):
-        self.horizon = int(horizon)
-
-    def space(self, policy_frequency: int = 1):
-        return Box(low=0, high=1, shape=(3, 3, int(self.horizon * policy_frequency)), dtype=np.float32)
-
-
-class BatchedRoundaboutEnv:
+class BatchedRoundaboutEnv(ObservationHost):
     ENV_ID = "roundabout-v0"
     N_VEHICLES = 5
+    EGO_SIDE_LANES = 1  # lanes of the road the controlled vehicle spawns on (default Kinematics y-range)
+    REWARD_NAMES = ("collision_reward", "high_speed_reward", "lane_change_reward", "on_road_reward")  # _rewards :58-65
     _kernel_events = None  # bench.py hook: list of (start, end) CUDA events around the step kernels
     metadata = {"render_modes": [], "autoreset_mode": "SameStep"}
 
@@ -223,33 +217,7 @@ class BatchedRoundaboutEnv:
         p.n_target_speeds = int(self.action_type.target_speeds.size)
         for k, t in enumerate(self.action_type.target_speeds):
             p.target_speeds[k] = float(t)
-        if obs["type"] == "TimeToCollision":
-            self.observation_type = TimeToCollisionObservation(**obs)
-            p.obs_type = N.OBS_TTC
-            p.ttc_horizon = self.observation_type.horizon
-            p.obs_vehicles_count = 5
-            self.single_observation_space = self.observation_type.space(p.policy_frequency)
-        elif obs["type"] == "Kinematics":
-            fr = obs.get("features_range")
-            if fr is None:
-                raise NotImplementedError("Kinematics without features_range on roundabout-v0")
-            if obs.get("features") not in (None, ["presence", "x", "y", "vx", "vy"]) or obs.get("order", "sorted") != "sorted":
-                raise NotImplementedError("Kinematics features / order")
-            p.obs_type = N.OBS_KINEMATICS
-            p.obs_vehicles_count = int(obs.get("vehicles_count", 5))
-            p.obs_see_behind = int(bool(obs.get("see_behind", False)))
-            p.obs_absolute = int(bool(obs.get("absolute", False)))
-            p.obs_normalize = int(bool(obs.get("normalize", True)))
-            p.obs_clip = int(bool(obs.get("clip", True)))
-            (p.obs_x_lo, p.obs_x_hi), (p.obs_y_lo, p.obs_y_hi) = (map(float, fr["x"]), map(float, fr["y"]))
-            (p.obs_vx_lo, p.obs_vx_hi), (p.obs_vy_lo, p.obs_vy_hi) = (map(float, fr["vx"]), map(float, fr["vy"]))
-            self.observation_type = None
-            self.single_observation_space = Box(low=-np.inf, high=np.inf, shape=(p.obs_vehicles_count, 5),
-                                                dtype=np.float32)
-        elif obs["type"] in ("OccupancyGrid", "KinematicsGoal", "GrayscaleObservation", "LidarObservation"):
-            raise NotImplementedError(f"observation type {obs['type']!r} on roundabout-v0")
-        else:
-            raise ValueError("Unknown observation type")
+        self._configure_observation(p, obs)
         p.normalize_reward = int(bool(cfg["normalize_reward"]))
         p.duration = float(cfg["duration"])
         p.collision_reward = float(cfg["collision_reward"])
@@ -268,6 +236,67 @@ class BatchedRoundaboutEnv:
         self.action_space = batch_space(self.single_action_space, self.num_envs)
         self.obs_shape = tuple(self.single_observation_space.shape)
 
+    # ------------------------------------------------------------------ observation plugin (one registry, any env)
+    FUSED_TTC_MAX_T, FUSED_TTC_MAX_SPEEDS = 16, 3  # EnvStage's shared TimeToCollision grid (hwy_network.cu)
+
+    def _configure_observation(self, p, obs: dict) -> None:
+        """Select the plugin with the reference's factory rule; decide whether the step kernel writes it itself
+        (fused: Kinematics with 5 / 7 columns, the default OccupancyGrid, TimeToCollision up to 16 time cells) or a
+        standalone kernel runs after the step (envs/common/observation.py)."""
+        plugin = observation_factory(self, obs)
+        self.observation_type = plugin
+        fused = False
+        if isinstance(plugin, TimeToCollisionObservation):
+            plugin.bind(p.policy_frequency, self.action_type.target_speeds)
+            n_t = plugin.horizon * p.policy_frequency
+            if n_t <= self.FUSED_TTC_MAX_T and p.n_target_speeds <= self.FUSED_TTC_MAX_SPEEDS:
+                p.obs_type, p.ttc_horizon, p.obs_vehicles_count, fused = N.OBS_TTC, plugin.horizon, 5, True
+        elif isinstance(plugin, OccupancyGridObservation):
+            if plugin.is_default:
+                p.obs_type, p.obs_vehicles_count, fused = N.OBS_OCCUPANCY, 5, True
+        elif isinstance(plugin, KinematicObservation):
+            feats = plugin.features
+            if feats[:5] != ["presence", "x", "y", "vx", "vy"] or feats[5:] not in ([], ["cos_h", "sin_h"]):
+                raise NotImplementedError(f"Kinematics features {feats} on the network kernels "
+                                          "(presence, x, y, vx, vy [, cos_h, sin_h])")
+            if obs.get("observe_intentions"):
+                raise NotImplementedError("Kinematics observe_intentions on the network kernels")
+            fr = plugin.features_range
+            if fr is None:  # normalize_obs (observation.py:214-226), computed at the first observation of an episode:
+                w = 4.0 * self.EGO_SIDE_LANES  # all_side_lanes of the controlled vehicle's spawn road
+                fr = {"x": [-5.0 * 40.0, 5.0 * 40.0], "y": [-w, w], "vx": [-2 * 40.0, 2 * 40.0], "vy": [-2 * 40.0, 2 * 40.0]}
+            p.obs_type, p.obs_features = N.OBS_KINEMATICS, len(feats)
+            p.obs_vehicles_count = plugin.vehicles_count
+            p.obs_see_behind, p.obs_absolute = int(plugin.see_behind), int(plugin.absolute)
+            p.obs_normalize, p.obs_clip = int(plugin.normalize), int(plugin.clip)
+            (p.obs_x_lo, p.obs_x_hi), (p.obs_y_lo, p.obs_y_hi) = (map(float, fr["x"]), map(float, fr["y"]))
+            (p.obs_vx_lo, p.obs_vx_hi), (p.obs_vy_lo, p.obs_vy_hi) = (map(float, fr["vx"]), map(float, fr["vy"]))
+            fused = True
+        self._plugin_standalone = not fused
+        if not fused:  # the step kernel writes one Kinematics row into a scratch buffer; the plugin observes after it
+            p.obs_type, p.obs_features, p.obs_vehicles_count = N.OBS_KINEMATICS, 5, 1
+            p.obs_x_lo = p.obs_y_lo = p.obs_vx_lo = p.obs_vy_lo = -1.0
+            p.obs_x_hi = p.obs_y_hi = p.obs_vx_hi = p.obs_vy_hi = 1.0
+        self.single_observation_space = plugin.space()
+
+    def _obs_view(self):
+        if getattr(self, "_plugin_view", None) is None:
+            v = N.HwyObsView()
+            v.n_envs, v.vp, v.n_vehicles = self.num_envs, self.vp, self.N_VEHICLES
+            v.n_agents = int(getattr(self._params, "n_agents", 0))
+            v.pos, v.hs, v.meta = self._pos.data_ptr(), self._hs.data_ptr(), self._meta.data_ptr()
+            cnt = getattr(self, "_count", None)
+            v.count = None if cnt is None else cnt.data_ptr()
+            v.route, v.route_len = self._route.data_ptr(), self._route_len.data_ptr()
+            v.speed_index = self._speed_index.data_ptr()
+            self._plugin_view = v
+        return self._plugin_view, self._graph_dev.data_ptr()
+
+    def _out_obs(self) -> torch.Tensor:
+        if getattr(self.observation_type, "as_image", False):
+            return self._obs.to(torch.uint8)
+        return self._obs
+
     def _allocate(self) -> None:
         n, dev, vp = self.num_envs, self.device, N.HWY_NET_GROUP
         z = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, device=dev)  # noqa: E731
@@ -281,11 +310,16 @@ class BatchedRoundaboutEnv:
         self._time = z(n, dtype=torch.float64)
         self._obs = z(n, *self.obs_shape, dtype=torch.float32)
         self._final_obs = z(n, *self.obs_shape, dtype=torch.float32)
+        # what the step / reset / observe kernels write: the observation itself, or a scratch row when a standalone
+        # plugin observes after them
+        self._fused_out = z(n, 5, dtype=torch.float32) if self._plugin_standalone else self._obs
+        self._plugin_view = None
         self._reward = z(n, dtype=torch.float64)
         self._terminated = z(n, dtype=torch.uint8)
         self._truncated = z(n, dtype=torch.uint8)
         self._info_speed = z(n, dtype=torch.float64)
         self._info_crashed = z(n, dtype=torch.uint8)
+        self._reward_terms = z(n, N.HWY_REWARD_TERMS, dtype=torch.float64)
         self._action_buf = z(n, dtype=torch.int32)
         # numpy PCG64 words (device reset mode).  A re-allocation (reset(options={"config": ...})) must keep the
         # env's stream: the reference's np_random survives a reset without a seed (abstract.py:219-249)
@@ -300,6 +334,7 @@ class BatchedRoundaboutEnv:
         st.delta, st.meta = self._delta.data_ptr(), self._meta.data_ptr()
         st.route, st.route_len = self._route.data_ptr(), self._route_len.data_ptr()
         st.speed_index, st.time = self._speed_index.data_ptr(), self._time.data_ptr()
+        st.reward_terms = self._reward_terms.data_ptr()
         self._state = st
 
     def _build_spawn_tables(self) -> None:
@@ -402,13 +437,15 @@ class BatchedRoundaboutEnv:
                 self._upload(ids, self._spawn(ids))
         self._autoreset_envs = None
         self.observe()
-        return self._obs, {"speed": self._hs[:, 0, 1], "crashed": (self._meta[:, 0] & N.META_CRASHED) != 0}
+        return self._out_obs(), {"speed": self._hs[:, 0, 1], "crashed": (self._meta[:, 0] & N.META_CRASHED) != 0}
 
     def observe(self) -> torch.Tensor:
         with torch.cuda.device(self.device):
             N.check(self._lib.hwy_network_observe(C.byref(self._params), self._graph_dev.data_ptr(),
-                                                  C.byref(self._state), self._obs.data_ptr(), self._stream()))
-        return self._obs
+                                                  C.byref(self._state), self._fused_out.data_ptr(), self._stream()))
+        if self._plugin_standalone:
+            self._observe_plugin(self._obs)
+        return self._out_obs()
 
     def step(self, actions):
         if self._rngs is None:
@@ -431,20 +468,28 @@ class BatchedRoundaboutEnv:
         with torch.cuda.device(self.device):
             N.check(self._lib.hwy_network_step(
                 C.byref(self._params), self._graph_dev.data_ptr(), C.byref(self._state), act.data_ptr(),
-                self._obs.data_ptr(), self._reward.data_ptr(), self._terminated.data_ptr(),
+                self._fused_out.data_ptr(), self._reward.data_ptr(), self._terminated.data_ptr(),
                 self._truncated.data_ptr(), self._info_speed.data_ptr(), self._info_crashed.data_ptr(),
                 self._stream()))
         if kev is not None:
             kev[-1][1].record(torch.cuda.current_stream(self.device))
-        info = {"speed": self._info_speed, "crashed": self._info_crashed.view(torch.bool), "action": act}
+        info = {"speed": self._info_speed, "crashed": self._info_crashed.view(torch.bool), "action": act,
+                "rewards": {name: self._reward_terms[:, k] for k, name in enumerate(self.REWARD_NAMES)}}
+        plugin = self._plugin_standalone
+        if plugin:
+            self._observe_plugin(self._obs)
         if self.autoreset_mode == "SameStep" and self.reset_mode == "device":
             self._final_obs.copy_(self._obs)
             info["final_obs"] = self._final_obs
-            self._device_reset(self._terminated.data_ptr(), self._truncated.data_ptr(), self._obs.data_ptr())
+            self._device_reset(self._terminated.data_ptr(), self._truncated.data_ptr(), self._fused_out.data_ptr())
+            if plugin:
+                self._observe_plugin(self._obs, self._terminated, self._truncated)
         elif self.autoreset_mode == "NextStep":  # see BatchedHighwayEnv._next_step_autoreset
             prev = getattr(self, "_autoreset_envs", None)
             if prev is not None:
-                self._device_reset(prev.data_ptr(), None, self._obs.data_ptr())
+                self._device_reset(prev.data_ptr(), None, self._fused_out.data_ptr())
+                if plugin:
+                    self._observe_plugin(self._obs, prev)
                 keep = prev == 0
                 self._reward.mul_(keep)
                 self._terminated.mul_(keep)
@@ -458,7 +503,13 @@ class BatchedRoundaboutEnv:
                 ids = np.nonzero(done)[0]
                 self._upload(ids, self._spawn(ids))
                 self.observe()
-        return (self._obs, self._reward, self._terminated.view(torch.bool), self._truncated.view(torch.bool), info)
+        return (self._out_obs(), self._reward, self._terminated.view(torch.bool), self._truncated.view(torch.bool), info)
+
+    def host_stepper(self):
+        """Host-buffer stepping through one CUDA graph (envs/common/host_stepper.py)."""
+        from .common.host_stepper import HostStepper
+
+        return HostStepper(self)
 
     def close(self) -> None:
         pass

@@ -31,6 +31,8 @@ def make_two_way_network(length: float = 800) -> NetworkTable:
 class BatchedTwoWayEnv(BatchedRoundaboutEnv):
     ENV_ID = "two-way-v0"
     N_VEHICLES = 6
+    EGO_SIDE_LANES = 2  # ("a", "b", 0 / 1)
+    REWARD_NAMES = ("high_speed_reward", "left_lane_reward")  # _rewards :50-59
 
     def _make_network(self) -> NetworkTable:
         return make_two_way_network()
@@ -39,8 +41,6 @@ class BatchedTwoWayEnv(BatchedRoundaboutEnv):
         if self.reset_mode != "device":
             raise NotImplementedError("two-way-v0 resets on the device (hwy_two_way_reset)")
         cfg = self.config
-        if cfg["observation"]["type"] == "Kinematics" and cfg["observation"].get("features_range") is None:
-            raise NotImplementedError("Kinematics without features_range on two-way-v0")
         for key, default in (("normalize_reward", False), ("duration", float("inf")), ("lane_change_reward", 0.0)):
             cfg.setdefault(key, default)  # AbstractEnv has none of these; TwoWayEnv never truncates
         super().define_spaces()

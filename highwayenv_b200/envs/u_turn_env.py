@@ -38,6 +38,8 @@ def make_u_turn_network(length: float = 128) -> NetworkTable:
 class BatchedUTurnEnv(BatchedRoundaboutEnv):
     ENV_ID = "u-turn-v0"
     N_VEHICLES = 7
+    EGO_SIDE_LANES = 2  # ("a", "b", 0 / 1)
+    REWARD_NAMES = ("collision_reward", "left_lane_reward", "high_speed_reward", "on_road_reward")  # _rewards :61-72
     # _make_vehicles (:203-275): (lane, longitudinal, speed) of the six IDM vehicles
     TRAFFIC = [(("a", "b", 0), 25.0, 13.5), (("a", "b", 1), 56.0, 14.5), (("b", "c", 1), 0.5, 4.5),
                (("b", "c", 0), 17.5, 5.5), (("c", "d", 0), 1.0, 3.5), (("c", "d", 1), 30.0, 5.5)]
@@ -49,8 +51,6 @@ class BatchedUTurnEnv(BatchedRoundaboutEnv):
         if self.reset_mode != "device":
             raise NotImplementedError("u-turn-v0 resets on the device (hwy_u_turn_reset)")
         cfg = self.config
-        if cfg["observation"]["type"] == "Kinematics" and cfg["observation"].get("features_range") is None:
-            raise NotImplementedError("Kinematics without features_range on u-turn-v0")
         cfg.setdefault("lane_change_reward", 0.0)
         super().define_spaces()
         p = self._params

@@ -59,6 +59,58 @@ class NetworkTable:
                     priority=int(priority))
         self._add(_from, _to, lane)
 
+    # ------------------------------------------------------------------ (de)serialisation
+    _CLASS_PATHS = {N.LANE_STRAIGHT: "highway_env.road.lane.StraightLane", N.LANE_SINE: "highway_env.road.lane.SineLane",
+                    N.LANE_CIRCULAR: "highway_env.road.lane.CircularLane"}
+
+    def to_config(self) -> dict:
+        """RoadNetwork.to_config (road/road.py:379-389) with AbstractLane.to_config of each lane class
+        (road/lane.py:221-233, 296-309, 369-384): {from: {to: [{"class_path", "config"}, ...]}} in insertion order.
+        `line_types` (a rendering attribute) is emitted only when the lane was given one."""
+        out: dict = {}
+        for f, tos in self._graph.items():
+            out[f] = {}
+            for t, lanes in tos.items():
+                out[f][t] = []
+                for L in lanes:
+                    if L["type"] == N.LANE_CIRCULAR:
+                        cfg = {"center": [L["cx"], L["cy"]], "radius": L["radius"], "start_phase": L["start_phase"],
+                               "end_phase": L["end_phase"], "clockwise": L["direction"] > 0}
+                    else:
+                        cfg = {"start": [L["sx"], L["sy"]], "end": [L["ex"], L["ey"]]}
+                    cfg.update(width=L["width"], forbidden=bool(L["forbidden"]), speed_limit=L["speed_limit"],
+                               priority=L["priority"])
+                    if L.get("line_types") is not None:
+                        cfg["line_types"] = L["line_types"]
+                    if L["type"] == N.LANE_SINE:
+                        cfg.update(amplitude=L["amplitude"], pulsation=L["pulsation"], phase=L["phase"])
+                    out[f][t].append({"class_path": self._CLASS_PATHS[L["type"]], "config": cfg})
+        return out
+
+    @classmethod
+    def from_config(cls, config: dict) -> "NetworkTable":
+        """RoadNetwork.from_config (road/road.py:370-377): rebuilds the table from the reference's (or our) dict
+        through the same constructors, so the lane parameters come out bit-identical."""
+        net = cls()
+        for f, tos in config.items():
+            for t, lanes in tos.items():
+                for ld in lanes:
+                    name, c = ld["class_path"].rsplit(".", 1)[-1], dict(ld["config"])
+                    common = dict(width=float(c.get("width", 4.0)), forbidden=bool(c.get("forbidden", False)),
+                                  speed_limit=float(c.get("speed_limit", 20.0)), priority=int(c.get("priority", 0)))
+                    if name == "CircularLane":
+                        net.add_circular(f, t, c["center"], c["radius"], c["start_phase"], c["end_phase"],
+                                         clockwise=bool(c.get("clockwise", True)), **common)
+                    elif name in ("StraightLane", "SineLane"):
+                        sine = (c["amplitude"], c["pulsation"], c["phase"]) if name == "SineLane" else None
+                        net.add_straight(f, t, c["start"], c["end"], sine=sine, **common)
+                    else:
+                        raise NotImplementedError(f"lane class {ld['class_path']!r} (PolyLane) is not on the accelerated path")
+                    if c.get("line_types") is not None:
+                        net._graph[f][t][-1]["line_types"] = list(c["line_types"])
+        net.finalize()
+        return net
+
     # ------------------------------------------------------------------ tables
     def finalize(self) -> None:
         self.node_id: Dict[str, int] = {}

@@ -26,11 +26,12 @@
 extern "C" {
 #endif
 
-#define HWY_ABI_VERSION 7
+#define HWY_ABI_VERSION 8
 #define HWY_MAX_LANES 8
 #define HWY_MAX_TARGET_SPEEDS 8
 #define HWY_MAX_VEHICLES 128 /* per env, incl. the ego */
 #define HWY_MAX_OBS_VEHICLES 16
+#define HWY_REWARD_TERMS 5 /* slots of the reward_terms rows (info["rewards"]) */
 
 /* vehicle kinds (bits 19-20 of `meta`) */
 #define HWY_KIND_IDM 0     /* highway_env/vehicle/behavior.py:12   IDMVehicle */
@@ -138,6 +139,9 @@ typedef struct HwyHighwayState {
     int32_t *speed_index;        /* [n_envs * max(1, n_agents)] MDPVehicle.speed_index of each controlled vehicle */
     double *time;                /* [n_envs] */
     uint64_t *rng;               /* [5*n_envs] */
+    double *reward_terms;        /* [n_envs*HWY_REWARD_TERMS] or NULL: the un-weighted terms of AbstractEnv._rewards
+                                  * (info["rewards"], abstract.py:213-216) of the step, before any autoreset.
+                                  * highway: collision, right_lane, high_speed, on_road (highway_env.py:118-137) */
 } HwyHighwayState;
 
 int hwy_abi_version(void);
@@ -276,6 +280,11 @@ typedef struct HwyNetState {
     int32_t *count;              /* [n_envs] vehicles currently on the road; NULL: always n_vehicles */
     int32_t *road_steps;         /* [n_envs] RegulatedRoad.steps; NULL when not regulated */
     uint64_t *rng;               /* [5*n_envs] numpy PCG64 stream (layout as HwyHighwayState.rng); NULL if unused */
+    double *reward_terms;        /* [n_envs*HWY_REWARD_TERMS] or NULL: un-weighted terms of _rewards (info["rewards"]) by
+                                  * reward_type: 0 roundabout {collision, high_speed, lane_change, on_road}; 1 intersection
+                                  * {collision, high_speed, arrived, on_road} (mean over the agents); 2 merge {collision,
+                                  * right_lane, high_speed, lane_change, merging_speed}; 3 two-way {high_speed, left_lane};
+                                  * 4 u-turn {collision, left_lane, high_speed, on_road} */
     int32_t *overflow;           /* [n_envs] or NULL: vehicles that _spawn_vehicle accepted but that found every slot of
                                   * the env taken (the reference's list is unbounded; HWY_NET_GROUP_LARGE slots here).
                                   * Incremented by the step / reset kernels, never cleared by them: a non-zero entry

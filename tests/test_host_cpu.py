@@ -33,10 +33,11 @@ def test_struct_layout_matches_header():
 
     from highwayenv_b200 import _native as N
 
-    src = ('#include <stdio.h>\n#include "hwyb200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", '
+    src = ('#include <stdio.h>\n#include "hwyb200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", '
            'sizeof(HwyHighwayParams), sizeof(HwyHighwayState), sizeof(HwyStraightLane), sizeof(HwyNetLane), '
            'sizeof(HwyNetGraph), sizeof(HwyNetParams), sizeof(HwyNetState), sizeof(HwyIntersectionSpawn), '
-           'sizeof(HwyRoundaboutSpawn));return 0;}\n')
+           'sizeof(HwyRoundaboutSpawn), sizeof(HwyObsView), sizeof(HwyGridParams), sizeof(HwyTtcParams), '
+           'sizeof(HwyLidarParams));return 0;}\n')
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "t.c"), "w").write(src)
         exe = os.path.join(d, "t")
@@ -44,7 +45,8 @@ def test_struct_layout_matches_header():
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
     assert sizes == [C.sizeof(t) for t in (N.HwyHighwayParams, N.HwyHighwayState, N.HwyStraightLane, N.HwyNetLane,
                                            N.HwyNetGraph, N.HwyNetParams, N.HwyNetState, N.HwyIntersectionSpawn,
-                                           N.HwyRoundaboutSpawn)]
+                                           N.HwyRoundaboutSpawn, N.HwyObsView, N.HwyGridParams, N.HwyTtcParams,
+                                           N.HwyLidarParams)]
 
 
 def test_abi_validation_without_gpu():
@@ -117,7 +119,17 @@ def test_plugin_factories():
     with pytest.raises(ValueError, match="Unknown observation type"):
         observation_factory(None, {"type": "Nope"})
     with pytest.raises(NotImplementedError):
-        observation_factory(None, {"type": "OccupancyGrid"})
+        observation_factory(None, {"type": "GrayscaleObservation"})  # needs the renderer
+    # one registry for every env family (reference observation.py:772-794): the spaces follow the reference's
+    g = observation_factory(None, {"type": "OccupancyGrid", "grid_size": [[-300, 300], [-10, 10]], "grid_step": [2, 2]})
+    assert g.space().shape == (4, 300, 10) and g.standalone  # the reference's own test (tests/envs/test_observations.py:27-42)
+    assert observation_factory(None, {"type": "OccupancyGrid"}).is_default
+    assert observation_factory(None, {"type": "OccupancyGrid", "as_image": True}).space().dtype == np.uint8
+    assert observation_factory(None, {"type": "TimeToCollision", "horizon": 7}).space().shape == (3, 3, 7)
+    li = observation_factory(None, {"type": "LidarObservation", "cells": 24, "normalize": False, "maximum_range": 80})
+    assert li.space().shape == (24, 2) and float(li.space().high.max()) == 80.0
+    with pytest.raises(NotImplementedError):
+        observation_factory(None, {"type": "OccupancyGrid", "absolute": True})  # as the reference's observe()
     # DiscreteAction (action.py:165-196): 3 x 3 grid over [-1, 1]^2 in itertools.product order, float32
     d = action_factory(None, {"type": "DiscreteAction"})
     assert d.space().n == 9 and d.table.dtype == np.float32
