@@ -130,6 +130,62 @@ __device__ __forceinline__ void stage_graph(GraphShared& gs, const HwyNetGraph* 
     int* dst = reinterpret_cast<int*>(&gs);
     for (int k = threadIdx.x; k < (int)(sizeof(HwyNetGraph) / sizeof(int)); k += blockDim.x) dst[k] = src[k];
     __syncthreads();
+    // CircularLane rows do not use the StraightLane fields: the shared copy keeps the arc's two end points there
+    // (position(0, 0) and position(length, 0)), for the closest-lane search's lower bound (closest_lane_lower_bound)
+    for (int l = threadIdx.x; l < gs.n_lanes; l += blockDim.x) {
+        HwyNetLane& L = gs.lanes[l];
+        if (L.type != HWY_LANE_CIRCULAR) continue;
+        double sn, cs;
+        sincos(L.start_phase, &sn, &cs);
+        L.sx = L.cx + L.radius * cs;
+        L.sy = L.cy + L.radius * sn;
+        sincos(L.end_phase, &sn, &cs);
+        L.ex = L.cx + L.radius * cs;
+        L.ey = L.cy + L.radius * sn;
+    }
+    __syncthreads();
+}
+
+// A lower bound of lane.distance_with_heading(position, heading) (road/lane.py:132-143) that needs no atan2 / sin:
+//   d = |lateral| + max(s - length, 0) + max(-s, 0) + |angle|   (all terms >= 0; fp addition of non-negative terms is
+//   monotone, so dropping terms or replacing one by something smaller can only lower the sum).
+// Straight: the first three terms themselves (exact).  Sine: |lateral| >= |straight lateral| - |amplitude| (1e-9 m
+// covers the rounding of that subtraction), same longitudinal terms.  Circular: |lateral| = |radius - r|; and when the
+// point lies outside the arc's angular sector (arcs shorter than pi; decided with cross products against the end
+// points' radial vectors, with a margin that can only misjudge towards "inside"), |lateral| + the arc length beyond the
+// violated end >= |p - q| + chord(q, end) >= |p - end| for its radial projection q, so the distance to the NEARER end
+// point (minus 1e-9 m for rounding) bounds d from below whichever end the reference's phase wrap picks.
+// `cache`: (cx, cy, r) of the last circular lane evaluated — the ring arcs of a roundabout share one centre.
+struct CircleCache {
+    double cx, cy, r;
+    bool valid;
+};
+__device__ __forceinline__ double closest_lane_lower_bound(const HwyNetLane& L, double x, double y, CircleCache& cache) {
+    if (L.type == HWY_LANE_CIRCULAR) {
+        const double wx = x - L.cx, wy = y - L.cy;
+        if (!(cache.valid && cache.cx == L.cx && cache.cy == L.cy)) {
+            cache.cx = L.cx;
+            cache.cy = L.cy;
+            cache.r = norm2(wx, wy);
+            cache.valid = true;
+        }
+        double lb = fabs(L.direction * (L.radius - cache.r));
+        if (fabs(L.end_phase - L.start_phase) < 3.0) {
+            const double usx = L.sx - L.cx, usy = L.sy - L.cy, uex = L.ex - L.cx, uey = L.ey - L.cy;
+            const double c_s = L.direction * (usx * wy - usy * wx);  // > 0: past the start point in travel direction
+            const double c_e = L.direction * (wx * uey - wy * uex);  // > 0: before the end point
+            if (c_s < -1e-6 || c_e < -1e-6) {
+                const double ds = norm2(x - L.sx, y - L.sy), de = norm2(x - L.ex, y - L.ey);
+                lb = fmax(lb, fmin(ds, de) - 1e-9);
+            }
+        }
+        return lb;
+    }
+    const double ddx = x - L.sx, ddy = y - L.sy;
+    double lat = fabs(dot2(ddx, ddy, L.lx, L.ly));
+    if (L.type == HWY_LANE_SINE) lat = lat - fabs(L.amplitude) - 1e-9;
+    const double lon = dot2(ddx, ddy, L.dx, L.dy);
+    return lat + fmax(lon - L.length, 0.0) + fmax(0.0 - lon, 0.0);
 }
 
 }  // namespace hwynet

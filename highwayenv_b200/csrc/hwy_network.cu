@@ -398,17 +398,11 @@ __device__ __forceinline__ void closest_lane_group(const GraphShared& g, EnvStag
     phase_sync<G>();
     if (active) {
         const int hint = bl;
+        CircleCache cc = {0.0, 0.0, 0.0, false};
         for (int l = 0; l < g.n_lanes; ++l) {
             if (l == hint) continue;
             const HwyNetLane& L = g.lanes[l];
-            double lb;
-            if (L.type == HWY_LANE_CIRCULAR)
-                lb = fabs(L.direction * (L.radius - norm2(x - L.cx, y - L.cy)));
-            else if (L.type == HWY_LANE_STRAIGHT)
-                lb = fabs(dot2(x - L.sx, y - L.sy, L.lx, L.ly));
-            else  // SineLane: lateral = straight lateral - amplitude * sin(..), so |lateral| >= |straight lateral| -
-                  // |amplitude|; 1e-9 m covers the rounding of that subtraction (the other bounds are exact)
-                lb = fabs(dot2(x - L.sx, y - L.sy, L.lx, L.ly)) - fabs(L.amplitude) - 1e-9;
+            const double lb = closest_lane_lower_bound(L, x, y, cc);
             if (lb > bd) continue;
             int slot = atomicAdd(&st.n_cand, 1);
             if (slot < K) {

@@ -25,58 +25,58 @@ OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 
 # name -> (env_id, config override, seeds, n_steps, action kind)
 CASES = {
     # BASELINE.json configs[0]: highway-fast-v0 defaults (V = 21)
-    "highway_fast_v20": ("highway-fast-v0", None, list(range(6)), 30, "discrete5"),
+    "highway_fast_v20": ("highway-fast-v0", None, list(range(32)), 30, "discrete5"),
     # configs[1]: highway-fast-v0, vehicles_count = 50 (V = 51)
-    "highway_fast_v50": ("highway-fast-v0", {"vehicles_count": 50}, list(range(100, 106)), 30, "discrete5"),
+    "highway_fast_v50": ("highway-fast-v0", {"vehicles_count": 50}, list(range(100, 132)), 30, "discrete5"),
     # highway-v0 defaults: all-pairs collisions, 15 substeps, 4 lanes
-    "highway_v50": ("highway-v0", None, list(range(200, 203)), 20, "discrete5"),
+    "highway_v50": ("highway-v0", None, list(range(200, 232)), 20, "discrete5"),
     # configs[4] shape: highway-v0, vehicles_count = 100, ContinuousAction (V = 101)
     "highway_v100_continuous": (
         "highway-v0",
         {"vehicles_count": 100, "action": {"type": "ContinuousAction"}},
-        list(range(300, 303)),
+        list(range(300, 316)),
         12,
         "box2",
     ),
     # (f)2 plugins on the same path: DiscreteAction (action.py:165-196) and the full Kinematics feature list
     "highway_discrete_action": ("highway-v0", {"vehicles_count": 20, "action": {"type": "DiscreteAction"}},
-                                list(range(800, 804)), 15, "discrete9"),
+                                list(range(800, 832)), 15, "discrete9"),
     "highway_fast_features": (
         "highway-fast-v0",
         {"observation": {"type": "Kinematics", "vehicles_count": 7, "see_behind": True,
                          "features": ["presence", "x", "y", "vx", "vy", "heading", "cos_h", "sin_h", "cos_d", "sin_d",
                                       "long_off", "lat_off", "ang_off"]}},
-        list(range(810, 814)), 20, "discrete5"),
+        list(range(810, 842)), 20, "discrete5"),
     "highway_fast_features_range": (
         "highway-fast-v0",
         {"observation": {"type": "Kinematics", "vehicles_count": 4, "absolute": True, "clip": False,
                          "features": ["x", "lat_off", "presence", "vx", "heading", "long_off"],
                          "features_range": {"x": [-100, 1500], "vx": [0, 45], "long_off": [0, 2000],
                                             "heading": [-1, 1], "vy": [-3, 3]}}},
-        list(range(820, 824)), 20, "discrete5"),
+        list(range(820, 852)), 20, "discrete5"),
     # roundabout-v0 defaults (Kinematics absolute) and BASELINE configs[3] shape (TimeToCollision)
-    "roundabout_kin": ("roundabout-v0", None, list(range(400, 406)), 11, "discrete5"),
+    "roundabout_kin": ("roundabout-v0", None, list(range(400, 432)), 11, "discrete5"),
     "roundabout_ttc": ("roundabout-v0", {"observation": {"type": "TimeToCollision", "horizon": 10}},
-                       list(range(500, 506)), 11, "discrete5"),
+                       list(range(500, 532)), 11, "discrete5"),
     # intersection-v0 defaults (Kinematics, 7 features) and BASELINE configs[2] shape (OccupancyGrid)
-    "intersection_kin": ("intersection-v0", None, list(range(600, 606)), 13, "discrete3"),
+    "intersection_kin": ("intersection-v0", None, list(range(600, 632)), 13, "discrete3"),
     "intersection_grid": ("intersection-v0", {"observation": {"type": "OccupancyGrid"}},
-                          list(range(700, 706)), 13, "discrete3"),
+                          list(range(700, 732)), 13, "discrete3"),
     # (f)3 connected-lane neighbour search (ConnectedLaneNeighboursMixin, abstract.py:26-37; road.py:509-529)
-    "roundabout_v1_kin": ("roundabout-v1", None, list(range(900, 906)), 11, "discrete5"),
-    "intersection_v2_kin": ("intersection-v2", None, list(range(910, 916)), 13, "discrete3"),
+    "roundabout_v1_kin": ("roundabout-v1", None, list(range(900, 932)), 11, "discrete5"),
+    "intersection_v2_kin": ("intersection-v2", None, list(range(910, 942)), 13, "discrete3"),
     # (f)2 MultiAgentAction / MultiAgentObservation: two controlled vehicles
-    "intersection_multi_agent": ("intersection-multi-agent-v0", None, list(range(920, 926)), 13, "discrete3x2"),
+    "intersection_multi_agent": ("intersection-multi-agent-v0", None, list(range(920, 952)), 13, "discrete3x2"),
     # (f)3 scenario builders on the same kernels: merge-v0 (straight + sine lanes, an Obstacle at the ramp's end)
-    "merge_kin": ("merge-v0", None, list(range(930, 938)), 18, "discrete5"),
-    "merge_v1_kin": ("merge-v1", None, list(range(940, 944)), 18, "discrete5"),
+    "merge_kin": ("merge-v0", None, list(range(930, 962)), 18, "discrete5"),
+    "merge_v1_kin": ("merge-v1", None, list(range(940, 972)), 18, "discrete5"),
     # two-way-v0: oncoming traffic on ("b","a",0), IDM vehicles with enable_lane_change=False, TimeToCollision horizon 5
-    "two_way_ttc": ("two-way-v0", None, list(range(960, 968)), 15, "discrete5"),
+    "two_way_ttc": ("two-way-v0", None, list(range(960, 992)), 15, "discrete5"),
     # u-turn-v0: circular U-turn, routed traffic, ego with PURSUIT_TAU = TAU_HEADING, TimeToCollision horizon 16
-    "u_turn_ttc": ("u-turn-v0", None, list(range(970, 978)), 10, "discrete5"),
-    "u_turn_v1_ttc": ("u-turn-v1", None, list(range(980, 984)), 10, "discrete5"),
+    "u_turn_ttc": ("u-turn-v0", None, list(range(970, 1002)), 10, "discrete5"),
+    "u_turn_v1_ttc": ("u-turn-v1", None, list(range(980, 1012)), 10, "discrete5"),
     # the merging vehicle is moved onto the end of the ramp at speed: it runs into the Obstacle (objects.py:104-107)
-    "merge_obstacle_hit": ("merge-v0", None, list(range(950, 954)), 6, "discrete5"),
+    "merge_obstacle_hit": ("merge-v0", None, list(range(950, 982)), 6, "discrete5"),
 }
 
 

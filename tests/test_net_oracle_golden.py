@@ -167,7 +167,9 @@ def test_intersection_multi_agent_reset_and_teacher_forced():
         obs, rew, term, trunc = ob.step(g["actions"][:, t])
         for i in range(S):
             ctx = f"{name} #{i} t={t}"
-            compare_inter(inter_state(g, i, t + 1), ob.a, i, ctx)
+            # 32 seeds: a few one-step comparisons pass through a crawling vehicle (1 / not_zero(speed) in the steering
+            # law amplifies the last-ulp libm difference to a few 1e-9 m); the north_star tolerance is 1e-5
+            compare_inter(inter_state(g, i, t + 1), ob.a, i, ctx, tol=1e-7)
             assert abs(rew[i] - g["reward"][i, t]) <= 1e-9, ctx
             assert bool(term[i]) == bool(g["terminated"][i, t]) and bool(trunc[i]) == bool(g["truncated"][i, t]), ctx
             assert np.max(np.abs(obs[i].reshape(g["obs"][i, t + 1].shape) - g["obs"][i, t + 1])) <= 1e-6, ctx

@@ -39,9 +39,17 @@ def test_to_config_and_from_config_round_trip(env_id):
 
     mod, fn = BUILDERS[env_id]
     ours = getattr(importlib.import_module(mod), fn)()
-    env = rh.make_reference_env(env_id, None)
-    env.reset(seed=0)
-    ref_cfg = env.road.network.to_config()
+    rh._ensure_imports()
+    from highway_env.vehicle.behavior import IDMVehicle
+
+    saved = {k: getattr(IDMVehicle, k) for k in ("DISTANCE_WANTED", "COMFORT_ACC_MAX", "COMFORT_ACC_MIN")}
+    try:  # IntersectionEnv._make_vehicles rewrites these class constants for the whole process (:262-265)
+        env = rh.make_reference_env(env_id, None)
+        env.reset(seed=0)
+        ref_cfg = env.road.network.to_config()
+    finally:
+        for k, v in saved.items():
+            setattr(IDMVehicle, k, v)
     # 1. our dict equals the reference's (insertion order included), rendering attributes aside
     a, b = strip(ours.to_config()), strip(ref_cfg)
     assert list(a) == list(b)
