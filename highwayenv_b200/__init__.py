@@ -31,6 +31,8 @@ REGISTRY = {
     "two-way-v0": "highwayenv_b200.envs.two_way_env:BatchedTwoWayEnv",
     "u-turn-v0": "highwayenv_b200.envs.u_turn_env:BatchedUTurnEnv",
     "u-turn-v1": "highwayenv_b200.envs.u_turn_env:BatchedConnectedLaneUTurnEnv",
+    "exit-v0": "highwayenv_b200.envs.exit_env:BatchedExitEnv",
+    "exit-v1": "highwayenv_b200.envs.exit_env:BatchedConnectedLaneExitEnv",
     "merge-v0": "highwayenv_b200.envs.merge_env:BatchedMergeEnv",
     "merge-v1": "highwayenv_b200.envs.merge_env:BatchedConnectedLaneMergeEnv",
     # MultiAgentAction / MultiAgentObservation (v1, v2: behind MultiAgentWrapper)

@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("HWYB200_LIB") or os.path.join(_HERE, "csrc", "libhwyb200.so")
 
-HWY_ABI_VERSION = 8  # bump with every change of a struct or signature: a stale libhwyb200.so then fails to load
+HWY_ABI_VERSION = 9  # bump with every change of a struct or signature: a stale libhwyb200.so then fails to load
 HWY_MAX_LANES = 8
 HWY_MAX_TARGET_SPEEDS = 8
 HWY_MAX_VEHICLES = 128
@@ -113,7 +113,9 @@ class HwyNetParams(C.Structure):
                                     "dynamic_population", "connected_lanes", "n_agents")]
         + [(n, C.c_double) for n in ("arrived_reward", "reward_speed_lo", "reward_speed_hi", "right_lane_reward",
                                      "merging_speed_reward")]
-        + [("merge_lane", C.c_int32), ("_pad_merge", C.c_int32), ("left_lane_reward", C.c_double)]
+        + [("merge_lane", C.c_int32), ("_pad_merge", C.c_int32), ("left_lane_reward", C.c_double),
+           ("goal_reward", C.c_double), ("exit_lane_a", C.c_int32), ("exit_lane_b", C.c_int32),
+           ("obs_exit_lane", C.c_int32), ("_pad_exit", C.c_int32)]
     )
 
 
@@ -150,6 +152,13 @@ class HwyUTurnSpawn(C.Structure):
 
 class HwyTwoWaySpawn(C.Structure):
     _fields_ = [("lane_ab1", C.c_int32), ("lane_ba0", C.c_int32), ("ego_speed_index", C.c_int32), ("_pad", C.c_int32)]
+
+
+class HwyExitSpawn(C.Structure):
+    _fields_ = [("lanes_count", C.c_int32), ("n_vehicles", C.c_int32), ("ego_speed_index", C.c_int32), ("_pad", C.c_int32),
+                ("ego_speed", C.c_double), ("ego_spacing", C.c_double), ("vehicles_density", C.c_double),
+                ("spawn_exp", C.c_double), ("cdf", C.c_double * HWY_MAX_LANES),
+                ("route_12", C.c_int32), ("route_23", C.c_int32)]
 
 
 class HwyRoundaboutSpawn(C.Structure):
@@ -196,7 +205,7 @@ class HwyLidarParams(C.Structure):
 
 
 EXPORTS = (
-    "hwy_observe_grid", "hwy_observe_ttc", "hwy_observe_lidar",
+    "hwy_observe_grid", "hwy_observe_ttc", "hwy_observe_lidar", "hwy_exit_reset",
     "hwy_abi_version", "hwy_last_error", "hwy_highway_slot_stride", "hwy_highway_reset",
     "hwy_highway_observe", "hwy_highway_step", "hwy_highway_autoreset", "hwy_launch_count",
     "hwy_network_obs_size", "hwy_network_step", "hwy_network_observe", "hwy_roundabout_reset",
@@ -258,6 +267,9 @@ def load():
     lib.hwy_two_way_reset.restype = C.c_int
     lib.hwy_two_way_reset.argtypes = [NP, NG, C.POINTER(HwyTwoWaySpawn), NS, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p]
+    lib.hwy_exit_reset.restype = C.c_int
+    lib.hwy_exit_reset.argtypes = [NP, NG, C.POINTER(HwyExitSpawn), NS, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p]
     lib.hwy_merge_reset.restype = C.c_int
     lib.hwy_merge_reset.argtypes = [NP, NG, C.POINTER(HwyMergeSpawn), NS, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p]

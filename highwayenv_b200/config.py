@@ -267,3 +267,34 @@ def u_turn_default_config() -> dict:
 
 DEFAULTS["u-turn-v0"] = u_turn_default_config
 DEFAULTS["u-turn-v1"] = _connected(u_turn_default_config)
+
+
+def exit_default_config() -> dict:
+    """ExitEnv.default_config (highway_env/envs/exit_env.py:18-44) over HighwayEnv's."""
+    config = highway_default_config()
+    update_config(config, {
+        "observation": {
+            "type": "ExitObservation",
+            "vehicles_count": 15,
+            "features": ["presence", "x", "y", "vx", "vy", "cos_h", "sin_h"],
+            "clip": False,
+        },
+        "action": {"type": "DiscreteMetaAction", "target_speeds": [18, 24, 30]},
+        "lanes_count": 6,
+        "collision_reward": 0,
+        "high_speed_reward": 0.1,
+        "right_lane_reward": 0,
+        "normalize_reward": True,
+        "goal_reward": 1,
+        "vehicles_count": 20,
+        "vehicles_density": 1.5,
+        "controlled_vehicles": 1,
+        "duration": 18,
+        "simulation_frequency": 5,
+        "scaling": 5,
+    })
+    return config
+
+
+DEFAULTS["exit-v0"] = exit_default_config
+DEFAULTS["exit-v1"] = _connected(exit_default_config)

@@ -18,6 +18,8 @@
 //
 // Reference paths are relative to /root/reference/highway_env.
 #include <cstdio>
+#include <mutex>
+
 #include <cuda_runtime.h>
 
 #include "../../include/hwyb200.h"
@@ -574,6 +576,8 @@ __device__ __forceinline__ void observe_kinematics(const HwyNetParams& P, const 
         r2 = ey;
         r3 = evx;
         r4 = evy;
+        // ExitObservation.observe (observation.py:632-636): ego_dict["x"] = exit_lane.local_coordinates(position)[0]
+        if (P.obs_exit_lane > 0) r1 = lane_s_of(g.lanes[P.obs_exit_lane], ex, ey);
     } else if (key < INFINITY && rank < K - 1) {
         row = rank + 1;
         r1 = st.x[i];
@@ -1344,6 +1348,22 @@ network_step_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGraph* _
             rt[2] = scaled_speed;
             rt[3] = (act == 0 || act == 2) ? 1.0 : 0.0;
             rt[4] = merging;
+        } else if (P.reward_type == 5) {
+            // envs/exit_env.py:147-198: collision, goal (the TARGET lane is the exit lane), clipped speed term, target
+            // lane id; normalised to [collision_reward, goal_reward] and clipped to [0, 1]
+            const int tl = st.tgt[i];
+            const bool success = tl == P.exit_lane_a || tl == P.exit_lane_b;
+            double scaled_speed = lmap(r.speed, P.reward_speed_lo, P.reward_speed_hi, 0.0, 1.0);
+            rew = rew + P.collision_reward * (is_crashed ? 1.0 : 0.0);
+            rew = rew + P.goal_reward * (success ? 1.0 : 0.0);
+            rew = rew + P.high_speed_reward * clipd(scaled_speed, 0.0, 1.0);
+            rew = rew + P.right_lane_reward * (double)g.lanes[tl].lane_id;
+            if (P.normalize_reward) rew = clipd(lmap(rew, P.collision_reward, P.goal_reward, 0.0, 1.0), 0.0, 1.0);
+            term = is_crashed;
+            rt[0] = is_crashed ? 1.0 : 0.0;
+            rt[1] = success ? 1.0 : 0.0;
+            rt[2] = clipd(scaled_speed, 0.0, 1.0);
+            rt[3] = (double)g.lanes[tl].lane_id;
         } else if (P.reward_type == 4) {
             // envs/u_turn_env.py:36-82: collision, current lane id (left-most = highest), clipped speed term;
             // normalised, then multiplied by on_road; truncated at `duration`
@@ -1828,6 +1848,85 @@ merge_reset_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGraph* __
     store_rng(rng, (size_t)S.n_envs, e, g);
 }
 
+// ExitEnv._create_vehicles (envs/exit_env.py:107-145), one env per thread (the longitudinal positions are a running
+// maximum over the vehicles created so far).  Draws per traffic vehicle: Generator.choice(lanes, p=lanes / lanes.sum())
+// = one random() searched in the normalised cumulative sum (numpy's legacy-free choice with p), then create_random's
+// uniform(0.9, 1.1); the ego draws only the latter.  No randomize_behavior: DELTA stays 4.
+__global__ void __launch_bounds__(128)
+exit_reset_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGraph* __restrict__ graph,
+                  const __grid_constant__ HwyExitSpawn SP, const __grid_constant__ HwyNetState S,
+                  uint64_t* __restrict__ rng, const uint8_t* __restrict__ mask_a, const uint8_t* __restrict__ mask_b) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= S.n_envs) return;
+    if ((mask_a || mask_b) && !((mask_a && mask_a[e]) || (mask_b && mask_b[e]))) return;
+    Pcg64 g = load_rng(rng, (size_t)S.n_envs, e);
+    double2* pos = reinterpret_cast<double2*>(S.pos);
+    double2* hs = reinterpret_cast<double2*>(S.hs);
+    double2* tt = reinterpret_cast<double2*>(S.tt);
+    double2* imp = reinterpret_cast<double2*>(S.imp);
+    const size_t base = (size_t)e * S.vp;
+    double x_max = 0.0;
+    for (int v = 0; v < SP.n_vehicles; ++v) {
+        const bool is_ego = v == 0;
+        int lane_id = 0;
+        if (!is_ego) {  // cdf.searchsorted(random(), side="right")
+            const double u = g.next_double();
+            lane_id = 0;
+            for (int k = 0; k < SP.lanes_count; ++k) lane_id += SP.cdf[k] <= u;
+            lane_id = min(lane_id, SP.lanes_count - 1);
+        }
+        const HwyNetLane& L = graph->lanes[lane_id];  // ("0", "1", lane_id): the first road of the table
+        const double speed = is_ego ? SP.ego_speed : L.speed_limit;
+        const double spacing = is_ego ? SP.ego_spacing : 1 / SP.vehicles_density;
+        const double default_spacing = 12 + 1.0 * speed;
+        const double offset = spacing * default_spacing * SP.spawn_exp;
+        double x0 = v > 0 ? x_max : 3 * offset;  // np.max of the local longitudinal coordinates (the lanes are aligned)
+        x0 += offset * g.uniform(0.9, 1.1);
+        double px, py;
+        lane_position(L, x0, 0.0, px, py);
+        const double heading = L.heading;
+        const double s_here = lane_s_of(graph->lanes[0], px, py);
+        x_max = v == 0 ? s_here : fmax(x_max, s_here);
+        int lane = 0;  // RoadObject.__init__: closest lane (objects.py:46-50)
+        double bd = 0;
+        for (int l = 0; l < graph->n_lanes; ++l) {
+            double d = lane_distance_with_heading(graph->lanes[l], px, py, heading);
+            if (l == 0 || d < bd) {
+                bd = d;
+                lane = l;
+            }
+        }
+        double target_speed = speed, timer = 0.0;
+        int kind = HWY_KIND_IDM, extra = HWY_META_NO_LANE_CHANGE;  // vehicle.enable_lane_change = False (:143)
+        int* route = S.route + (base + v) * R;
+        if (is_ego) {  // MDPVehicle.__init__ (controller.py:283-293); no route
+            kind = HWY_KIND_MDP;
+            extra = 0;
+            target_speed = P.target_speeds[SP.ego_speed_index];
+            S.route_len[base + v] = 0;
+        } else {
+            timer = py_mod_pos((px + py) * kPi, P.lane_change_delay);  // behavior.py:64
+            const HwyNetLane& CL = graph->lanes[lane];  // plan_route_to("3") (controller.py:71-87)
+            route[0] = CL.from_node | (CL.to_node << 8) | ((CL.lane_id + 1) << 16);
+            route[1] = SP.route_12;
+            route[2] = SP.route_23;
+            S.route_len[base + v] = 3;
+        }
+        pos[base + v] = make_double2(px, py);
+        hs[base + v] = make_double2(heading, speed);
+        tt[base + v] = make_double2(target_speed, timer);
+        imp[base + v] = make_double2(0.0, 0.0);
+        S.delta[base + v] = 4.0;
+        S.meta[base + v] = (lane << HWY_META_LANE_SHIFT) | (lane << HWY_META_TARGET_SHIFT) | HWY_META_CHECK_COLLISIONS |
+                           (kind << HWY_META_KIND_SHIFT) | HWY_META_PRESENT | extra;
+    }
+    S.speed_index[e] = SP.ego_speed_index;
+    S.time[e] = 0.0;
+    if (S.count) S.count[e] = SP.n_vehicles;
+    if (S.road_steps) S.road_steps[e] = 0;
+    store_rng(rng, (size_t)S.n_envs, e, g);
+}
+
 // UTurnEnv._make_vehicles (envs/u_turn_env.py:179-275), one env per thread: the MDPVehicle at the start of
 // ("a","b",0) and six IDM vehicles made on fixed lanes with normal-jittered longitudinal / speed, all routed to "d"
 __global__ void __launch_bounds__(128)
@@ -1987,6 +2086,34 @@ int validate_net(const HwyNetParams* p, const HwyNetGraph* graph, const HwyNetSt
     return 0;
 }
 
+// one side stream (+ fork / join events) per device, created on first use
+struct SideStream {
+    cudaStream_t stream;
+    cudaEvent_t fork, join;
+};
+SideStream* side_stream() {
+    static std::mutex mu;
+    static SideStream* table[64] = {nullptr};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+        fail("%s", "cudaGetDevice failed");
+        return nullptr;
+    }
+    std::lock_guard<std::mutex> lock(mu);
+    if (!table[dev]) {
+        SideStream* s = new SideStream;
+        if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s->join, cudaEventDisableTiming) != cudaSuccess) {
+            fail("%s", "side stream creation failed");
+            delete s;
+            return nullptr;
+        }
+        table[dev] = s;
+    }
+    return table[dev];
+}
+
 template <int G, bool REG>
 size_t net_smem_bytes() {
     return ((sizeof(hwynet::GraphShared) + 15) & ~size_t(15)) +
@@ -2081,12 +2208,24 @@ int hwy_intersection_step_agents(const HwyNetParams* p, const HwyNetGraph* graph
         cudaMemsetAsync(large, 0, sizeof(int), st);
         hwynet::classify_envs_kernel<<<(s->n_envs + 255) / 256, 256, 0, st>>>(s->count, s->n_envs, small, large);
         if (check_launch("classify_envs_kernel")) return 1;
+        // The two kernels serve disjoint envs, and the 32-slot one rarely fills the GPU (the few envs that hold more
+        // than 15 vehicles): it runs on a side stream forked from and joined back into the caller's stream (under a
+        // CUDA-graph capture the fork / join become graph edges), so it overlaps the 16-slot kernel instead of
+        // following it with most SMs idle.
+        SideStream* side = side_stream();
+        if (!side) return 1;
+        cudaEventRecord(side->fork, st);
+        cudaStreamWaitEvent(side->stream, side->fork, 0);
+        if (launch_step<HWY_NET_GROUP_LARGE, true>(p, graph, *spawn, s, action, obs, reward, terminated, truncated,
+                                                   info_speed, info_crashed, side->stream, large, agents_reward,
+                                                   agents_terminated))
+            return 1;
+        cudaEventRecord(side->join, side->stream);
         if (launch_step<16, true>(p, graph, *spawn, s, action, obs, reward, terminated, truncated, info_speed,
                                   info_crashed, st, small, agents_reward, agents_terminated))
             return 1;
-        return launch_step<HWY_NET_GROUP_LARGE, true>(p, graph, *spawn, s, action, obs, reward, terminated, truncated,
-                                                      info_speed, info_crashed, st, large, agents_reward,
-                                                      agents_terminated);
+        cudaStreamWaitEvent(st, side->join, 0);
+        return 0;
     }
     return launch_step<HWY_NET_GROUP_LARGE, true>(p, graph, spawn ? *spawn : none, s, action, obs, reward, terminated,
                                                   truncated, info_speed, info_crashed, st, nullptr, agents_reward,
@@ -2161,6 +2300,20 @@ int hwy_merge_reset(const HwyNetParams* p, const HwyNetGraph* graph, const HwyMe
     cudaStream_t st = (cudaStream_t)stream;
     hwynet::merge_reset_kernel<<<(s->n_envs + 127) / 128, 128, 0, st>>>(*p, graph, *spawn, *s, rng, mask_a, mask_b);
     if (check_launch("merge_reset_kernel")) return 1;
+    if (obs) return observe_dispatch(p, graph, s, mask_a, mask_b, obs, st);
+    return 0;
+}
+
+int hwy_exit_reset(const HwyNetParams* p, const HwyNetGraph* graph, const HwyExitSpawn* spawn, const HwyNetState* s,
+                   uint64_t* rng, const uint8_t* mask_a, const uint8_t* mask_b, float* obs, void* stream) {
+    if (validate_net(p, graph, s)) return 1;
+    if (!spawn || !rng) return fail("%s", "null spawn / rng");
+    if (s->vp != HWY_NET_GROUP_LARGE || spawn->n_vehicles < 1 || spawn->n_vehicles > HWY_NET_GROUP_LARGE)
+        return fail("%s", "exit-v0: 1..32 vehicles on 32 slots");
+    if (spawn->lanes_count < 1 || spawn->lanes_count > HWY_MAX_LANES) return fail("%s", "lanes_count out of range");
+    cudaStream_t st = (cudaStream_t)stream;
+    hwynet::exit_reset_kernel<<<(s->n_envs + 127) / 128, 128, 0, st>>>(*p, graph, *spawn, *s, rng, mask_a, mask_b);
+    if (check_launch("exit_reset_kernel")) return 1;
     if (obs) return observe_dispatch(p, graph, s, mask_a, mask_b, obs, st);
     return 0;
 }

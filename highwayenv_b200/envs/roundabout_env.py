@@ -153,6 +153,7 @@ class BatchedRoundaboutEnv(ObservationHost):
     ENV_ID = "roundabout-v0"
     N_VEHICLES = 5
     EGO_SIDE_LANES = 1  # lanes of the road the controlled vehicle spawns on (default Kinematics y-range)
+    SLOTS = N.HWY_NET_GROUP  # vehicle slots per env: 8 (one warp serves four envs) or 32 (HWY_NET_GROUP_LARGE)
     REWARD_NAMES = ("collision_reward", "high_speed_reward", "lane_change_reward", "on_road_reward")  # _rewards :58-65
     _kernel_events = None  # bench.py hook: list of (start, end) CUDA events around the step kernels
     metadata = {"render_modes": [], "autoreset_mode": "SameStep"}
@@ -298,7 +299,7 @@ class BatchedRoundaboutEnv(ObservationHost):
         return self._obs
 
     def _allocate(self) -> None:
-        n, dev, vp = self.num_envs, self.device, N.HWY_NET_GROUP
+        n, dev, vp = self.num_envs, self.device, self.SLOTS
         z = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, device=dev)  # noqa: E731
         self.V, self.vp = self.N_VEHICLES, vp
         self._pos, self._hs, self._tt, self._imp = (z(n, vp, 2, dtype=torch.float64) for _ in range(4))
@@ -335,6 +336,10 @@ class BatchedRoundaboutEnv(ObservationHost):
         st.route, st.route_len = self._route.data_ptr(), self._route_len.data_ptr()
         st.speed_index, st.time = self._speed_index.data_ptr(), self._time.data_ptr()
         st.reward_terms = self._reward_terms.data_ptr()
+        if vp == N.HWY_NET_GROUP_LARGE:  # the 32-slot kernels read the population and RegulatedRoad.steps from the state
+            self._count = torch.full((n,), self.N_VEHICLES, dtype=torch.int32, device=dev)
+            self._road_steps = z(n, dtype=torch.int32)
+            st.count, st.road_steps = self._count.data_ptr(), self._road_steps.data_ptr()
         self._state = st
 
     def _build_spawn_tables(self) -> None:
@@ -466,11 +471,18 @@ class BatchedRoundaboutEnv(ObservationHost):
             kev.append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
             kev[-1][0].record(torch.cuda.current_stream(self.device))
         with torch.cuda.device(self.device):
-            N.check(self._lib.hwy_network_step(
-                C.byref(self._params), self._graph_dev.data_ptr(), C.byref(self._state), act.data_ptr(),
-                self._fused_out.data_ptr(), self._reward.data_ptr(), self._terminated.data_ptr(),
-                self._truncated.data_ptr(), self._info_speed.data_ptr(), self._info_crashed.data_ptr(),
-                self._stream()))
+            if self.SLOTS == N.HWY_NET_GROUP:
+                N.check(self._lib.hwy_network_step(
+                    C.byref(self._params), self._graph_dev.data_ptr(), C.byref(self._state), act.data_ptr(),
+                    self._fused_out.data_ptr(), self._reward.data_ptr(), self._terminated.data_ptr(),
+                    self._truncated.data_ptr(), self._info_speed.data_ptr(), self._info_crashed.data_ptr(),
+                    self._stream()))
+            else:  # 32 slots: the intersection family's kernel without rules / population changes
+                N.check(self._lib.hwy_intersection_step(
+                    C.byref(self._params), self._graph_dev.data_ptr(), None, C.byref(self._state), act.data_ptr(),
+                    self._fused_out.data_ptr(), self._reward.data_ptr(), self._terminated.data_ptr(),
+                    self._truncated.data_ptr(), self._info_speed.data_ptr(), self._info_crashed.data_ptr(),
+                    self._stream()))
         if kev is not None:
             kev[-1][1].record(torch.cuda.current_stream(self.device))
         info = {"speed": self._info_speed, "crashed": self._info_crashed.view(torch.bool), "action": act,

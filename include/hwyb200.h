@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define HWY_ABI_VERSION 8
+#define HWY_ABI_VERSION 9
 #define HWY_MAX_LANES 8
 #define HWY_MAX_TARGET_SPEEDS 8
 #define HWY_MAX_VEHICLES 128 /* per env, incl. the ego */
@@ -264,6 +264,13 @@ typedef struct HwyNetParams {
     int32_t _pad_merge;
     double left_lane_reward;    /* two-way-v0 (envs/two_way_env.py:17-62): reward_type 3; u-turn-v0
                                  * (envs/u_turn_env.py:14-82): reward_type 4 */
+    /* exit-v0 (envs/exit_env.py:147-198): reward_type 5 = collision, goal (the TARGET lane is ("1","2",lanes_count) or
+     * ("2","exit",0)), clipped speed term, target lane id; normalised to [collision_reward, goal_reward], clipped */
+    double goal_reward;
+    int32_t exit_lane_a, exit_lane_b;
+    int32_t obs_exit_lane;      /* ExitObservation (observation.py:624-675): table index (> 0) of ("1","2",-1), whose
+                                 * longitudinal coordinate replaces x in the ego row of the Kinematics table; 0: none */
+    int32_t _pad_exit;
 } HwyNetParams;
 
 /* route entry: from_node | to_node << 8 | (lane_id + 1) << 16  (lane_id + 1 == 0: None) */
@@ -393,6 +400,21 @@ typedef struct HwyUTurnSpawn {
 int hwy_u_turn_reset(const HwyNetParams *p, const HwyNetGraph *graph, const HwyUTurnSpawn *spawn,
                      const HwyNetState *s, uint64_t *rng, const uint8_t *mask_a, const uint8_t *mask_b,
                      float *obs, void *stream);
+
+/* ExitEnv._create_vehicles (envs/exit_env.py:107-145) on the device: the MDPVehicle from Vehicle.create_random(speed=25,
+ * lane ("0","1",0), spacing=ego_spacing); vehicles_count IDMVehicles on ("0","1", choice(lanes, p=lanes/sum)) at the
+ * lane's speed limit, spacing 1 / vehicles_density, routed to "3", enable_lane_change=False.  State stride 32, s->count
+ * is set to n_vehicles. */
+typedef struct HwyExitSpawn {
+    int32_t lanes_count, n_vehicles;   /* config["lanes_count"], 1 + config["vehicles_count"] */
+    int32_t ego_speed_index, _pad;
+    double ego_speed, ego_spacing, vehicles_density;
+    double spawn_exp;                  /* np.exp(-5 / 40 * lanes_count) (vehicle/kinematics.py:95) */
+    double cdf[HWY_MAX_LANES];         /* Generator.choice(p=lanes / lanes.sum()): p.cumsum() / cumsum[-1] */
+    int32_t route_12, route_23;        /* encoded route entries ("1","2",None), ("2","3",None) */
+} HwyExitSpawn;
+int hwy_exit_reset(const HwyNetParams *p, const HwyNetGraph *graph, const HwyExitSpawn *spawn, const HwyNetState *s,
+                   uint64_t *rng, const uint8_t *mask_a, const uint8_t *mask_b, float *obs, void *stream);
 
 /* TwoWayEnv._make_vehicles (envs/two_way_env.py:113-158) on the device: the MDPVehicle on ("a","b",1) at s = 30,
  * three IDM vehicles ahead at 70 + 40 i + 10 normal() with speed 24 + 2 normal(), two oncoming ones on ("b","a",0)

@@ -75,6 +75,9 @@ CASES = {
     # u-turn-v0: circular U-turn, routed traffic, ego with PURSUIT_TAU = TAU_HEADING, TimeToCollision horizon 16
     "u_turn_ttc": ("u-turn-v0", None, list(range(970, 1002)), 10, "discrete5"),
     "u_turn_v1_ttc": ("u-turn-v1", None, list(range(980, 1012)), 10, "discrete5"),
+    # exit-v0: three highway sections (6 / 7 / 6 lanes) with an exit ramp, routed traffic without lane changes,
+    # ExitObservation, goal reward on the exit lane
+    "exit_obs": ("exit-v0", None, list(range(1100, 1132)), 18, "discrete5"),
     # the merging vehicle is moved onto the end of the ramp at speed: it runs into the Obstacle (objects.py:104-107)
     "merge_obstacle_hit": ("merge-v0", None, list(range(950, 982)), 6, "discrete5"),
 }
@@ -130,6 +133,12 @@ def main() -> None:
             lanes = [li for li, _ in rh.lane_list(env)]
             cfg["_merge_lane"] = lanes.index(("b", "c", 2))
             cfg["_default_side_lanes"] = len(env.road.network.all_side_lanes(env.vehicle.lane_index))
+        if env_id.startswith("exit"):
+            lanes = [li for li, _ in rh.lane_list(env)]
+            n_l = int(cfg["lanes_count"])
+            cfg["_exit_lane_a"], cfg["_exit_lane_b"] = lanes.index(("1", "2", n_l)), lanes.index(("2", "exit", 0))
+            cfg["_obs_exit_lane"] = lanes.index(("1", "2", n_l))  # get_lane(("1", "2", -1)): the last lane of the road
+            cfg["_default_side_lanes"] = n_l  # the controlled vehicle spawns on ("0", "1", 0)
         out["config_json"] = np.array(json.dumps(cfg))
         path = os.path.join(OUT, name + ".npz")
         np.savez_compressed(path, **out)

@@ -849,6 +849,8 @@ static void observe_kinematics_from(const World *w, int ego, float *obs) {
     rows[2] = s->y[ego];
     rows[3] = evx;
     rows[4] = evy;
+    if (c->obs_exit_lane > 0) /* ExitObservation.observe :632-636: ego_dict["x"] = exit_lane.local_coordinates(position)[0] */
+        rows[1] = lane_s(&w->g->lanes[c->obs_exit_lane], s->x[ego], s->y[ego]);
     if (F == 7) {
         rows[5] = cos(s->heading[ego]);
         rows[6] = sin(s->heading[ego]);
@@ -1073,6 +1075,29 @@ static void reward_done_u_turn(const World *w, double *reward, int32_t *terminat
     *truncated = s->time[0] >= c->duration;
 }
 
+/* envs/exit_env.py:147-198: collision, goal (the TARGET lane is the exit lane), clipped speed term, target lane id;
+ * normalised to [collision_reward, goal_reward] and clipped to [0, 1]; terminated on a crash, truncated at `duration` */
+static void reward_done_exit(const World *w, double *reward, int32_t *terminated, int32_t *truncated) {
+    const NetCfg *c = w->c;
+    const NetState *s = w->s;
+    const int ego = 0;
+    const int tl = s->target_lane[ego];
+    const int success = tl == c->exit_lane_a || tl == c->exit_lane_b;
+    double scaled_speed = lmap(s->speed[ego], c->reward_speed_lo, c->reward_speed_hi, 0, 1);
+    double r = 0;
+    r = r + c->collision_reward * (double)(s->crashed[ego] != 0);
+    r = r + c->goal_reward * (double)success;
+    r = r + c->high_speed_reward * clipd(scaled_speed, 0, 1);
+    r = r + c->right_lane_reward * (double)LANE(w, tl)->lane_id;
+    if (c->normalize_reward) {
+        r = lmap(r, c->collision_reward, c->goal_reward, 0, 1);
+        r = clipd(r, 0, 1);
+    }
+    *reward = r;
+    *terminated = s->crashed[ego] != 0;
+    *truncated = s->time[0] >= c->duration;
+}
+
 /* ------------------------------------------------------------------ road/regulation.py */
 
 /* road/road.py:323-362 position_heading_along_route(route, longitudinal, 0, current_lane_index) */
@@ -1246,6 +1271,8 @@ void net_step(const NetGraph *g, const NetCfg *c, NetState *s, int action, float
         reward_done_two_way(&w, reward, terminated, truncated);
     else if (c->reward_type == 4)
         reward_done_u_turn(&w, reward, terminated, truncated);
+    else if (c->reward_type == 5)
+        reward_done_exit(&w, reward, terminated, truncated);
     else
         reward_done(&w, action, reward, terminated, truncated);
     free(act_buf);

@@ -85,6 +85,12 @@ typedef struct NetCfg {
     /* two-way-v0 (envs/two_way_env.py): reward_type 3; u-turn-v0 (envs/u_turn_env.py): reward_type 4 */
     double left_lane_reward;
     double ego_pursuit_tau; /* u_turn_env.py:193 ego.PURSUIT_TAU = TAU_HEADING; 0: the class default */
+    /* exit-v0 (envs/exit_env.py): reward_type 5 */
+    double goal_reward;
+    int32_t exit_lane_a, exit_lane_b; /* table indices of ("1","2",lanes_count) and ("2","exit",0): _is_success (:178-190) */
+    int32_t obs_exit_lane;            /* ExitObservation (observation.py:624-675): table index of ("1","2",-1) whose
+                                       * longitudinal coordinate replaces the ego row's x; -1: plain Kinematics */
+    int32_t _pad4;
 } NetCfg;
 
 /* route entry: from | to << 8 | (lane_id + 1) << 16   (lane_id + 1 == 0: None) */

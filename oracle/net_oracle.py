@@ -52,7 +52,8 @@ class NetCfg(C.Structure):
         + [(k, C.c_double) for k in ("arrived_reward", "reward_speed_lo", "reward_speed_hi", "right_lane_reward",
                                      "merging_speed_reward")]
         + [("merge_lane", C.c_int32), ("_pad3", C.c_int32), ("left_lane_reward", C.c_double),
-           ("ego_pursuit_tau", C.c_double)]
+           ("ego_pursuit_tau", C.c_double), ("goal_reward", C.c_double), ("exit_lane_a", C.c_int32),
+           ("exit_lane_b", C.c_int32), ("obs_exit_lane", C.c_int32), ("_pad4", C.c_int32)]
     )
 
 
@@ -215,7 +216,7 @@ def cfg_from_dict(config: dict, n_vehicles: int = 5) -> NetCfg:
         c.ttc_horizon = int(obs.get("horizon", 10))
         c.obs_vehicles_count = 5
     else:
-        assert obs["type"] == "Kinematics"
+        assert obs["type"] in ("Kinematics", "ExitObservation")
         c.obs_type = OBS_KINEMATICS
         c.obs_vehicles_count = int(obs.get("vehicles_count", 5))
         c.obs_see_behind = int(bool(obs.get("see_behind", False)))
@@ -261,6 +262,15 @@ def cfg_from_dict(config: dict, n_vehicles: int = 5) -> NetCfg:
             # u_turn_env.py:196 sets ego.PURSUIT_TAU, but steering_control reads self.TAU_PURSUIT
             # (controller.py:28,159): the assignment is inert in the reference, so the default tau applies
             c.ego_pursuit_tau = 0.0
+    c.obs_exit_lane = -1
+    if "goal_reward" in config:  # exit-v0 (envs/exit_env.py:18-44)
+        c.reward_type = 5
+        c.goal_reward = float(config["goal_reward"])
+        c.right_lane_reward = float(config["right_lane_reward"])
+        c.reward_speed_lo, c.reward_speed_hi = (float(v) for v in config["reward_speed_range"])
+        c.exit_lane_a, c.exit_lane_b = int(config["_exit_lane_a"]), int(config["_exit_lane_b"])
+        if obs["type"] == "ExitObservation":
+            c.obs_exit_lane = int(config["_obs_exit_lane"])
     c.connected_lanes = int(bool(config.get("neighbour_vehicles_connected_lanes", False)))
     c.politeness, c.lane_change_min_acc_gain = 0.0, 0.2
     c.lane_change_max_braking_imposed, c.lane_change_delay = 2.0, 1.0
@@ -571,3 +581,82 @@ class IntersectionOracle(NetOracleBatch):
             self._clear_vehicles(e)
             self._spawn_vehicle(e, spawn_probability=p)
         return out
+
+
+class ExitOracle(NetOracleBatch):
+    """exit-v0 (envs/exit_env.py): the C oracle for act / step / observe / reward plus the numpy restatement of
+    ExitEnv._create_vehicles (:107-145) on each env's numpy Generator.  `lanes` maps (from, to, id) to table indices;
+    lanes 0..lanes_count-1 are ("0", "1", id)."""
+
+    def __init__(self, graph: NetGraph, cfg: NetCfg, n_envs: int, config: dict, node_names):
+        cfg.n_vehicles = int(config["vehicles_count"]) + 1
+        super().__init__(graph, cfg, n_envs)
+        self.config = config
+        names = [str(x) for x in node_names]
+        self.node = {nm: i for i, nm in enumerate(names)}
+        self.rng = [np.random.Generator(np.random.PCG64(0)) for _ in range(n_envs)]
+        self.a["no_lane_change"][:, 1:] = 1  # vehicle.enable_lane_change = False (:143)
+        self.a["check_collisions"][...] = 1
+        self.a["kind"][:, 0] = KIND_MDP
+
+    def _route_to_3(self, lane_idx: int):
+        L = self.g.lanes[lane_idx]
+        enc = np.zeros(NET_MAX_ROUTE, dtype=np.int32)
+        enc[0] = L.from_node | (L.to_node << 8) | ((L.lane_id + 1) << 16)
+        enc[1] = self.node["1"] | (self.node["2"] << 8)  # ("1", "2", None)
+        enc[2] = self.node["2"] | (self.node["3"] << 8)  # ("2", "3", None)
+        return enc, 3
+
+    def reset_env(self, e: int, seed=None):
+        if seed is not None:
+            self.rng[e] = np.random.Generator(np.random.PCG64(np.random.SeedSequence(int(seed))))
+        g, cfg, a = self.rng[e], self.config, self.a
+        n_lanes = int(cfg["lanes_count"])
+        xs = []
+
+        def create_random(lane_id, speed, spacing):  # Vehicle.create_random (vehicle/kinematics.py:50-104), lane given
+            L = self.g.lanes[lane_id]  # ("0", "1", lane_id)
+            default_spacing = 12 + 1.0 * speed
+            offset = spacing * default_spacing * np.exp(-5 / 40 * n_lanes)
+            x0 = np.max(xs) if xs else 3 * offset
+            x0 += offset * g.uniform(0.9, 1.1)
+            px, py = C.c_double(), C.c_double()
+            lib().net_lane_position(C.byref(L), float(x0), 0.0, C.byref(px), C.byref(py))
+            return px.value, py.value, L.heading
+
+        ts = [self.cfg.target_speeds[i] for i in range(self.cfg.n_target_speeds)]
+        for v in range(self.V):
+            if v == 0:
+                x, y, h = create_random(0, 25.0, float(cfg["ego_spacing"]))
+                speed = 25.0
+            else:
+                lanes = np.arange(n_lanes)
+                lane_id = int(g.choice(lanes, size=1, p=lanes / lanes.sum()).astype(int)[0])
+                speed = float(self.g.lanes[lane_id].speed_limit)
+                x, y, h = create_random(lane_id, speed, 1 / float(cfg["vehicles_density"]))
+            L0 = self.g.lanes[0]
+            s0, lat0 = C.c_double(), C.c_double()
+            lib().net_lane_local(C.byref(L0), x, y, C.byref(s0), C.byref(lat0))
+            xs.append(s0.value)
+            lane = lib().net_closest_lane(C.byref(self.g), x, y, h)
+            a["x"][e, v], a["y"][e, v], a["heading"][e, v], a["speed"][e, v] = x, y, h, speed
+            a["lane"][e, v] = a["target_lane"][e, v] = lane
+            a["crashed"][e, v] = a["has_impact"][e, v] = 0
+            a["impact_x"][e, v] = a["impact_y"][e, v] = 0.0
+            a["delta"][e, v] = 4.0
+            if v == 0:  # MDPVehicle.__init__ (controller.py:283-293): speed index of its speed, target speed from it
+                si = int(np.clip(np.round((speed - ts[0]) / (ts[-1] - ts[0]) * (len(ts) - 1)), 0, len(ts) - 1))
+                a["speed_index"][e] = si
+                a["target_speed"][e, v], a["timer"][e, v] = ts[si], 0.0
+                a["route_len"][e, v] = 0
+            else:
+                a["target_speed"][e, v] = speed
+                a["timer"][e, v] = ((x + y) * np.pi) % 1.0  # IDMVehicle.__init__ (behavior.py:64)
+                a["route"][e, v], a["route_len"][e, v] = self._route_to_3(lane)
+        a["time"][e] = 0.0
+
+    def rng_words(self, e):
+        st = self.rng[e].bit_generator.state
+        m = (1 << 64) - 1
+        return np.array([st["state"]["state"] >> 64, st["state"]["state"] & m, st["state"]["inc"] >> 64,
+                         st["state"]["inc"] & m, (int(st["has_uint32"]) << 32) | int(st["uinteger"])], dtype=np.uint64)

@@ -58,6 +58,7 @@ ENV_CLASSES = {
     "two-way-v0": ("highway_env.envs.two_way_env", "TwoWayEnv"),
     "u-turn-v0": ("highway_env.envs.u_turn_env", "UTurnEnv"),
     "u-turn-v1": ("highway_env.envs.u_turn_env", "ConnectedLaneUTurnEnv"),
+    "exit-v0": ("highway_env.envs.exit_env", "ExitEnv"),
     "merge-v0": ("highway_env.envs.merge_env", "MergeEnv"),
     "merge-v1": ("highway_env.envs.merge_env", "ConnectedLaneMergeEnv"),
 }

@@ -33,11 +33,11 @@ def test_struct_layout_matches_header():
 
     from highwayenv_b200 import _native as N
 
-    src = ('#include <stdio.h>\n#include "hwyb200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", '
+    src = ('#include <stdio.h>\n#include "hwyb200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", '
            'sizeof(HwyHighwayParams), sizeof(HwyHighwayState), sizeof(HwyStraightLane), sizeof(HwyNetLane), '
            'sizeof(HwyNetGraph), sizeof(HwyNetParams), sizeof(HwyNetState), sizeof(HwyIntersectionSpawn), '
            'sizeof(HwyRoundaboutSpawn), sizeof(HwyObsView), sizeof(HwyGridParams), sizeof(HwyTtcParams), '
-           'sizeof(HwyLidarParams));return 0;}\n')
+           'sizeof(HwyLidarParams), sizeof(HwyExitSpawn));return 0;}\n')
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "t.c"), "w").write(src)
         exe = os.path.join(d, "t")
@@ -46,7 +46,7 @@ def test_struct_layout_matches_header():
     assert sizes == [C.sizeof(t) for t in (N.HwyHighwayParams, N.HwyHighwayState, N.HwyStraightLane, N.HwyNetLane,
                                            N.HwyNetGraph, N.HwyNetParams, N.HwyNetState, N.HwyIntersectionSpawn,
                                            N.HwyRoundaboutSpawn, N.HwyObsView, N.HwyGridParams, N.HwyTtcParams,
-                                           N.HwyLidarParams)]
+                                           N.HwyLidarParams, N.HwyExitSpawn)]
 
 
 def test_abi_validation_without_gpu():
