@@ -25,6 +25,7 @@ REGISTRY = {
     "highway-fast-v0": "highwayenv_b200.envs.highway_env:BatchedHighwayEnvFast",
     "roundabout-v0": "highwayenv_b200.envs.roundabout_env:BatchedRoundaboutEnv",
     "intersection-v0": "highwayenv_b200.envs.intersection_env:BatchedIntersectionEnv",
+    "intersection-v1": "highwayenv_b200.envs.intersection_env:BatchedContinuousIntersectionEnv",
     # ConnectedLaneNeighboursMixin variants (neighbour search across lane segments)
     "roundabout-v1": "highwayenv_b200.envs.roundabout_env:BatchedConnectedLaneRoundaboutEnv",
     "intersection-v2": "highwayenv_b200.envs.intersection_env:BatchedConnectedLaneIntersectionEnv",
@@ -55,6 +56,16 @@ def make(env_id: str, num_envs: int = 1, config: Optional[dict] = None, device: 
     return env_cls(config=config, render_mode=render_mode, num_envs=num_envs, device=device, **kwargs)
 
 
+def make_single(env_id: str, config: Optional[dict] = None, **kwargs):
+    """`gym.make(env_id, config=...)` equivalent: ONE env with the gymnasium.Env surface (numpy observation, python
+    float / bool returns, no autoreset) over the same kernels — see highwayenv_b200/single.py."""
+    from .single import SingleEnv
+
+    if ":" in env_id:
+        env_id = env_id.split(":", 1)[1]
+    return SingleEnv(env_id, config=config, **kwargs)
+
+
 def _register_with_gymnasium() -> None:
     """When gymnasium is installed, expose the ids as vector envs:
     ``gymnasium.make_vec("hwyb200/highway-fast-v0", num_envs=4096)``."""
@@ -63,10 +74,11 @@ def _register_with_gymnasium() -> None:
     except Exception:
         return
     for env_id, entry in REGISTRY.items():
-        gid = f"hwyb200/{env_id}"
+        gid = f"hwyb200/{env_id}"  # hwyb200/<reference id>: gymnasium.make -> SingleEnv, gymnasium.make_vec -> batched env
         if gid not in registry:
             try:
-                register(id=gid, vector_entry_point=entry)
+                register(id=gid, entry_point="highwayenv_b200.single:SingleEnv", vector_entry_point=entry,
+                         kwargs={"env_id": env_id})
             except Exception:
                 pass
 

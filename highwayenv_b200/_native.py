@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("HWYB200_LIB") or os.path.join(_HERE, "csrc", "libhwyb200.so")
 
-HWY_ABI_VERSION = 9  # bump with every change of a struct or signature: a stale libhwyb200.so then fails to load
+HWY_ABI_VERSION = 10  # bump with every change of a struct or signature: a stale libhwyb200.so then fails to load
 HWY_MAX_LANES = 8
 HWY_MAX_TARGET_SPEEDS = 8
 HWY_MAX_VEHICLES = 128
@@ -115,7 +115,11 @@ class HwyNetParams(C.Structure):
                                      "merging_speed_reward")]
         + [("merge_lane", C.c_int32), ("_pad_merge", C.c_int32), ("left_lane_reward", C.c_double),
            ("goal_reward", C.c_double), ("exit_lane_a", C.c_int32), ("exit_lane_b", C.c_int32),
-           ("obs_exit_lane", C.c_int32), ("_pad_exit", C.c_int32)]
+           ("obs_exit_lane", C.c_int32), ("_pad_exit", C.c_int32),
+           ("action_type", C.c_int32), ("act_clip", C.c_int32), ("dynamical", C.c_int32), ("obs_n_feat", C.c_int32),
+           ("acc_lo", C.c_double), ("acc_hi", C.c_double), ("steer_lo", C.c_double), ("steer_hi", C.c_double),
+           ("obs_feat", C.c_int32 * HWY_MAX_OBS_FEATURES), ("obs_feat_ranged", C.c_int32 * HWY_MAX_OBS_FEATURES),
+           ("obs_feat_lo", C.c_double * HWY_MAX_OBS_FEATURES), ("obs_feat_hi", C.c_double * HWY_MAX_OBS_FEATURES)]
     )
 
 

@@ -298,3 +298,33 @@ def exit_default_config() -> dict:
 
 DEFAULTS["exit-v0"] = exit_default_config
 DEFAULTS["exit-v1"] = _connected(exit_default_config)
+
+
+def continuous_intersection_default_config() -> dict:
+    """ContinuousIntersectionEnv.default_config (highway_env/envs/intersection_env.py:432-473)."""
+    import numpy as np
+
+    config = intersection_default_config()
+    update_config(config, {
+        "observation": {
+            "type": "Kinematics",
+            "vehicles_count": 5,
+            "features": ["presence", "x", "y", "vx", "vy", "long_off", "lat_off", "ang_off"],
+            "features_range": {"x": [-100, 100], "y": [-100, 100], "vx": [-20, 20], "vy": [-20, 20]},
+            "absolute": True,
+            "flatten": False,
+            "observe_intentions": False,
+        },
+        "action": {
+            "type": "ContinuousAction",
+            "steering_range": [-np.pi / 3, np.pi / 3],
+            "longitudinal": True,
+            "lateral": True,
+            "dynamical": True,
+            "target_speeds": [0, 4.5, 9],
+        },
+    })
+    return config
+
+
+DEFAULTS["intersection-v1"] = continuous_intersection_default_config

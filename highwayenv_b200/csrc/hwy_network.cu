@@ -267,6 +267,8 @@ __device__ __noinline__ double idm_acceleration(const HwyNetParams& P, const Gra
 }
 
 __device__ __forceinline__ int isign(int a) { return (a > 0) - (a < 0); }
+// env.controlled_vehicles: MDPVehicle (DiscreteMetaAction) or a plain Vehicle / BicycleVehicle (ContinuousAction)
+__device__ __forceinline__ bool is_controlled_kind(int kind) { return kind == HWY_KIND_MDP || kind == HWY_KIND_VEHICLE; }
 
 // vehicle/behavior.py:265-324 mobil(lane_index), incl. the planned-route branch
 template <int G, bool REG>
@@ -548,7 +550,7 @@ template <int G, bool REG>
 __device__ __forceinline__ void observe_kinematics(const HwyNetParams& P, const GraphShared& g,
                                                    EnvStage<G, REG>& st, int V, int i,
                                                    float* __restrict__ obs_env) {
-    const int K = P.obs_vehicles_count, F = P.obs_features == 7 ? 7 : 5;
+    const int K = P.obs_vehicles_count, F = P.obs_n_feat > 0 ? P.obs_n_feat : (P.obs_features == 7 ? 7 : 5);
     const int ego = st.ego;
     const double ex = st.x[ego], ey = st.y[ego];
     const double evx = st.v[ego] * st.c[ego], evy = st.v[ego] * st.s[ego];
@@ -591,7 +593,36 @@ __device__ __forceinline__ void observe_kinematics(const HwyNetParams& P, const 
             r4 -= evy;
         }
     }
-    if (row >= 0) {
+    if (row >= 0 && P.obs_n_feat > 0) {
+        // configured column list (any Vehicle.to_dict key, vehicle/kinematics.py:237-261) with per-column ranges
+        // (normalize_obs, observation.py:207-232); road objects lack the vehicle-only columns (NaN in the frame -> 0)
+        const int NF = P.obs_n_feat;
+        const bool object = st.kind[i] == HWY_KIND_OBSTACLE;
+        const HwyNetLane& L = g.lanes[st.lane[i]];
+        float* o = obs_env + NF * row;
+        for (int col = 0; col < NF; ++col) {
+            double v = 0.0;
+            switch (P.obs_feat[col]) {
+                case HWY_FEAT_PRESENCE: v = 1.0; break;
+                case HWY_FEAT_X: v = r1; break;
+                case HWY_FEAT_Y: v = r2; break;
+                case HWY_FEAT_VX: v = object ? r3 - st.v[i] * st.c[i] : r3; break;  // objects: vx = vy = 0 (objects.py:146)
+                case HWY_FEAT_VY: v = object ? r4 - st.v[i] * st.s[i] : r4; break;
+                case HWY_FEAT_HEADING: v = object ? 0.0 : st.heading[i]; break;
+                case HWY_FEAT_COS_H: v = st.c[i]; break;
+                case HWY_FEAT_SIN_H: v = st.s[i]; break;
+                case HWY_FEAT_LONG_OFF: v = object ? 0.0 : st.own_s[i]; break;  // Vehicle.lane_offset (:228-235)
+                case HWY_FEAT_LAT_OFF: v = object ? 0.0 : st.own_lat[i]; break;
+                case HWY_FEAT_ANG_OFF: v = object ? 0.0 : wrap_to_pi(st.heading[i] - lane_heading_at(L, st.own_s[i])); break;
+                default: v = 0.0; break;  // cos_d / sin_d with observe_intentions=False (the only supported setting)
+            }
+            if (P.obs_normalize && P.obs_feat_ranged[col]) {
+                v = lmap(v, P.obs_feat_lo[col], P.obs_feat_hi[col], -1.0, 1.0);
+                if (P.obs_clip) v = clipd(v, -1.0, 1.0);
+            }
+            o[col] = (float)v;
+        }
+    } else if (row >= 0) {
         if (P.obs_normalize) {
             r1 = lmap(r1, P.obs_x_lo, P.obs_x_hi, -1.0, 1.0);
             r2 = lmap(r2, P.obs_y_lo, P.obs_y_hi, -1.0, 1.0);
@@ -683,7 +714,7 @@ __device__ __forceinline__ void observe_occupancy(const HwyNetParams& P, const G
 __device__ __forceinline__ int obs_size(const HwyNetParams& P) {
     if (P.obs_type == HWY_OBS_OCCUPANCY) return 4 * 11 * 11;
     if (P.obs_type == HWY_OBS_TTC) return 9 * (int)(P.ttc_horizon / (1.0 / P.policy_frequency));
-    return P.obs_vehicles_count * (P.obs_features == 7 ? 7 : 5);
+    return P.obs_vehicles_count * (P.obs_n_feat > 0 ? P.obs_n_feat : (P.obs_features == 7 ? 7 : 5));
 }
 
 template <int G, bool REG>
@@ -736,9 +767,78 @@ __device__ __forceinline__ void publish(EnvStage<G, REG>& st, int i, const Regs&
     st.c[i] = cs;
     st.s[i] = sn;
     st.v[i] = r.speed;
-    st.ts[i] = r.target_speed;
+    // getattr(ego_vehicle, "target_speed", 0) (behavior.py:172): a plain Vehicle has none (its tt pair holds the
+    // BicycleVehicle's lateral_speed / yaw_rate)
+    st.ts[i] = meta_kind(r.meta) == HWY_KIND_VEHICLE ? 0.0 : r.target_speed;
 }
 
+
+// ------------------------------------------------------------------ the ContinuousAction ego (plain Vehicle / BicycleVehicle)
+// BicycleVehicle.derivative_func (vehicle/dynamics.py:73-111) on (x, y, heading, speed, lateral_speed, yaw_rate)
+__device__ __noinline__ void bicycle_derivative(const double (&st)[6], double steering, double acceleration,
+                                                double (&d)[6]) {
+    const double mass = 1.0, len_a = kVehLength / 2, len_b = kVehLength / 2;
+    const double inertia_z = 1.0 / 12 * mass * (kVehLength * kVehLength + kVehWidth * kVehWidth);
+    const double friction_front = 15.0 * mass, friction_rear = 15.0 * mass;
+    const double heading = st[2], speed = st[3], lateral_speed = st[4], yaw_rate = st[5];
+    const double theta_vf = atan2(lateral_speed + len_a * yaw_rate, speed);
+    const double theta_vr = atan2(lateral_speed - len_b * yaw_rate, speed);
+    double f_yf = 2 * friction_front * (steering - theta_vf);
+    double f_yr = 2 * friction_rear * (0.0 - theta_vr);
+    if (fabs(speed) < 1) {  // low speed dynamics: damping of lateral speed and yaw rate
+        f_yf = -mass * lateral_speed - inertia_z / len_a * yaw_rate;
+        f_yr = -mass * lateral_speed + inertia_z / len_a * yaw_rate;
+    }
+    const double d_lateral_speed = 1 / mass * (f_yf + f_yr) - yaw_rate * speed;
+    const double d_yaw_rate = 1 / inertia_z * (len_a * f_yf - len_b * f_yr);
+    double sn, cs;
+    sincos(heading, &sn, &cs);
+    d[0] = cs * speed + (-sn) * lateral_speed;
+    d[1] = sn * speed + cs * lateral_speed;
+    d[2] = yaw_rate;
+    d[3] = acceleration;
+    d[4] = d_lateral_speed;
+    d[5] = d_yaw_rate;
+}
+// Vehicle.clip_actions (kinematics.py:155-168), shared by both vehicle classes
+__device__ __forceinline__ void clip_plain_actions(double speed, bool crashed, double& steering, double& acceleration) {
+    if (crashed) {
+        steering = 0.0;
+        acceleration = -1.0 * speed;
+    }
+    if (speed > kMaxSpeed)
+        acceleration = fmin(acceleration, 1.0 * (kMaxSpeed - speed));
+    else if (speed < kMinSpeed)
+        acceleration = fmax(acceleration, 1.0 * (kMinSpeed - speed));
+}
+// BicycleVehicle.step (dynamics.py:142-161): clip_actions, then one rk4 step (:13-30)
+__device__ __noinline__ void bicycle_advance(double (&st)[6], bool crashed, double& steering, double& acceleration,
+                                             double dt) {
+    clip_plain_actions(st[3], crashed, steering, acceleration);
+    steering = clipd(steering, -kPi / 2, kPi / 2);
+    st[5] = clipd(st[5], -2 * kPi, 2 * kPi);  // MAX_ANGULAR_SPEED
+    double f1[6], f2[6], f3[6], f4[6], tmp[6];
+    bicycle_derivative(st, steering, acceleration, f1);
+    for (int k = 0; k < 6; ++k) tmp[k] = st[k] + (f1[k] * (dt / 2));
+    bicycle_derivative(tmp, steering, acceleration, f2);
+    for (int k = 0; k < 6; ++k) tmp[k] = st[k] + (f2[k] * (dt / 2));
+    bicycle_derivative(tmp, steering, acceleration, f3);
+    for (int k = 0; k < 6; ++k) tmp[k] = st[k] + (f3[k] * dt);
+    bicycle_derivative(tmp, steering, acceleration, f4);
+    for (int k = 0; k < 6; ++k) st[k] = st[k] + (dt / 6) * (f1[k] + (2 * f2[k]) + (2 * f3[k]) + f4[k]);
+}
+// Vehicle.step (kinematics.py:130-153) on an explicit state; the pending impact is the caller's
+__device__ __noinline__ void kinematic_advance(double (&st)[6], bool crashed, double& steering, double& acceleration,
+                                               double dt) {
+    clip_plain_actions(st[3], crashed, steering, acceleration);
+    const double beta = atan(1.0 / 2 * tan(steering));
+    double sn, cs;
+    sincos(st[2] + beta, &sn, &cs);
+    st[0] += (st[3] * cs) * dt;
+    st[1] += (st[3] * sn) * dt;
+    st[2] += st[3] * sin(beta) / (kVehLength / 2) * dt;
+    st[3] += acceleration * dt;
+}
 
 // ------------------------------------------------------------------ RegulatedRoad (road/regulation.py)
 __device__ __forceinline__ int HwyNetLane_route(const HwyNetLane& L) {
@@ -797,9 +897,11 @@ __device__ __forceinline__ bool has_corner_inside(double c1x, double c1y, double
 
 // regulation.py:42-111: enforce_road_rules with is_conflict_possible / respect_priorities.
 // All threads of the group call this; r is the caller's vehicle.
-template <int G, bool REG>
+// PLAIN: the env may hold a ContinuousAction ego (kind HWY_KIND_VEHICLE); compiled out otherwise so that the
+// DiscreteMetaAction kernels keep their register budget (198 vs 128 registers measured with the code always in)
+template <int G, bool REG, bool PLAIN>
 __device__ __forceinline__ void enforce_road_rules(const HwyNetParams& P, const GraphShared& g,
-                                                   EnvStage<G, REG>& st, int V, int i, Regs& r) {
+                                                   EnvStage<G, REG>& st, int V, int i, Regs& r, double act_steer) {
     const bool active = i < V;
     // un-freeze (YIELD_DURATION = 0: every yielding vehicle is released at the next regulation tick)
     if (active && (r.meta & HWY_META_YIELDING)) {
@@ -824,12 +926,43 @@ __device__ __forceinline__ void enforce_road_rules(const HwyNetParams& P, const 
     };
     unsigned conflict = 0;
     const double s0 = active ? st.own_s[i] : 0.0;
+    // A plain Vehicle / BicycleVehicle (ContinuousAction ego) is not a ControlledVehicle: its
+    // predict_trajectory_constant_speed (vehicle/kinematics.py:179-198) steps a copy 11 x 0.25 s with acceleration 0
+    // and its current steering; the copy's state is carried across the horizon chunks.
+    const bool plain = PLAIN && active && meta_kind(r.meta) == HWY_KIND_VEHICLE;
+    double sim[PLAIN ? 6 : 1];
+    double sim_steer = act_steer, sim_acc = 0.0;
+    bool sim_crashed = (r.meta & HWY_META_CRASHED) != 0, sim_impact = (r.meta & HWY_META_HAS_IMPACT) != 0;
+    if constexpr (PLAIN) {
+        sim[0] = r.x, sim[1] = r.y, sim[2] = r.heading, sim[3] = r.speed, sim[4] = r.target_speed, sim[5] = r.timer;
+    }
     for (int k0 = 0; k0 < kPred; k0 += kPredChunk) {
         const int nk = min(kPredChunk, kPred - k0);
         if (active) {
             for (int k = 0; k < nk; ++k) {
                 double px, py, ph;
-                position_heading_along_route(g, st, i, s0 + r.speed * (0.25 * (k0 + k + 1)), px, py, ph);
+                bool simulated = false;
+                if constexpr (PLAIN) {
+                    if (plain) {
+                        if (P.dynamical) {
+                            bicycle_advance(sim, sim_crashed, sim_steer, sim_acc, 0.25);
+                        } else {
+                            kinematic_advance(sim, sim_crashed, sim_steer, sim_acc, 0.25);
+                            if (sim_impact) {  // kinematics.py:147-150
+                                sim[0] += r.imp_x;
+                                sim[1] += r.imp_y;
+                                sim_crashed = true;
+                                sim_impact = false;
+                            }
+                        }
+                        px = sim[0];
+                        py = sim[1];
+                        ph = sim[2];
+                        simulated = true;
+                    }
+                }
+                if (!simulated)
+                    position_heading_along_route(g, st, i, s0 + r.speed * (0.25 * (k0 + k + 1)), px, py, ph);
                 st.pred[i][k][0] = px;
                 st.pred[i][k][1] = py;
                 st.pred[i][k][2] = ph;
@@ -911,13 +1044,26 @@ __device__ __forceinline__ void observe_agents(const HwyNetParams& P, const Grap
 // ------------------------------------------------------------------ one simulation substep
 // Road.act() then [RegulatedRoad rules] Road.step(dt) for one env; all threads of the group call it.
 // `ego_label` >= 0 on the first frame of a policy step: the meta-action label of the controlled vehicle.
-template <int G, bool REG>
+template <int G, bool REG, bool PLAIN = false>
 __device__ __forceinline__ void substep(const HwyNetParams& P, const GraphShared& g, EnvStage<G, REG>& st, int i,
-                                        Regs& r, double& act_accel, double dt, int ego_label,
-                                        int* my_speed_index = nullptr) {
+                                        Regs& r, double& act_accel, double& act_steer, double dt, int ego_label,
+                                        int* my_speed_index = nullptr, const float* act_f = nullptr) {
     const int V = st.count;
     const bool active = i < V;
     const int kind = meta_kind(r.meta);
+    // ---- ContinuousAction.get_action / act on the first frame (envs/common/action.py:136-162): the Box is float32
+    // and NEP 50 keeps utils.lmap (utils.py:31-33) in float32; the vehicle's action dict persists until the next act
+    if (PLAIN && act_f && active && kind == HWY_KIND_VEHICLE) {
+        float a0 = act_f[0], a1 = act_f[1];
+        if (P.act_clip) {
+            a0 = fminf(fmaxf(a0, -1.0f), 1.0f);
+            a1 = fminf(fmaxf(a1, -1.0f), 1.0f);
+        }
+        const float acc = __fadd_rn((float)P.acc_lo, __fdiv_rn(__fmul_rn(__fsub_rn(a0, -1.0f), (float)(P.acc_hi - P.acc_lo)), 2.0f));
+        const float stf = __fadd_rn((float)P.steer_lo, __fdiv_rn(__fmul_rn(__fsub_rn(a1, -1.0f), (float)(P.steer_hi - P.steer_lo)), 2.0f));
+        act_accel = (double)acc;
+        act_steer = (double)stf;
+    }
     // ---- action_type.act on the first frame: MDPVehicle.act (controller.py:295-315)
     // (every controlled vehicle has its own label: MultiAgentAction.act, action.py:316-321)
     if (ego_label >= 0 && active && kind == HWY_KIND_MDP) {
@@ -947,7 +1093,8 @@ __device__ __forceinline__ void substep(const HwyNetParams& P, const GraphShared
     if (active) {
         st.tgt_prev[i] = st.tgt[i];
         // road.objects neither act nor step (road/road.py:464-476)
-        if (kind != HWY_KIND_OBSTACLE && (kind != HWY_KIND_IDM || !crashed))
+        // (nor does a plain Vehicle: Vehicle.act(None) keeps its action, kinematics.py:119-128)
+        if (kind != HWY_KIND_OBSTACLE && kind != HWY_KIND_VEHICLE && (kind != HWY_KIND_IDM || !crashed))
             follow_road(g, st, i);  // behavior.py:102-103, controller.py:98
         // IDMVehicle(enable_lane_change=False) never runs change_lane_policy (behavior.py:104-105)
         if (kind == HWY_KIND_IDM && !crashed && !(r.meta & HWY_META_NO_LANE_CHANGE)) {
@@ -974,7 +1121,8 @@ __device__ __forceinline__ void substep(const HwyNetParams& P, const GraphShared
     // ---- parallel part: steering + acceleration
     const bool mobile = active && kind != HWY_KIND_OBSTACLE;  // road.objects neither act nor step
     double sin_beta = 0.0, cos_beta = 1.0;
-    if (mobile) {
+    const bool plain = PLAIN && mobile && kind == HWY_KIND_VEHICLE;  // the ContinuousAction ego: its action dict persists
+    if (mobile && !plain) {
         const int lane = st.lane[i], tgt = st.tgt[i];
         if (!crashed) {
             double lc_s = st.own_s[i], lc_lat = st.own_lat[i];
@@ -1001,10 +1149,26 @@ __device__ __forceinline__ void substep(const HwyNetParams& P, const GraphShared
     if (REG) {
         if (i == 0) st.road_steps += 1;
         group_sync<G>();
-        if (P.regulated && st.road_steps % (int)(1 / dt / 2) == 0) enforce_road_rules(P, g, st, V, i, r);
+        if (P.regulated && st.road_steps % (int)(1 / dt / 2) == 0)
+            enforce_road_rules<G, REG, PLAIN>(P, g, st, V, i, r, act_steer);
     }
     // ---- Road.step: Vehicle.step (kinematics.py:130-177), IDMVehicle.step timer (behavior.py:139-148)
-    if (mobile) {
+    if (PLAIN && plain && P.dynamical) {
+        // BicycleVehicle.step (dynamics.py:142-150): rk4 over (x, y, heading, speed, lateral_speed, yaw_rate); it never
+        // consumes Vehicle.impact (crashed is set by the collision test itself)
+        double bs[6] = {r.x, r.y, r.heading, r.speed, r.target_speed, r.timer};
+        bicycle_advance(bs, crashed, act_steer, act_accel, dt);
+        r.x = bs[0];
+        r.y = bs[1];
+        r.heading = bs[2];
+        r.speed = bs[3];
+        r.target_speed = bs[4];
+        r.timer = bs[5];
+    } else if (mobile) {
+        if (plain) {  // Vehicle.step with the action's steering angle: beta = arctan(1/2 tan(delta_f))
+            if (crashed) act_steer = 0.0;
+            beta_of_angle(act_steer, sin_beta, cos_beta);
+        }
         if (kind == HWY_KIND_IDM) r.timer += dt;
         if (crashed) act_accel = -1.0 * r.speed;
         if (r.speed > kMaxSpeed)
@@ -1027,6 +1191,7 @@ __device__ __forceinline__ void substep(const HwyNetParams& P, const GraphShared
     if (active) publish(st, i, r);
     phase_sync<G>();
     closest_lane_group(g, st, V, i, mobile);  // on_state_update
+    if (plain) st.tgt[i] = st.lane[i];  // schema: a plain Vehicle has no target lane of its own
     // ---- collision sweep (road/road.py:477-481): partners in ascending order => the surviving impact is
     // the one of the largest partner index
     // Road objects (Obstacle: 2 x 2 m, kind 3) sit in the slots after the vehicles, so vehicle i meets its vehicle
@@ -1082,7 +1247,7 @@ __device__ __forceinline__ void load_env(const HwyNetParams& P, const GraphShare
     st.kind[i] = meta_kind(r.meta);
     if (i < count) lane_local(g.lanes[st.lane[i]], r.x, r.y, st.own_s[i], st.own_lat[i]);
     // the controlled vehicle: first MDPVehicle of the list
-    unsigned is_mdp = __ballot_sync(group_mask<G>(), i < count && meta_kind(r.meta) == HWY_KIND_MDP);
+    unsigned is_mdp = __ballot_sync(group_mask<G>(), i < count && is_controlled_kind(meta_kind(r.meta)));
     is_mdp >>= ((threadIdx.x & 31) & ~(G - 1));
     if (i == 0) {
         st.ego = is_mdp ? __ffs(is_mdp) - 1 : 0;
@@ -1167,6 +1332,10 @@ __device__ __forceinline__ void adopt_spawn(const HwyNetParams& P, const HwyInte
         r.target_speed = st.sp_speed;
         r.timer = py_mod_pos((st.sp_x + st.sp_y) * kPi, P.lane_change_delay);  // behavior.py:59
         r.delta = st.sp_delta;
+    } else if (kind == HWY_KIND_VEHICLE) {  // no target speed; (lateral_speed, yaw_rate) = 0 (dynamics.py:52-53)
+        r.target_speed = 0.0;
+        r.timer = 0.0;
+        r.delta = 4.0;
     } else {
         r.target_speed = st.sp_ts;
         r.timer = 0.0;
@@ -1177,7 +1346,8 @@ __device__ __forceinline__ void adopt_spawn(const HwyNetParams& P, const HwyInte
              (kind << HWY_META_KIND_SHIFT) | HWY_META_PRESENT;
     const int* rs = SP.route_table + ((size_t)st.sp_lane * 4 + st.sp_dest) * R;
     for (int k = 0; k < R; ++k) st.route[i][k] = rs[k];
-    st.route_len[i] = SP.route_len[(size_t)st.sp_lane * 4 + st.sp_dest];
+    // plan_route_to raises AttributeError on a plain Vehicle: no route (intersection_env.py:309-315)
+    st.route_len[i] = kind == HWY_KIND_VEHICLE ? 0 : SP.route_len[(size_t)st.sp_lane * 4 + st.sp_dest];
     st.lane[i] = st.tgt[i] = st.sp_lane;
     st.kind[i] = kind;
     lane_local(g.lanes[st.sp_lane], r.x, r.y, st.own_s[i], st.own_lat[i]);
@@ -1202,7 +1372,7 @@ __device__ __forceinline__ void store_rng(uint64_t* rng, size_t n, int e, const 
 }
 
 // ------------------------------------------------------------------ the step kernel
-template <int G, bool REG>
+template <int G, bool REG, bool PLAIN>
 __global__ void __launch_bounds__(kBlockThreads)
 network_step_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGraph* __restrict__ graph, const __grid_constant__ HwyNetState S,
                     const __grid_constant__ HwyIntersectionSpawn SP, const int32_t* __restrict__ action, float* __restrict__ obs,
@@ -1234,16 +1404,20 @@ network_step_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGraph* _
     const double dt = 1.0 / P.simulation_frequency;
     const int A = n_agents_of(P);
     // this thread's agent number (controlled vehicles in list order), its action and its MDPVehicle.speed_index
-    const bool is_agent = i < st.count && meta_kind(r.meta) == HWY_KIND_MDP;
+    const bool is_agent = i < st.count && is_controlled_kind(meta_kind(r.meta));
     const int my_agent = is_agent ? min(__popc(st.agent_mask & ((1u << i) - 1u)), A - 1) : 0;
-    const int act = action[(size_t)e * A + my_agent];
+    // ContinuousAction (P.action_type == 1): `action` holds float32 (throttle, steering) pairs, one per controlled vehicle
+    const bool continuous = P.action_type == 1;
+    const float* act_f = continuous ? reinterpret_cast<const float*>(action) + 2 * ((size_t)e * A + my_agent) : nullptr;
+    const int act = continuous ? 1 : action[(size_t)e * A + my_agent];
     // action label: DiscreteMetaAction.ACTIONS_ALL, or ACTIONS_LONGI {0 SLOWER, 1 IDLE, 2 FASTER} (action.py:204-206)
-    const int label = P.action_mode == 1 ? (act == 0 ? 4 : (act == 2 ? 3 : 1)) : act;
+    const int label = continuous ? -1 : (P.action_mode == 1 ? (act == 0 ? 4 : (act == 2 ? 3 : 1)) : act);
     int my_speed_index = is_agent ? S.speed_index[(size_t)e * A + my_agent] : 0;
-    double act_accel = 0.0;
+    double act_accel = 0.0, act_steer = 0.0;
 
     for (int frame = 0; frame < frames; ++frame)
-        substep(P, g, st, i, r, act_accel, dt, frame == 0 ? label : -1, &my_speed_index);
+        substep<G, REG, PLAIN>(P, g, st, i, r, act_accel, act_steer, dt, frame == 0 ? label : -1, &my_speed_index,
+                               frame == 0 ? act_f : nullptr);
     group_sync<G>();
 
     // ---- epilogue: observation, reward, termination (before any population change)
@@ -1421,7 +1595,7 @@ network_step_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGraph* _
     int dst = i < V ? i : -1;
     if (REG && P.dynamic_population) {
         bool keep = i < V;
-        if (keep && meta_kind(r.meta) != HWY_KIND_MDP) {  // _clear_vehicles :354-366
+        if (keep && !is_controlled_kind(meta_kind(r.meta))) {  // _clear_vehicles :354-366
             const HwyNetLane& L = g.lanes[st.lane[i]];
             if (L.exit_lane && st.own_s[i] >= L.length - 4 * kVehLength) keep = false;
         }
@@ -1535,8 +1709,8 @@ network_substeps_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGrap
     Regs r;
     load_env(P, g, S, st, env, i, r);
     const double dt = 1.0 / P.simulation_frequency;
-    double act_accel = 0.0;
-    for (int k = 0; k < n_substeps; ++k) substep(P, g, st, i, r, act_accel, dt, -1);
+    double act_accel = 0.0, act_steer = 0.0;
+    for (int k = 0; k < n_substeps; ++k) substep(P, g, st, i, r, act_accel, act_steer, dt, -1);
     group_sync<G>();
     if (!selected) return;
     store_env(S, st, env, i, i < st.count ? i : -1, r);
@@ -1640,8 +1814,8 @@ intersection_reset_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGr
     }
     // ---- :271-278  3 s of simulation under the RegulatedRoad rules
     const double dt = 1.0 / P.simulation_frequency;
-    double act_accel = 0.0;
-    for (int k = 0; k < 3 * P.simulation_frequency; ++k) substep(P, g, st, i, r, act_accel, dt, -1);
+    double act_accel = 0.0, act_steer = 0.0;
+    for (int k = 0; k < 3 * P.simulation_frequency; ++k) substep(P, g, st, i, r, act_accel, act_steer, dt, -1);
     group_sync<G>();
     // ---- :281-288  the challenger: certain, going straight, tight deviations
     if (i == 0) {
@@ -1674,21 +1848,24 @@ intersection_reset_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGr
             }
             st.sp_lane = cl;
             st.sp_dest = dest;
-            st.speed_index = speed_to_index(P, st.sp_speed);  // MDPVehicle.__init__ (controller.py:283-293)
-            st.sp_ts = P.target_speeds[st.speed_index];
+            // MDPVehicle.__init__ (controller.py:283-293); a plain Vehicle has no speed index (-1 in the state)
+            const int si0 = speed_to_index(P, st.sp_speed);
+            st.speed_index = P.action_type == 1 ? -1 : si0;
+            st.sp_ts = P.target_speeds[si0];
             st.sp_ok = st.count < G ? 1 : 0;
             if (!st.sp_ok && selected && S.overflow) S.overflow[e] += 1;
             if (agent == 0) st.ego = st.count;
         }
-        commit(HWY_KIND_MDP);
+        // action_type.vehicle_class (:291-300): MDPVehicle, or Vehicle / BicycleVehicle for a ContinuousAction
+        commit(P.action_type == 1 ? HWY_KIND_VEHICLE : HWY_KIND_MDP);
     }
     // ---- :317-323  after each controlled vehicle the TRAFFIC within 20 m of it is dropped; controlled vehicles are
     // never dropped and their creation does not look at the others, so all prunings can run at the end
     const int V = st.count;
     bool keep = i < V;
-    if (keep && st.kind[i] != HWY_KIND_MDP) {
+    if (keep && !is_controlled_kind(st.kind[i])) {
         for (int v = 0; v < V; ++v)
-            if (st.kind[v] == HWY_KIND_MDP && norm2(st.x[i] - st.x[v], st.y[i] - st.y[v]) < 20) keep = false;
+            if (is_controlled_kind(st.kind[v]) && norm2(st.x[i] - st.x[v], st.y[i] - st.y[v]) < 20) keep = false;
     }
     const unsigned keep_mask = __ballot_sync(group_mask<G>(), keep) >> ((threadIdx.x & 31) & ~(G - 1));
     const int dst = keep ? __popc(keep_mask & ((1u << i) - 1u)) : -1;
@@ -2136,8 +2313,18 @@ int launch_step(const HwyNetParams* p, const HwyNetGraph* graph, const HwyInters
                 double* info_speed, uint8_t* info_crashed, cudaStream_t st, const int* list = nullptr,
                 double* agents_reward = nullptr, uint8_t* agents_terminated = nullptr) {
     const size_t smem = net_smem_bytes<G, REG>();
-    if (configure_smem(hwynet::network_step_kernel<G, REG>, smem)) return 1;
-    hwynet::network_step_kernel<G, REG><<<blocks_for(s->n_envs, G), hwynet::kBlockThreads, smem, st>>>(
+    if constexpr (REG) {
+        if (p->action_type == 1) {  // a ContinuousAction ego (plain Vehicle / BicycleVehicle): its own instantiation
+            if (configure_smem(hwynet::network_step_kernel<G, REG, true>, smem)) return 1;
+            hwynet::network_step_kernel<G, REG, true><<<blocks_for(s->n_envs, G), hwynet::kBlockThreads, smem, st>>>(
+                *p, graph, *s, sp, action, obs, reward, terminated, truncated, info_speed, info_crashed, list,
+                agents_reward, agents_terminated);
+            return check_launch("network_step_kernel");
+        }
+    }
+    if (p->action_type == 1) return fail("%s", "ContinuousAction is implemented on the intersection family (32-slot state)");
+    if (configure_smem(hwynet::network_step_kernel<G, REG, false>, smem)) return 1;
+    hwynet::network_step_kernel<G, REG, false><<<blocks_for(s->n_envs, G), hwynet::kBlockThreads, smem, st>>>(
         *p, graph, *s, sp, action, obs, reward, terminated, truncated, info_speed, info_crashed, list, agents_reward,
         agents_terminated);
     return check_launch("network_step_kernel");
@@ -2165,7 +2352,7 @@ int hwy_network_obs_size(const HwyNetParams* p) {
     const int agents = p->n_agents > 1 ? p->n_agents : 1;  // one observation per controlled vehicle
     if (p->obs_type == HWY_OBS_OCCUPANCY) return agents * 4 * 11 * 11;
     if (p->obs_type == HWY_OBS_TTC) return agents * 9 * (int)(p->ttc_horizon / (1.0 / p->policy_frequency));
-    return agents * p->obs_vehicles_count * (p->obs_features == 7 ? 7 : 5);
+    return agents * p->obs_vehicles_count * (p->obs_n_feat > 0 ? p->obs_n_feat : (p->obs_features == 7 ? 7 : 5));
 }
 
 int hwy_network_step(const HwyNetParams* p, const HwyNetGraph* graph, const HwyNetState* s,

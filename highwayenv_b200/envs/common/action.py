@@ -81,8 +81,8 @@ class ContinuousAction(ActionType):
                  clip: bool = True, **kwargs):
         if not (longitudinal and lateral):
             raise NotImplementedError("ContinuousAction needs both longitudinal and lateral control here")
-        if dynamical:
-            raise NotImplementedError("dynamical=True (BicycleVehicle, vehicle/dynamics.py) is out of scope")
+        # dynamical=True selects BicycleVehicle (vehicle/dynamics.py:33-160): on the network kernels only
+        self.dynamical = bool(dynamical)
         if speed_range is not None:
             raise NotImplementedError("speed_range (per-vehicle MIN/MAX_SPEED override) is not supported")
         self.acceleration_range = tuple(acceleration_range) if acceleration_range else self.ACCELERATION_RANGE
@@ -93,6 +93,8 @@ class ContinuousAction(ActionType):
         return Box(-1.0, 1.0, shape=(2,), dtype=np.float32)
 
     def fill_params(self, p):
+        if self.dynamical:
+            raise NotImplementedError("dynamical=True (BicycleVehicle) is implemented on the intersection family only")
         p.action_type = 1
         p.n_target_speeds = 3
         for k, t in enumerate(np.linspace(20, 30, 3)):

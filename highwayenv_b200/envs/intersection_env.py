@@ -30,6 +30,7 @@ from .. import _native as N
 from ..config import default_config
 from ..road.network import NetworkTable
 from ..spaces import Box, Discrete, batch_space
+from .common.action import ContinuousAction, DiscreteAction
 from .common.observation import (KinematicObservation, ObservationHost, OccupancyGridObservation,
                                  observation_factory)
 
@@ -134,12 +135,19 @@ class BatchedIntersectionEnv(ObservationHost):
         if not 1 <= self.n_agents <= 4:
             raise ValueError("controlled_vehicles must be in 1..4")
         self.multi_agent = multi
-        if act["type"] != "DiscreteMetaAction":
-            if act["type"] in ("ContinuousAction", "DiscreteAction", "MultiAgentAction"):
-                raise NotImplementedError(f"action type {act['type']!r} on intersection-v0")
-            raise ValueError("Unknown action type")
+        # ContinuousAction / DiscreteAction (envs/common/action.py:73-196; the reference's intersection-v1): the controlled
+        # vehicle is a plain Vehicle, or with dynamical=True a BicycleVehicle (vehicle/dynamics.py)
+        self.action_type = None
         longi, lat = act.get("longitudinal", True), act.get("lateral", True)
-        if not longi:
+        if act["type"] in ("ContinuousAction", "DiscreteAction"):
+            if multi:
+                raise NotImplementedError("MultiAgentAction over ContinuousAction")
+            self.action_type = (DiscreteAction if act["type"] == "DiscreteAction" else ContinuousAction)(**act)
+        elif act["type"] != "DiscreteMetaAction":
+            if act["type"] == "MultiAgentAction":
+                raise NotImplementedError("nested MultiAgentAction")
+            raise ValueError("Unknown action type")
+        elif not longi:
             raise NotImplementedError("lateral-only meta-actions")
         ts = act.get("target_speeds")
         self.target_speeds = np.linspace(20, 30, 3) if ts is None else np.array(ts, dtype=np.float64)
@@ -153,6 +161,14 @@ class BatchedIntersectionEnv(ObservationHost):
             p.target_speeds[k] = float(t)
         p.action_mode = 1 if not lat else 0
         self.single_action_space = Discrete(3 if not lat else 5)
+        if self.action_type is not None:
+            if self.reset_mode != "device":
+                raise NotImplementedError("ContinuousAction / DiscreteAction envs reset on the device")
+            at = self.action_type
+            p.action_type, p.act_clip, p.dynamical = 1, int(at.clip), int(at.dynamical)
+            p.acc_lo, p.acc_hi = float(at.acceleration_range[0]), float(at.acceleration_range[1])
+            p.steer_lo, p.steer_hi = float(at.steering_range[0]), float(at.steering_range[1])
+            self.single_action_space = at.space()
         p.obs_features = 5
         # ---- observation plugin: the reference's factory rule (one registry, envs/common/observation.py); the step
         # kernel writes Kinematics (5 / 7 columns) and the default OccupancyGrid itself, any other plugin observes
@@ -164,11 +180,17 @@ class BatchedIntersectionEnv(ObservationHost):
             p.obs_type, p.obs_vehicles_count, fused = N.OBS_OCCUPANCY, 5, True
         elif isinstance(plugin, KinematicObservation):
             feats = plugin.features
-            if feats[:5] != ["presence", "x", "y", "vx", "vy"] or feats[5:] not in ([], ["cos_h", "sin_h"]):
-                raise NotImplementedError(f"Kinematics features {feats}")
             if obs.get("observe_intentions"):
                 raise NotImplementedError("Kinematics observe_intentions")
             fr = plugin.features_range
+            if feats[:5] != ["presence", "x", "y", "vx", "vy"] or feats[5:] not in ([], ["cos_h", "sin_h"]):
+                # any Vehicle.to_dict column list (vehicle/kinematics.py:237-261) with per-column ranges
+                rng = fr if fr is not None else {"x": [-200.0, 200.0], "y": [-4.0, 4.0], "vx": [-80.0, 80.0], "vy": [-80.0, 80.0]}
+                p.obs_n_feat = len(feats)
+                for k, f in enumerate(feats):
+                    p.obs_feat[k] = N.FEATURE_CODES[f]
+                    if f in rng:
+                        p.obs_feat_ranged[k], p.obs_feat_lo[k], p.obs_feat_hi[k] = 1, float(rng[f][0]), float(rng[f][1])
             if fr is None:  # normalize_obs (observation.py:214-226): the controlled vehicle spawns on a one-lane road
                 fr = {"x": [-5.0 * 40.0, 5.0 * 40.0], "y": [-4.0, 4.0], "vx": [-2 * 40.0, 2 * 40.0], "vy": [-2 * 40.0, 2 * 40.0]}
             p.obs_type, p.obs_features = N.OBS_KINEMATICS, len(feats)
@@ -245,7 +267,10 @@ class BatchedIntersectionEnv(ObservationHost):
         self._reward = z(n, dtype=torch.float64)
         self._terminated, self._truncated = z(n, dtype=torch.uint8), z(n, dtype=torch.uint8)
         self._info_speed, self._info_crashed = z(n, dtype=torch.float64), z(n, dtype=torch.uint8)
-        self._action_buf = z(n, A, dtype=torch.int32) if self.multi_agent else z(n, dtype=torch.int32)
+        if self.action_type is not None:  # ContinuousAction: float32 (throttle, steering); DiscreteAction gathers into it
+            self._action_buf = z(n, 2, dtype=torch.float32)
+        else:
+            self._action_buf = z(n, A, dtype=torch.int32) if self.multi_agent else z(n, dtype=torch.int32)
         st = N.HwyNetState()
         st.n_envs, st.vp = n, vp
         st.pos, st.hs, st.tt, st.imp = (t.data_ptr() for t in (self._pos, self._hs, self._tt, self._imp))
@@ -302,6 +327,9 @@ class BatchedIntersectionEnv(ObservationHost):
             "kind": (meta >> N.META_KIND_SHIFT) & 3, "crashed": (meta & N.META_CRASHED) != 0,
             "has_impact": (meta & N.META_HAS_IMPACT) != 0, "check_collisions": (meta & N.META_CHECK_COLLISIONS) != 0,
             "is_yielding": (meta & N.META_YIELDING) != 0,
+            # BicycleVehicle.lateral_speed / yaw_rate (vehicle/dynamics.py:52-53) live in the tt pair of a plain Vehicle
+            "lat_speed": np.where(((meta >> N.META_KIND_SHIFT) & 3) == N.KIND_VEHICLE, tt[..., 0], 0.0),
+            "yaw_rate": np.where(((meta >> N.META_KIND_SHIFT) & 3) == N.KIND_VEHICLE, tt[..., 1], 0.0),
             "route": self._route.cpu().numpy(), "route_len": self._route_len.cpu().numpy(),
             "speed_index": (self._speed_index.cpu().numpy().reshape(self.num_envs, self.n_agents)
                             if self.multi_agent else self._speed_index.cpu().numpy()),
@@ -316,7 +344,11 @@ class BatchedIntersectionEnv(ObservationHost):
         f = lambda a, dt=np.float64: torch.from_numpy(np.ascontiguousarray(np.nan_to_num(np.asarray(a, dtype=dt)))).to(dev)  # noqa: E731
         self._pos[idx] = f(np.stack([sd["x"], sd["y"]], axis=-1))
         self._hs[idx] = f(np.stack([sd["heading"], sd["speed"]], axis=-1))
-        self._tt[idx] = f(np.stack([sd["target_speed"], sd["timer"]], axis=-1))
+        ts, tm = np.asarray(sd["target_speed"], dtype=np.float64), np.asarray(sd["timer"], dtype=np.float64)
+        if "lat_speed" in sd:  # plain Vehicle slots carry (lateral_speed, yaw_rate) instead of (target_speed, timer)
+            plain = np.asarray(sd["kind"]) == N.KIND_VEHICLE
+            ts, tm = np.where(plain, np.nan_to_num(sd["lat_speed"]), ts), np.where(plain, np.nan_to_num(sd["yaw_rate"]), tm)
+        self._tt[idx] = f(np.stack([ts, tm], axis=-1))
         self._imp[idx] = f(np.stack([sd["impact_x"], sd["impact_y"]], axis=-1))
         self._delta[idx] = f(sd["delta"])
         meta = ((np.asarray(sd["lane"], dtype=np.int64) << N.META_LANE_SHIFT)
@@ -532,7 +564,14 @@ class BatchedIntersectionEnv(ObservationHost):
         if self._rngs is None:
             raise RuntimeError("call reset() before step()")
         buf = self._action_buf
-        if isinstance(actions, torch.Tensor) and actions.device == buf.device and actions.dtype == buf.dtype \
+        table = getattr(self.action_type, "table", None)
+        if table is not None:  # DiscreteAction (action.py:165-196): index -> (throttle, steering), then ContinuousAction
+            if getattr(self, "_action_table", None) is None or self._action_table.device != buf.device:
+                self._action_table = torch.from_numpy(table).to(buf.device)
+            idx = actions if isinstance(actions, torch.Tensor) else torch.from_numpy(np.asarray(actions))
+            torch.index_select(self._action_table, 0, idx.to(device=buf.device, dtype=torch.long).reshape(-1), out=buf)
+            act = buf
+        elif isinstance(actions, torch.Tensor) and actions.device == buf.device and actions.dtype == buf.dtype \
                 and actions.shape == buf.shape and actions.is_contiguous():
             act = actions
         elif isinstance(actions, torch.Tensor):  # dtype / device conversion without a host round trip
@@ -618,6 +657,16 @@ class BatchedIntersectionEnv(ObservationHost):
     @property
     def unwrapped(self):
         return self
+
+
+class BatchedContinuousIntersectionEnv(BatchedIntersectionEnv):
+    """`intersection-v1` (ContinuousIntersectionEnv, envs/intersection_env.py:431-473): ContinuousAction with the
+    dynamical BicycleVehicle (vehicle/dynamics.py:33-160: RK4 over a 6-state tyre model), steering range +-pi/3, and an
+    8-column absolute Kinematics observation (presence, x, y, vx, vy, long_off, lat_off, ang_off).  Under RegulatedRoad
+    such an ego is not a ControlledVehicle: `is_conflict_possible` forward-simulates a copy of it
+    (Vehicle.predict_trajectory_constant_speed, vehicle/kinematics.py:179-198) — restated in the rules kernel."""
+
+    ENV_ID = "intersection-v1"
 
 
 class BatchedConnectedLaneIntersectionEnv(BatchedIntersectionEnv):

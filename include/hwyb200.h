@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define HWY_ABI_VERSION 9
+#define HWY_ABI_VERSION 10
 #define HWY_MAX_LANES 8
 #define HWY_MAX_TARGET_SPEEDS 8
 #define HWY_MAX_VEHICLES 128 /* per env, incl. the ego */
@@ -271,6 +271,17 @@ typedef struct HwyNetParams {
     int32_t obs_exit_lane;      /* ExitObservation (observation.py:624-675): table index (> 0) of ("1","2",-1), whose
                                  * longitudinal coordinate replaces x in the ego row of the Kinematics table; 0: none */
     int32_t _pad_exit;
+    /* ContinuousAction / DiscreteAction on a network env (envs/common/action.py:73-196; intersection-v1): the
+     * controlled vehicle is a plain Vehicle (kind HWY_KIND_VEHICLE) or, with `dynamical`, a BicycleVehicle
+     * (vehicle/dynamics.py:33-160, whose lateral_speed / yaw_rate live in the vehicle's tt pair).  `action` of the
+     * step entry points then points to float32 [n_envs][2] = (throttle, steering) in [-1, 1]. */
+    int32_t action_type;        /* 0 DiscreteMetaAction labels (int32), 1 ContinuousAction (float32 pairs) */
+    int32_t act_clip, dynamical;
+    int32_t obs_n_feat;         /* > 0: Kinematics columns obs_feat[0..n) (HWY_FEAT_*, any Vehicle.to_dict key) with
+                                 * per-column ranges; 0: the (presence, x, y, vx, vy [, cos_h, sin_h]) table above */
+    double acc_lo, acc_hi, steer_lo, steer_hi;
+    int32_t obs_feat[HWY_MAX_OBS_FEATURES], obs_feat_ranged[HWY_MAX_OBS_FEATURES];
+    double obs_feat_lo[HWY_MAX_OBS_FEATURES], obs_feat_hi[HWY_MAX_OBS_FEATURES];
 } HwyNetParams;
 
 /* route entry: from_node | to_node << 8 | (lane_id + 1) << 16  (lane_id + 1 == 0: None) */

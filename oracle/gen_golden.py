@@ -75,6 +75,12 @@ CASES = {
     # u-turn-v0: circular U-turn, routed traffic, ego with PURSUIT_TAU = TAU_HEADING, TimeToCollision horizon 16
     "u_turn_ttc": ("u-turn-v0", None, list(range(970, 1002)), 10, "discrete5"),
     "u_turn_v1_ttc": ("u-turn-v1", None, list(range(980, 1012)), 10, "discrete5"),
+    # intersection-v1 (ContinuousIntersectionEnv): ContinuousAction with the dynamical BicycleVehicle, 8-column Kinematics;
+    # and intersection-v0 with a kinematic ContinuousAction / DiscreteAction ego (plain Vehicle under RegulatedRoad)
+    "intersection_v1": ("intersection-v1", None, list(range(1200, 1232)), 13, "box2"),
+    "intersection_continuous": ("intersection-v0", {"action": {"type": "ContinuousAction", "longitudinal": True,
+                                                               "lateral": True}},
+                                list(range(1240, 1272)), 13, "box2"),
     # exit-v0: three highway sections (6 / 7 / 6 lanes) with an exit ramp, routed traffic without lane changes,
     # ExitObservation, goal reward on the exit lane
     "exit_obs": ("exit-v0", None, list(range(1100, 1132)), 18, "discrete5"),

@@ -378,7 +378,9 @@ static double idm_acceleration(const World *w, int self_, int ego, int front) {
     const NetCfg *c = w->c;
     const NetState *s = w->s;
     if (ego < 0 || s->kind[ego] == NET_KIND_OBSTACLE) return 0; /* `not isinstance(ego_vehicle, Vehicle)` (behavior.py:171) */
-    double ego_target_speed = clipd(s->target_speed[ego], 0, LANE(w, s->lane[ego])->speed_limit);
+    /* getattr(ego_vehicle, "target_speed", 0): a plain Vehicle has none (behavior.py:172) */
+    double ego_ts = s->kind[ego] == NET_KIND_VEHICLE ? 0.0 : s->target_speed[ego];
+    double ego_target_speed = clipd(ego_ts, 0, LANE(w, s->lane[ego])->speed_limit);
     double acceleration =
         c->comfort_acc_max *
         (1 - pow(fmax(s->speed[ego], 0) / fabs(orc_not_zero(ego_target_speed)), s->delta[self_]));
@@ -615,20 +617,21 @@ static void mdp_act(World *w, int v, int action) { mdp_act_agent(w, v, action, 0
 /* the k-th controlled vehicle (env.controlled_vehicles order == list order of the MDP vehicles); -1: none */
 static int agent_vehicle(const World *w, int k) {
     for (int v = 0; v < w->V; v++)
-        if (w->s->kind[v] == NET_KIND_MDP && k-- == 0) return v;
+        if ((w->s->kind[v] == NET_KIND_MDP || w->s->kind[v] == NET_KIND_VEHICLE) && k-- == 0) return v;
     return -1;
 }
 
 /* index of the controlled vehicle: first MDP vehicle of the list */
 static int ego_index(const World *w) {
     for (int v = 0; v < w->V; v++)
-        if (w->s->kind[v] == NET_KIND_MDP) return v;
+        if (w->s->kind[v] == NET_KIND_MDP || w->s->kind[v] == NET_KIND_VEHICLE) return v;
     return 0;
 }
 
 static void road_act(World *w) {
     for (int v = 0; v < w->V; v++) {
         if (w->s->kind[v] == NET_KIND_OBSTACLE) continue; /* road.objects do not act (road.py:464-467) */
+        if (w->s->kind[v] == NET_KIND_VEHICLE) continue;  /* Vehicle.act(None): keeps its action (kinematics.py:119-128) */
         if (w->s->kind[v] == NET_KIND_IDM)
             idm_act(w, v);
         else
@@ -636,10 +639,92 @@ static void road_act(World *w) {
     }
 }
 
+/* BicycleVehicle.derivative_func (vehicle/dynamics.py:73-111) on state (x, y, heading, speed, lateral_speed,
+ * yaw_rate) with the action's steering / acceleration */
+#define BIKE_MASS 1.0
+#define BIKE_LENGTH_A (VEH_LENGTH / 2)
+#define BIKE_LENGTH_B (VEH_LENGTH / 2)
+#define BIKE_INERTIA_Z (1.0 / 12 * BIKE_MASS * (VEH_LENGTH * VEH_LENGTH + VEH_WIDTH * VEH_WIDTH))
+#define BIKE_FRICTION_FRONT (15.0 * BIKE_MASS)
+#define BIKE_FRICTION_REAR (15.0 * BIKE_MASS)
+static void bicycle_derivative(const double st[6], double steering, double acceleration, double d[6]) {
+    const double heading = st[2], speed = st[3], lateral_speed = st[4], yaw_rate = st[5];
+    const double delta_f = steering, delta_r = 0;
+    double theta_vf = atan2(lateral_speed + BIKE_LENGTH_A * yaw_rate, speed);
+    double theta_vr = atan2(lateral_speed - BIKE_LENGTH_B * yaw_rate, speed);
+    double f_yf = 2 * BIKE_FRICTION_FRONT * (delta_f - theta_vf);
+    double f_yr = 2 * BIKE_FRICTION_REAR * (delta_r - theta_vr);
+    if (fabs(speed) < 1) { /* low speed dynamics: damping of lateral speed and yaw rate */
+        f_yf = -BIKE_MASS * lateral_speed - BIKE_INERTIA_Z / BIKE_LENGTH_A * yaw_rate;
+        f_yr = -BIKE_MASS * lateral_speed + BIKE_INERTIA_Z / BIKE_LENGTH_A * yaw_rate;
+    }
+    double d_lateral_speed = 1 / BIKE_MASS * (f_yf + f_yr) - yaw_rate * speed;
+    double d_yaw_rate = 1 / BIKE_INERTIA_Z * (BIKE_LENGTH_A * f_yf - BIKE_LENGTH_B * f_yr);
+    double c = cos(heading), sn = sin(heading);
+    d[0] = c * speed + (-sn) * lateral_speed; /* R @ [speed, lateral_speed] */
+    d[1] = sn * speed + c * lateral_speed;
+    d[2] = yaw_rate;
+    d[3] = acceleration;
+    d[4] = d_lateral_speed;
+    d[5] = d_yaw_rate;
+}
+/* dynamics.py:13-30 rk4 and BicycleVehicle.step (:142-150) on an explicit state; clip_actions (:153-161) first */
+static void bicycle_advance(double st[6], int crashed, double *steering, double *acceleration, double dt) {
+    if (crashed) { /* Vehicle.clip_actions (kinematics.py:155-168) */
+        *steering = 0;
+        *acceleration = -1.0 * st[3];
+    }
+    if (st[3] > MAX_SPEED)
+        *acceleration = fmin(*acceleration, 1.0 * (MAX_SPEED - st[3]));
+    else if (st[3] < MIN_SPEED)
+        *acceleration = fmax(*acceleration, 1.0 * (MIN_SPEED - st[3]));
+    *steering = clipd(*steering, -M_PI / 2, M_PI / 2);
+    st[5] = clipd(st[5], -2 * M_PI, 2 * M_PI); /* MAX_ANGULAR_SPEED */
+    double f1[6], f2[6], f3[6], f4[6], tmp[6];
+    bicycle_derivative(st, *steering, *acceleration, f1);
+    for (int k = 0; k < 6; k++) tmp[k] = st[k] + (f1[k] * (dt / 2));
+    bicycle_derivative(tmp, *steering, *acceleration, f2);
+    for (int k = 0; k < 6; k++) tmp[k] = st[k] + (f2[k] * (dt / 2));
+    bicycle_derivative(tmp, *steering, *acceleration, f3);
+    for (int k = 0; k < 6; k++) tmp[k] = st[k] + (f3[k] * dt);
+    bicycle_derivative(tmp, *steering, *acceleration, f4);
+    for (int k = 0; k < 6; k++) st[k] = st[k] + (dt / 6) * (f1[k] + (2 * f2[k]) + (2 * f3[k]) + f4[k]);
+}
+/* Vehicle.step on an explicit state (kinematics.py:130-153), the impact handled by the caller */
+static void kinematic_advance(double st[4], int crashed, double *steering, double *acceleration, double dt) {
+    if (crashed) {
+        *steering = 0;
+        *acceleration = -1.0 * st[3];
+    }
+    if (st[3] > MAX_SPEED)
+        *acceleration = fmin(*acceleration, 1.0 * (MAX_SPEED - st[3]));
+    else if (st[3] < MIN_SPEED)
+        *acceleration = fmax(*acceleration, 1.0 * (MIN_SPEED - st[3]));
+    double beta = atan(1.0 / 2 * tan(*steering));
+    double vx = st[3] * cos(st[2] + beta), vy = st[3] * sin(st[2] + beta);
+    st[0] += vx * dt;
+    st[1] += vy * dt;
+    st[2] += st[3] * sin(beta) / (VEH_LENGTH / 2) * dt;
+    st[3] += *acceleration * dt;
+}
+
 /* vehicle/kinematics.py:130-177 (+ behavior.py:139-148) */
 static void vehicle_step(World *w, int v, double dt) {
     NetState *s = w->s;
     if (s->kind[v] == NET_KIND_OBSTACLE) return; /* only road.vehicles step (road.py:475-476) */
+    if (s->kind[v] == NET_KIND_VEHICLE && w->c->dynamical) { /* BicycleVehicle.step: no impact handling of its own */
+        double st[6] = {s->x[v], s->y[v], s->heading[v], s->speed[v], s->lat_speed[v], s->yaw_rate[v]};
+        /* clip_actions clips yaw_rate in place before the state is read */
+        bicycle_advance(st, s->crashed[v], &w->act_steer[v], &w->act_accel[v], dt);
+        s->x[v] = st[0];
+        s->y[v] = st[1];
+        s->heading[v] = st[2];
+        s->speed[v] = st[3];
+        s->lat_speed[v] = st[4];
+        s->yaw_rate[v] = st[5];
+        s->lane[v] = s->target_lane[v] = net_closest_lane(w->g, s->x[v], s->y[v], s->heading[v]);
+        return;
+    }
     if (s->kind[v] == NET_KIND_IDM) s->timer[v] += dt;
     if (s->crashed[v]) {
         w->act_steer[v] = 0;
@@ -663,6 +748,7 @@ static void vehicle_step(World *w, int v, double dt) {
     s->heading[v] += s->speed[v] * sin(beta) / (VEH_LENGTH / 2) * dt;
     s->speed[v] += w->act_accel[v] * dt;
     s->lane[v] = net_closest_lane(w->g, s->x[v], s->y[v], s->heading[v]);
+    if (s->kind[v] == NET_KIND_VEHICLE) s->target_lane[v] = s->lane[v]; /* schema: no target lane of its own */
 }
 
 static double object_length(const NetState *s, int v) { /* RoadObject.LENGTH 2 (objects.py:25), Vehicle 5 */
@@ -835,11 +921,64 @@ void net_observe_ttc_from(const NetGraph *g, const NetCfg *c, const NetState *s,
 
 /* envs/common/observation.py:234-276 with explicit features_range / absolute; optional
  * cos_h, sin_h columns (vehicle/kinematics.py:247-248), which have no features_range entry */
+static double vehicle_feature(const NetGraph *g, const NetState *s, int v, int origin, int feat, int observe_intentions);
 static void observe_kinematics_from(const World *w, int ego, float *obs);
 static void observe_kinematics(const World *w, float *obs) { observe_kinematics_from(w, ego_index(w), obs); }
+/* KinematicObservation.observe (observation.py:234-276) with a configured column list (any Vehicle.to_dict key,
+ * vehicle/kinematics.py:237-261) and per-column ranges: cfg->obs_n_feat > 0 */
+static void observe_kinematics_features(const World *w, int ego, float *obs) {
+    const NetCfg *c = w->c;
+    const NetState *s = w->s;
+    const int K = c->obs_vehicles_count, V = w->V, F = c->obs_n_feat;
+    int *cand = (int *)malloc(sizeof(int) * (V > 0 ? V : 1));
+    double *key = (double *)malloc(sizeof(double) * (V > 0 ? V : 1));
+    int nc = 0;
+    for (int v = 0; v < V; v++) { /* close_objects_to, as observe_kinematics_from */
+        if (!(norm2(s->x[v] - s->x[ego], s->y[v] - s->y[ego]) < c->perception_distance)) continue;
+        if (v == ego) continue;
+        double d = lane_distance_to(w, ego, v);
+        if (!((c->obs_see_behind && s->kind[v] != NET_KIND_OBSTACLE) || -2 * VEH_LENGTH < d)) continue;
+        cand[nc] = v;
+        key[nc] = fabs(d);
+        nc++;
+    }
+    for (int i = 1; i < nc; i++) { /* stable insertion sort == sorted(key=...) */
+        int cv = cand[i];
+        double ck = key[i];
+        int j = i - 1;
+        while (j >= 0 && key[j] > ck) {
+            cand[j + 1] = cand[j];
+            key[j + 1] = key[j];
+            j--;
+        }
+        cand[j + 1] = cv;
+        key[j + 1] = ck;
+    }
+    for (int k = 0; k < K * F; k++) obs[k] = 0.0f;
+    int n_rows = 1 + (nc < K - 1 ? nc : K - 1);
+    for (int row = 0; row < n_rows; row++) {
+        const int v = row == 0 ? ego : cand[row - 1];
+        const int origin = (row == 0 || c->obs_absolute) ? -1 : ego;
+        for (int col = 0; col < F; col++) {
+            double val = vehicle_feature(w->g, s, v, origin, c->obs_feat[col], 0);
+            if (isnan(val)) val = 0; /* road objects have no such column: NaN in the frame */
+            if (c->obs_normalize && c->obs_feat_ranged[col]) {
+                val = lmap(val, c->obs_feat_lo[col], c->obs_feat_hi[col], -1, 1);
+                if (c->obs_clip) val = clipd(val, -1, 1);
+            }
+            obs[row * F + col] = (float)val;
+        }
+    }
+    free(cand);
+    free(key);
+}
 static void observe_kinematics_from(const World *w, int ego, float *obs) {
     const NetCfg *c = w->c;
     const NetState *s = w->s;
+    if (c->obs_n_feat > 0) {
+        observe_kinematics_features(w, ego, obs);
+        return;
+    }
     int K = c->obs_vehicles_count, V = w->V;
     const int F = c->obs_features == 7 ? 7 : 5;
     double *rows = (double *)calloc((size_t)K * F, sizeof(double));
@@ -974,6 +1113,7 @@ static void observe_occupancy(const World *w, float *obs) {
 
 int net_obs_size(const NetCfg *c) {
     if (c->obs_type == NET_OBS_OCCUPANCY) return 4 * 11 * 11;
+    if (c->obs_type == NET_OBS_KINEMATICS && c->obs_n_feat > 0) return c->obs_vehicles_count * c->obs_n_feat;
     if (c->obs_type == NET_OBS_KINEMATICS) return c->obs_vehicles_count * (c->obs_features == 7 ? 7 : 5);
     if (c->obs_type == NET_OBS_TTC) return 3 * 3 * (int)(c->ttc_horizon / (1.0 / c->policy_frequency));
     return c->obs_vehicles_count * 5;
@@ -1131,16 +1271,55 @@ static void position_heading_along_route(const World *w, int v, double longitudi
     }
 }
 
+/* Vehicle.predict_trajectory_constant_speed (vehicle/kinematics.py:179-198) of a NON-controlled-class vehicle (the
+ * ContinuousAction ego): a deep copy acts {acceleration 0, steering = its current steering} ("constant_steering") and
+ * steps through the 11 horizon points with dt = 0.25 (Vehicle.step, or BicycleVehicle.step when dynamical). */
+static void predict_plain_vehicle(const World *w, int v, double px[11], double py[11], double ph[11]) {
+    const NetState *s = w->s;
+    double steering = w->act_steer[v], acceleration = 0.0;
+    double st[6] = {s->x[v], s->y[v], s->heading[v], s->speed[v], s->lat_speed ? s->lat_speed[v] : 0.0,
+                    s->yaw_rate ? s->yaw_rate[v] : 0.0};
+    int crashed = s->crashed[v], has_impact = s->has_impact[v];
+    for (int k = 0; k < 11; k++) {
+        if (w->c->dynamical) {
+            bicycle_advance(st, crashed, &steering, &acceleration, 0.25);
+        } else {
+            kinematic_advance(st, crashed, &steering, &acceleration, 0.25);
+            if (has_impact) { /* kinematics.py:147-150 (applied after the position update) */
+                st[0] += s->impact_x[v];
+                st[1] += s->impact_y[v];
+                crashed = 1;
+                has_impact = 0;
+            }
+        }
+        px[k] = st[0];
+        py[k] = st[1];
+        ph[k] = st[2];
+    }
+}
+
 /* regulation.py:85-111 is_conflict_possible (horizon 3, step 0.25) */
 static int is_conflict_possible(const World *w, int v1, int v2) {
     const NetState *s = w->s;
     double s1 = lane_s(LANE(w, s->lane[v1]), s->x[v1], s->y[v1]);
     double s2 = lane_s(LANE(w, s->lane[v2]), s->x[v2], s->y[v2]);
+    double q1x[11], q1y[11], q1h[11], q2x[11], q2y[11], q2h[11];
+    const int plain1 = s->kind[v1] == NET_KIND_VEHICLE, plain2 = s->kind[v2] == NET_KIND_VEHICLE;
+    if (plain1) predict_plain_vehicle(w, v1, q1x, q1y, q1h);
+    if (plain2) predict_plain_vehicle(w, v2, q2x, q2y, q2h);
     for (int k = 1; k < 12; k++) {
         double t = 0.25 * k; /* np.arange(0.25, 3, 0.25) */
         double p1x, p1y, h1, p2x, p2y, h2;
-        position_heading_along_route(w, v1, s1 + s->speed[v1] * t, &p1x, &p1y, &h1);
-        position_heading_along_route(w, v2, s2 + s->speed[v2] * t, &p2x, &p2y, &h2);
+        if (plain1) {
+            p1x = q1x[k - 1], p1y = q1y[k - 1], h1 = q1h[k - 1];
+        } else {
+            position_heading_along_route(w, v1, s1 + s->speed[v1] * t, &p1x, &p1y, &h1);
+        }
+        if (plain2) {
+            p2x = q2x[k - 1], p2y = q2y[k - 1], h2 = q2h[k - 1];
+        } else {
+            position_heading_along_route(w, v2, s2 + s->speed[v2] * t, &p2x, &p2y, &h2);
+        }
         if (norm2(p2x - p1x, p2y - p1y) > VEH_LENGTH) continue;
         if (orc_rotated_rectangles_intersect(p1x, p1y, 1.5 * VEH_LENGTH, 0.9 * VEH_WIDTH, h1, p2x, p2y,
                                              1.5 * VEH_LENGTH, 0.9 * VEH_WIDTH, h2))
@@ -1238,9 +1417,35 @@ static void reward_done_intersection(const World *w, double *reward, int32_t *te
     *truncated = s->time[0] >= c->duration;
 }
 
-/* envs/common/abstract.py:259-317 */
+/* envs/common/action.py:136-162 ContinuousAction.get_action / act: the Box action is float32 and NEP 50 keeps
+ * utils.lmap (utils.py:31-33) in float32; the vehicle's action dict then holds the widened values */
+static void continuous_act(World *w, int v, const float *a) {
+    const NetCfg *c = w->c;
+    float a0 = a[0], a1 = a[1];
+    if (c->act_clip) {
+        a0 = fminf(fmaxf(a0, -1.0f), 1.0f);
+        a1 = fminf(fmaxf(a1, -1.0f), 1.0f);
+    }
+    float acc = (float)c->acc_lo + (a0 - (-1.0f)) * (float)(c->acc_hi - c->acc_lo) / 2.0f;
+    float steer = (float)c->steer_lo + (a1 - (-1.0f)) * (float)(c->steer_hi - c->steer_lo) / 2.0f;
+    w->act_accel[v] = (double)acc;
+    w->act_steer[v] = (double)steer;
+}
+
+static void net_step_any(const NetGraph *g, const NetCfg *c, NetState *s, int action, const float *action_f,
+                         float *obs, double *reward, int32_t *terminated, int32_t *truncated);
 void net_step(const NetGraph *g, const NetCfg *c, NetState *s, int action, float *obs, double *reward,
               int32_t *terminated, int32_t *truncated) {
+    net_step_any(g, c, s, action, NULL, obs, reward, terminated, truncated);
+}
+void net_step_continuous(const NetGraph *g, const NetCfg *c, NetState *s, const float *action, float *obs,
+                         double *reward, int32_t *terminated, int32_t *truncated) {
+    net_step_any(g, c, s, -1, action, obs, reward, terminated, truncated);
+}
+
+/* envs/common/abstract.py:259-317 */
+static void net_step_any(const NetGraph *g, const NetCfg *c, NetState *s, int action, const float *action_f,
+                         float *obs, double *reward, int32_t *terminated, int32_t *truncated) {
     World w;
     w.g = g;
     w.c = c;
@@ -1257,7 +1462,12 @@ void net_step(const NetGraph *g, const NetCfg *c, NetState *s, int action, float
     int label = action;
     if (c->action_mode == 1) label = action == 0 ? 4 : (action == 2 ? 3 : 1); /* SLOWER / IDLE / FASTER */
     for (int frame = 0; frame < frames; frame++) {
-        if (frame == 0) mdp_act(&w, ego, label);
+        if (frame == 0) {
+            if (action_f)
+                continuous_act(&w, ego, action_f);
+            else
+                mdp_act(&w, ego, label);
+        }
         road_act(&w);
         if (c->regulated) regulated_pre_step(&w, dt);
         road_step(&w, dt);

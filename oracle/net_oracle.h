@@ -27,6 +27,7 @@ extern "C" {
 
 #define NET_KIND_IDM 0
 #define NET_KIND_MDP 1
+#define NET_KIND_VEHICLE 2  /* vehicle/kinematics.py:13 Vehicle (ContinuousAction ego); with cfg->dynamical: BicycleVehicle */
 #define NET_KIND_OBSTACLE 3 /* vehicle/objects.py:213-220 Obstacle: a static 2 x 2 m road object (road.objects);
                              * objects occupy the slots AFTER the vehicles */
 
@@ -88,6 +89,13 @@ typedef struct NetCfg {
     /* exit-v0 (envs/exit_env.py): reward_type 5 */
     double goal_reward;
     int32_t exit_lane_a, exit_lane_b; /* table indices of ("1","2",lanes_count) and ("2","exit",0): _is_success (:178-190) */
+    /* ContinuousAction / DiscreteAction (envs/common/action.py:73-196): the controlled vehicle is a plain Vehicle, or
+     * with `dynamical` a BicycleVehicle (vehicle/dynamics.py:33-160) */
+    int32_t action_type;              /* 0 DiscreteMetaAction, 1 ContinuousAction (float32 [throttle, steering]) */
+    int32_t act_clip, dynamical, obs_n_feat; /* obs_n_feat > 0: Kinematics columns from obs_feat[] (NET_FEAT_*) */
+    double acc_lo, acc_hi, steer_lo, steer_hi;
+    int32_t obs_feat[16], obs_feat_ranged[16];
+    double obs_feat_lo[16], obs_feat_hi[16];
     int32_t obs_exit_lane;            /* ExitObservation (observation.py:624-675): table index of ("1","2",-1) whose
                                        * longitudinal coordinate replaces the ego row's x; -1: plain Kinematics */
     int32_t _pad4;
@@ -107,12 +115,16 @@ typedef struct NetState {
     int32_t *is_yielding; /* [V] RegulatedRoad yield flag */
     int32_t *road_steps;  /* [1] RegulatedRoad.steps */
     int32_t *no_lane_change; /* [V] IDMVehicle(enable_lane_change=False) (behavior.py:48-62,104-105); NULL: all enabled */
+    double *lat_speed, *yaw_rate; /* [V] BicycleVehicle.lateral_speed / yaw_rate (dynamics.py:52-53); NULL: kinematic */
 } NetState;
 
 /* One AbstractEnv.step of a roundabout-v0 style env (MDPVehicle ego in slot 0). */
 void net_step(const NetGraph *g, const NetCfg *c, NetState *s, int action, float *obs,
               double *reward, int32_t *terminated, int32_t *truncated);
 void net_observe(const NetGraph *g, const NetCfg *c, const NetState *s, float *obs);
+/* the same step with a ContinuousAction ego: action = float32 [throttle, steering] in [-1, 1] */
+void net_step_continuous(const NetGraph *g, const NetCfg *c, NetState *s, const float *action, float *obs,
+                         double *reward, int32_t *terminated, int32_t *truncated);
 /* several controlled vehicles (MultiAgentAction / MultiAgentObservation, intersection-multi-agent-v0):
  * actions [n_agents], obs [n_agents][net_obs_size], speed_index [n_agents] in the state */
 void net_step_agents(const NetGraph *g, const NetCfg *c, NetState *s, const int32_t *actions, int n_agents,

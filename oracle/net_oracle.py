@@ -13,7 +13,7 @@ _LIB_PATH = os.path.join(_HERE, "libnet_oracle.so")
 
 NET_MAX_LANES, NET_MAX_NODES, NET_MAX_SUCC, NET_MAX_ROUTE, NET_MAX_TARGET_SPEEDS = 64, 64, 6, 16, 8
 OBS_KINEMATICS, OBS_OCCUPANCY, OBS_TTC = 0, 1, 2
-KIND_IDM, KIND_MDP = 0, 1
+KIND_IDM, KIND_MDP, KIND_VEHICLE = 0, 1, 2
 
 _LANE_I = ("type", "from_node", "to_node", "lane_id", "road_first", "road_count", "forbidden", "priority",
            "exit_lane", "_pad")
@@ -53,7 +53,12 @@ class NetCfg(C.Structure):
                                      "merging_speed_reward")]
         + [("merge_lane", C.c_int32), ("_pad3", C.c_int32), ("left_lane_reward", C.c_double),
            ("ego_pursuit_tau", C.c_double), ("goal_reward", C.c_double), ("exit_lane_a", C.c_int32),
-           ("exit_lane_b", C.c_int32), ("obs_exit_lane", C.c_int32), ("_pad4", C.c_int32)]
+           ("exit_lane_b", C.c_int32),
+           ("action_type", C.c_int32), ("act_clip", C.c_int32), ("dynamical", C.c_int32), ("obs_n_feat", C.c_int32),
+           ("acc_lo", C.c_double), ("acc_hi", C.c_double), ("steer_lo", C.c_double), ("steer_hi", C.c_double),
+           ("obs_feat", C.c_int32 * 16), ("obs_feat_ranged", C.c_int32 * 16),
+           ("obs_feat_lo", C.c_double * 16), ("obs_feat_hi", C.c_double * 16),
+           ("obs_exit_lane", C.c_int32), ("_pad4", C.c_int32)]
     )
 
 
@@ -108,7 +113,8 @@ class NetState(C.Structure):
     _fields_ = ([(k, C.c_void_p) for k in _SF] + [(k, C.c_void_p) for k in _SI]
                 + [("route", C.c_void_p), ("route_len", C.c_void_p), ("speed_index", C.c_void_p),
                    ("time", C.c_void_p), ("count", C.c_void_p), ("is_yielding", C.c_void_p),
-                   ("road_steps", C.c_void_p), ("no_lane_change", C.c_void_p)])
+                   ("road_steps", C.c_void_p), ("no_lane_change", C.c_void_p), ("lat_speed", C.c_void_p),
+                   ("yaw_rate", C.c_void_p)])
 
 
 def build(force: bool = False) -> str:
@@ -131,6 +137,9 @@ def lib():
         _lib.net_step.restype = None
         _lib.net_step.argtypes = [C.POINTER(NetGraph), C.POINTER(NetCfg), C.POINTER(NetState), C.c_int,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.net_step_continuous.restype = None
+        _lib.net_step_continuous.argtypes = [C.POINTER(NetGraph), C.POINTER(NetCfg), C.POINTER(NetState), C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.net_observe.restype = None
         _lib.net_observe.argtypes = [C.POINTER(NetGraph), C.POINTER(NetCfg), C.POINTER(NetState), C.c_void_p]
         _lib.net_step_agents.restype = None
@@ -208,6 +217,11 @@ def cfg_from_dict(config: dict, n_vehicles: int = 5) -> NetCfg:
     for i, t in enumerate(ts):
         c.target_speeds[i] = t
     c.obs_features = 5
+    if act["type"] in ("ContinuousAction", "DiscreteAction"):  # action.py:73-196
+        c.action_type, c.act_clip = 1, int(bool(act.get("clip", True)))
+        c.dynamical = int(bool(act.get("dynamical", False)))
+        ar, sr = act.get("acceleration_range") or (-5, 5.0), act.get("steering_range") or (-np.pi / 4, np.pi / 4)
+        c.acc_lo, c.acc_hi, c.steer_lo, c.steer_hi = float(ar[0]), float(ar[1]), float(sr[0]), float(sr[1])
     if obs["type"] == "OccupancyGrid":
         c.obs_type = OBS_OCCUPANCY
         c.obs_vehicles_count = 5
@@ -224,9 +238,16 @@ def cfg_from_dict(config: dict, n_vehicles: int = 5) -> NetCfg:
         c.obs_normalize = int(bool(obs.get("normalize", True)))
         c.obs_clip = int(bool(obs.get("clip", True)))
         feats = obs.get("features") or ["presence", "x", "y", "vx", "vy"]
-        assert feats[:5] == ["presence", "x", "y", "vx", "vy"] and feats[5:] in ([], ["cos_h", "sin_h"]), feats
+        generic = not (feats[:5] == ["presence", "x", "y", "vx", "vy"] and feats[5:] in ([], ["cos_h", "sin_h"]))
         c.obs_features = len(feats)
         fr = obs.get("features_range")
+        if generic:  # any Vehicle.to_dict column list, per-column ranges
+            assert fr is not None, "generic Kinematics columns: give features_range"
+            c.obs_n_feat = len(feats)
+            for k, f in enumerate(feats):
+                c.obs_feat[k] = FEATURE_CODES[f]
+                if f in fr:
+                    c.obs_feat_ranged[k], c.obs_feat_lo[k], c.obs_feat_hi[k] = 1, float(fr[f][0]), float(fr[f][1])
         if fr is None:  # observation.py:214-226, computed once at the first observe: ego on ("a","b",1), 2 side lanes
             assert "_default_side_lanes" in config, "no features_range: the fixture records the side-lane count"
             w = 4.0 * int(config["_default_side_lanes"])
@@ -294,6 +315,8 @@ class NetOracleBatch:
         self.a["is_yielding"] = np.zeros((n, V), dtype=np.int32)
         self.a["road_steps"] = np.zeros(n, dtype=np.int32)
         self.a["no_lane_change"] = np.zeros((n, V), dtype=np.int32)
+        self.a["lat_speed"] = np.zeros((n, V), dtype=np.float64)
+        self.a["yaw_rate"] = np.zeros((n, V), dtype=np.float64)
         self.obs_size = lib().net_obs_size(C.byref(cfg))
         self.obs = np.zeros((n, self.obs_size), dtype=np.float32)
         self.reward = np.zeros(n, dtype=np.float64)
@@ -309,6 +332,7 @@ class NetOracleBatch:
         st.count = self.a["count"][e:e + 1].ctypes.data
         st.road_steps = self.a["road_steps"][e:e + 1].ctypes.data
         st.no_lane_change = self.a["no_lane_change"][e].ctypes.data
+        st.lat_speed, st.yaw_rate = self.a["lat_speed"][e].ctypes.data, self.a["yaw_rate"][e].ctypes.data
         return st
 
     def observe(self):
@@ -350,8 +374,15 @@ class NetOracleBatch:
         return out
 
     def step(self, actions):
+        if self.cfg.action_type == 1:  # ContinuousAction: float32 [n, 2]
+            acts = np.ascontiguousarray(actions, dtype=np.float32).reshape(self.n, 2)
         for e in range(self.n):
             st = self._state(e)
+            if self.cfg.action_type == 1:
+                lib().net_step_continuous(C.byref(self.g), C.byref(self.cfg), C.byref(st), acts[e].ctypes.data,
+                                          self.obs[e].ctypes.data, self.reward[e:e + 1].ctypes.data,
+                                          self.terminated[e:e + 1].ctypes.data, self.truncated[e:e + 1].ctypes.data)
+                continue
             lib().net_step(C.byref(self.g), C.byref(self.cfg), C.byref(st), int(actions[e]),
                            self.obs[e].ctypes.data, self.reward[e:e + 1].ctypes.data,
                            self.terminated[e:e + 1].ctypes.data, self.truncated[e:e + 1].ctypes.data)
@@ -363,7 +394,8 @@ class NetOracleBatch:
         self.a["target_speed"][e] = np.nan_to_num(st["target_speed"])
         self.a["timer"][e] = np.nan_to_num(st["timer"])
         self.a["delta"][e] = np.nan_to_num(st["delta"], nan=4.0)
-        self.a["lane"][e], self.a["target_lane"][e] = st["lane"], st["target_lane"]
+        self.a["lane"][e] = st["lane"]
+        self.a["target_lane"][e] = np.where(np.asarray(st["target_lane"]) < 0, st["lane"], st["target_lane"])
         self.a["crashed"][e] = st["crashed"]
         has = ~np.isnan(st["impact"][:, 0])
         self.a["has_impact"][e] = has
@@ -380,6 +412,8 @@ class NetOracleBatch:
             kind[0] = KIND_MDP
             self.a["kind"][e] = kind
         self.a["no_lane_change"][e] = st["no_lane_change"] if "no_lane_change" in st else 0
+        self.a["lat_speed"][e] = np.nan_to_num(st["lat_speed"]) if "lat_speed" in st else 0.0
+        self.a["yaw_rate"][e] = np.nan_to_num(st["yaw_rate"]) if "yaw_rate" in st else 0.0
         self.a["route"][e], self.a["route_len"][e] = st["route"], st["route_len"]
         if self.a["speed_index"].ndim == 2:  # one entry per controlled vehicle, in list order
             si = np.asarray(st["speed_index"])[np.asarray(st["kind"]) == KIND_MDP]
@@ -510,7 +544,7 @@ class IntersectionOracle(NetOracleBatch):
             s_, lat_ = C.c_double(), C.c_double()
             lib().net_lane_local(C.byref(L), float(self.a["x"][e, v]), float(self.a["y"][e, v]), C.byref(s_), C.byref(lat_))
             leaving = bool(L.exit_lane) and s_.value >= L.length - 4 * 5.0
-            if self.a["kind"][e, v] == KIND_MDP or not leaving:
+            if self.a["kind"][e, v] in (KIND_MDP, KIND_VEHICLE) or not leaving:
                 keep.append(v)
         if len(keep) != n:
             for k in self.a:
@@ -541,14 +575,20 @@ class IntersectionOracle(NetOracleBatch):
             speed_limit = self.g.lanes[ego_lane].speed_limit
             ts = [self.cfg.target_speeds[i] for i in range(self.cfg.n_target_speeds)]
             si = int(np.clip(np.round((speed_limit - ts[0]) / (ts[-1] - ts[0]) * (len(ts) - 1)), 0, len(ts) - 1))
-            self._append(e, x, y, heading, speed_limit, KIND_MDP, destination, 4.0, target_speed=ts[si], timer=0.0)
+            if self.cfg.action_type == 1:  # vehicle_class = Vehicle / BicycleVehicle: plan_route_to raises
+                idx = self._append(e, x, y, heading, speed_limit, KIND_VEHICLE, destination, 4.0, target_speed=0.0, timer=0.0)
+                self.a["route_len"][e, idx] = 0  # AttributeError -> no route, no speed index (:309-315)
+                self.a["lat_speed"][e, idx] = self.a["yaw_rate"][e, idx] = 0.0
+                si = -1
+            else:
+                self._append(e, x, y, heading, speed_limit, KIND_MDP, destination, 4.0, target_speed=ts[si], timer=0.0)
             if self.A > 1:
                 self.a["speed_index"][e, ego_id] = si
             else:
                 self.a["speed_index"][e] = si
             # prevent early collisions: drop the TRAFFIC within 20 m of this controlled vehicle (:317-323)
             n = int(self.a["count"][e])
-            keep = [v for v in range(n) if self.a["kind"][e, v] == KIND_MDP or not (
+            keep = [v for v in range(n) if self.a["kind"][e, v] in (KIND_MDP, KIND_VEHICLE) or not (
                 np.linalg.norm(np.array([self.a["x"][e, v] - x, self.a["y"][e, v] - y])) < 20)]
             for k in self.a:
                 if k in ("speed_index", "time", "count", "road_steps"):

@@ -53,6 +53,7 @@ ENV_CLASSES = {
     "intersection-v0": ("highway_env.envs.intersection_env", "IntersectionEnv"),
     "roundabout-v0": ("highway_env.envs.roundabout_env", "RoundaboutEnv"),
     "roundabout-v1": ("highway_env.envs.roundabout_env", "ConnectedLaneRoundaboutEnv"),
+    "intersection-v1": ("highway_env.envs.intersection_env", "ContinuousIntersectionEnv"),
     "intersection-v2": ("highway_env.envs.intersection_env", "ConnectedLaneIntersectionEnv"),
     "intersection-multi-agent-v0": ("highway_env.envs.intersection_env", "MultiAgentIntersectionEnv"),
     "two-way-v0": ("highway_env.envs.two_way_env", "TwoWayEnv"),
@@ -209,7 +210,12 @@ def dump_state(env, pad: int = 0) -> dict:
     if hasattr(env.road, "steps"):  # RegulatedRoad (road/regulation.py)
         d["road_steps"] = np.int64(env.road.steps)
         d["is_yielding"] = np.array([bool(getattr(v, "is_yielding", False)) for v in vs], dtype=np.bool_)
-        d["kind"] = np.array([1 if v in env.controlled_vehicles else 0 for v in vs], dtype=np.int32)
+        # 1 MDPVehicle, 2 plain Vehicle / BicycleVehicle (ContinuousAction ego), 0 traffic
+        d["kind"] = np.array([(1 if hasattr(v, "speed_index") else 2) if v in env.controlled_vehicles else 0
+                              for v in vs], dtype=np.int32)
+        if any(hasattr(v, "lateral_speed") for v in vs):  # BicycleVehicle (vehicle/dynamics.py:52-53)
+            d["lat_speed"] = np.array([float(getattr(v, "lateral_speed", 0.0)) for v in vs], dtype=np.float64)
+            d["yaw_rate"] = np.array([float(getattr(v, "yaw_rate", 0.0)) for v in vs], dtype=np.float64)
     if objects and "kind" not in d:
         d["kind"] = np.array([3 if v in objects else (1 if v in env.controlled_vehicles else 0) for v in vs], dtype=np.int32)
         d["is_yielding"] = np.zeros(n, dtype=np.bool_)

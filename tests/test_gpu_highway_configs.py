@@ -102,3 +102,32 @@ def test_get_available_actions_on_device_state():
     lane, si = sd["lane"][:, 0], sd["speed_index"]
     assert np.array_equal(m[:, 0], lane > 0) and np.array_equal(m[:, 2], lane < 2)
     assert np.array_equal(m[:, 3], si < 2) and np.array_equal(m[:, 4], si > 0) and (si == 2).any()
+
+
+def test_single_env_facade_matches_the_reference_episode():
+    """make_single: gymnasium.Env-shaped returns (numpy obs, python float / bool, info of python scalars incl.
+    info["rewards"]); reset(seed=s) + the golden actions reproduce the reference's episode for seed s."""
+    import highwayenv_b200 as hb
+    from parity_utils import load_golden
+
+    g = load_golden("highway_fast_v20")
+    env = hb.make_single("highway-fast-v0")
+    seed = int(g["seeds"][1])
+    obs, info = env.reset(seed=seed)
+    assert isinstance(obs, np.ndarray) and obs.shape == (5, 5) and obs.dtype == np.float32
+    assert np.max(np.abs(obs - g["obs"][1, 0])) <= 1e-6
+    assert set(info) >= {"speed", "crashed"}
+    for t in range(8):
+        obs, reward, terminated, truncated, info = env.step(int(g["actions"][1, t]))
+        assert isinstance(reward, float) and isinstance(terminated, bool) and isinstance(truncated, bool)
+        assert abs(reward - g["reward"][1, t]) <= 1e-6 and terminated == bool(g["terminated"][1, t])
+        assert np.max(np.abs(obs - g["obs"][1, t + 1])) <= 1e-5
+        assert set(info["rewards"]) == {"collision_reward", "right_lane_reward", "high_speed_reward", "on_road_reward"}
+        assert isinstance(info["speed"], float) and isinstance(info["crashed"], bool)
+        if terminated or truncated:
+            break
+    assert env.action_space.n == 5 and 1 in env.get_available_actions()
+    env2 = hb.make_single("intersection-v0")
+    o, _ = env2.reset(seed=3)
+    o, r, te, tr, info = env2.step(1)
+    assert o.shape == (15, 7) and isinstance(r, float) and "rewards" in info

@@ -1,0 +1,139 @@
+"""GPU parity of intersection-v1 (ContinuousAction + the dynamical BicycleVehicle + 8-column Kinematics) and of
+intersection-v0 with a kinematic ContinuousAction / DiscreteAction ego, through the C ABI: device reset against the
+reference (incl. the numpy stream), every step teacher-forced against golden rollouts of the unmodified reference
+(state incl. lateral_speed / yaw_rate, reward, flags, observation, generator words), free-running against the oracle."""
+import numpy as np
+import pytest
+
+import net_oracle as no
+from parity_utils import FLOAT_TOL, load_golden
+from test_gpu_intersection_parity import make_env, oracle_view, to_sd
+from test_net_oracle_golden import compare_inter, inter_state
+
+pytestmark = pytest.mark.gpu
+CASES = ["intersection_v1", "intersection_continuous"]
+V = 32
+
+
+def to_sd_c(states, rng_words=None):
+    sd = to_sd(states, rng_words)
+    live = np.stack([np.arange(V) < int(s["count"]) for s in states])
+    for k in ("lat_speed", "yaw_rate"):
+        sd[k] = np.where(live, np.nan_to_num(np.stack([s[k] for s in states])), 0.0) if k in states[0] else np.zeros(live.shape)
+    sd["speed_index"] = np.array([max(int(np.ravel(s["speed_index"]).max()), -1) for s in states], dtype=np.int32)
+    return sd
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_device_reset_matches_reference(name):
+    g = load_golden(name)
+    S = len(g["seeds"])
+    env = make_env(g["config"], S, autoreset_mode="Disabled")
+    obs, _ = env.reset(seed=[int(s) for s in g["seeds"]])
+    sd = env.state_dict()
+    for i in range(S):
+        compare_inter(inter_state(g, i, 0), oracle_view(sd), i, f"{name} reset#{i}", tol=1e-7)
+        assert np.array_equal(sd["rng"][:, i], g["rng_words"][i, 0]), i
+    assert np.max(np.abs(obs.cpu().numpy() - g["obs"][:, 0])) <= 1e-6
+    assert tuple(env.single_action_space.shape) == (2,)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_teacher_forced_vs_reference(name):
+    g = load_golden(name)
+    S, T = g["actions"].shape[:2]
+    env = make_env(g["config"], S, autoreset_mode="Disabled")
+    env.reset(seed=0)
+    for t in range(T):
+        env.load_state_dict(to_sd_c([inter_state(g, i, t) for i in range(S)], g["rng_words"][:, t]))
+        obs, rew, term, trunc, _ = env.step(g["actions"][:, t].astype(np.float32))
+        sd = env.state_dict()
+        obs, rew, term, trunc = obs.cpu().numpy(), rew.cpu().numpy(), term.cpu().numpy(), trunc.cpu().numpy()
+        for i in range(S):
+            ctx = f"{name} #{i} t={t}"
+            st1 = inter_state(g, i, t + 1)
+            compare_inter(st1, oracle_view(sd), i, ctx, tol=1e-7)
+            if "lat_speed" in st1:
+                n = int(st1["count"])
+                for k in ("lat_speed", "yaw_rate"):
+                    assert np.max(np.abs(np.nan_to_num(st1[k][:n]) - sd[k][i][:n])) <= 1e-7, (ctx, k)
+            assert abs(rew[i] - g["reward"][i, t]) <= 1e-9, ctx
+            assert bool(term[i]) == bool(g["terminated"][i, t]) and bool(trunc[i]) == bool(g["truncated"][i, t]), ctx
+            assert np.max(np.abs(obs[i] - g["obs"][i, t + 1])) <= 1e-6, ctx
+            assert np.array_equal(sd["rng"][:, i], g["rng_words"][i, t + 1]), ctx
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_free_running_vs_oracle_and_autoreset(name):
+    g = load_golden(name)
+    cfg = g["config"]
+    n = 64
+    ob = no.IntersectionOracle(no.graph_from_arrays(g), no.cfg_from_dict(cfg), n, g, cfg)
+    env = make_env(cfg, n, autoreset_mode="Disabled")
+    env.reset(seed=66000)
+    sd = env.state_dict()
+    for k in ob.a:
+        if k in sd:
+            ob.a[k][...] = sd[k].reshape(ob.a[k].shape)
+    for e in range(n):
+        ob.set_rng_words(e, sd["rng"][:, e])
+    rng = np.random.default_rng(17)
+    alive = np.ones(n, dtype=bool)
+    tracking = np.ones(n, dtype=bool)
+    compared = 0
+    for t in range(int(cfg["duration"]) + 1):
+        act = rng.uniform(-1, 1, size=(n, 2)).astype(np.float32)
+        o_obs, o_rew, o_term, o_trunc = ob.step(act)
+        obs, rew, term, trunc, _ = env.step(act)
+        sd = env.state_dict()
+        live = np.arange(V)[None, :] < ob.a["count"][:, None]
+        tracking &= ~(live & ~ob.a["crashed"].astype(bool) & (np.abs(ob.a["speed"]) < 1.0)).any(axis=1)
+        m = alive & tracking
+        assert np.array_equal(sd["count"][m], ob.a["count"][m]), t
+        lm = live & m[:, None]
+        # the BicycleVehicle's tyre model is stiff (friction 15, 15 Hz RK4): free-running, last-ulp libm differences grow
+        # by about a decade per policy step; one step from a common state (teacher-forced, above) agrees to 1e-7
+        tol = 1e-3 if name == "intersection_v1" else FLOAT_TOL
+        for k in ("x", "y", "heading", "speed", "lat_speed", "yaw_rate"):
+            assert float(np.max(np.abs(np.where(lm, sd[k] - ob.a[k], 0.0)))) <= tol, (name, t, k)
+        for k in ("lane", "crashed", "kind", "is_yielding"):
+            assert np.array_equal(np.where(lm, sd[k], 0).astype(np.int32), np.where(lm, ob.a[k], 0).astype(np.int32)), (t, k)
+        for e in np.nonzero(m)[0]:
+            assert np.array_equal(sd["rng"][:, e], ob.rng_words(e)), (t, e)
+        assert np.max(np.abs(rew.cpu().numpy() - o_rew)[m], initial=0.0) <= (1e-3 if name == "intersection_v1" else 1e-6)
+        assert np.array_equal(term.cpu().numpy()[m], o_term.astype(bool)[m])
+        assert np.max(np.abs(obs.cpu().numpy().reshape(n, -1) - o_obs.reshape(n, -1))[m], initial=0.0) <= (1e-3 if name == "intersection_v1" else 1e-4)
+        compared += int(m.sum())
+        alive &= ~(o_term.astype(bool) | o_trunc.astype(bool))
+        if not alive.any():
+            break
+    assert compared >= n  # random steering leaves the road / crashes within a few steps; every compared step matched
+    env = make_env(cfg, 64)  # SameStep autoreset on the device
+    env.reset(seed=4)
+    resets = 0
+    for t in range(20):
+        _, _, term, trunc, info = env.step(rng.uniform(-1, 1, size=(64, 2)).astype(np.float32))
+        done = (term | trunc).cpu().numpy()
+        resets += int(done.sum())
+        assert np.all(env.state_dict()["time"][done] == 0)
+    assert resets >= 32
+
+
+def test_discrete_action_on_intersection_equals_its_continuous_table():
+    """DiscreteAction (action.py:165-196) = an index into the product grid, then ContinuousAction.act"""
+    import highwayenv_b200 as hb
+
+    cfg = {"action": {"type": "DiscreteAction", "longitudinal": True, "lateral": True, "actions_per_axis": 3}}
+    cfc = {"action": {"type": "ContinuousAction", "longitudinal": True, "lateral": True}}
+    a = hb.make("intersection-v0", num_envs=32, config=cfg, autoreset_mode="Disabled")
+    b = hb.make("intersection-v0", num_envs=32, config=cfc, autoreset_mode="Disabled")
+    a.reset(seed=1)
+    b.reset(seed=1)
+    assert a.single_action_space.n == 9
+    rng = np.random.default_rng(0)
+    table = a.action_type.table
+    for t in range(6):
+        idx = rng.integers(0, 9, size=32)
+        oa = a.step(idx)[0].cpu().numpy()
+        ob_ = b.step(table[idx])[0].cpu().numpy()
+        assert np.array_equal(oa, ob_), t
