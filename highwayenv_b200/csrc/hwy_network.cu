@@ -18,6 +18,7 @@
 //
 // Reference paths are relative to /root/reference/highway_env.
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include <cuda_runtime.h>
@@ -399,6 +400,10 @@ __device__ __forceinline__ void closest_lane_group(const GraphShared& g, EnvStag
         bl = st.lane[i];
         bd = lane_distance_with_heading(g.lanes[bl], x, y, h, bs, blat);
     }
+    // (this barrier and the one that ends the function are not needed for memory ordering — n_cand could be re-armed in
+    // the reduce phase and nothing after the function reads another vehicle's lane before the next barrier — but removing
+    // them cost 10-25 %: the block-wide barriers keep the block's warps on the same instruction-cache lines, measured
+    // again in round 2, profiles/r2_kernel_history.md)
     phase_sync<G>();
     if (active) {
         const int hint = bl;
@@ -1237,6 +1242,7 @@ __device__ __forceinline__ void load_env(const HwyNetParams& P, const GraphShare
     st.route_len[i] = S.route_len[slot];
     const int count = S.count ? S.count[e] : P.n_vehicles;
     if (i == 0) {
+        st.n_cand = 0;
         st.count = count;
         st.speed_index = S.speed_index[e];
         st.road_steps = S.road_steps ? S.road_steps[e] : 0;
@@ -1763,7 +1769,9 @@ intersection_reset_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGr
     GraphShared& g = *reinterpret_cast<GraphShared*>(smem_raw);
     EnvStage<G, REG>* stages =
         reinterpret_cast<EnvStage<G, REG>*>(smem_raw + ((sizeof(GraphShared) + 15) & ~size_t(15)));
-    constexpr int kEnvs = kBlockThreads / G;
+    // The reset is a long dependent chain per env (9 spawn attempts, 45 warm-up substeps, ...) for the few envs that
+    // ended (~8 % per step): small blocks (kResetThreads) spread them over all SMs and shorten the lock-step waits.
+    const int kEnvs = blockDim.x / G;
     const int n_sel = list[0];
     if (blockIdx.x * kEnvs >= n_sel) return;  // uniform per block
     stage_graph(g, graph);
@@ -1782,6 +1790,7 @@ intersection_reset_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGr
     st.own_s[i] = st.own_lat[i] = 0.0;
     Pcg64 rng;
     if (i == 0) {
+        st.n_cand = 0;
         st.count = 0;
         st.ego = 0;
         st.speed_index = 0;
@@ -2302,6 +2311,14 @@ int configure_smem(K kernel, size_t bytes) {
     if (err != cudaSuccess) return fail("cudaFuncSetAttribute: %s", cudaGetErrorString(err));
     return 0;
 }
+int reset_threads() {  // HWYB200_RESET_THREADS overrides (64 / 128 / 256)
+    if (const char* e = getenv("HWYB200_RESET_THREADS")) {
+        int v = atoi(e);
+        if (v == 64 || v == 128 || v == 256) return v;
+    }
+    return 64;
+}
+const int kResetThreads = reset_threads();
 int blocks_for(int n_envs, int g) {
     int per = hwynet::kBlockThreads / g;
     return (n_envs + per - 1) / per;
@@ -2437,16 +2454,18 @@ int hwy_intersection_reset(const HwyNetParams* p, const HwyNetGraph* graph, cons
                         cudaMemcpyDeviceToDevice, st);
     if (check_launch("compact_envs_kernel")) return 1;
     if (spawn->initial_vehicle_count + 1 <= 16) {  // n-1 draws + challenger + controlled vehicle fit 16 slots
-        const size_t smem = net_smem_bytes<16, true>();
+        const int per = kResetThreads / 16;
+        const size_t smem = ((sizeof(hwynet::GraphShared) + 15) & ~size_t(15)) + per * sizeof(hwynet::EnvStage<16, true>);
         if (configure_smem(hwynet::intersection_reset_kernel<16, true>, smem)) return 1;
         hwynet::intersection_reset_kernel<16, true>
-            <<<blocks_for(s->n_envs, 16), hwynet::kBlockThreads, smem, st>>>(*p, graph, *s, *spawn, spawn->scratch, obs);
+            <<<(s->n_envs + per - 1) / per, kResetThreads, smem, st>>>(*p, graph, *s, *spawn, spawn->scratch, obs);
     } else {
-        const size_t smem = net_smem_bytes<HWY_NET_GROUP_LARGE, true>();
+        const int per = kResetThreads / HWY_NET_GROUP_LARGE;
+        const size_t smem = ((sizeof(hwynet::GraphShared) + 15) & ~size_t(15)) +
+                            per * sizeof(hwynet::EnvStage<HWY_NET_GROUP_LARGE, true>);
         if (configure_smem(hwynet::intersection_reset_kernel<HWY_NET_GROUP_LARGE, true>, smem)) return 1;
         hwynet::intersection_reset_kernel<HWY_NET_GROUP_LARGE, true>
-            <<<blocks_for(s->n_envs, HWY_NET_GROUP_LARGE), hwynet::kBlockThreads, smem, st>>>(*p, graph, *s, *spawn,
-                                                                                             spawn->scratch, obs);
+            <<<(s->n_envs + per - 1) / per, kResetThreads, smem, st>>>(*p, graph, *s, *spawn, spawn->scratch, obs);
     }
     return check_launch("intersection_reset_kernel");
 }

@@ -28,7 +28,7 @@ if [ "$WHAT" = all ] || [ "$WHAT" = ncu ]; then
       python tools/ncu_target.py $cfg > gpurun_out/${TAG}_${cfg}_ncu.log 2>&1
     echo "ncu $cfg rc=$?"
     ncu -i /tmp/${TAG}_${cfg}.ncu-rep --page raw --csv > gpurun_out/${TAG}_${cfg}_raw.csv 2>/dev/null
-    ncu -i /tmp/${TAG}_${cfg}.ncu-rep --page source --csv --print-source cuda,sass -k regex:step_kernel -c 1 \
+    ncu -i /tmp/${TAG}_${cfg}.ncu-rep --page source --csv --print-source cuda,sass -k regex:step_kernel -c 2 \
       > /tmp/${TAG}_${cfg}_src.csv 2>/dev/null
     python tools/ncu_lines.py /tmp/${TAG}_${cfg}_src.csv 60 > gpurun_out/${TAG}_${cfg}_lines.txt 2>&1
   done
