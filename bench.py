@@ -87,58 +87,118 @@ def workload_name(key: str) -> str:
 
 # ------------------------------------------------------------------ clocks
 class ClockSampler:
-    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+    """SM clock / throttle-reason sampling DURING the timed region (B200_PROFILING.md clocks line).
 
+    The headline's timed region is tens of milliseconds, shorter than one `nvidia-smi -lms` period, so the samples come
+    from NVML directly (the library nvidia-smi reads, via nvidia-ml-py) on a thread polling every `period` seconds; the
+    NVML calls release the GIL.  Without NVML bindings: one nvidia-smi query loop, which needs a region of >= 0.2 s."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int):
-        self.gpu_index = gpu_index
-        self.rows = []
-        self.proc = None
+    def __init__(self, gpu_index: int, uuid: str = None, period: float = 0.004):
+        self.gpu_index, self.uuid, self.period = gpu_index, uuid, period
+        self.sm, self.mx, self.reasons, self.power = [], [], set(), []
+        self.source, self.nvml, self.handle, self.proc, self.thread = None, None, None, None, None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            try:  # the CUDA ordinal is not the NVML index under CUDA_VISIBLE_DEVICES: prefer the UUID
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.nvml, self.source = pynvml, "nvml"
+            self.mx.append(float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)))
+        except Exception:
+            self.nvml = None
+
+    def _poll_once(self):
+        n, h = self.nvml, self.handle
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)))
+        try:
+            get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = int(get(h))
+            for bit, name in self.REASONS.items():
+                if bits & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+        try:
+            self.power.append(n.nvmlDeviceGetPowerUsage(h) / 1000.0)
+        except Exception:
+            pass
+
+    def _poll(self):
+        while not self._stop.is_set():
+            try:
+                self._poll_once()
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def _read_smi(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.proc.stdout:
+            r = [c.strip() for c in line.split(",")]
+            try:
+                self.sm.append(float(r[1]))
+                self.mx.append(float(r[2]))
+                for k, nme in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        self.reasons.add(nme)
+            except Exception:
+                continue
 
     def start(self):
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.gpu_index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.source = "nvidia-smi"
+            self.thread = threading.Thread(target=self._read_smi, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        if self.nvml is not None:
             try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-                for k, nme in enumerate(names):
-                    if r[5 + k].lower().startswith("active"):
-                        reasons.add(nme)
+                self._poll_once()  # one more inside the region's closing synchronize window
             except Exception:
-                continue
-        return {
-            "sm_mhz": statistics.median(sm) if sm else None,
-            "sm_max_mhz": max(mx) if mx else None,
-            "reasons": sorted(reasons),
-            "samples": len(sm),
+                pass
+            self._stop.set()
+            if self.thread:
+                self.thread.join(timeout=1)
+        elif self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML bindings and no nvidia-smi"], "samples": 0}
+        out = {
+            "sm_mhz": statistics.median(self.sm) if self.sm else None,
+            "sm_min_mhz": min(self.sm) if self.sm else None,
+            "sm_max_mhz": max(self.mx) if self.mx else None,
+            "reasons": sorted(self.reasons),
+            "samples": len(self.sm),
+            "source": self.source,
         }
+        if self.power:
+            out["power_w"] = statistics.median(self.power)
+        return out
 
 
 # ------------------------------------------------------------------ CPU arm (C oracle port, pinned processes)
@@ -430,7 +490,13 @@ def measure_config(key, E, K, W, rank, world, dev, ctx, do_e2e=True, gather=Fals
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K)]
     env._kernel_events = []
     launches0 = lib.hwy_launch_count()
-    sampler = ClockSampler(dev.index or 0) if (rank == 0 and key == HEADLINE) else None
+    sampler = None
+    if rank == 0 and key == HEADLINE:
+        try:
+            uuid = "GPU-" + str(torch.cuda.get_device_properties(dev).uuid)
+        except Exception:
+            uuid = None
+        sampler = ClockSampler(dev.index or 0, uuid)
     if sampler:
         sampler.start()
     barrier()

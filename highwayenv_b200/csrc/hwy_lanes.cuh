@@ -20,35 +20,58 @@ struct GraphShared {
 
 // ------------------------------------------------------------------ lanes (road/lane.py)
 // local_coordinates: StraightLane :205-209, SineLane :285-289, CircularLane :351-358
-// `gate`: callers that go on to test on_lane(.., margin) (lane.py:100-118) pass width/2 + margin; the lateral
-// offset is computed first and the longitudinal one (an atan2 on a CircularLane) only when |lat| <= gate.
-// Returns false (s untouched) when the lateral test already fails.  gate = +inf: plain local_coordinates.
-static __device__ __noinline__ bool lane_local_gated(const HwyNetLane& L, double x, double y, double gate, double& s,
-                                              double& lat) {
+static __device__ __noinline__ void lane_local(const HwyNetLane& L, double x, double y, double& s, double& lat) {
     if (L.type == HWY_LANE_CIRCULAR) {
         double ddx = x - L.cx, ddy = y - L.cy;
         double r = norm2(ddx, ddy);
         lat = L.direction * (L.radius - r);
-        if (!(fabs(lat) <= gate)) return false;
         double phi = atan2(ddy, ddx);
         phi = L.start_phase + wrap_to_pi(phi - L.start_phase);
         s = L.direction * (phi - L.start_phase) * L.radius;
-        return true;
+        return;
     }
     double ddx = x - L.sx, ddy = y - L.sy;
     double la = dot2(ddx, ddy, L.lx, L.ly);
-    if (L.type != HWY_LANE_SINE && !(fabs(la) <= gate)) {
-        lat = la;
-        return false;
-    }
     double lon = dot2(ddx, ddy, L.dx, L.dy);
     if (L.type == HWY_LANE_SINE) la = la - L.amplitude * m_sin(L.pulsation * lon + L.phase);
     s = lon;
     lat = la;
-    return fabs(la) <= gate;
 }
-__device__ __forceinline__ void lane_local(const HwyNetLane& L, double x, double y, double& s, double& lat) {
-    lane_local_gated(L, x, y, INFINITY, s, lat);
+// on_lane(position, margin = 1) pre-test for the neighbour search (road/road.py:483-547 -> lane.py:100-118): false only
+// when local_coordinates followed by on_lane CANNOT hold, decided without sqrt / atan2 / sin, so that the expensive
+// exact evaluation runs for the few real candidates only (and, gathered in a pending mask, converged across the warp).
+//   circular: |radius - r| <= gate compared on squares with a 1e-12 relative slack; and for arcs shorter than pi, a point
+//     outside the arc's angular sector (cross products against the end points' radial vectors, margin towards "inside")
+//     whose distance to the nearer end point exceeds gate + VEHICLE_LENGTH cannot have -LENGTH <= s < length + LENGTH:
+//     at an angular excess of at most LENGTH / radius beyond an end, |p - end| <= |r - radius| + chord <= gate + LENGTH.
+//     (`L` is the kernel's shared copy: stage_graph keeps the arc's end points in sx, sy, ex, ey.)
+//   sine: |lateral| >= |straight lateral| - |amplitude| (|A sin| <= |A| and rounding is monotone);
+//   straight / sine: the longitudinal test itself (s is the straight longitudinal on both).
+__device__ __forceinline__ bool lane_maybe_on(const HwyNetLane& L, double x, double y) {
+    const double gate = L.width / 2 + 1.0;
+    if (L.type == HWY_LANE_CIRCULAR) {
+        const double wx = x - L.cx, wy = y - L.cy;
+        const double r2 = dot2(wx, wy, wx, wy);
+        const double hi = L.radius + gate, lo = L.radius - gate;
+        if (r2 > hi * hi * (1.0 + 1e-12)) return false;
+        if (lo > 0.0 && r2 < lo * lo * (1.0 - 1e-12)) return false;
+        if (fabs(L.end_phase - L.start_phase) < 3.0) {
+            const double usx = L.sx - L.cx, usy = L.sy - L.cy, uex = L.ex - L.cx, uey = L.ey - L.cy;
+            const double c_s = L.direction * (usx * wy - usy * wx);  // > 0: past the start point in travel direction
+            const double c_e = L.direction * (wx * uey - wy * uex);  // > 0: before the end point
+            if (c_s < -1e-6 || c_e < -1e-6) {
+                const double ax = x - L.sx, ay = y - L.sy, bx = x - L.ex, by = y - L.ey;
+                const double reach = gate + kLaneVehLength + 1e-6;
+                if (fmin(dot2(ax, ay, ax, ay), dot2(bx, by, bx, by)) > reach * reach) return false;
+            }
+        }
+        return true;
+    }
+    const double ddx = x - L.sx, ddy = y - L.sy;
+    const double la = fabs(dot2(ddx, ddy, L.lx, L.ly));
+    if (L.type == HWY_LANE_SINE ? la - fabs(L.amplitude) > gate : !(la <= gate)) return false;
+    const double lon = dot2(ddx, ddy, L.dx, L.dy);
+    return -kLaneVehLength <= lon && lon < L.length + kLaneVehLength;
 }
 // position: StraightLane :192-197, SineLane :268-273, CircularLane :338-342
 static __device__ __noinline__ void lane_position(const HwyNetLane& L, double s, double lat, double& x, double& y) {
@@ -131,7 +154,7 @@ __device__ __forceinline__ void stage_graph(GraphShared& gs, const HwyNetGraph* 
     for (int k = threadIdx.x; k < (int)(sizeof(HwyNetGraph) / sizeof(int)); k += blockDim.x) dst[k] = src[k];
     __syncthreads();
     // CircularLane rows do not use the StraightLane fields: the shared copy keeps the arc's two end points there
-    // (position(0, 0) and position(length, 0)), for the closest-lane search's lower bound (closest_lane_lower_bound)
+    // (position(0, 0) and position(length, 0)), for the closest-lane pruning and the neighbour pre-test (closest_lane_prunable, lane_maybe_on)
     for (int l = threadIdx.x; l < gs.n_lanes; l += blockDim.x) {
         HwyNetLane& L = gs.lanes[l];
         if (L.type != HWY_LANE_CIRCULAR) continue;
@@ -146,46 +169,54 @@ __device__ __forceinline__ void stage_graph(GraphShared& gs, const HwyNetGraph* 
     __syncthreads();
 }
 
-// A lower bound of lane.distance_with_heading(position, heading) (road/lane.py:132-143) that needs no atan2 / sin:
+// get_closest_lane_index pruning (road/road.py:55-71): true when lane.distance_with_heading(position, heading)
+// (road/lane.py:132-143) of L certainly exceeds `bd` (the distance to the lane the vehicle was on), decided without
+// sqrt / atan2 / sin:
 //   d = |lateral| + max(s - length, 0) + max(-s, 0) + |angle|   (all terms >= 0; fp addition of non-negative terms is
 //   monotone, so dropping terms or replacing one by something smaller can only lower the sum).
 // Straight: the first three terms themselves (exact).  Sine: |lateral| >= |straight lateral| - |amplitude| (1e-9 m
-// covers the rounding of that subtraction), same longitudinal terms.  Circular: |lateral| = |radius - r|; and when the
-// point lies outside the arc's angular sector (arcs shorter than pi; decided with cross products against the end
+// covers the rounding of that subtraction), same longitudinal terms.  Circular: |lateral| = |radius - r| > bd, compared
+// on squares (r^2 against (radius +- bd)^2 with a 1e-12 relative slack, far above the rounding of either side); and when
+// the point lies outside the arc's angular sector (arcs shorter than pi; decided with cross products against the end
 // points' radial vectors, with a margin that can only misjudge towards "inside"), |lateral| + the arc length beyond the
 // violated end >= |p - q| + chord(q, end) >= |p - end| for its radial projection q, so the distance to the NEARER end
-// point (minus 1e-9 m for rounding) bounds d from below whichever end the reference's phase wrap picks.
-// `cache`: (cx, cy, r) of the last circular lane evaluated — the ring arcs of a roundabout share one centre.
+// point bounds d from below whichever end the reference's phase wrap picks (squares again, 1e-9 m + 1e-12 slack).
+// A lane that is not pruned is evaluated exactly, so slack only costs time.
+// `cache`: (cx, cy, r^2) of the last circular lane evaluated — the ring arcs of a roundabout share one centre.
 struct CircleCache {
-    double cx, cy, r;
+    double cx, cy, r2;
     bool valid;
 };
-__device__ __forceinline__ double closest_lane_lower_bound(const HwyNetLane& L, double x, double y, CircleCache& cache) {
+__device__ __forceinline__ bool closest_lane_prunable(const HwyNetLane& L, double x, double y, double bd,
+                                                      CircleCache& cache) {
     if (L.type == HWY_LANE_CIRCULAR) {
         const double wx = x - L.cx, wy = y - L.cy;
         if (!(cache.valid && cache.cx == L.cx && cache.cy == L.cy)) {
             cache.cx = L.cx;
             cache.cy = L.cy;
-            cache.r = norm2(wx, wy);
+            cache.r2 = dot2(wx, wy, wx, wy);
             cache.valid = true;
         }
-        double lb = fabs(L.direction * (L.radius - cache.r));
+        const double hi = L.radius + bd, lo = L.radius - bd;
+        if (cache.r2 > hi * hi * (1.0 + 1e-12)) return true;
+        if (lo > 0.0 && cache.r2 < lo * lo * (1.0 - 1e-12)) return true;
         if (fabs(L.end_phase - L.start_phase) < 3.0) {
             const double usx = L.sx - L.cx, usy = L.sy - L.cy, uex = L.ex - L.cx, uey = L.ey - L.cy;
             const double c_s = L.direction * (usx * wy - usy * wx);  // > 0: past the start point in travel direction
             const double c_e = L.direction * (wx * uey - wy * uex);  // > 0: before the end point
             if (c_s < -1e-6 || c_e < -1e-6) {
-                const double ds = norm2(x - L.sx, y - L.sy), de = norm2(x - L.ex, y - L.ey);
-                lb = fmax(lb, fmin(ds, de) - 1e-9);
+                const double ax = x - L.sx, ay = y - L.sy, bx = x - L.ex, by = y - L.ey;
+                const double reach = bd + 1e-9;
+                if (fmin(dot2(ax, ay, ax, ay), dot2(bx, by, bx, by)) > reach * reach * (1.0 + 1e-12)) return true;
             }
         }
-        return lb;
+        return false;
     }
     const double ddx = x - L.sx, ddy = y - L.sy;
     double lat = fabs(dot2(ddx, ddy, L.lx, L.ly));
     if (L.type == HWY_LANE_SINE) lat = lat - fabs(L.amplitude) - 1e-9;
     const double lon = dot2(ddx, ddy, L.dx, L.dy);
-    return lat + fmax(lon - L.length, 0.0) + fmax(0.0 - lon, 0.0);
+    return lat + fmax(lon - L.length, 0.0) + fmax(0.0 - lon, 0.0) > bd;
 }
 
 }  // namespace hwynet

@@ -17,6 +17,7 @@
 // The lane table lives in HBM (HwyNetGraph) and is staged into shared memory once per block.  DESIGN.md 3.5-3.9.
 //
 // Reference paths are relative to /root/reference/highway_env.
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
@@ -33,7 +34,15 @@ namespace hwynet {
 using namespace hwy;
 
 constexpr int R = HWY_NET_MAX_ROUTE;
-constexpr int kBlockThreads = 256;
+constexpr int kBlockThreads = 256;  // observe / substeps / debug kernels
+// The step kernels run ONE block per SM (128 registers x 512 threads): one instruction stream per SM.  The step body is
+// ~110 KB of SASS against a 32 KB instruction cache, and two co-resident blocks in different phases evict each other:
+// 512 x 1 measured +12-14 % over 256 x 2 (same warps per SM), 128 x 4 -20 % (profiles/r2_kernel_history.md).  The
+// launch uses fewer threads per block when that spreads the envs over all SMs (step_plan).
+#ifndef HWY_NET_STEP_THREADS
+#define HWY_NET_STEP_THREADS 512
+#endif
+constexpr int kStepThreads = HWY_NET_STEP_THREADS;
 constexpr int kPred = 11;  // np.arange(0.25, 3, 0.25) prediction points of RegulatedRoad.is_conflict_possible
 constexpr int kPredChunk = 4;  // horizon points staged in shared memory at a time
 
@@ -164,25 +173,43 @@ __device__ __noinline__ void neighbours(const GraphShared& g, const EnvStage<G, 
     const HwyNetLane& L = g.lanes[lane_idx];
     const double s = lane_idx == st.lane[veh] ? st.own_s[veh] : lane_s_of(L, st.x[veh], st.y[veh]);
     if (!connected) {  // same-segment search: one lane, no list
-        const double gate = L.width / 2 + 1.0;  // the lateral half of on_lane(margin=1)
         double s_front = 0, s_rear = 0;
         front = -1;
         rear = -1;
+        // The reference scans the vehicles in list order: the front neighbour is the smallest s_v >= s with ties going
+        // to the LATER vehicle (`<=`), the rear one the largest s_v < s with ties going to the EARLIER vehicle (`>`).
+        // Stated as an order on (s_v, index) the scan can be split: vehicles on the query lane use their cached
+        // coordinates at once; the others take the sqrt / atan2 / sin-free pre-test (lane_maybe_on) and only the
+        // survivors — gathered in a mask so that the lanes of a warp evaluate theirs together — get exact coordinates.
+        unsigned pending = 0;
         for (int v = 0; v < V; ++v) {
             if (v == veh) continue;
-            double s_v, lat_v;
-            if (st.lane[v] == lane_idx) {
-                s_v = st.own_s[v];
-                lat_v = st.own_lat[v];
-            } else if (!lane_local_gated(L, st.x[v], st.y[v], gate, s_v, lat_v)) {
+            if (st.lane[v] != lane_idx) {
+                if (lane_maybe_on(L, st.x[v], st.y[v])) pending |= 1u << v;
                 continue;
             }
-            if (!lane_on(L, s_v, lat_v, 1.0)) continue;
-            if (s <= s_v && (front < 0 || s_v <= s_front)) {
+            const double s_v = st.own_s[v];
+            if (!lane_on(L, s_v, st.own_lat[v], 1.0)) continue;
+            if (s <= s_v && (front < 0 || s_v < s_front || (s_v == s_front && v > front))) {
                 s_front = s_v;
                 front = v;
             }
-            if (s_v < s && (rear < 0 || s_v > s_rear)) {
+            if (s_v < s && (rear < 0 || s_v > s_rear || (s_v == s_rear && v < rear))) {
+                s_rear = s_v;
+                rear = v;
+            }
+        }
+        while (pending) {
+            const int v = __ffs(pending) - 1;
+            pending &= pending - 1;
+            double s_v, lat_v;
+            lane_local(L, st.x[v], st.y[v], s_v, lat_v);
+            if (!lane_on(L, s_v, lat_v, 1.0)) continue;
+            if (s <= s_v && (front < 0 || s_v < s_front || (s_v == s_front && v > front))) {
+                s_front = s_v;
+                front = v;
+            }
+            if (s_v < s && (rear < 0 || s_v > s_rear || (s_v == s_rear && v < rear))) {
                 s_rear = s_v;
                 rear = v;
             }
@@ -217,8 +244,9 @@ __device__ __noinline__ void neighbours(const GraphShared& g, const EnvStage<G, 
             if (st.lane[v] == sl) {
                 s_v = st.own_s[v];
                 lat_v = st.own_lat[v];
-            } else if (!lane_local_gated(SL, st.x[v], st.y[v], SL.width / 2 + 1.0, s_v, lat_v)) {
-                continue;  // the lateral half of on_lane(margin=1) already fails
+            } else {
+                if (!lane_maybe_on(SL, st.x[v], st.y[v])) continue;  // on_lane(margin=1) cannot hold
+                lane_local(SL, st.x[v], st.y[v], s_v, lat_v);
             }
             if (!lane_on(SL, s_v, lat_v, 1.0)) continue;
             if (k > 0) s_v += k <= n_next ? L.length : -SL.length;
@@ -411,8 +439,7 @@ __device__ __forceinline__ void closest_lane_group(const GraphShared& g, EnvStag
         for (int l = 0; l < g.n_lanes; ++l) {
             if (l == hint) continue;
             const HwyNetLane& L = g.lanes[l];
-            const double lb = closest_lane_lower_bound(L, x, y, cc);
-            if (lb > bd) continue;
+            if (closest_lane_prunable(L, x, y, bd, cc)) continue;
             int slot = atomicAdd(&st.n_cand, 1);
             if (slot < K) {
                 st.o.cand.vl[slot] = (unsigned short)((i << 8) | l);
@@ -1202,18 +1229,30 @@ __device__ __forceinline__ void substep(const HwyNetParams& P, const GraphShared
     // Road objects (Obstacle: 2 x 2 m, kind 3) sit in the slots after the vehicles, so vehicle i meets its vehicle
     // partners first and the objects last, as in the reference; only vehicles call handle_collisions; against an
     // Obstacle the vehicle takes the WHOLE transition (vehicle/objects.py:104-107).
+    // The reference's sphere pre-check (vehicle/objects.py:122-126) first runs on squared distances with a 1e-9 m slack
+    // (no sqrt) and the partners that survive are gathered in a mask, so that the lanes of a warp run the exact pre-check
+    // and the separating-axis test together instead of one at a time.
     if (active) {
+        // RoadObject.diagonal = sqrt(LENGTH^2 + WIDTH^2) (objects.py:63): sqrt(29) and sqrt(8), correctly rounded
+        const double diag_v = 0x1.58a68a4a8d9f3p+2, diag_o = 0x1.6a09e667f3bcdp+1;
+        unsigned pending = 0;
         for (int j = 0; j < V; ++j) {
             if (j == i) continue;
-            int a = i < j ? i : j, b = i < j ? j : i;
+            const int a = i < j ? i : j, b = i < j ? j : i;
             if (st.kind[a] == HWY_KIND_OBSTACLE) continue;
+            const double reach = (diag_v + (st.kind[b] == HWY_KIND_OBSTACLE ? diag_o : diag_v)) / 2 + st.v[a] * dt + 1e-9;
+            const double dx = st.x[b] - st.x[a], dy = st.y[b] - st.y[a];
+            const bool far = reach <= 0.0 || dot2(dx, dy, dx, dy) > reach * reach * (1.0 + 1e-12);
+            if (!far) pending |= 1u << j;  // (a NaN distance stays pending, as it passes the reference's `>` test)
+        }
+        while (pending) {
+            const int j = __ffs(pending) - 1;
+            pending &= pending - 1;
+            const int a = i < j ? i : j, b = i < j ? j : i;
             const bool b_object = st.kind[b] == HWY_KIND_OBSTACLE;
             const double len_b = b_object ? 2.0 : kVehLength;
-            // RoadObject.diagonal = sqrt(LENGTH^2 + WIDTH^2) (objects.py:63): sqrt(29) and sqrt(8), correctly rounded
-            const double diag_a = 0x1.58a68a4a8d9f3p+2;
-            const double diag_b = b_object ? 0x1.6a09e667f3bcdp+1 : 0x1.58a68a4a8d9f3p+2;
-            double dist = norm2(st.x[b] - st.x[a], st.y[b] - st.y[a]);
-            if (dist > (diag_a + diag_b) / 2 + st.v[a] * dt) continue;
+            const double dist = norm2(st.x[b] - st.x[a], st.y[b] - st.y[a]);
+            if (dist > (diag_v + (b_object ? diag_o : diag_v)) / 2 + st.v[a] * dt) continue;
             Quad pa = make_polygon(st.x[a], st.y[a], st.c[a], st.s[a]);
             Quad pb = make_polygon(st.x[b], st.y[b], st.c[b], st.s[b], len_b);
             bool inter, will;
@@ -1379,7 +1418,7 @@ __device__ __forceinline__ void store_rng(uint64_t* rng, size_t n, int e, const 
 
 // ------------------------------------------------------------------ the step kernel
 template <int G, bool REG, bool PLAIN>
-__global__ void __launch_bounds__(kBlockThreads)
+__global__ void __launch_bounds__(kStepThreads, 1)
 network_step_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGraph* __restrict__ graph, const __grid_constant__ HwyNetState S,
                     const __grid_constant__ HwyIntersectionSpawn SP, const int32_t* __restrict__ action, float* __restrict__ obs,
                     double* __restrict__ reward, uint8_t* __restrict__ terminated,
@@ -1390,7 +1429,7 @@ network_step_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGraph* _
     GraphShared& g = *reinterpret_cast<GraphShared*>(smem_raw);
     EnvStage<G, REG>* stages =
         reinterpret_cast<EnvStage<G, REG>*>(smem_raw + ((sizeof(GraphShared) + 15) & ~size_t(15)));
-    constexpr int kEnvs = kBlockThreads / G;
+    const int kEnvs = blockDim.x / G;  // the launch sizes the block (step_plan)
     // with a work list (list[0] = how many, list[1..] = env ids) the grid is dense over the list and the
     // blocks past its end leave as a whole; partial blocks let the spare groups ride along on the last entry
     const int n_work = list ? list[0] : S.n_envs;
@@ -2324,24 +2363,74 @@ int blocks_for(int n_envs, int g) {
     return (n_envs + per - 1) / per;
 }
 
+// Block shape of a step launch: the fewest whole waves of one block per SM that cover n_envs, the envs spread evenly
+// over waves x SMs blocks (8 192 roundabout envs, 8 slots: 147 blocks of 56 envs = 448 threads instead of 128 blocks
+// of 64 envs on 148 SMs).  Work-list launches (16- / 32-slot intersection kernels) are planned for n_envs, the upper
+// bound of a list known only on the device; blocks past the list's end leave at once.
+struct StepPlan {
+    int threads, blocks, per;
+    size_t smem;
+};
+int sm_count() {
+    static std::atomic<int> cached[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    int n = cached[dev].load(std::memory_order_relaxed);
+    if (n == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev].store(n, std::memory_order_relaxed);
+    }
+    return n;
+}
+template <int G, bool REG>
+StepPlan step_plan(int n_envs) {
+    static const int forced = [] {  // HWYB200_STEP_THREADS: fixed block size (experiments)
+        const char* e = getenv("HWYB200_STEP_THREADS");
+        const int v = e ? atoi(e) : 0;
+        return (v >= 32 && v <= hwynet::kStepThreads && v % 32 == 0) ? v : 0;
+    }();
+    const int per_max = hwynet::kStepThreads / G, sms = sm_count();
+    int per = per_max;
+    if (forced) {
+        per = forced / G > 0 ? forced / G : 1;
+    } else {
+        const int waves = (n_envs + sms * per_max - 1) / (sms * per_max);
+        per = (n_envs + waves * sms - 1) / (waves * sms);
+    }
+    int threads = ((per * G + 31) / 32) * 32;
+    if (threads > hwynet::kStepThreads) threads = hwynet::kStepThreads;
+    per = threads / G;
+    StepPlan plan;
+    plan.threads = threads;
+    plan.per = per;
+    plan.blocks = (n_envs + per - 1) / per;
+    plan.smem = ((sizeof(hwynet::GraphShared) + 15) & ~size_t(15)) + (size_t)per * sizeof(hwynet::EnvStage<G, REG>);
+    return plan;
+}
+template <int G, bool REG>
+size_t step_smem_max() {
+    return ((sizeof(hwynet::GraphShared) + 15) & ~size_t(15)) +
+           (size_t)(hwynet::kStepThreads / G) * sizeof(hwynet::EnvStage<G, REG>);
+}
+
 template <int G, bool REG>
 int launch_step(const HwyNetParams* p, const HwyNetGraph* graph, const HwyIntersectionSpawn& sp, const HwyNetState* s,
                 const int32_t* action, float* obs, double* reward, uint8_t* terminated, uint8_t* truncated,
                 double* info_speed, uint8_t* info_crashed, cudaStream_t st, const int* list = nullptr,
                 double* agents_reward = nullptr, uint8_t* agents_terminated = nullptr) {
-    const size_t smem = net_smem_bytes<G, REG>();
+    const StepPlan plan = step_plan<G, REG>(s->n_envs);
     if constexpr (REG) {
         if (p->action_type == 1) {  // a ContinuousAction ego (plain Vehicle / BicycleVehicle): its own instantiation
-            if (configure_smem(hwynet::network_step_kernel<G, REG, true>, smem)) return 1;
-            hwynet::network_step_kernel<G, REG, true><<<blocks_for(s->n_envs, G), hwynet::kBlockThreads, smem, st>>>(
+            if (configure_smem(hwynet::network_step_kernel<G, REG, true>, step_smem_max<G, REG>())) return 1;
+            hwynet::network_step_kernel<G, REG, true><<<plan.blocks, plan.threads, plan.smem, st>>>(
                 *p, graph, *s, sp, action, obs, reward, terminated, truncated, info_speed, info_crashed, list,
                 agents_reward, agents_terminated);
             return check_launch("network_step_kernel");
         }
     }
     if (p->action_type == 1) return fail("%s", "ContinuousAction is implemented on the intersection family (32-slot state)");
-    if (configure_smem(hwynet::network_step_kernel<G, REG, false>, smem)) return 1;
-    hwynet::network_step_kernel<G, REG, false><<<blocks_for(s->n_envs, G), hwynet::kBlockThreads, smem, st>>>(
+    if (configure_smem(hwynet::network_step_kernel<G, REG, false>, step_smem_max<G, REG>())) return 1;
+    hwynet::network_step_kernel<G, REG, false><<<plan.blocks, plan.threads, plan.smem, st>>>(
         *p, graph, *s, sp, action, obs, reward, terminated, truncated, info_speed, info_crashed, list, agents_reward,
         agents_terminated);
     return check_launch("network_step_kernel");
