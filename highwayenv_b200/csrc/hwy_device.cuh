@@ -96,7 +96,7 @@ static __device__ __noinline__ double steering_sin_slip(const HwyStraightLane L,
     lane_local(L, x, y, lc_s, lc_lat);
     double lane_future_heading = L.heading;  // StraightLane.heading_at
     double lateral_speed_command = -kKpLateral * lc_lat;
-    double heading_command = m_asin(clipd(lateral_speed_command / not_zero(speed), -1.0, 1.0));
+    double heading_command = m_asin(clipd(div_finite(lateral_speed_command, not_zero(speed)), -1.0, 1.0));
     double heading_ref = lane_future_heading + clipd(heading_command, -kPi / 4, kPi / 4);
     double heading_rate_command = kKpHeading * wrap_to_pi(heading_ref - heading);
     return clipd(kVehLength / 2 / not_zero(speed) * heading_rate_command, -1.0, 1.0);

@@ -184,7 +184,7 @@ __device__ __forceinline__ double lane_distance(const HwyHighwayParams& P, const
 __device__ __noinline__ double idm_free_term(double comfort_acc_max, double speed, double target_speed,
                                              double speed_limit, double delta) {
     double ego_target_speed = clipd(target_speed, 0.0, speed_limit);
-    return comfort_acc_max * (1 - m_pow(fmax(speed, 0.0) / fabs(not_zero(ego_target_speed)), delta));
+    return comfort_acc_max * (1 - idm_pow(fmax(speed, 0.0) / fabs(not_zero(ego_target_speed)), delta));
 }
 // ... and the interaction term COMFORT_ACC_MAX * (d* / not_zero(d))^2 for a given gap d
 template <int TPE>
@@ -449,7 +449,7 @@ __device__ __noinline__ void pair_sat(const Frame<TPE>& F, int a, int b, double 
 template <int TPE>
 __device__ __forceinline__ void build_frame(const HwyHighwayParams& P, EnvShared<TPE>& sm, Frame<TPE>& F,
                                             int i, bool active, bool aligned, const VehicleRegs& r,
-                                            double dt, bool do_sweep, bool pruned) {
+                                            double dt, bool do_sweep, bool pruned, const Frame<TPE>* prev) {
     const int V = P.n_vehicles;
     const int wie = i >> 5;  // warp within the env
     const int lane = meta_lane(r.meta), tgt = meta_target(r.meta);
@@ -459,7 +459,21 @@ __device__ __forceinline__ void build_frame(const HwyHighwayParams& P, EnvShared
     const float fi = active ? F.lsf[i] : 0.0f;
     int rank = 0;
     bool ambiguous = false;
-    {
+    // The order along the road rarely changes within one substep: with the previous frame of the same launch at hand
+    // (`prev`, uniform), every warp of the env checks the whole chain key[perm[k-1]] < key[perm[k]] under the previous
+    // permutation (V - 1 float comparisons spread over its 32 lanes, no communication between the warps: each reaches
+    // the same verdict).  A strictly increasing chain of float keys is a strictly increasing chain of the doubles they
+    // were rounded from, so the ranks are the previous ones and there is neither a tie nor an ambiguity — the O(V)
+    // scan per thread (14 % of the kernel's instructions at V = 51) runs only when some pair swapped or drew level.
+    bool reuse = false;
+    if (prev) {
+        bool ok = true;
+        for (int k = (i & 31) + 1; k < V; k += 32) ok = ok && (F.lsf[prev->perm[k - 1]] < F.lsf[prev->perm[k]]);
+        reuse = __all_sync(0xffffffffu, ok);
+    }
+    if (reuse) {
+        rank = active ? prev->rank[i] : 0;
+    } else {
         const float4* lsf4 = reinterpret_cast<const float4*>(F.lsf);
         const int n4 = V >> 2;
         for (int q = 0; q < n4; ++q) {
@@ -903,7 +917,7 @@ highway_step_kernel(const __grid_constant__ HwyHighwayParams P, const HwyHighway
         if (i == 0) sm.n_items = 0;
         // frame 0: masks only — the sweep of the stored state ran at the end of the substep that
         // produced it (previous launch).  Later: Road.step's sweep (road/road.py:477-481).
-        build_frame(P, sm, F, i, active, aligned, r, dt, frame > 0, pruned);
+        build_frame(P, sm, F, i, active, aligned, r, dt, frame > 0, pruned, frame > 0 ? &sm.f[p ^ 1] : nullptr);
         PHASE_MARK(3);  // ranks, masks, sweep pass 1
         if (pruned && frame > 0) {  // uniform over the grid
             env_sync<TPE>();
@@ -1153,7 +1167,7 @@ highway_step_kernel(const __grid_constant__ HwyHighwayParams P, const HwyHighway
                 r.y += r.imp_y;
                 r.meta = (r.meta | HWY_META_CRASHED) & ~HWY_META_HAS_IMPACT;
             }
-            r.heading += r.speed * sin_beta / (kVehLength / 2) * dt;
+            r.heading += div_finite(r.speed * sin_beta, kVehLength / 2) * dt;
             r.speed += act_accel * dt;
             int nl = closest_lane(P, r.x, r.y, r.heading, congruent);  // on_state_update :170-177
             r.meta = meta_set_lane(r.meta, nl);

@@ -91,14 +91,30 @@ __device__ __forceinline__ void m_sincos(double x, double* s, double* c) {
 }
 static __device__ __noinline__ double m_pow(double x, double y) { return pow(x, y); }
 static __device__ __noinline__ double m_fmod(double a, double b) { return fmod(a, b); }
+// n / d for a finite non-zero d.  An exactly zero numerator (a vehicle that sits on its lane centre with the lane's
+// heading: most of a highway) sends the compiler's fp64 division to its out-of-line slow path (~100 instructions);
+// (+-0) / d = (+-0) * d for every finite non-zero d, sign included.
+__device__ __forceinline__ double div_finite(double n, double d) { return n == 0.0 ? n * d : n / d; }
+// x ** delta of IDMVehicle.acceleration (behavior.py:183-186) for x >= 0.  DELTA = 4.0 unless randomize_behavior was
+// called: x^4 from two exact squarings (x*x = p + e and p*p = q + f with fma residuals), (p + e)^2 = q + f + 2pe + e^2
+// rounded once — within 0.51 ulp of the exact power, the quality of glibc's pow behind numpy's `**` (CUDA's pow is a
+// ~200-instruction routine with a 2 ulp bound).  Any other exponent, huge or non-finite x: the library pow.
+__device__ __forceinline__ double idm_pow(double x, double delta) {
+    if (delta == 4.0 && x < 1e70) {
+        const double p = x * x, e = fma(x, x, -p);
+        const double q = p * p, f = fma(p, p, -q);
+        return q + (f + 2.0 * (p * e));
+    }
+    return m_pow(x, delta);
+}
+
 
 // Python floored float modulo (b > 0 here).  fmod() is exact, so the cases around the principal range need no call:
 //   0 <= a < b      -> a
 //   b <= a < 2b     -> a - b        (exact by Sterbenz: b <= a <= 2b)
 //   -b <= a < 0     -> fmod = a, then the sign fix-up `+= b` (one rounded add, as CPython's float_rem does)
 //   b == 1          -> a - floor(a) (exact) for a >= 0
-// Everything else takes the library fmod (a bit-serial loop: it was 11 % of the step kernel's instructions when
-// every wrap_to_pi went through it, profiles/r2_step_kernel_history.md).
+// Everything else takes the library fmod (a bit-serial loop).
 static __device__ __noinline__ double py_mod_slow(double a, double b) {
     double m = m_fmod(a, b);
     if (m != 0.0) {

@@ -286,7 +286,7 @@ __device__ __noinline__ double idm_acceleration(const HwyNetParams& P, const Gra
     if (ego < 0 || st.kind[ego] == HWY_KIND_OBSTACLE) return 0.0;  // `not isinstance(ego_vehicle, Vehicle)`
     double ego_target_speed = clipd(st.ts[ego], 0.0, g.lanes[st.lane[ego]].speed_limit);
     double acc = P.comfort_acc_max *
-                 (1 - m_pow(fmax(st.v[ego], 0.0) / fabs(not_zero(ego_target_speed)), delta));
+                 (1 - idm_pow(fmax(st.v[ego], 0.0) / fabs(not_zero(ego_target_speed)), delta));
     if (front >= 0) {
         double d = lane_distance_to(g, st, ego, front);
         double q = desired_gap(P, st, ego, front) / not_zero(d);
@@ -371,7 +371,7 @@ __device__ __noinline__ double steering_sin_slip(const HwyNetLane& L, double lc_
                                                  double speed) {
     double lane_future_heading = lane_heading_at(L, lc_s + speed * kTauPursuit);
     double lateral_speed_command = -kKpLateral * lc_lat;
-    double heading_command = m_asin(clipd(lateral_speed_command / not_zero(speed), -1.0, 1.0));
+    double heading_command = m_asin(clipd(div_finite(lateral_speed_command, not_zero(speed)), -1.0, 1.0));
     double heading_ref = lane_future_heading + clipd(heading_command, -kPi / 4, kPi / 4);
     double heading_rate_command = kKpHeading * wrap_to_pi(heading_ref - heading);
     return clipd(kVehLength / 2 / not_zero(speed) * heading_rate_command, -1.0, 1.0);
@@ -1216,7 +1216,7 @@ __device__ __forceinline__ void substep(const HwyNetParams& P, const GraphShared
             r.y += r.imp_y;
             r.meta = (r.meta | HWY_META_CRASHED) & ~HWY_META_HAS_IMPACT;
         }
-        r.heading += r.speed * sin_beta / (kVehLength / 2) * dt;
+        r.heading += div_finite(r.speed * sin_beta, kVehLength / 2) * dt;
         r.speed += act_accel * dt;
     }
     phase_sync<G>();  // everyone is done reading the pre-step staging
@@ -2350,14 +2350,15 @@ int configure_smem(K kernel, size_t bytes) {
     if (err != cudaSuccess) return fail("cudaFuncSetAttribute: %s", cudaGetErrorString(err));
     return 0;
 }
-int reset_threads() {  // HWYB200_RESET_THREADS overrides (64 / 128 / 256)
+int reset_threads() {  // HWYB200_RESET_THREADS overrides (32 / 64 / 128 / 256)
     if (const char* e = getenv("HWYB200_RESET_THREADS")) {
         int v = atoi(e);
-        if (v == 64 || v == 128 || v == 256) return v;
+        if (v == 32 || v == 64 || v == 128 || v == 256) return v;
     }
     return 64;
 }
 const int kResetThreads = reset_threads();
+const bool kResetWide = getenv("HWYB200_RESET_WIDE") != nullptr;  // experiment: one env per warp in the reset kernel
 int blocks_for(int n_envs, int g) {
     int per = hwynet::kBlockThreads / g;
     return (n_envs + per - 1) / per;
@@ -2542,7 +2543,7 @@ int hwy_intersection_reset(const HwyNetParams* p, const HwyNetGraph* graph, cons
         cudaMemcpyAsync(final_obs, obs, (size_t)s->n_envs * hwy_network_obs_size(p) * sizeof(float),
                         cudaMemcpyDeviceToDevice, st);
     if (check_launch("compact_envs_kernel")) return 1;
-    if (spawn->initial_vehicle_count + 1 <= 16) {  // n-1 draws + challenger + controlled vehicle fit 16 slots
+    if (spawn->initial_vehicle_count + 1 <= 16 && !kResetWide && kResetThreads >= 32) {  // n-1 draws + challenger + controlled vehicle fit 16 slots
         const int per = kResetThreads / 16;
         const size_t smem = ((sizeof(hwynet::GraphShared) + 15) & ~size_t(15)) + per * sizeof(hwynet::EnvStage<16, true>);
         if (configure_smem(hwynet::intersection_reset_kernel<16, true>, smem)) return 1;

@@ -11,3 +11,5 @@ ncu -i /tmp/${TAG}.ncu-rep --page raw --csv > gpurun_out/${TAG}_raw.csv 2>/dev/n
 ncu -i /tmp/${TAG}.ncu-rep --page source --csv --print-source cuda,sass -c 1 > /tmp/${TAG}_src.csv 2>/dev/null
 python tools/ncu_lines.py /tmp/${TAG}_src.csv 70 > gpurun_out/${TAG}_lines.txt 2>&1
 head -3 gpurun_out/${TAG}_lines.txt
+# executed counts of the CALL instructions (which call sites of a __noinline__ helper are hot)
+python tools/ncu_calls.py /tmp/${TAG}_src.csv 70 > gpurun_out/${TAG}_calls.txt 2>&1
