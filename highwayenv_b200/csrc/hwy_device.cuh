@@ -43,6 +43,7 @@ __device__ __forceinline__ int closest_lane(const HwyHighwayParams& P, double x,
         const double s = dot2(x - L0.start_x, y - L0.start_y, L0.dir_x, L0.dir_y);
         const double t1 = fmax(s - L0.length, 0.0), t2 = fmax(0.0 - s, 0.0);
         const double angle = 1.0 * fabs(wrap_to_pi(h - L0.heading));
+#pragma unroll 1
         for (int l = 0; l < P.lanes_count; ++l) {
             const HwyStraightLane& L = P.lanes[l];
             const double r = dot2(x - L.start_x, y - L.start_y, L.lat_x, L.lat_y);
@@ -113,9 +114,10 @@ __device__ __forceinline__ void beta_of_controlled(double x, double& sin_beta, d
     const double T3 = 1.7320508075688767;  // np.tan(np.pi / 3)
     double c = sqrt(1.0 - x * x);          // cos(arcsin x) >= 0
     if (2.0 * fabs(x) > T3 * c) {          // steering saturated at MAX_STEERING_ANGLE
-        double t = copysign(0.5 * T3, x);
-        double inv = 1.0 / sqrt(1.0 + t * t);
-        sin_beta = t * inv;
+        // t = +-T3/2: 1/sqrt(1 + t*t) does not depend on the sign and (-t)*inv = -(t*inv), so the constants fold
+        const double t0 = 0.5 * T3;
+        const double inv = 1.0 / sqrt(1.0 + t0 * t0);
+        sin_beta = copysign(t0 * inv, x);
         cos_beta = inv;
     } else {
         sin_beta = x;
@@ -123,7 +125,7 @@ __device__ __forceinline__ void beta_of_controlled(double x, double& sin_beta, d
     }
 }
 // beta = arctan(1/2 tan(delta)) for an explicit steering angle (ContinuousAction ego)
-__device__ __forceinline__ void beta_of_angle(double delta, double& sin_beta, double& cos_beta) {
+static __device__ __noinline__ void beta_of_angle(double delta, double& sin_beta, double& cos_beta) {
     double t = 0.5 * m_tan(delta);
     double inv = 1.0 / sqrt(1.0 + t * t);
     sin_beta = t * inv;

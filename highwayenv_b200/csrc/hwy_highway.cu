@@ -89,9 +89,36 @@ struct EnvShared {
 // All envs of a block advance in lock-step (block-wide barriers): besides ordering the shared
 // staging it keeps the block's warps on the same code at the same time, which is what the
 // instruction cache wants from a ~100 KB kernel (measured: 1.4x over per-env barriers).
+// HWY_ENV_BARRIER (experiment switch, default 0 = shipped): 1 = every barrier is a per-env named barrier,
+// 2 = only the phase barriers inside a substep (env_sync_phase) are per-env; the barrier after publish stays
+// block-wide and re-aligns the block's warps once per substep; 3 = only the two barriers around the MOBIL items.
+#ifndef HWY_ENV_BARRIER
+#define HWY_ENV_BARRIER 0
+#endif
+template <int TPE>
+__device__ __forceinline__ void env_sync_named() {
+    if (TPE == 32)
+        __syncwarp();
+    else
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)(threadIdx.x / TPE)), "n"(TPE) : "memory");
+}
 template <int TPE>
 __device__ __forceinline__ void env_sync() {
+#if HWY_ENV_BARRIER == 1
+    env_sync_named<TPE>();
+#else
     __syncthreads();
+#endif
+}
+template <int TPE, int LEVEL>
+__device__ __forceinline__ void env_sync_phase() {
+#if HWY_ENV_BARRIER == 1 || HWY_ENV_BARRIER == 2
+    env_sync_named<TPE>();
+#elif HWY_ENV_BARRIER == 3
+    if (LEVEL == 2) env_sync_named<TPE>(); else __syncthreads();
+#else
+    __syncthreads();
+#endif
 }
 
 template <int NW>
@@ -148,6 +175,37 @@ __device__ __forceinline__ void neighbours(const HwyHighwayParams& P, const Fram
     w = w0;
     while (m == 0 && --w >= 0) m = F.smask[l][w];
     if (m) rear = F.perm[w * 32 + 31 - __clz(m)];
+}
+
+// The same query as a real call (front | rear << 8, 0xff = none) for the places that are not on every thread's path
+// (MOBIL items, the target-lane query of a vehicle that is changing lanes): three inlined copies of the bit scans cost
+// 5 KB of the per-substep loop.
+template <int TPE>
+__device__ __noinline__ int neighbours_packed(const uint32_t* __restrict__ smask_l, const Frame<TPE>& F, int self) {
+    constexpr int NW = TPE / 32;
+    const int r = F.rank[self];
+    const int w0 = r >> 5, b = r & 31;
+    int front = 0xff, rear = 0xff;
+    uint32_t m = smask_l[w0] & (b == 31 ? 0u : (~0u << (b + 1)));
+    int w = w0;
+    while (m == 0 && ++w < NW) m = smask_l[w];
+    if (m) front = F.perm[w * 32 + __ffs(m) - 1];
+    m = smask_l[w0] & ((1u << b) - 1u);
+    w = w0;
+    while (m == 0 && --w >= 0) m = smask_l[w];
+    if (m) rear = F.perm[w * 32 + 31 - __clz(m)];
+    return front | (rear << 8);
+}
+template <int TPE>
+__device__ __forceinline__ void neighbours_cold(const HwyHighwayParams& P, const Frame<TPE>& F, int V, int l,
+                                                int self, int& front, int& rear) {
+    if (F.slow) {
+        neighbours_linear(F, P.lanes[l], V, self, front, rear);
+        return;
+    }
+    const int fr = neighbours_packed(F.smask[l], F, self);
+    front = (fr & 0xff) == 0xff ? -1 : (fr & 0xff);
+    rear = (fr >> 8) == 0xff ? -1 : (fr >> 8);
 }
 
 // ------------------------------------------------------------------ IDM (vehicle/behavior.py)
@@ -266,14 +324,36 @@ __device__ __forceinline__ void kinematics_observe(const HwyHighwayParams& P, co
         ok = ok && (P.obs_see_behind || -2 * kVehLength < d);
         if (ok) key = fabs(d);
     }
+    // Float copies of the keys in the frame's (by now unused) rank-key array: rounding to float is monotone, so a float
+    // key below ours is a double key below ours and only equal finite floats need the doubles (same scheme as
+    // rank_count); four keys per shared-memory load.  Slot 0 (the observer) and the padding slots hold +inf.
+    float* __restrict__ kf = const_cast<float*>(F.lsf);
+    const float keyf = (float)key;
     key_scratch[i] = key;
+    kf[i] = keyf;
     env_sync<TPE>();
     // stable rank among the valid candidates (python sorted() on |lane_distance_to|)
     int rank = 0, n_valid = 0;
-    for (int u = 1; u < V; ++u) {
-        double ku = key_scratch[u];
-        n_valid += ku < INFINITY;
-        rank += (ku < key) || (ku == key && u < i);
+    bool ambiguous = false;
+    {
+        const float4* kf4 = reinterpret_cast<const float4*>(kf);
+#pragma unroll 1
+        for (int q = 0; q < TPE / 4; ++q) {
+            const float4 f = kf4[q];
+            const int u = q << 2;
+            n_valid += (f.x < INFINITY) + (f.y < INFINITY) + (f.z < INFINITY) + (f.w < INFINITY);
+            rank += (f.x < keyf) + (f.y < keyf) + (f.z < keyf) + (f.w < keyf);
+            ambiguous = ambiguous || (f.x == keyf && u != i) || (f.y == keyf && u + 1 != i) ||
+                        (f.z == keyf && u + 2 != i) || (f.w == keyf && u + 3 != i);
+        }
+    }
+    if (ambiguous && keyf < INFINITY) {  // two candidates within float rounding of each other: exact count
+        rank = 0;
+#pragma unroll 1
+        for (int u = 1; u < V; ++u) {
+            const double ku = key_scratch[u];
+            rank += (ku < key) || (ku == key && u < i);
+        }
     }
     const double xr = 5.0 * kMaxSpeed, yr = 4.0 * P.lanes_count, vr = 2 * kMaxSpeed;
     int row = -1;
@@ -399,19 +479,30 @@ __device__ __forceinline__ void publish(const HwyHighwayParams& P, Frame<TPE>& F
 
 // Collision test of the pair a < b on the staged positions (vehicle/objects.py:92-138):
 // handle_collisions' gate is applied by the caller, _is_colliding here.
+// The sphere pre-check is split: the squared-distance reject (the vast majority of the pairs) is inline, the exact
+// `dist > thr` of the reference with its square root sits at the top of the out-of-line pair_sat.
 template <int TPE>
 __device__ __forceinline__ bool pair_precheck(const Frame<TPE>& F, int a, int b, double dt) {
     const double diag = sqrt(kVehLength * kVehLength + kVehWidth * kVehWidth);
     const double thr = (diag + diag) / 2 + F.v[a] * dt;
     const double dx = F.x[b] - F.x[a], dy = F.y[b] - F.y[a];
-    // far pairs (the vast majority): d^2 clearly above thr^2 => the exact test below is true too
-    if (thr >= 0.0 && dx * dx + dy * dy > thr * thr * 1.000001 + 1e-9) return false;
-    double dist = norm2(dx, dy);
-    return !(dist > thr);
+    // far pairs: d^2 clearly above thr^2 => the exact test in pair_sat is true too
+    return !(thr >= 0.0 && dx * dx + dy * dy > thr * thr * 1.000001 + 1e-9);
 }
 template <int TPE>
 __device__ __noinline__ void pair_sat(const Frame<TPE>& F, int a, int b, double dt, bool& inter,
                                       bool& will, double& trx, double& try_) {
+    {
+        const double diag = sqrt(kVehLength * kVehLength + kVehWidth * kVehWidth);
+        const double thr = (diag + diag) / 2 + F.v[a] * dt;
+        const double dist = norm2(F.x[b] - F.x[a], F.y[b] - F.y[a]);
+        if (dist > thr) {  // vehicle/objects.py:122-126
+            inter = false;
+            will = false;
+            trx = try_ = 0.0;
+            return;
+        }
+    }
     // Conservative shortcut.  The reference's flags are sticky ANDs over the visited edge
     // normals and its `break` only triggers once both are False, so if ONE of the four distinct
     // rectangle axes separates the rectangles statically AND after the relative-displacement
@@ -443,6 +534,42 @@ __device__ __noinline__ void pair_sat(const Frame<TPE>& F, int a, int b, double 
                           F.v[b] * F.s[b] * dt, inter, will, trx, try_);
 }
 
+// Rank of vehicle i along the road by counting (O(V) per thread), out of line: it runs on the first frame of a launch
+// and when the previous order broke (see build_frame), and its unrolled loops are 8 KB of code that the per-substep
+// loop should not carry.  Returns rank | tie << 8.
+template <int TPE>
+__device__ __noinline__ int rank_count(const Frame<TPE>& F, int V, int i, bool active) {
+    const double si = active ? F.ls[i] : 0.0;
+    const float fi = active ? F.lsf[i] : 0.0f;
+    int rank = 0;
+    bool ambiguous = false;
+    const float4* lsf4 = reinterpret_cast<const float4*>(F.lsf);
+    const int n4 = V >> 2;
+    for (int q = 0; q < n4; ++q) {
+        float4 f = lsf4[q];
+        const int u = q << 2;
+        rank += (f.x < fi) + (f.y < fi) + (f.z < fi) + (f.w < fi);
+        ambiguous = ambiguous || (f.x == fi && u != i) || (f.y == fi && u + 1 != i) ||
+                    (f.z == fi && u + 2 != i) || (f.w == fi && u + 3 != i);
+    }
+    for (int u = n4 << 2; u < V; ++u) {
+        float fu = F.lsf[u];
+        rank += fu < fi;
+        ambiguous = ambiguous || (fu == fi && u != i);
+    }
+    bool tie = false;
+    if (ambiguous) {
+        rank = 0;
+#pragma unroll 1
+        for (int u = 0; u < V; ++u) {
+            double su = F.ls[u];
+            rank += (su < si) || (su == si && u < i);
+            tie = tie || (su == si && u != i);
+        }
+    }
+    return rank | ((int)tie << 8);
+}
+
 // After a barrier that follows publish(): ranks, rank-ordered membership masks, lane / target
 // masks (warp ballots) and the first pass of the collision sweep of Road.step
 // (road/road.py:477-481).  All threads of the env call this convergently.
@@ -455,10 +582,7 @@ __device__ __forceinline__ void build_frame(const HwyHighwayParams& P, EnvShared
     const int lane = meta_lane(r.meta), tgt = meta_target(r.meta);
     // -- rank along the road (s, slot) and tie detection.  Float keys first: rounding to float
     // is monotone, so fu < fi implies su < si; only equal float keys need the doubles.
-    const double si = active ? F.ls[i] : 0.0;
-    const float fi = active ? F.lsf[i] : 0.0f;
     int rank = 0;
-    bool ambiguous = false;
     // The order along the road rarely changes within one substep: with the previous frame of the same launch at hand
     // (`prev`, uniform), every warp of the env checks the whole chain key[perm[k-1]] < key[perm[k]] under the previous
     // permutation (V - 1 float comparisons spread over its 32 lanes, no communication between the warps: each reaches
@@ -468,40 +592,23 @@ __device__ __forceinline__ void build_frame(const HwyHighwayParams& P, EnvShared
     bool reuse = false;
     if (prev) {
         bool ok = true;
+#pragma unroll 1
         for (int k = (i & 31) + 1; k < V; k += 32) ok = ok && (F.lsf[prev->perm[k - 1]] < F.lsf[prev->perm[k]]);
         reuse = __all_sync(0xffffffffu, ok);
     }
+    bool tie = false;
     if (reuse) {
         rank = active ? prev->rank[i] : 0;
     } else {
-        const float4* lsf4 = reinterpret_cast<const float4*>(F.lsf);
-        const int n4 = V >> 2;
-        for (int q = 0; q < n4; ++q) {
-            float4 f = lsf4[q];
-            const int u = q << 2;
-            rank += (f.x < fi) + (f.y < fi) + (f.z < fi) + (f.w < fi);
-            ambiguous = ambiguous || (f.x == fi && u != i) || (f.y == fi && u + 1 != i) ||
-                        (f.z == fi && u + 2 != i) || (f.w == fi && u + 3 != i);
-        }
-        for (int u = n4 << 2; u < V; ++u) {
-            float fu = F.lsf[u];
-            rank += fu < fi;
-            ambiguous = ambiguous || (fu == fi && u != i);
-        }
-    }
-    bool tie = false;
-    if (ambiguous) {
-        rank = 0;
-        for (int u = 0; u < V; ++u) {
-            double su = F.ls[u];
-            rank += (su < si) || (su == si && u < i);
-            tie = tie || (su == si && u != i);
-        }
+        const int rt = rank_count(F, V, i, active);
+        rank = rt & 0xff;
+        tie = (rt >> 8) != 0;
     }
     if (active) {
         F.perm[rank] = (unsigned char)i;
         F.rank[i] = (unsigned char)rank;
         if (tie || !aligned) F.slow = 1;
+#pragma unroll 1
         for (int l = 0; l < P.lanes_count; ++l) {
             double s_l, lat_l;
             lane_local(P.lanes[l], r.x, r.y, s_l, lat_l);
@@ -510,6 +617,7 @@ __device__ __forceinline__ void build_frame(const HwyHighwayParams& P, EnvShared
     }
     // -- slot-ordered masks by ballot
     const bool is_idm = meta_kind(r.meta) == HWY_KIND_IDM;
+#pragma unroll 1
     for (int l = 0; l < P.lanes_count; ++l) {
         uint32_t b_lane = __ballot_sync(0xffffffffu, active && lane == l);
         uint32_t b_tgt = __ballot_sync(0xffffffffu, active && tgt == l);
@@ -849,7 +957,12 @@ constexpr int kMaxBlockThreads = 512;  // 128 registers/thread => one full regis
 #endif
 
 // blockDim.x = TPE * (envs per block); dynamic shared memory = envs per block * sizeof(EnvShared).
-template <int TPE>
+// AL (host-checked, lanes_congruent): every lane is a copy of lane 0 shifted sideways — what
+// RoadNetwork.straight_road_network builds (road/road.py:291-321) — so the general-geometry branches (per-lane
+// projections in lane_distance / closest_lane, F.slow for unaligned lanes) are compiled out.  The per-substep loop
+// of this kernel is larger than the 32 KB L1.5 instruction cache and instruction fetch is one of its top stalls:
+// code bytes on the hot path are a first-order cost (profiles/r2_kernel_history.md).
+template <int TPE, bool AL>
 __global__ void __launch_bounds__(HWY_STEP_BOUND_THREADS, HWY_STEP_BOUND_BLOCKS)
 highway_step_kernel(const __grid_constant__ HwyHighwayParams P, const HwyHighwayState S,
                     const int32_t* __restrict__ action_i, const float* __restrict__ action_f,
@@ -870,11 +983,15 @@ highway_step_kernel(const __grid_constant__ HwyHighwayParams P, const HwyHighway
     const int V = P.n_vehicles;
     const bool active = i < V;
     const size_t slot = (size_t)e * S.vp + (active ? i : 0);
-    const bool aligned = lanes_aligned(P);
-    const bool congruent = lanes_congruent(P);
+    const bool aligned = AL || lanes_aligned(P);
+    const bool congruent = AL || lanes_congruent(P);
 
     VehicleRegs r;
     load_vehicle(S, slot, r);
+    // bits 24-30 of the stored meta word: this vehicle's rank along the road at the end of the previous step (a hint,
+    // validated below and again by build_frame's chain check, so any value is safe)
+    const int rank_hint = (r.meta >> HWY_META_RANK_SHIFT) & (TPE - 1);
+    r.meta &= (1 << HWY_META_RANK_SHIFT) - 1;
     const int kind = meta_kind(r.meta);
     int speed_index = (i == 0) ? S.speed_index[e] : 0;
     double act_steer = 0.0, act_accel = 0.0;
@@ -895,7 +1012,19 @@ highway_step_kernel(const __grid_constant__ HwyHighwayParams P, const HwyHighway
         if (i < NW) sm.ok_left[i] = sm.ok_right[i] = 0;
         if (i == 0) sm.n_items = 0;
         if (active) sm.delta[i] = r.delta;
+        sm.f[1].perm[i] = (unsigned char)i;
     }
+    // Rank hints -> a "previous frame" for the first build_frame of the launch: perm[hint] = slot.  The hints form a
+    // permutation exactly when every vehicle finds itself in its slot; then build_frame's strictly-increasing chain
+    // check decides whether the order still holds (it does unless the state was edited or re-spawned), and the O(V)
+    // per-thread rank count of the first frame — a sixth of all rank counts at 5 substeps — is skipped.
+    env_sync<TPE>();
+    if (active) {
+        sm.f[1].perm[rank_hint] = (unsigned char)i;
+        sm.f[1].rank[i] = (unsigned char)rank_hint;
+    }
+    env_sync<TPE>();
+    const bool hints_ok = __syncthreads_and(!active || (rank_hint < V && sm.f[1].perm[rank_hint] == i)) != 0;
     const IdmK K = make_idm(P);
     // all-pairs gate (every vehicle checks collisions): rank-pruned sweep; a single checking vehicle (highway-fast)
     // already costs one pre-check per thread
@@ -917,13 +1046,14 @@ highway_step_kernel(const __grid_constant__ HwyHighwayParams P, const HwyHighway
         if (i == 0) sm.n_items = 0;
         // frame 0: masks only — the sweep of the stored state ran at the end of the substep that
         // produced it (previous launch).  Later: Road.step's sweep (road/road.py:477-481).
-        build_frame(P, sm, F, i, active, aligned, r, dt, frame > 0, pruned, frame > 0 ? &sm.f[p ^ 1] : nullptr);
+        build_frame(P, sm, F, i, active, aligned, r, dt, frame > 0, pruned,
+                    (frame > 0 || hints_ok) ? &sm.f[p ^ 1] : nullptr);
         PHASE_MARK(3);  // ranks, masks, sweep pass 1
         if (pruned && frame > 0) {  // uniform over the grid
-            env_sync<TPE>();
+            env_sync_phase<TPE, 3>();
             sweep_pruned(sm, F, V, i, active, dt);
         }
-        env_sync<TPE>();
+        env_sync_phase<TPE, 3>();
         PHASE_MARK(4);  // barrier after build
         if (active && frame > 0) apply_collisions(sm, F, i, r, dt);
         PHASE_MARK(5);  // sweep pass 2
@@ -1037,7 +1167,7 @@ highway_step_kernel(const __grid_constant__ HwyHighwayParams P, const HwyHighway
             }
         }
         PHASE_MARK(7);  // phase A1
-        env_sync<TPE>();
+        env_sync_phase<TPE, 2>();
         PHASE_MARK(8);  // barrier after phase A1
 
         // ---- phase A2: mobil(lane_index) (behavior.py:265-324; route None => acceleration-gain
@@ -1047,7 +1177,7 @@ highway_step_kernel(const __grid_constant__ HwyHighwayParams P, const HwyHighway
             const int v = it & 0xff, cand = (it >> 8) & 0x7f, right = it >> 15;
             const double delta_v = sm.delta[v];
             int new_preceding, new_following;
-            neighbours(P, F, V, cand, v, new_preceding, new_following);
+            neighbours_cold(P, F, V, cand, v, new_preceding, new_following);
             double new_following_pred_a = idm_acceleration_of(P, K, F, aligned, delta_v, new_following, v);
             if (new_following_pred_a < -P.lane_change_max_braking_imposed) continue;
             double self_pred_a = sm.free_t[v];
@@ -1068,7 +1198,7 @@ highway_step_kernel(const __grid_constant__ HwyHighwayParams P, const HwyHighway
             atomicOr(right ? &sm.ok_right[v >> 5] : &sm.ok_left[v >> 5], 1u << (v & 31));
         }
         PHASE_MARK(13);  // phase A2
-        env_sync<TPE>();
+        env_sync_phase<TPE, 2>();
         PHASE_MARK(14);  // barrier after phase A2
 
         // ---- Road.act() phase B (steering + target-lane IDM with the final target), then
@@ -1135,7 +1265,7 @@ highway_step_kernel(const __grid_constant__ HwyHighwayParams P, const HwyHighway
             if (idm_active) {
                 if (lane != tgt) {  // behavior.py:121-131
                     int f_t, r_t;
-                    neighbours(P, F, V, tgt, i, f_t, r_t);
+                    neighbours_cold(P, F, V, tgt, i, f_t, r_t);
                     double tacc = free_i;
                     if (f_t >= 0) tacc -= idm_gap_term(P, K, F, aligned, i, f_t);
                     acc = fmin(acc, tacc);
@@ -1248,7 +1378,10 @@ highway_step_kernel(const __grid_constant__ HwyHighwayParams P, const HwyHighway
             env_sync<TPE>();
         }
     }
-    if (active && env_ok) store_vehicle(S, slot, r);
+    if (active && env_ok) {
+        r.meta |= (int)sm.f[p].rank[i] << HWY_META_RANK_SHIFT;  // rank hint for the next launch (see the prologue)
+        store_vehicle(S, slot, r);
+    }
     if (autoreset && active && env_ok && sm.done) S.delta[slot] = r.delta;
     PHASE_MARK(12);  // epilogue
 }
@@ -1501,7 +1634,18 @@ int ensure_pcg_jump(cudaStream_t st) {
     return 0;
 }
 
-template <int TPE>
+// host copy of hwy::lanes_congruent (hwy_device.cuh)
+bool lanes_congruent_host(const HwyHighwayParams* p) {
+    const HwyStraightLane* L = p->lanes;
+    bool ok = L[0].dir_y == 0.0;
+    for (int l = 1; l < p->lanes_count; ++l)
+        ok = ok && L[l].start_x == L[0].start_x && L[l].dir_x == L[0].dir_x && L[l].dir_y == 0.0 &&
+             L[l].heading == L[0].heading && L[l].length == L[0].length && L[l].lat_x == L[0].lat_x &&
+             L[l].lat_y == L[0].lat_y;
+    return ok;
+}
+
+template <int TPE, bool AL>
 int launch_step(const HwyHighwayParams* p, const HwyHighwayState* s, const int32_t* action_i,
                 const float* action_f, float* obs, double* reward, uint8_t* terminated,
                 uint8_t* truncated, double* info_speed, uint8_t* info_crashed, int autoreset,
@@ -1513,12 +1657,12 @@ int launch_step(const HwyHighwayParams* p, const HwyHighwayState* s, const int32
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return fail("%s", "cudaGetDevice failed");
     if (smem > configured[dev].load(std::memory_order_relaxed)) {
-        cudaError_t err = cudaFuncSetAttribute(hwy::highway_step_kernel<TPE>,
+        cudaError_t err = cudaFuncSetAttribute(hwy::highway_step_kernel<TPE, AL>,
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return fail("cudaFuncSetAttribute: %s", cudaGetErrorString(err));
         configured[dev].store(smem, std::memory_order_relaxed);
     }
-    hwy::highway_step_kernel<TPE><<<blocks, TPE * epb, smem, st>>>(
+    hwy::highway_step_kernel<TPE, AL><<<blocks, TPE * epb, smem, st>>>(
         *p, *s, action_i, action_f, obs, reward, terminated, truncated, info_speed, info_crashed,
         autoreset, final_obs);
     return 0;
@@ -1606,16 +1750,19 @@ int hwy_highway_step(const HwyHighwayParams* p, const HwyHighwayState* s, const 
     int tpe = tpe_for(p->n_vehicles);
     int epb = step_envs_per_block(tpe, s->n_envs);
     int blocks = (s->n_envs + epb - 1) / epb;
-    if (tpe == 32) {
-        if (launch_step<32>(p, s, action_i, action_f, obs, reward, terminated, truncated, info_speed,
-                            info_crashed, autoreset, final_obs, blocks, epb, st)) return 1;
-    } else if (tpe == 64) {
-        if (launch_step<64>(p, s, action_i, action_f, obs, reward, terminated, truncated, info_speed,
-                            info_crashed, autoreset, final_obs, blocks, epb, st)) return 1;
-    } else {
-        if (launch_step<128>(p, s, action_i, action_f, obs, reward, terminated, truncated, info_speed,
-                             info_crashed, autoreset, final_obs, blocks, epb, st)) return 1;
-    }
+    const bool al = lanes_congruent_host(p);
+#define HWY_LAUNCH_STEP(T, A)                                                                              \
+    launch_step<T, A>(p, s, action_i, action_f, obs, reward, terminated, truncated, info_speed, info_crashed, \
+                      autoreset, final_obs, blocks, epb, st)
+    int rc;
+    if (tpe == 32)
+        rc = al ? HWY_LAUNCH_STEP(32, true) : HWY_LAUNCH_STEP(32, false);
+    else if (tpe == 64)
+        rc = al ? HWY_LAUNCH_STEP(64, true) : HWY_LAUNCH_STEP(64, false);
+    else
+        rc = al ? HWY_LAUNCH_STEP(128, true) : HWY_LAUNCH_STEP(128, false);
+#undef HWY_LAUNCH_STEP
+    if (rc) return 1;
     if (check_launch("highway_step_kernel")) return 1;
     return 0;
 }

@@ -99,11 +99,31 @@ __device__ __forceinline__ double div_finite(double n, double d) { return n == 0
 // called: x^4 from two exact squarings (x*x = p + e and p*p = q + f with fma residuals), (p + e)^2 = q + f + 2pe + e^2
 // rounded once — within 0.51 ulp of the exact power, the quality of glibc's pow behind numpy's `**` (CUDA's pow is a
 // ~200-instruction routine with a 2 ulp bound).  Any other exponent, huge or non-finite x: the library pow.
+//
+// randomize_behavior (highway-v0 / highway-fast-v0 traffic) draws DELTA from U(3.5, 4.5): then x^delta = x^4 * x^d with
+// |d| = |delta - 4| <= 0.5, the first factor as above and the second as exp(d * log(x)).  The usual weakness of
+// exp(y log x) — the error of log(x) is multiplied by y log x — is small here because |d log x| <= 0.35 for x in
+// [0.5, 2] (ratios of a speed to its target): ~1.5 ulp on top of the two functions' own 1 ulp, the same class as the
+// library pow's 2 ulp bound, and an absolute error below 1e-15 * x^delta for small x where (1 - x^delta) is what is
+// used.  It replaces ~175 issued instructions per call (7 % of the highway step kernel's instructions,
+// profiles/r2_kernel_history.md) by ~80.  HWY_LIBRARY_POW restores the library call.
+static __device__ __noinline__ double m_exp_dlog(double d, double x) { return exp(d * log(x)); }
 __device__ __forceinline__ double idm_pow(double x, double delta) {
+#ifndef HWY_LIBRARY_POW
+    if (x < 1e60 && fabs(delta - 4.0) <= 0.5) {
+#else
     if (delta == 4.0 && x < 1e70) {
+#endif
         const double p = x * x, e = fma(x, x, -p);
         const double q = p * p, f = fma(p, p, -q);
-        return q + (f + 2.0 * (p * e));
+        const double x4 = q + (f + 2.0 * (p * e));
+#ifndef HWY_LIBRARY_POW
+        if (delta == 4.0) return x4;
+        if (x > 1e-60) return x4 * m_exp_dlog(delta - 4.0, x);
+        if (x == 0.0) return 0.0;  // 0 ** delta, delta > 0
+#else
+        return x4;
+#endif
     }
     return m_pow(x, delta);
 }

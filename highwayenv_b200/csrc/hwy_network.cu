@@ -909,6 +909,35 @@ __device__ __noinline__ void position_heading_along_route(const GraphShared& g, 
 
 // utils.py:77-174 rotated_rectangles_intersect: 9 points (corners, centre, edge midpoints) of one
 // rectangle inside the other, both ways, with the reference's rotation convention
+// Out of line and rolled: the pair test runs only for predicted positions closer than one vehicle length, at the
+// regulation ticks, and its two fully unrolled copies were 13 KB in the middle of the substep loop.
+__device__ __noinline__ bool rotated_rectangles_intersect(double c1x, double c1y, double a1, double c2x, double c2y,
+                                                          double a2, double l, double w) {
+    const double hl = l / 2, hw = w / 2;
+    double s1, c1, s2, c2;
+    m_sincos(a1, &s1, &c1);
+    m_sincos(a2, &s2, &c2);
+#pragma unroll 1
+    for (int dir = 0; dir < 2; ++dir) {
+        // has_corner_inside(rect1, rect2) then has_corner_inside(rect2, rect1) (utils.py:77-90)
+        const double ox = dir ? c2x : c1x, oy = dir ? c2y : c1y, os = dir ? s2 : s1, oc = dir ? c2 : c1;
+        const double tx = dir ? c1x : c2x, ty = dir ? c1y : c2y, ts = dir ? s1 : s2, tc = dir ? c1 : c2;
+#pragma unroll 1
+        for (int k = 0; k < 9; ++k) {
+            // corners, centre, edge midpoints in the reference's order
+            const double fx = (k == 2 || k == 3 || k == 6) ? hl : ((k == 4 || k == 7 || k == 8) ? 0.0 : -hl);
+            const double fy = (k == 1 || k == 2 || k == 8) ? hw : ((k == 4 || k == 5 || k == 6) ? 0.0 : -hw);
+            double px = oc * fx + (-os) * fy + ox;
+            double py = os * fx + oc * fy + oy;
+            double dx = px - tx, dy = py - ty;
+            double rx = tc * dx + (-ts) * dy, ry = ts * dx + tc * dy;
+            if (-l / 2 <= rx && rx <= l / 2 && -w / 2 <= ry && ry <= w / 2) return true;
+        }
+    }
+    return false;
+}
+
+// general form (two sizes) for the known-answer hook debug_rectangles_kernel
 __device__ __forceinline__ bool has_corner_inside(double c1x, double c1y, double l1, double w1, double a1,
                                                   double c2x, double c2y, double l2, double w2, double a2) {
     const double hl = l1 / 2, hw = w1 / 2;
@@ -917,6 +946,11 @@ __device__ __forceinline__ bool has_corner_inside(double c1x, double c1y, double
     double s1, c1, s2, c2;
     m_sincos(a1, &s1, &c1);
     m_sincos(a2, &s2, &c2);
+#ifdef HWY_NET_INLINE_RECT
+#pragma unroll
+#else
+#pragma unroll 1
+#endif
     for (int k = 0; k < 9; ++k) {
         double px = c1 * pxs[k] + (-s1) * pys[k] + c1x;
         double py = s1 * pxs[k] + c1 * pys[k] + c1y;
@@ -932,7 +966,7 @@ __device__ __forceinline__ bool has_corner_inside(double c1x, double c1y, double
 // PLAIN: the env may hold a ContinuousAction ego (kind HWY_KIND_VEHICLE); compiled out otherwise so that the
 // DiscreteMetaAction kernels keep their register budget (198 vs 128 registers measured with the code always in)
 template <int G, bool REG, bool PLAIN>
-__device__ __forceinline__ void enforce_road_rules(const HwyNetParams& P, const GraphShared& g,
+__device__ __forceinline__ void enforce_road_rules(const bool dynamical, const GraphShared& g,
                                                    EnvStage<G, REG>& st, int V, int i, Regs& r, double act_steer) {
     const bool active = i < V;
     // un-freeze (YIELD_DURATION = 0: every yielding vehicle is released at the next regulation tick)
@@ -976,7 +1010,7 @@ __device__ __forceinline__ void enforce_road_rules(const HwyNetParams& P, const 
                 bool simulated = false;
                 if constexpr (PLAIN) {
                     if (plain) {
-                        if (P.dynamical) {
+                        if (dynamical) {
                             bicycle_advance(sim, sim_crashed, sim_steer, sim_acc, 0.25);
                         } else {
                             kinematic_advance(sim, sim_crashed, sim_steer, sim_acc, 0.25);
@@ -1011,10 +1045,14 @@ __device__ __forceinline__ void enforce_road_rules(const HwyNetParams& P, const 
                 double p1x = st.pred[a][k][0], p1y = st.pred[a][k][1], p2x = st.pred[b][k][0], p2y = st.pred[b][k][1];
                 if (norm2(p2x - p1x, p2y - p1y) > kVehLength) continue;
                 double h1 = st.pred[a][k][2], h2 = st.pred[b][k][2];
+#ifdef HWY_NET_INLINE_RECT
                 hit = has_corner_inside(p1x, p1y, 1.5 * kVehLength, 0.9 * kVehWidth, h1, p2x, p2y, 1.5 * kVehLength,
                                         0.9 * kVehWidth, h2) ||
                       has_corner_inside(p2x, p2y, 1.5 * kVehLength, 0.9 * kVehWidth, h2, p1x, p1y, 1.5 * kVehLength,
                                         0.9 * kVehWidth, h1);
+#else
+                hit = rotated_rectangles_intersect(p1x, p1y, h1, p2x, p2y, h2, 1.5 * kVehLength, 0.9 * kVehWidth);
+#endif
             }
             if (hit) conflict |= 1u << q;
         }
@@ -1046,6 +1084,20 @@ __device__ __forceinline__ void enforce_road_rules(const HwyNetParams& P, const 
     group_sync<G>();
 }
 
+// Out-of-line form for the kernels without a ContinuousAction ego: 1 = released (target speed back to the lane's
+// limit, YIELDING cleared), 2 = yields (target speed 0, YIELDING set), 0 = unchanged.
+template <int G, bool REG>
+__device__ __noinline__ int enforce_road_rules_call(const GraphShared& g, EnvStage<G, REG>& st, int V, int i,
+                                                    int meta, double speed) {
+    Regs r;
+    r.x = r.y = r.heading = r.target_speed = r.timer = r.delta = r.imp_x = r.imp_y = 0.0;
+    r.speed = speed;
+    r.meta = meta;
+    enforce_road_rules<G, REG, false>(false, g, st, V, i, r, 0.0);
+    if (r.meta & HWY_META_YIELDING) return 2;
+    return (meta & HWY_META_YIELDING) ? 1 : 0;
+}
+
 __device__ __forceinline__ int n_agents_of(const HwyNetParams& P) { return P.n_agents > 1 ? P.n_agents : 1; }
 // slot of the a-th controlled vehicle (-1: none)
 __device__ __forceinline__ int agent_slot(unsigned agent_mask, int a) {
@@ -1071,6 +1123,25 @@ __device__ __forceinline__ void observe_agents(const HwyNetParams& P, const Grap
     group_sync<G>();
     if (i == 0) st.ego = first;
     group_sync<G>();
+}
+
+// The exact half of _is_colliding (vehicle/objects.py:118-138) for a pair that survived the squared-distance reject:
+// the sphere pre-check with its square root, then the separating-axis test.  Out of line — a few pairs per env-step
+// get here, and inlined it was 6 KB of the substep loop.  Returns will_intersect | intersecting << 1; tr = transition.
+__device__ __noinline__ int collide_exact(double xa, double ya, double ca, double sa, double va, double xb, double yb,
+                                          double cb, double sb, double vb, bool b_object, double dt, double* tr) {
+    const double diag_v = 0x1.58a68a4a8d9f3p+2, diag_o = 0x1.6a09e667f3bcdp+1;
+    const double dist = norm2(xb - xa, yb - ya);
+    if (dist > (diag_v + (b_object ? diag_o : diag_v)) / 2 + va * dt) return 0;
+    const double len_b = b_object ? 2.0 : kVehLength;
+    Quad pa = make_polygon(xa, ya, ca, sa);
+    Quad pb = make_polygon(xb, yb, cb, sb, len_b);
+    bool inter, will;
+    double trx, try_;
+    polygons_intersecting(pa, pb, va * ca * dt, va * sa * dt, vb * cb * dt, vb * sb * dt, inter, will, trx, try_);
+    tr[0] = trx;
+    tr[1] = try_;
+    return (will ? 1 : 0) | (inter ? 2 : 0);
 }
 
 // ------------------------------------------------------------------ one simulation substep
@@ -1182,7 +1253,28 @@ __device__ __forceinline__ void substep(const HwyNetParams& P, const GraphShared
         if (i == 0) st.road_steps += 1;
         group_sync<G>();
         if (P.regulated && st.road_steps % (int)(1 / dt / 2) == 0)
-            enforce_road_rules<G, REG, PLAIN>(P, g, st, V, i, r, act_steer);
+        {
+#ifdef HWY_NET_INLINE_RULES
+            if constexpr (true) {
+                enforce_road_rules<G, REG, PLAIN>(P.dynamical != 0, g, st, V, i, r, act_steer);
+            } else {
+#else
+            if constexpr (PLAIN) {
+                enforce_road_rules<G, REG, true>(P.dynamical != 0, g, st, V, i, r, act_steer);
+            } else {
+#endif
+                // the rules only read this vehicle's flags and speed and only move its target speed and YIELDING bit:
+                // a real call with those in registers keeps 10 KB that run every 7th substep out of the loop body
+                const int code = enforce_road_rules_call<G, REG>(g, st, V, i, r.meta, r.speed);
+                if (code == 1) {
+                    r.target_speed = g.lanes[st.lane[i]].speed_limit;
+                    r.meta &= ~HWY_META_YIELDING;
+                } else if (code == 2) {
+                    r.target_speed = 0.0;
+                    r.meta |= HWY_META_YIELDING;
+                }
+            }
+        }
     }
     // ---- Road.step: Vehicle.step (kinematics.py:130-177), IDMVehicle.step timer (behavior.py:139-148)
     if (PLAIN && plain && P.dynamical) {
@@ -1236,6 +1328,7 @@ __device__ __forceinline__ void substep(const HwyNetParams& P, const GraphShared
         // RoadObject.diagonal = sqrt(LENGTH^2 + WIDTH^2) (objects.py:63): sqrt(29) and sqrt(8), correctly rounded
         const double diag_v = 0x1.58a68a4a8d9f3p+2, diag_o = 0x1.6a09e667f3bcdp+1;
         unsigned pending = 0;
+#pragma unroll 1
         for (int j = 0; j < V; ++j) {
             if (j == i) continue;
             const int a = i < j ? i : j, b = i < j ? j : i;
@@ -1250,22 +1343,31 @@ __device__ __forceinline__ void substep(const HwyNetParams& P, const GraphShared
             pending &= pending - 1;
             const int a = i < j ? i : j, b = i < j ? j : i;
             const bool b_object = st.kind[b] == HWY_KIND_OBSTACLE;
-            const double len_b = b_object ? 2.0 : kVehLength;
-            const double dist = norm2(st.x[b] - st.x[a], st.y[b] - st.y[a]);
-            if (dist > (diag_v + (b_object ? diag_o : diag_v)) / 2 + st.v[a] * dt) continue;
-            Quad pa = make_polygon(st.x[a], st.y[a], st.c[a], st.s[a]);
-            Quad pb = make_polygon(st.x[b], st.y[b], st.c[b], st.s[b], len_b);
-            bool inter, will;
-            double trx, try_;
-            polygons_intersecting(pa, pb, st.v[a] * st.c[a] * dt, st.v[a] * st.s[a] * dt, st.v[b] * st.c[b] * dt,
-                                  st.v[b] * st.s[b] * dt, inter, will, trx, try_);
-            if (will && !(b_object && i == b)) {
+            double tr[2];
+#ifdef HWY_NET_INLINE_COLLIDE
+            int flags = 0;
+            {
+                const double len_b = b_object ? 2.0 : kVehLength;
+                const double dist = norm2(st.x[b] - st.x[a], st.y[b] - st.y[a]);
+                if (dist > (diag_v + (b_object ? diag_o : diag_v)) / 2 + st.v[a] * dt) continue;
+                Quad pa = make_polygon(st.x[a], st.y[a], st.c[a], st.s[a]);
+                Quad pb = make_polygon(st.x[b], st.y[b], st.c[b], st.s[b], len_b);
+                bool inter, will;
+                polygons_intersecting(pa, pb, st.v[a] * st.c[a] * dt, st.v[a] * st.s[a] * dt, st.v[b] * st.c[b] * dt,
+                                      st.v[b] * st.s[b] * dt, inter, will, tr[0], tr[1]);
+                flags = (will ? 1 : 0) | (inter ? 2 : 0);
+            }
+#else
+            const int flags = collide_exact(st.x[a], st.y[a], st.c[a], st.s[a], st.v[a], st.x[b], st.y[b], st.c[b], st.s[b],
+                                            st.v[b], b_object, dt, tr);
+#endif
+            if ((flags & 1) && !(b_object && i == b)) {
                 const double share = b_object ? 1.0 : 0.5;
-                r.imp_x = i == a ? trx * share : -trx * share;
-                r.imp_y = i == a ? try_ * share : -try_ * share;
+                r.imp_x = i == a ? tr[0] * share : -tr[0] * share;
+                r.imp_y = i == a ? tr[1] * share : -tr[1] * share;
                 r.meta |= HWY_META_HAS_IMPACT;
             }
-            if (inter) r.meta |= HWY_META_CRASHED;
+            if (flags & 2) r.meta |= HWY_META_CRASHED;
         }
     }
 }
@@ -1728,8 +1830,11 @@ __global__ void debug_rectangles_kernel(const double* __restrict__ rects, int n,
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const double* q = rects + 10 * k;
-    out[k] = has_corner_inside(q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7], q[8], q[9]) ||
-             has_corner_inside(q[5], q[6], q[7], q[8], q[9], q[0], q[1], q[2], q[3], q[4]);
+    if (q[2] == q[7] && q[3] == q[8])  // equal sizes: the function the regulation step calls
+        out[k] = rotated_rectangles_intersect(q[0], q[1], q[4], q[5], q[6], q[9], q[2], q[3]);
+    else
+        out[k] = has_corner_inside(q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7], q[8], q[9]) ||
+                 has_corner_inside(q[5], q[6], q[7], q[8], q[9], q[0], q[1], q[2], q[3], q[4]);
 }
 
 // Road.act + Road.step `n_substeps` times with no ego action (IntersectionEnv._make_vehicles warm-up)
