@@ -324,36 +324,14 @@ __device__ __forceinline__ void kinematics_observe(const HwyHighwayParams& P, co
         ok = ok && (P.obs_see_behind || -2 * kVehLength < d);
         if (ok) key = fabs(d);
     }
-    // Float copies of the keys in the frame's (by now unused) rank-key array: rounding to float is monotone, so a float
-    // key below ours is a double key below ours and only equal finite floats need the doubles (same scheme as
-    // rank_count); four keys per shared-memory load.  Slot 0 (the observer) and the padding slots hold +inf.
-    float* __restrict__ kf = const_cast<float*>(F.lsf);
-    const float keyf = (float)key;
     key_scratch[i] = key;
-    kf[i] = keyf;
     env_sync<TPE>();
     // stable rank among the valid candidates (python sorted() on |lane_distance_to|)
     int rank = 0, n_valid = 0;
-    bool ambiguous = false;
-    {
-        const float4* kf4 = reinterpret_cast<const float4*>(kf);
-#pragma unroll 1
-        for (int q = 0; q < TPE / 4; ++q) {
-            const float4 f = kf4[q];
-            const int u = q << 2;
-            n_valid += (f.x < INFINITY) + (f.y < INFINITY) + (f.z < INFINITY) + (f.w < INFINITY);
-            rank += (f.x < keyf) + (f.y < keyf) + (f.z < keyf) + (f.w < keyf);
-            ambiguous = ambiguous || (f.x == keyf && u != i) || (f.y == keyf && u + 1 != i) ||
-                        (f.z == keyf && u + 2 != i) || (f.w == keyf && u + 3 != i);
-        }
-    }
-    if (ambiguous && keyf < INFINITY) {  // two candidates within float rounding of each other: exact count
-        rank = 0;
-#pragma unroll 1
-        for (int u = 1; u < V; ++u) {
-            const double ku = key_scratch[u];
-            rank += (ku < key) || (ku == key && u < i);
-        }
+    for (int u = 1; u < V; ++u) {
+        double ku = key_scratch[u];
+        n_valid += ku < INFINITY;
+        rank += (ku < key) || (ku == key && u < i);
     }
     const double xr = 5.0 * kMaxSpeed, yr = 4.0 * P.lanes_count, vr = 2 * kMaxSpeed;
     int row = -1;
@@ -570,6 +548,57 @@ __device__ __noinline__ int rank_count(const Frame<TPE>& F, int V, int i, bool a
     return rank | ((int)tie << 8);
 }
 
+// When the chain check of build_frame fails it is almost always because one vehicle overtook its rank-neighbour during
+// the substep: boundary k of the previous permutation (between positions k-1 and k) is inverted.  If every inverted
+// boundary is strictly inverted (no equal float keys), at least three boundaries away from the next inverted one, and
+// swapping its two vehicles leaves them in order with their unmoved outer neighbours, the swapped permutation is again
+// a strictly increasing chain of float keys — hence of the doubles — and every vehicle's rank is its old one, +-1 for
+// the swapped ones.  Like the chain check this runs redundantly in every warp of the env on shared data (ballots, no
+// barrier, no shared-memory writes), ~70 instructions instead of the ~400 of rank_count.  Returns the rank, or -1 when
+// the pattern is anything else (rank_count decides).  Boundary k = 32 w + b + 1 is bit b of word w.
+template <int TPE>
+__device__ __noinline__ int rank_repair(const Frame<TPE>& F, const Frame<TPE>& prev, int V, int i, bool active) {
+    constexpr int NW = TPE / 32;
+    const int wl = i & 31;
+    uint32_t inv[NW];
+    uint32_t bad = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        const int k = w * 32 + wl + 1;
+        const bool in = k < V;
+        const float a = in ? F.lsf[prev.perm[k - 1]] : 0.0f, c = in ? F.lsf[prev.perm[k]] : 1.0f;
+        bool wrong = in && !(a < c) && !(a > c);  // equal (or NaN) keys: not this path
+        if (in && a > c) {
+            // the swapped pair against its outer neighbours (positions k-2 and k+1 are unmoved, see the spacing rule)
+            if (k >= 2 && !(F.lsf[prev.perm[k - 2]] < c)) wrong = true;
+            if (k + 1 < V && !(a < F.lsf[prev.perm[k + 1]])) wrong = true;
+        }
+        inv[w] = __ballot_sync(0xffffffffu, in && a > c);
+        bad |= __ballot_sync(0xffffffffu, wrong);
+    }
+    // spacing: no other inverted boundary within two boundaries of an inverted one (also across the word seam)
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        uint32_t near = (inv[w] << 1) | (inv[w] << 2);
+        if (w > 0) near |= (inv[w - 1] >> 31) | (inv[w - 1] >> 30);
+        bad |= inv[w] & near;
+    }
+    if (bad) return -1;
+    if (!active) return 0;
+    const int r0 = prev.rank[i];
+    // upper vehicle of an inverted boundary r0 moves down, lower vehicle of an inverted boundary r0 + 1 moves up
+    // (static indices only: a dynamically indexed register array would live in local memory)
+    uint32_t w_dn = 0, w_up = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        if (r0 >= 1 && w == ((r0 - 1) >> 5)) w_dn = inv[w];
+        if (w == (r0 >> 5)) w_up = inv[w];
+    }
+    if (r0 >= 1 && ((w_dn >> ((r0 - 1) & 31)) & 1u)) return r0 - 1;
+    if (r0 + 1 < V && ((w_up >> (r0 & 31)) & 1u)) return r0 + 1;
+    return r0;
+}
+
 // After a barrier that follows publish(): ranks, rank-ordered membership masks, lane / target
 // masks (warp ballots) and the first pass of the collision sweep of Road.step
 // (road/road.py:477-481).  All threads of the env call this convergently.
@@ -600,7 +629,9 @@ __device__ __forceinline__ void build_frame(const HwyHighwayParams& P, EnvShared
     if (reuse) {
         rank = active ? prev->rank[i] : 0;
     } else {
-        const int rt = rank_count(F, V, i, active);
+        // (the repair pays for itself only where the count is long: V = 101 +3 %, V = 51 +-0, V = 21 -5 %)
+        int rt = (TPE >= 128 && prev) ? rank_repair(F, *prev, V, i, active) : -1;
+        if (rt < 0) rt = rank_count(F, V, i, active);  // first frame of a launch, ties, or more than isolated swaps
         rank = rt & 0xff;
         tie = (rt >> 8) != 0;
     }
@@ -988,10 +1019,6 @@ highway_step_kernel(const __grid_constant__ HwyHighwayParams P, const HwyHighway
 
     VehicleRegs r;
     load_vehicle(S, slot, r);
-    // bits 24-30 of the stored meta word: this vehicle's rank along the road at the end of the previous step (a hint,
-    // validated below and again by build_frame's chain check, so any value is safe)
-    const int rank_hint = (r.meta >> HWY_META_RANK_SHIFT) & (TPE - 1);
-    r.meta &= (1 << HWY_META_RANK_SHIFT) - 1;
     const int kind = meta_kind(r.meta);
     int speed_index = (i == 0) ? S.speed_index[e] : 0;
     double act_steer = 0.0, act_accel = 0.0;
@@ -1012,19 +1039,7 @@ highway_step_kernel(const __grid_constant__ HwyHighwayParams P, const HwyHighway
         if (i < NW) sm.ok_left[i] = sm.ok_right[i] = 0;
         if (i == 0) sm.n_items = 0;
         if (active) sm.delta[i] = r.delta;
-        sm.f[1].perm[i] = (unsigned char)i;
     }
-    // Rank hints -> a "previous frame" for the first build_frame of the launch: perm[hint] = slot.  The hints form a
-    // permutation exactly when every vehicle finds itself in its slot; then build_frame's strictly-increasing chain
-    // check decides whether the order still holds (it does unless the state was edited or re-spawned), and the O(V)
-    // per-thread rank count of the first frame — a sixth of all rank counts at 5 substeps — is skipped.
-    env_sync<TPE>();
-    if (active) {
-        sm.f[1].perm[rank_hint] = (unsigned char)i;
-        sm.f[1].rank[i] = (unsigned char)rank_hint;
-    }
-    env_sync<TPE>();
-    const bool hints_ok = __syncthreads_and(!active || (rank_hint < V && sm.f[1].perm[rank_hint] == i)) != 0;
     const IdmK K = make_idm(P);
     // all-pairs gate (every vehicle checks collisions): rank-pruned sweep; a single checking vehicle (highway-fast)
     // already costs one pre-check per thread
@@ -1046,8 +1061,7 @@ highway_step_kernel(const __grid_constant__ HwyHighwayParams P, const HwyHighway
         if (i == 0) sm.n_items = 0;
         // frame 0: masks only — the sweep of the stored state ran at the end of the substep that
         // produced it (previous launch).  Later: Road.step's sweep (road/road.py:477-481).
-        build_frame(P, sm, F, i, active, aligned, r, dt, frame > 0, pruned,
-                    (frame > 0 || hints_ok) ? &sm.f[p ^ 1] : nullptr);
+        build_frame(P, sm, F, i, active, aligned, r, dt, frame > 0, pruned, frame > 0 ? &sm.f[p ^ 1] : nullptr);
         PHASE_MARK(3);  // ranks, masks, sweep pass 1
         if (pruned && frame > 0) {  // uniform over the grid
             env_sync_phase<TPE, 3>();
@@ -1378,10 +1392,7 @@ highway_step_kernel(const __grid_constant__ HwyHighwayParams P, const HwyHighway
             env_sync<TPE>();
         }
     }
-    if (active && env_ok) {
-        r.meta |= (int)sm.f[p].rank[i] << HWY_META_RANK_SHIFT;  // rank hint for the next launch (see the prologue)
-        store_vehicle(S, slot, r);
-    }
+    if (active && env_ok) store_vehicle(S, slot, r);
     if (autoreset && active && env_ok && sm.done) S.delta[slot] = r.delta;
     PHASE_MARK(12);  // epilogue
 }
@@ -1750,7 +1761,9 @@ int hwy_highway_step(const HwyHighwayParams* p, const HwyHighwayState* s, const 
     int tpe = tpe_for(p->n_vehicles);
     int epb = step_envs_per_block(tpe, s->n_envs);
     int blocks = (s->n_envs + epb - 1) / epb;
-    const bool al = lanes_congruent_host(p);
+    // HWYB200_GENERAL_LANES=1 (tests): run the general-geometry instantiation on a congruent lane table too
+    const char* force_general = getenv("HWYB200_GENERAL_LANES");
+    const bool al = lanes_congruent_host(p) && !(force_general && force_general[0] == '1');
 #define HWY_LAUNCH_STEP(T, A)                                                                              \
     launch_step<T, A>(p, s, action_i, action_f, obs, reward, terminated, truncated, info_speed, info_crashed, \
                       autoreset, final_obs, blocks, epb, st)

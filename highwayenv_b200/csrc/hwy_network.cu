@@ -909,32 +909,33 @@ __device__ __noinline__ void position_heading_along_route(const GraphShared& g, 
 
 // utils.py:77-174 rotated_rectangles_intersect: 9 points (corners, centre, edge midpoints) of one
 // rectangle inside the other, both ways, with the reference's rotation convention
-// Out of line and rolled: the pair test runs only for predicted positions closer than one vehicle length, at the
-// regulation ticks, and its two fully unrolled copies were 13 KB in the middle of the substep loop.
-__device__ __noinline__ bool rotated_rectangles_intersect(double c1x, double c1y, double a1, double c2x, double c2y,
-                                                          double a2, double l, double w) {
+// One direction of utils.py:77-174 rotated_rectangles_intersect with the sines / cosines of both headings given:
+// the 9 points (corners, centre, edge midpoints, the reference's order) of rectangle 1 tested inside rectangle 2.
+__device__ __forceinline__ bool corner_inside(double c1x, double c1y, double s1, double c1, double c2x, double c2y,
+                                              double s2, double c2, double l, double w) {
     const double hl = l / 2, hw = w / 2;
+    const double pxs[9] = {-hl, -hl, hl, hl, 0, -hl, hl, 0, 0};
+    const double pys[9] = {-hw, hw, hw, -hw, 0, 0, 0, -hw, hw};
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        double px = c1 * pxs[k] + (-s1) * pys[k] + c1x;
+        double py = s1 * pxs[k] + c1 * pys[k] + c1y;
+        double dx = px - c2x, dy = py - c2y;
+        double rx = c2 * dx + (-s2) * dy, ry = s2 * dx + c2 * dy;
+        if (-l / 2 <= rx && rx <= l / 2 && -w / 2 <= ry && ry <= w / 2) return true;
+    }
+    return false;
+}
+// Both directions for two rectangles of the same size.  Inlined into enforce_road_rules, which is itself a real call
+// from the substep loop (enforce_road_rules_call): its two unrolled copies used to be 13 KB in the middle of that
+// loop.  Measured on cfg 3 (profiles/r2_kernel_history.md): rolled loops -7 %, a call per pair -4 %, this form +5 %.
+__device__ __forceinline__ bool rotated_rectangles_intersect(double c1x, double c1y, double a1, double c2x, double c2y,
+                                                          double a2, double l, double w) {
     double s1, c1, s2, c2;
     m_sincos(a1, &s1, &c1);
     m_sincos(a2, &s2, &c2);
-#pragma unroll 1
-    for (int dir = 0; dir < 2; ++dir) {
-        // has_corner_inside(rect1, rect2) then has_corner_inside(rect2, rect1) (utils.py:77-90)
-        const double ox = dir ? c2x : c1x, oy = dir ? c2y : c1y, os = dir ? s2 : s1, oc = dir ? c2 : c1;
-        const double tx = dir ? c1x : c2x, ty = dir ? c1y : c2y, ts = dir ? s1 : s2, tc = dir ? c1 : c2;
-#pragma unroll 1
-        for (int k = 0; k < 9; ++k) {
-            // corners, centre, edge midpoints in the reference's order
-            const double fx = (k == 2 || k == 3 || k == 6) ? hl : ((k == 4 || k == 7 || k == 8) ? 0.0 : -hl);
-            const double fy = (k == 1 || k == 2 || k == 8) ? hw : ((k == 4 || k == 5 || k == 6) ? 0.0 : -hw);
-            double px = oc * fx + (-os) * fy + ox;
-            double py = os * fx + oc * fy + oy;
-            double dx = px - tx, dy = py - ty;
-            double rx = tc * dx + (-ts) * dy, ry = ts * dx + tc * dy;
-            if (-l / 2 <= rx && rx <= l / 2 && -w / 2 <= ry && ry <= w / 2) return true;
-        }
-    }
-    return false;
+    return corner_inside(c1x, c1y, s1, c1, c2x, c2y, s2, c2, l, w) ||
+           corner_inside(c2x, c2y, s2, c2, c1x, c1y, s1, c1, l, w);
 }
 
 // general form (two sizes) for the known-answer hook debug_rectangles_kernel
@@ -1452,18 +1453,38 @@ __device__ __noinline__ void spawn_vehicle(const HwyNetParams& P, const HwyInter
     st.sp_y = py;
     st.sp_h = heading;
     st.sp_speed = speed;
-    int cl = 0;
-    double bd = 0;
-    for (int l = 0; l < g.n_lanes; ++l) {
-        double d = lane_distance_with_heading(g.lanes[l], px, py, heading);
-        if (l == 0 || d < bd) {
+    st.sp_dest = r1;
+    st.sp_ok = 1;  // sp_lane: spawn_closest_lane, by the whole group
+}
+
+// RoadObject.__init__'s closest-lane search (objects.py:46-50) for the spawn record, by ALL threads of the group after
+// a group_sync that follows the spawning thread: lane l of the network goes to thread l mod G, then a (distance, index)
+// minimum over the group = np.argmin's first minimum.  (One thread used to walk all 20 lanes, atan2 included, while
+// the other slots of the env waited: every step in the step kernel, ten times in a reset.)
+template <int G, bool REG>
+__device__ __forceinline__ void spawn_closest_lane(const GraphShared& g, EnvStage<G, REG>& st, int i) {
+    if (!st.sp_ok) return;  // uniform over the group
+    const double px = st.sp_x, py = st.sp_y, h = st.sp_h;
+    double bd = INFINITY;
+    int bl = 0x7fffffff;
+    for (int l = i; l < g.n_lanes; l += G) {
+        const double d = lane_distance_with_heading(g.lanes[l], px, py, h);
+        if (bl == 0x7fffffff || d < bd) {
             bd = d;
-            cl = l;
+            bl = l;
         }
     }
-    st.sp_lane = cl;
-    st.sp_dest = r1;
-    st.sp_ok = 1;
+#pragma unroll
+    for (int off = G / 2; off > 0; off >>= 1) {
+        const double d2 = __shfl_xor_sync(group_mask<G>(), bd, off);
+        const int l2 = __shfl_xor_sync(group_mask<G>(), bl, off);
+        if (l2 != 0x7fffffff && (bl == 0x7fffffff || d2 < bd || (d2 == bd && l2 < bl))) {
+            bd = d2;
+            bl = l2;
+        }
+    }
+    if (i == 0) st.sp_lane = bl;
+    group_sync<G>();
 }
 
 // the thread owning the new slot adopts the spawn record: an IDMVehicle, or the MDPVehicle of _make_vehicles
@@ -1761,6 +1782,7 @@ network_step_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGraph* _
         group_sync<G>();
         if (env_ok) store_env(S, st, e, i, dst, r);
         group_sync<G>();
+        spawn_closest_lane(g, st, i);
         if (st.sp_ok && i == n_keep) {
             adopt_spawn(P, SP, g, st, i, r);
             if (env_ok) store_env(S, st, e, i, i, r);
@@ -1945,6 +1967,7 @@ intersection_reset_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGr
     group_sync<G>();
     auto commit = [&](int kind) {  // the spawn record (if accepted) becomes vehicle number `count`
         group_sync<G>();
+        spawn_closest_lane(g, st, i);
         if (st.sp_ok && i == st.count) adopt_spawn(P, SP, g, st, i, r, kind);
         group_sync<G>();
         if (i == 0 && st.sp_ok) st.count += 1;
@@ -1990,17 +2013,7 @@ intersection_reset_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGr
             lane_position(EL, lon, 0.0, st.sp_x, st.sp_y);
             st.sp_h = lane_heading_at(EL, 60.0);
             st.sp_speed = EL.speed_limit;
-            int cl = 0;
-            double bd = 0;
-            for (int l = 0; l < g.n_lanes; ++l) {
-                double d = lane_distance_with_heading(g.lanes[l], st.sp_x, st.sp_y, st.sp_h);
-                if (l == 0 || d < bd) {
-                    bd = d;
-                    cl = l;
-                }
-            }
-            st.sp_lane = cl;
-            st.sp_dest = dest;
+            st.sp_dest = dest;  // sp_lane: spawn_closest_lane inside commit()
             // MDPVehicle.__init__ (controller.py:283-293); a plain Vehicle has no speed index (-1 in the state)
             const int si0 = speed_to_index(P, st.sp_speed);
             st.speed_index = P.action_type == 1 ? -1 : si0;
@@ -2037,14 +2050,19 @@ intersection_reset_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGr
     observe_agents(P, g, st, i, obs + (size_t)e * A * obs_size(P));
 }
 
-// RoundaboutEnv._make_vehicles (envs/roundabout_env.py:317-391), one env per thread (the draws
-// are a sequential chain on the env's numpy stream).
+// RoundaboutEnv._make_vehicles (envs/roundabout_env.py:317-391), one env per WARP.  The draws are a sequential chain
+// on the env's numpy stream: every lane of the warp walks it redundantly (same instructions, same values — no
+// shuffles), and the expensive part, RoadObject.__init__'s closest-lane search over all 32 lanes of the network for
+// each of the 5 vehicles (objects.py:46-50), is spread over the warp: lane l evaluates graph lane l, then a
+// (distance, index) minimum over the warp = np.argmin's first minimum.  One thread per env spent 165 us per step on
+// the ~9 % of the envs that had ended (16 % of a cfg 4 step).
 __global__ void __launch_bounds__(128)
 roundabout_reset_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGraph* __restrict__ graph, const __grid_constant__ HwyRoundaboutSpawn SP,
                         const __grid_constant__ HwyNetState S, uint64_t* __restrict__ rng, const uint8_t* __restrict__ mask_a,
                         const uint8_t* __restrict__ mask_b) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= S.n_envs) return;
+    const int e = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int wl = threadIdx.x & 31;
+    if (e >= S.n_envs) return;  // warp-uniform
     if ((mask_a || mask_b) && !((mask_a && mask_a[e]) || (mask_b && mask_b[e]))) return;
     const size_t n = (size_t)S.n_envs;
     Pcg64 g;
@@ -2080,13 +2098,23 @@ roundabout_reset_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGrap
             lane_position(L, lon, 0.0, px, py);  // make_on_lane (vehicle/objects.py:68-90)
             heading = lane_heading_at(L, lon);
         }
-        int lane = 0;  // RoadObject.__init__: closest lane (objects.py:46-50)
-        double bd = 0;
-        for (int l = 0; l < graph->n_lanes; ++l) {
-            double d = lane_distance_with_heading(graph->lanes[l], px, py, heading);
-            if (l == 0 || d < bd) {
+        // RoadObject.__init__: closest lane (objects.py:46-50), first minimum in graph-enumeration order
+        double bd = INFINITY;
+        int lane = 0x7fffffff;
+        for (int l = wl; l < graph->n_lanes; l += 32) {
+            const double d = lane_distance_with_heading(graph->lanes[l], px, py, heading);
+            if (lane == 0x7fffffff || d < bd) {
                 bd = d;
                 lane = l;
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double d2 = __shfl_xor_sync(0xffffffffu, bd, off);
+            const int l2 = __shfl_xor_sync(0xffffffffu, lane, off);
+            if (l2 != 0x7fffffff && (lane == 0x7fffffff || d2 < bd || (d2 == bd && l2 < lane))) {
+                bd = d2;
+                lane = l2;
             }
         }
         double target_speed = speed, timer = 0.0;
@@ -2097,23 +2125,27 @@ roundabout_reset_kernel(const __grid_constant__ HwyNetParams P, const HwyNetGrap
         } else {
             timer = py_mod_pos((px + py) * kPi, P.lane_change_delay);  // behavior.py:64
         }
-        pos[base + v] = make_double2(px, py);
-        hs[base + v] = make_double2(heading, speed);
-        tt[base + v] = make_double2(target_speed, timer);
-        imp[base + v] = make_double2(0.0, 0.0);
-        S.delta[base + v] = delta;
-        S.meta[base + v] = (lane << HWY_META_LANE_SHIFT) | (lane << HWY_META_TARGET_SHIFT) |
-                           HWY_META_CHECK_COLLISIONS | (kind << HWY_META_KIND_SHIFT) | HWY_META_PRESENT;
+        if (wl == 0) {
+            pos[base + v] = make_double2(px, py);
+            hs[base + v] = make_double2(heading, speed);
+            tt[base + v] = make_double2(target_speed, timer);
+            imp[base + v] = make_double2(0.0, 0.0);
+            S.delta[base + v] = delta;
+            S.meta[base + v] = (lane << HWY_META_LANE_SHIFT) | (lane << HWY_META_TARGET_SHIFT) |
+                               HWY_META_CHECK_COLLISIONS | (kind << HWY_META_KIND_SHIFT) | HWY_META_PRESENT;
+            S.route_len[base + v] = SP.route_len[(size_t)lane * 4 + dest];
+        }
         const int* rsrc = SP.route_table + ((size_t)lane * 4 + dest) * R;
         int* rdst = S.route + (base + v) * R;
-        for (int k = 0; k < R; ++k) rdst[k] = rsrc[k];
-        S.route_len[base + v] = SP.route_len[(size_t)lane * 4 + dest];
+        for (int k = wl; k < R; k += 32) rdst[k] = rsrc[k];
     }
-    S.speed_index[e] = SP.ego_speed_index;
-    S.time[e] = 0.0;
-    rng[0 * n + e] = g.s_hi;
-    rng[1 * n + e] = g.s_lo;
-    rng[4 * n + e] = ((uint64_t)g.has32 << 32) | g.u32;
+    if (wl == 0) {
+        S.speed_index[e] = SP.ego_speed_index;
+        S.time[e] = 0.0;
+        rng[0 * n + e] = g.s_hi;
+        rng[1 * n + e] = g.s_lo;
+        rng[4 * n + e] = ((uint64_t)g.has32 << 32) | g.u32;
+    }
 }
 
 // MergeEnv._make_vehicles and the ramp's Obstacle (envs/merge_env.py:150-190), one env per thread
@@ -2777,7 +2809,7 @@ int hwy_roundabout_reset(const HwyNetParams* p, const HwyNetGraph* graph, const 
     if (!spawn || !rng || !spawn->route_table || !spawn->route_len) return fail("%s", "null spawn / rng pointer");
     if (p->n_vehicles != 5 || s->vp != HWY_NET_GROUP) return fail("%s", "roundabout spawn places exactly 5 vehicles in 8 slots");
     cudaStream_t st = (cudaStream_t)stream;
-    hwynet::roundabout_reset_kernel<<<(s->n_envs + 127) / 128, 128, 0, st>>>(*p, graph, *spawn, *s, rng, mask_a, mask_b);
+    hwynet::roundabout_reset_kernel<<<(s->n_envs + 3) / 4, 128, 0, st>>>(*p, graph, *spawn, *s, rng, mask_a, mask_b);  // a warp per env
     if (check_launch("roundabout_reset_kernel")) return 1;
     if (obs) return observe_dispatch(p, graph, s, mask_a, mask_b, obs, st);
     return 0;

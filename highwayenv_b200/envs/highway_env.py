@@ -272,7 +272,8 @@ class BatchedHighwayEnv(ObservationHost):
             idx = idx.to(device=buf.device, dtype=torch.long).reshape(-1)
             if idx.numel() != buf.shape[0]:
                 raise ValueError("one action per env")
-            if bool(((idx < 0) | (idx >= table.shape[0])).any()):
+            # (the check reads the device: not under CUDA-graph capture — HostStepper checks its host array instead)
+            if not torch.cuda.is_current_stream_capturing() and bool(((idx < 0) | (idx >= table.shape[0])).any()):
                 raise IndexError("list index out of range")  # all_actions[action] in the reference
             torch.index_select(self._action_table, 0, idx, out=buf)
             return buf

@@ -46,9 +46,6 @@ extern "C" {
 #define HWY_META_CHECK_COLLISIONS (1 << 18)
 #define HWY_META_KIND_SHIFT 19        /* 2 bits */
 #define HWY_META_PRESENT (1 << 21)
-/* bits 24-30 (highway state only): the vehicle's rank along the road when the last step ended.  A performance hint
-   written by hwy_highway_step and validated when read; any value (e.g. 0 after a host-side state edit) is safe. */
-#define HWY_META_RANK_SHIFT 24
 /* kinds (2 bits): 0 IDMVehicle, 1 MDPVehicle, 2 plain Vehicle (ContinuousAction ego), 3 Obstacle — a static 2 x 2 m
  * road object (vehicle/objects.py:213-220); road.objects occupy the slots after the vehicles */
 #define HWY_KIND_OBSTACLE 3
