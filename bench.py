@@ -54,11 +54,11 @@ CONFIGS = {
         baseline="highway-fast-v0, 1 env, vehicles_count=20, Kinematics, DiscreteMetaAction (CPU plumbing case; "
                  "batched here)",
         env_id="highway-fast-v0", config=None, envs_per_gpu=4096, actions="discrete5", vehicles=21, substeps=5,
-        algo_bytes=2 * 21 * 96 + 4 + 100 + 6, kernel="highway_step_kernel<32>", ncu="r2_ncu_highway_step_v21.json"),
+        algo_bytes=2 * 21 * 96 + 4 + 100 + 6, kernel="highway_step_kernel<32, true>", ncu="r2_ncu_highway_step_v21.json"),
     "cfg2": dict(
         baseline="highway-fast-v0, 4096 batched envs, vehicles_count=50, Kinematics, 1xB200",
         env_id="highway-fast-v0", config={"vehicles_count": 50}, envs_per_gpu=4096, actions="discrete5",
-        vehicles=51, substeps=5, algo_bytes=2 * 51 * 96 + 4 + 100 + 6, kernel="highway_step_kernel<64>",
+        vehicles=51, substeps=5, algo_bytes=2 * 51 * 96 + 4 + 100 + 6, kernel="highway_step_kernel<64, true>",
         ncu="r2_ncu_highway_step_v51.json"),
     "cfg3": dict(
         baseline="intersection-v0, 8192 envs, IDM + priority-yield, OccupancyGrid observation, 1xB200",
@@ -75,7 +75,7 @@ CONFIGS = {
                  "ContinuousAction",
         env_id="highway-v0", config={"vehicles_count": 100, "action": {"type": "ContinuousAction"}},
         envs_per_gpu=8192, actions="box2", vehicles=101, substeps=15, algo_bytes=2 * 101 * 96 + 8 + 100 + 6,
-        kernel="highway_step_kernel<128>", ncu="r2_ncu_highway_step_v101.json"),
+        kernel="highway_step_kernel<128, true>", ncu="r2_ncu_highway_step_v101.json"),
 }
 
 
