@@ -89,36 +89,15 @@ struct EnvShared {
 // All envs of a block advance in lock-step (block-wide barriers): besides ordering the shared
 // staging it keeps the block's warps on the same code at the same time, which is what the
 // instruction cache wants from a ~100 KB kernel (measured: 1.4x over per-env barriers).
-// HWY_ENV_BARRIER (experiment switch, default 0 = shipped): 1 = every barrier is a per-env named barrier,
-// 2 = only the phase barriers inside a substep (env_sync_phase) are per-env; the barrier after publish stays
-// block-wide and re-aligns the block's warps once per substep; 3 = only the two barriers around the MOBIL items.
-#ifndef HWY_ENV_BARRIER
-#define HWY_ENV_BARRIER 0
-#endif
-template <int TPE>
-__device__ __forceinline__ void env_sync_named() {
-    if (TPE == 32)
-        __syncwarp();
-    else
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)(threadIdx.x / TPE)), "n"(TPE) : "memory");
-}
+// (Per-env named barriers — all of them, only the ones inside a substep, only the two around the MOBIL items — were
+// measured again on the 32 KB loop: 10.7-11.6 M against 12.8 M env-steps/s on the headline, profiles/r2_kernel_history.md.)
 template <int TPE>
 __device__ __forceinline__ void env_sync() {
-#if HWY_ENV_BARRIER == 1
-    env_sync_named<TPE>();
-#else
     __syncthreads();
-#endif
 }
 template <int TPE, int LEVEL>
 __device__ __forceinline__ void env_sync_phase() {
-#if HWY_ENV_BARRIER == 1 || HWY_ENV_BARRIER == 2
-    env_sync_named<TPE>();
-#elif HWY_ENV_BARRIER == 3
-    if (LEVEL == 2) env_sync_named<TPE>(); else __syncthreads();
-#else
     __syncthreads();
-#endif
 }
 
 template <int NW>
@@ -333,6 +312,9 @@ __device__ __forceinline__ void kinematics_observe(const HwyHighwayParams& P, co
         n_valid += ku < INFINITY;
         rank += (ku < key) || (ku == key && u < i);
     }
+    // obs_env == nullptr: an env of the block that is not observed (masked out, a surplus slot of the last block, not
+    // re-spawned).  It still runs to here so that every thread of the block meets the same barrier instruction.
+    if (!obs_env) return;
     const double xr = 5.0 * kMaxSpeed, yr = 4.0 * P.lanes_count, vr = 2 * kMaxSpeed;
     int row = -1;
     double r1 = 0, r2 = 0, r3 = 0, r4 = 0;
@@ -1325,11 +1307,8 @@ highway_step_kernel(const __grid_constant__ HwyHighwayParams P, const HwyHighway
     const Frame<TPE>& F = sm.f[p];
     const size_t obs_off = (size_t)e * P.obs_vehicles_count * obs_columns(P);
     float* obs_env = obs + obs_off;
-    if (env_ok)
-        kinematics_observe(P, F, sm.key, i, r.heading, obs_env,
-                           (autoreset && final_obs) ? final_obs + obs_off : nullptr);
-    else
-        env_sync<TPE>();
+    kinematics_observe(P, F, sm.key, i, r.heading, env_ok ? obs_env : nullptr,
+                       (autoreset && final_obs) ? final_obs + obs_off : nullptr);
     if (i == 0) {
         sm.done = 0;
         sm.sp_fallback = 0;
@@ -1381,15 +1360,16 @@ highway_step_kernel(const __grid_constant__ HwyHighwayParams P, const HwyHighway
         spawn_fused(P, S, sm, e, i, active, do_reset, simple_geometry, r, speed_index);
         Frame<TPE>& G = sm.f[p ^ 1];
         if (do_reset) publish(P, G, i, active, r);
-        env_sync<TPE>();
-        if (do_reset) {
-            kinematics_observe(P, G, sm.key, i, r.heading, obs_env);
-            if (i == 0) {
+        // barrier + "does any env of this block re-spawn?": the second observation runs under a block-uniform
+        // condition, so that all threads of the block meet the same barrier instructions (a per-env condition around
+        // __syncthreads() is what compute-sanitizer's synccheck rejects, even though the arrival counts match)
+        const bool any_reset = __syncthreads_or(do_reset) != 0;
+        if (any_reset) {
+            kinematics_observe(P, G, sm.key, i, r.heading, do_reset ? obs_env : nullptr);
+            if (do_reset && i == 0) {
                 S.time[e] = 0.0;
                 S.speed_index[e] = speed_index;
             }
-        } else {
-            env_sync<TPE>();
         }
     }
     if (active && env_ok) store_vehicle(S, slot, r);
@@ -1422,10 +1402,8 @@ highway_observe_kernel(const __grid_constant__ HwyHighwayParams P, const HwyHigh
     publish(P, sm.f, i, active, r);
     env_sync<TPE>();
     const bool wanted = env_ok && (!use_mask || (mask_a && mask_a[e]) || (mask_b && mask_b[e]));
-    if (wanted)
-        kinematics_observe(P, sm.f, sm.key, i, r.heading, obs + (size_t)e * P.obs_vehicles_count * obs_columns(P));
-    else
-        env_sync<TPE>();
+    kinematics_observe(P, sm.f, sm.key, i, r.heading,
+                       wanted ? obs + (size_t)e * P.obs_vehicles_count * obs_columns(P) : nullptr);
 }
 
 // ------------------------------------------------------------------ reset kernel
