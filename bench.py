@@ -581,6 +581,23 @@ def measure_config(key, E, K, W, rank, world, dev, ctx, do_e2e=True, gather=Fals
                 res["e2e_api"] += f" (host_stepper unavailable: {type(exc).__name__}: {exc})"[:200]
         res["h2d"] = int(h_actions.numel() * h_actions.element_size())
         res["d2h"] = int(h_obs.numel() * 4 + E * (8 + 1 + 1))
+    # BASELINE.md's other timing: Road.act() + Road.step(dt) alone (no action mapping, observation, reward or reset),
+    # `substeps` of them per launch = the simulation part of one env.step.  Last, on a freshly reset batch: without resets
+    # the population drifts (crashed vehicles stay), so only a few launches are timed.
+    if hasattr(env, "road_substeps"):
+        env.reset(seed=0)
+        n_road = 12
+        for _ in range(2):
+            env.road_substeps(c["substeps"])
+        barrier()
+        rv = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(n_road)]
+        for k in range(n_road):
+            flush.fill_(k & 0xFF)
+            rv[k][0].record(stream)
+            env.road_substeps(c["substeps"])
+            rv[k][1].record(stream)
+        barrier()
+        res["road_ms"] = sum(a.elapsed_time(b) for a, b in rv) / n_road
     del env
     return res
 
@@ -658,6 +675,14 @@ def run_gpu_arm(args) -> None:
                 "note": "compute/latency bound (fp64 + libm, branchy), not HBM bound: see DESIGN.md roofline",
             },
         }
+        if "road_ms" in r:
+            (road_ms,) = reduce_max([r["road_ms"]])
+            entry["road_only"] = {
+                "what": (f"{c['substeps']} x (Road.act + Road.step) per launch through env.road_substeps "
+                         f"({'hwy_highway_substeps' if c['env_id'].startswith('highway') else 'hwy_network_substeps'}), "
+                         "fresh populations, no resets"),
+                "ms_per_launch": road_ms, "value": n_total / (road_ms * 1e-3), "unit": "env-steps/s equivalent",
+                "road_substeps_per_s": n_total * c["substeps"] / (road_ms * 1e-3)}
         if key == HEADLINE:
             head, head_raw = entry, r
         entries.append(entry)

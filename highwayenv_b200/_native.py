@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("HWYB200_LIB") or os.path.join(_HERE, "csrc", "libhwyb200.so")
 
-HWY_ABI_VERSION = 12  # bump with every change of a struct or signature: a stale libhwyb200.so then fails to load
+HWY_ABI_VERSION = 13  # bump with every change of a struct or signature: a stale libhwyb200.so then fails to load
 HWY_MAX_LANES = 8
 HWY_MAX_TARGET_SPEEDS = 8
 HWY_MAX_VEHICLES = 128
@@ -211,7 +211,7 @@ class HwyLidarParams(C.Structure):
 EXPORTS = (
     "hwy_observe_grid", "hwy_observe_ttc", "hwy_observe_lidar", "hwy_exit_reset",
     "hwy_abi_version", "hwy_last_error", "hwy_highway_slot_stride", "hwy_highway_reset",
-    "hwy_highway_observe", "hwy_highway_step", "hwy_highway_autoreset", "hwy_launch_count",
+    "hwy_highway_observe", "hwy_highway_step", "hwy_highway_autoreset", "hwy_highway_substeps", "hwy_launch_count",
     "hwy_network_obs_size", "hwy_network_step", "hwy_network_observe", "hwy_roundabout_reset",
     "hwy_intersection_step", "hwy_network_substeps", "hwy_intersection_reset", "hwy_intersection_step_agents",
     "hwy_debug_network_neighbours", "hwy_debug_rotated_rectangles_intersect", "hwy_merge_reset",
@@ -246,6 +246,8 @@ def load():
     lib.hwy_highway_step.argtypes = [P, S, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                      C.c_void_p, C.c_void_p]
+    lib.hwy_highway_substeps.restype = C.c_int
+    lib.hwy_highway_substeps.argtypes = [P, S, C.c_int, C.c_void_p, C.c_void_p]
     lib.hwy_highway_autoreset.restype = C.c_int
     lib.hwy_highway_autoreset.argtypes = [P, S, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     NP, NG, NS = C.POINTER(HwyNetParams), C.c_void_p, C.POINTER(HwyNetState)

@@ -1004,7 +1004,10 @@ highway_step_kernel(const __grid_constant__ HwyHighwayParams P, const HwyHighway
     const int kind = meta_kind(r.meta);
     int speed_index = (i == 0) ? S.speed_index[e] : 0;
     double act_steer = 0.0, act_accel = 0.0;
-    const int frames = P.simulation_frequency / P.policy_frequency;
+    // autoreset < 0 (hwy_highway_substeps): -autoreset times Road.act() + Road.step(dt) and nothing else — no
+    // action_type.act, no observation / reward / clock; the controlled vehicle acts like ControlledVehicle.act(None)
+    const int substeps_only = autoreset < 0 ? -autoreset : 0;
+    const int frames = substeps_only ? substeps_only : P.simulation_frequency / P.policy_frequency;
     const double dt = 1.0 / P.simulation_frequency;
 
     // ---- static masks
@@ -1063,7 +1066,7 @@ highway_step_kernel(const __grid_constant__ HwyHighwayParams P, const HwyHighway
                     // (:99-124); labels action.py:204.  follow_road (:135-143) cannot change the
                     // target on the single-road highway graph (next_lane hits KeyError,
                     // road/road.py:129-130).
-                    int a = action_i[e];
+                    int a = substeps_only ? 1 : action_i[e];  // substeps only: act(None) = IDLE
                     if (a == 3 || a == 4) {
                         int idx = speed_to_index(P, r.speed) + (a == 3 ? 1 : -1);
                         idx = max(0, min(idx, P.n_target_speeds - 1));
@@ -1084,7 +1087,9 @@ highway_step_kernel(const __grid_constant__ HwyHighwayParams P, const HwyHighway
                 } else {
                     // ContinuousAction.get_action/act (action.py:136-162): Box is float32 and
                     // lmap (utils.py:31-33) stays in float32 (NEP 50 weak python scalars)
-                    float a0 = action_f[2 * (size_t)e], a1 = action_f[2 * (size_t)e + 1];
+                    // (substeps only: the vehicle's current action dict, or the default {0, 0} when none is given —
+                    // lmap(0) of the symmetric default ranges)
+                    float a0 = action_f ? action_f[2 * (size_t)e] : 0.0f, a1 = action_f ? action_f[2 * (size_t)e + 1] : 0.0f;
                     if (P.act_clip) {
                         a0 = fminf(fmaxf(a0, -1.0f), 1.0f);
                         a1 = fminf(fmaxf(a1, -1.0f), 1.0f);
@@ -1303,6 +1308,10 @@ highway_step_kernel(const __grid_constant__ HwyHighwayParams P, const HwyHighway
     }
 
     PHASE_MARK(11);
+    if (substeps_only) {  // uniform over the grid
+        if (active && env_ok) store_vehicle(S, slot, r);
+        return;
+    }
     // ---- epilogue: state back to HBM, observation, reward, termination
     const Frame<TPE>& F = sm.f[p];
     const size_t obs_off = (size_t)e * P.obs_vehicles_count * obs_columns(P);
@@ -1639,7 +1648,7 @@ int launch_step(const HwyHighwayParams* p, const HwyHighwayState* s, const int32
                 const float* action_f, float* obs, double* reward, uint8_t* terminated,
                 uint8_t* truncated, double* info_speed, uint8_t* info_crashed, int autoreset,
                 float* final_obs, int blocks, int epb, cudaStream_t st) {
-    if (autoreset && ensure_pcg_jump(st)) return 1;
+    if (autoreset > 0 && ensure_pcg_jump(st)) return 1;
     size_t smem = (size_t)epb * sizeof(hwy::EnvShared<TPE>);
     // the attribute is per device (and per template instance): cache it by device ordinal
     static std::atomic<size_t> configured[64];
@@ -1677,6 +1686,12 @@ int launch_reset(const HwyHighwayParams* p, const HwyHighwayState* s, const uint
     return check_launch("highway_reset_kernel");
 }
 }  // namespace
+
+namespace {
+int dispatch_step(const HwyHighwayParams* p, const HwyHighwayState* s, const int32_t* action_i, const float* action_f,
+                  float* obs, double* reward, uint8_t* terminated, uint8_t* truncated, double* info_speed,
+                  uint8_t* info_crashed, int autoreset, float* final_obs, cudaStream_t st);
+}
 
 extern "C" {
 
@@ -1735,7 +1750,25 @@ int hwy_highway_step(const HwyHighwayParams* p, const HwyHighwayState* s, const 
     if (p->action_type == 1 && !action_f) return fail("%s", "ContinuousAction needs action_f");
     if (autoreset != HWY_AUTORESET_DISABLED && autoreset != HWY_AUTORESET_SAME_STEP)
         return fail("%s", "unknown autoreset mode");
-    cudaStream_t st = (cudaStream_t)stream;
+    return dispatch_step(p, s, action_i, action_f, obs, reward, terminated, truncated, info_speed, info_crashed, autoreset,
+                         final_obs, (cudaStream_t)stream);
+}
+
+/* B4 seam of the reference (abstract.py:304-307 minus action_type.act): n_substeps x (Road.act(); Road.step(dt)). */
+int hwy_highway_substeps(const HwyHighwayParams* p, const HwyHighwayState* s, int n_substeps, const float* action_f,
+                         void* stream) {
+    if (validate(p, s)) return 1;
+    if (n_substeps < 1 || n_substeps > 4096) return fail("%s", "n_substeps must be in 1..4096");
+    return dispatch_step(p, s, nullptr, action_f, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, -n_substeps, nullptr,
+                         (cudaStream_t)stream);
+}
+
+}  // extern "C"
+
+namespace {
+int dispatch_step(const HwyHighwayParams* p, const HwyHighwayState* s, const int32_t* action_i, const float* action_f,
+                  float* obs, double* reward, uint8_t* terminated, uint8_t* truncated, double* info_speed,
+                  uint8_t* info_crashed, int autoreset, float* final_obs, cudaStream_t st) {
     int tpe = tpe_for(p->n_vehicles);
     int epb = step_envs_per_block(tpe, s->n_envs);
     int blocks = (s->n_envs + epb - 1) / epb;
@@ -1757,5 +1790,4 @@ int hwy_highway_step(const HwyHighwayParams* p, const HwyHighwayState* s, const 
     if (check_launch("highway_step_kernel")) return 1;
     return 0;
 }
-
-}  // extern "C"
+}  // namespace

@@ -393,6 +393,24 @@ class BatchedHighwayEnv(ObservationHost):
         return available_actions_mask(self._pos[:, 0, 0], self._pos[:, 0, 1], lane, self._speed_index.long(), table,
                                       int(self._params.n_target_speeds))
 
+    def road_substeps(self, n_substeps: int, action=None) -> None:
+        """The reference's operator seam (`AbstractEnv._simulate` without `action_type.act`, abstract.py:304-307):
+        `n_substeps` x (`Road.act()`; `Road.step(1 / simulation_frequency)`) on the device state and nothing else — no
+        observation, reward, clock or autoreset.  The controlled vehicle acts like `ControlledVehicle.act(None)`; with
+        ContinuousAction, `action` ([N, 2] in [-1, 1]) is the action dict the plain Vehicle keeps (default zeros)."""
+        if not self._seeded:
+            raise RuntimeError("call reset() before road_substeps()")
+        af = None
+        if action is not None:
+            if self._params.action_type != 1:
+                raise ValueError("action is only meaningful for a ContinuousAction ego")
+            if getattr(self.action_type, "table", None) is not None:
+                raise ValueError("pass the continuous (throttle, steering) pair, not a DiscreteAction index")
+            af = self._stage_actions(action).data_ptr()
+        with torch.cuda.device(self.device):
+            N.check(self._lib.hwy_highway_substeps(C.byref(self._params), C.byref(self._state), int(n_substeps), af,
+                                                   self._stream()))
+
     def host_stepper(self) -> "HostStepper":
         """Host-buffer stepping through one CUDA graph (see HostStepper)."""
         return HostStepper(self)

@@ -517,6 +517,17 @@ class BatchedRoundaboutEnv(ObservationHost):
                 self.observe()
         return (self._out_obs(), self._reward, self._terminated.view(torch.bool), self._truncated.view(torch.bool), info)
 
+    def road_substeps(self, n_substeps: int) -> None:
+        """The reference's operator seam (`AbstractEnv._simulate` without `action_type.act`, abstract.py:304-307):
+        `n_substeps` x (`Road.act()`; `Road.step(1 / simulation_frequency)`, with the RegulatedRoad rules where the
+        scenario has them) on the device state of every env and nothing else — no observation, reward, clock,
+        population change or autoreset; the controlled vehicle acts like `ControlledVehicle.act(None)`."""
+        if self._rngs is None:
+            raise RuntimeError("call reset() before road_substeps()")
+        with torch.cuda.device(self.device):
+            N.check(self._lib.hwy_network_substeps(C.byref(self._params), self._graph_dev.data_ptr(),
+                                                   C.byref(self._state), None, int(n_substeps), self._stream()))
+
     def host_stepper(self):
         """Host-buffer stepping through one CUDA graph (envs/common/host_stepper.py)."""
         from .common.host_stepper import HostStepper

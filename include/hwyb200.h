@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define HWY_ABI_VERSION 12
+#define HWY_ABI_VERSION 13
 #define HWY_MAX_LANES 8
 #define HWY_MAX_TARGET_SPEEDS 8
 #define HWY_MAX_VEHICLES 128 /* per env, incl. the ego */
@@ -178,6 +178,15 @@ int hwy_highway_step(const HwyHighwayParams *p, const HwyHighwayState *s, const 
                      const float *action_f, float *obs, double *reward, uint8_t *terminated,
                      uint8_t *truncated, double *info_speed, uint8_t *info_crashed, int autoreset,
                      float *final_obs, void *stream);
+
+/* The operator seam `_simulate` uses (envs/common/abstract.py:304-307 without action_type.act):
+ * `n_substeps` times  Road.act()  (road/road.py:464-467)  then  Road.step(1 / simulation_frequency)  (:469-481)
+ * on the stored state, and nothing else — no observation, reward, clock or reset.  The controlled vehicle acts like
+ * ControlledVehicle.act(None) (its current target lane / speed); a ContinuousAction ego keeps the action dict given in
+ * `action_f` ([n_envs, 2] in [-1, 1], as for hwy_highway_step) or the default {steering 0, acceleration 0} if NULL.
+ * What BASELINE.md's "Road.act() + Road.step(dt)" timing runs. */
+int hwy_highway_substeps(const HwyHighwayParams *p, const HwyHighwayState *s, int n_substeps, const float *action_f,
+                         void *stream);
 
 /* The SameStep autoreset half of hwy_highway_step on its own: re-spawn the envs whose
  * terminated | truncated byte is set and overwrite their rows of `obs` with the reset
