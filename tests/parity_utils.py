@@ -37,6 +37,20 @@ def well_conditioned(st: dict, min_speed: float = 1.0) -> bool:
     return bool(np.all(np.abs(st["speed"][alive]) >= min_speed))
 
 
+def comparable_steps(g: dict) -> int:
+    """How many (seed, step) pairs of a golden rollout a free-running comparison covers: for every seed the prefix of
+    steps whose golden state is well conditioned.  A property of the fixture alone, so the free-running tests assert
+    this exact count instead of a floor (round-1 verdict: `compared >= 3 * S` was 10 % of the steps)."""
+    S, T = g["actions"].shape[:2]
+    n = 0
+    for i in range(S):
+        for t in range(T):
+            if not well_conditioned(golden_state(g, i, t + 1)):
+                break
+            n += 1
+    return n
+
+
 def compare_state(st: dict, got: dict, tol: float = FLOAT_TOL, ctx: str = "") -> float:
     """st: golden (dump_state layout); got: dict of arrays with the same schema where
     target_lane mirrors lane for vehicles without one and impact is (has_impact, ix, iy)."""

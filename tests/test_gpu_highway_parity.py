@@ -8,7 +8,7 @@ import pytest
 import torch
 
 import hwy_oracle as ho
-from parity_utils import compare_state, golden_state, load_golden, well_conditioned
+from parity_utils import comparable_steps, compare_state, golden_state, load_golden, well_conditioned
 
 pytestmark = pytest.mark.gpu
 
@@ -114,7 +114,8 @@ def test_free_running_vs_reference(name):
             assert bool(term[i]) == bool(g["terminated"][i, t])
             assert np.max(np.abs(obs[i] - g["obs"][i, t + 1])) <= 1e-6
             compared += 1
-    assert compared >= 3 * S
+    # every well-conditioned (seed, step) of the fixture was compared: 96-100 % of the rollout (test_host_cpu pins that)
+    assert compared == comparable_steps(g), (compared, comparable_steps(g), S * T)
 
 
 def _oracle_pair(name, n, seed0):

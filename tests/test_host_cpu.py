@@ -274,3 +274,16 @@ def test_available_actions_mask_matches_reference_rule():
     assert m[3].tolist() == [False, True, False, True, True]   # before the lane start: 0 <= longitudinal fails
     assert m[4].tolist() == [True, True, True, True, True]     # longitudinal < length + VEHICLE_LENGTH
     assert m[5].tolist() == [False, True, False, True, True]
+
+
+def test_free_running_coverage_of_the_highway_fixtures():
+    """The free-running GPU tests compare every well-conditioned (seed, step) of a golden rollout and assert that exact
+    count (`parity_utils.comparable_steps`); this pins how much of each rollout that is — at least 95 % — so that a
+    fixture regenerated with mostly ill-conditioned states cannot hollow the tests out."""
+    from parity_utils import comparable_steps, load_golden
+
+    for name in ("highway_fast_v20", "highway_fast_v50", "highway_v50", "highway_v100_continuous",
+                 "highway_discrete_action", "highway_fast_features", "highway_fast_features_range"):
+        g = load_golden(name)
+        S, T = g["actions"].shape[:2]
+        assert comparable_steps(g) >= 0.95 * S * T, (name, comparable_steps(g), S * T)
