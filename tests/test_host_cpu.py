@@ -287,3 +287,31 @@ def test_free_running_coverage_of_the_highway_fixtures():
         g = load_golden(name)
         S, T = g["actions"].shape[:2]
         assert comparable_steps(g) >= 0.95 * S * T, (name, comparable_steps(g), S * T)
+
+
+def test_gymnasium_registration_hook_registers_every_id(monkeypatch):
+    """`highwayenv_b200._register_with_gymnasium` (B1 of the boundary): with a gymnasium on the path — here the stub the
+    oracle harness runs the reference under — every reference id appears as `hwyb200/<id>` with the single-env facade as
+    `entry_point` (gymnasium.make) and the batched class as `vector_entry_point` (gymnasium.make_vec), and every entry
+    point resolves to a class of this package."""
+    import importlib
+    import sys
+
+    import highwayenv_b200 as hb
+
+    shim = os.path.join(ROOT, "oracle", "shim")
+    monkeypatch.syspath_prepend(shim)
+    for name in [m for m in sys.modules if m == "gymnasium" or m.startswith("gymnasium.")]:
+        monkeypatch.delitem(sys.modules, name)
+    hb._register_with_gymnasium()
+    from gymnasium.envs.registration import registry
+
+    for env_id, entry in hb.REGISTRY.items():
+        spec = registry["hwyb200/" + env_id]
+        assert spec["entry_point"] == "highwayenv_b200.single:SingleEnv" and spec["kwargs"] == {"env_id": env_id}
+        assert spec["vector_entry_point"] == entry
+        mod, cls = entry.split(":")
+        assert isinstance(getattr(importlib.import_module(mod), cls), type)
+    assert len([k for k in registry if k.startswith("hwyb200/")]) == len(hb.REGISTRY)
+    for name in [m for m in sys.modules if m == "gymnasium" or m.startswith("gymnasium.")]:
+        monkeypatch.delitem(sys.modules, name)  # leave no stub behind for the tests that follow
