@@ -314,4 +314,4 @@ def test_gymnasium_registration_hook_registers_every_id(monkeypatch):
         assert isinstance(getattr(importlib.import_module(mod), cls), type)
     assert len([k for k in registry if k.startswith("hwyb200/")]) == len(hb.REGISTRY)
     for name in [m for m in sys.modules if m == "gymnasium" or m.startswith("gymnasium.")]:
-        monkeypatch.delitem(sys.modules, name)  # leave no stub behind for the tests that follow
+        sys.modules.pop(name, None)  # leave no stub behind for the tests that follow
